@@ -1,0 +1,229 @@
+"""Kernel dispatch layer: shape/broadcast inference + native call (CPU OpenMP
+library or sm_100a CUDA library), no autograd here.
+
+Parity: /root/reference/python/dgl/_sparse_ops.py:156-266 (_gspmm), :482-566
+(_gsddmm), :641-800 (segment ops) and /root/reference/src/array/kernel.cc:20-248.
+Operand broadcasting is encoded as ``idx = (f // div) % mod`` per operand; shapes
+that cannot be encoded that way are expanded to the full output shape first.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from ._native import loader
+from .base import DGLError, dtype_code, id_code
+
+OPS = {"add": 0, "sub": 1, "mul": 2, "div": 3, "copy_lhs": 4, "copy_rhs": 5, "dot": 6}
+REDS = {"sum": 0, "max": 1, "min": 2}
+TARGETS = {"u": 0, "e": 1, "v": 2, 0: 0, 1: 1, 2: 2}
+
+
+def _prod(xs):
+    return int(math.prod(xs)) if len(xs) else 1
+
+
+def infer_broadcast_shape(op, shp1, shp2):
+    """Trailing-feature-shape broadcasting, NumPy rules
+    (reference: python/dgl/_sparse_ops.py:10-60)."""
+    pad = max(len(shp1), len(shp2))
+    s1 = (1,) * (pad - len(shp1)) + tuple(shp1)
+    s2 = (1,) * (pad - len(shp2)) + tuple(shp2)
+    if op == "dot" and s1[-1] != s2[-1]:
+        raise DGLError(f"dot requires equal reduce dims, got {shp1} and {shp2}")
+    for a, b in zip(s1, s2):
+        if a != b and a != 1 and b != 1:
+            raise DGLError(f"feature shapes {shp1} and {shp2} are not broadcastable")
+    out = tuple(max(a, b) for a, b in zip(s1, s2))
+    if op == "dot":
+        out = out[:-1] + (1,)
+    return out
+
+
+def _div_mod(shape, out_shape):
+    """Return (div, mod) with operand_idx = (f // div) % mod, or None if the
+    operand's non-broadcast dims are not one contiguous run."""
+    pad = len(out_shape) - len(shape)
+    s = (1,) * pad + tuple(shape)
+    live = [i for i, (a, o) in enumerate(zip(s, out_shape)) if o > 1 and a == o]
+    dead = [i for i, (a, o) in enumerate(zip(s, out_shape)) if o > 1 and a == 1]
+    if not live:
+        return 1, 1
+    a, b = live[0], live[-1] + 1
+    if any(a < d < b for d in dead):
+        return None
+    return _prod(out_shape[b:]), _prod(out_shape[a:b])
+
+
+def _prep_operands(op, lhs, rhs):
+    """Flatten trailing dims and compute broadcast descriptors.
+    Returns (lhs2d, rhs2d, out_trailing_shape, F, rsz, (ldiv, lmod, rdiv, rmod))."""
+    use_l = op != "copy_rhs"
+    use_r = op != "copy_lhs"
+    if not (use_l and use_r):
+        return _prep_single(op, lhs, rhs)
+    ls = tuple(lhs.shape[1:]) if use_l else ()
+    rs = tuple(rhs.shape[1:]) if use_r else ()
+    if use_l and use_r:
+        out_shape = infer_broadcast_shape(op, ls, rs)
+    else:
+        out_shape = ls if use_l else rs
+    rsz = 1
+    if op == "dot":
+        rsz = max(ls[-1] if ls else 1, rs[-1] if rs else 1)
+        full = out_shape[:-1]
+        ls_b, rs_b = ls[:-1], rs[:-1]
+    else:
+        full = out_shape
+        ls_b, rs_b = ls, rs
+    F = _prod(full)
+    ld = _div_mod(ls_b, full) if use_l else (1, 1)
+    rd = _div_mod(rs_b, full) if use_r else (1, 1)
+    if use_l and ld is None:
+        lhs = lhs.expand(lhs.shape[0], *full, *( (rsz,) if op == "dot" else ()))
+        ld = (1, F)
+    if use_r and rd is None:
+        rhs = rhs.expand(rhs.shape[0], *full, *((rsz,) if op == "dot" else ()))
+        rd = (1, F)
+    if use_l:
+        lhs = lhs.reshape(lhs.shape[0], -1).contiguous()
+    if use_r:
+        rhs = rhs.reshape(rhs.shape[0], -1).contiguous()
+    return lhs, rhs, out_shape, F, rsz, (ld[0], ld[1], rd[0], rd[1])
+
+
+def _dev_lib(t):
+    if t.is_cuda:
+        return loader.cuda_lib(), True
+    return loader.cpu_lib(), False
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def gspmm(csr, op, reduce_op, ufeat, efeat, num_dst):
+    """out[v] = reduce_{(u,e,v)} op(ufeat[u], efeat[e]).
+
+    ``csr`` = (indptr, indices, eids|None) indexed by *destination* rows (CSC of the
+    graph). Returns (out, arg_u, arg_e); args are None for ``sum``.
+    """
+    indptr, indices, eids = csr
+    use_l = op != "copy_rhs"
+    use_r = op != "copy_lhs"
+    ref = ufeat if use_l else efeat
+    if use_l and use_r and ufeat.dtype != efeat.dtype:
+        raise DGLError(f"node and edge feature dtypes differ: {ufeat.dtype} vs {efeat.dtype}")
+    l2, r2, out_shape, F, _, bc = _prep_operands(op, ufeat, efeat)
+    out = torch.empty((num_dst, F), dtype=ref.dtype, device=ref.device)
+    arg_u = arg_e = None
+    if reduce_op != "sum":
+        if use_l:
+            arg_u = torch.empty((num_dst, F), dtype=indptr.dtype, device=ref.device)
+        if use_r:
+            arg_e = torch.empty((num_dst, F), dtype=indptr.dtype, device=ref.device)
+    if num_dst > 0 and F > 0:
+        lib, is_cuda = _dev_lib(ref)
+        args = [OPS[op], REDS[reduce_op], dtype_code(ref.dtype), id_code(indptr.dtype), _p(indptr), _p(indices),
+                _p(eids), num_dst, _p(l2), _p(r2), _p(out), _p(arg_u), _p(arg_e), F, *bc]
+        if is_cuda:
+            lib.fn("dglb200_cuda_gspmm", "iiiipppl" + "ppppp" + "lllll" + "p")(*args, loader.stream_ptr())
+        else:
+            lib.fn("dglb200_cpu_gspmm", "iiiipppl" + "ppppp" + "lllll")(*args)
+    out = out.reshape(num_dst, *out_shape)
+    if arg_u is not None:
+        arg_u = arg_u.reshape(num_dst, *out_shape)
+    if arg_e is not None:
+        arg_e = arg_e.reshape(num_dst, *out_shape)
+    return out, arg_u, arg_e
+
+
+def _prep_single(op, ufeat, efeat):
+    x = ufeat if op == "copy_lhs" else efeat
+    shp = tuple(x.shape[1:])
+    F = _prod(shp)
+    x2 = x.reshape(x.shape[0], -1).contiguous()
+    if op == "copy_lhs":
+        return x2, None, shp, F, 1, (1, F, 1, 1)
+    return None, x2, shp, F, 1, (1, 1, 1, F)
+
+
+def gsddmm(coo, op, lhs, rhs, lhs_target="u", rhs_target="v"):
+    """out[e] = op(lhs[target_l(e)], rhs[target_r(e)]) in edge-id order.
+    ``coo`` = (row, col) giving (src, dst) per edge id."""
+    row, col = coo
+    E = row.shape[0]
+    use_l = op != "copy_rhs"
+    use_r = op != "copy_lhs"
+    ref = lhs if use_l else rhs
+    if use_l and use_r and lhs.dtype != rhs.dtype:
+        raise DGLError(f"operand dtypes differ: {lhs.dtype} vs {rhs.dtype}")
+    l2, r2, out_shape, F, rsz, bc = _prep_operands(op, lhs, rhs)
+    out = torch.empty((E, F), dtype=ref.dtype, device=ref.device)
+    if E > 0 and F > 0:
+        lib, is_cuda = _dev_lib(ref)
+        args = [OPS[op], dtype_code(ref.dtype), id_code(row.dtype), _p(row), _p(col), E, _p(l2), _p(r2), _p(out),
+                TARGETS[lhs_target], TARGETS[rhs_target], F, rsz, *bc]
+        if is_cuda:
+            lib.fn("dglb200_cuda_gsddmm", "iiipplpppiillllllp")(*args, loader.stream_ptr())
+        else:
+            lib.fn("dglb200_cpu_gsddmm", "iiipplpppiillllll")(*args)
+    return out.reshape(E, *out_shape)
+
+
+def segment_reduce(offsets, x, reduce_op):
+    """Reduce contiguous row segments of ``x``; offsets has nseg+1 entries.
+    Returns (out, arg|None)."""
+    nseg = offsets.shape[0] - 1
+    shp = tuple(x.shape[1:])
+    F = _prod(shp)
+    x2 = x.reshape(x.shape[0], -1).contiguous()
+    out = torch.empty((nseg, F), dtype=x.dtype, device=x.device)
+    arg = None
+    if reduce_op != "sum":
+        arg = torch.empty((nseg, F), dtype=offsets.dtype, device=x.device)
+    if nseg > 0 and F > 0:
+        lib, is_cuda = _dev_lib(x)
+        args = [REDS[reduce_op], dtype_code(x.dtype), id_code(offsets.dtype), _p(offsets), nseg, _p(x2), _p(out),
+                _p(arg), F]
+        if is_cuda:
+            lib.fn("dglb200_cuda_segment_reduce", "iiiplppplp")(*args, loader.stream_ptr())
+        else:
+            lib.fn("dglb200_cpu_segment_reduce", "iiiplpppl")(*args)
+    out = out.reshape(nseg, *shp)
+    if arg is not None:
+        arg = arg.reshape(nseg, *shp)
+    return out, arg
+
+
+def edge_softmax_forward(csc, score, num_dst):
+    indptr, _, eids = csc
+    shp = tuple(score.shape[1:])
+    F = _prod(shp)
+    s2 = score.reshape(score.shape[0], -1).contiguous()
+    out = torch.empty_like(s2)
+    if num_dst > 0 and s2.numel() > 0:
+        lib, is_cuda = _dev_lib(score)
+        args = [dtype_code(score.dtype), id_code(indptr.dtype), _p(indptr), _p(eids), num_dst, _p(s2), _p(out), F]
+        if is_cuda:
+            lib.fn("dglb200_cuda_edge_softmax_fwd", "iipplpplp")(*args, loader.stream_ptr())
+        else:
+            lib.fn("dglb200_cpu_edge_softmax_fwd", "iipplppl")(*args)
+    return out.reshape(score.shape)
+
+
+def edge_softmax_backward(csc, out, grad_out, num_dst):
+    indptr, _, eids = csc
+    F = _prod(tuple(out.shape[1:]))
+    o2 = out.reshape(out.shape[0], -1).contiguous()
+    g2 = grad_out.reshape(out.shape[0], -1).contiguous()
+    gs = torch.empty_like(o2)
+    if num_dst > 0 and o2.numel() > 0:
+        lib, is_cuda = _dev_lib(out)
+        args = [dtype_code(out.dtype), id_code(indptr.dtype), _p(indptr), _p(eids), num_dst, _p(o2), _p(g2), _p(gs), F]
+        if is_cuda:
+            lib.fn("dglb200_cuda_edge_softmax_bwd", "iipplppplp")(*args, loader.stream_ptr())
+        else:
+            lib.fn("dglb200_cpu_edge_softmax_bwd", "iipplpppl")(*args)
+    return gs.reshape(out.shape)
