@@ -1,0 +1,235 @@
+// Neighbor sampling kernels for sm_100a (graph on device or host-pinned/UVA).
+//  * sample_ell_kernel : the hot path — uniform, without replacement, fanout <= 64; output is
+//    a dense ELL block [n_rows, fanout] (pad -1) + per-row counts, sized by an upper bound so
+//    NO host synchronisation is needed and multi-layer sampling chains on device-side counts.
+//    One thread per seed runs Floyd's subset algorithm (k RNG draws, O(k^2) dedup in registers)
+//    instead of the reference's block-per-row reservoir with atomics
+//    (/root/reference/src/array/cuda/rowwise_sampling.cu:43-229, graphbolt neighbor_sampler.cu:76-145).
+//  * sample_count / sample_fill : exact-size COO output for the DGL-compatible API, uniform or
+//    weighted (exponential-race keys == A-Res), with or without replacement.
+// RNG is counter based: (seed, global row, draw) -> value, so results do not depend on the launch
+// shape and are reproducible.
+#include "common.cuh"
+
+namespace dglb {
+
+constexpr int kMaxFloyd = 64;
+
+template <typename I>
+__global__ void __launch_bounds__(128) sample_ell_kernel(const I* __restrict__ indptr, const I* __restrict__ indices,
+                                                         const I* __restrict__ seeds, int64_t n_cap,
+                                                         const int64_t* __restrict__ n_dev, int fanout, uint64_t seed,
+                                                         I* __restrict__ out_nbr, I* __restrict__ out_eid,
+                                                         int32_t* __restrict__ out_cnt, int64_t* __restrict__ out_total) {
+  const int64_t n = n_dev ? *n_dev : n_cap;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_cap) return;
+  I* nb = out_nbr + i * fanout;
+  I* ne = out_eid ? out_eid + i * fanout : nullptr;
+  int cnt = 0;
+  if (i < n) {
+    const int64_t v = seeds[i];
+    if (v >= 0) {
+      const int64_t s = indptr[v], deg = indptr[v + 1] - s;
+      if (deg <= fanout) {
+        cnt = (int)deg;
+        for (int k = 0; k < cnt; ++k) {
+          nb[k] = indices[s + k];
+          if (ne) ne[k] = (I)(s + k);
+        }
+      } else {
+        cnt = fanout;
+        uint32_t chosen[kMaxFloyd];
+        int m = 0;
+        for (int64_t j = deg - fanout; j < deg; ++j, ++m) {
+          uint32_t t = rng_below(seed, (uint64_t)v * 0x9E37ull + (uint64_t)i, (uint64_t)m, (uint32_t)(j + 1));
+          bool dup = false;
+          for (int q = 0; q < m; ++q) dup |= (chosen[q] == t);
+          chosen[m] = dup ? (uint32_t)j : t;
+        }
+        for (int k = 0; k < fanout; ++k) {
+          nb[k] = indices[s + chosen[k]];
+          if (ne) ne[k] = (I)(s + chosen[k]);
+        }
+      }
+    }
+  }
+  for (int k = cnt; k < fanout; ++k) {
+    nb[k] = (I)-1;
+    if (ne) ne[k] = (I)-1;
+  }
+  out_cnt[i] = cnt;
+  if (out_total && i == 0) *out_total = n * (int64_t)fanout;  // upper bound of valid ELL slots
+}
+
+template <typename I>
+__global__ void __launch_bounds__(256) sample_count_kernel(const I* __restrict__ indptr, const I* __restrict__ eids,
+                                                           const I* __restrict__ seeds, int64_t n, int64_t fanout,
+                                                           int replace, const float* __restrict__ prob,
+                                                           int64_t* __restrict__ counts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t v = seeds[i];
+  const int64_t s = indptr[v], deg = indptr[v + 1] - s;
+  int64_t c;
+  if (deg == 0) {
+    c = 0;
+  } else if (prob) {
+    int64_t nz = 0;
+    for (int64_t k = 0; k < deg; ++k) nz += prob[eids ? (int64_t)eids[s + k] : s + k] > 0.f;
+    c = nz == 0 ? 0 : (fanout < 0 ? nz : (replace ? fanout : min(fanout, nz)));
+  } else {
+    c = fanout < 0 ? deg : (replace ? fanout : min(fanout, deg));
+  }
+  counts[i] = c;
+}
+
+template <typename I>
+__global__ void __launch_bounds__(128) sample_fill_kernel(const I* __restrict__ indptr, const I* __restrict__ indices,
+                                                          const I* __restrict__ eids, const I* __restrict__ seeds,
+                                                          int64_t n, int64_t fanout, int replace,
+                                                          const float* __restrict__ prob,
+                                                          const int64_t* __restrict__ offsets, uint64_t seed,
+                                                          I* __restrict__ out_src, I* __restrict__ out_dst,
+                                                          I* __restrict__ out_eid) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int64_t v = seeds[i];
+  const int64_t s = indptr[v], deg = indptr[v + 1] - s;
+  const int64_t o = offsets[i], cnt = offsets[i + 1] - o;
+  if (cnt == 0) return;
+  const uint64_t stream = (uint64_t)v * 0x9E37ull + (uint64_t)i;
+  auto emit = [&](int64_t slot, int64_t k) {
+    out_src[o + slot] = indices[s + k];
+    out_dst[o + slot] = (I)v;
+    out_eid[o + slot] = eids ? eids[s + k] : (I)(s + k);
+  };
+  if (!prob) {
+    if (!replace && cnt == deg) {
+      for (int64_t k = 0; k < deg; ++k) emit(k, k);
+    } else if (replace) {
+      for (int64_t k = 0; k < cnt; ++k) emit(k, rng_below(seed, stream, k, (uint32_t)deg));
+    } else if (cnt <= kMaxFloyd) {
+      uint32_t chosen[kMaxFloyd];
+      int m = 0;
+      for (int64_t j = deg - cnt; j < deg; ++j, ++m) {
+        uint32_t t = rng_below(seed, stream, m, (uint32_t)(j + 1));
+        bool dup = false;
+        for (int q = 0; q < m; ++q) dup |= (chosen[q] == t);
+        chosen[m] = dup ? (uint32_t)j : t;
+      }
+      for (int k = 0; k < cnt; ++k) emit(k, chosen[k]);
+    } else {
+      // selection sampling (Knuth algorithm S): O(deg), exact uniform subset
+      int64_t taken = 0;
+      for (int64_t k = 0; k < deg && taken < cnt; ++k) {
+        const float u = rng_uniform(seed, stream, k);
+        if (u * (float)(deg - k) < (float)(cnt - taken)) emit(taken++, k);
+      }
+    }
+  } else {
+    auto w = [&](int64_t k) { return prob[eids ? (int64_t)eids[s + k] : s + k]; };
+    if (replace) {
+      float tot = 0.f;
+      for (int64_t k = 0; k < deg; ++k) tot += fmaxf(w(k), 0.f);
+      for (int64_t c = 0; c < cnt; ++c) {
+        const float r = rng_uniform(seed, stream, c) * tot;
+        float acc = 0.f;
+        int64_t pick = -1;
+        for (int64_t k = 0; k < deg; ++k) {
+          const float wk = fmaxf(w(k), 0.f);
+          if (wk <= 0.f) continue;
+          acc += wk;
+          pick = k;
+          if (acc >= r) break;
+        }
+        emit(c, pick);
+      }
+    } else {
+      // keep the cnt smallest exponential-race keys (insertion into a sorted local buffer)
+      constexpr int KMAX = 128;
+      float keys[KMAX];
+      int32_t idx[KMAX];
+      const int kk = (int)min(cnt, (int64_t)KMAX);
+      int m = 0;
+      for (int64_t k = 0; k < deg; ++k) {
+        const float wk = w(k);
+        if (wk <= 0.f) continue;
+        const float key = -__logf(rng_uniform(seed, stream, k)) / wk;
+        if (m < kk) {
+          int p = m++;
+          while (p > 0 && keys[p - 1] > key) { keys[p] = keys[p - 1]; idx[p] = idx[p - 1]; --p; }
+          keys[p] = key; idx[p] = (int32_t)k;
+        } else if (key < keys[kk - 1]) {
+          int p = kk - 1;
+          while (p > 0 && keys[p - 1] > key) { keys[p] = keys[p - 1]; idx[p] = idx[p - 1]; --p; }
+          keys[p] = key; idx[p] = (int32_t)k;
+        }
+      }
+      for (int c = 0; c < kk && c < m; ++c) emit(c, idx[c]);
+    }
+  }
+}
+
+}  // namespace dglb
+
+using namespace dglb;
+
+// graph arrays may be host-pinned (uva=1): device aliases are resolved here.
+static const void* dev_alias(const void* p, int uva) {
+  if (!uva || !p) return p;
+  void* d = nullptr;
+  cudaError_t e = cudaHostGetDevicePointer(&d, const_cast<void*>(p), 0);
+  if (e != cudaSuccess) throw std::runtime_error(std::string("cudaHostGetDevicePointer: ") + cudaGetErrorString(e));
+  return d;
+}
+
+DGLB_API int dglb200_cuda_sample_ell(int idtype, const void* indptr, const void* indices, int uva, const void* seeds,
+                                     int64_t n_cap, const void* n_dev, int fanout, int64_t seed, void* out_nbr,
+                                     void* out_eid, void* out_cnt, void* out_total, void* stream) {
+  DGLB_TRY
+  DGLB_CHECK(fanout > 0 && fanout <= kMaxFloyd, "sample_ell supports 1 <= fanout <= 64");
+  if (n_cap == 0) return 0;
+  const void* ip = dev_alias(indptr, uva);
+  const void* ix = dev_alias(indices, uva);
+  DGLB_ID_SWITCH(idtype, I, {
+    sample_ell_kernel<I><<<(unsigned)((n_cap + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (const I*)ip, (const I*)ix, (const I*)seeds, n_cap, (const int64_t*)n_dev, fanout, (uint64_t)seed,
+        (I*)out_nbr, (I*)out_eid, (int32_t*)out_cnt, (int64_t*)out_total);
+  });
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}
+
+DGLB_API int dglb200_cuda_sample_count(int idtype, const void* indptr, const void* eids, int uva, const void* seeds,
+                                       int64_t n, int64_t fanout, int replace, const void* prob, void* counts,
+                                       void* stream) {
+  DGLB_TRY
+  if (n == 0) return 0;
+  const void* ip = dev_alias(indptr, uva);
+  const void* ep = dev_alias(eids, uva);
+  DGLB_ID_SWITCH(idtype, I, {
+    sample_count_kernel<I><<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const I*)ip, (const I*)ep, (const I*)seeds, n, fanout, replace, (const float*)prob, (int64_t*)counts);
+  });
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}
+
+DGLB_API int dglb200_cuda_sample_fill(int idtype, const void* indptr, const void* indices, const void* eids, int uva,
+                                      const void* seeds, int64_t n, int64_t fanout, int replace, const void* prob,
+                                      const void* offsets, int64_t seed, void* out_src, void* out_dst, void* out_eid,
+                                      void* stream) {
+  DGLB_TRY
+  if (n == 0) return 0;
+  const void* ip = dev_alias(indptr, uva);
+  const void* ix = dev_alias(indices, uva);
+  const void* ep = dev_alias(eids, uva);
+  DGLB_ID_SWITCH(idtype, I, {
+    sample_fill_kernel<I><<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        (const I*)ip, (const I*)ix, (const I*)ep, (const I*)seeds, n, fanout, replace, (const float*)prob,
+        (const int64_t*)offsets, (uint64_t)seed, (I*)out_src, (I*)out_dst, (I*)out_eid);
+  });
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}

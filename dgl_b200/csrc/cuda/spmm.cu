@@ -1,0 +1,265 @@
+// g-SpMM for sm_100a:  out[v, f] = reduce_{e=(u->v)} op(ufeat[u, lidx(f)], efeat[eid, ridx(f)])
+//
+// Two kernel families (both CSC row-parallel, fp32 accumulation for 16-bit inputs):
+//  * spmm_vec     : the hot path (copy_u / u_mul_e with a per-edge scalar, sum) — a sub-warp per
+//                   destination row, 4/8/16-byte vector gathers of whole feature rows, 4 neighbour
+//                   rows in flight per lane (MLP), column tiles on grid.y for wide features.
+//  * spmm_generic : every (op, reducer, broadcast) combination incl. arg-max/min outputs.
+// Replaces the reference's SpMMCsrKernel / cuSPARSE / COO-atomic paths
+// (/root/reference/src/array/cuda/spmm.cuh:413-732, spmm.cu:27-58) with one CSC family; no
+// descriptor creation, no workspace allocation, no host synchronisation per call.
+#include "common.cuh"
+
+namespace dglb {
+
+static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const char* get_last_error() { return g_last_error.c_str(); }
+
+template <int VB>
+struct VecT;
+template <>
+struct VecT<16> {
+  using type = uint4;
+};
+template <>
+struct VecT<8> {
+  using type = uint2;
+};
+template <>
+struct VecT<4> {
+  using type = uint32_t;
+};
+
+template <typename T, int VB>
+struct VecOps {
+  static constexpr int VE = VB / sizeof(T);
+  using V = typename VecT<VB>::type;
+  __device__ static __forceinline__ void fma(float* acc, const V& v, float w) {
+    const T* p = reinterpret_cast<const T*>(&v);
+#pragma unroll
+    for (int i = 0; i < VE; ++i) acc[i] = fmaf(to_f<T>(p[i]), w, acc[i]);
+  }
+  __device__ static __forceinline__ V pack(const float* acc, float scale) {
+    V v;
+    T* p = reinterpret_cast<T*>(&v);
+#pragma unroll
+    for (int i = 0; i < VE; ++i) p[i] = from_f<T>(acc[i] * scale);
+    return v;
+  }
+};
+
+template <typename V>
+__device__ __forceinline__ V ldg_vec(const V* p) {
+  return __ldg(p);
+}
+
+// sub lanes cooperate on one row; each lane owns NV vectors per column tile.
+template <typename T, typename I, int VB, int NV, bool HAS_W>
+__global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ indptr, const I* __restrict__ indices,
+                                                       const I* __restrict__ eids, int64_t num_rows,
+                                                       const T* __restrict__ x, const T* __restrict__ w,
+                                                       T* __restrict__ out, int64_t F, int nvec, int sub) {
+  using VO = VecOps<T, VB>;
+  using V = typename VO::V;
+  constexpr int VE = VO::VE;
+  constexpr int U = 4;
+  const int rows_per_block = blockDim.x / sub;
+  const int64_t row = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / sub;
+  if (row >= num_rows) return;
+  const int lane = threadIdx.x % sub;
+  const int vbase = blockIdx.y * sub * NV + lane;  // first vector owned by this lane
+  float acc[NV][VE];
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int i = 0; i < VE; ++i) acc[j][i] = 0.f;
+  const int64_t s = indptr[row], t = indptr[row + 1];
+  const int64_t rowvecs = F / VE;  // == nvec
+  int64_t p = s;
+  for (; p + U <= t; p += U) {
+    int64_t u[U];
+    float wt[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      u[k] = indices[p + k];
+      if (HAS_W) wt[k] = to_f<T>(w[eids ? (int64_t)eids[p + k] : p + k]);
+      else wt[k] = 1.f;
+    }
+    V v[U][NV];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const V* xr = reinterpret_cast<const V*>(x + u[k] * F);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = vbase + j * sub;
+        if (c < nvec) v[k][j] = ldg_vec(xr + c);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k)
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (vbase + j * sub < nvec) VO::fma(acc[j], v[k][j], wt[k]);
+  }
+  for (; p < t; ++p) {
+    const int64_t u = indices[p];
+    const float wt = HAS_W ? to_f<T>(w[eids ? (int64_t)eids[p] : p]) : 1.f;
+    const V* xr = reinterpret_cast<const V*>(x + u * F);
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const int c = vbase + j * sub;
+      if (c < nvec) {
+        V v = ldg_vec(xr + c);
+        VO::fma(acc[j], v, wt);
+      }
+    }
+  }
+  V* orow = reinterpret_cast<V*>(out + row * F);
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = vbase + j * sub;
+    if (c < nvec) orow[c] = VO::pack(acc[j], 1.f);
+  }
+  (void)rowvecs;
+}
+
+template <typename T, typename I, int OP, int RED>
+__global__ void __launch_bounds__(256) spmm_generic_kernel(const I* __restrict__ indptr, const I* __restrict__ indices,
+                                                           const I* __restrict__ eids, int64_t num_rows,
+                                                           const T* __restrict__ ufeat, const T* __restrict__ efeat,
+                                                           T* __restrict__ out, I* __restrict__ arg_u,
+                                                           I* __restrict__ arg_e, int64_t F, Bcast bc, int sub) {
+  using A = typename AccT<T>::type;
+  constexpr bool use_l = OP != kCopyRhs;
+  constexpr bool use_r = OP != kCopyLhs;
+  const int rows_per_block = blockDim.x / sub;
+  const int64_t row = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / sub;
+  if (row >= num_rows) return;
+  const int lane = threadIdx.x % sub;
+  const int64_t s = indptr[row], t = indptr[row + 1];
+  for (int64_t f = lane; f < F; f += sub) {
+    const int64_t lf = use_l ? (f / bc.ldiv) % bc.lmod : 0;
+    const int64_t rf = use_r ? (f / bc.rdiv) % bc.rmod : 0;
+    A acc = RED == kSum ? A(0) : (RED == kMax ? -INFINITY : INFINITY);
+    I au = -1, ae = -1;
+    for (int64_t p = s; p < t; ++p) {
+      const I u = indices[p];
+      const I e = eids ? eids[p] : (I)p;
+      const A l = use_l ? ld_acc<T, A>(ufeat + (int64_t)u * bc.lmod + lf) : A(0);
+      const A r = use_r ? ld_acc<T, A>(efeat + (int64_t)e * bc.rmod + rf) : A(0);
+      const A val = apply_op<A, OP>(l, r);
+      if (RED == kSum) {
+        acc += val;
+      } else if (RED == kMax ? (val > acc) : (val < acc)) {
+        acc = val;
+        au = u;
+        ae = e;
+      }
+    }
+    if (RED != kSum && s == t) acc = A(0);
+    out[row * F + f] = st_acc<T, A>(acc);
+    if (RED != kSum) {
+      if (arg_u) arg_u[row * F + f] = au;
+      if (arg_e) arg_e[row * F + f] = ae;
+    }
+  }
+}
+
+static int pow2_ge(int64_t x, int cap) {
+  int p = 1;
+  while (p < x && p < cap) p <<= 1;
+  return p;
+}
+
+template <typename T, typename I, int VB, bool HAS_W>
+void launch_vec(const I* indptr, const I* indices, const I* eids, int64_t n, const T* x, const T* w, T* out, int64_t F,
+                cudaStream_t st) {
+  constexpr int VE = VB / sizeof(T);
+  const int nvec = (int)(F / VE);
+  const int sub = pow2_ge(nvec, 32);
+  const int rows_per_block = 256 / sub;
+  const unsigned gx = (unsigned)((n + rows_per_block - 1) / rows_per_block);
+  const int per_lane = (nvec + sub - 1) / sub;
+  if (per_lane <= 1) {
+    spmm_vec_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub);
+  } else if (per_lane <= 2) {
+    spmm_vec_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub);
+  } else {
+    const unsigned gy = (unsigned)((nvec + sub * 4 - 1) / (sub * 4));
+    spmm_vec_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub);
+  }
+}
+
+template <typename T, typename I>
+bool try_vec(int op, int red, const I* indptr, const I* indices, const I* eids, int64_t n, const T* x, const T* w,
+             T* out, int64_t F, Bcast bc, cudaStream_t st) {
+  if (red != kSum) return false;
+  const bool copy = op == kCopyLhs;
+  const bool mul_scalar = op == kMul && bc.rmod == 1 && bc.ldiv == 1 && bc.lmod == F;
+  if (!copy && !mul_scalar) return false;
+  if (sizeof(T) == 8) return false;
+  const int64_t row_bytes = F * (int64_t)sizeof(T);
+  const uintptr_t xa = (uintptr_t)x, oa = (uintptr_t)out;
+  int vb = 0;
+  if (row_bytes % 16 == 0 && xa % 16 == 0 && oa % 16 == 0) vb = 16;
+  else if (row_bytes % 8 == 0 && xa % 8 == 0 && oa % 8 == 0) vb = 8;
+  else if (row_bytes % 4 == 0 && xa % 4 == 0 && oa % 4 == 0) vb = 4;
+  if (vb == 0) return false;
+#define LV(VBV)                                                                          \
+  if (vb == VBV) {                                                                       \
+    if (copy) launch_vec<T, I, VBV, false>(indptr, indices, eids, n, x, w, out, F, st);  \
+    else launch_vec<T, I, VBV, true>(indptr, indices, eids, n, x, w, out, F, st);        \
+    return true;                                                                         \
+  }
+  LV(16) LV(8) LV(4)
+#undef LV
+  return false;
+}
+
+template <typename T, typename I>
+void spmm_dispatch(int op, int red, const I* indptr, const I* indices, const I* eids, int64_t n, const T* u, const T* e,
+                   T* out, I* au, I* ae, int64_t F, Bcast bc, cudaStream_t st) {
+  if constexpr (!std::is_same<T, double>::value) {
+    if (try_vec<T, I>(op, red, indptr, indices, eids, n, u, e, out, F, bc, st)) return;
+  }
+  const int sub = pow2_ge(F, 32);
+  const int rows_per_block = 256 / sub;
+  const unsigned gx = (unsigned)((n + rows_per_block - 1) / rows_per_block);
+#define CASE(OPC, REDC)                                                                                              \
+  if (op == OPC && red == REDC) {                                                                                    \
+    spmm_generic_kernel<T, I, OPC, REDC><<<gx, 256, 0, st>>>(indptr, indices, eids, n, u, e, out, au, ae, F, bc, sub); \
+    return;                                                                                                          \
+  }
+  CASE(kAdd, kSum) CASE(kAdd, kMax) CASE(kAdd, kMin)
+  CASE(kMul, kSum) CASE(kMul, kMax) CASE(kMul, kMin)
+  CASE(kSub, kSum) CASE(kSub, kMax) CASE(kSub, kMin)
+  CASE(kDiv, kSum) CASE(kDiv, kMax) CASE(kDiv, kMin)
+  CASE(kCopyLhs, kSum) CASE(kCopyLhs, kMax) CASE(kCopyLhs, kMin)
+  CASE(kCopyRhs, kSum) CASE(kCopyRhs, kMax) CASE(kCopyRhs, kMin)
+#undef CASE
+  throw std::runtime_error("gspmm: bad op/reduce");
+}
+
+}  // namespace dglb
+
+using namespace dglb;
+
+DGLB_API const char* dglb200_last_error() { return dglb::get_last_error(); }
+
+DGLB_API int dglb200_cuda_gspmm(int op, int red, int dtype, int idtype, const void* indptr, const void* indices,
+                                const void* eids, int64_t num_rows, const void* ufeat, const void* efeat, void* out,
+                                void* arg_u, void* arg_e, int64_t F, int64_t ldiv, int64_t lmod, int64_t rdiv,
+                                int64_t rmod, void* stream) {
+  DGLB_TRY
+  Bcast bc{ldiv, lmod, rdiv, rmod};
+  cudaStream_t st = (cudaStream_t)stream;
+  DGLB_FLOAT_SWITCH(dtype, T, {
+    DGLB_ID_SWITCH(idtype, I, {
+      spmm_dispatch<T, I>(op, red, (const I*)indptr, (const I*)indices, (const I*)eids, num_rows, (const T*)ufeat,
+                          (const T*)efeat, (T*)out, (I*)arg_u, (I*)arg_e, F, bc, st);
+    });
+  });
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}

@@ -47,7 +47,7 @@ class DGLGraph:
         if graphs is None:
             graphs = [UnitGraph.from_coo(0, 0, torch.empty(0, dtype=torch.int64), torch.empty(0, dtype=torch.int64))]
             num_nodes = [0]
-        self._init(list(graphs), list(ntypes), [tuple(c) for c in canonical_etypes], list(num_nodes), node_frames,
+        self._init(list(graphs), None if ntypes is None else list(ntypes), [tuple(c) for c in canonical_etypes], list(num_nodes), node_frames,
                    edge_frames, srctypes, dsttypes)
 
     def _init(self, graphs, ntypes, canonical_etypes, num_nodes, node_frames, edge_frames, srctypes=None,
