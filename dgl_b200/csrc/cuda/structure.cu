@@ -295,6 +295,13 @@ DGLB_API int dglb200_cuda_unique_compact(int idtype, const void* first, int64_t 
     return 0;
   }
   const uint64_t mask = (uint64_t)cap - 1;
+  {
+    // (re)initialise the table and the output inside the stream so the call is graph-replayable
+    const size_t isz = idtype == kI32 ? 4 : 8;
+    DGLB_CUDA_CHECK(cudaMemsetAsync(keys, 0xFF, (size_t)cap * isz, st));
+    DGLB_CUDA_CHECK(cudaMemsetAsync(minpos, 0x7F, (size_t)cap * 4, st));
+    DGLB_CUDA_CHECK(cudaMemsetAsync(out_unique, 0xFF, (size_t)N * isz, st));
+  }
   DGLB_ID_SWITCH(idtype, I, {
     ht_insert_kernel<I><<<grid_for(N), 256, 0, st>>>((const I*)first, nfirst, (const I*)ids, n, (const int64_t*)n_dev,
                                                      (I*)keys, (int32_t*)minpos, (int32_t*)slot, mask);
@@ -320,6 +327,11 @@ DGLB_API int dglb200_cuda_map_ids(int idtype, const void* universe, int64_t nu, 
   cudaStream_t st = (cudaStream_t)stream;
   DGLB_CHECK((cap & (cap - 1)) == 0 && cap >= 2 * nu, "hash capacity must be a power of two >= 2*nu");
   const uint64_t mask = (uint64_t)cap - 1;
+  {
+    const size_t isz = idtype == kI32 ? 4 : 8;
+    DGLB_CUDA_CHECK(cudaMemsetAsync(keys, 0xFF, (size_t)cap * isz, st));
+    DGLB_CUDA_CHECK(cudaMemsetAsync(vals, 0x7F, (size_t)cap * 4, st));
+  }
   DGLB_ID_SWITCH(idtype, I, {
     if (nu > 0) ht_insert_kv_kernel<I><<<grid_for(nu), 256, 0, st>>>((const I*)universe, nu, (I*)keys, (int32_t*)vals, mask);
     if (n > 0) ht_find_kernel<I><<<grid_for(n), 256, 0, st>>>((const I*)ids, n, (const I*)keys, (const int32_t*)vals, mask, (I*)out);

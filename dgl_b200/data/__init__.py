@@ -1,0 +1,12 @@
+"""Datasets (parity: /root/reference/python/dgl/data/). No network access in this environment, so builtin
+datasets are synthesised with the published shapes (see synthetic.py); loaders for on-disk data are kept."""
+from .synthetic import SHAPES, rmat_edges, rmat_graph, shaped_dataset  # noqa: F401
+
+
+def __getattr__(name):
+    import importlib
+    for modname in ("dgl_dataset", "graph_serialize", "builtin", "csv_dataset", "utils"):
+        mod = importlib.import_module(f"{__name__}.{modname}")
+        if hasattr(mod, name):
+            return getattr(mod, name)
+    raise AttributeError(name)

@@ -1,0 +1,418 @@
+"""GraphSAGE: the DGL-style module and the fused B200 training engine.
+
+``GraphSAGE`` is the reference model of /root/reference/examples/multigpu/node_classification_sage.py:61-80
+(3x SAGEConv-mean, ReLU, dropout 0.5) written against the public ``dgl_b200.nn`` API.
+
+``FusedSAGETrainer`` is the B200-first execution of the same training step: sampling, block
+construction, aggregation, GEMMs, loss, backward, gradient all-reduce and Adam run from ONE CUDA
+graph with no host synchronisation (see csrc/cuda/engine.cu for the design notes). Mini-batches are
+mathematically the same computation as DataLoader + NeighborSampler + SAGEConv('mean') + Adam.
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .._native import loader
+from ..base import DGLError, dtype_code, id_code
+from ..nn import SAGEConv
+
+__all__ = ["GraphSAGE", "FusedSAGETrainer"]
+
+
+class GraphSAGE(nn.Module):
+    """Multi-layer GraphSAGE-mean on message-flow graphs."""
+
+    def __init__(self, in_size, hid_size, out_size, num_layers=3, dropout=0.5, aggregator="mean"):
+        super().__init__()
+        self.layers = nn.ModuleList()
+        sizes = [in_size] + [hid_size] * (num_layers - 1) + [out_size]
+        for i in range(num_layers):
+            self.layers.append(SAGEConv(sizes[i], sizes[i + 1], aggregator))
+        self.dropout = nn.Dropout(dropout)
+        self.hid_size = hid_size
+        self.out_size = out_size
+
+    def forward(self, blocks, x):
+        h = x
+        for l, (layer, block) in enumerate(zip(self.layers, blocks)):
+            h = layer(block, h)
+            if l != len(self.layers) - 1:
+                h = F.relu(h)
+                h = self.dropout(h)
+        return h
+
+    def full_forward(self, g, x):
+        h = x
+        for l, layer in enumerate(self.layers):
+            h = layer(g, h)
+            if l != len(self.layers) - 1:
+                h = F.relu(h)
+        return h
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
+
+
+class FusedSAGETrainer:
+    """Whole-step fused GraphSAGE trainer.
+
+    Parameters
+    ----------
+    graph : DGLGraph on the GPU (homogeneous). Its CSC is used (in-neighbour sampling).
+    feat : [N, F] node features (GPU). Stored in ``dtype`` (bf16 by default).
+    labels : [N] class ids (GPU).
+    fanouts : list, ``fanouts[i]`` = fan-out of layer i (same convention as NeighborSampler).
+    comm : optional :class:`dgl_b200.parallel.P2PComm` for multi-GPU data-parallel training; gradients
+        are averaged by a peer-memory kernel fused with the Adam update (no NCCL call).
+    """
+
+    def __init__(self, graph, feat, labels, num_classes, hidden=256, fanouts=(10, 10, 10), batch_size=1024, lr=1e-3,
+                 weight_decay=5e-4, dropout=0.5, dtype=torch.bfloat16, seed=0, comm=None, use_cuda_graph=True,
+                 betas=(0.9, 0.999), eps=1e-8):
+        if not feat.is_cuda:
+            raise DGLError("FusedSAGETrainer needs CUDA tensors (B200); use GraphSAGE + DataLoader on CPU")
+        self.dev = feat.device
+        self.lib = loader.cuda_lib()
+        indptr, indices, _ = graph._graphs[0].csc()
+        E = indices.shape[0]
+        N = graph.num_nodes()
+        if E >= 2 ** 31 or N >= 2 ** 31:
+            raise DGLError("fused engine uses int32 ids; graph too large for one shard")
+        self.indptr = indptr.to(torch.int32).contiguous()
+        self.indices = indices.to(torch.int32).contiguous()
+        self.N, self.E = N, E
+        self.dtype = dtype
+        self.feat = feat.to(dtype).contiguous()
+        self.labels = labels.to(torch.int32).contiguous()
+        self.F_in = feat.shape[1]
+        self.H = hidden
+        self.C = num_classes
+        self.L = len(fanouts)
+        self.fanouts = list(fanouts)
+        self.B = batch_size
+        self.lr, self.wd, self.p_drop = lr, weight_decay, dropout
+        self.betas, self.eps = betas, eps
+        self.seed = seed
+        self.comm = comm
+        self.world = 1 if comm is None else comm.world_size
+        self.rank = 0 if comm is None else comm.rank
+        if self.F_in % 2 or hidden % 8:
+            raise DGLError("feature sizes must be even (F_in) / multiples of 8 (hidden)")
+        # ---- layer dims: layer l (1-based) maps in_dims[l-1] -> out_dims[l-1]
+        self.in_dims = [self.F_in] + [hidden] * (self.L - 1)
+        self.out_dims = [hidden] * (self.L - 1) + [num_classes]
+        # ---- capacities: caps[l] = max |S_l|, S_L = seeds, S_{l-1} = unique(S_l U nbrs)
+        caps = [0] * (self.L + 1)
+        caps[self.L] = batch_size
+        for l in range(self.L, 1, -1):
+            caps[l - 1] = caps[l] * (1 + self.fanouts[l - 1])
+        self.caps = caps
+        self._alloc_params()
+        self._alloc_buffers()
+        self.use_graph = use_cuda_graph
+        self.graph = None
+        self._probe_mm()
+        self.gpu_launches_per_step = 0
+
+    # ------------------------------------------------------------------ parameters
+    def _alloc_params(self):
+        dev = self.dev
+        segs = []
+        off = 0
+        for l in range(self.L):
+            k, n = 2 * self.in_dims[l], self.out_dims[l]
+            segs.append(("W", l, off, (k, n)))
+            off += _pad8(k * n)
+            segs.append(("b", l, off, (n,)))
+            off += _pad8(n)
+        self.numel = off
+        self.segs = segs
+        self.param = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.adam_m = torch.zeros_like(self.param)
+        self.adam_v = torch.zeros_like(self.param)
+        self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev) if self.comm is None else self.comm.grad_buffer(off)
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(self.seed)
+        gain = math.sqrt(2.0)
+        self.W, self.b, self.Wb, self.gW, self.gb = [], [], [], [], []
+        for kind, l, o, shape in segs:
+            n = int(torch.tensor(shape).prod())
+            view = self.param[o:o + n].view(*shape)
+            if kind == "W":
+                k_in, n_out = self.in_dims[l], self.out_dims[l]
+                # same init as SAGEConv: xavier_uniform(gain=relu) on fc_self.weight / fc_neigh.weight [out, in]
+                bound = gain * math.sqrt(6.0 / (k_in + n_out))
+                w_self = (torch.rand(n_out, k_in, generator=gen) * 2 - 1) * bound
+                w_neigh = (torch.rand(n_out, k_in, generator=gen) * 2 - 1) * bound
+                view.copy_(torch.cat([w_self.t(), w_neigh.t()], 0).to(dev))
+                self.W.append(view)
+                self.Wb.append(self.shadow[o:o + n].view(*shape))
+                self.gW.append(self.grad[o:o + n].view(*shape))
+            else:
+                self.b.append(view)
+                self.gb.append(self.grad[o:o + n].view(*shape))
+        self.shadow.copy_(self.param)
+        self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def state_dict(self):
+        return {"param": self.param.clone(), "m": self.adam_m.clone(), "v": self.adam_v.clone(),
+                "step": self.step_dev.clone()}
+
+    def load_state_dict(self, sd):
+        self.param.copy_(sd["param"]); self.adam_m.copy_(sd["m"]); self.adam_v.copy_(sd["v"])
+        self.step_dev.copy_(sd["step"]); self.shadow.copy_(self.param)
+
+    def export_to_module(self, module: GraphSAGE):
+        """Copy the trained weights into a ``GraphSAGE`` module (fc_self / fc_neigh / bias)."""
+        with torch.no_grad():
+            for l, layer in enumerate(module.layers):
+                k = self.in_dims[l]
+                layer.fc_self.weight.copy_(self.W[l][:k].t())
+                layer.fc_neigh.weight.copy_(self.W[l][k:].t())
+                layer.fc_self.bias.copy_(self.b[l])
+
+    def import_from_module(self, module: GraphSAGE):
+        with torch.no_grad():
+            for l, layer in enumerate(module.layers):
+                self.W[l].copy_(torch.cat([layer.fc_self.weight.t(), layer.fc_neigh.weight.t()], 0))
+                self.b[l].copy_(layer.fc_self.bias)
+            self.shadow.copy_(self.param)
+
+    # ------------------------------------------------------------------ buffers
+    def _alloc_buffers(self):
+        dev, L = self.dev, self.L
+        i32 = torch.int32
+        self.seeds_pinned = torch.full((self.B,), -1, dtype=i32).pin_memory()
+        self.nvalid_pinned = torch.zeros(1, dtype=torch.int64).pin_memory()
+        self.loss_pinned = torch.zeros(1, dtype=torch.float32).pin_memory()
+        self.S = [None] * (L + 1)      # node sets (global ids), S[L] = seeds
+        self.n = [None] * (L + 1)      # device counts
+        self.nbr = [None] * (L + 1)    # ELL neighbour ids for layer l (global for l=1 else local in S[l-1])
+        self.nbr_g = [None] * (L + 1)  # global ids before relabel
+        self.cnt = [None] * (L + 1)
+        self.ws = [None] * (L + 1)     # compaction workspaces
+        for l in range(L, 0, -1):
+            cap, f = self.caps[l], self.fanouts[l - 1]
+            if l == L:
+                self.S[l] = torch.full((cap,), -1, dtype=i32, device=dev)
+            self.n[l] = torch.zeros(1, dtype=torch.int64, device=dev)
+            self.nbr_g[l] = torch.empty((cap, f), dtype=i32, device=dev)
+            self.cnt[l] = torch.empty(cap, dtype=i32, device=dev)
+            if l > 1:
+                N = cap + cap * f
+                hcap = 16
+                while hcap < 2 * N + 2:
+                    hcap <<= 1
+                sb = int(self.lib.raw("dglb200_cuda_scan_temp_bytes", ctypes.c_int64, [ctypes.c_int64])(N))
+                self.ws[l] = dict(keys=torch.empty(hcap, dtype=i32, device=dev),
+                                  minpos=torch.empty(hcap, dtype=i32, device=dev),
+                                  local=torch.empty(hcap, dtype=i32, device=dev), cap=hcap,
+                                  work=torch.empty((3, N), dtype=i32, device=dev),
+                                  temp=torch.empty(max(sb, 1), dtype=torch.uint8, device=dev), sb=sb)
+                self.S[l - 1] = torch.empty(N, dtype=i32, device=dev)
+                self.nbr[l] = torch.empty((cap, f), dtype=i32, device=dev)
+            else:
+                self.nbr[l] = self.nbr_g[l]
+        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.correct_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        # activations
+        self.A = [None] * (L + 1)
+        self.dH = [None] * (L + 1)
+        for l in range(1, L + 1):
+            self.A[l] = torch.empty((self.caps[l], 2 * self.in_dims[l - 1]), dtype=self.dtype, device=dev)
+            if l < L:
+                self.dH[l] = torch.empty((self.caps[l], self.out_dims[l - 1]), dtype=torch.float32, device=dev)
+        self.dlogits = torch.empty((self.B, self.C), dtype=torch.float32, device=dev)
+
+    def _probe_mm(self):
+        """Can torch.mm emit an fp32 result from bf16 operands (keeps dW in full precision)?"""
+        self.mm_fp32_out = False
+        try:
+            a = torch.zeros(8, 8, dtype=self.dtype, device=self.dev)
+            r = torch.mm(a, a, out_dtype=torch.float32)
+            self.mm_fp32_out = r.dtype == torch.float32
+        except Exception:  # noqa: BLE001
+            self.mm_fp32_out = False
+
+    def _mm32(self, a, b):
+        if a.dtype == torch.float32:
+            return torch.mm(a, b)
+        if self.mm_fp32_out:
+            return torch.mm(a, b, out_dtype=torch.float32)
+        return torch.mm(a, b).float()
+
+    # ------------------------------------------------------------------ the step (device side)
+    def _launch(self, name, sig, *args, kernels=1):
+        self.lib.fn(name, sig + "p")(*args, loader.stream_ptr())
+        self._launch_count += kernels
+        self._my_kernels += kernels
+
+    def _step_impl(self):
+        L, dt, it = self.L, dtype_code(self.dtype), id_code(torch.int32)
+        self._launch_count = 0
+        self._my_kernels = 0
+        self.S[L].copy_(self.seeds_pinned, non_blocking=True)
+        self.n[L].copy_(self.nvalid_pinned, non_blocking=True)
+        # ---------------- sampling + compaction, output layer first
+        for l in range(L, 0, -1):
+            cap, f = self.caps[l], self.fanouts[l - 1]
+            self._launch("dglb200_cuda_sample_ell", "ippiplpilppppp", it, _p(self.indptr), _p(self.indices), 0,
+                         _p(self.S[l]), cap, _p(self.n[l]), f, self.seed * 7919 + l, _p(self.step_dev),
+                         _p(self.nbr_g[l]), 0, _p(self.cnt[l]), 0)
+            if l > 1:
+                w = self.ws[l]
+                self._launch("dglb200_cuda_unique_compact", "iplplppppl" + "pppplppp", it, _p(self.S[l]), cap,
+                             _p(self.nbr_g[l]), cap * f, 0, _p(w["keys"]), _p(w["minpos"]), _p(w["local"]), w["cap"],
+                             _p(w["work"][0]), _p(w["work"][1]), _p(w["work"][2]), _p(w["temp"]), w["sb"],
+                             _p(self.S[l - 1]), _p(self.nbr[l]), _p(self.n[l - 1]), kernels=5)
+                self._launch_count += 5  # 3 memsets + 2 cub scan kernels
+        # ---------------- forward
+        Hs = [None] * (L + 1)
+        X = self.feat
+        for l in range(1, L + 1):
+            cap, f, Fi = self.caps[l], self.fanouts[l - 1], self.in_dims[l - 1]
+            self._launch("dglb200_engine_agg_concat", "iippppplii" + "p", dt, it, _p(X), _p(self.S[1]) if l == 1 else 0,
+                         _p(self.nbr[l]), _p(self.cnt[l]), _p(self.n[l]), cap, f, Fi, _p(self.A[l]))
+            if l < L:
+                Z = torch.mm(self.A[l], self.Wb[l - 1])
+                self._launch_count += 1
+                self._launch("dglb200_engine_bias_relu_dropout", "ippplifl" + "pi", dt, _p(Z), _p(self.b[l - 1]),
+                             _p(self.n[l]), cap, self.out_dims[l - 1], float(self.p_drop), self.seed * 104729 + l,
+                             _p(self.step_dev), 1)
+                Hs[l] = Z
+                X = Z
+            else:
+                logits = self._mm32(self.A[l], self.Wb[l - 1])
+                self._launch_count += 1
+        self.loss_dev.zero_()
+        self.correct_dev.zero_()
+        self._launch_count += 2
+        self._launch("dglb200_engine_ce_loss", "ppppplippp", _p(logits), _p(self.b[L - 1]), _p(self.labels),
+                     _p(self.S[L]), _p(self.n[L]), self.B, self.C, _p(self.dlogits), _p(self.loss_dev),
+                     _p(self.correct_dev))
+        # ---------------- backward
+        self.grad.zero_()
+        self._launch_count += 1
+        dZ = self.dlogits
+        for l in range(L, 0, -1):
+            cap, f, Fi = self.caps[l], self.fanouts[l - 1], self.in_dims[l - 1]
+            A = self.A[l]
+            if l == L:
+                self.gW[l - 1].copy_(torch.mm(A.float().t(), dZ))
+                self.gb[l - 1].copy_(dZ.sum(0))
+                self._launch_count += 5
+                dA = torch.mm(dZ, self.W[l - 1].t()) if l > 1 else None
+                dA_dt = dtype_code(torch.float32)
+            else:
+                self.gW[l - 1].copy_(self._mm32(A.t(), dZ))
+                self._launch_count += 2
+                dA = torch.mm(dZ, self.Wb[l - 1].t()) if l > 1 else None
+                dA_dt = dt
+            if l > 1:
+                self._launch_count += 1
+                dH = self.dH[l - 1]
+                dH.zero_()
+                self._launch_count += 1
+                self._launch("dglb200_engine_scatter_grad", "iippppliip", dA_dt, it, _p(dA), _p(self.nbr[l]),
+                             _p(self.cnt[l]), _p(self.n[l]), cap, f, Fi, _p(dH))
+                dZn = torch.empty((self.caps[l - 1], Fi), dtype=self.dtype, device=self.dev)
+                scale = 1.0 / (1.0 - self.p_drop) if self.p_drop > 0 else 1.0
+                self._launch("dglb200_engine_relu_bwd", "ippplifpp", dt, _p(dH), _p(Hs[l - 1]), _p(self.n[l - 1]),
+                             self.caps[l - 1], Fi, float(scale), _p(dZn), _p(self.gb[l - 2]))
+                dZ = dZn
+        # ---------------- gradient all-reduce fused with Adam
+        if self.comm is not None:
+            self.comm.barrier(0)  # every rank's gradients are complete and visible
+            self._launch_count += 1
+            self._my_kernels += 1
+            peers = self.comm.peer_grad_ptrs()
+        else:
+            peers = (ctypes.c_void_p * 1)(self.grad.data_ptr())
+        self._peers_keepalive = peers
+        self._launch("dglb200_engine_allreduce_adam", "ppippplfffffp", _p(self.param), ctypes.cast(peers, ctypes.c_void_p),
+                     self.world, _p(self.adam_m), _p(self.adam_v), _p(self.shadow), self.numel, float(self.lr),
+                     float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd), _p(self.step_dev), kernels=2)
+        if self.comm is not None:
+            self.comm.barrier(1)  # all ranks finished reading before anyone rewrites its gradients
+            self._launch_count += 1
+            self._my_kernels += 1
+        self.loss_pinned.copy_(self.loss_dev, non_blocking=True)
+        self.gpu_launches_per_step = self._my_kernels
+        self.total_launches_per_step = self._launch_count
+
+    # ------------------------------------------------------------------ public API
+    def _capture(self):
+        # warm-up on a side stream (cuBLAS handles / workspaces), then capture
+        s = torch.cuda.Stream(self.dev)
+        s.wait_stream(torch.cuda.current_stream(self.dev))
+        saved = self.state_dict()
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self._step_impl()
+        torch.cuda.current_stream(self.dev).wait_stream(s)
+        torch.cuda.synchronize(self.dev)
+        self.load_state_dict(saved)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self._step_impl()
+        self.load_state_dict(saved)
+        torch.cuda.synchronize(self.dev)
+
+    def load_seeds(self, seeds):
+        """Stage a batch of seed node ids (CPU tensor/list, <= batch_size) in pinned host memory."""
+        n = len(seeds)
+        if n > self.B:
+            raise DGLError(f"batch of {n} seeds exceeds batch_size={self.B}")
+        self.seeds_pinned[:n] = torch.as_tensor(seeds, dtype=torch.int32)
+        if n < self.B:
+            self.seeds_pinned[n:] = -1
+        self.nvalid_pinned[0] = n
+
+    def step_async(self, seeds=None):
+        """Enqueue one training step (H2D of seeds -> ... -> Adam -> D2H of the loss). No host sync."""
+        if seeds is not None:
+            self.load_seeds(seeds)
+        if self.use_graph:
+            if self.graph is None:
+                self._capture()
+            self.graph.replay()
+        else:
+            self._step_impl()
+
+    def train_step(self, seeds):
+        """One training step on ``seeds``; returns the mini-batch loss as a Python float (syncs)."""
+        self.step_async(seeds)
+        torch.cuda.current_stream(self.dev).synchronize()
+        return float(self.loss_pinned[0])
+
+    def last_loss(self):
+        return float(self.loss_pinned[0])
+
+    def sampled_edges_upper_bound(self):
+        return sum(self.caps[l] * self.fanouts[l - 1] for l in range(1, self.L + 1))
+
+    def last_sampled_edges(self):
+        """Exact number of sampled edges of the last step (reads device counters; syncs)."""
+        tot = 0
+        for l in range(1, self.L + 1):
+            n = int(self.n[l].item())
+            tot += int(self.cnt[l][:n].sum().item())
+        return tot
+
+    @torch.no_grad()
+    def predict(self, seeds):
+        """Sampled-neighbourhood inference for ``seeds`` (no dropout): returns logits [len(seeds), C]."""
+        mod = GraphSAGE(self.F_in, self.H, self.C, self.L, 0.0).to(self.dev)
+        self.export_to_module(mod)
+        raise NotImplementedError("use export_to_module() + DataLoader for inference")

@@ -36,8 +36,8 @@ def cuda_unique_compact(first, ids, return_device_count=False):
     if N >= _INT_MAX:
         raise DGLError("unique_compact supports fewer than 2^31 ids per call")
     cap = _pow2_cap(N)
-    keys = torch.full((cap,), -1, dtype=idt, device=dev)
-    minpos = torch.full((cap,), _INT_MAX, dtype=torch.int32, device=dev)
+    keys = torch.empty(cap, dtype=idt, device=dev)
+    minpos = torch.empty(cap, dtype=torch.int32, device=dev)
     local = torch.empty(cap, dtype=torch.int32, device=dev)
     work = torch.empty((3, max(N, 1)), dtype=torch.int32, device=dev)
     sb = _scan_bytes(max(N, 1))
@@ -59,8 +59,8 @@ def cuda_map_ids(universe, ids):
     universe = universe.to(device=dev, dtype=idt).contiguous()
     nu, n = universe.shape[0], ids.shape[0]
     cap = _pow2_cap(nu)
-    keys = torch.full((cap,), -1, dtype=idt, device=dev)
-    vals = torch.full((cap,), _INT_MAX, dtype=torch.int32, device=dev)
+    keys = torch.empty(cap, dtype=idt, device=dev)
+    vals = torch.empty(cap, dtype=torch.int32, device=dev)
     out = torch.empty(n, dtype=idt, device=dev)
     loader.cuda_lib().fn("dglb200_cuda_map_ids", "iplplpplpp")(
         id_code(idt), universe.data_ptr(), nu, ids.contiguous().data_ptr(), n, keys.data_ptr(), vals.data_ptr(), cap,

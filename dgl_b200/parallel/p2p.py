@@ -1,0 +1,158 @@
+"""Symmetric peer-mapped memory + device-side collectives over NVLink 5 / NVSwitch.
+
+``P2PComm`` allocates buffers with cudaMalloc, exchanges CUDA-IPC handles through the (NCCL/gloo) process
+group once at creation time, and afterwards every rank holds a table of peer pointers it can pass to
+kernels: barrier, one-shot all-reduce, halo-fused g-SpMM, sharded-table gather / scatter-add.
+Replaces the reference's python/dgl/cuda/nccl.py + DDP all-reduce + cooperative all-to-all
+ for the single-node 8xB200 case; NCCL remains the bootstrap and the baseline.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from .._native import loader
+from ..base import DGLError, dtype_code, id_code
+
+
+class _RawCuda:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+class SymmetricBuffer:
+    """One allocation per rank of identical size; ``local`` is a torch view of this rank's copy,
+    ``ptrs`` the table of all ranks' device pointers (index = rank)."""
+
+    def __init__(self, comm, nbytes):
+        self.comm = comm
+        self.nbytes = int(nbytes)
+        lib = comm.lib
+        p = ctypes.c_void_p()
+        lib.fn("dglb200_comm_malloc", "lp")(self.nbytes, ctypes.addressof(p))
+        self.local_ptr = p.value
+        ptrs = [None] * comm.world_size
+        ptrs[comm.rank] = self.local_ptr
+        if comm.world_size > 1:
+            handle = (ctypes.c_char * 64)()
+            lib.fn("dglb200_comm_ipc_get", "pp")(self.local_ptr, ctypes.addressof(handle))
+            gathered = [None] * comm.world_size
+            dist.all_gather_object(gathered, bytes(handle.raw), group=comm.group)
+            for r, h in enumerate(gathered):
+                if r == comm.rank:
+                    continue
+                buf = ctypes.create_string_buffer(h, 64)
+                q = ctypes.c_void_p()
+                lib.fn("dglb200_comm_ipc_open", "pp")(ctypes.addressof(buf), ctypes.addressof(q))
+                ptrs[r] = q.value
+        self.ptrs = ptrs
+        self.ptr_array = (ctypes.c_void_p * comm.world_size)(*ptrs)
+        self._raw = _RawCuda(self.local_ptr, self.nbytes)
+        self.local_bytes = torch.as_tensor(self._raw, device=comm.device)
+
+    def view(self, dtype, shape=None):
+        t = self.local_bytes.view(dtype)
+        return t if shape is None else t[: int(torch.tensor(shape).prod())].view(*shape)
+
+    def ptr_table(self):
+        return ctypes.cast(self.ptr_array, ctypes.c_void_p)
+
+
+class P2PComm:
+    """Per-process communicator over peer-mapped memory. Requires all ranks on one NVLink domain."""
+
+    def __init__(self, group=None, device=None, timeout_s=20.0):
+        if not torch.cuda.is_available():
+            raise DGLError("P2PComm needs CUDA devices")
+        self.group = group
+        if dist.is_initialized():
+            self.rank = dist.get_rank(group)
+            self.world_size = dist.get_world_size(group)
+        else:
+            self.rank, self.world_size = 0, 1
+        if self.world_size > 8:
+            raise DGLError("P2PComm supports up to 8 ranks (one NVSwitch domain)")
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.lib = loader.cuda_lib()
+        self.timeout_s = float(timeout_s)
+        self._flags = SymmetricBuffer(self, 8 * 8 * 4)  # 4 barrier channels x 8 ranks x u64
+        self._epoch = torch.zeros(4, dtype=torch.int64, device=self.device)
+        self._error = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._grad = None
+        self._bufs = []
+        if self.world_size > 1:
+            dist.barrier(group=self.group)
+
+    # ------------------------------------------------------------------ memory
+    def alloc(self, nbytes):
+        b = SymmetricBuffer(self, nbytes)
+        self._bufs.append(b)
+        return b
+
+    def grad_buffer(self, numel):
+        self._grad = self.alloc(int(numel) * 4)
+        return self._grad.view(torch.float32)[:numel]
+
+    def peer_grad_ptrs(self):
+        return self._grad.ptr_array
+
+    # ------------------------------------------------------------------ collectives
+    def barrier(self, channel=0):
+        """Device-side barrier enqueued on the current stream (no host sync; CUDA-graph capturable)."""
+        flag_ptrs = (ctypes.c_void_p * self.world_size)(*[p + channel * 64 for p in self._flags.ptrs])
+        self._keep = flag_ptrs
+        self.lib.fn("dglb200_comm_barrier", "piippdp")(
+            ctypes.cast(flag_ptrs, ctypes.c_void_p), self.rank, self.world_size,
+            self._epoch.data_ptr() + 8 * channel, self._error.data_ptr(), self.timeout_s, loader.stream_ptr())
+
+    def publish_and_barrier(self, step_dev=None):
+        self.barrier(0)
+
+    def check_error(self):
+        if int(self._error.item()) != 0:
+            raise DGLError("device-side barrier timed out (a peer rank is stuck or dead)")
+
+    def all_reduce(self, buf: SymmetricBuffer, out, numel, scale=1.0, out_bf16=None, sync=True):
+        """out = scale * sum over ranks of ``buf`` (fp32). One-shot: every rank pulls every peer's copy
+        with 16-byte P2P loads; ``sync`` adds the barriers that order it against producers/consumers."""
+        if sync:
+            self.barrier(1)
+        self.lib.fn("dglb200_comm_allreduce", "pipplfp")(
+            buf.ptr_table(), self.world_size, out.data_ptr(), 0 if out_bf16 is None else out_bf16.data_ptr(),
+            int(numel), float(scale), loader.stream_ptr())
+        if sync:
+            self.barrier(2)
+
+    def halo_spmm(self, indptr, indices, shards: SymmetricBuffer, shard_rows, feat_dim, dtype, out, mean=True,
+                  edge_weight=None):
+        """Aggregation over a range-partitioned feature table with remote rows fetched over NVLink inside
+        the kernel (no materialised halo exchange). ``indices`` hold GLOBAL source ids."""
+        self.lib.fn("dglb200_comm_halo_spmm", "iipplpilipipp")(
+            dtype_code(dtype), id_code(indptr.dtype), indptr.data_ptr(), indices.data_ptr(), indptr.shape[0] - 1,
+            shards.ptr_table(), self.world_size, int(shard_rows), int(feat_dim), out.data_ptr(), 1 if mean else 0,
+            0 if edge_weight is None else edge_weight.data_ptr(), loader.stream_ptr())
+        return out
+
+    def halo_spmm_backward(self, indptr, indices, dshards: SymmetricBuffer, shard_rows, feat_dim, dout, mean=True):
+        self.lib.fn("dglb200_comm_halo_spmm_bwd", "iipplpilipip")(
+            dtype_code(dout.dtype), id_code(indptr.dtype), indptr.data_ptr(), indices.data_ptr(),
+            indptr.shape[0] - 1, dshards.ptr_table(), self.world_size, int(shard_rows), int(feat_dim),
+            dout.data_ptr(), 1 if mean else 0, loader.stream_ptr())
+
+    def gather(self, shards: SymmetricBuffer, shard_rows, idx, out):
+        row_bytes = out.element_size() * int(out[0].numel()) if out.shape[0] else 0
+        if out.shape[0]:
+            self.lib.fn("dglb200_comm_p2p_gather", "ipilplplp")(
+                id_code(idx.dtype), shards.ptr_table(), self.world_size, int(shard_rows), idx.data_ptr(),
+                idx.shape[0], out.data_ptr(), row_bytes, loader.stream_ptr())
+        return out
+
+    def scatter_add(self, shards: SymmetricBuffer, shard_rows, idx, vals):
+        if idx.shape[0]:
+            self.lib.fn("dglb200_comm_p2p_scatter_add", "ipilplpip")(
+                id_code(idx.dtype), shards.ptr_table(), self.world_size, int(shard_rows), idx.data_ptr(),
+                idx.shape[0], vals.data_ptr(), int(vals.shape[1]), loader.stream_ptr())
