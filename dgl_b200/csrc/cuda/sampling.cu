@@ -23,12 +23,12 @@ __global__ void __launch_bounds__(128) sample_ell_kernel(const I* __restrict__ i
                                                          int32_t* __restrict__ out_cnt, int64_t* __restrict__ out_total) {
   const int64_t n = n_dev ? *n_dev : n_cap;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_cap) return;
+  const bool active = i < n_cap;
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0xD6E8FEB86659FD93ull;  // per-step stream under graph replay
   I* nb = out_nbr + i * fanout;
   I* ne = out_eid ? out_eid + i * fanout : nullptr;
   int cnt = 0;
-  if (i < n) {
+  if (active && i < n) {
     const int64_t v = seeds[i];
     if (v >= 0) {
       const int64_t s = indptr[v], deg = indptr[v + 1] - s;
@@ -55,12 +55,18 @@ __global__ void __launch_bounds__(128) sample_ell_kernel(const I* __restrict__ i
       }
     }
   }
-  for (int k = cnt; k < fanout; ++k) {
-    nb[k] = (I)-1;
-    if (ne) ne[k] = (I)-1;
+  if (active) {
+    for (int k = cnt; k < fanout; ++k) {
+      nb[k] = (I)-1;
+      if (ne) ne[k] = (I)-1;
+    }
+    out_cnt[i] = cnt;
   }
-  out_cnt[i] = cnt;
-  if (out_total && i == 0) *out_total = n * (int64_t)fanout;  // upper bound of valid ELL slots
+  if (out_total) {  // running total of sampled edges (warp-aggregated atomic)
+    int wsum = cnt;
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if ((threadIdx.x & 31) == 0 && wsum > 0) atomicAdd((unsigned long long*)out_total, (unsigned long long)wsum);
+  }
 }
 
 template <typename I>

@@ -104,6 +104,8 @@ class FusedSAGETrainer:
         self.betas, self.eps = betas, eps
         self.seed = seed
         self.comm = comm
+        if dtype not in (torch.bfloat16, torch.float32):
+            raise DGLError("FusedSAGETrainer supports dtype bfloat16 (tensor-core path) or float32")
         self.world = 1 if comm is None else comm.world_size
         self.rank = 0 if comm is None else comm.rank
         if self.F_in % 2 or hidden % 8:
@@ -157,7 +159,7 @@ class FusedSAGETrainer:
                 w_neigh = (torch.rand(n_out, k_in, generator=gen) * 2 - 1) * bound
                 view.copy_(torch.cat([w_self.t(), w_neigh.t()], 0).to(dev))
                 self.W.append(view)
-                self.Wb.append(self.shadow[o:o + n].view(*shape))
+                self.Wb.append(self.shadow[o:o + n].view(*shape) if self.dtype == torch.bfloat16 else view)
                 self.gW.append(self.grad[o:o + n].view(*shape))
             else:
                 self.b.append(view)
@@ -193,8 +195,12 @@ class FusedSAGETrainer:
     def _alloc_buffers(self):
         dev, L = self.dev, self.L
         i32 = torch.int32
-        self.seeds_pinned = torch.full((self.B,), -1, dtype=i32).pin_memory()
-        self.nvalid_pinned = torch.zeros(1, dtype=torch.int64).pin_memory()
+        # host->device staging: ring of pinned slots [B seeds | int64 count] + one device landing buffer
+        self.RING = 4
+        self.stage_pinned = [torch.full((self.B + 2,), -1, dtype=i32).pin_memory() for _ in range(self.RING)]
+        self.stage_events = [None] * self.RING
+        self.stage_dev = torch.full((self.B + 2,), -1, dtype=i32, device=dev)
+        self._slot = 0
         self.loss_pinned = torch.zeros(1, dtype=torch.float32).pin_memory()
         self.S = [None] * (L + 1)      # node sets (global ids), S[L] = seeds
         self.n = [None] * (L + 1)      # device counts
@@ -205,8 +211,10 @@ class FusedSAGETrainer:
         for l in range(L, 0, -1):
             cap, f = self.caps[l], self.fanouts[l - 1]
             if l == L:
-                self.S[l] = torch.full((cap,), -1, dtype=i32, device=dev)
-            self.n[l] = torch.zeros(1, dtype=torch.int64, device=dev)
+                self.S[l] = self.stage_dev[: self.B]
+                self.n[l] = self.stage_dev[self.B:].view(torch.int64)
+            else:
+                self.n[l] = torch.zeros(1, dtype=torch.int64, device=dev)
             self.nbr_g[l] = torch.empty((cap, f), dtype=i32, device=dev)
             self.cnt[l] = torch.empty(cap, dtype=i32, device=dev)
             if l > 1:
@@ -225,6 +233,7 @@ class FusedSAGETrainer:
             else:
                 self.nbr[l] = self.nbr_g[l]
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.edges_total = torch.zeros(1, dtype=torch.int64, device=dev)  # running count of sampled edges
         self.correct_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         # activations
         self.A = [None] * (L + 1)
@@ -262,14 +271,12 @@ class FusedSAGETrainer:
         L, dt, it = self.L, dtype_code(self.dtype), id_code(torch.int32)
         self._launch_count = 0
         self._my_kernels = 0
-        self.S[L].copy_(self.seeds_pinned, non_blocking=True)
-        self.n[L].copy_(self.nvalid_pinned, non_blocking=True)
         # ---------------- sampling + compaction, output layer first
         for l in range(L, 0, -1):
             cap, f = self.caps[l], self.fanouts[l - 1]
             self._launch("dglb200_cuda_sample_ell", "ippiplpilppppp", it, _p(self.indptr), _p(self.indices), 0,
                          _p(self.S[l]), cap, _p(self.n[l]), f, self.seed * 7919 + l, _p(self.step_dev),
-                         _p(self.nbr_g[l]), 0, _p(self.cnt[l]), 0)
+                         _p(self.nbr_g[l]), 0, _p(self.cnt[l]), _p(self.edges_total))
             if l > 1:
                 w = self.ws[l]
                 self._launch("dglb200_cuda_unique_compact", "iplplppppl" + "pppplppp", it, _p(self.S[l]), cap,
@@ -341,7 +348,7 @@ class FusedSAGETrainer:
             peers = (ctypes.c_void_p * 1)(self.grad.data_ptr())
         self._peers_keepalive = peers
         self._launch("dglb200_engine_allreduce_adam", "ppippplfffffp", _p(self.param), ctypes.cast(peers, ctypes.c_void_p),
-                     self.world, _p(self.adam_m), _p(self.adam_v), _p(self.shadow), self.numel, float(self.lr),
+                     self.world, _p(self.adam_m), _p(self.adam_v), _p(self.shadow) if self.dtype == torch.bfloat16 else 0, self.numel, float(self.lr),
                      float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd), _p(self.step_dev), kernels=2)
         if self.comm is not None:
             self.comm.barrier(1)  # all ranks finished reading before anyone rewrites its gradients
@@ -359,7 +366,7 @@ class FusedSAGETrainer:
         saved = self.state_dict()
         with torch.cuda.stream(s):
             for _ in range(2):
-                self._step_impl()
+                self._step_impl()  # runs on whatever seeds are staged (valid ids: load_seeds precedes capture)
         torch.cuda.current_stream(self.dev).wait_stream(s)
         torch.cuda.synchronize(self.dev)
         self.load_state_dict(saved)
@@ -370,19 +377,30 @@ class FusedSAGETrainer:
         torch.cuda.synchronize(self.dev)
 
     def load_seeds(self, seeds):
-        """Stage a batch of seed node ids (CPU tensor/list, <= batch_size) in pinned host memory."""
+        """Stage a batch of seed ids (CPU tensor/list, <= batch_size): write them to a pinned ring slot and
+        enqueue the host->device copy on the current stream. Never blocks unless the ring wraps onto a
+        slot whose copy has not executed yet."""
         n = len(seeds)
         if n > self.B:
             raise DGLError(f"batch of {n} seeds exceeds batch_size={self.B}")
-        self.seeds_pinned[:n] = torch.as_tensor(seeds, dtype=torch.int32)
+        k = self._slot
+        self._slot = (k + 1) % self.RING
+        if self.stage_events[k] is not None:
+            self.stage_events[k].synchronize()
+        buf = self.stage_pinned[k]
+        buf[:n] = torch.as_tensor(seeds, dtype=torch.int32)
         if n < self.B:
-            self.seeds_pinned[n:] = -1
-        self.nvalid_pinned[0] = n
+            buf[n:self.B] = -1
+        buf[self.B:].view(torch.int64)[0] = n
+        self.stage_dev.copy_(buf, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self.stage_events[k] = ev
 
-    def step_async(self, seeds=None):
-        """Enqueue one training step (H2D of seeds -> ... -> Adam -> D2H of the loss). No host sync."""
-        if seeds is not None:
-            self.load_seeds(seeds)
+    def step_async(self, seeds):
+        """Enqueue one training step: H2D of the seeds from pinned memory -> sample -> ... -> Adam -> D2H of
+        the loss into pinned memory. Does not synchronise with the host."""
+        self.load_seeds(seeds)
         if self.use_graph:
             if self.graph is None:
                 self._capture()
@@ -398,6 +416,10 @@ class FusedSAGETrainer:
 
     def last_loss(self):
         return float(self.loss_pinned[0])
+
+    def total_sampled_edges(self):
+        """Edges sampled since construction (device counter; syncs)."""
+        return int(self.edges_total.item())
 
     def sampled_edges_upper_bound(self):
         return sum(self.caps[l] * self.fanouts[l - 1] for l in range(1, self.L + 1))

@@ -97,7 +97,7 @@ def test_engine_matches_torch(dtype):
         w.grad = ww.grad
     o.step()
     for l in range(tr.L):
-        big = W[l].grad.abs() > 1e-4
+        big = W[l].grad.abs() > (1e-4 if dtype == torch.float32 else 0.05 * W[l].grad.abs().max())
         assert (tr.W[l][big] - opt_ref[l][big]).abs().max() < 5e-3
 
 
