@@ -229,7 +229,9 @@ def run_ours(args):
             loss = tr.train_step(next(it))  # pinned seeds -> H2D -> step -> D2H loss -> host float
         return loss
 
+    torch.cuda.profiler.start()  # no-op unless run under `ncu --profile-from-start off`
     ms = timed(dev, loop_async)
+    torch.cuda.profiler.stop()
     clk = clocks.stop() if rank == 0 else None
     e_after = tr.total_sampled_edges()
     edges = sum_over_ranks(float(e_after - e_before), dev)
