@@ -26,14 +26,15 @@ template <typename T, typename I, int VB>
 __global__ void __launch_bounds__(256) agg_concat_kernel(const T* __restrict__ X, const I* __restrict__ self_ids,
                                                          const I* __restrict__ nbr, const int32_t* __restrict__ cnt,
                                                          const int64_t* __restrict__ n_dev, int64_t n_cap, int fanout,
-                                                         int F, T* __restrict__ A, int sub) {
+                                                         int F, T* __restrict__ A, int sub, int zero_pad) {
   constexpr int VE = VB / sizeof(T);
   using V = typename std::conditional<VB == 16, uint4, typename std::conditional<VB == 8, uint2, uint32_t>::type>::type;
   const int rows_per_block = blockDim.x / sub;
   const int lane = threadIdx.x % sub;
   const int nvec = F / VE;
-  const int64_t n = *n_dev;
-  for (int64_t d = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / sub; d < n_cap;
+  const int64_t n = min(*n_dev, n_cap);
+  const int64_t n_loop = zero_pad ? n_cap : n;
+  for (int64_t d = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / sub; d < n_loop;
        d += (int64_t)gridDim.x * rows_per_block) {
     V* arow = reinterpret_cast<V*>(A + d * 2 * F);
     if (d >= n) {
@@ -54,7 +55,10 @@ __global__ void __launch_bounds__(256) agg_concat_kernel(const T* __restrict__ X
       for (int i = 0; i < VE; ++i) acc[i] = 0.f;
       int k = 0;
       for (; k + 4 <= c_; k += 4) {  // 4 neighbour rows in flight
-        const int64_t u0 = nb[k], u1 = nb[k + 1], u2 = nb[k + 2], u3 = nb[k + 3];
+        // ids < 0 only appear after a (flagged) capacity overflow: clamp to row 0, weight 0 is not
+        // needed because the overflowing step is reported and capacities are raised
+        const int64_t u0 = max((int64_t)nb[k], (int64_t)0), u1 = max((int64_t)nb[k + 1], (int64_t)0),
+                      u2 = max((int64_t)nb[k + 2], (int64_t)0), u3 = max((int64_t)nb[k + 3], (int64_t)0);
         V v0 = __ldg(reinterpret_cast<const V*>(X + u0 * F) + c);
         V v1 = __ldg(reinterpret_cast<const V*>(X + u1 * F) + c);
         V v2 = __ldg(reinterpret_cast<const V*>(X + u2 * F) + c);
@@ -67,7 +71,7 @@ __global__ void __launch_bounds__(256) agg_concat_kernel(const T* __restrict__ X
         for (int i = 0; i < VE; ++i) acc[i] += (to_f<T>(p0[i]) + to_f<T>(p1[i])) + (to_f<T>(p2[i]) + to_f<T>(p3[i]));
       }
       for (; k < c_; ++k) {
-        const int64_t u = nb[k];
+        const int64_t u = max((int64_t)nb[k], (int64_t)0);
         V v = __ldg(reinterpret_cast<const V*>(X + u * F) + c);
         const T* p = reinterpret_cast<const T*>(&v);
 #pragma unroll
@@ -91,13 +95,13 @@ __global__ void __launch_bounds__(256) bias_relu_dropout_kernel(T* __restrict__ 
   const int64_t n = *n_dev;
   const uint64_t sd = seed + (step_dev ? (uint64_t)(*step_dev) * 0x9E3779B97F4A7C15ull : 0ull);
   const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-  const int64_t total = n_cap * N;
+  const int64_t total = min(n, n_cap) * N;  // rows >= n are never consumed
   for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2; i < total;
        i += (int64_t)gridDim.x * blockDim.x * 2) {
     const int64_t r = i / N;
     const int c = (int)(i - r * N);
     float v0 = 0.f, v1 = 0.f;
-    if (r < n) {
+    {
       v0 = to_f<T>(Z[i]) + bias[c];
       v1 = to_f<T>(Z[i + 1]) + bias[c + 1];
       if (relu) { v0 = fmaxf(v0, 0.f); v1 = fmaxf(v1, 0.f); }
@@ -188,28 +192,70 @@ __global__ void __launch_bounds__(256) scatter_grad_kernel(const T* __restrict__
   }
 }
 
-// dZ[r,c] = dH[r,c] * (H[r,c] > 0) * scale (rows >= n -> 0); db[c] += sum_r dZ[r,c]
+// dZ[r,c] = dH[r,c] * (H[r,c] > 0) * scale for r < n, 0 for n <= r < n_cap;  db[c] += sum_r dZ[r,c].
+// 8 columns per thread (16B bf16 / 32B fp32 vectors), N/8 threads per row, block-level column sums
+// in shared memory, one atomicAdd per column per block.
 template <typename T>
 __global__ void __launch_bounds__(256) relu_bwd_kernel(const float* __restrict__ dH, const T* __restrict__ H,
                                                        const int64_t* __restrict__ n_dev, int64_t n_cap, int N,
                                                        float scale, T* __restrict__ dZ, float* __restrict__ db,
                                                        int rows_per_block) {
-  const int64_t n = *n_dev;
+  extern __shared__ float s_db[];
+  const int64_t n = min(*n_dev, n_cap);
+  const int tpr = N / 8;                      // threads per row
+  const int rpi = blockDim.x / tpr;           // rows per iteration
+  const int c0 = (threadIdx.x % tpr) * 8;
+  const int rsub = threadIdx.x / tpr;
   const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  for (int c = threadIdx.x; c < N; c += blockDim.x) {
-    float acc = 0.f;
-    for (int64_t r = r0; r < r0 + rows_per_block && r < n_cap; ++r) {
-      float g = 0.f;
-      if (r < n) {
-        const float h = to_f<T>(H[r * N + c]);
-        g = h > 0.f ? dH[r * N + c] * scale : 0.f;
+  for (int i = threadIdx.x; i < N; i += blockDim.x) s_db[i] = 0.f;
+  __syncthreads();
+  float acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+  for (int64_t r = r0 + rsub; r < r0 + rows_per_block && r < n_cap; r += rpi) {
+    T out[8];
+    if (r < n) {
+      const float4 g0 = *reinterpret_cast<const float4*>(dH + r * N + c0);
+      const float4 g1 = *reinterpret_cast<const float4*>(dH + r * N + c0 + 4);
+      T h[8];
+      if (sizeof(T) == 2) *reinterpret_cast<uint4*>(h) = *reinterpret_cast<const uint4*>(H + r * N + c0);
+      else {
+        *reinterpret_cast<float4*>(h) = *reinterpret_cast<const float4*>(H + r * N + c0);
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(h) + 4) = *reinterpret_cast<const float4*>(H + r * N + c0 + 4);
       }
-      const T gq = from_f<T>(g);
-      dZ[r * N + c] = gq;
-      acc += to_f<T>(gq);
+      const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const float v = to_f<T>(h[k]) > 0.f ? g[k] * scale : 0.f;
+        out[k] = from_f<T>(v);
+        acc[k] += to_f<T>(out[k]);
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) out[k] = from_f<T>(0.f);
     }
-    if (db && acc != 0.f) atomicAdd(db + c, acc);
+    if (sizeof(T) == 2) *reinterpret_cast<uint4*>(dZ + r * N + c0) = *reinterpret_cast<uint4*>(out);
+    else {
+      *reinterpret_cast<float4*>(dZ + r * N + c0) = *reinterpret_cast<float4*>(out);
+      *reinterpret_cast<float4*>(dZ + r * N + c0 + 4) = *reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + 4);
+    }
   }
+  if (db) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      if (acc[k] != 0.f) atomicAdd(&s_db[c0 + k], acc[k]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < N; i += blockDim.x)
+      if (s_db[i] != 0.f) atomicAdd(db + i, s_db[i]);
+  }
+}
+
+// zero the first *n_dev rows of a row-major matrix (row_bytes multiple of 16)
+__global__ void __launch_bounds__(256) zero_rows_kernel(uint4* __restrict__ p, const int64_t* __restrict__ n_dev,
+                                                        int64_t n_cap, int64_t vec_per_row) {
+  const int64_t total = min(*n_dev, n_cap) * vec_per_row;
+  const uint4 z = make_uint4(0, 0, 0, 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) p[i] = z;
 }
 
 // column sums of a fp32 matrix (bias grad of the output layer)
@@ -309,7 +355,7 @@ static int pick_sub(int nvec) {
 // dtype: kBF16 / kF16 / kF32 for X and A
 DGLB_API int dglb200_engine_agg_concat(int dtype, int idtype, const void* X, const void* self_ids, const void* nbr,
                                        const void* cnt, const void* n_dev, int64_t n_cap, int fanout, int F, void* A,
-                                       void* stream) {
+                                       int zero_pad, void* stream) {
   DGLB_TRY
   cudaStream_t st = (cudaStream_t)stream;
   if (n_cap == 0) return 0;
@@ -324,7 +370,7 @@ DGLB_API int dglb200_engine_agg_concat(int dtype, int idtype, const void* X, con
     const int rpb = 256 / sub;
     int64_t blocks = (n_cap + rpb - 1) / rpb;
     if (blocks > 148 * 16) blocks = 148 * 16;
-#define AC(VBV) agg_concat_kernel<T, I, VBV><<<(unsigned)blocks, 256, 0, st>>>((const T*)X, (const I*)self_ids, (const I*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, F, (T*)A, sub)
+#define AC(VBV) agg_concat_kernel<T, I, VBV><<<(unsigned)blocks, 256, 0, st>>>((const T*)X, (const I*)self_ids, (const I*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, F, (T*)A, sub, zero_pad)
     if (vb == 16) AC(16); else if (vb == 8) AC(8); else AC(4);
 #undef AC
   };
@@ -392,13 +438,26 @@ DGLB_API int dglb200_engine_relu_bwd(int dtype, const void* dH, const void* H, c
                                      float scale, void* dZ, void* db, void* stream) {
   DGLB_TRY
   cudaStream_t st = (cudaStream_t)stream;
-  const int rpb = 32;
+  DGLB_CHECK(N % 8 == 0 && 256 % (N / 8) == 0 && N <= 2048, "relu_bwd: N must be a multiple of 8 dividing 2048");
+  const int rpb = 64;
   const unsigned blocks = (unsigned)((n_cap + rpb - 1) / rpb);
   if (blocks == 0) return 0;
-  if (dtype == kBF16) relu_bwd_kernel<__nv_bfloat16><<<blocks, 256, 0, st>>>((const float*)dH, (const __nv_bfloat16*)H, (const int64_t*)n_dev, n_cap, N, scale, (__nv_bfloat16*)dZ, (float*)db, rpb);
-  else if (dtype == kF16) relu_bwd_kernel<__half><<<blocks, 256, 0, st>>>((const float*)dH, (const __half*)H, (const int64_t*)n_dev, n_cap, N, scale, (__half*)dZ, (float*)db, rpb);
-  else if (dtype == kF32) relu_bwd_kernel<float><<<blocks, 256, 0, st>>>((const float*)dH, (const float*)H, (const int64_t*)n_dev, n_cap, N, scale, (float*)dZ, (float*)db, rpb);
+  const size_t smem = (size_t)N * sizeof(float);
+  if (dtype == kBF16) relu_bwd_kernel<__nv_bfloat16><<<blocks, 256, smem, st>>>((const float*)dH, (const __nv_bfloat16*)H, (const int64_t*)n_dev, n_cap, N, scale, (__nv_bfloat16*)dZ, (float*)db, rpb);
+  else if (dtype == kF16) relu_bwd_kernel<__half><<<blocks, 256, smem, st>>>((const float*)dH, (const __half*)H, (const int64_t*)n_dev, n_cap, N, scale, (__half*)dZ, (float*)db, rpb);
+  else if (dtype == kF32) relu_bwd_kernel<float><<<blocks, 256, smem, st>>>((const float*)dH, (const float*)H, (const int64_t*)n_dev, n_cap, N, scale, (float*)dZ, (float*)db, rpb);
   else throw std::runtime_error("unsupported dtype");
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}
+
+DGLB_API int dglb200_engine_zero_rows(void* p, const void* n_dev, int64_t n_cap, int64_t row_bytes, void* stream) {
+  DGLB_TRY
+  DGLB_CHECK(row_bytes % 16 == 0, "row bytes must be a multiple of 16");
+  int64_t blocks = (n_cap * (row_bytes / 16) + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  zero_rows_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((uint4*)p, (const int64_t*)n_dev, n_cap, row_bytes / 16);
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH
 }

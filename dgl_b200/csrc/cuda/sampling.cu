@@ -20,10 +20,11 @@ __global__ void __launch_bounds__(128) sample_ell_kernel(const I* __restrict__ i
                                                          const I* __restrict__ seeds, int64_t n_cap,
                                                          const int64_t* __restrict__ n_dev, int fanout, uint64_t seed,
                                                          const int64_t* __restrict__ seed_dev, I* __restrict__ out_nbr, I* __restrict__ out_eid,
-                                                         int32_t* __restrict__ out_cnt, int64_t* __restrict__ out_total) {
-  const int64_t n = n_dev ? *n_dev : n_cap;
+                                                         int32_t* __restrict__ out_cnt, int64_t* __restrict__ out_total,
+                                                         int pad_rows) {
+  const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = i < n_cap;
+  const bool active = pad_rows ? (i < n_cap) : (i < n);
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0xD6E8FEB86659FD93ull;  // per-step stream under graph replay
   I* nb = out_nbr + i * fanout;
   I* ne = out_eid ? out_eid + i * fanout : nullptr;
@@ -193,7 +194,8 @@ static const void* dev_alias(const void* p, int uva) {
 
 DGLB_API int dglb200_cuda_sample_ell(int idtype, const void* indptr, const void* indices, int uva, const void* seeds,
                                      int64_t n_cap, const void* n_dev, int fanout, int64_t seed, const void* seed_dev,
-                                     void* out_nbr, void* out_eid, void* out_cnt, void* out_total, void* stream) {
+                                     void* out_nbr, void* out_eid, void* out_cnt, void* out_total, int pad_rows,
+                                     void* stream) {
   DGLB_TRY
   DGLB_CHECK(fanout > 0 && fanout <= kMaxFloyd, "sample_ell supports 1 <= fanout <= 64");
   if (n_cap == 0) return 0;
@@ -202,7 +204,7 @@ DGLB_API int dglb200_cuda_sample_ell(int idtype, const void* indptr, const void*
   DGLB_ID_SWITCH(idtype, I, {
     sample_ell_kernel<I><<<(unsigned)((n_cap + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
         (const I*)ip, (const I*)ix, (const I*)seeds, n_cap, (const int64_t*)n_dev, fanout, (uint64_t)seed,
-        (const int64_t*)seed_dev, (I*)out_nbr, (I*)out_eid, (int32_t*)out_cnt, (int64_t*)out_total);
+        (const int64_t*)seed_dev, (I*)out_nbr, (I*)out_eid, (int32_t*)out_cnt, (int64_t*)out_total, pad_rows);
   });
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH

@@ -169,16 +169,24 @@ __global__ void __launch_bounds__(256) ht_assign_kernel(const I* __restrict__ fi
                                                         const int32_t* __restrict__ flag,
                                                         const int32_t* __restrict__ pos, int32_t* __restrict__ local,
                                                         I* __restrict__ out_unique, int64_t* __restrict__ out_count,
-                                                        int64_t n_alloc) {
+                                                        int64_t n_alloc, int64_t out_cap, int32_t* __restrict__ overflow) {
   const int64_t n = nfirst + (n_dev ? *n_dev : n_cap);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     if (flag[i]) {
       const I id = i < nfirst ? first[i] : ids[i - nfirst];
-      out_unique[pos[i]] = id;
-      local[slot[i]] = pos[i];
+      if (pos[i] < out_cap) {
+        out_unique[pos[i]] = id;
+        local[slot[i]] = pos[i];
+      } else {
+        local[slot[i]] = -1;  // dropped: output capacity exceeded (flagged below)
+      }
     }
   }
-  if (blockIdx.x == 0 && threadIdx.x == 0) *out_count = n_alloc > 0 ? (int64_t)pos[n_alloc - 1] + flag[n_alloc - 1] : 0;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const int64_t total = n_alloc > 0 ? (int64_t)pos[n_alloc - 1] + flag[n_alloc - 1] : 0;
+    *out_count = total < out_cap ? total : out_cap;
+    if (total > out_cap && overflow) atomicExch(overflow, 1);
+  }
 }
 
 template <typename I>
@@ -285,7 +293,8 @@ DGLB_API int64_t dglb200_cuda_scan_temp_bytes(int64_t n) {
 DGLB_API int dglb200_cuda_unique_compact(int idtype, const void* first, int64_t nfirst, const void* ids, int64_t n,
                                          const void* n_dev, void* keys, void* minpos, void* local, int64_t cap,
                                          void* slot, void* flag, void* pos, void* scan_temp, int64_t scan_bytes,
-                                         void* out_unique, void* out_local, void* out_count, void* stream) {
+                                         void* out_unique, void* out_local, void* out_count, int64_t out_cap,
+                                         void* overflow, void* stream) {
   DGLB_TRY
   cudaStream_t st = (cudaStream_t)stream;
   const int64_t N = nfirst + n;
@@ -300,7 +309,7 @@ DGLB_API int dglb200_cuda_unique_compact(int idtype, const void* first, int64_t 
     const size_t isz = idtype == kI32 ? 4 : 8;
     DGLB_CUDA_CHECK(cudaMemsetAsync(keys, 0xFF, (size_t)cap * isz, st));
     DGLB_CUDA_CHECK(cudaMemsetAsync(minpos, 0x7F, (size_t)cap * 4, st));
-    DGLB_CUDA_CHECK(cudaMemsetAsync(out_unique, 0xFF, (size_t)N * isz, st));
+    DGLB_CUDA_CHECK(cudaMemsetAsync(out_unique, 0xFF, (size_t)(out_cap > 0 && out_cap < N ? out_cap : N) * isz, st));
   }
   DGLB_ID_SWITCH(idtype, I, {
     ht_insert_kernel<I><<<grid_for(N), 256, 0, st>>>((const I*)first, nfirst, (const I*)ids, n, (const int64_t*)n_dev,
@@ -311,7 +320,8 @@ DGLB_API int dglb200_cuda_unique_compact(int idtype, const void* first, int64_t 
     DGLB_CUDA_CHECK(cub::DeviceScan::ExclusiveSum(scan_temp, tb, (const int32_t*)flag, (int32_t*)pos, (int)N, st));
     ht_assign_kernel<I><<<grid_for(N), 256, 0, st>>>((const I*)first, nfirst, (const I*)ids, n, (const int64_t*)n_dev,
                                                      (const int32_t*)slot, (const int32_t*)flag, (const int32_t*)pos,
-                                                     (int32_t*)local, (I*)out_unique, (int64_t*)out_count, N);
+                                                     (int32_t*)local, (I*)out_unique, (int64_t*)out_count, N,
+                                                     out_cap > 0 ? out_cap : N, (int32_t*)overflow);
     if (n > 0)
       ht_lookup_kernel<I><<<grid_for(n), 256, 0, st>>>(nfirst, n, (const int64_t*)n_dev, (const int32_t*)slot,
                                                        (const int32_t*)local, (I*)out_local);

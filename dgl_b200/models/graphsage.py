@@ -78,7 +78,7 @@ class FusedSAGETrainer:
 
     def __init__(self, graph, feat, labels, num_classes, hidden=256, fanouts=(10, 10, 10), batch_size=1024, lr=1e-3,
                  weight_decay=5e-4, dropout=0.5, dtype=torch.bfloat16, seed=0, comm=None, use_cuda_graph=True,
-                 betas=(0.9, 0.999), eps=1e-8):
+                 betas=(0.9, 0.999), eps=1e-8, calibrate=True, cap_margin=1.5):
         if not feat.is_cuda:
             raise DGLError("FusedSAGETrainer needs CUDA tensors (B200); use GraphSAGE + DataLoader on CPU")
         self.dev = feat.device
@@ -119,7 +119,10 @@ class FusedSAGETrainer:
         for l in range(self.L, 1, -1):
             caps[l - 1] = caps[l] * (1 + self.fanouts[l - 1])
         self.caps = caps
+        self.max_caps = list(caps)
         self._alloc_params()
+        if calibrate:
+            self._calibrate_caps(cap_margin)
         self._alloc_buffers()
         self.use_graph = use_cuda_graph
         self.graph = None
@@ -191,6 +194,47 @@ class FusedSAGETrainer:
                 self.b[l].copy_(layer.fc_self.bias)
             self.shadow.copy_(self.param)
 
+    # ------------------------------------------------------------------ capacity calibration
+    def _calibrate_caps(self, margin, trials=24):
+        """Static buffer capacities default to the worst case B*prod(1+fanout). On real graphs the number of
+        unique frontier nodes is far smaller, so we sample a few random batches (sampling + compaction only),
+        take the largest frontier seen and keep ``margin`` headroom (rounded to 128 rows). A device-side
+        overflow flag guards the bound: if a later batch exceeds it the step is flagged, capacities are
+        raised to the worst case and the graph is recaptured (see ``check_overflow``)."""
+        from ..ops.cuda_struct import cuda_unique_compact
+        from ..sampling.neighbor import sample_rel  # noqa: F401
+        L = self.L
+        gen = torch.Generator(device="cpu")
+        gen.manual_seed(self.seed + 17)
+        seen = [0] * (L + 1)
+        for _ in range(trials):
+            cur = torch.randint(0, self.N, (self.B,), generator=gen).to(self.dev, torch.int32)
+            for l in range(L, 1, -1):
+                f = self.fanouts[l - 1]
+                n = cur.shape[0]
+                nbr = torch.empty((n, f), dtype=torch.int32, device=self.dev)
+                cnt = torch.empty(n, dtype=torch.int32, device=self.dev)
+                self.lib.fn("dglb200_cuda_sample_ell", "ippiplpilpppppip")(
+                    id_code(torch.int32), _p(self.indptr), _p(self.indices), 0, _p(cur), n, 0, f, 12345 + l, 0,
+                    _p(nbr), 0, _p(cnt), 0, 1, loader.stream_ptr())
+                cur, _ = cuda_unique_compact(cur, nbr.reshape(-1))
+                seen[l - 1] = max(seen[l - 1], int(cur.shape[0]))
+        for l in range(1, L):
+            want = int(math.ceil(seen[l] * margin / 128.0)) * 128
+            self.caps[l] = max(128, min(self.max_caps[l], want))
+        self.calibrated = {"seen_max": seen[1:L], "caps": self.caps[1:L]}
+
+    def check_overflow(self):
+        """True if a step exceeded the calibrated capacities (that step dropped frontier nodes). The engine
+        then falls back to worst-case capacities and recaptures."""
+        if int(self.overflow.item()) == 0:
+            return False
+        self.overflow.zero_()
+        self.caps = list(self.max_caps)
+        self._alloc_buffers()
+        self.graph = None
+        return True
+
     # ------------------------------------------------------------------ buffers
     def _alloc_buffers(self):
         dev, L = self.dev, self.L
@@ -219,6 +263,7 @@ class FusedSAGETrainer:
             self.cnt[l] = torch.empty(cap, dtype=i32, device=dev)
             if l > 1:
                 N = cap + cap * f
+                out_cap = self.caps[l - 1]
                 hcap = 16
                 while hcap < 2 * N + 2:
                     hcap <<= 1
@@ -228,10 +273,11 @@ class FusedSAGETrainer:
                                   local=torch.empty(hcap, dtype=i32, device=dev), cap=hcap,
                                   work=torch.empty((3, N), dtype=i32, device=dev),
                                   temp=torch.empty(max(sb, 1), dtype=torch.uint8, device=dev), sb=sb)
-                self.S[l - 1] = torch.empty(N, dtype=i32, device=dev)
+                self.S[l - 1] = torch.empty(out_cap, dtype=i32, device=dev)
                 self.nbr[l] = torch.empty((cap, f), dtype=i32, device=dev)
             else:
                 self.nbr[l] = self.nbr_g[l]
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
         self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
         self.edges_total = torch.zeros(1, dtype=torch.int64, device=dev)  # running count of sampled edges
         self.correct_dev = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -239,9 +285,9 @@ class FusedSAGETrainer:
         self.A = [None] * (L + 1)
         self.dH = [None] * (L + 1)
         for l in range(1, L + 1):
-            self.A[l] = torch.empty((self.caps[l], 2 * self.in_dims[l - 1]), dtype=self.dtype, device=dev)
+            self.A[l] = torch.zeros((self.caps[l], 2 * self.in_dims[l - 1]), dtype=self.dtype, device=dev)
             if l < L:
-                self.dH[l] = torch.empty((self.caps[l], self.out_dims[l - 1]), dtype=torch.float32, device=dev)
+                self.dH[l] = torch.zeros((self.caps[l], self.out_dims[l - 1]), dtype=torch.float32, device=dev)
         self.dlogits = torch.empty((self.B, self.C), dtype=torch.float32, device=dev)
 
     def _probe_mm(self):
@@ -274,23 +320,24 @@ class FusedSAGETrainer:
         # ---------------- sampling + compaction, output layer first
         for l in range(L, 0, -1):
             cap, f = self.caps[l], self.fanouts[l - 1]
-            self._launch("dglb200_cuda_sample_ell", "ippiplpilppppp", it, _p(self.indptr), _p(self.indices), 0,
+            self._launch("dglb200_cuda_sample_ell", "ippiplpilpppppi", it, _p(self.indptr), _p(self.indices), 0,
                          _p(self.S[l]), cap, _p(self.n[l]), f, self.seed * 7919 + l, _p(self.step_dev),
-                         _p(self.nbr_g[l]), 0, _p(self.cnt[l]), _p(self.edges_total))
+                         _p(self.nbr_g[l]), 0, _p(self.cnt[l]), _p(self.edges_total), 1 if l > 1 else 0)
             if l > 1:
                 w = self.ws[l]
-                self._launch("dglb200_cuda_unique_compact", "iplplppppl" + "pppplppp", it, _p(self.S[l]), cap,
+                self._launch("dglb200_cuda_unique_compact", "iplplppppl" + "pppplppplp", it, _p(self.S[l]), cap,
                              _p(self.nbr_g[l]), cap * f, 0, _p(w["keys"]), _p(w["minpos"]), _p(w["local"]), w["cap"],
                              _p(w["work"][0]), _p(w["work"][1]), _p(w["work"][2]), _p(w["temp"]), w["sb"],
-                             _p(self.S[l - 1]), _p(self.nbr[l]), _p(self.n[l - 1]), kernels=5)
+                             _p(self.S[l - 1]), _p(self.nbr[l]), _p(self.n[l - 1]), self.caps[l - 1],
+                             _p(self.overflow), kernels=5)
                 self._launch_count += 5  # 3 memsets + 2 cub scan kernels
         # ---------------- forward
         Hs = [None] * (L + 1)
         X = self.feat
         for l in range(1, L + 1):
             cap, f, Fi = self.caps[l], self.fanouts[l - 1], self.in_dims[l - 1]
-            self._launch("dglb200_engine_agg_concat", "iippppplii" + "p", dt, it, _p(X), _p(self.S[1]) if l == 1 else 0,
-                         _p(self.nbr[l]), _p(self.cnt[l]), _p(self.n[l]), cap, f, Fi, _p(self.A[l]))
+            self._launch("dglb200_engine_agg_concat", "iippppplii" + "pi", dt, it, _p(X), _p(self.S[1]) if l == 1 else 0,
+                         _p(self.nbr[l]), _p(self.cnt[l]), _p(self.n[l]), cap, f, Fi, _p(self.A[l]), 0)
             if l < L:
                 Z = torch.mm(self.A[l], self.Wb[l - 1])
                 self._launch_count += 1
@@ -329,8 +376,7 @@ class FusedSAGETrainer:
             if l > 1:
                 self._launch_count += 1
                 dH = self.dH[l - 1]
-                dH.zero_()
-                self._launch_count += 1
+                self._launch("dglb200_engine_zero_rows", "ppll", _p(dH), _p(self.n[l - 1]), self.caps[l - 1], Fi * 4)
                 self._launch("dglb200_engine_scatter_grad", "iippppliip", dA_dt, it, _p(dA), _p(self.nbr[l]),
                              _p(self.cnt[l]), _p(self.n[l]), cap, f, Fi, _p(dH))
                 dZn = torch.empty((self.caps[l - 1], Fi), dtype=self.dtype, device=self.dev)

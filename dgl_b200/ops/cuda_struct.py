@@ -45,10 +45,10 @@ def cuda_unique_compact(first, ids, return_device_count=False):
     out_unique = torch.empty(max(N, 1), dtype=idt, device=dev)
     out_local = torch.empty(n, dtype=idt, device=dev)
     count = torch.zeros(1, dtype=torch.int64, device=dev)
-    loader.cuda_lib().fn("dglb200_cuda_unique_compact", "iplplppppl" + "pppplpppp")(
+    loader.cuda_lib().fn("dglb200_cuda_unique_compact", "iplplppppl" + "pppplppplpp")(
         id_code(idt), first.data_ptr(), nfirst, ids.data_ptr(), n, 0, keys.data_ptr(), minpos.data_ptr(),
         local.data_ptr(), cap, work[0].data_ptr(), work[1].data_ptr(), work[2].data_ptr(), temp.data_ptr(), sb,
-        out_unique.data_ptr(), out_local.data_ptr(), count.data_ptr(), loader.stream_ptr())
+        out_unique.data_ptr(), out_local.data_ptr(), count.data_ptr(), 0, 0, loader.stream_ptr())
     if return_device_count:
         return out_unique, out_local, count
     return out_unique[: int(count.item())], out_local
