@@ -1,0 +1,243 @@
+"""Relational / heterogeneous convolutions: RelGraphConv, HeteroGraphConv, HGTConv.
+Parity: /root/reference/python/dgl/nn/pytorch/conv/relgraphconv.py:13-200, hetero.py:13-260, hgtconv.py."""
+from __future__ import annotations
+
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+
+from ... import function as fn
+from ...base import DGLError
+from ...ops import edge_softmax, gather_mm, segment_mm
+from ..linear import TypedLinear
+
+
+class RelGraphConv(nn.Module):
+    r"""R-GCN layer: h_i' = sigma(sum_r sum_{j in N_r(i)} e_ji W_r h_j + W_0 h_i).
+
+    The typed message ``W_{etype} h_src`` is computed edge-parallel through TypedLinear (grouped GEMM) and
+    reduced with one copy_e-sum g-SpMM; with ``presorted=True`` edges grouped by type use segment_mm."""
+
+    def __init__(self, in_feat, out_feat, num_rels, regularizer=None, num_bases=None, bias=True, activation=None,
+                 self_loop=True, dropout=0.0, layer_norm=False):
+        super().__init__()
+        if regularizer is not None and num_bases is None:
+            num_bases = num_rels
+        self.linear_r = TypedLinear(in_feat, out_feat, num_rels, regularizer, num_bases)
+        self.bias = bias
+        self.activation = activation
+        self.self_loop = self_loop
+        self.layer_norm = layer_norm
+        if self.bias:
+            self.h_bias = nn.Parameter(torch.Tensor(out_feat))
+            nn.init.zeros_(self.h_bias)
+        if self.layer_norm:
+            self.layer_norm_weight = nn.LayerNorm(out_feat, elementwise_affine=True)
+        if self.self_loop:
+            self.loop_weight = nn.Parameter(torch.Tensor(in_feat, out_feat))
+            nn.init.xavier_uniform_(self.loop_weight, gain=nn.init.calculate_gain("relu"))
+        self.dropout = nn.Dropout(dropout)
+
+    def message(self, edges):
+        m = self.linear_r(edges.src["h"], edges.data["etype"], self.presorted)
+        if "norm" in edges.data:
+            m = m * edges.data["norm"]
+        return {"m": m}
+
+    def forward(self, g, feat, etypes, norm=None, *, presorted=False):
+        self.presorted = presorted
+        with g.local_scope():
+            g.srcdata["h"] = feat
+            if norm is not None:
+                g.edata["norm"] = norm
+            g.edata["etype"] = etypes
+            g.update_all(self.message, fn.sum("m", "h"))
+            h = g.dstdata["h"]
+            if self.layer_norm:
+                h = self.layer_norm_weight(h)
+            if self.bias:
+                h = h + self.h_bias
+            if self.self_loop:
+                h = h + feat[: g.num_dst_nodes()] @ self.loop_weight
+            if self.activation:
+                h = self.activation(h)
+            return self.dropout(h)
+
+
+class HeteroGraphConv(nn.Module):
+    r"""Run one sub-module per relation and aggregate per destination type (reference hetero.py:13-260)."""
+
+    def __init__(self, mods, aggregate="sum"):
+        super().__init__()
+        self.mod_dict = mods
+        mods = {str(k): v for k, v in mods.items()}
+        self.mods = nn.ModuleDict(mods)
+        for _, v in self.mods.items():
+            set_allow_zero_in_degree_fn = getattr(v, "set_allow_zero_in_degree", None)
+            if callable(set_allow_zero_in_degree_fn):
+                set_allow_zero_in_degree_fn(True)
+        if isinstance(aggregate, str):
+            self.agg_fn = get_aggregate_fn(aggregate)
+        else:
+            self.agg_fn = aggregate
+
+    def _get_module(self, etype):
+        mod = self.mod_dict.get(etype, None)
+        if mod is not None:
+            return mod
+        if isinstance(etype, tuple):
+            _, etype, _ = etype
+            return self.mod_dict[etype]
+        raise KeyError("Cannot find module with edge type %s" % etype)
+
+    def forward(self, g, inputs, mod_args=None, mod_kwargs=None):
+        if mod_args is None:
+            mod_args = {}
+        if mod_kwargs is None:
+            mod_kwargs = {}
+        outputs = {nty: [] for nty in g.dsttypes}
+        if isinstance(inputs, tuple) or g.is_block:
+            if isinstance(inputs, tuple):
+                src_inputs, dst_inputs = inputs
+            else:
+                src_inputs = inputs
+                dst_inputs = {k: v[: g.number_of_dst_nodes(k)] for k, v in inputs.items() if k in g.dsttypes}
+            for stype, etype, dtype in g.canonical_etypes:
+                rel_graph = g[stype, etype, dtype]
+                if stype not in src_inputs or dtype not in dst_inputs:
+                    continue
+                dstdata = self._get_module((stype, etype, dtype))(
+                    rel_graph, (src_inputs[stype], dst_inputs[dtype]), *mod_args.get(etype, ()),
+                    **mod_kwargs.get(etype, {}))
+                outputs[dtype].append(dstdata)
+        else:
+            for stype, etype, dtype in g.canonical_etypes:
+                rel_graph = g[stype, etype, dtype]
+                if stype not in inputs:
+                    continue
+                dstdata = self._get_module((stype, etype, dtype))(
+                    rel_graph, (inputs[stype], inputs[dtype]), *mod_args.get(etype, ()), **mod_kwargs.get(etype, {}))
+                outputs[dtype].append(dstdata)
+        rsts = {}
+        for nty, alist in outputs.items():
+            if len(alist) != 0:
+                rsts[nty] = self.agg_fn(alist, nty)
+        return rsts
+
+
+def _max_reduce_func(inputs, dim):
+    return torch.max(inputs, dim=dim)[0]
+
+
+def _min_reduce_func(inputs, dim):
+    return torch.min(inputs, dim=dim)[0]
+
+
+def _sum_reduce_func(inputs, dim):
+    return torch.sum(inputs, dim=dim)
+
+
+def _mean_reduce_func(inputs, dim):
+    return torch.mean(inputs, dim=dim)
+
+
+def _stack_agg_func(inputs, dsttype):
+    if len(inputs) == 0:
+        return None
+    return torch.stack(inputs, dim=1)
+
+
+def _agg_func(inputs, dsttype, fn):
+    if len(inputs) == 0:
+        return None
+    stacked = torch.stack(inputs, dim=0)
+    return fn(stacked, dim=0)
+
+
+def get_aggregate_fn(agg):
+    if agg == "sum":
+        f = _sum_reduce_func
+    elif agg == "max":
+        f = _max_reduce_func
+    elif agg == "min":
+        f = _min_reduce_func
+    elif agg == "mean":
+        f = _mean_reduce_func
+    elif agg == "stack":
+        f = None
+    else:
+        raise DGLError('Invalid cross type aggregator. Must be one of "sum", "max", "min", "mean" or "stack". '
+                       "But got %r" % agg)
+    if agg == "stack":
+        return _stack_agg_func
+    return partial(_agg_func, fn=f)
+
+
+class HGTConv(nn.Module):
+    r"""Heterogeneous graph transformer layer on a homogenised graph with ntype/etype ids (reference hgtconv.py)."""
+
+    def __init__(self, in_size, head_size, num_heads, num_ntypes, num_etypes, dropout=0.2, use_norm=False):
+        super().__init__()
+        self.in_size, self.head_size, self.num_heads = in_size, head_size, num_heads
+        self.sqrt_d = math.sqrt(head_size)
+        self.use_norm = use_norm
+        self.linear_k = TypedLinear(in_size, head_size * num_heads, num_ntypes)
+        self.linear_q = TypedLinear(in_size, head_size * num_heads, num_ntypes)
+        self.linear_v = TypedLinear(in_size, head_size * num_heads, num_ntypes)
+        self.linear_a = TypedLinear(head_size * num_heads, head_size * num_heads, num_ntypes)
+        self.relation_pri = nn.ParameterList([nn.Parameter(torch.ones(num_etypes)) for i in range(num_heads)])
+        self.relation_att = nn.ModuleList([TypedLinear(head_size, head_size, num_etypes) for i in range(num_heads)])
+        self.relation_msg = nn.ModuleList([TypedLinear(head_size, head_size, num_etypes) for i in range(num_heads)])
+        self.skip = nn.Parameter(torch.ones(num_ntypes))
+        self.drop = nn.Dropout(dropout)
+        if use_norm:
+            self.norm = nn.LayerNorm(head_size * num_heads)
+        if in_size != head_size * num_heads:
+            self.residual_w = nn.Parameter(torch.Tensor(in_size, head_size * num_heads))
+            nn.init.xavier_uniform_(self.residual_w)
+
+    def forward(self, g, x, ntype, etype, *, presorted=False):
+        self.presorted = presorted
+        if g.is_block:
+            x_src = x
+            x_dst = x[: g.num_dst_nodes()]
+            srcntype = ntype
+            dstntype = ntype[: g.num_dst_nodes()]
+        else:
+            x_src = x_dst = x
+            srcntype = dstntype = ntype
+        with g.local_scope():
+            k = self.linear_k(x_src, srcntype, presorted).view(-1, self.num_heads, self.head_size)
+            q = self.linear_q(x_dst, dstntype, presorted).view(-1, self.num_heads, self.head_size)
+            v = self.linear_v(x_src, srcntype, presorted).view(-1, self.num_heads, self.head_size)
+            g.srcdata["k"] = k
+            g.dstdata["q"] = q
+            g.srcdata["v"] = v
+            g.edata["etype"] = etype
+            g.apply_edges(self.message)
+            g.edata["m"] = g.edata["m"] * edge_softmax(g, g.edata["a"]).unsqueeze(-1)
+            g.update_all(fn.copy_e("m", "m"), fn.sum("m", "h"))
+            h = g.dstdata["h"].view(-1, self.num_heads * self.head_size)
+            h = self.drop(self.linear_a(h, dstntype, presorted))
+            alpha = torch.sigmoid(self.skip[dstntype.long()]).unsqueeze(-1)
+            if x_dst.shape != h.shape:
+                h = h * alpha + (x_dst @ self.residual_w) * (1 - alpha)
+            else:
+                h = h * alpha + x_dst * (1 - alpha)
+            if self.use_norm:
+                h = self.norm(h)
+            return h
+
+    def message(self, edges):
+        a, m = [], []
+        etype = edges.data["etype"]
+        k = torch.unbind(edges.src["k"], dim=1)
+        q = torch.unbind(edges.dst["q"], dim=1)
+        v = torch.unbind(edges.src["v"], dim=1)
+        for i in range(self.num_heads):
+            kw = self.relation_att[i](k[i], etype, self.presorted)
+            a.append((kw * q[i]).sum(-1) * self.relation_pri[i][etype.long()] / self.sqrt_d)
+            m.append(self.relation_msg[i](v[i], etype, self.presorted))
+        return {"a": torch.stack(a, dim=1), "m": torch.stack(m, dim=1)}
