@@ -1,0 +1,16 @@
+"""GraphBolt: the data-loading stack (parity: /root/reference/python/dgl/graphbolt/__init__.py + graphbolt/ C++)."""
+from .base import (CANONICAL_ETYPE_DELIMITER, ORIGINAL_EDGE_ID, CSCFormatBase, etype_str_to_tuple, etype_tuple_to_str,  # noqa: F401
+                   expand_indptr, index_select, isin, seed_type_str_to_ntypes)
+from .datapipes import CopyTo, DataLoader, FeatureFetcher, MiniBatchTransformer, SubgraphSampler  # noqa: F401
+from .impl import *  # noqa: F401,F403
+from .impl.fused_csc_sampling_graph import load_from_shared_memory  # noqa: F401
+from .itemset import DistributedItemSampler, HeteroItemSet, ItemSampler, ItemSet, ItemSetDict  # noqa: F401
+from .minibatch import MiniBatch, SampledSubgraph, SampledSubgraphImpl  # noqa: F401
+from .utils import (add_reverse_edges, compact_csc_format, exclude_seed_edges, unique_and_compact,  # noqa: F401
+                    unique_and_compact_csc_formats)
+from .impl.cooperative import rank_assignment, rank_sort  # noqa: F401
+
+
+def set_seed(seed):
+    from .. import random as _r
+    _r.seed(seed)

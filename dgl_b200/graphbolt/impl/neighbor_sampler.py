@@ -1,0 +1,64 @@
+"""GraphBolt NeighborSampler / LayerNeighborSampler datapipes (parity:
+/root/reference/python/dgl/graphbolt/impl/neighbor_sampler.py:745-1098)."""
+from __future__ import annotations
+
+import torch
+
+from ..datapipes import SubgraphSampler
+from ..minibatch import SampledSubgraphImpl
+from ..utils import unique_and_compact_csc_formats
+
+
+class NeighborSampler(SubgraphSampler):
+    """Multi-layer neighbour sampling on a FusedCSCSamplingGraph; ``fanouts[i]`` = fan-out(s) of layer i
+    (an int/tensor, or one entry per edge type)."""
+
+    def __init__(self, datapipe, graph, fanouts, replace=False, prob_name=None, deduplicate=True, overlap_fetch=False,
+                 num_gpu_cached_edges=0, gpu_cache_threshold=1, cooperative=False, asynchronous=False, layer=False,
+                 batch_dependency=1, layer_dependency=False):
+        super().__init__(datapipe)
+        self.graph = graph
+        self.fanouts = [torch.as_tensor(f).reshape(-1) for f in fanouts]
+        self.replace = replace
+        self.prob_name = prob_name
+        self.deduplicate = deduplicate
+        self.layer = layer
+        self.batch_dependency = batch_dependency
+        self.layer_dependency = layer_dependency
+        self._cnt = 0
+
+    def _sample_one(self, seeds, fanout, layer_idx):
+        if self.layer:
+            from ... import random as dgl_random
+            self_seed = getattr(self, "_base_seed", None)
+            if self_seed is None:
+                self._base_seed = self_seed = dgl_random.next_seed()
+            t = (self._cnt % self.batch_dependency) / self.batch_dependency if self.batch_dependency > 1 else 0.0
+            rs = self_seed + (self._cnt // max(self.batch_dependency, 1)) * 7919 + (0 if self.layer_dependency else layer_idx + 1)
+            return self.graph.sample_layer_neighbors(seeds, fanout, self.replace, self.prob_name, random_seed=rs,
+                                                     seed2_contribution=t)
+        return self.graph.sample_neighbors(seeds, fanout, self.replace, self.prob_name)
+
+    def sample_subgraphs(self, seeds, seeds_timestamp=None):
+        subgraphs = []
+        self._cnt += 1
+        for hop in reversed(range(len(self.fanouts))):
+            sg = self._sample_one(seeds, self.fanouts[hop], hop)
+            if self.deduplicate:
+                uniq, compacted = unique_and_compact_csc_formats(sg.sampled_csc, seeds)
+            else:
+                from ..utils import compact_csc_format
+                uniq, compacted = compact_csc_format(sg.sampled_csc, seeds)
+            subgraphs.insert(0, SampledSubgraphImpl(sampled_csc=compacted, original_column_node_ids=seeds,
+                                                    original_row_node_ids=uniq, original_edge_ids=sg.original_edge_ids))
+            seeds = uniq
+        return seeds, subgraphs
+
+
+class LayerNeighborSampler(NeighborSampler):
+    """LABOR layer-neighbour sampler (reference impl/neighbor_sampler.py:LayerNeighborSampler)."""
+
+    def __init__(self, datapipe, graph, fanouts, replace=False, prob_name=None, deduplicate=True, layer_dependency=False,
+                 batch_dependency=1, **kw):
+        super().__init__(datapipe, graph, fanouts, replace, prob_name, deduplicate, layer=True,
+                         batch_dependency=batch_dependency, layer_dependency=layer_dependency)

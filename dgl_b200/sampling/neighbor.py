@@ -24,7 +24,7 @@ def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
-def sample_rel(ug, seeds, fanout, edge_dir="in", prob=None, replace=False, seed=None):
+def sample_rel(ug, seeds, fanout, edge_dir="in", prob=None, replace=False, seed=None, return_counts=False):
     """Sample one relation. Returns (src, dst, eid) tensors on the seeds' device."""
     if edge_dir == "in":
         indptr, indices, eids = ug.csc()
@@ -48,6 +48,8 @@ def sample_rel(ug, seeds, fanout, edge_dir="in", prob=None, replace=False, seed=
             prob = prob.to(dev)
     if n == 0:
         e = torch.empty(0, dtype=idt, device=dev)
+        if return_counts:
+            return e, e.clone(), e.clone(), torch.empty(0, dtype=torch.int64, device=dev)
         return e, e.clone(), e.clone()
     counts = torch.empty(n, dtype=torch.int64, device=dev)
     if dev.type == "cuda":
@@ -78,6 +80,8 @@ def sample_rel(ug, seeds, fanout, edge_dir="in", prob=None, replace=False, seed=
     if edge_dir == "out":
         # rows were sources: native fills (neighbor, seed) => (dst, src)
         src, dst = dst, src
+    if return_counts:
+        return src, dst, eid, counts
     return src, dst, eid
 
 
