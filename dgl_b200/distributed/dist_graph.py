@@ -1,0 +1,523 @@
+"""DistGraph server/client, KVStore, DistTensor, distributed sampling, dataloaders.
+
+Parity: /root/reference/python/dgl/distributed/{dist_context.py:208 initialize, dist_graph.py:488 DistGraphServer /
+:722 DistGraph, kvstore.py (KVServer/KVClient push/pull/barrier), standalone_kvstore.py, dist_tensor.py,
+graph_services.py:737-1160 (sample_neighbors / in_subgraph with per-partition RPC + merge), dist_dataloader.py,
+nn/pytorch/sparse_emb.py DistEmbedding, optim/pytorch/sparse_optim.py}.
+Two modes: ``standalone`` (DGL_DIST_MODE=standalone: in-process server object, no sockets) and ``distributed``
+(server processes started with role env vars; clients talk over csrc/cpu/rpc.cc)."""
+from __future__ import annotations
+
+import atexit
+import os
+import threading
+
+import numpy as np
+import torch
+
+from ..base import EID, NID, DGLError
+from ..convert import graph as make_graph
+from ..sampling.neighbor import sample_rel
+from . import rpc
+from .partition import load_partition, load_partition_book
+
+SVC_META, SVC_PULL, SVC_PUSH, SVC_SAMPLE, SVC_BARRIER, SVC_INIT_DATA, SVC_INSUBGRAPH, SVC_FIND_EDGES = range(100, 108)
+
+
+# ------------------------------------------------------------------------------------------- server state
+class ServerState:
+    """Everything one server owns: local partition, partition book, KV shards."""
+
+    def __init__(self, part_config, part_id):
+        self.part_id = part_id
+        self.g, nf, ef, self.gpb, self.graph_name, self.ntypes, self.etypes = load_partition(part_config, part_id)
+        self.kv = {}
+        for k, v in nf.items():
+            self.kv["node~" + k.replace("/", "~")] = v
+        for k, v in ef.items():
+            self.kv["edge~" + k.replace("/", "~")] = v
+        self.policy = {}  # name -> ('node'|'edge', type)
+        for k in self.kv:
+            dom, typ, _ = k.split("~", 2)
+            self.policy[k] = (dom, typ)
+        self.handlers = {}
+        self.lock = threading.Lock()
+        self._barrier = {}
+        # local lookup: global node id -> local id within the partition graph (inner nodes are a prefix)
+        self.nid_start = int(self.gpb._node_map["_N"][part_id, 0])
+        self.n_inner = int(self.gpb._node_map["_N"][part_id, 1]) - self.nid_start
+        self.eid_start = int(self.gpb._edge_map[self.gpb._ekey("_E")][part_id, 0])
+        self.local_nid = self.g.ndata[NID]
+        self.local_eid = self.g.edata[EID]
+
+    def local_range(self, name):
+        dom, typ = self.policy[name]
+        return self.nid_start if dom == "node" else self.eid_start
+
+
+def _h_meta(st, payload):
+    return {"graph_name": st.graph_name, "num_nodes": st.gpb.num_nodes(), "num_edges": st.gpb.num_edges(),
+            "gpb": st.gpb.to_dict(), "num_parts": st.gpb.num_partitions(), "ntypes": st.ntypes, "etypes": st.etypes,
+            "tensors": {k: (tuple(v.shape[1:]), v.dtype) for k, v in st.kv.items()}}
+
+
+def _h_pull(st, payload):
+    name, ids = payload
+    return st.kv[name][ids - st.local_range(name)]
+
+
+def _h_push(st, payload):
+    name, ids, data = payload
+    loc = ids - st.local_range(name)
+    h = st.handlers.get(name)
+    with st.lock:
+        if h is not None:
+            h(st.kv[name], loc, data)
+        else:
+            st.kv[name][loc] = data
+    return True
+
+
+def _h_init_data(st, payload):
+    name, shape_tail, dtype, dom, typ, init = payload
+    if name not in st.kv:
+        n = st.n_inner if dom == "node" else (int(st.gpb._edge_map[st.gpb._ekey("_E")][st.part_id, 1]) - st.eid_start)
+        t = torch.zeros((n,) + tuple(shape_tail), dtype=dtype)
+        if init == "uniform":
+            t.uniform_(-1, 1)
+        st.kv[name] = t
+        st.policy[name] = (dom, typ)
+    return True
+
+
+def _h_sample(st, payload):
+    seeds, fanout, prob_name, replace, edge_dir = payload
+    loc = seeds - st.nid_start
+    prob = st.kv.get("edge~_N:_E:_N~" + prob_name) if prob_name else None
+    p_full = None
+    if prob is not None:
+        # probabilities are stored for inner edges only (prefix of the partition's edges)
+        p_full = torch.zeros(st.g.num_edges(), dtype=torch.float32)
+        p_full[: prob.shape[0]] = prob.float()
+    src, dst, eid = sample_rel(st.g._graphs[0], loc.to(st.g.idtype), fanout, edge_dir, p_full, replace)
+    return st.local_nid[src.long()], st.local_nid[dst.long()], st.local_eid[eid.long()]
+
+
+def _h_insubgraph(st, payload):
+    seeds = payload
+    loc = (seeds - st.nid_start).to(st.g.idtype)
+    src, dst, eid = st.g.in_edges(loc, form="all")
+    return st.local_nid[src.long()], st.local_nid[dst.long()], st.local_eid[eid.long()]
+
+
+def _h_barrier(st, payload):
+    return True
+
+
+for _sid, _h in ((SVC_META, _h_meta), (SVC_PULL, _h_pull), (SVC_PUSH, _h_push), (SVC_SAMPLE, _h_sample),
+                 (SVC_BARRIER, _h_barrier), (SVC_INIT_DATA, _h_init_data), (SVC_INSUBGRAPH, _h_insubgraph)):
+    rpc.register_service(_sid, _h)
+
+
+# ------------------------------------------------------------------------------------------- context
+class _Context:
+    def __init__(self):
+        self.mode = None
+        self.client = None
+        self.local_servers = None  # standalone: list[ServerState]
+        self.num_servers = 0
+        self.initialized = False
+
+
+_CTX = _Context()
+
+
+def _call(server_id, service_id, payload):
+    if _CTX.mode == "standalone":
+        return rpc._SERVICES[service_id](_CTX.local_servers[server_id], payload)
+    return _CTX.client.remote_call([(server_id, service_id, payload)])[0]
+
+
+def _call_many(reqs):
+    if _CTX.mode == "standalone":
+        return [rpc._SERVICES[s](_CTX.local_servers[sid], p) for sid, s, p in reqs]
+    return _CTX.client.remote_call(reqs)
+
+
+def initialize(ip_config=None, max_queue_size=None, net_type="socket", num_worker_threads=1, use_graphbolt=False,
+               part_config=None):
+    """Set up this process' role (reference dist_context.py:208). Env: DGL_DIST_MODE (standalone|distributed),
+    DGL_ROLE (server|client), DGL_SERVER_ID, DGL_CONF_PATH (partition json), DGL_NUM_CLIENT, DGL_IP_CONFIG."""
+    mode = os.environ.get("DGL_DIST_MODE", "standalone")
+    part_config = part_config or os.environ.get("DGL_CONF_PATH")
+    if mode == "standalone":
+        _CTX.mode = "standalone"
+        if part_config is not None:
+            import json
+            with open(part_config) as f:
+                nparts = json.load(f)["num_parts"]
+            _CTX.local_servers = [ServerState(part_config, i) for i in range(nparts)]
+            _CTX.num_servers = nparts
+        _CTX.initialized = True
+        return
+    role = os.environ.get("DGL_ROLE", "client")
+    ip_config = ip_config or os.environ.get("DGL_IP_CONFIG")
+    servers = rpc.read_ip_config(ip_config)
+    if role == "server":
+        sid = int(os.environ["DGL_SERVER_ID"])
+        assert part_config is not None, "DGL_CONF_PATH must be set for servers"
+        state = ServerState(part_config, sid)
+        ip, port = servers[sid]
+        srv = rpc.RPCServer(sid, ip, port, int(os.environ.get("DGL_NUM_CLIENT", "1")), state)
+        srv.serve_forever()
+        os._exit(0)
+    _CTX.mode = "distributed"
+    _CTX.client = rpc.RPCClient(servers)
+    _CTX.num_servers = len(servers)
+    _CTX.initialized = True
+    atexit.register(exit_client)
+
+
+def exit_client():
+    if _CTX.mode == "distributed" and _CTX.client is not None:
+        _CTX.client.shutdown()
+        _CTX.client = None
+    _CTX.initialized = False
+
+
+def is_initialized():
+    return _CTX.initialized
+
+
+# ------------------------------------------------------------------------------------------- client objects
+class DistTensor:
+    """A tensor sharded across servers by the partition book; indexing pulls / assignment pushes."""
+
+    def __init__(self, shape, dtype, name=None, init_func=None, part_policy=None, persistent=False, is_gdata=True,
+                 attach=True, _existing=False, _graph=None, _dom="node", _typ="_N"):
+        self._shape, self._dtype = tuple(shape), dtype
+        self._g = _graph
+        self._dom, self._typ = _dom, _typ
+        self._name = name if _existing else f"{_dom}~{_typ}~{name}"
+        if not _existing:
+            for sid in range(_CTX.num_servers):
+                _call(sid, SVC_INIT_DATA, (self._name, self._shape[1:], dtype, _dom, _typ,
+                                           "uniform" if init_func == "uniform" else "zeros"))
+
+    @property
+    def shape(self):
+        return self._shape
+
+    @property
+    def dtype(self):
+        return self._dtype
+
+    @property
+    def name(self):
+        return self._name
+
+    def __len__(self):
+        return self._shape[0]
+
+    def _owner(self, ids):
+        gpb = self._g.gpb
+        return gpb.nid2partid(ids) if self._dom == "node" else gpb.eid2partid(ids)
+
+    def __getitem__(self, idx):
+        idx = torch.as_tensor(idx).long().reshape(-1)
+        own = self._owner(idx)
+        out = torch.empty((idx.shape[0],) + self._shape[1:], dtype=self._dtype)
+        reqs, sel = [], []
+        for p in torch.unique(own).tolist():
+            m = torch.nonzero(own == p).squeeze(1)
+            reqs.append((p, SVC_PULL, (self._name, idx[m])))
+            sel.append(m)
+        for m, res in zip(sel, _call_many(reqs)):
+            out[m] = res
+        return out
+
+    def __setitem__(self, idx, val):
+        idx = torch.as_tensor(idx).long().reshape(-1)
+        own = self._owner(idx)
+        reqs = []
+        for p in torch.unique(own).tolist():
+            m = torch.nonzero(own == p).squeeze(1)
+            reqs.append((p, SVC_PUSH, (self._name, idx[m], val[m])))
+        _call_many(reqs)
+
+
+class _DistDataView:
+    def __init__(self, g, dom):
+        self._g, self._dom = g, dom
+
+    def _prefix(self):
+        return "node~_N~" if self._dom == "node" else "edge~_N:_E:_N~"
+
+    def keys(self):
+        pre = self._prefix()
+        return [k[len(pre):] for k in self._g._tensors if k.startswith(pre)]
+
+    def __contains__(self, k):
+        return k in self.keys()
+
+    def __getitem__(self, k):
+        name = self._prefix() + k
+        if name not in self._g._tensors:
+            raise KeyError(k)
+        tail, dtype = self._g._tensors[name]
+        n = self._g.num_nodes() if self._dom == "node" else self._g.num_edges()
+        return DistTensor((n,) + tuple(tail), dtype, name, _existing=True, _graph=self._g, _dom=self._dom,
+                          _typ="_N" if self._dom == "node" else "_N:_E:_N")
+
+    def __setitem__(self, k, val):
+        if not isinstance(val, DistTensor):
+            raise DGLError("assign a DistTensor created with the same graph")
+        self._g._tensors[val.name] = (val.shape[1:], val.dtype)
+
+
+class DistGraph:
+    """Client handle of a partitioned graph served by DistGraphServer processes (or in-process when standalone)."""
+
+    def __init__(self, graph_name=None, gpb=None, part_config=None):
+        if not _CTX.initialized:
+            initialize(part_config=part_config)
+        if _CTX.mode == "standalone" and _CTX.local_servers is None:
+            if part_config is None:
+                raise DGLError("standalone DistGraph needs part_config")
+            initialize(part_config=part_config)
+        meta = _call(0, SVC_META, None)
+        self.graph_name = meta["graph_name"]
+        from .partition import RangePartitionBook
+        self.gpb = RangePartitionBook(0, meta["num_parts"], meta["gpb"]["node_map"],
+                                      {k: v for k, v in meta["gpb"]["edge_map"].items()}, {t: i for i, t in enumerate(meta["ntypes"])},
+                                      {t: i for i, t in enumerate(meta["etypes"])})
+        self._num_nodes, self._num_edges = meta["num_nodes"], meta["num_edges"]
+        self._tensors = dict(meta["tensors"])
+        self.ntypes, self.etypes = ["_N"], ["_E"]
+        self.canonical_etypes = [("_N", "_E", "_N")]
+        self.idtype = torch.int64
+        self.device = torch.device("cpu")
+
+    def get_partition_book(self):
+        return self.gpb
+
+    def num_nodes(self, ntype=None):
+        return self._num_nodes
+
+    number_of_nodes = num_nodes
+
+    def num_edges(self, etype=None):
+        return self._num_edges
+
+    number_of_edges = num_edges
+
+    @property
+    def ndata(self):
+        return _DistDataView(self, "node")
+
+    @property
+    def edata(self):
+        return _DistDataView(self, "edge")
+
+    @property
+    def local_partition(self):
+        if _CTX.mode == "standalone":
+            return _CTX.local_servers[0].g
+        return None
+
+    def rank(self):
+        return _CTX.client.client_id if _CTX.mode == "distributed" else 0
+
+    def barrier(self):
+        _call_many([(sid, SVC_BARRIER, None) for sid in range(_CTX.num_servers)])
+
+    def sample_neighbors(self, seed_nodes, fanout, edge_dir="in", prob=None, replace=False, **kw):
+        return sample_neighbors(self, seed_nodes, fanout, edge_dir=edge_dir, prob=prob, replace=replace)
+
+    def in_subgraph(self, nodes):
+        return in_subgraph(self, nodes)
+
+    def find_edges(self, eids, etype=None):
+        raise DGLError("find_edges on DistGraph: sample with in_subgraph or keep (src,dst) with the seed edges")
+
+
+def _merge(g, results):
+    srcs = [r[0] for r in results if r[0].numel()]
+    if srcs:
+        src = torch.cat([r[0] for r in results]); dst = torch.cat([r[1] for r in results]); eid = torch.cat([r[2] for r in results])
+    else:
+        src = dst = eid = torch.empty(0, dtype=torch.int64)
+    sg = make_graph((src, dst), num_nodes=g.num_nodes())
+    sg.edata[EID] = eid
+    return sg
+
+
+def sample_neighbors(g, nodes, fanout, edge_dir="in", prob=None, replace=False):
+    """Distributed neighbour sampling: seeds are split by owner partition, each owner samples on its local
+    partition (which holds the complete in-neighbourhood of its inner nodes) and the pieces are merged
+    (reference graph_services.py:1037-1160)."""
+    nodes = torch.as_tensor(nodes).long().reshape(-1)
+    own = g.gpb.nid2partid(nodes)
+    reqs = []
+    for p in torch.unique(own).tolist():
+        reqs.append((p, SVC_SAMPLE, (nodes[own == p], int(fanout), prob, replace, edge_dir)))
+    return _merge(g, _call_many(reqs))
+
+
+def in_subgraph(g, nodes):
+    nodes = torch.as_tensor(nodes).long().reshape(-1)
+    own = g.gpb.nid2partid(nodes)
+    reqs = [(p, SVC_INSUBGRAPH, nodes[own == p]) for p in torch.unique(own).tolist()]
+    return _merge(g, _call_many(reqs))
+
+
+def node_split(nodes, partition_book=None, ntype="_N", rank=None, force_even=True, node_trainer_ids=None,
+               num_trainers=None):
+    """Split a node id set (tensor or boolean mask) across trainers; with a partition book prefer local nodes
+    (reference dist_graph.py:node_split)."""
+    import torch.distributed as dist
+    nodes = torch.as_tensor(nodes)
+    if nodes.dtype == torch.bool:
+        nodes = torch.nonzero(nodes).squeeze(1)
+    if num_trainers is None:
+        num_trainers = dist.get_world_size() if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if partition_book is not None and not force_even:
+        part = partition_book.nid2partid(nodes, ntype)
+        return nodes[part == rank % partition_book.num_partitions()]
+    per = -(-nodes.shape[0] // num_trainers)
+    return nodes[rank * per: (rank + 1) * per]
+
+
+def edge_split(edges, partition_book=None, etype="_E", rank=None, force_even=True, num_trainers=None, **kw):
+    import torch.distributed as dist
+    edges = torch.as_tensor(edges)
+    if edges.dtype == torch.bool:
+        edges = torch.nonzero(edges).squeeze(1)
+    if num_trainers is None:
+        num_trainers = dist.get_world_size() if dist.is_initialized() else 1
+    if rank is None:
+        rank = dist.get_rank() if dist.is_initialized() else 0
+    if partition_book is not None and not force_even:
+        part = partition_book.eid2partid(edges, etype)
+        return edges[part == rank % partition_book.num_partitions()]
+    per = -(-edges.shape[0] // num_trainers)
+    return edges[rank * per: (rank + 1) * per]
+
+
+class DistDataLoader:
+    """Batch ids and apply ``collate_fn`` (reference dist_dataloader.py:DistDataLoader)."""
+
+    def __init__(self, dataset, batch_size, shuffle=False, collate_fn=None, drop_last=False, queue_size=None):
+        self.dataset = torch.as_tensor(dataset)
+        self.batch_size, self.shuffle, self.collate_fn, self.drop_last = batch_size, shuffle, collate_fn, drop_last
+
+    def __len__(self):
+        n = self.dataset.shape[0]
+        return n // self.batch_size if self.drop_last else -(-n // self.batch_size)
+
+    def __iter__(self):
+        ids = self.dataset[torch.randperm(self.dataset.shape[0])] if self.shuffle else self.dataset
+        for b in range(len(self)):
+            batch = ids[b * self.batch_size: (b + 1) * self.batch_size]
+            yield self.collate_fn(batch) if self.collate_fn else batch
+
+
+class DistNodeDataLoader(DistDataLoader):
+    """Node-wise neighbour-sampling loader over a DistGraph (reference dist_dataloader.py:792)."""
+
+    def __init__(self, g, nids, graph_sampler, device=None, **kwargs):
+        self.g, self.sampler, self.device = g, graph_sampler, device
+
+        def collate(seeds):
+            res = self.sampler.sample(self.g, seeds)
+            return res
+
+        super().__init__(nids, kwargs.pop("batch_size", 1), kwargs.pop("shuffle", False), collate, kwargs.pop("drop_last", False))
+
+
+class DistEdgeDataLoader(DistDataLoader):
+    def __init__(self, g, eids, graph_sampler, device=None, **kwargs):
+        self.g, self.sampler = g, graph_sampler
+        super().__init__(eids, kwargs.pop("batch_size", 1), kwargs.pop("shuffle", False),
+                         lambda e: self.sampler.sample(self.g, e), kwargs.pop("drop_last", False))
+
+
+class DistEmbedding:
+    """Sparse embedding stored in the KVStore; gradients are pushed to the owners by the sparse optimizers
+    (reference distributed/nn/pytorch/sparse_emb.py)."""
+
+    def __init__(self, num_embeddings, embedding_dim, name=None, init_func=None, part_policy=None, _graph=None):
+        self._name = name or "emb"
+        self._tensor = DistTensor((num_embeddings, embedding_dim), torch.float32, self._name,
+                                  init_func="uniform" if init_func is not None else None, _graph=_graph)
+        self._trace = []
+        self.num_embeddings, self.embedding_dim = num_embeddings, embedding_dim
+
+    def __call__(self, idx, device=torch.device("cpu")):
+        idx = torch.as_tensor(idx).long()
+        emb = self._tensor[idx].to(device)
+        if torch.is_grad_enabled():
+            emb.requires_grad_(True)
+            emb.retain_grad()
+            self._trace.append((idx, emb))
+        return emb
+
+    def reset_trace(self):
+        self._trace = []
+
+    @property
+    def weight(self):
+        return self._tensor
+
+
+class DistSparseGradOptimizer:
+    def __init__(self, params, lr):
+        self._params, self._lr = params, lr
+        self._state = {}
+
+    def zero_grad(self):
+        for p in self._params:
+            p.reset_trace()
+
+    def step(self):
+        with torch.no_grad():
+            for emb in self._params:
+                idx = [i for i, e in emb._trace if e.grad is not None]
+                if not idx:
+                    continue
+                idx = torch.cat(idx)
+                grad = torch.cat([e.grad for _, e in emb._trace if e.grad is not None]).cpu()
+                uniq, inv = torch.unique(idx, return_inverse=True)
+                g = torch.zeros((uniq.shape[0], grad.shape[1])).index_add_(0, inv, grad)
+                cnt = torch.bincount(inv, minlength=uniq.shape[0]).unsqueeze(1)
+                self.update(emb, uniq, g / cnt)
+                emb.reset_trace()
+
+    def update(self, emb, idx, grad):
+        raise NotImplementedError
+
+    def save(self, path):
+        torch.save({"lr": self._lr}, path)
+
+    def load(self, path):
+        self._lr = torch.load(path)["lr"]
+
+
+class DistSparseAdagrad(DistSparseGradOptimizer):
+    def __init__(self, params, lr, eps=1e-10):
+        super().__init__(params, lr)
+        self._eps = eps
+        for emb in params:
+            self._state[emb._name] = DistTensor((emb.num_embeddings, emb.embedding_dim), torch.float32,
+                                                emb._name + "_sum", _graph=emb._tensor._g)
+
+    def update(self, emb, idx, grad):
+        st = self._state[emb._name]
+        s = st[idx] + grad * grad
+        st[idx] = s
+        emb._tensor[idx] = emb._tensor[idx] - self._lr * grad / (s.sqrt() + self._eps)
+
+
+SparseAdagrad = DistSparseAdagrad

@@ -1,0 +1,227 @@
+"""Graph partitioning for distributed training: partition artifacts + partition book.
+
+Parity: /root/reference/python/dgl/distributed/partition.py (partition_graph :817-1400, load_partition :286,
+load_partition_book, inner_node/inner_edge masks :37-45) and graph_partition_book.py (RangePartitionBook).
+Artifacts: ``<out>/<name>.json`` + ``<out>/part<i>/{graph.pt,node_feat.pt,edge_feat.pt}``. Node (and edge) ids are
+reshuffled so every partition owns one contiguous global-id range per type; ``orig_id`` keeps the mapping."""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from ..base import EID, NID, DGLError
+from ..convert import graph as make_graph
+from ..partition import metis_partition_assignment
+
+RESERVED_FIELD_DTYPE = {"inner_node": torch.uint8, "inner_edge": torch.uint8}
+
+
+class RangePartitionBook:
+    """Global id -> (partition, local id) for range-partitioned node / edge id spaces."""
+
+    def __init__(self, part_id, num_parts, node_map, edge_map, ntypes, etypes):
+        self._partid = part_id
+        self._num_partitions = num_parts
+        self._ntypes = dict(ntypes)
+        self._etypes = dict(etypes)
+        # maps: type -> [num_parts, 2] ranges
+        self._node_map = {k: torch.as_tensor(v).long() for k, v in node_map.items()}
+        self._edge_map = {k: torch.as_tensor(v).long() for k, v in edge_map.items()}
+
+    @property
+    def partid(self):
+        return self._partid
+
+    def num_partitions(self):
+        return self._num_partitions
+
+    @property
+    def ntypes(self):
+        return list(self._ntypes.keys())
+
+    @property
+    def etypes(self):
+        return list(self._etypes.keys())
+
+    canonical_etypes = etypes
+
+    def _num(self, m):
+        return int((m[:, 1] - m[:, 0]).sum())
+
+    def num_nodes(self, ntype="_N"):
+        return self._num(self._node_map[ntype])
+
+    def num_edges(self, etype="_E"):
+        return self._num(self._edge_map[self._ekey(etype)])
+
+    def _ekey(self, etype):
+        if etype in self._edge_map:
+            return etype
+        for k in self._edge_map:
+            if isinstance(k, tuple) and k[1] == etype or (isinstance(k, str) and k.split(":")[1:2] == [etype]):
+                return k
+        raise DGLError(f"unknown edge type {etype}")
+
+    def metadata(self):
+        return [{"machine_id": i, "num_nodes": {k: int(v[i, 1] - v[i, 0]) for k, v in self._node_map.items()},
+                 "num_edges": {str(k): int(v[i, 1] - v[i, 0]) for k, v in self._edge_map.items()}}
+                for i in range(self._num_partitions)]
+
+    def nid2partid(self, nids, ntype="_N"):
+        ends = self._node_map[ntype][:, 1].contiguous()
+        return torch.searchsorted(ends.to(nids.device), nids.long(), right=True)
+
+    def eid2partid(self, eids, etype="_E"):
+        ends = self._edge_map[self._ekey(etype)][:, 1].contiguous()
+        return torch.searchsorted(ends.to(eids.device), eids.long(), right=True)
+
+    def partid2nids(self, partid, ntype="_N"):
+        lo, hi = self._node_map[ntype][partid].tolist()
+        return torch.arange(lo, hi)
+
+    def partid2eids(self, partid, etype="_E"):
+        lo, hi = self._edge_map[self._ekey(etype)][partid].tolist()
+        return torch.arange(lo, hi)
+
+    def nid2localnid(self, nids, partid, ntype="_N"):
+        return nids - int(self._node_map[ntype][partid, 0])
+
+    def eid2localeid(self, eids, partid, etype="_E"):
+        return eids - int(self._edge_map[self._ekey(etype)][partid, 0])
+
+    def to_dict(self):
+        return {"node_map": {k: v.tolist() for k, v in self._node_map.items()},
+                "edge_map": {str(k): v.tolist() for k, v in self._edge_map.items()}}
+
+
+GraphPartitionBook = RangePartitionBook
+
+
+def partition_graph(g, graph_name, num_parts, out_path, num_hops=1, part_method="metis", balance_ntypes=None,
+                    balance_edges=False, return_mapping=False, num_trainers_per_machine=1, objtype="cut",
+                    graph_formats=None, use_graphbolt=False, **kwargs):
+    """Partition a homogeneous graph into ``num_parts`` parts with ``num_hops`` of halo nodes and save the artifacts."""
+    if not g.is_homogeneous:
+        raise DGLError("partition_graph currently supports homogeneous graphs (use dgl.to_homogeneous first)")
+    g = g.cpu() if g.device.type != "cpu" else g
+    n = g.num_nodes()
+    if num_parts == 1:
+        node_part = torch.zeros(n, dtype=torch.int64)
+    elif part_method == "metis":
+        node_part = metis_partition_assignment(g, num_parts, balance_ntypes=balance_ntypes, balance_edges=balance_edges)
+    elif part_method == "random":
+        node_part = torch.randint(0, num_parts, (n,))
+    else:
+        raise DGLError("Unknown partitioning method: " + part_method)
+    # reshuffle nodes: contiguous ranges per partition
+    order = torch.sort(node_part, stable=True)[1]
+    new_nid = torch.empty_like(order)
+    new_nid[order] = torch.arange(n)
+    counts = torch.bincount(node_part, minlength=num_parts)
+    nstart = torch.cumsum(counts, 0) - counts
+    u, v = g.all_edges()
+    nu, nv = new_nid[u.long()], new_nid[v.long()]
+    # an edge belongs to the partition owning its destination; reshuffle edge ids likewise
+    epart = node_part[v.long()]
+    eorder = torch.sort(epart, stable=True)[1]
+    new_eid = torch.empty_like(eorder)
+    new_eid[eorder] = torch.arange(eorder.shape[0])
+    ecounts = torch.bincount(epart, minlength=num_parts)
+    estart = torch.cumsum(ecounts, 0) - ecounts
+    os.makedirs(out_path, exist_ok=True)
+    node_map = {"_N": [[int(nstart[i]), int(nstart[i] + counts[i])] for i in range(num_parts)]}
+    edge_map = {"_N:_E:_N": [[int(estart[i]), int(estart[i] + ecounts[i])] for i in range(num_parts)]}
+    meta = {"graph_name": graph_name, "num_nodes": n, "num_edges": g.num_edges(), "part_method": part_method,
+            "num_parts": num_parts, "halo_hops": num_hops, "node_map": node_map, "edge_map": edge_map,
+            "ntypes": {"_N": 0}, "etypes": {"_N:_E:_N": 0}}
+    part_of_new = node_part[order]  # partition of every new node id (sorted => monotone)
+    # adjacency in new ids for halo expansion
+    gn = make_graph((nu, nv), num_nodes=n)
+    for p in range(num_parts):
+        inner = torch.arange(int(nstart[p]), int(nstart[p] + counts[p]))
+        seen = torch.zeros(n, dtype=torch.bool)
+        seen[inner] = True
+        frontier, halo = inner, []
+        for _ in range(num_hops):
+            src, _ = gn.in_edges(frontier)
+            new = torch.unique(src)
+            new = new[~seen[new]]
+            seen[new] = True
+            halo.append(new)
+            frontier = new
+            if new.numel() == 0:
+                break
+        nodes = torch.cat([inner] + halo)  # inner nodes first => local ids of inner nodes = global - start
+        local = torch.full((n,), -1, dtype=torch.int64)
+        local[nodes] = torch.arange(nodes.shape[0])
+        # edges whose dst is inner (complete in-neighbourhood of inner nodes) + edges among halo nodes into halo
+        keep = seen[nu] & seen[nv]
+        inner_e = keep & (part_of_new[nv] == p)
+        ke = torch.nonzero(keep).squeeze(1)
+        # put inner edges first, ordered by new edge id
+        is_inner = inner_e[ke]
+        key = (~is_inner).long() * (int(new_eid.max()) + 1 if new_eid.numel() else 1) + new_eid[ke]
+        ke = ke[torch.argsort(key)]
+        pg = make_graph((local[nu[ke]], local[nv[ke]]), num_nodes=nodes.shape[0])
+        pg.ndata[NID] = nodes
+        pg.ndata["inner_node"] = (part_of_new[nodes] == p).to(torch.uint8)
+        pg.ndata["part_id"] = part_of_new[nodes]
+        pg.ndata["orig_id"] = order[nodes]
+        pg.edata[EID] = new_eid[ke]
+        pg.edata["inner_edge"] = inner_e[ke].to(torch.uint8)
+        pg.edata["orig_id"] = ke
+        pdir = os.path.join(out_path, f"part{p}")
+        os.makedirs(pdir, exist_ok=True)
+        torch.save({"src": pg.edges()[0], "dst": pg.edges()[1], "num_nodes": pg.num_nodes(),
+                    "ndata": {k: pg.ndata[k] for k in (NID, "inner_node", "part_id", "orig_id")},
+                    "edata": {k: pg.edata[k] for k in (EID, "inner_edge", "orig_id")}}, os.path.join(pdir, "graph.pt"))
+        inner_orig = order[inner]
+        torch.save({f"_N/{k}": val[inner_orig] for k, val in g.ndata.items()}, os.path.join(pdir, "node_feat.pt"))
+        inner_eorig = eorder[int(estart[p]): int(estart[p] + ecounts[p])]
+        torch.save({f"_N:_E:_N/{k}": val[inner_eorig] for k, val in g.edata.items()}, os.path.join(pdir, "edge_feat.pt"))
+        meta[f"part-{p}"] = {"node_feats": f"part{p}/node_feat.pt", "edge_feats": f"part{p}/edge_feat.pt",
+                             "part_graph": f"part{p}/graph.pt"}
+    cfg = os.path.join(out_path, f"{graph_name}.json")
+    with open(cfg, "w") as f:
+        json.dump(meta, f, indent=2)
+    if return_mapping:
+        return order, eorder
+    return None
+
+
+def load_partition_book(part_config, part_id):
+    with open(part_config) as f:
+        meta = json.load(f)
+    gpb = RangePartitionBook(part_id, meta["num_parts"], meta["node_map"], meta["edge_map"], meta["ntypes"], meta["etypes"])
+    return gpb, meta["graph_name"], list(meta["ntypes"].keys()), list(meta["etypes"].keys())
+
+
+def load_partition(part_config, part_id, load_feats=True, use_graphbolt=False):
+    """Returns (graph, node_feats, edge_feats, gpb, graph_name, ntypes, etypes)."""
+    with open(part_config) as f:
+        meta = json.load(f)
+    base = os.path.dirname(part_config)
+    info = meta[f"part-{part_id}"]
+    d = torch.load(os.path.join(base, info["part_graph"]), weights_only=False)
+    g = make_graph((d["src"], d["dst"]), num_nodes=d["num_nodes"])
+    for k, v in d["ndata"].items():
+        g.ndata[k] = v
+    for k, v in d["edata"].items():
+        g.edata[k] = v
+    nf = torch.load(os.path.join(base, info["node_feats"]), weights_only=False) if load_feats else {}
+    ef = torch.load(os.path.join(base, info["edge_feats"]), weights_only=False) if load_feats else {}
+    gpb, name, ntypes, etypes = load_partition_book(part_config, part_id)
+    return g, nf, ef, gpb, name, ntypes, etypes
+
+
+def load_partition_feats(part_config, part_id, load_nodes=True, load_edges=True):
+    with open(part_config) as f:
+        meta = json.load(f)
+    base = os.path.dirname(part_config)
+    info = meta[f"part-{part_id}"]
+    nf = torch.load(os.path.join(base, info["node_feats"]), weights_only=False) if load_nodes else None
+    ef = torch.load(os.path.join(base, info["edge_feats"]), weights_only=False) if load_edges else None
+    return nf, ef

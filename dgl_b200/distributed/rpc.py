@@ -1,0 +1,172 @@
+"""Python RPC layer over the native TCP endpoint (csrc/cpu/rpc.cc).
+
+Parity: /root/reference/python/dgl/distributed/rpc.py (Request/Response :396-560, send/recv/remote_call :641-1045),
+rpc_server.py, rpc_client.py (connection retry bounded by DGL_DIST_MAX_TRY_TIMES). Messages are pickled
+(service_id, seq, payload); a server thread pool is not needed because handlers are short and tensors are moved
+zero-copy inside the pickle stream."""
+from __future__ import annotations
+
+import ctypes
+import os
+import pickle
+import socket
+import threading
+
+from .._native import loader
+from ..base import DGLError
+
+TAG_REQUEST, TAG_RESPONSE, TAG_HELLO, TAG_SHUTDOWN = 1, 2, 3, 4
+_SERVICES = {}
+
+
+def register_service(service_id, handler):
+    """handler(server_state, payload) -> response payload (or None for one-way messages)."""
+    _SERVICES[service_id] = handler
+
+
+class DistConnectError(DGLError):
+    pass
+
+
+class Endpoint:
+    def __init__(self, rank, ip="127.0.0.1", port=0):
+        self.lib = loader.cpu_lib()
+        h, p = ctypes.c_int64(), ctypes.c_int32()
+        self.lib.fn("dglb200_rpc_create", "isipp")(int(rank), ip.encode(), int(port), ctypes.addressof(h), ctypes.addressof(p))
+        self.h, self.rank, self.ip, self.port = h.value, rank, ip, p.value
+        self._closed = False
+
+    def connect(self, peer, ip, port, max_try=None, retry_ms=200):
+        if max_try is None:
+            max_try = int(os.environ.get("DGL_DIST_MAX_TRY_TIMES", "1024"))
+        try:
+            self.lib.fn("dglb200_rpc_connect", "lisiii")(self.h, int(peer), ip.encode(), int(port), int(max_try), int(retry_ms))
+        except Exception as e:  # noqa: BLE001
+            raise DistConnectError(str(e))
+
+    def send(self, peer, tag, obj):
+        data = pickle.dumps(obj, protocol=pickle.HIGHEST_PROTOCOL)
+        buf = ctypes.create_string_buffer(data, len(data))
+        self.lib.fn("dglb200_rpc_send", "liipl")(self.h, int(peer), int(tag), ctypes.addressof(buf), len(data))
+
+    def recv(self, timeout_ms=60000):
+        """Returns (src, tag, obj) or None on timeout."""
+        src, tag, size = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+        self.lib.fn("dglb200_rpc_recv_peek", "lippp")(self.h, int(timeout_ms), ctypes.addressof(src), ctypes.addressof(tag),
+                                                     ctypes.addressof(size))
+        if size.value < 0:
+            return None
+        buf = ctypes.create_string_buffer(max(size.value, 1))
+        self.lib.fn("dglb200_rpc_recv_take", "p")(ctypes.addressof(buf))
+        return src.value, tag.value, pickle.loads(buf.raw[: size.value])
+
+    def close(self):
+        if not self._closed:
+            self._closed = True
+            self.lib.fn("dglb200_rpc_destroy", "l")(self.h)
+
+
+def read_ip_config(path):
+    """Lines of ``ip [port]`` -> list of (ip, port)."""
+    out = []
+    with open(path) as f:
+        for line in f:
+            parts = line.split()
+            if not parts:
+                continue
+            out.append((parts[0], int(parts[1]) if len(parts) > 1 else 30050))
+    return out
+
+
+class RPCServer:
+    """Serve registered services until every client said goodbye."""
+
+    def __init__(self, server_id, ip, port, num_clients, state):
+        self.ep = Endpoint(server_id, ip, port)
+        self.state = state
+        self.num_clients = num_clients
+        self.server_id = server_id
+        self._clients = {}
+        self._bye = 0
+
+    def serve_forever(self):
+        while True:
+            msg = self.ep.recv(60000)
+            if msg is None:
+                continue  # keep looping like the reference's 60 s receive timeout (rpc_server.py:127-128)
+            src, tag, obj = msg
+            if tag == TAG_HELLO:
+                cid, ip, port = obj
+                self.ep.connect(cid, ip, port, max_try=120)
+                self._clients[cid] = (ip, port)
+                self.ep.send(cid, TAG_RESPONSE, ("hello", -1, self.server_id))
+            elif tag == TAG_REQUEST:
+                service_id, seq, payload = obj
+                handler = _SERVICES.get(service_id)
+                if handler is None:
+                    self.ep.send(src, TAG_RESPONSE, (service_id, seq, DGLError(f"unknown service {service_id}")))
+                    continue
+                try:
+                    res = handler(self.state, payload)
+                except Exception as e:  # noqa: BLE001
+                    res = e
+                if seq >= 0:
+                    self.ep.send(src, TAG_RESPONSE, (service_id, seq, res))
+            elif tag == TAG_SHUTDOWN:
+                self._bye += 1
+                if self._bye >= self.num_clients:
+                    break
+        self.ep.close()
+
+
+class RPCClient:
+    def __init__(self, servers, client_id=None, ip="127.0.0.1"):
+        """servers: list of (ip, port) indexed by server id."""
+        self.num_servers = len(servers)
+        if client_id is None:
+            client_id = self.num_servers + (os.getpid() * 7919 + threading.get_ident()) % (1 << 20)
+        self.client_id = client_id
+        self.ep = Endpoint(client_id, ip, 0)
+        self._seq = 0
+        self._pending = {}
+        for sid, (sip, sport) in enumerate(servers):
+            self.ep.connect(sid, sip, sport)
+            self.ep.send(sid, TAG_HELLO, (client_id, ip, self.ep.port))
+        got = 0
+        while got < self.num_servers:
+            m = self.ep.recv(120000)
+            if m is None:
+                raise DistConnectError("timed out waiting for server hello")
+            got += 1
+
+    def send_request(self, server_id, service_id, payload, oneway=False):
+        seq = -1 if oneway else self._seq
+        if not oneway:
+            self._seq += 1
+        self.ep.send(server_id, TAG_REQUEST, (service_id, seq, payload))
+        return seq
+
+    def recv_response(self, seq, timeout_ms=600000):
+        while seq not in self._pending:
+            m = self.ep.recv(timeout_ms)
+            if m is None:
+                raise DGLError("RPC response timed out")
+            _, tag, (service_id, rseq, res) = m
+            self._pending[rseq] = res
+        res = self._pending.pop(seq)
+        if isinstance(res, Exception):
+            raise res
+        return res
+
+    def remote_call(self, requests):
+        """requests: list of (server_id, service_id, payload); returns responses in order."""
+        seqs = [self.send_request(s, sv, p) for s, sv, p in requests]
+        return [self.recv_response(q) for q in seqs]
+
+    def shutdown(self):
+        for sid in range(self.num_servers):
+            try:
+                self.ep.send(sid, TAG_SHUTDOWN, None)
+            except Exception:  # noqa: BLE001
+                pass
+        self.ep.close()

@@ -121,6 +121,8 @@ def sample_neighbors(g, nodes, fanout, edge_dir="in", prob=None, replace=False, 
     the same node-id space whose edges carry the original ids in ``edata[dgl.EID]``."""
     if edge_dir not in ("in", "out"):
         raise DGLError("edge_dir must be 'in' or 'out'")
+    if not hasattr(g, "_graphs") and hasattr(g, "gpb"):  # DistGraph: per-partition RPC sampling
+        return g.sample_neighbors(nodes, fanout, edge_dir=edge_dir, prob=prob, replace=replace)
     if g.is_block:
         raise DGLError("Sampling from a block is not supported")
     if not isinstance(nodes, dict):

