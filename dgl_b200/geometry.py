@@ -1,0 +1,61 @@
+"""Geometry ops (parity: /root/reference/python/dgl/geometry/{fps,edge_coarsening}.py, src/geometry/*):
+farthest point sampling (batched, GPU friendly) and neighbour-matching edge coarsening."""
+from __future__ import annotations
+
+import torch
+
+from .base import DGLError
+
+__all__ = ["farthest_point_sampler", "neighbor_matching"]
+
+
+def farthest_point_sampler(pos, npoints, start_idx=None):
+    """pos: [B, N, C] -> indices [B, npoints]; iterative FPS, each step one batched distance update."""
+    B, N, C = pos.shape
+    dev = pos.device
+    dist = torch.full((B, N), float("inf"), device=dev, dtype=pos.dtype)
+    if start_idx is None:
+        cur = torch.randint(0, N, (B,), device=dev)
+    else:
+        cur = torch.full((B,), int(start_idx), device=dev, dtype=torch.long)
+    out = torch.empty((B, npoints), dtype=torch.long, device=dev)
+    ar = torch.arange(B, device=dev)
+    for i in range(npoints):
+        out[:, i] = cur
+        d = ((pos - pos[ar, cur].unsqueeze(1)) ** 2).sum(-1)
+        dist = torch.minimum(dist, d)
+        cur = dist.argmax(1)
+    return out
+
+
+def neighbor_matching(graph, e_weights=None, relabel_idx=True):
+    """Greedy maximal matching used for graph coarsening (Metis/Graclus style): returns a cluster id per node."""
+    if not graph.is_homogeneous:
+        raise DGLError("The graph should be homogeneous")
+    n = graph.num_nodes()
+    u, v = graph.edges()
+    u, v = u.cpu().tolist(), v.cpu().tolist()
+    w = e_weights.cpu().tolist() if e_weights is not None else None
+    adj = [[] for _ in range(n)]
+    for i, (a, b) in enumerate(zip(u, v)):
+        if a != b:
+            adj[a].append((b, w[i] if w else 1.0))
+            adj[b].append((a, w[i] if w else 1.0))
+    match = [-1] * n
+    order = torch.randperm(n).tolist()
+    for a in order:
+        if match[a] >= 0:
+            continue
+        best, bw = -1, -1.0
+        for b, ww in adj[a]:
+            if match[b] < 0 and b != a and ww > bw:
+                best, bw = b, ww
+        if best >= 0:
+            match[a] = match[best] = min(a, best)
+        else:
+            match[a] = a
+    res = torch.tensor(match, dtype=graph.idtype, device=graph.device)
+    if relabel_idx:
+        _, res = torch.unique(res, return_inverse=True)
+        res = res.to(graph.idtype)
+    return res

@@ -1,0 +1,80 @@
+"""GraphBolt GPU path, GPU cache kernel, P2P comm kernels in single-rank mode."""
+import pytest
+import torch
+
+import dgl_b200 as dgl
+import dgl_b200.graphbolt as gb
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_graphbolt_gpu_pipeline():
+    g = dgl.rand_graph(3000, 60000)
+    fg = gb.from_dglgraph(g).to(DEV)
+    feat = torch.randn(3000, 32)
+    store = gb.TorchBasedFeatureStore({("node", None, "feat"): feat}).pin_memory_()
+    items = gb.ItemSet((torch.arange(500), torch.randint(0, 3, (500,))), names=("seeds", "labels"))
+    dp = gb.ItemSampler(items, batch_size=128, shuffle=True).copy_to(DEV).sample_neighbor(fg, [4, 4]).fetch_feature(store, ["feat"])
+    n = 0
+    for mb in gb.DataLoader(dp, num_workers=1):
+        assert mb.node_features["feat"].is_cuda
+        assert torch.equal(mb.node_features["feat"].cpu(), feat[mb.input_nodes.cpu()])
+        b = mb.blocks
+        h = dgl.nn.SAGEConv(32, 8, "mean").to(DEV)(b[0], mb.node_features["feat"])
+        assert h.shape[0] == b[0].num_dst_nodes()
+        sg = mb.sampled_subgraphs[-1]
+        src = sg.original_row_node_ids[sg.sampled_csc.indices.long()]
+        deg = sg.sampled_csc.indptr[1:] - sg.sampled_csc.indptr[:-1]
+        dst = torch.repeat_interleave(sg.original_column_node_ids, deg.long())
+        assert bool(g.has_edges_between(src.cpu(), dst.cpu()).all())
+        n += 1
+    assert n == 4
+
+
+def test_gpu_cache_kernel():
+    base = torch.arange(5000, dtype=torch.float32).unsqueeze(1).repeat(1, 16)
+    fb = gb.TorchBasedFeature(base.clone()).pin_memory_()
+    cf = gb.GPUCachedFeature(fb, 512 * 16 * 4)
+    for it in range(20):
+        k = (torch.randn(600).abs() * 300).long().clamp(max=4999).to(DEV)
+        out = cf.read(k)
+        assert torch.equal(out.cpu(), base[k.cpu()])
+    assert cf.miss_rate < 0.9
+    c = gb.GPUCache((64, 4), torch.float32)
+    keys = torch.arange(40, device=DEV)
+    c.replace(keys, torch.ones(40, 4, device=DEV) * keys.unsqueeze(1))
+    out, miss, mk = c.query(torch.tensor([3, 7, 1000], device=DEV))
+    assert miss.tolist() == [2] and out[0, 0] == 3 and out[1, 0] == 7
+
+
+def test_p2p_single_rank_kernels():
+    from dgl_b200.parallel import P2PComm
+    comm = P2PComm()
+    n, F = 2000, 64
+    shard = comm.alloc(n * F * 2)
+    x = shard.view(torch.bfloat16)[: n * F].view(n, F)
+    x.copy_(torch.randn(n, F, device=DEV))
+    g = dgl.rand_graph(n, 30000, idtype=torch.int32).to(DEV)
+    indptr, indices, _ = g._graphs[0].csc()
+    out = torch.empty(n, F, dtype=torch.bfloat16, device=DEV)
+    comm.halo_spmm(indptr, indices, shard, n, F, torch.bfloat16, out, mean=True)
+    ref = dgl.ops.copy_u_mean(g, x.float())
+    assert (out.float() - ref).abs().max() < 0.05
+    dsh = comm.alloc(n * F * 4)
+    dx = dsh.view(torch.float32)[: n * F].view(n, F)
+    dout = torch.randn(n, F, device=DEV)
+    comm.halo_spmm_backward(indptr, indices, dsh, n, F, dout, mean=False)
+    u, v = g.edges()
+    ref = torch.zeros(n, F, device=DEV).index_add_(0, u.long(), dout[v.long()])
+    assert torch.allclose(dx, ref, atol=1e-3)
+    buf = comm.alloc(1024 * 4)
+    buf.view(torch.float32)[:1024].copy_(torch.arange(1024.0))
+    res = torch.empty(1024, device=DEV)
+    comm.all_reduce(buf, res, 1024, scale=0.5)
+    assert torch.allclose(res, torch.arange(1024.0, device=DEV) * 0.5)
+    idx = torch.randint(0, n, (500,), device=DEV)
+    got = torch.empty(500, F, dtype=torch.bfloat16, device=DEV)
+    comm.gather(shard, n, idx, got)
+    assert torch.equal(got, x[idx])
+    comm.check_error()
