@@ -103,6 +103,58 @@ def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
+SPLIT_DEG = 128  # rows longer than this are split into edge-balanced work items
+
+
+def _split_meta(indptr):
+    """Per-CSC load-balancing metadata (cached on the indptr tensor): long rows and their work items."""
+    meta = getattr(indptr, "_dglb_split_meta", None)
+    if meta is None:
+        deg = (indptr[1:] - indptr[:-1]).long()
+        long_rows = torch.nonzero(deg > SPLIT_DEG).squeeze(1)
+        if long_rows.numel() == 0:
+            meta = {"n_long": 0}
+        else:
+            ldeg = deg[long_rows]
+            nchunks = (ldeg + SPLIT_DEG - 1) // SPLIT_DEG
+            ord_ = torch.repeat_interleave(torch.arange(long_rows.shape[0], device=indptr.device), nchunks)
+            first = torch.cumsum(nchunks, 0) - nchunks
+            k = torch.arange(int(nchunks.sum()), device=indptr.device) - first[ord_]
+            start = indptr[long_rows].long()[ord_] + k * SPLIT_DEG
+            length = torch.minimum(torch.full_like(k, SPLIT_DEG), ldeg[ord_] - k * SPLIT_DEG)
+            meta = {"n_long": int(long_rows.shape[0]), "long_rows": long_rows.contiguous(),
+                    "ord": ord_.to(torch.int32).contiguous(), "start": start.contiguous(),
+                    "len": length.to(torch.int32).contiguous(), "items": int(ord_.shape[0])}
+        try:
+            indptr._dglb_split_meta = meta
+        except Exception:  # noqa: BLE001
+            pass
+    return meta
+
+
+def _gspmm_balanced(csr, ufeat2d, ew, num_dst, F):
+    indptr, indices, eids = csr
+    meta = _split_meta(indptr)
+    if ew is not None and eids is not None:
+        # bring the per-edge scalars into CSC order once (sequential reads in the kernel instead of
+        # one random 32-byte sector per edge)
+        from .ops.cuda_struct import gather_rows
+        ew = gather_rows(ew, eids)
+        eids = None
+    out = torch.empty((num_dst, F), dtype=ufeat2d.dtype, device=ufeat2d.device)
+    lib = loader.cuda_lib()
+    if meta["n_long"]:
+        scratch = torch.empty((meta["n_long"], F), dtype=torch.float32, device=ufeat2d.device)
+        args = (_p(meta["ord"]), _p(meta["start"]), _p(meta["len"]), meta["items"], _p(meta["long_rows"]), meta["n_long"],
+                _p(scratch))
+    else:
+        args = (0, 0, 0, 0, 0, 0, 0)
+    lib.fn("dglb200_cuda_gspmm_balanced", "iiippplppp" + "ll" + "ppp" + "l" + "p" + "l" + "pp")(
+        1 if ew is not None else 0, dtype_code(ufeat2d.dtype), id_code(indptr.dtype), _p(indptr), _p(indices), _p(eids),
+        num_dst, _p(ufeat2d), _p(ew), _p(out), F, SPLIT_DEG, *args, loader.stream_ptr())
+    return out
+
+
 def gspmm(csr, op, reduce_op, ufeat, efeat, num_dst):
     """out[v] = reduce_{(u,e,v)} op(ufeat[u], efeat[e]).
 
@@ -116,6 +168,12 @@ def gspmm(csr, op, reduce_op, ufeat, efeat, num_dst):
     if use_l and use_r and ufeat.dtype != efeat.dtype:
         raise DGLError(f"node and edge feature dtypes differ: {ufeat.dtype} vs {efeat.dtype}")
     l2, r2, out_shape, F, _, bc = _prep_operands(op, ufeat, efeat)
+    # hot path on CUDA: copy_u / u_mul_e(scalar) with sum -> load-balanced vector kernel
+    if (ref.is_cuda and reduce_op == "sum" and num_dst > 0 and F > 0 and ref.dtype != torch.float64
+            and (F * ref.element_size()) % 4 == 0
+            and (op == "copy_lhs" or (op == "mul" and bc[3] == 1 and bc[0] == 1 and bc[1] == F))):
+        out = _gspmm_balanced(csr, l2, r2 if op == "mul" else None, num_dst, F)
+        return out.reshape(num_dst, *out_shape), None, None
     out = torch.empty((num_dst, F), dtype=ref.dtype, device=ref.device)
     arg_u = arg_e = None
     if reduce_op != "sum":

@@ -59,7 +59,8 @@ template <typename T, typename I, int VB, int NV, bool HAS_W>
 __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ indptr, const I* __restrict__ indices,
                                                        const I* __restrict__ eids, int64_t num_rows,
                                                        const T* __restrict__ x, const T* __restrict__ w,
-                                                       T* __restrict__ out, int64_t F, int nvec, int sub) {
+                                                       T* __restrict__ out, int64_t F, int nvec, int sub,
+                                                       int64_t max_deg) {
   using VO = VecOps<T, VB>;
   using V = typename VO::V;
   constexpr int VE = VO::VE;
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ ind
 #pragma unroll
     for (int i = 0; i < VE; ++i) acc[j][i] = 0.f;
   const int64_t s = indptr[row], t = indptr[row + 1];
+  if (max_deg > 0 && t - s > max_deg) return;  // long rows are handled by the edge-balanced split kernel
   const int64_t rowvecs = F / VE;  // == nvec
   int64_t p = s;
   for (; p + U <= t; p += U) {
@@ -174,7 +176,7 @@ static int pow2_ge(int64_t x, int cap) {
 
 template <typename T, typename I, int VB, bool HAS_W>
 void launch_vec(const I* indptr, const I* indices, const I* eids, int64_t n, const T* x, const T* w, T* out, int64_t F,
-                cudaStream_t st) {
+                cudaStream_t st, int64_t max_deg = 0) {
   constexpr int VE = VB / sizeof(T);
   const int nvec = (int)(F / VE);
   const int sub = pow2_ge(nvec, 32);
@@ -182,13 +184,125 @@ void launch_vec(const I* indptr, const I* indices, const I* eids, int64_t n, con
   const unsigned gx = (unsigned)((n + rows_per_block - 1) / rows_per_block);
   const int per_lane = (nvec + sub - 1) / sub;
   if (per_lane <= 1) {
-    spmm_vec_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub);
+    spmm_vec_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg);
   } else if (per_lane <= 2) {
-    spmm_vec_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub);
+    spmm_vec_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg);
   } else {
     const unsigned gy = (unsigned)((nvec + sub * 4 - 1) / (sub * 4));
-    spmm_vec_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub);
+    spmm_vec_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg);
   }
+}
+
+
+// ---- edge-balanced path for long rows --------------------------------------------------------
+// Work item = (long-row ordinal, first edge, #edges <= chunk). One sub-warp per item accumulates its
+// chunk in registers and adds the partial row into an fp32 scratch row with vector red.global.add;
+// spmm_split_finalize converts scratch -> out. Hub rows of power-law graphs are thereby spread over
+// the whole GPU instead of serialising on one warp.
+template <typename T, typename I, int VB, int NV, bool HAS_W>
+__global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ indices, const I* __restrict__ eids,
+                                                         const int32_t* __restrict__ item_ord,
+                                                         const int64_t* __restrict__ item_start,
+                                                         const int32_t* __restrict__ item_len, int64_t num_items,
+                                                         const T* __restrict__ x, const T* __restrict__ w,
+                                                         float* __restrict__ scratch, int64_t F, int nvec, int sub) {
+  using VO = VecOps<T, VB>;
+  using V = typename VO::V;
+  constexpr int VE = VO::VE;
+  constexpr int U = 4;
+  const int items_per_block = blockDim.x / sub;
+  const int64_t item = (int64_t)blockIdx.x * items_per_block + threadIdx.x / sub;
+  if (item >= num_items) return;
+  const int lane = threadIdx.x % sub;
+  const int vbase = blockIdx.y * sub * NV + lane;
+  float acc[NV][VE];
+#pragma unroll
+  for (int j = 0; j < NV; ++j)
+#pragma unroll
+    for (int i = 0; i < VE; ++i) acc[j][i] = 0.f;
+  const int64_t s = item_start[item], t = s + item_len[item];
+  int64_t p = s;
+  for (; p + U <= t; p += U) {
+    int64_t u[U];
+    float wt[U];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      u[k] = indices[p + k];
+      wt[k] = HAS_W ? to_f<T>(w[eids ? (int64_t)eids[p + k] : p + k]) : 1.f;
+    }
+    V v[U][NV];
+#pragma unroll
+    for (int k = 0; k < U; ++k) {
+      const V* xr = reinterpret_cast<const V*>(x + u[k] * F);
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (vbase + j * sub < nvec) v[k][j] = ldg_vec(xr + vbase + j * sub);
+    }
+#pragma unroll
+    for (int k = 0; k < U; ++k)
+#pragma unroll
+      for (int j = 0; j < NV; ++j)
+        if (vbase + j * sub < nvec) VO::fma(acc[j], v[k][j], wt[k]);
+  }
+  for (; p < t; ++p) {
+    const int64_t u = indices[p];
+    const float wt = HAS_W ? to_f<T>(w[eids ? (int64_t)eids[p] : p]) : 1.f;
+    const V* xr = reinterpret_cast<const V*>(x + u * F);
+#pragma unroll
+    for (int j = 0; j < NV; ++j)
+      if (vbase + j * sub < nvec) {
+        V v = ldg_vec(xr + vbase + j * sub);
+        VO::fma(acc[j], v, wt);
+      }
+  }
+  float* srow = scratch + (int64_t)item_ord[item] * F;
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    const int c = vbase + j * sub;
+    if (c < nvec) {
+#pragma unroll
+      for (int i = 0; i < VE; ++i) atomicAdd(srow + c * VE + i, acc[j][i]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) spmm_split_finalize_kernel(const float* __restrict__ scratch,
+                                                                  const int64_t* __restrict__ long_rows,
+                                                                  int64_t n_long, int64_t F, T* __restrict__ out) {
+  const int64_t total = n_long * F;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = i / F, f = i - o * F;
+    out[long_rows[o] * F + f] = from_f<T>(scratch[i]);
+  }
+}
+
+template <typename T, typename I, int VB, bool HAS_W>
+void launch_split(const I* indices, const I* eids, const int32_t* item_ord, const int64_t* item_start,
+                  const int32_t* item_len, int64_t num_items, const T* x, const T* w, float* scratch, int64_t F,
+                  cudaStream_t st) {
+  constexpr int VE = VB / sizeof(T);
+  const int nvec = (int)(F / VE);
+  const int sub = pow2_ge(nvec, 32);
+  const int ipb = 256 / sub;
+  const unsigned gx = (unsigned)((num_items + ipb - 1) / ipb);
+  const int per_lane = (nvec + sub - 1) / sub;
+  if (per_lane <= 1) {
+    spmm_split_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub);
+  } else if (per_lane <= 2) {
+    spmm_split_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub);
+  } else {
+    const unsigned gy = (unsigned)((nvec + sub * 4 - 1) / (sub * 4));
+    spmm_split_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub);
+  }
+}
+
+static int pick_vb_spmm(int64_t row_bytes, const void* x, const void* out) {
+  const uintptr_t xa = (uintptr_t)x, oa = (uintptr_t)out;
+  if (row_bytes % 16 == 0 && xa % 16 == 0 && oa % 16 == 0) return 16;
+  if (row_bytes % 8 == 0 && xa % 8 == 0 && oa % 8 == 0) return 8;
+  if (row_bytes % 4 == 0 && xa % 4 == 0 && oa % 4 == 0) return 4;
+  return 0;
 }
 
 template <typename T, typename I>
@@ -259,6 +373,48 @@ DGLB_API int dglb200_cuda_gspmm(int op, int red, int dtype, int idtype, const vo
       spmm_dispatch<T, I>(op, red, (const I*)indptr, (const I*)indices, (const I*)eids, num_rows, (const T*)ufeat,
                           (const T*)efeat, (T*)out, (I*)arg_u, (I*)arg_e, F, bc, st);
     });
+  });
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}
+
+// Load-balanced g-SpMM (copy_u / u_mul_e with per-edge scalar, sum): rows with degree <= max_deg go through the
+// row-parallel kernel, longer rows through edge-balanced work items (see spmm_split_kernel).
+DGLB_API int dglb200_cuda_gspmm_balanced(int has_w, int dtype, int idtype, const void* indptr, const void* indices,
+                                         const void* eids, int64_t num_rows, const void* x, const void* w, void* out,
+                                         int64_t F, int64_t max_deg, const void* item_ord, const void* item_start,
+                                         const void* item_len, int64_t num_items, const void* long_rows,
+                                         int64_t n_long, void* scratch, void* stream) {
+  DGLB_TRY
+  cudaStream_t st = (cudaStream_t)stream;
+  auto run = [&](auto tag, auto itag) {
+    using T = decltype(tag);
+    using I = decltype(itag);
+    const int vb = pick_vb_spmm(F * (int64_t)sizeof(T), x, out);
+    DGLB_CHECK(vb != 0, "feature rows must be 4-byte aligned for the balanced g-SpMM");
+#define RUN(VBV, HW)                                                                                              \
+    launch_vec<T, I, VBV, HW>((const I*)indptr, (const I*)indices, (const I*)eids, num_rows, (const T*)x,           \
+                              (const T*)w, (T*)out, F, st, max_deg);                                                \
+    if (num_items > 0) {                                                                                            \
+      DGLB_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)n_long * F * sizeof(float), st));                         \
+      launch_split<T, I, VBV, HW>((const I*)indices, (const I*)eids, (const int32_t*)item_ord,                      \
+                                  (const int64_t*)item_start, (const int32_t*)item_len, num_items, (const T*)x,     \
+                                  (const T*)w, (float*)scratch, F, st);                                             \
+      int64_t blocks = (n_long * F + 255) / 256;                                                                    \
+      if (blocks > 148 * 16) blocks = 148 * 16;                                                                     \
+      spmm_split_finalize_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const float*)scratch,                        \
+                                                                      (const int64_t*)long_rows, n_long, F, (T*)out); \
+    }
+    if (vb == 16) { if (has_w) { RUN(16, true) } else { RUN(16, false) } }
+    else if (vb == 8) { if (has_w) { RUN(8, true) } else { RUN(8, false) } }
+    else { if (has_w) { RUN(4, true) } else { RUN(4, false) } }
+#undef RUN
+  };
+  DGLB_ID_SWITCH(idtype, I, {
+    if (dtype == kF32) run(float(), I());
+    else if (dtype == kBF16) run(__nv_bfloat16(), I());
+    else if (dtype == kF16) run(__half(), I());
+    else throw std::runtime_error("balanced gspmm: unsupported dtype");
   });
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH

@@ -1,0 +1,35 @@
+"""Python entry points of the fused tensor-core kernels (csrc/cuda/sage_tc.cu)."""
+from __future__ import annotations
+
+import torch
+
+from .._native import loader
+from ..base import DGLError
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def sage_layer_tc(X, self_ids, nbr, cnt, n_dev, Wt, bias, relu=True, p_drop=0.0, seed=0, step_dev=None, out=None,
+                  save_A=False, A_out=None):
+    """out[d] = act([X[self(d)] | mean_k X[nbr[d,k]]] @ Wt^T + bias) for d < n_dev (tcgen05 + TMA + TMEM kernel).
+
+    X: [rows, Fp] bf16 (Fp % 64 == 0); self_ids: int32 [n_cap] or None (identity); nbr: int32 [n_cap, fanout];
+    cnt: int32 [n_cap]; n_dev: int64 [1] device tensor; Wt: [Np, 2*Fp] bf16 (K-major); bias: fp32 [Np].
+    Returns (out [n_cap, Np] bf16, A or None)."""
+    if X.dtype != torch.bfloat16 or Wt.dtype != torch.bfloat16:
+        raise DGLError("sage_layer_tc needs bf16 operands")
+    n_cap, fanout = nbr.shape
+    Fp = X.shape[1]
+    Np = Wt.shape[0]
+    if Wt.shape[1] != 2 * Fp:
+        raise DGLError("Wt must be [Np, 2*Fp]")
+    if out is None:
+        out = torch.empty((n_cap, Np), dtype=torch.bfloat16, device=X.device)
+    if save_A and A_out is None:
+        A_out = torch.zeros((n_cap, 2 * Fp), dtype=torch.bfloat16, device=X.device)
+    loader.cuda_lib().fn("dglb200_engine_sage_layer_tc", "ppppplliiipppp" + "iflpp")(
+        _p(X), _p(self_ids), _p(nbr), _p(cnt), _p(n_dev), n_cap, fanout, Fp, Np, _p(Wt), _p(bias), _p(out), _p(A_out),
+        1 if relu else 0, float(p_drop), int(seed), _p(step_dev), loader.stream_ptr())
+    return out, A_out
