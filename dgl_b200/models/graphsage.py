@@ -78,7 +78,7 @@ class FusedSAGETrainer:
 
     def __init__(self, graph, feat, labels, num_classes, hidden=256, fanouts=(10, 10, 10), batch_size=1024, lr=1e-3,
                  weight_decay=5e-4, dropout=0.5, dtype=torch.bfloat16, seed=0, comm=None, use_cuda_graph=True,
-                 betas=(0.9, 0.999), eps=1e-8, calibrate=True, cap_margin=1.5):
+                 betas=(0.9, 0.999), eps=1e-8, calibrate=True, cap_margin=1.5, use_tc=None):
         if not feat.is_cuda:
             raise DGLError("FusedSAGETrainer needs CUDA tensors (B200); use GraphSAGE + DataLoader on CPU")
         self.dev = feat.device
@@ -92,7 +92,20 @@ class FusedSAGETrainer:
         self.indices = indices.to(torch.int32).contiguous()
         self.N, self.E = N, E
         self.dtype = dtype
-        self.feat = feat.to(dtype).contiguous()
+        # tensor-core path (tcgen05 fused gather+GEMM kernel): bf16, hidden % 32 == 0, feature rows padded to a
+        # multiple of 64 elements (zero columns: mathematically identical, their weights receive zero gradient)
+        if use_tc is None:
+            use_tc = dtype == torch.bfloat16 and hidden % 32 == 0 and hidden <= 256
+        self.use_tc = bool(use_tc)
+        self.F_orig = feat.shape[1]
+        if self.use_tc and feat.shape[1] % 64:
+            Fp = (feat.shape[1] + 63) // 64 * 64
+            padded = torch.zeros((feat.shape[0], Fp), dtype=dtype, device=feat.device)
+            padded[:, : feat.shape[1]] = feat.to(dtype)
+            self.feat = padded
+        else:
+            self.feat = feat.to(dtype).contiguous()
+        feat = self.feat
         self.labels = labels.to(torch.int32).contiguous()
         self.F_in = feat.shape[1]
         self.H = hidden
@@ -160,6 +173,9 @@ class FusedSAGETrainer:
                 bound = gain * math.sqrt(6.0 / (k_in + n_out))
                 w_self = (torch.rand(n_out, k_in, generator=gen) * 2 - 1) * bound
                 w_neigh = (torch.rand(n_out, k_in, generator=gen) * 2 - 1) * bound
+                if l == 0 and self.F_orig != self.F_in:
+                    w_self[:, self.F_orig:] = 0
+                    w_neigh[:, self.F_orig:] = 0
                 view.copy_(torch.cat([w_self.t(), w_neigh.t()], 0).to(dev))
                 self.W.append(view)
                 self.Wb.append(self.shadow[o:o + n].view(*shape) if self.dtype == torch.bfloat16 else view)
@@ -169,6 +185,9 @@ class FusedSAGETrainer:
                 self.gb.append(self.grad[o:o + n].view(*shape))
         self.shadow.copy_(self.param)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        # K-major (transposed) bf16 weights for the tcgen05 kernel, refreshed from the shadow every step
+        self.Wt = [torch.zeros((self.out_dims[l], 2 * self.in_dims[l]), dtype=torch.bfloat16, device=dev)
+                   if (self.use_tc and l < self.L - 1) else None for l in range(self.L)]
 
     def state_dict(self):
         return {"param": self.param.clone(), "m": self.adam_m.clone(), "v": self.adam_v.clone(),
@@ -183,14 +202,19 @@ class FusedSAGETrainer:
         with torch.no_grad():
             for l, layer in enumerate(module.layers):
                 k = self.in_dims[l]
-                layer.fc_self.weight.copy_(self.W[l][:k].t())
-                layer.fc_neigh.weight.copy_(self.W[l][k:].t())
+                ko = self.F_orig if l == 0 else k
+                layer.fc_self.weight.copy_(self.W[l][:ko].t())
+                layer.fc_neigh.weight.copy_(self.W[l][k:k + ko].t())
                 layer.fc_self.bias.copy_(self.b[l])
 
     def import_from_module(self, module: GraphSAGE):
         with torch.no_grad():
             for l, layer in enumerate(module.layers):
-                self.W[l].copy_(torch.cat([layer.fc_self.weight.t(), layer.fc_neigh.weight.t()], 0))
+                k = self.in_dims[l]
+                ko = self.F_orig if l == 0 else k
+                self.W[l].zero_()
+                self.W[l][:ko].copy_(layer.fc_self.weight.t())
+                self.W[l][k:k + ko].copy_(layer.fc_neigh.weight.t())
                 self.b[l].copy_(layer.fc_self.bias)
             self.shadow.copy_(self.param)
 
@@ -289,6 +313,10 @@ class FusedSAGETrainer:
             if l < L:
                 self.dH[l] = torch.zeros((self.caps[l], self.out_dims[l - 1]), dtype=torch.float32, device=dev)
         self.dlogits = torch.empty((self.B, self.C), dtype=torch.float32, device=dev)
+        self.Hbuf = [None] * (L + 1)
+        if self.use_tc:
+            for l in range(1, L):
+                self.Hbuf[l] = torch.zeros((self.caps[l], self.out_dims[l - 1]), dtype=self.dtype, device=dev)
 
     def _probe_mm(self):
         """Can torch.mm emit an fp32 result from bf16 operands (keeps dW in full precision)?"""
@@ -334,8 +362,21 @@ class FusedSAGETrainer:
         # ---------------- forward
         Hs = [None] * (L + 1)
         X = self.feat
+        if self.use_tc:
+            for l in range(L - 1):
+                self.Wt[l].copy_(self.Wb[l].t())
+                self._launch_count += 1
         for l in range(1, L + 1):
             cap, f, Fi = self.caps[l], self.fanouts[l - 1], self.in_dims[l - 1]
+            if self.use_tc and l < L:
+                # gather + mean + concat + GEMM + bias + ReLU + dropout in ONE tcgen05 kernel
+                self._launch("dglb200_engine_sage_layer_tc", "ppppp" + "l" + "iii" + "pppp" + "iflp", _p(X),
+                             _p(self.S[1]) if l == 1 else 0, _p(self.nbr[l]), _p(self.cnt[l]), _p(self.n[l]), cap, f, Fi,
+                             self.out_dims[l - 1], _p(self.Wt[l - 1]), _p(self.b[l - 1]), _p(self.Hbuf[l]), _p(self.A[l]),
+                             1, float(self.p_drop), self.seed * 104729 + l, _p(self.step_dev))
+                Hs[l] = self.Hbuf[l]
+                X = self.Hbuf[l]
+                continue
             self._launch("dglb200_engine_agg_concat", "iippppplii" + "pi", dt, it, _p(X), _p(self.S[1]) if l == 1 else 0,
                          _p(self.nbr[l]), _p(self.cnt[l]), _p(self.n[l]), cap, f, Fi, _p(self.A[l]), 0)
             if l < L:

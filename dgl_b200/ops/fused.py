@@ -29,7 +29,7 @@ def sage_layer_tc(X, self_ids, nbr, cnt, n_dev, Wt, bias, relu=True, p_drop=0.0,
         out = torch.empty((n_cap, Np), dtype=torch.bfloat16, device=X.device)
     if save_A and A_out is None:
         A_out = torch.zeros((n_cap, 2 * Fp), dtype=torch.bfloat16, device=X.device)
-    loader.cuda_lib().fn("dglb200_engine_sage_layer_tc", "ppppplliiipppp" + "iflpp")(
+    loader.cuda_lib().fn("dglb200_engine_sage_layer_tc", "ppppp" + "l" + "iii" + "pppp" + "iflpp")(
         _p(X), _p(self_ids), _p(nbr), _p(cnt), _p(n_dev), n_cap, fanout, Fp, Np, _p(Wt), _p(bias), _p(out), _p(A_out),
         1 if relu else 0, float(p_drop), int(seed), _p(step_dev), loader.stream_ptr())
     return out, A_out

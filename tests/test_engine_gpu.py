@@ -10,13 +10,14 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
-def _make(n=5000, e=100000, fin=32, hid=64, C=7, B=128, fan=(5, 4, 3), dtype=torch.bfloat16, dropout=0.0, graph=False):
+def _make(n=5000, e=100000, fin=32, hid=64, C=7, B=128, fan=(5, 4, 3), dtype=torch.bfloat16, dropout=0.0, graph=False,
+          use_tc=None):
     torch.manual_seed(0)
     g = dgl.rand_graph(n, e, idtype=torch.int32).to(DEV)
     feat = torch.randn(n, fin, device=DEV)
     labels = torch.randint(0, C, (n,), device=DEV)
     tr = FusedSAGETrainer(g, feat, labels, C, hidden=hid, fanouts=fan, batch_size=B, dropout=dropout, dtype=dtype,
-                          use_cuda_graph=graph, lr=1e-2, weight_decay=0.0)
+                          use_cuda_graph=graph, lr=1e-2, weight_decay=0.0, use_tc=use_tc)
     return g, feat, labels, tr
 
 
@@ -49,9 +50,9 @@ def _reference(tr, feat, labels):
     return loss.item(), W, b, n
 
 
-@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
-def test_engine_matches_torch(dtype):
-    g, feat, labels, tr = _make(dtype=dtype)
+@pytest.mark.parametrize("dtype,use_tc", [(torch.float32, False), (torch.bfloat16, False), (torch.bfloat16, True)])
+def test_engine_matches_torch(dtype, use_tc):
+    g, feat, labels, tr = _make(dtype=dtype, use_tc=use_tc)
     seeds = torch.randperm(5000)[:128]
     p0 = tr.param.clone()
     loss = tr.train_step(seeds)
