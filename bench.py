@@ -206,7 +206,7 @@ def run_ours(args):
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     tr = FusedSAGETrainer(g, feat, labels, CLASSES, hidden=HIDDEN, fanouts=FANOUTS, batch_size=BATCH, lr=1e-3,
                           weight_decay=5e-4, dropout=0.5, dtype=dtype, seed=1234, comm=comm,
-                          use_cuda_graph=not args.no_graph)
+                          use_cuda_graph=not args.no_graph, use_tc=(False if args.no_tc else None))
     del feat
     total = args.warmup + args.steps
     batches = seed_batches(train_idx.cpu(), rank, world, 2 * total + 4, BATCH, seed=99)
@@ -388,6 +388,7 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (testing only; 1.0 = named config)")
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay (debug)")
+    ap.add_argument("--no-tc", action="store_true", help="use the unfused cuBLAS layer path (A/B debug)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device"}))

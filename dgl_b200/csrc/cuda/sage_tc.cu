@@ -2,14 +2,20 @@
 //
 //   out[d, :] = act( [ X[self(d)] | mean_k X[nbr(d,k)] ] @ W + b )          d < *n_dev  (device-side row count)
 //
-// One CTA = one 128-row output tile. The A operand is never read from global memory as a matrix: four
-// producer warps GATHER the self row and the sampled neighbour rows straight from the feature table
-// (16-byte lanes, up to 2*fanout independent loads in flight per lane), reduce the neighbour mean in fp32
-// registers and write the bf16 tile into shared memory in the canonical K-major SWIZZLE_128B UMMA layout.
-// W^T tiles arrive by TMA (cp.async.bulk.tensor, 128B swizzle) on the same mbarrier pipeline. One elected
-// thread issues tcgen05.mma (M=128, N<=256, K=16 per instruction) with the accumulator in TMEM; the producer
-// warps then become the epilogue: tcgen05.ld -> +bias -> ReLU -> dropout -> bf16 -> global.
-// The tile of A can optionally be spilled to global (A_out) for the backward dW GEMM.
+// Persistent, warp-specialised kernel: one CTA per SM walks output tiles (tile = blockIdx.x, += gridDim.x).
+//   * 16 producer warps GATHER the self row and the sampled neighbour rows straight from the feature table
+//     (16-byte lanes, up to 12 independent row loads in flight per lane, ~100 KB in flight per SM), reduce the
+//     neighbour mean in fp32 registers and write the bf16 A tile into shared memory in the canonical K-major
+//     SWIZZLE_128B UMMA layout. The A operand is never read from global memory as a matrix. The index lists of
+//     the NEXT tile are prefetched into shared memory with cp.async while the current tile is gathered.
+//   * one TMA thread streams the W^T chunks (cp.async.bulk.tensor, 128B swizzle) through the same mbarrier ring;
+//   * one elected thread issues tcgen05.mma (M=128, N<=256, K=16 per instruction) into one of TWO TMEM accumulators;
+//   * 4 epilogue warps drain the other accumulator (tcgen05.ld -> +bias -> ReLU -> dropout -> bf16 -> global) while
+//     the producers are already gathering the next tile, so neither the epilogue nor the per-tile set-up sits on the
+//     memory-bound critical path.
+// The MMA is far from the bottleneck (the layer is gather-bound), so when there are few rows a tile carries only
+// 64 live rows of the 128-row MMA tile: twice as many tiles -> all SMs pull on HBM and wave quantisation halves.
+// The A tile can optionally be spilled to global (A_out) for the backward dW GEMM.
 //
 // This fuses what the reference runs as: index_select (feature gather) + g-SpMM copy_u mean + 2 cuBLAS GEMMs +
 // bias/activation/dropout elementwise kernels (SURVEY.md 2.4 "Fusion status", sageconv.py:230-287).
@@ -21,8 +27,7 @@ namespace dglb {
 
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;  // bf16 elements per K chunk = 128 bytes = one swizzle atom row
-constexpr int kStages = 2;
-constexpr int kProducerThreads = 128;
+constexpr int kMaxStages = 4;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -113,18 +118,36 @@ __device__ __forceinline__ void acc_add(AccRow& a, const uint4& q) {
 // swizzled byte offset of (row r, 16-byte chunk c) inside a [rows x 128 B] K-major SW128 tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
 
+constexpr int kProducerWarps = 16;
+constexpr int kEpilogueWarps = 4;
+constexpr int kTmaWarp = kProducerWarps + kEpilogueWarps;
+constexpr int kMmaWarp = kTmaWarp + 1;
+constexpr int kThreads = (kMmaWarp + 1) * 32;  // 704
+constexpr int kGatherBatch = 12;               // independent 16-byte row loads in flight per producer lane
+constexpr int kRowsPerPass = kProducerWarps * 4;  // 8 lanes cover one 128-byte row slice -> 64 rows per pass
+
+__device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory"); }
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t fmix32(uint32_t x) {
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+
 template <bool RELU>
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(kThreads, 1)
 sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bfloat16* __restrict__ X,
                      const int32_t* __restrict__ self_ids, const int32_t* __restrict__ nbr,
                      const int32_t* __restrict__ cnt, const int64_t* __restrict__ n_dev, int64_t n_cap, int fanout,
                      int Fp, int Np, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                      __nv_bfloat16* __restrict__ A_out, float p_drop, uint64_t seed,
-                     const int64_t* __restrict__ step_dev) {
+                     const int64_t* __restrict__ step_dev, int kStages, int R) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int64_t n = min(*n_dev, n_cap);
-  const int64_t tile0 = (int64_t)blockIdx.x * kTileM;
-  if (tile0 >= n) return;  // device-side M: tiles past the live row count do no work at all
+  if ((int64_t)blockIdx.x * R >= n) return;  // device-side M: CTAs past the live row count do no work at all
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KH = Fp / kChunkK;  // chunks per half (self | neigh)
@@ -133,29 +156,29 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
   const uint32_t a_bytes = kTileM * 128;
   const uint32_t b_bytes = (uint32_t)Np * 128;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA[kStages];
-  uint8_t* sB[kStages];
-#pragma unroll
-  for (int s = 0; s < kStages; ++s) {
-    sA[s] = smem + s * (a_bytes + b_bytes);
-    sB[s] = sA[s] + a_bytes;
-  }
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * (a_bytes + b_bytes));
-  // bars[0..S) full, bars[S..2S) empty, bars[2S] tmem_full ; then tmem base holder
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 1);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages), tfull = smem_u32(bars + 2 * kStages);
+  const uint32_t stage_bytes = a_bytes + b_bytes;  // stage s: A tile at smem + s*stage_bytes, B tile right after it
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
+  // bars: full[4] | empty[4] | acc_full[2] | acc_empty[2] ; tmem base holder ; 2 x index lists (cnt | self | nbr)
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  int32_t* idx_base = reinterpret_cast<int32_t*>(bars + 2 * kMaxStages + 5);
+  const int idx_words = kTileM * (2 + fanout);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
+  const uint32_t accf0 = smem_u32(bars + 2 * kMaxStages), acce0 = smem_u32(bars + 2 * kMaxStages + 2);
 
   if (threadIdx.x == 0) {
-#pragma unroll
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full0 + 8 * s, 4 + 1);  // 4 producer warps + the TMA thread
-      mbar_init(empty0 + 8 * s, 1);     // one tcgen05.commit
+      mbar_init(full0 + 8 * s, kProducerWarps + 1);  // producer warps + the TMA thread
+      mbar_init(empty0 + 8 * s, 1);                  // one tcgen05.commit
     }
-    mbar_init(tfull, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(accf0 + 8 * a, 1);               // tcgen05.commit after the tile's last MMA
+      mbar_init(acce0 + 8 * a, kEpilogueWarps);  // every epilogue warp has drained the accumulator
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const uint32_t tmem_cols = Np <= 32 ? 32 : (Np <= 64 ? 64 : (Np <= 128 ? 128 : 256));
-  if (warp == 5) {
+  const uint32_t acc_cols = Np <= 32 ? 32 : (Np <= 64 ? 64 : (Np <= 128 ? 128 : 256));
+  const uint32_t tmem_cols = 2 * acc_cols;  // double-buffered accumulator
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -163,127 +186,194 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  const int64_t tile_stride = (int64_t)gridDim.x * R;
 
-  if (warp < 4) {
+  if (warp < kProducerWarps) {
     // ===================== producers: gather + mean -> swizzled smem A tile =====================
-    const int tid = threadIdx.x;       // 0..127
-    const int c = tid & 7;             // 16-byte chunk inside the 128-byte row slice
-    const int r0 = tid >> 3;           // 0..15
-    for (int kc = 0; kc < KC; ++kc) {
-      const int stage = kc % kStages;
-      const uint32_t phase = (kc / kStages) & 1;
-      mbar_wait(empty0 + 8 * stage, phase ^ 1);
-      const bool self_half = kc < KH;
-      const int col0 = (self_half ? kc : kc - KH) * kChunkK + c * 8;  // element offset inside the X row
-#pragma unroll 2
-      for (int pass = 0; pass < kTileM / 16; ++pass) {
-        const int r = pass * 16 + r0;
-        const int64_t grow = tile0 + r;
-        uint4 val = make_uint4(0, 0, 0, 0);
-        if (grow < n) {
-          if (self_half) {
-            const int64_t sid = self_ids ? (int64_t)self_ids[grow] : grow;
-            val = __ldg(reinterpret_cast<const uint4*>(X + sid * Fp + col0));
-          } else {
-            const int cn = cnt[grow];
-            const int32_t* nb = nbr + grow * fanout;
+    const int tid = threadIdx.x;  // 0..511
+    const int c = tid & 7;        // 16-byte chunk inside the 128-byte row slice
+    const int r0 = tid >> 3;      // 0..63
+    const int passes = R / kRowsPerPass;  // 1 or 2
+
+    // index lists of a tile -> smem buffer `buf` (asynchronously; rows past the live count get cnt = 0)
+    auto stage_indices = [&](int64_t t0, int buf) {
+      int32_t* s_cnt = idx_base + buf * idx_words;
+      int32_t* s_self = s_cnt + kTileM;
+      int32_t* s_nbr = s_self + kTileM;
+      const int rows = (int)max((int64_t)0, min((int64_t)R, n - t0));
+      for (int i = tid; i < R; i += kProducerWarps * 32) {
+        if (i < rows) {
+          cp_async4(smem_u32(s_cnt + i), cnt + t0 + i);
+          if (self_ids) cp_async4(smem_u32(s_self + i), self_ids + t0 + i);
+          else s_self[i] = (int32_t)(t0 + i);
+        } else {
+          s_cnt[i] = 0;
+          s_self[i] = 0;
+        }
+      }
+      const int32_t* nb_g = nbr + t0 * fanout;
+      for (int i = tid; i < rows * fanout; i += kProducerWarps * 32) cp_async4(smem_u32(s_nbr + i), nb_g + i);
+    };
+
+    stage_indices((int64_t)blockIdx.x * R, 0);
+    uint32_t g = 0;  // running chunk counter across tiles -> smem ring slot + parity
+    int it = 0;
+    for (int64_t tile0 = (int64_t)blockIdx.x * R; tile0 < n; tile0 += tile_stride, ++it) {
+      cp_async_wait_all();
+      producer_bar();  // this tile's lists are visible; everyone is done reading the other buffer
+      if (tile0 + tile_stride < n) stage_indices(tile0 + tile_stride, (it + 1) & 1);
+      const int32_t* s_cnt = idx_base + (it & 1) * idx_words;
+      const int32_t* s_self = s_cnt + kTileM;
+      const int32_t* s_nbr = s_self + kTileM;
+      const int rows_here = (int)min((int64_t)R, n - tile0);
+      for (int kc = 0; kc < KC; ++kc, ++g) {
+        const int stage = g % kStages;
+        const uint32_t phase = (g / kStages) & 1;
+        mbar_wait(empty0 + 8 * stage, phase ^ 1);
+        const bool self_half = kc < KH;
+        const __nv_bfloat16* Xc = X + (self_half ? kc : kc - KH) * kChunkK + c * 8;  // column slice of this lane
+        uint8_t* sa = smem + stage * stage_bytes;
+        __nv_bfloat16* Ao = A_out ? A_out + kc * kChunkK + c * 8 : nullptr;
+        if (self_half) {
+          uint4 val[2];
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const int r = pass * kRowsPerPass + r0;
+            val[pass] = (pass < passes && r < rows_here) ? __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)s_self[r] * Fp))
+                                                         : make_uint4(0, 0, 0, 0);
+          }
+#pragma unroll
+          for (int pass = 0; pass < 2; ++pass) {
+            const int r = pass * kRowsPerPass + r0;
+            if (pass < passes) {
+              if (Ao && r < rows_here) *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp) = val[pass];
+              *reinterpret_cast<uint4*>(sa + sw128_off(r, c)) = val[pass];
+            }
+          }
+        } else {
+#pragma unroll 1
+          for (int pass = 0; pass < passes; ++pass) {
+            const int r = pass * kRowsPerPass + r0;
+            const int cn = s_cnt[r];  // 0 for rows past the live count
+            const int32_t* nb = s_nbr + r * fanout;
             AccRow acc;
 #pragma unroll
             for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
-            int k = 0;
-            for (; k + 4 <= cn; k += 4) {
-              const int64_t u0 = max(nb[k], 0), u1 = max(nb[k + 1], 0), u2 = max(nb[k + 2], 0), u3 = max(nb[k + 3], 0);
-              const uint4 q0 = __ldg(reinterpret_cast<const uint4*>(X + u0 * Fp + col0));
-              const uint4 q1 = __ldg(reinterpret_cast<const uint4*>(X + u1 * Fp + col0));
-              const uint4 q2 = __ldg(reinterpret_cast<const uint4*>(X + u2 * Fp + col0));
-              const uint4 q3 = __ldg(reinterpret_cast<const uint4*>(X + u3 * Fp + col0));
-              acc_add(acc, q0); acc_add(acc, q1); acc_add(acc, q2); acc_add(acc, q3);
-            }
-            for (; k < cn; ++k) {
-              const int64_t u = max(nb[k], 0);
-              acc_add(acc, __ldg(reinterpret_cast<const uint4*>(X + u * Fp + col0)));
+            for (int k0 = 0; k0 < cn; k0 += kGatherBatch) {
+              uint4 q[kGatherBatch];
+#pragma unroll
+              for (int j = 0; j < kGatherBatch; ++j)
+                q[j] = (k0 + j < cn) ? __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)max(nb[k0 + j], 0) * Fp))
+                                     : make_uint4(0, 0, 0, 0);
+#pragma unroll
+              for (int j = 0; j < kGatherBatch; ++j) acc_add(acc, q[j]);
             }
             const float inv = cn > 0 ? 1.f / (float)cn : 0.f;
+            uint4 val;
             __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
 #pragma unroll
             for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc.v[2 * i] * inv, acc.v[2 * i + 1] * inv);
+            if (Ao && r < rows_here) *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp) = val;
+            *reinterpret_cast<uint4*>(sa + sw128_off(r, c)) = val;
           }
-          if (A_out) *reinterpret_cast<uint4*>(A_out + grow * Kp + kc * kChunkK + c * 8) = val;
         }
-        *reinterpret_cast<uint4*>(sA[stage] + sw128_off(r, c)) = val;
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0) mbar_arrive(full0 + 8 * stage);
       }
-      fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full0 + 8 * stage);
     }
+  } else if (warp < kTmaWarp) {
     // ===================== epilogue: TMEM -> registers -> bias/ReLU/dropout -> bf16 -> global =====
-    mbar_wait(tfull, 0);
-    tc_fence_after();
-    const int row = warp * 32 + lane;
-    const int64_t grow = tile0 + row;
+    // warp w may touch TMEM lanes 32*(w%4)..+31  (kProducerWarps % 4 == 0, so quarter = warp & 3)
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
     const uint64_t sd = seed + (step_dev ? (uint64_t)(*step_dev) * 0x9E3779B97F4A7C15ull : 0ull);
+    const uint32_t sd32 = fmix32((uint32_t)sd ^ fmix32((uint32_t)(sd >> 32)));
+    const uint32_t thresh = (uint32_t)(fminf(fmaxf(p_drop, 0.f), 1.f) * 65536.f);
     const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
-    for (int n0 = 0; n0 < Np; n0 += 32) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)n0, v);
-      if (grow < n) {
-        uint32_t packed[16];
+    int it = 0;
+    for (int64_t tile0 = (int64_t)blockIdx.x * R; tile0 < n; tile0 += tile_stride, ++it) {
+      const int acc = it & 1;
+      mbar_wait(accf0 + 8 * acc, (it >> 1) & 1);
+      tc_fence_after();
+      const int64_t grow = tile0 + row;
+      const bool live = row < R && grow < n;
+      if (quarter * 32 < R) {  // warp-uniform: quarters past the live rows of a 64-row tile have nothing to drain
+        for (int n0 = 0; n0 < Np; n0 += 32) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + n0), v);
+          if (live) {
+            uint32_t packed[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          float a = __uint_as_float(v[j]) + bias[n0 + j];
-          float b = __uint_as_float(v[j + 1]) + bias[n0 + j + 1];
-          if (RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-          if (p_drop > 0.f) {
-            const uint64_t rb = rng_u64(sd, 0x51ull, (uint64_t)(grow * Np + n0 + j));
-            const float ua = (float)(rb & 0xffffff) * (1.f / 16777216.f);
-            const float ub = (float)((rb >> 24) & 0xffffff) * (1.f / 16777216.f);
-            a = ua < p_drop ? 0.f : a * keep_scale;
-            b = ub < p_drop ? 0.f : b * keep_scale;
+            for (int j = 0; j < 32; j += 2) {
+              float a = __uint_as_float(v[j]) + __ldg(bias + n0 + j);
+              float b = __uint_as_float(v[j + 1]) + __ldg(bias + n0 + j + 1);
+              if (RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
+              if (p_drop > 0.f) {
+                const uint64_t e = (uint64_t)(grow * Np + n0 + j) >> 1;
+                const uint32_t rb = fmix32(((uint32_t)e * 0x9E3779B9u) ^ ((uint32_t)(e >> 32) * 0x85ebca77u) ^ sd32);
+                a = (rb & 0xffffu) < thresh ? 0.f : a * keep_scale;
+                b = (rb >> 16) < thresh ? 0.f : b * keep_scale;
+              }
+              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(out + grow * Np + n0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
           }
-          __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-          packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
         }
-        uint4* dst = reinterpret_cast<uint4*>(out + grow * Np + n0);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(acce0 + 8 * acc);  // accumulator may be overwritten by tile it+2
     }
-    tc_fence_before();
-  } else if (warp == 4) {
+  } else if (warp == kTmaWarp) {
     // ===================== TMA producer for the W^T tiles =====================
     if (lane == 0) {
-      for (int kc = 0; kc < KC; ++kc) {
-        const int stage = kc % kStages;
-        const uint32_t phase = (kc / kStages) & 1;
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        mbar_arrive_expect_tx(full0 + 8 * stage, b_bytes);
-        tma_load_2d(smem_u32(sB[stage]), &tmap_w, full0 + 8 * stage, kc * kChunkK, 0);
+      uint32_t g = 0;
+      for (int64_t tile0 = (int64_t)blockIdx.x * R; tile0 < n; tile0 += tile_stride) {
+        for (int kc = 0; kc < KC; ++kc, ++g) {
+          const int stage = g % kStages;
+          const uint32_t phase = (g / kStages) & 1;
+          mbar_wait(empty0 + 8 * stage, phase ^ 1);
+          mbar_arrive_expect_tx(full0 + 8 * stage, b_bytes);
+          tma_load_2d(smem_u32(smem + stage * stage_bytes + a_bytes), &tmap_w, full0 + 8 * stage, kc * kChunkK, 0);
+        }
       }
     }
   } else {
     // ===================== MMA issuer (one elected thread) =====================
     // instruction descriptor: D=F32, A=B=BF16, both K-major, N = Np, M = 128
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
-    for (int kc = 0; kc < KC; ++kc) {
-      const int stage = kc % kStages;
-      const uint32_t phase = (kc / kStages) & 1;
-      mbar_wait(full0 + 8 * stage, phase);
+    uint32_t g = 0;
+    int it = 0;
+    for (int64_t tile0 = (int64_t)blockIdx.x * R; tile0 < n; tile0 += tile_stride, ++it) {
+      const int acc = it & 1;
+      mbar_wait(acce0 + 8 * acc, ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator (free on first use)
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t a0 = smem_u32(sA[stage]), b0 = smem_u32(sB[stage]);
+      const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
+      for (int kc = 0; kc < KC; ++kc, ++g) {
+        const int stage = g % kStages;
+        const uint32_t phase = (g / kStages) & 1;
+        mbar_wait(full0 + 8 * stage, phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a0 = smem_u32(smem + stage * stage_bytes), b0 = a0 + a_bytes;
 #pragma unroll
-        for (int k = 0; k < kChunkK / 16; ++k) {
-          umma_bf16(tmem_base, make_sw128_kmajor_desc(a0 + k * 32), make_sw128_kmajor_desc(b0 + k * 32), idesc,
-                    (kc | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kChunkK / 16; ++k) {
+            umma_bf16(tmem_d, make_sw128_kmajor_desc(a0 + k * 32), make_sw128_kmajor_desc(b0 + k * 32), idesc,
+                      (kc | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(empty0 + 8 * stage);                    // smem slot reusable once these MMAs retire
+          if (kc == KC - 1) umma_commit(accf0 + 8 * acc);     // accumulator complete -> epilogue
         }
-        umma_commit(empty0 + 8 * stage);          // smem slot reusable once these MMAs retire
-        if (kc == KC - 1) umma_commit(tfull);     // accumulator complete -> epilogue
+        __syncwarp();
       }
-      __syncwarp();
     }
   }
   __syncthreads();
-  if (warp == 5) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
@@ -328,15 +418,28 @@ DGLB_API int dglb200_engine_sage_layer_tc(const void* X, const void* self_ids, c
                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-  const size_t smem = (size_t)kStages * (kTileM * 128 + (size_t)Np * 128) + 1024 + 128;
-  const unsigned grid = (unsigned)((n_cap + kTileM - 1) / kTileM);
+  const size_t stage_bytes = kTileM * 128 + (size_t)Np * 128;
+  const size_t fixed = 1024 + 256 + 2 * (size_t)kTileM * 4 * (2 + fanout);
+  DGLB_CHECK(fixed + 2 * stage_bytes <= 227 * 1024, "fanout too large for the fused layer kernel");
+  const int stages = (int)std::min<size_t>(kMaxStages, (227 * 1024 - fixed) / stage_bytes);
+  const size_t smem = (size_t)stages * stage_bytes + fixed;
+  static int num_sms = 0;
+  if (!num_sms) {
+    int dev = 0;
+    DGLB_CUDA_CHECK(cudaGetDevice(&dev));
+    DGLB_CUDA_CHECK(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // gather-bound layer: with fewer than 8 waves of 128-row tiles use 64 live rows per (128-row) MMA tile
+  const int64_t tiles128 = (n_cap + kTileM - 1) / kTileM;
+  const int R = tiles128 < 8 * (int64_t)num_sms ? 64 : 128;
+  const unsigned grid = (unsigned)std::min<int64_t>((n_cap + R - 1) / R, num_sms);
   cudaStream_t st = (cudaStream_t)stream;
   if (relu) {
     DGLB_CUDA_CHECK(cudaFuncSetAttribute(sage_layer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sage_layer_tc_kernel<true><<<grid, 192, smem, st>>>(tmap, (const __nv_bfloat16*)X, (const int32_t*)self_ids, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np, (const float*)bias, (__nv_bfloat16*)out, (__nv_bfloat16*)A_out, p_drop, (uint64_t)seed, (const int64_t*)step_dev);
+    sage_layer_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmap, (const __nv_bfloat16*)X, (const int32_t*)self_ids, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np, (const float*)bias, (__nv_bfloat16*)out, (__nv_bfloat16*)A_out, p_drop, (uint64_t)seed, (const int64_t*)step_dev, stages, R);
   } else {
     DGLB_CUDA_CHECK(cudaFuncSetAttribute(sage_layer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sage_layer_tc_kernel<false><<<grid, 192, smem, st>>>(tmap, (const __nv_bfloat16*)X, (const int32_t*)self_ids, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np, (const float*)bias, (__nv_bfloat16*)out, (__nv_bfloat16*)A_out, p_drop, (uint64_t)seed, (const int64_t*)step_dev);
+    sage_layer_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmap, (const __nv_bfloat16*)X, (const int32_t*)self_ids, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np, (const float*)bias, (__nv_bfloat16*)out, (__nv_bfloat16*)A_out, p_drop, (uint64_t)seed, (const int64_t*)step_dev, stages, R);
   }
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH

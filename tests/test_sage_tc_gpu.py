@@ -7,7 +7,8 @@ DEV = "cuda"
 
 
 @pytest.mark.parametrize("Fp,Np,ncap,nvalid,fan,use_self", [(128, 256, 1000, 900, 10, True), (256, 256, 300, 300, 5, False),
-                                                          (64, 64, 129, 1, 3, True), (128, 32, 4096, 4000, 10, True)])
+                                                          (64, 64, 129, 1, 3, True), (128, 32, 4096, 4000, 10, True),
+                                                          (128, 256, 30000, 29000, 10, True), (64, 128, 160000, 159990, 4, True)])
 def test_sage_layer_tc(Fp, Np, ncap, nvalid, fan, use_self):
     from dgl_b200.ops.fused import sage_layer_tc
     torch.manual_seed(0)
