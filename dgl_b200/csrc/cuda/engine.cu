@@ -163,6 +163,76 @@ __global__ void __launch_bounds__(256) ce_loss_kernel(const float* __restrict__ 
   }
 }
 
+// Cross entropy, second generation: strided logits (e.g. the 64-column padded output of the fused layer kernel),
+// optional bias, gradient emitted in fp32 [n_cap, C] and/or bf16 [n_cap, ldd] (padding columns zeroed, ready to be the
+// operand of the backward GEMMs) and the bias gradient reduced in the same pass (block partial sums -> atomics).
+__global__ void __launch_bounds__(256) ce_loss2_kernel(const float* __restrict__ logits, int ldl,
+                                                       const float* __restrict__ bias,
+                                                       const int32_t* __restrict__ labels_all,
+                                                       const int32_t* __restrict__ seeds,
+                                                       const int64_t* __restrict__ n_dev, int64_t n_cap, int C,
+                                                       float* __restrict__ dlog32, __nv_bfloat16* __restrict__ dlog16,
+                                                       int ldd, float* __restrict__ db, float* __restrict__ loss_out,
+                                                       int32_t* __restrict__ correct_out) {
+  __shared__ float s_db[8][64];
+  const int64_t n = min(*n_dev, n_cap);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * 8 + w;
+  float g[2] = {0.f, 0.f};  // this lane's columns: lane, lane + 32   (C <= 64)
+  if (r < n) {
+    const int y = labels_all[seeds[r]];
+    float v[2];
+    float mx = -INFINITY;
+    int amax = 0;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = lane + 32 * q;
+      v[q] = c < C ? logits[r * ldl + c] + (bias ? bias[c] : 0.f) : -INFINITY;
+      if (v[q] > mx) { mx = v[q]; amax = c; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+      const float om = __shfl_xor_sync(0xffffffffu, mx, o);
+      const int oa = __shfl_xor_sync(0xffffffffu, amax, o);
+      if (om > mx || (om == mx && oa < amax)) { mx = om; amax = oa; }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) sum += lane + 32 * q < C ? __expf(v[q] - mx) : 0.f;
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv_n = 1.f / (float)n;
+    const float lse = mx + __logf(sum);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = lane + 32 * q;
+      if (c < C) g[q] = (__expf(v[q] - lse) - (c == y ? 1.f : 0.f)) * inv_n;
+    }
+    const float vy = __shfl_sync(0xffffffffu, v[y >> 5], y & 31);
+    if (lane == 0) {
+      atomicAdd(loss_out, (lse - vy) * inv_n);
+      if (correct_out && amax == y) atomicAdd(correct_out, 1);
+    }
+  }
+  if (r < n_cap) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int c = lane + 32 * q;
+      if (dlog32 && c < C) dlog32[r * C + c] = g[q];
+      if (dlog16 && c < ldd) dlog16[r * ldd + c] = __float2bfloat16(g[q]);
+    }
+  }
+  if (db) {
+    s_db[w][lane] = g[0];
+    s_db[w][lane + 32] = g[1];
+    __syncthreads();
+    if (threadIdx.x < C) {
+      float t = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += s_db[k][threadIdx.x];
+      if (t != 0.f) atomicAdd(db + threadIdx.x, t);
+    }
+  }
+}
+
 // dH[self(d)] += dA[d, 0:F];  dH[nbr[d,k]] += dA[d, F:2F] / cnt[d]     (dH fp32, pre-zeroed)
 template <typename T, typename I>
 __global__ void __launch_bounds__(256) scatter_grad_kernel(const T* __restrict__ dA, const I* __restrict__ nbr,
@@ -410,6 +480,20 @@ DGLB_API int dglb200_engine_ce_loss(const void* logits, const void* bias, const 
   DGLB_TRY
   cudaStream_t st = (cudaStream_t)stream;
   ce_loss_kernel<<<(unsigned)((n_cap + 7) / 8), 256, 0, st>>>((const float*)logits, (const float*)bias, (const int32_t*)labels_all, (const int32_t*)seeds, (const int64_t*)n_dev, n_cap, C, (float*)dlogits, (float*)loss_out, (int32_t*)correct_out);
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}
+
+DGLB_API int dglb200_engine_ce_loss2(const void* logits, int ldl, const void* bias, const void* labels_all,
+                                     const void* seeds, const void* n_dev, int64_t n_cap, int C, void* dlog32,
+                                     void* dlog16, int ldd, void* db, void* loss_out, void* correct_out, void* stream) {
+  DGLB_TRY
+  DGLB_CHECK(C >= 1 && C <= 64 && ldd <= 64, "ce_loss2 supports up to 64 classes");
+  if (n_cap == 0) return 0;
+  ce_loss2_kernel<<<(unsigned)((n_cap + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
+      (const float*)logits, ldl, (const float*)bias, (const int32_t*)labels_all, (const int32_t*)seeds,
+      (const int64_t*)n_dev, n_cap, C, (float*)dlog32, (__nv_bfloat16*)dlog16, ldd, (float*)db, (float*)loss_out,
+      (int32_t*)correct_out);
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH
 }

@@ -41,16 +41,18 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  // try_wait with a suspend-time hint: a waiting warp sleeps in hardware until the phase flips instead of
+  // burning issue slots that the gather / epilogue warps of the same SM sub-partition need
   asm volatile(
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
       "}\n" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)
       : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
@@ -119,12 +121,11 @@ __device__ __forceinline__ void acc_add(AccRow& a, const uint4& q) {
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
 
 constexpr int kProducerWarps = 16;
-constexpr int kEpilogueWarps = 4;
+constexpr int kEpilogueWarps = 8;
 constexpr int kTmaWarp = kProducerWarps + kEpilogueWarps;
 constexpr int kMmaWarp = kTmaWarp + 1;
-constexpr int kThreads = (kMmaWarp + 1) * 32;  // 704
-constexpr int kGatherBatch = 12;               // independent 16-byte row loads in flight per producer lane
-constexpr int kRowsPerPass = kProducerWarps * 4;  // 8 lanes cover one 128-byte row slice -> 64 rows per pass
+constexpr int kThreads = (kMmaWarp + 1) * 32;  // 832
+constexpr int kGatherBatch = 10;               // independent 16-byte row loads in flight per producer lane
 
 __device__ __forceinline__ void producer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(kProducerWarps * 32) : "memory"); }
 __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
@@ -144,7 +145,7 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
                      const int32_t* __restrict__ cnt, const int64_t* __restrict__ n_dev, int64_t n_cap, int fanout,
                      int Fp, int Np, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
                      __nv_bfloat16* __restrict__ A_out, float p_drop, uint64_t seed,
-                     const int64_t* __restrict__ step_dev, int kStages, int R) {
+                     const int64_t* __restrict__ step_dev, int kStages, int R, int out_f32, long long* __restrict__ trace) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int64_t n = min(*n_dev, n_cap);
   if ((int64_t)blockIdx.x * R >= n) return;  // device-side M: CTAs past the live row count do no work at all
@@ -160,7 +161,8 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
   // bars: full[4] | empty[4] | acc_full[2] | acc_empty[2] ; tmem base holder ; 2 x index lists (cnt | self | nbr)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
-  int32_t* idx_base = reinterpret_cast<int32_t*>(bars + 2 * kMaxStages + 5);
+  float* s_bias = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6);  // [256] bias * dropout rescale (16-B aligned)
+  int32_t* idx_base = reinterpret_cast<int32_t*>(s_bias + 256);
   const int idx_words = kTileM * (2 + fanout);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
   const uint32_t accf0 = smem_u32(bars + 2 * kMaxStages), acce0 = smem_u32(bars + 2 * kMaxStages + 2);
@@ -186,14 +188,14 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_holder;
+  // optional cycle-stamp trace of CTA 0 (debug / profiling aid; null in production)
+#define SAGE_TRACE(slot, cond) do { if (trace && blockIdx.x == 0 && (cond)) trace[(slot)] = clock64(); } while (0)
+  SAGE_TRACE(0, threadIdx.x == 0);
   const int64_t tile_stride = (int64_t)gridDim.x * R;
 
   if (warp < kProducerWarps) {
     // ===================== producers: gather + mean -> swizzled smem A tile =====================
     const int tid = threadIdx.x;  // 0..511
-    const int c = tid & 7;        // 16-byte chunk inside the 128-byte row slice
-    const int r0 = tid >> 3;      // 0..63
-    const int passes = R / kRowsPerPass;  // 1 or 2
 
     // index lists of a tile -> smem buffer `buf` (asynchronously; rows past the live count get cnt = 0)
     auto stage_indices = [&](int64_t t0, int buf) {
@@ -222,101 +224,140 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
       cp_async_wait_all();
       producer_bar();  // this tile's lists are visible; everyone is done reading the other buffer
       if (tile0 + tile_stride < n) stage_indices(tile0 + tile_stride, (it + 1) & 1);
+      SAGE_TRACE(144 + it, tid == 0 && it < 8);
       const int32_t* s_cnt = idx_base + (it & 1) * idx_words;
       const int32_t* s_self = s_cnt + kTileM;
       const int32_t* s_nbr = s_self + kTileM;
       const int rows_here = (int)min((int64_t)R, n - tile0);
-      for (int kc = 0; kc < KC; ++kc, ++g) {
-        const int stage = g % kStages;
-        const uint32_t phase = (g / kStages) & 1;
-        mbar_wait(empty0 + 8 * stage, phase ^ 1);
-        const bool self_half = kc < KH;
-        const __nv_bfloat16* Xc = X + (self_half ? kc : kc - KH) * kChunkK + c * 8;  // column slice of this lane
-        uint8_t* sa = smem + stage * stage_bytes;
-        __nv_bfloat16* Ao = A_out ? A_out + kc * kChunkK + c * 8 : nullptr;
-        if (self_half) {
-          uint4 val[2];
+      // K is walked in groups of up to two 64-column chunks: a lane group then reads 256 contiguous bytes of a
+      // feature row at once (DRAM page / sector locality) and fills two ring slots in one pass.
+      for (int half = 0; half < 2; ++half) {
+        for (int k0 = 0; k0 < KH; k0 += 2) {
+          const int nch = min(2, KH - k0);
+          const int lpr_shift = nch == 2 ? 4 : 3;  // lanes per row piece: 16 or 8
+          const int rpp = (kProducerWarps * 32) >> lpr_shift;  // rows per pass: 32 or 64
+          const int piece = tid & ((1 << lpr_shift) - 1);
+          const int r0 = tid >> lpr_shift;
+          const int kcl = piece >> 3, c = piece & 7;
+          for (int u = 0; u < nch; ++u) mbar_wait(empty0 + 8 * ((g + u) % kStages), (((g + u) / kStages) & 1) ^ 1);
+          uint8_t* sa = smem + ((g + kcl) % kStages) * stage_bytes;
+          const int col = (k0 + kcl) * kChunkK + c * 8;  // column of this lane's 16 bytes inside the half
+          const __nv_bfloat16* Xc = X + col;
+          __nv_bfloat16* Ao = A_out ? A_out + half * Fp + col : nullptr;
+          const int npass = R / rpp;  // 1..4
+          if (half == 0) {
+            uint4 val[4];
 #pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            const int r = pass * kRowsPerPass + r0;
-            val[pass] = (pass < passes && r < rows_here) ? __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)s_self[r] * Fp))
-                                                         : make_uint4(0, 0, 0, 0);
-          }
-#pragma unroll
-          for (int pass = 0; pass < 2; ++pass) {
-            const int r = pass * kRowsPerPass + r0;
-            if (pass < passes) {
-              if (Ao && r < rows_here) *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp) = val[pass];
-              *reinterpret_cast<uint4*>(sa + sw128_off(r, c)) = val[pass];
+            for (int pass = 0; pass < 4; ++pass) {
+              const int r = pass * rpp + r0;
+              val[pass] = (pass < npass && r < rows_here) ? __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)s_self[r] * Fp))
+                                                          : make_uint4(0, 0, 0, 0);
             }
-          }
-        } else {
+#pragma unroll
+            for (int pass = 0; pass < 4; ++pass) {
+              const int r = pass * rpp + r0;
+              if (pass < npass) {
+                if (Ao && r < rows_here) *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp) = val[pass];
+                *reinterpret_cast<uint4*>(sa + sw128_off(r, c)) = val[pass];
+              }
+            }
+          } else {
 #pragma unroll 1
-          for (int pass = 0; pass < passes; ++pass) {
-            const int r = pass * kRowsPerPass + r0;
-            const int cn = s_cnt[r];  // 0 for rows past the live count
-            const int32_t* nb = s_nbr + r * fanout;
-            AccRow acc;
+            for (int pass = 0; pass < npass; ++pass) {
+              const int r = pass * rpp + r0;
+              const int cn = s_cnt[r];  // 0 for rows past the live count
+              const int32_t* nb = s_nbr + r * fanout;
+              AccRow acc;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
-            for (int k0 = 0; k0 < cn; k0 += kGatherBatch) {
-              uint4 q[kGatherBatch];
+              for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+              for (int j0 = 0; j0 < cn; j0 += kGatherBatch) {
+                uint4 q[kGatherBatch];
 #pragma unroll
-              for (int j = 0; j < kGatherBatch; ++j)
-                q[j] = (k0 + j < cn) ? __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)max(nb[k0 + j], 0) * Fp))
-                                     : make_uint4(0, 0, 0, 0);
+                for (int j = 0; j < kGatherBatch; ++j)
+                  q[j] = (j0 + j < cn) ? __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)max(nb[j0 + j], 0) * Fp))
+                                       : make_uint4(0, 0, 0, 0);
 #pragma unroll
-              for (int j = 0; j < kGatherBatch; ++j) acc_add(acc, q[j]);
+                for (int j = 0; j < kGatherBatch; ++j) acc_add(acc, q[j]);
+              }
+              const float inv = cn > 0 ? 1.f / (float)cn : 0.f;
+              uint4 val;
+              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc.v[2 * i] * inv, acc.v[2 * i + 1] * inv);
+              if (Ao && r < rows_here) *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp) = val;
+              *reinterpret_cast<uint4*>(sa + sw128_off(r, c)) = val;
             }
-            const float inv = cn > 0 ? 1.f / (float)cn : 0.f;
-            uint4 val;
-            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc.v[2 * i] * inv, acc.v[2 * i + 1] * inv);
-            if (Ao && r < rows_here) *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp) = val;
-            *reinterpret_cast<uint4*>(sa + sw128_off(r, c)) = val;
           }
+          fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+          __syncwarp();
+          if (lane == 0)
+            for (int u = 0; u < nch; ++u) mbar_arrive(full0 + 8 * ((g + u) % kStages));
+          SAGE_TRACE(16 + it * 16 + half * KH + k0, tid == 0 && it < 8 && half * KH + k0 < 16);
+          g += nch;
         }
-        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full0 + 8 * stage);
       }
     }
   } else if (warp < kTmaWarp) {
     // ===================== epilogue: TMEM -> registers -> bias/ReLU/dropout -> bf16 -> global =====
-    // warp w may touch TMEM lanes 32*(w%4)..+31  (kProducerWarps % 4 == 0, so quarter = warp & 3)
-    const int quarter = warp & 3;
+    // warp w may touch TMEM lanes 32*(w%4)..+31 (kProducerWarps % 4 == 0, so quarter = warp & 3); the two warps
+    // of a quarter take alternate 32-column blocks.
+    const int ew = warp - kProducerWarps;
+    const int quarter = ew & 3;
     const int row = quarter * 32 + lane;
     const uint64_t sd = seed + (step_dev ? (uint64_t)(*step_dev) * 0x9E3779B97F4A7C15ull : 0ull);
     const uint32_t sd32 = fmix32((uint32_t)sd ^ fmix32((uint32_t)(sd >> 32)));
-    const uint32_t thresh = (uint32_t)(fminf(fmaxf(p_drop, 0.f), 1.f) * 65536.f);
-    const float keep_scale = p_drop > 0.f ? 1.f / (1.f - p_drop) : 1.f;
+    // drop probability quantised to 1/256 (the rescale uses the quantised value, so the estimator stays unbiased)
+    const uint32_t thresh = p_drop > 0.f ? min(255u, (uint32_t)(fminf(p_drop, 1.f) * 256.f + 0.5f)) : 0u;
+    const uint32_t thresh4 = thresh * 0x01010101u;
+    const float keep_scale = 256.f / (256.f - (float)thresh);
+    // bias pre-multiplied by the dropout rescale: relu(x + b) * s == relu(x * s + b * s)
+    for (int i = ew * 32 + lane; i < Np; i += kEpilogueWarps * 32) s_bias[i] = bias ? bias[i] * keep_scale : 0.f;
+    asm volatile("bar.sync 2, %0;" ::"n"(kEpilogueWarps * 32) : "memory");
     int it = 0;
     for (int64_t tile0 = (int64_t)blockIdx.x * R; tile0 < n; tile0 += tile_stride, ++it) {
       const int acc = it & 1;
+      SAGE_TRACE(300 + it * 4, ew == 0 && lane == 0 && it < 8);
       mbar_wait(accf0 + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
+      SAGE_TRACE(301 + it * 4, ew == 0 && lane == 0 && it < 8);
       const int64_t grow = tile0 + row;
       const bool live = row < R && grow < n;
+      const uint32_t sd_row = sd32 ^ ((uint32_t)((uint64_t)grow >> 20) * 0x85ebca77u);
       if (quarter * 32 < R) {  // warp-uniform: quarters past the live rows of a 64-row tile have nothing to drain
-        for (int n0 = 0; n0 < Np; n0 += 32) {
+        for (int n0 = (ew >> 2) * 32; n0 < Np; n0 += 32 * (kEpilogueWarps / 4)) {
           uint32_t v[32];
           tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + n0), v);
-          if (live) {
-            uint32_t packed[16];
+          if (live && out_f32) {  // fp32 output (logits of an output layer): bias (+ReLU), no dropout, no rounding
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + grow * Np + n0);
 #pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              float a = __uint_as_float(v[j]) + __ldg(bias + n0 + j);
-              float b = __uint_as_float(v[j + 1]) + __ldg(bias + n0 + j + 1);
-              if (RELU) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
-              if (p_drop > 0.f) {
-                const uint64_t e = (uint64_t)(grow * Np + n0 + j) >> 1;
-                const uint32_t rb = fmix32(((uint32_t)e * 0x9E3779B9u) ^ ((uint32_t)(e >> 32) * 0x85ebca77u) ^ sd32);
-                a = (rb & 0xffffu) < thresh ? 0.f : a * keep_scale;
-                b = (rb >> 16) < thresh ? 0.f : b * keep_scale;
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sb = *reinterpret_cast<const float4*>(s_bias + n0 + j);
+              float4 x = make_float4(__uint_as_float(v[j]) + sb.x, __uint_as_float(v[j + 1]) + sb.y,
+                                     __uint_as_float(v[j + 2]) + sb.z, __uint_as_float(v[j + 3]) + sb.w);
+              if (RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+              dst[j >> 2] = x;
+            }
+          } else if (live) {
+            uint32_t packed[16];
+            const uint32_t e0 = (uint32_t)(((uint64_t)grow * (uint64_t)Np + (uint64_t)n0) >> 2);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sb = *reinterpret_cast<const float4*>(s_bias + n0 + j);
+              float x0 = fmaf(__uint_as_float(v[j]), keep_scale, sb.x);
+              float x1 = fmaf(__uint_as_float(v[j + 1]), keep_scale, sb.y);
+              float x2 = fmaf(__uint_as_float(v[j + 2]), keep_scale, sb.z);
+              float x3 = fmaf(__uint_as_float(v[j + 3]), keep_scale, sb.w);
+              if (RELU) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); x2 = fmaxf(x2, 0.f); x3 = fmaxf(x3, 0.f); }
+              __nv_bfloat162 h01 = __floats2bfloat162_rn(x0, x1), h23 = __floats2bfloat162_rn(x2, x3);
+              uint32_t p01 = *reinterpret_cast<uint32_t*>(&h01), p23 = *reinterpret_cast<uint32_t*>(&h23);
+              if (thresh) {  // one 32-bit hash -> four 8-bit keep/drop decisions, applied as bit masks on the bf16 pairs
+                const uint32_t rb = fmix32(((e0 + (uint32_t)(j >> 2)) * 0x9E3779B9u) ^ sd_row);
+                const uint32_t drop = __vcmpltu4(rb, thresh4);  // 0xff in every byte that is below the threshold
+                p01 &= ~__byte_perm(drop, 0, 0x1100);
+                p23 &= ~__byte_perm(drop, 0, 0x3322);
               }
-              __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-              packed[j >> 1] = *reinterpret_cast<uint32_t*>(&h);
+              packed[j >> 1] = p01;
+              packed[(j >> 1) + 1] = p23;
             }
             uint4* dst = reinterpret_cast<uint4*>(out + grow * Np + n0);
 #pragma unroll
@@ -327,6 +368,7 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce0 + 8 * acc);  // accumulator may be overwritten by tile it+2
+      SAGE_TRACE(302 + it * 4, ew == 0 && lane == 0 && it < 8);
     }
   } else if (warp == kTmaWarp) {
     // ===================== TMA producer for the W^T tiles =====================
@@ -367,12 +409,15 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
           }
           umma_commit(empty0 + 8 * stage);                    // smem slot reusable once these MMAs retire
           if (kc == KC - 1) umma_commit(accf0 + 8 * acc);     // accumulator complete -> epilogue
+          SAGE_TRACE(160 + it * 16 + kc, it < 8 && kc < 16);
         }
         __syncwarp();
       }
     }
   }
   __syncthreads();
+  SAGE_TRACE(1, threadIdx.x == 0);
+#undef SAGE_TRACE
   if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
@@ -399,15 +444,17 @@ static EncodeTiledFn get_encode() {
 
 using namespace dglb;
 
-// X: [rows, Fp] bf16, Wt: [Np, 2*Fp] bf16 (K contiguous), out: [n_cap, Np] bf16, A_out: [n_cap, 2*Fp] bf16 or null
+// X: [rows, Fp] bf16, Wt: [Np, 2*Fp] bf16 (K contiguous), out: [n_cap, Np] bf16 (fp32 when out_f32),
+// A_out: [n_cap, 2*Fp] bf16 or null
 DGLB_API int dglb200_engine_sage_layer_tc(const void* X, const void* self_ids, const void* nbr, const void* cnt,
                                           const void* n_dev, int64_t n_cap, int fanout, int Fp, int Np,
                                           const void* Wt, const void* bias, void* out, void* A_out, int relu,
-                                          float p_drop, int64_t seed, const void* step_dev, void* stream) {
+                                          float p_drop, int64_t seed, const void* step_dev, int out_f32, void* trace, void* stream) {
   DGLB_TRY
   DGLB_CHECK(Fp % 64 == 0 && Fp >= 64, "Fp must be a multiple of 64");
   DGLB_CHECK(Np % 32 == 0 && Np >= 32 && Np <= 256, "Np must be a multiple of 32 in [32, 256]");
   DGLB_CHECK(((uintptr_t)X % 16 == 0) && ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)out % 16 == 0), "16-byte alignment required");
+  DGLB_CHECK(!out_f32 || p_drop == 0.f, "fp32 output does not support dropout");
   if (n_cap == 0) return 0;
   CUtensorMap tmap;
   const cuuint64_t gdim[2] = {(cuuint64_t)(2 * Fp), (cuuint64_t)Np};
@@ -419,7 +466,7 @@ DGLB_API int dglb200_engine_sage_layer_tc(const void* X, const void* self_ids, c
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
   const size_t stage_bytes = kTileM * 128 + (size_t)Np * 128;
-  const size_t fixed = 1024 + 256 + 2 * (size_t)kTileM * 4 * (2 + fanout);
+  const size_t fixed = 1024 + 256 + 1024 + 2 * (size_t)kTileM * 4 * (2 + fanout);
   DGLB_CHECK(fixed + 2 * stage_bytes <= 227 * 1024, "fanout too large for the fused layer kernel");
   const int stages = (int)std::min<size_t>(kMaxStages, (227 * 1024 - fixed) / stage_bytes);
   const size_t smem = (size_t)stages * stage_bytes + fixed;
@@ -436,10 +483,10 @@ DGLB_API int dglb200_engine_sage_layer_tc(const void* X, const void* self_ids, c
   cudaStream_t st = (cudaStream_t)stream;
   if (relu) {
     DGLB_CUDA_CHECK(cudaFuncSetAttribute(sage_layer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sage_layer_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmap, (const __nv_bfloat16*)X, (const int32_t*)self_ids, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np, (const float*)bias, (__nv_bfloat16*)out, (__nv_bfloat16*)A_out, p_drop, (uint64_t)seed, (const int64_t*)step_dev, stages, R);
+    sage_layer_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmap, (const __nv_bfloat16*)X, (const int32_t*)self_ids, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np, (const float*)bias, (__nv_bfloat16*)out, (__nv_bfloat16*)A_out, p_drop, (uint64_t)seed, (const int64_t*)step_dev, stages, R, out_f32, (long long*)trace);
   } else {
     DGLB_CUDA_CHECK(cudaFuncSetAttribute(sage_layer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sage_layer_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmap, (const __nv_bfloat16*)X, (const int32_t*)self_ids, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np, (const float*)bias, (__nv_bfloat16*)out, (__nv_bfloat16*)A_out, p_drop, (uint64_t)seed, (const int64_t*)step_dev, stages, R);
+    sage_layer_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmap, (const __nv_bfloat16*)X, (const int32_t*)self_ids, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np, (const float*)bias, (__nv_bfloat16*)out, (__nv_bfloat16*)A_out, p_drop, (uint64_t)seed, (const int64_t*)step_dev, stages, R, out_f32, (long long*)trace);
   }
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH

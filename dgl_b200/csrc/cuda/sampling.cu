@@ -14,6 +14,7 @@
 namespace dglb {
 
 constexpr int kMaxFloyd = 64;
+constexpr int kTotalSlots = 16;  // out_total is int64[16]: the sum of the slots is the running edge count
 
 template <typename I>
 __global__ void __launch_bounds__(128) sample_ell_kernel(const I* __restrict__ indptr, const I* __restrict__ indices,
@@ -63,10 +64,80 @@ __global__ void __launch_bounds__(128) sample_ell_kernel(const I* __restrict__ i
     }
     out_cnt[i] = cnt;
   }
-  if (out_total) {  // running total of sampled edges (warp-aggregated atomic)
+  if (out_total) {  // running total of sampled edges (warp-aggregated atomic, spread over kTotalSlots addresses)
     int wsum = cnt;
     for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
-    if ((threadIdx.x & 31) == 0 && wsum > 0) atomicAdd((unsigned long long*)out_total, (unsigned long long)wsum);
+    if ((threadIdx.x & 31) == 0 && wsum > 0)
+      atomicAdd((unsigned long long*)out_total + (blockIdx.x & (kTotalSlots - 1)), (unsigned long long)wsum);
+  }
+}
+
+// Sub-warp variant (fanout <= 32): G lanes cooperate on one seed. Every lane draws its own Floyd candidate, the
+// sequential "already chosen?" rule is resolved with fanout-1 register shuffles (lane q's pick is final after step
+// q-1), and the neighbour ids are fetched / written by G lanes at once - no local-memory scratch, and the three
+// dependent memory round trips (seed -> indptr -> indices) are the whole critical path. Same RNG stream and the same
+// picks as the thread-per-seed kernel.
+template <typename I, int G>
+__global__ void __launch_bounds__(256) sample_ell_group_kernel(const I* __restrict__ indptr, const I* __restrict__ indices,
+                                                               const I* __restrict__ seeds, int64_t n_cap,
+                                                               const int64_t* __restrict__ n_dev, int fanout, uint64_t seed,
+                                                               const int64_t* __restrict__ seed_dev, I* __restrict__ out_nbr,
+                                                               I* __restrict__ out_eid, int32_t* __restrict__ out_cnt,
+                                                               int64_t* __restrict__ out_total, int pad_rows) {
+  const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
+  const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t i = gtid / G;
+  const int k = (int)(gtid % G);
+  const bool active = pad_rows ? (i < n_cap) : (i < n);
+  if (seed_dev) seed += (uint64_t)(*seed_dev) * 0xD6E8FEB86659FD93ull;  // per-step stream under graph replay
+  int cnt = 0;
+  int64_t pick = -1;  // CSR position of this lane's neighbour
+  int64_t v = -1, s = 0, deg = 0;
+  if (active && i < n) {
+    v = seeds[i];
+    if (v >= 0) {
+      s = indptr[v];
+      deg = indptr[v + 1] - s;
+    }
+  }
+  const bool floyd = deg > fanout;  // uniform inside the group
+  uint32_t t = 0, val = 0, j = 0;
+  if (floyd && k < fanout) {
+    j = (uint32_t)(deg - fanout + k);
+    t = rng_below(seed, (uint64_t)v * 0x9E37ull + (uint64_t)i, (uint64_t)k, j + 1);
+    val = t;
+  }
+  bool dup = false;
+  for (int q = 0; q + 1 < fanout; ++q) {  // warp-uniform trip count; groups without a Floyd row just ride along
+    const uint32_t cq = __shfl_sync(0xffffffffu, val, q, G);
+    if (k > q && t == cq) dup = true;
+    if (k == q + 1) val = dup ? j : t;
+  }
+  if (deg > 0) {
+    if (floyd) {
+      cnt = fanout;
+      if (k < fanout) pick = s + val;
+    } else {
+      cnt = (int)deg;
+      if (k < cnt) pick = s + k;
+    }
+  }
+  if (active && k < fanout) {
+    const int64_t o = i * fanout + k;
+    out_nbr[o] = pick >= 0 ? indices[pick] : (I)-1;
+    if (out_eid) out_eid[o] = (I)pick;
+  }
+  if (active && k == 0) out_cnt[i] = cnt;
+  if (out_total) {  // running total of sampled edges: one atomic per block, spread over kTotalSlots addresses
+    __shared__ int s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    int wsum = k == 0 ? cnt : 0;
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    if ((threadIdx.x & 31) == 0 && wsum > 0) atomicAdd(&s_sum, wsum);
+    __syncthreads();
+    if (threadIdx.x == 0 && s_sum > 0)
+      atomicAdd((unsigned long long*)out_total + (blockIdx.x & (kTotalSlots - 1)), (unsigned long long)s_sum);
   }
 }
 
@@ -192,6 +263,11 @@ static const void* dev_alias(const void* p, int uva) {
   return d;
 }
 
+#define DGLB_ELL_GROUP(G)                                                                                         \
+  sample_ell_group_kernel<I, G><<<(unsigned)((n_cap * G + 255) / 256), 256, 0, (cudaStream_t)stream>>>(            \
+      (const I*)ip, (const I*)ix, (const I*)seeds, n_cap, (const int64_t*)n_dev, fanout, (uint64_t)seed,           \
+      (const int64_t*)seed_dev, (I*)out_nbr, (I*)out_eid, (int32_t*)out_cnt, (int64_t*)out_total, pad_rows)
+
 DGLB_API int dglb200_cuda_sample_ell(int idtype, const void* indptr, const void* indices, int uva, const void* seeds,
                                      int64_t n_cap, const void* n_dev, int fanout, int64_t seed, const void* seed_dev,
                                      void* out_nbr, void* out_eid, void* out_cnt, void* out_total, int pad_rows,
@@ -202,9 +278,14 @@ DGLB_API int dglb200_cuda_sample_ell(int idtype, const void* indptr, const void*
   const void* ip = dev_alias(indptr, uva);
   const void* ix = dev_alias(indices, uva);
   DGLB_ID_SWITCH(idtype, I, {
-    sample_ell_kernel<I><<<(unsigned)((n_cap + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        (const I*)ip, (const I*)ix, (const I*)seeds, n_cap, (const int64_t*)n_dev, fanout, (uint64_t)seed,
-        (const int64_t*)seed_dev, (I*)out_nbr, (I*)out_eid, (int32_t*)out_cnt, (int64_t*)out_total, pad_rows);
+    if (fanout <= 8) DGLB_ELL_GROUP(8);
+    else if (fanout <= 16) DGLB_ELL_GROUP(16);
+    else if (fanout <= 32) DGLB_ELL_GROUP(32);
+    else
+      sample_ell_kernel<I><<<(unsigned)((n_cap + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+          (const I*)ip, (const I*)ix, (const I*)seeds, n_cap, (const int64_t*)n_dev, fanout, (uint64_t)seed,
+          (const int64_t*)seed_dev, (I*)out_nbr, (I*)out_eid, (int32_t*)out_cnt, (int64_t*)out_total, pad_rows);
+
   });
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH

@@ -95,7 +95,7 @@ class FusedSAGETrainer:
         # tensor-core path (tcgen05 fused gather+GEMM kernel): bf16, hidden % 32 == 0, feature rows padded to a
         # multiple of 64 elements (zero columns: mathematically identical, their weights receive zero gradient)
         if use_tc is None:
-            use_tc = dtype == torch.bfloat16 and hidden % 32 == 0 and hidden <= 256
+            use_tc = dtype == torch.bfloat16 and hidden % 64 == 0 and hidden <= 256
         self.use_tc = bool(use_tc)
         self.F_orig = feat.shape[1]
         if self.use_tc and feat.shape[1] % 64:
@@ -145,10 +145,17 @@ class FusedSAGETrainer:
     # ------------------------------------------------------------------ parameters
     def _alloc_params(self):
         dev = self.dev
+        # Layers that run on the tcgen05 kernel keep their weight in the K-major layout the tensor core wants:
+        # storage [n_pad, 2*in] (= W^T, output rows padded to the MMA N granularity, padding rows stay exactly 0).
+        # self.W / self.Wb / self.gW are [2*in, out] *views* of that storage, so everything else is layout agnostic.
+        self.tc_last = self.use_tc and self.C <= 64
+        self.tc_layer = [self.use_tc and (l < self.L - 1 or self.tc_last) for l in range(self.L)]
+        self.n_pad = [(64 if l == self.L - 1 else self.out_dims[l]) if self.tc_layer[l] else self.out_dims[l]
+                      for l in range(self.L)]
         segs = []
         off = 0
         for l in range(self.L):
-            k, n = 2 * self.in_dims[l], self.out_dims[l]
+            k, n = 2 * self.in_dims[l], self.n_pad[l]
             segs.append(("W", l, off, (k, n)))
             off += _pad8(k * n)
             segs.append(("b", l, off, (n,)))
@@ -159,16 +166,32 @@ class FusedSAGETrainer:
         self.adam_m = torch.zeros_like(self.param)
         self.adam_v = torch.zeros_like(self.param)
         self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=dev)
-        self.grad = torch.zeros(off, dtype=torch.float32, device=dev) if self.comm is None else self.comm.grad_buffer(off)
+        # flat gradient + 8 trailing words (loss, accuracy counter): one memset per step clears all of it
+        self.zero_block = (torch.zeros(off + 8, dtype=torch.float32, device=dev) if self.comm is None
+                           else self.comm.grad_buffer(off + 8))
+        self.grad = self.zero_block[:off]
+        self.loss_dev = self.zero_block[off:off + 1]
+        self.correct_dev = self.zero_block[off + 1:off + 2].view(torch.int32)
         gen = torch.Generator(device="cpu")
         gen.manual_seed(self.seed)
         gain = math.sqrt(2.0)
         self.W, self.b, self.Wb, self.gW, self.gb = [], [], [], [], []
+        self.Wt = [None] * self.L      # [n_pad, 2*in] bf16 K-major operand of the fused layer kernel
+        self.gWt = [None] * self.L     # gradient in the same layout
+        self.b_pad = [None] * self.L   # bias incl. padding entries
         for kind, l, o, shape in segs:
             n = int(torch.tensor(shape).prod())
-            view = self.param[o:o + n].view(*shape)
+            n_out = self.out_dims[l]
             if kind == "W":
-                k_in, n_out = self.in_dims[l], self.out_dims[l]
+                k2, npad = shape
+
+                def wview(buf, o=o, n=n, k2=k2, npad=npad, l=l, n_out=n_out):
+                    if self.tc_layer[l]:
+                        return buf[o:o + n].view(npad, k2).t()[:, :n_out]  # [2*in, out] strided view of W^T storage
+                    return buf[o:o + n].view(k2, npad)
+
+                view = wview(self.param)
+                k_in = self.in_dims[l]
                 # same init as SAGEConv: xavier_uniform(gain=relu) on fc_self.weight / fc_neigh.weight [out, in]
                 bound = gain * math.sqrt(6.0 / (k_in + n_out))
                 w_self = (torch.rand(n_out, k_in, generator=gen) * 2 - 1) * bound
@@ -178,16 +201,17 @@ class FusedSAGETrainer:
                     w_neigh[:, self.F_orig:] = 0
                 view.copy_(torch.cat([w_self.t(), w_neigh.t()], 0).to(dev))
                 self.W.append(view)
-                self.Wb.append(self.shadow[o:o + n].view(*shape) if self.dtype == torch.bfloat16 else view)
-                self.gW.append(self.grad[o:o + n].view(*shape))
+                self.Wb.append(wview(self.shadow) if self.dtype == torch.bfloat16 else view)
+                self.gW.append(wview(self.grad))
+                if self.tc_layer[l]:
+                    self.Wt[l] = self.shadow[o:o + n].view(npad, k2)
+                    self.gWt[l] = self.grad[o:o + n].view(npad, k2)
             else:
-                self.b.append(view)
-                self.gb.append(self.grad[o:o + n].view(*shape))
+                self.b.append(self.param[o:o + n][:n_out])
+                self.gb.append(self.grad[o:o + n][:n_out])
+                self.b_pad[l] = self.param[o:o + n]
         self.shadow.copy_(self.param)
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
-        # K-major (transposed) bf16 weights for the tcgen05 kernel, refreshed from the shadow every step
-        self.Wt = [torch.zeros((self.out_dims[l], 2 * self.in_dims[l]), dtype=torch.bfloat16, device=dev)
-                   if (self.use_tc and l < self.L - 1) else None for l in range(self.L)]
 
     def state_dict(self):
         return {"param": self.param.clone(), "m": self.adam_m.clone(), "v": self.adam_v.clone(),
@@ -302,9 +326,7 @@ class FusedSAGETrainer:
             else:
                 self.nbr[l] = self.nbr_g[l]
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.loss_dev = torch.zeros(1, dtype=torch.float32, device=dev)
-        self.edges_total = torch.zeros(1, dtype=torch.int64, device=dev)  # running count of sampled edges
-        self.correct_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.edges_total = torch.zeros(16, dtype=torch.int64, device=dev)  # running count of sampled edges
         # activations
         self.A = [None] * (L + 1)
         self.dH = [None] * (L + 1)
@@ -317,6 +339,9 @@ class FusedSAGETrainer:
         if self.use_tc:
             for l in range(1, L):
                 self.Hbuf[l] = torch.zeros((self.caps[l], self.out_dims[l - 1]), dtype=self.dtype, device=dev)
+        if self.tc_last:
+            self.logits_pad = torch.zeros((self.B, 64), dtype=torch.float32, device=dev)
+            self.dlogits16 = torch.zeros((self.B, 64), dtype=torch.bfloat16, device=dev)
 
     def _probe_mm(self):
         """Can torch.mm emit an fp32 result from bf16 operands (keeps dW in full precision)?"""
@@ -362,20 +387,21 @@ class FusedSAGETrainer:
         # ---------------- forward
         Hs = [None] * (L + 1)
         X = self.feat
-        if self.use_tc:
-            for l in range(L - 1):
-                self.Wt[l].copy_(self.Wb[l].t())
-                self._launch_count += 1
         for l in range(1, L + 1):
             cap, f, Fi = self.caps[l], self.fanouts[l - 1], self.in_dims[l - 1]
-            if self.use_tc and l < L:
-                # gather + mean + concat + GEMM + bias + ReLU + dropout in ONE tcgen05 kernel
-                self._launch("dglb200_engine_sage_layer_tc", "ppppp" + "l" + "iii" + "pppp" + "iflp", _p(X),
+            if self.tc_layer[l - 1]:
+                # gather + mean + concat + GEMM + bias (+ ReLU + dropout) in ONE tcgen05 kernel; the output layer
+                # emits fp32 logits (bias included) into a 64-column padded buffer
+                last = l == L
+                self._launch("dglb200_engine_sage_layer_tc", "ppppp" + "l" + "iii" + "pppp" + "iflpip", _p(X),
                              _p(self.S[1]) if l == 1 else 0, _p(self.nbr[l]), _p(self.cnt[l]), _p(self.n[l]), cap, f, Fi,
-                             self.out_dims[l - 1], _p(self.Wt[l - 1]), _p(self.b[l - 1]), _p(self.Hbuf[l]), _p(self.A[l]),
-                             1, float(self.p_drop), self.seed * 104729 + l, _p(self.step_dev))
-                Hs[l] = self.Hbuf[l]
-                X = self.Hbuf[l]
+                             self.n_pad[l - 1], _p(self.Wt[l - 1]), _p(self.b_pad[l - 1]),
+                             _p(self.logits_pad if last else self.Hbuf[l]), _p(self.A[l]), 0 if last else 1,
+                             0.0 if last else float(self.p_drop), self.seed * 104729 + l, _p(self.step_dev),
+                             1 if last else 0, 0)
+                if not last:
+                    Hs[l] = self.Hbuf[l]
+                    X = self.Hbuf[l]
                 continue
             self._launch("dglb200_engine_agg_concat", "iippppplii" + "pi", dt, it, _p(X), _p(self.S[1]) if l == 1 else 0,
                          _p(self.nbr[l]), _p(self.cnt[l]), _p(self.n[l]), cap, f, Fi, _p(self.A[l]), 0)
@@ -390,23 +416,31 @@ class FusedSAGETrainer:
             else:
                 logits = self._mm32(self.A[l], self.Wb[l - 1])
                 self._launch_count += 1
-        self.loss_dev.zero_()
-        self.correct_dev.zero_()
-        self._launch_count += 2
-        self._launch("dglb200_engine_ce_loss", "ppppplippp", _p(logits), _p(self.b[L - 1]), _p(self.labels),
-                     _p(self.S[L]), _p(self.n[L]), self.B, self.C, _p(self.dlogits), _p(self.loss_dev),
-                     _p(self.correct_dev))
-        # ---------------- backward
-        self.grad.zero_()
+        # one memset clears loss / accuracy counters and the whole flat gradient (they are adjacent views)
+        self.zero_block.zero_()
         self._launch_count += 1
-        dZ = self.dlogits
+        if self.tc_last:
+            self._launch("dglb200_engine_ce_loss2", "pipppplippipp" + "p", _p(self.logits_pad), 64, 0, _p(self.labels),
+                         _p(self.S[L]), _p(self.n[L]), self.B, self.C, 0, _p(self.dlogits16), 64, _p(self.gb[L - 1]),
+                         _p(self.loss_dev), _p(self.correct_dev))
+        else:
+            self._launch("dglb200_engine_ce_loss2", "pipppplippipp" + "p", _p(logits), self.C, _p(self.b[L - 1]),
+                         _p(self.labels), _p(self.S[L]), _p(self.n[L]), self.B, self.C, _p(self.dlogits), 0, 0,
+                         _p(self.gb[L - 1]), _p(self.loss_dev), _p(self.correct_dev))
+        # ---------------- backward
+        dZ = self.dlogits16 if self.tc_last else self.dlogits
         for l in range(L, 0, -1):
             cap, f, Fi = self.caps[l], self.fanouts[l - 1], self.in_dims[l - 1]
             A = self.A[l]
-            if l == L:
+            if self.tc_layer[l - 1]:
+                # weights live as W^T [n_pad, 2*in]: dW^T = dZ^T A, dA = dZ W^T - no transposes materialised
+                self.gWt[l - 1].copy_(self._mm32(dZ.t(), A))
+                self._launch_count += 2
+                dA = torch.mm(dZ, self.Wt[l - 1]) if l > 1 else None
+                dA_dt = dt
+            elif l == L:
                 self.gW[l - 1].copy_(torch.mm(A.float().t(), dZ))
-                self.gb[l - 1].copy_(dZ.sum(0))
-                self._launch_count += 5
+                self._launch_count += 3
                 dA = torch.mm(dZ, self.W[l - 1].t()) if l > 1 else None
                 dA_dt = dtype_code(torch.float32)
             else:
@@ -506,7 +540,7 @@ class FusedSAGETrainer:
 
     def total_sampled_edges(self):
         """Edges sampled since construction (device counter; syncs)."""
-        return int(self.edges_total.item())
+        return int(self.edges_total.sum().item())
 
     def sampled_edges_upper_bound(self):
         return sum(self.caps[l] * self.fanouts[l - 1] for l in range(1, self.L + 1))

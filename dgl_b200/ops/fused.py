@@ -12,7 +12,7 @@ def _p(t):
 
 
 def sage_layer_tc(X, self_ids, nbr, cnt, n_dev, Wt, bias, relu=True, p_drop=0.0, seed=0, step_dev=None, out=None,
-                  save_A=False, A_out=None):
+                  save_A=False, A_out=None, trace=None, out_f32=False):
     """out[d] = act([X[self(d)] | mean_k X[nbr[d,k]]] @ Wt^T + bias) for d < n_dev (tcgen05 + TMA + TMEM kernel).
 
     X: [rows, Fp] bf16 (Fp % 64 == 0); self_ids: int32 [n_cap] or None (identity); nbr: int32 [n_cap, fanout];
@@ -26,10 +26,30 @@ def sage_layer_tc(X, self_ids, nbr, cnt, n_dev, Wt, bias, relu=True, p_drop=0.0,
     if Wt.shape[1] != 2 * Fp:
         raise DGLError("Wt must be [Np, 2*Fp]")
     if out is None:
-        out = torch.empty((n_cap, Np), dtype=torch.bfloat16, device=X.device)
+        out = torch.empty((n_cap, Np), dtype=torch.float32 if out_f32 else torch.bfloat16, device=X.device)
     if save_A and A_out is None:
         A_out = torch.zeros((n_cap, 2 * Fp), dtype=torch.bfloat16, device=X.device)
-    loader.cuda_lib().fn("dglb200_engine_sage_layer_tc", "ppppp" + "l" + "iii" + "pppp" + "iflpp")(
+    loader.cuda_lib().fn("dglb200_engine_sage_layer_tc", "ppppp" + "l" + "iii" + "pppp" + "iflpipp")(
         _p(X), _p(self_ids), _p(nbr), _p(cnt), _p(n_dev), n_cap, fanout, Fp, Np, _p(Wt), _p(bias), _p(out), _p(A_out),
-        1 if relu else 0, float(p_drop), int(seed), _p(step_dev), loader.stream_ptr())
+        1 if relu else 0, float(p_drop), int(seed), _p(step_dev), 1 if out_f32 else 0, _p(trace), loader.stream_ptr())
     return out, A_out
+
+
+def sample_ell(indptr, indices, seeds, fanout, seed=0, n_dev=None, step_dev=None, return_eids=False, pad_rows=True):
+    """Uniform neighbour sampling without replacement into a dense ELL block (no host synchronisation).
+
+    indptr/indices: CSC of the graph (int32 or int64, on the device); seeds: [n_cap] ids (-1 = empty slot).
+    Returns (nbr [n_cap, fanout] padded with -1, cnt int32 [n_cap], eids or None, total int64 [1]).
+    Reference semantics: sampling/neighbor.py sample_neighbors(replace=False) / rowwise_sampling.cu:43-229."""
+    idt = indptr.dtype
+    n_cap = seeds.shape[0]
+    dev = seeds.device
+    nbr = torch.empty((n_cap, fanout), dtype=idt, device=dev)
+    eid = torch.empty((n_cap, fanout), dtype=idt, device=dev) if return_eids else None
+    cnt = torch.empty(n_cap, dtype=torch.int32, device=dev)
+    total = torch.zeros(16, dtype=torch.int64, device=dev)  # kTotalSlots partial sums
+    from ..base import id_code
+    loader.cuda_lib().fn("dglb200_cuda_sample_ell", "ippiplpilpppppi" + "p")(
+        id_code(idt), _p(indptr), _p(indices), 0, _p(seeds.to(idt).contiguous()), n_cap, _p(n_dev), fanout, int(seed),
+        _p(step_dev), _p(nbr), _p(eid), _p(cnt), _p(total), 1 if pad_rows else 0, loader.stream_ptr())
+    return nbr, cnt, eid, total.sum(0, keepdim=True)

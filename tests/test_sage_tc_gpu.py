@@ -34,3 +34,36 @@ def test_sage_layer_tc(Fp, Np, ncap, nvalid, fan, use_self):
     err = (out[:nvalid].float() - ref[:nvalid]).abs().max().item()
     scale = ref[:nvalid].abs().max().item()
     assert err < 2e-2 * max(scale, 1.0), (err, scale)
+
+
+def test_sage_layer_tc_dropout():
+    """Dropout in the epilogue: kept entries are the no-dropout values times 1/(1-p), the rest exactly 0."""
+    from dgl_b200.ops.fused import sage_layer_tc
+    torch.manual_seed(1)
+    rows, Fp, Np, n, fan, p = 4000, 128, 256, 20000, 10, 0.25
+    X = (torch.randn(rows, Fp, device=DEV) * 0.5).bfloat16()
+    nbr = torch.randint(0, rows, (n, fan), device=DEV, dtype=torch.int32)
+    cnt = torch.full((n,), fan, device=DEV, dtype=torch.int32)
+    self_ids = torch.randint(0, rows, (n,), device=DEV, dtype=torch.int32)
+    n_dev = torch.tensor([n], device=DEV, dtype=torch.int64)
+    Wt = (torch.randn(Np, 2 * Fp, device=DEV) * 0.05).bfloat16()
+    bias = torch.randn(Np, device=DEV).abs() + 0.5  # mostly positive outputs so zeros come from dropout
+    base, _ = sage_layer_tc(X, self_ids, nbr, cnt, n_dev, Wt, bias, relu=True)
+    step = torch.tensor([5], device=DEV, dtype=torch.int64)
+    d1, _ = sage_layer_tc(X, self_ids, nbr, cnt, n_dev, Wt, bias, relu=True, p_drop=p, seed=3, step_dev=step)
+    d2, _ = sage_layer_tc(X, self_ids, nbr, cnt, n_dev, Wt, bias, relu=True, p_drop=p, seed=3, step_dev=step)
+    step += 1
+    d3, _ = sage_layer_tc(X, self_ids, nbr, cnt, n_dev, Wt, bias, relu=True, p_drop=p, seed=3, step_dev=step)
+    torch.cuda.synchronize()
+    assert torch.equal(d1, d2)          # counter-based: same (seed, step) -> same mask
+    assert not torch.equal(d1, d3)      # new step -> new mask
+    pos = base.float() > 0.05
+    dropped = (d1.float() == 0) & pos
+    frac = dropped.float().sum() / pos.float().sum()
+    assert abs(frac.item() - p) < 0.01, frac
+    kept = pos & ~dropped
+    ratio = d1.float()[kept] / base.float()[kept]
+    assert (ratio - 1.0 / (1.0 - p)).abs().max() < 0.02
+    # masks must not be correlated along rows or columns
+    m = dropped.float()
+    assert abs(m.mean(0).std().item()) < 0.02 and abs(m.mean(1).std().item()) < 0.05

@@ -1,0 +1,65 @@
+"""GPU sampling kernels: ELL neighbour sampler invariants (uniform, without replacement)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _csc(n, m, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    src = torch.randint(0, n, (m,), generator=g)
+    dst = (torch.rand(m, generator=g) ** 3 * n).long().clamp(max=n - 1)  # skewed in-degrees incl. hubs and isolated nodes
+    order = torch.argsort(dst, stable=True)
+    src, dst = src[order], dst[order]
+    indptr = torch.zeros(n + 1, dtype=torch.int64)
+    indptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n), 0)
+    return indptr, src
+
+
+@pytest.mark.parametrize("idtype", [torch.int32, torch.int64])
+@pytest.mark.parametrize("fanout", [3, 8, 10, 16, 25, 32, 40])
+def test_sample_ell_invariants(idtype, fanout):
+    from dgl_b200.ops.fused import sample_ell
+    n, m = 3000, 60000
+    indptr, indices = _csc(n, m, seed=fanout)
+    ip, ix = indptr.to(DEV, idtype), indices.to(DEV, idtype)
+    seeds = torch.randint(0, n, (2000,), generator=torch.Generator().manual_seed(1)).to(DEV, idtype)
+    seeds[5] = -1  # empty slot
+    n_dev = torch.tensor([1900], device=DEV, dtype=torch.int64)
+    nbr, cnt, eid, total = sample_ell(ip, ix, seeds, fanout, seed=42, n_dev=n_dev, return_eids=True)
+    torch.cuda.synchronize()
+    nbr, cnt, eid, seeds_c = nbr.cpu().long(), cnt.cpu().long(), eid.cpu().long(), seeds.cpu().long()
+    assert int(total.item()) == int(cnt[:1900].sum())
+    assert (cnt[1900:] == 0).all() and (nbr[1900:] == -1).all()
+    deg = indptr[1:] - indptr[:-1]
+    for i in range(1900):
+        v = int(seeds_c[i])
+        if v < 0:
+            assert cnt[i] == 0 and (nbr[i] == -1).all()
+            continue
+        d = int(deg[v])
+        c = int(cnt[i])
+        assert c == min(d, fanout)
+        e = eid[i, :c]
+        assert len(set(e.tolist())) == c  # without replacement
+        assert ((e >= indptr[v]) & (e < indptr[v + 1])).all()
+        assert torch.equal(indices[e], nbr[i, :c])
+        assert (nbr[i, c:] == -1).all()
+
+
+def test_sample_ell_uniform():
+    """Each in-edge of a hub must be picked with probability fanout/deg."""
+    from dgl_b200.ops.fused import sample_ell
+    deg, fanout, reps = 50, 10, 20000
+    indptr = torch.tensor([0, deg], dtype=torch.int32, device=DEV)
+    indices = torch.arange(deg, dtype=torch.int32, device=DEV)
+    seeds = torch.zeros(reps, dtype=torch.int32, device=DEV)
+    nbr, cnt, _, _ = sample_ell(indptr, indices, seeds, fanout, seed=7)
+    hist = torch.bincount(nbr.flatten().long(), minlength=deg).float() / reps
+    assert (cnt == fanout).all()
+    assert (hist - fanout / deg).abs().max() < 0.02, hist
+    # a different step counter gives a different draw
+    step = torch.tensor([3], dtype=torch.int64, device=DEV)
+    nbr2, _, _, _ = sample_ell(indptr, indices, seeds, fanout, seed=7, step_dev=step)
+    assert not torch.equal(nbr, nbr2)
