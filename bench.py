@@ -225,9 +225,11 @@ def run_ours(args):
             tr.step_async(next(it))  # pinned ring slot -> H2D -> CUDA-graph replay; host never waits
 
     def loop_e2e():
-        for _ in range(args.steps):
-            loss = tr.train_step(next(it))  # pinned seeds -> H2D -> step -> D2H loss -> host float
-        return loss
+        # public API, pipelined: per step pinned seeds -> H2D -> step -> D2H loss into pinned memory -> host float
+        # (the host reads step i's loss while step i+3 is already enqueued)
+        losses = tr.fit(next(it) for _ in range(args.steps))
+        assert len(losses) == args.steps and all(l == l for l in losses)
+        return losses[-1]
 
     torch.cuda.profiler.start()  # no-op unless run under `ncu --profile-from-start off`
     ms = timed(dev, loop_async)
@@ -261,7 +263,7 @@ def run_ours(args):
             "clocks": clk,
             "e2e": {"value": edges_e2e / (ms_e2e / 1e3), "unit": "edges/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": (BATCH + 2) * 4, "d2h_bytes_per_step": 4,
-                    "note": "per step: host writes seeds to pinned memory, H2D copy, fused step, D2H loss, host sync"},
+                    "note": "FusedSAGETrainer.fit(): per step the host writes seeds to pinned memory, H2D copy, fused step, D2H loss to pinned memory, host reads every loss (3 steps behind the enqueue)"},
             "gpu_launches": tr.gpu_launches_per_step * args.steps,
             "gpu_launches_per_step": {"own_kernels": tr.gpu_launches_per_step, "all_nodes": tr.total_launches_per_step},
         }

@@ -25,7 +25,8 @@ __global__ void __launch_bounds__(128) sample_ell_kernel(const I* __restrict__ i
                                                          int pad_rows) {
   const int64_t n = n_dev ? min(*n_dev, n_cap) : n_cap;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const bool active = pad_rows ? (i < n_cap) : (i < n);
+  const bool active = (pad_rows & 1) ? (i < n_cap) : (i < n);
+  const uint64_t pos_key = (pad_rows & 2) ? 0ull : (uint64_t)i;
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0xD6E8FEB86659FD93ull;  // per-step stream under graph replay
   I* nb = out_nbr + i * fanout;
   I* ne = out_eid ? out_eid + i * fanout : nullptr;
@@ -45,7 +46,7 @@ __global__ void __launch_bounds__(128) sample_ell_kernel(const I* __restrict__ i
         uint32_t chosen[kMaxFloyd];
         int m = 0;
         for (int64_t j = deg - fanout; j < deg; ++j, ++m) {
-          uint32_t t = rng_below(seed, (uint64_t)v * 0x9E37ull + (uint64_t)i, (uint64_t)m, (uint32_t)(j + 1));
+          uint32_t t = rng_below(seed, (uint64_t)v * 0x9E37ull + pos_key, (uint64_t)m, (uint32_t)(j + 1));
           bool dup = false;
           for (int q = 0; q < m; ++q) dup |= (chosen[q] == t);
           chosen[m] = dup ? (uint32_t)j : t;
@@ -88,7 +89,8 @@ __global__ void __launch_bounds__(256) sample_ell_group_kernel(const I* __restri
   const int64_t gtid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t i = gtid / G;
   const int k = (int)(gtid % G);
-  const bool active = pad_rows ? (i < n_cap) : (i < n);
+  const bool active = (pad_rows & 1) ? (i < n_cap) : (i < n);
+  const uint64_t pos_key = (pad_rows & 2) ? 0ull : (uint64_t)i;  // bit 1: picks depend on the node only, not on its row
   if (seed_dev) seed += (uint64_t)(*seed_dev) * 0xD6E8FEB86659FD93ull;  // per-step stream under graph replay
   int cnt = 0;
   int64_t pick = -1;  // CSR position of this lane's neighbour
@@ -104,7 +106,7 @@ __global__ void __launch_bounds__(256) sample_ell_group_kernel(const I* __restri
   uint32_t t = 0, val = 0, j = 0;
   if (floyd && k < fanout) {
     j = (uint32_t)(deg - fanout + k);
-    t = rng_below(seed, (uint64_t)v * 0x9E37ull + (uint64_t)i, (uint64_t)k, j + 1);
+    t = rng_below(seed, (uint64_t)v * 0x9E37ull + pos_key, (uint64_t)k, j + 1);
     val = t;
   }
   bool dup = false;

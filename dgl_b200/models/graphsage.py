@@ -315,13 +315,12 @@ class FusedSAGETrainer:
                 hcap = 16
                 while hcap < 2 * N + 2:
                     hcap <<= 1
-                sb = int(self.lib.raw("dglb200_cuda_scan_temp_bytes", ctypes.c_int64, [ctypes.c_int64])(N))
-                self.ws[l] = dict(keys=torch.empty(hcap, dtype=i32, device=dev),
-                                  minpos=torch.empty(hcap, dtype=i32, device=dev),
-                                  local=torch.empty(hcap, dtype=i32, device=dev), cap=hcap,
-                                  work=torch.empty((3, N), dtype=i32, device=dev),
-                                  temp=torch.empty(max(sb, 1), dtype=torch.uint8, device=dev), sb=sb)
-                self.S[l - 1] = torch.empty(out_cap, dtype=i32, device=dev)
+                # hash table of the cooperative frontier-compaction kernel (left clean by every call)
+                self.ws[l] = dict(keys=torch.full((hcap,), -1, dtype=i32, device=dev),
+                                  vals=torch.full((hcap,), -2, dtype=i32, device=dev), cap=hcap,
+                                  slot=torch.empty(N, dtype=i32, device=dev),
+                                  counter=torch.zeros(1, dtype=i32, device=dev))
+                self.S[l - 1] = torch.full((out_cap,), -1, dtype=i32, device=dev)
                 self.nbr[l] = torch.empty((cap, f), dtype=i32, device=dev)
             else:
                 self.nbr[l] = self.nbr_g[l]
@@ -375,15 +374,13 @@ class FusedSAGETrainer:
             cap, f = self.caps[l], self.fanouts[l - 1]
             self._launch("dglb200_cuda_sample_ell", "ippiplpilpppppi", it, _p(self.indptr), _p(self.indices), 0,
                          _p(self.S[l]), cap, _p(self.n[l]), f, self.seed * 7919 + l, _p(self.step_dev),
-                         _p(self.nbr_g[l]), 0, _p(self.cnt[l]), _p(self.edges_total), 1 if l > 1 else 0)
+                         _p(self.nbr_g[l]), 0, _p(self.cnt[l]), _p(self.edges_total), (1 if l > 1 else 0) | 2)
             if l > 1:
                 w = self.ws[l]
-                self._launch("dglb200_cuda_unique_compact", "iplplppppl" + "pppplppplp", it, _p(self.S[l]), cap,
-                             _p(self.nbr_g[l]), cap * f, 0, _p(w["keys"]), _p(w["minpos"]), _p(w["local"]), w["cap"],
-                             _p(w["work"][0]), _p(w["work"][1]), _p(w["work"][2]), _p(w["temp"]), w["sb"],
-                             _p(self.S[l - 1]), _p(self.nbr[l]), _p(self.n[l - 1]), self.caps[l - 1],
-                             _p(self.overflow), kernels=5)
-                self._launch_count += 5  # 3 memsets + 2 cub scan kernels
+                self._launch("dglb200_frontier_compact", "pplpipplpplpppp", _p(self.S[l]), _p(self.n[l]), cap,
+                             _p(self.nbr_g[l]), f, _p(w["keys"]), _p(w["vals"]), w["cap"], _p(w["slot"]),
+                             _p(self.S[l - 1]), self.caps[l - 1], _p(self.nbr[l]), _p(self.n[l - 1]), _p(w["counter"]),
+                             _p(self.overflow))
         # ---------------- forward
         Hs = [None] * (L + 1)
         X = self.feat
@@ -537,6 +534,39 @@ class FusedSAGETrainer:
 
     def last_loss(self):
         return float(self.loss_pinned[0])
+
+    def fit(self, batches, on_step=None):
+        """Pipelined training over an iterable of seed batches; returns the list of per-step losses.
+
+        Every step still copies its seeds from pinned host memory to the device and its loss back into pinned host
+        memory, but the host reads the loss of step ``i`` only after it has enqueued step ``i + RING - 1``, so the
+        CPU never idles the GPU (the reference's loop reads ``loss.item()`` synchronously,
+        examples/multigpu/node_classification_sage.py:229-256). ``on_step(i, loss)`` is called as losses arrive."""
+        import collections
+        if not hasattr(self, "loss_ring"):
+            self.loss_ring = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(self.RING)]
+        pending = collections.deque()
+        losses = []
+
+        def drain_one():
+            k, ev = pending.popleft()
+            ev.synchronize()
+            losses.append(float(self.loss_ring[k][0]))
+            if on_step is not None:
+                on_step(len(losses) - 1, losses[-1])
+
+        for i, seeds in enumerate(batches):
+            if len(pending) == self.RING:
+                drain_one()
+            self.step_async(seeds)
+            k = i % self.RING
+            self.loss_ring[k].copy_(self.loss_dev, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            pending.append((k, ev))
+        while pending:
+            drain_one()
+        return losses
 
     def total_sampled_edges(self):
         """Edges sampled since construction (device counter; syncs)."""

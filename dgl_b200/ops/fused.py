@@ -53,3 +53,35 @@ def sample_ell(indptr, indices, seeds, fanout, seed=0, n_dev=None, step_dev=None
         id_code(idt), _p(indptr), _p(indices), 0, _p(seeds.to(idt).contiguous()), n_cap, _p(n_dev), fanout, int(seed),
         _p(step_dev), _p(nbr), _p(eid), _p(cnt), _p(total), 1 if pad_rows else 0, loader.stream_ptr())
     return nbr, cnt, eid, total.sum(0, keepdim=True)
+
+
+class FrontierCompactor:
+    """Workspace + launcher of the cooperative frontier-compaction kernel (csrc/cuda/frontier.cu).
+
+    ``compact(first, n_first_dev, nbr_global)`` returns (nodes [out_cap] = first ++ new ids (order of the new ids is
+    unspecified) padded with -1, nbr_local like nbr_global, count int64[1] on the device, overflow int32[1]).
+    Same contract as to_block / unique_and_compact (transforms/functional.py to_block) minus the ordering of new ids."""
+
+    def __init__(self, first_cap, fanout, out_cap, device):
+        N = first_cap * (1 + fanout)
+        hcap = 16
+        while hcap < 2 * N + 2:
+            hcap <<= 1
+        i32 = torch.int32
+        self.first_cap, self.fanout, self.out_cap, self.hcap = first_cap, fanout, out_cap, hcap
+        self.keys = torch.full((hcap,), -1, dtype=i32, device=device)
+        self.vals = torch.full((hcap,), -2, dtype=i32, device=device)
+        self.slot = torch.empty(N, dtype=i32, device=device)
+        self.counter = torch.zeros(1, dtype=i32, device=device)
+        self.overflow = torch.zeros(1, dtype=i32, device=device)
+
+    def compact(self, first, n_first_dev, nbr_global):
+        dev = first.device
+        nodes = torch.full((self.out_cap,), -1, dtype=torch.int32, device=dev)
+        nbr_local = torch.empty_like(nbr_global)
+        count = torch.zeros(1, dtype=torch.int64, device=dev)
+        loader.cuda_lib().fn("dglb200_frontier_compact", "pplpipplpplpppp" + "p")(
+            _p(first), _p(n_first_dev), self.first_cap, _p(nbr_global), self.fanout, _p(self.keys), _p(self.vals),
+            self.hcap, _p(self.slot), _p(nodes), self.out_cap, _p(nbr_local), _p(count), _p(self.counter),
+            _p(self.overflow), loader.stream_ptr())
+        return nodes, nbr_local, count, self.overflow

@@ -63,3 +63,33 @@ def test_sample_ell_uniform():
     step = torch.tensor([3], dtype=torch.int64, device=DEV)
     nbr2, _, _, _ = sample_ell(indptr, indices, seeds, fanout, seed=7, step_dev=step)
     assert not torch.equal(nbr, nbr2)
+
+
+@pytest.mark.parametrize("first_cap,nf,fan,universe", [(1000, 900, 10, 5000), (64, 64, 3, 50000), (5000, 4321, 7, 30000)])
+def test_frontier_compact(first_cap, nf, fan, universe):
+    from dgl_b200.ops.fused import FrontierCompactor
+    g = torch.Generator().manual_seed(3)
+    first = torch.randperm(universe, generator=g)[:first_cap].to(DEV, torch.int32)
+    nbr = torch.randint(0, universe, (first_cap, fan), generator=g).to(DEV, torch.int32)
+    nbr[torch.rand(first_cap, fan, generator=g).to(DEV) < 0.2] = -1  # padding inside rows
+    n_dev = torch.tensor([nf], device=DEV, dtype=torch.int64)
+    out_cap = first_cap * (1 + fan)
+    fc = FrontierCompactor(first_cap, fan, out_cap, DEV)
+    for rep in range(3):  # the table must come back clean: repeated calls give consistent results
+        nodes, loc, count, ovf = fc.compact(first, n_dev, nbr)
+        torch.cuda.synchronize()
+        c = int(count.item())
+        live = nbr[:nf]
+        expect = torch.unique(torch.cat([first[:nf].long(), live[live >= 0].long()]))
+        assert c == expect.numel() and int(ovf.item()) == 0
+        assert torch.equal(nodes[:nf], first[:nf])                       # dst nodes are a prefix
+        assert torch.equal(torch.sort(nodes[:c].long()).values, expect)   # exactly the unique set
+        assert (nodes[c:] == -1).all()
+        valid = live >= 0
+        assert torch.equal(nodes[loc[:nf][valid].long()], live[valid])   # relabel is consistent
+        assert (loc[:nf][~valid] == -1).all() and (loc[nf:] == -1).all()
+        assert (fc.keys == -1).all() and (fc.vals == -2).all() and int(fc.counter.item()) == 0
+    # capacity overflow is flagged and clamps the count
+    fc2 = FrontierCompactor(first_cap, fan, nf + 5, DEV)
+    nodes, loc, count, ovf = fc2.compact(first, n_dev, nbr)
+    assert int(count.item()) == nf + 5 and int(ovf.item()) == 1
