@@ -55,7 +55,7 @@ def rmat_graph(num_nodes, num_edges, symmetrize=False, seed=0, device="cpu", idt
 def shaped_dataset(name, device="cpu", seed=0, idtype=torch.int32, feat_dtype=torch.float32, scale=1.0,
                    train_frac=0.0803):
     """Random-init dataset with the node/edge/feature/class counts of ``name`` (optionally scaled down).
-    Returns (graph, feat, labels, train_idx)."""
+    Returns (graph, feat, labels, train_idx, num_classes)."""
     n, e, f, c, sym = SHAPES[name]
     n = max(64, int(n * scale))
     e = max(256, int(e * scale))

@@ -1,0 +1,37 @@
+"""The example scripts (one per BASELINE config) must run end to end on CPU at toy scale."""
+import os
+import runpy
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _run(script, *argv):
+    old = sys.argv
+    sys.argv = [script, *argv]
+    try:
+        return runpy.run_path(os.path.join(ROOT, "examples", script), run_name="__main__")
+    finally:
+        sys.argv = old
+
+
+def test_gcn_cora_cpu():
+    _run("gcn_cora.py", "--epochs", "3")
+
+
+def test_gat_fullgraph_cpu():
+    _run("gat_fullgraph.py", "--epochs", "1", "--heads", "2")
+
+
+def test_rgcn_hetero_cpu():
+    _run("rgcn_hetero.py", "--epochs", "1", "--scale", "0.0005", "--hidden", "8")
+
+
+def test_graphsage_graphbolt_cpu():
+    _run("graphsage_graphbolt.py", "--steps", "2", "--scale", "0.00005", "--batch-size", "64", "--fanout", "3,3")
+
+
+def test_graphsage_dist_standalone(tmp_path):
+    _run("graphsage_dist.py", "--epochs", "1", "--out", str(tmp_path))
