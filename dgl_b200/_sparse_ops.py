@@ -132,7 +132,7 @@ def _split_meta(indptr):
     return meta
 
 
-def _gspmm_balanced(csr, ufeat2d, ew, num_dst, F):
+def _gspmm_balanced(csr, ufeat2d, ew, num_dst, F, heads=1):
     indptr, indices, eids = csr
     meta = _split_meta(indptr)
     if ew is not None and eids is not None:
@@ -150,7 +150,7 @@ def _gspmm_balanced(csr, ufeat2d, ew, num_dst, F):
     else:
         args = (0, 0, 0, 0, 0, 0, 0)
     lib.fn("dglb200_cuda_gspmm_balanced", "iiippplppp" + "ll" + "ppp" + "l" + "p" + "l" + "pp")(
-        1 if ew is not None else 0, dtype_code(ufeat2d.dtype), id_code(indptr.dtype), _p(indptr), _p(indices), _p(eids),
+        (max(1, int(heads)) if ew is not None else 0), dtype_code(ufeat2d.dtype), id_code(indptr.dtype), _p(indptr), _p(indices), _p(eids),
         num_dst, _p(ufeat2d), _p(ew), _p(out), F, SPLIT_DEG, *args, loader.stream_ptr())
     return out
 
@@ -171,8 +171,10 @@ def gspmm(csr, op, reduce_op, ufeat, efeat, num_dst):
     # hot path on CUDA: copy_u / u_mul_e(scalar) with sum -> load-balanced vector kernel
     if (ref.is_cuda and reduce_op == "sum" and num_dst > 0 and F > 0 and ref.dtype != torch.float64
             and (F * ref.element_size()) % 4 == 0
-            and (op == "copy_lhs" or (op == "mul" and bc[3] == 1 and bc[0] == 1 and bc[1] == F))):
-        out = _gspmm_balanced(csr, l2, r2 if op == "mul" else None, num_dst, F)
+            and (op == "copy_lhs" or (op == "mul" and bc[0] == 1 and bc[1] == F and
+                                      (bc[3] == 1 or (bc[2] * bc[3] == F and (bc[2] * ref.element_size()) % 4 == 0))))):
+        # u_mul_e with one scalar per edge, or one scalar per (edge, head) - the GAT aggregation
+        out = _gspmm_balanced(csr, l2, r2 if op == "mul" else None, num_dst, F, heads=bc[3] if op == "mul" else 1)
         return out.reshape(num_dst, *out_shape), None, None
     out = torch.empty((num_dst, F), dtype=ref.dtype, device=ref.device)
     arg_u = arg_e = None
@@ -264,11 +266,35 @@ def edge_softmax_forward(csc, score, num_dst):
     if num_dst > 0 and s2.numel() > 0:
         lib, is_cuda = _dev_lib(score)
         args = [dtype_code(score.dtype), id_code(indptr.dtype), _p(indptr), _p(eids), num_dst, _p(s2), _p(out), F]
-        if is_cuda:
+        if is_cuda and score.dtype != torch.float64:
+            work = _softmax_work(score)
+            if eids is not None and s2.shape[0] >= _PERMUTE_MIN_EDGES:
+                # large graph whose edge ids are not in CSC order: one gather brings the scores into CSC order, the
+                # three softmax passes then stream sequentially, one scatter puts the result back (2 random passes
+                # over the edge data instead of 4)
+                from .ops.cuda_struct import gather_rows, scatter_rows
+                s_csc = gather_rows(s2, eids)
+                o_csc = torch.empty_like(s_csc)
+                lib.fn("dglb200_cuda_edge_softmax_fwd2", "iipplpplplp")(
+                    args[0], args[1], _p(indptr), 0, num_dst, _p(s_csc), _p(o_csc), F, _p(work), work.numel(),
+                    loader.stream_ptr())
+                scatter_rows(out, eids, o_csc)
+            else:
+                lib.fn("dglb200_cuda_edge_softmax_fwd2", "iipplpplplp")(*args, _p(work), work.numel(),
+                                                                        loader.stream_ptr())
+        elif is_cuda:
             lib.fn("dglb200_cuda_edge_softmax_fwd", "iipplpplp")(*args, loader.stream_ptr())
         else:
             lib.fn("dglb200_cpu_edge_softmax_fwd", "iipplppl")(*args)
     return out.reshape(score.shape)
+
+
+_PERMUTE_MIN_EDGES = 1 << 20
+
+
+def _softmax_work(score):
+    """int32 work list for hub rows (> 2048 in-edges): [count, row ids...]; E/2048 + 2 entries always suffice."""
+    return torch.empty(score.shape[0] // 2048 + 2, dtype=torch.int32, device=score.device)
 
 
 def edge_softmax_backward(csc, out, grad_out, num_dst):
@@ -280,7 +306,20 @@ def edge_softmax_backward(csc, out, grad_out, num_dst):
     if num_dst > 0 and o2.numel() > 0:
         lib, is_cuda = _dev_lib(out)
         args = [dtype_code(out.dtype), id_code(indptr.dtype), _p(indptr), _p(eids), num_dst, _p(o2), _p(g2), _p(gs), F]
-        if is_cuda:
+        if is_cuda and out.dtype != torch.float64:
+            work = _softmax_work(out)
+            if eids is not None and o2.shape[0] >= _PERMUTE_MIN_EDGES:
+                from .ops.cuda_struct import gather_rows, scatter_rows
+                o_csc, g_csc = gather_rows(o2, eids), gather_rows(g2, eids)
+                gs_csc = torch.empty_like(o_csc)
+                lib.fn("dglb200_cuda_edge_softmax_bwd2", "iipplppplplp")(
+                    args[0], args[1], _p(indptr), 0, num_dst, _p(o_csc), _p(g_csc), _p(gs_csc), F, _p(work),
+                    work.numel(), loader.stream_ptr())
+                scatter_rows(gs, eids, gs_csc)
+            else:
+                lib.fn("dglb200_cuda_edge_softmax_bwd2", "iipplppplplp")(*args, _p(work), work.numel(),
+                                                                         loader.stream_ptr())
+        elif is_cuda:
             lib.fn("dglb200_cuda_edge_softmax_bwd", "iipplppplp")(*args, loader.stream_ptr())
         else:
             lib.fn("dglb200_cpu_edge_softmax_bwd", "iipplpppl")(*args)

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ ind
                                                        const I* __restrict__ eids, int64_t num_rows,
                                                        const T* __restrict__ x, const T* __restrict__ w,
                                                        T* __restrict__ out, int64_t F, int nvec, int sub,
-                                                       int64_t max_deg) {
+                                                       int64_t max_deg, int wH, int vph) {
   using VO = VecOps<T, VB>;
   using V = typename VO::V;
   constexpr int VE = VO::VE;
@@ -70,6 +70,9 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ ind
   if (row >= num_rows) return;
   const int lane = threadIdx.x % sub;
   const int vbase = blockIdx.y * sub * NV + lane;  // first vector owned by this lane
+  int hd[NV];  // weight column (attention head) of each owned vector; wH == 1: one scalar per edge
+#pragma unroll
+  for (int j = 0; j < NV; ++j) hd[j] = wH > 1 ? min(vbase + j * sub, nvec - 1) / vph : 0;
   float acc[NV][VE];
 #pragma unroll
   for (int j = 0; j < NV; ++j)
@@ -81,12 +84,13 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ ind
   int64_t p = s;
   for (; p + U <= t; p += U) {
     int64_t u[U];
-    float wt[U];
+    float wt[U][NV];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       u[k] = indices[p + k];
-      if (HAS_W) wt[k] = to_f<T>(w[eids ? (int64_t)eids[p + k] : p + k]);
-      else wt[k] = 1.f;
+      const int64_t eidx = (eids ? (int64_t)eids[p + k] : p + k) * wH;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) wt[k][j] = HAS_W ? to_f<T>(w[eidx + hd[j]]) : 1.f;
     }
     V v[U][NV];
 #pragma unroll
@@ -102,18 +106,18 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ ind
     for (int k = 0; k < U; ++k)
 #pragma unroll
       for (int j = 0; j < NV; ++j)
-        if (vbase + j * sub < nvec) VO::fma(acc[j], v[k][j], wt[k]);
+        if (vbase + j * sub < nvec) VO::fma(acc[j], v[k][j], wt[k][j]);
   }
   for (; p < t; ++p) {
     const int64_t u = indices[p];
-    const float wt = HAS_W ? to_f<T>(w[eids ? (int64_t)eids[p] : p]) : 1.f;
+    const int64_t eidx = (eids ? (int64_t)eids[p] : p) * wH;
     const V* xr = reinterpret_cast<const V*>(x + u * F);
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
       const int c = vbase + j * sub;
       if (c < nvec) {
         V v = ldg_vec(xr + c);
-        VO::fma(acc[j], v, wt);
+        VO::fma(acc[j], v, HAS_W ? to_f<T>(w[eidx + hd[j]]) : 1.f);
       }
     }
   }
@@ -176,20 +180,21 @@ static int pow2_ge(int64_t x, int cap) {
 
 template <typename T, typename I, int VB, bool HAS_W>
 void launch_vec(const I* indptr, const I* indices, const I* eids, int64_t n, const T* x, const T* w, T* out, int64_t F,
-                cudaStream_t st, int64_t max_deg = 0) {
+                cudaStream_t st, int64_t max_deg = 0, int wH = 1) {
   constexpr int VE = VB / sizeof(T);
   const int nvec = (int)(F / VE);
+  const int vph = wH > 1 ? nvec / wH : nvec;  // vectors per head
   const int sub = pow2_ge(nvec, 32);
   const int rows_per_block = 256 / sub;
   const unsigned gx = (unsigned)((n + rows_per_block - 1) / rows_per_block);
   const int per_lane = (nvec + sub - 1) / sub;
   if (per_lane <= 1) {
-    spmm_vec_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg);
+    spmm_vec_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg, wH, vph);
   } else if (per_lane <= 2) {
-    spmm_vec_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg);
+    spmm_vec_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg, wH, vph);
   } else {
     const unsigned gy = (unsigned)((nvec + sub * 4 - 1) / (sub * 4));
-    spmm_vec_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg);
+    spmm_vec_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg, wH, vph);
   }
 }
 
@@ -205,7 +210,8 @@ __global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ i
                                                          const int64_t* __restrict__ item_start,
                                                          const int32_t* __restrict__ item_len, int64_t num_items,
                                                          const T* __restrict__ x, const T* __restrict__ w,
-                                                         float* __restrict__ scratch, int64_t F, int nvec, int sub) {
+                                                         float* __restrict__ scratch, int64_t F, int nvec, int sub,
+                                                         int wH, int vph) {
   using VO = VecOps<T, VB>;
   using V = typename VO::V;
   constexpr int VE = VO::VE;
@@ -215,6 +221,9 @@ __global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ i
   if (item >= num_items) return;
   const int lane = threadIdx.x % sub;
   const int vbase = blockIdx.y * sub * NV + lane;
+  int hd[NV];
+#pragma unroll
+  for (int j = 0; j < NV; ++j) hd[j] = wH > 1 ? min(vbase + j * sub, nvec - 1) / vph : 0;
   float acc[NV][VE];
 #pragma unroll
   for (int j = 0; j < NV; ++j)
@@ -224,11 +233,13 @@ __global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ i
   int64_t p = s;
   for (; p + U <= t; p += U) {
     int64_t u[U];
-    float wt[U];
+    float wt[U][NV];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       u[k] = indices[p + k];
-      wt[k] = HAS_W ? to_f<T>(w[eids ? (int64_t)eids[p + k] : p + k]) : 1.f;
+      const int64_t eidx = (eids ? (int64_t)eids[p + k] : p + k) * wH;
+#pragma unroll
+      for (int j = 0; j < NV; ++j) wt[k][j] = HAS_W ? to_f<T>(w[eidx + hd[j]]) : 1.f;
     }
     V v[U][NV];
 #pragma unroll
@@ -242,17 +253,17 @@ __global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ i
     for (int k = 0; k < U; ++k)
 #pragma unroll
       for (int j = 0; j < NV; ++j)
-        if (vbase + j * sub < nvec) VO::fma(acc[j], v[k][j], wt[k]);
+        if (vbase + j * sub < nvec) VO::fma(acc[j], v[k][j], wt[k][j]);
   }
   for (; p < t; ++p) {
     const int64_t u = indices[p];
-    const float wt = HAS_W ? to_f<T>(w[eids ? (int64_t)eids[p] : p]) : 1.f;
+    const int64_t eidx = (eids ? (int64_t)eids[p] : p) * wH;
     const V* xr = reinterpret_cast<const V*>(x + u * F);
 #pragma unroll
     for (int j = 0; j < NV; ++j)
       if (vbase + j * sub < nvec) {
         V v = ldg_vec(xr + vbase + j * sub);
-        VO::fma(acc[j], v, wt);
+        VO::fma(acc[j], v, HAS_W ? to_f<T>(w[eidx + hd[j]]) : 1.f);
       }
   }
   float* srow = scratch + (int64_t)item_ord[item] * F;
@@ -280,20 +291,21 @@ __global__ void __launch_bounds__(256) spmm_split_finalize_kernel(const float* _
 template <typename T, typename I, int VB, bool HAS_W>
 void launch_split(const I* indices, const I* eids, const int32_t* item_ord, const int64_t* item_start,
                   const int32_t* item_len, int64_t num_items, const T* x, const T* w, float* scratch, int64_t F,
-                  cudaStream_t st) {
+                  cudaStream_t st, int wH = 1) {
   constexpr int VE = VB / sizeof(T);
   const int nvec = (int)(F / VE);
+  const int vph = wH > 1 ? nvec / wH : nvec;
   const int sub = pow2_ge(nvec, 32);
   const int ipb = 256 / sub;
   const unsigned gx = (unsigned)((num_items + ipb - 1) / ipb);
   const int per_lane = (nvec + sub - 1) / sub;
   if (per_lane <= 1) {
-    spmm_split_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub);
+    spmm_split_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub, wH, vph);
   } else if (per_lane <= 2) {
-    spmm_split_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub);
+    spmm_split_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub, wH, vph);
   } else {
     const unsigned gy = (unsigned)((nvec + sub * 4 - 1) / (sub * 4));
-    spmm_split_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub);
+    spmm_split_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub, wH, vph);
   }
 }
 
@@ -390,16 +402,20 @@ DGLB_API int dglb200_cuda_gspmm_balanced(int has_w, int dtype, int idtype, const
   auto run = [&](auto tag, auto itag) {
     using T = decltype(tag);
     using I = decltype(itag);
-    const int vb = pick_vb_spmm(F * (int64_t)sizeof(T), x, out);
-    DGLB_CHECK(vb != 0, "feature rows must be 4-byte aligned for the balanced g-SpMM");
+    // has_w = number of weight columns per edge (0: copy_u, 1: scalar, H > 1: one per head of F/H features);
+    // a vector must not straddle two heads, so the vector width has to divide the per-head byte count
+    const int wH = has_w > 1 ? has_w : 1;
+    DGLB_CHECK(F % wH == 0, "feature size must be a multiple of the number of weight columns");
+    const int vb = pick_vb_spmm((F / wH) * (int64_t)sizeof(T), x, out);
+    DGLB_CHECK(vb != 0 && (F * (int64_t)sizeof(T)) % vb == 0, "feature rows must be 4-byte aligned for the balanced g-SpMM");
 #define RUN(VBV, HW)                                                                                              \
     launch_vec<T, I, VBV, HW>((const I*)indptr, (const I*)indices, (const I*)eids, num_rows, (const T*)x,           \
-                              (const T*)w, (T*)out, F, st, max_deg);                                                \
+                              (const T*)w, (T*)out, F, st, max_deg, wH);                                            \
     if (num_items > 0) {                                                                                            \
       DGLB_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)n_long * F * sizeof(float), st));                         \
       launch_split<T, I, VBV, HW>((const I*)indices, (const I*)eids, (const int32_t*)item_ord,                      \
                                   (const int64_t*)item_start, (const int32_t*)item_len, num_items, (const T*)x,     \
-                                  (const T*)w, (float*)scratch, F, st);                                             \
+                                  (const T*)w, (float*)scratch, F, st, wH);                                         \
       int64_t blocks = (n_long * F + 255) / 256;                                                                    \
       if (blocks > 148 * 16) blocks = 148 * 16;                                                                     \
       spmm_split_finalize_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const float*)scratch,                        \

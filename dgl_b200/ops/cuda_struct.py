@@ -113,3 +113,17 @@ def uva_index_scatter(dest, index, source):
     loader.cuda_lib().fn("dglb200_cuda_scatter_rows", "ipplplip")(
         id_code(index.dtype), dest.data_ptr(), index.data_ptr(), index.shape[0], source.data_ptr(), row_bytes, 1,
         loader.stream_ptr())
+
+
+def scatter_rows(dest, index, source):
+    """dest[index[i]] = source[i] on the device (index int32/int64, unique)."""
+    index = index.contiguous()
+    source = source.contiguous()
+    row_bytes = dest.element_size()
+    for s_ in dest.shape[1:]:
+        row_bytes *= s_
+    if index.shape[0] and row_bytes:
+        loader.cuda_lib().fn("dglb200_cuda_scatter_rows", "ipplplip")(
+            id_code(index.dtype), dest.data_ptr(), index.data_ptr(), index.shape[0], source.data_ptr(), row_bytes, 0,
+            loader.stream_ptr())
+    return dest
