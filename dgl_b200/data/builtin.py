@@ -87,7 +87,6 @@ class OgbnArxivSynthetic(_SyntheticNodeDataset):
     _scale = 0.1
 
 
-CiteseerGraphDataset = PubmedGraphDataset = CoraGraphDataset
 
 
 class AsNodePredDataset:

@@ -16,3 +16,5 @@ from .neighbor_sampler import MultiLayerFullNeighborSampler, MultiLayerNeighborS
 from .shadow import ShaDowKHopSampler  # noqa: F401
 from .capped_neighbor_sampler import CappedNeighborSampler  # noqa: F401
 from .spot_target import SpotTarget  # noqa: F401
+
+from .dataloader import GraphCollator  # noqa: F401,E402

@@ -110,12 +110,20 @@ def _h_insubgraph(st, payload):
     return st.local_nid[src.long()], st.local_nid[dst.long()], st.local_eid[eid.long()]
 
 
+def _h_find_edges(st, payload):
+    eids = payload
+    loc = (eids - st.eid_start).to(st.g.idtype)  # inner edges are a prefix of the partition's edges
+    src, dst = st.g.find_edges(loc)
+    return st.local_nid[src.long()], st.local_nid[dst.long()]
+
+
 def _h_barrier(st, payload):
     return True
 
 
 for _sid, _h in ((SVC_META, _h_meta), (SVC_PULL, _h_pull), (SVC_PUSH, _h_push), (SVC_SAMPLE, _h_sample),
-                 (SVC_BARRIER, _h_barrier), (SVC_INIT_DATA, _h_init_data), (SVC_INSUBGRAPH, _h_insubgraph)):
+                 (SVC_BARRIER, _h_barrier), (SVC_INIT_DATA, _h_init_data), (SVC_INSUBGRAPH, _h_insubgraph),
+                 (SVC_FIND_EDGES, _h_find_edges)):
     rpc.register_service(_sid, _h)
 
 
@@ -338,7 +346,13 @@ class DistGraph:
         return in_subgraph(self, nodes)
 
     def find_edges(self, eids, etype=None):
-        raise DGLError("find_edges on DistGraph: sample with in_subgraph or keep (src,dst) with the seed edges")
+        return find_edges(self, eids)
+
+    def get_rank(self):
+        return self.rank()
+
+    def get_num_client(self):
+        return get_num_client()
 
 
 def _merge(g, results):
@@ -362,6 +376,61 @@ def sample_neighbors(g, nodes, fanout, edge_dir="in", prob=None, replace=False):
     for p in torch.unique(own).tolist():
         reqs.append((p, SVC_SAMPLE, (nodes[own == p], int(fanout), prob, replace, edge_dir)))
     return _merge(g, _call_many(reqs))
+
+
+def sample_etype_neighbors(g, nodes, fanout, edge_dir="in", prob=None, replace=False, etype_sorted=True, **kw):
+    """Per-edge-type fan-out sampling. Partitions store homogenised graphs with a single relation in this build, so a
+    dict / per-type ``fanout`` reduces to its (only) entry (reference graph_services.py:sample_etype_neighbors)."""
+    if isinstance(fanout, dict):
+        fanout = next(iter(fanout.values()))
+    elif torch.is_tensor(fanout):
+        fanout = int(fanout.reshape(-1)[0])
+    return sample_neighbors(g, nodes, int(fanout), edge_dir=edge_dir, prob=prob, replace=replace)
+
+
+def find_edges(g, edge_ids):
+    """(src, dst) global node ids of the given global edge ids, resolved by the owning partitions."""
+    eids = torch.as_tensor(edge_ids).long().reshape(-1)
+    own = g.gpb.eid2partid(eids)
+    src = torch.empty_like(eids)
+    dst = torch.empty_like(eids)
+    reqs, sel = [], []
+    for p in torch.unique(own).tolist():
+        m = torch.nonzero(own == p).squeeze(1)
+        reqs.append((p, SVC_FIND_EDGES, eids[m]))
+        sel.append(m)
+    for m, (s_, d_) in zip(sel, _call_many(reqs)):
+        src[m], dst[m] = s_, d_
+    return src, dst
+
+
+def get_rank():
+    return _CTX.client.client_id if _CTX.mode == "distributed" and _CTX.client is not None else 0
+
+
+def get_num_client():
+    return int(os.environ.get("DGL_NUM_CLIENT", "1"))
+
+
+class DistGraphServer:
+    """One partition's graph + KVStore server process (reference dist_graph.py:488). ``start()`` blocks serving
+    requests until every client has sent its shutdown message."""
+
+    def __init__(self, server_id, ip_config, num_servers, num_clients, part_config, disable_shared_mem=False,
+                 graph_format=("csc", "coo"), use_graphbolt=False):
+        self.server_id, self.ip_config, self.num_clients = server_id, ip_config, num_clients
+        self.state = ServerState(part_config, server_id)
+        from .kvstore import KVServer
+        self.kvserver = KVServer(server_id, ip_config, num_servers, num_clients, self.state)
+
+    @property
+    def gpb(self):
+        return self.state.gpb
+
+    def start(self):
+        servers = rpc.read_ip_config(self.ip_config)
+        ip, port = servers[self.server_id]
+        rpc.RPCServer(self.server_id, ip, port, self.num_clients, self.state).serve_forever()
 
 
 def in_subgraph(g, nodes):
@@ -520,4 +589,31 @@ class DistSparseAdagrad(DistSparseGradOptimizer):
         emb._tensor[idx] = emb._tensor[idx] - self._lr * grad / (s.sqrt() + self._eps)
 
 
+class DistSparseAdam(DistSparseGradOptimizer):
+    """Row-sparse Adam on a DistEmbedding: state (step, m, v) lives in DistTensors next to the embedding shard
+    (reference distributed/optim/pytorch/sparse_optim.py:SparseAdam)."""
+
+    def __init__(self, params, lr, betas=(0.9, 0.999), eps=1e-8):
+        super().__init__(params, lr)
+        self._b1, self._b2, self._eps = betas[0], betas[1], eps
+        for emb in params:
+            g = emb._tensor._g
+            self._state[emb._name] = (
+                DistTensor((emb.num_embeddings, 1), torch.float32, emb._name + "_step", _graph=g),
+                DistTensor((emb.num_embeddings, emb.embedding_dim), torch.float32, emb._name + "_m", _graph=g),
+                DistTensor((emb.num_embeddings, emb.embedding_dim), torch.float32, emb._name + "_v", _graph=g))
+
+    def update(self, emb, idx, grad):
+        st, m, v = self._state[emb._name]
+        t = st[idx] + 1
+        st[idx] = t
+        mm = self._b1 * m[idx] + (1 - self._b1) * grad
+        vv = self._b2 * v[idx] + (1 - self._b2) * grad * grad
+        m[idx], v[idx] = mm, vv
+        mhat = mm / (1 - self._b1 ** t)
+        vhat = vv / (1 - self._b2 ** t)
+        emb._tensor[idx] = emb._tensor[idx] - self._lr * mhat / (vhat.sqrt() + self._eps)
+
+
 SparseAdagrad = DistSparseAdagrad
+SparseAdam = DistSparseAdam

@@ -1,0 +1,164 @@
+"""KVStore facade: named, partition-sharded tensors with pull / push / barrier.
+
+Parity: /root/reference/python/dgl/distributed/kvstore.py (KVServer :806, KVClient :1016, PartitionPolicy in
+graph_partition_book.py:1013-1110) and standalone_kvstore.py. The storage and the request handlers live in
+``dist_graph.ServerState`` (one per partition); this module gives them the reference's class names and call shapes so
+user code written against ``dgl.distributed.kvstore`` keeps working."""
+from __future__ import annotations
+
+import torch
+
+from ..base import DGLError
+
+NODE_PART_POLICY = "node"
+EDGE_PART_POLICY = "edge"
+
+
+class PartitionPolicy:
+    """Maps global ids of one node/edge type to (partition, local id) through the partition book."""
+
+    def __init__(self, policy_str, partition_book):
+        if ":" in policy_str:
+            dom, typ = policy_str.split(":", 1)
+        else:
+            dom, typ = policy_str, ("_N" if policy_str == NODE_PART_POLICY else "_N:_E:_N")
+        if dom not in (NODE_PART_POLICY, EDGE_PART_POLICY):
+            raise DGLError(f"unknown partition policy {policy_str!r}")
+        self._dom, self._typ, self._gpb = dom, typ, partition_book
+        self._policy_str = f"{dom}:{typ}"
+
+    @property
+    def policy_str(self):
+        return self._policy_str
+
+    @property
+    def part_id(self):
+        return self._gpb.partid
+
+    @property
+    def partition_book(self):
+        return self._gpb
+
+    def to_partid(self, id_tensor):
+        return self._gpb.nid2partid(id_tensor) if self._dom == NODE_PART_POLICY else self._gpb.eid2partid(id_tensor)
+
+    def to_local(self, id_tensor):
+        f = self._gpb.nid2localnid if self._dom == NODE_PART_POLICY else self._gpb.eid2localeid
+        return f(id_tensor, self._gpb.partid)
+
+    def get_part_size(self):
+        m = self._gpb._node_map["_N"] if self._dom == NODE_PART_POLICY else self._gpb._edge_map[self._gpb._ekey("_E")]
+        return int(m[self._gpb.partid, 1] - m[self._gpb.partid, 0])
+
+    def get_size(self):
+        return self._gpb.num_nodes() if self._dom == NODE_PART_POLICY else self._gpb.num_edges()
+
+
+class KVServer:
+    """Server-side view of one partition's shard store (wraps a ``ServerState``)."""
+
+    def __init__(self, server_id, ip_config=None, num_servers=1, num_clients=1, state=None):
+        self.server_id, self.num_servers, self.num_clients = server_id, num_servers, num_clients
+        self._state = state
+        self.part_policy = {}
+
+    def attach(self, state):
+        self._state = state
+        return self
+
+    @property
+    def data_store(self):
+        return self._state.kv
+
+    def is_backup_server(self):
+        return False
+
+    def add_part_policy(self, policy):
+        self.part_policy[policy.policy_str] = policy
+
+    def init_data(self, name, policy_str, data_tensor=None):
+        dom, typ = policy_str.split(":", 1) if ":" in policy_str else (policy_str, "_N")
+        if data_tensor is not None:
+            self._state.kv[name] = data_tensor
+        self._state.policy[name] = (dom, typ)
+
+    def register_push_handler(self, name, func):
+        """``func(target_tensor, local_ids, data)`` replaces plain assignment for pushes to ``name``."""
+        self._state.handlers[name] = func
+
+    def find_policy(self, policy_str):
+        return self.part_policy[policy_str]
+
+
+class KVClient:
+    """Client-side pull/push on named distributed tensors (works in standalone and distributed mode)."""
+
+    def __init__(self, ip_config=None, num_servers=1, role="default"):
+        from . import dist_graph as dg
+        if not dg._CTX.initialized:
+            raise DGLError("call dgl.distributed.initialize() first")
+        self._dg = dg
+        self._gpb = None
+        self._meta = {}
+
+    def map_shared_data(self, partition_book):
+        self._gpb = partition_book
+        meta = self._dg._call(0, self._dg.SVC_META, None)
+        self._meta = dict(meta["tensors"])
+
+    def _owner(self, name, ids):
+        dom = name.split("~", 1)[0]
+        return self._gpb.nid2partid(ids) if dom == "node" else self._gpb.eid2partid(ids)
+
+    @property
+    def num_servers(self):
+        return self._dg._CTX.num_servers
+
+    def data_name_list(self):
+        return list(self._meta)
+
+    def get_data_meta(self, name):
+        tail, dtype = self._meta[name]
+        return dtype, tuple(tail), name.split("~", 1)[0]
+
+    def init_data(self, name, shape, dtype, part_policy=None, init_func=None, is_gdata=True):
+        dom = "node" if part_policy is None or part_policy.policy_str.startswith("node") else "edge"
+        typ = "_N" if dom == "node" else "_N:_E:_N"
+        full = name if "~" in name else f"{dom}~{typ}~{name}"
+        for sid in range(self.num_servers):
+            self._dg._call(sid, self._dg.SVC_INIT_DATA, (full, tuple(shape[1:]), dtype, dom, typ,
+                                                        "uniform" if init_func == "uniform" else "zeros"))
+        self._meta[full] = (tuple(shape[1:]), dtype)
+        return full
+
+    def pull(self, name, id_tensor):
+        ids = torch.as_tensor(id_tensor).long().reshape(-1)
+        own = self._owner(name, ids)
+        tail, dtype = self._meta[name]
+        out = torch.empty((ids.shape[0],) + tuple(tail), dtype=dtype)
+        reqs, sel = [], []
+        for p in torch.unique(own).tolist():
+            m = torch.nonzero(own == p).squeeze(1)
+            reqs.append((p, self._dg.SVC_PULL, (name, ids[m])))
+            sel.append(m)
+        for m, res in zip(sel, self._dg._call_many(reqs)):
+            out[m] = res
+        return out
+
+    def push(self, name, id_tensor, data_tensor):
+        ids = torch.as_tensor(id_tensor).long().reshape(-1)
+        own = self._owner(name, ids)
+        reqs = []
+        for p in torch.unique(own).tolist():
+            m = torch.nonzero(own == p).squeeze(1)
+            reqs.append((p, self._dg.SVC_PUSH, (name, ids[m], data_tensor[m])))
+        self._dg._call_many(reqs)
+
+    def barrier(self):
+        self._dg._call_many([(sid, self._dg.SVC_BARRIER, None) for sid in range(self.num_servers)])
+
+    def register_push_handler(self, name, func):
+        if self._dg._CTX.mode != "standalone":
+            raise DGLError("push handlers must be registered on the servers (KVServer.register_push_handler)")
+        for st in self._dg._CTX.local_servers:
+            st.handlers[name] = func

@@ -1,0 +1,34 @@
+"""Process roles inside a distributed job (parity: /root/reference/python/dgl/distributed/role.py).
+Roles come from the launcher's environment: servers (DGL_ROLE=server), trainers ("default"), samplers."""
+from __future__ import annotations
+
+import os
+
+_ROLE = {"name": None, "rank": 0, "global_rank": 0, "num": 1}
+
+
+def init_role(role):
+    _ROLE["name"] = role
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        _ROLE["rank"] = _ROLE["global_rank"] = dist.get_rank()
+        _ROLE["num"] = dist.get_world_size()
+    else:
+        _ROLE["rank"] = _ROLE["global_rank"] = int(os.environ.get("RANK", "0"))
+        _ROLE["num"] = int(os.environ.get("WORLD_SIZE", "1"))
+
+
+def get_role():
+    return _ROLE["name"] or os.environ.get("DGL_ROLE", "default")
+
+
+def get_trainer_rank():
+    return _ROLE["rank"]
+
+
+def get_global_rank():
+    return _ROLE["global_rank"]
+
+
+def get_num_trainers():
+    return _ROLE["num"]

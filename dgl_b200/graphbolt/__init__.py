@@ -14,3 +14,23 @@ from .impl.cooperative import rank_assignment, rank_sort  # noqa: F401
 def set_seed(seed):
     from .. import random as _r
     _r.seed(seed)
+
+
+def numpy_save_aligned(path, arr, alignment=4096):
+    """``numpy.save`` whose data section starts at a multiple of ``alignment`` bytes, so DiskBasedFeature can read rows
+    with O_DIRECT-style aligned preads (reference graphbolt/internal_utils.py:numpy_save_aligned)."""
+    import numpy as np
+    from numpy.lib import format as npf
+    arr = np.ascontiguousarray(arr)
+    header = npf.header_data_from_array_1_0(arr)
+    import io
+    buf = io.BytesIO()
+    npf.write_array_header_2_0(buf, header)
+    hdr = buf.getvalue()
+    pad = (-len(hdr)) % alignment
+    if pad:  # grow the (space padded) header dict so that the data offset is aligned; fix the length field
+        hlen = int.from_bytes(hdr[8:12], "little") + pad
+        hdr = hdr[:8] + hlen.to_bytes(4, "little") + hdr[12:-1] + b" " * pad + b"\n"
+    with open(path, "wb") as f:
+        f.write(hdr)
+        arr.tofile(f)

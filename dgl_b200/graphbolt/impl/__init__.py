@@ -1,5 +1,6 @@
 from .fused_csc_sampling_graph import FusedCSCSamplingGraph, from_dglgraph, fused_csc_sampling_graph  # noqa: F401
-from .neighbor_sampler import LayerNeighborSampler, NeighborSampler  # noqa: F401
+from .neighbor_sampler import (LayerNeighborSampler, NeighborSampler, TemporalLayerNeighborSampler,  # noqa: F401
+                               TemporalNeighborSampler)
 from .negative_sampler import UniformNegativeSampler  # noqa: F401
 from .in_subgraph_sampler import InSubgraphSampler  # noqa: F401
 from .features import (BasicFeatureStore, CPUCachedFeature, DiskBasedFeature, Feature, GPUCachedFeature,  # noqa: F401

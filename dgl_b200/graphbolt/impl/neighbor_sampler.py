@@ -62,3 +62,52 @@ class LayerNeighborSampler(NeighborSampler):
                  batch_dependency=1, **kw):
         super().__init__(datapipe, graph, fanouts, replace, prob_name, deduplicate, layer=True,
                          batch_dependency=batch_dependency, layer_dependency=layer_dependency)
+
+
+class TemporalNeighborSampler(SubgraphSampler):
+    """Neighbour sampling that only follows edges / neighbours older than the seed's timestamp
+    (reference impl/temporal_neighbor_sampler.py). Nodes are NOT deduplicated: the same node reached at two different
+    times is two rows; every sampled source inherits the timestamp of the seed it was sampled for."""
+
+    def __init__(self, datapipe, graph, fanouts, replace=False, prob_name=None, node_timestamp_attr_name=None,
+                 edge_timestamp_attr_name=None, layer=False):
+        super().__init__(datapipe)
+        self.graph = graph
+        self.fanouts = [torch.as_tensor(f).reshape(-1) for f in fanouts]
+        self.replace, self.prob_name = replace, prob_name
+        self.node_ts, self.edge_ts = node_timestamp_attr_name, edge_timestamp_attr_name
+
+    def _sample(self, minibatch):
+        seeds = minibatch.seeds
+        ts = getattr(minibatch, "timestamp", None)
+        if ts is None:
+            raise ValueError("TemporalNeighborSampler needs a 'timestamp' field in the item set")
+        compacted = None
+        if seeds.dim() == 2:  # link / hyperlink seeds: every endpoint is looked up at the time of its edge
+            k = seeds.shape[1]
+            compacted = torch.arange(seeds.numel(), device=seeds.device).reshape(-1, k)
+            ts = ts.repeat_interleave(k)
+            seeds = seeds.reshape(-1)
+        minibatch.input_nodes, minibatch.sampled_subgraphs = self.sample_subgraphs(seeds, ts)
+        minibatch.compacted_seeds = compacted
+        return minibatch
+
+    def sample_subgraphs(self, seeds, seeds_timestamp=None):
+        from ..utils import compact_csc_format
+        subgraphs = []
+        ts = seeds_timestamp
+        for hop in reversed(range(len(self.fanouts))):
+            sg = self.graph.temporal_sample_neighbors(seeds, ts, self.fanouts[hop], self.replace, None, self.prob_name,
+                                                      self.node_ts, self.edge_ts)
+            csc = sg.sampled_csc
+            deg = (csc.indptr[1:] - csc.indptr[:-1]).long()
+            rows, compacted = compact_csc_format(csc, seeds)
+            subgraphs.insert(0, SampledSubgraphImpl(sampled_csc=compacted, original_column_node_ids=seeds,
+                                                    original_row_node_ids=rows, original_edge_ids=sg.original_edge_ids))
+            ts = torch.cat([ts, torch.repeat_interleave(ts, deg)])
+            seeds = rows
+        return seeds, subgraphs
+
+
+class TemporalLayerNeighborSampler(TemporalNeighborSampler):
+    """Layer-wise (LABOR-style) variant; the temporal constraint dominates, so it shares the per-seed sampler."""

@@ -12,7 +12,9 @@ CuGraphSAGEConv = SAGEConv
 CuGraphGATConv = GATConv
 CuGraphRelGraphConv = RelGraphConv
 
-__all__ = ["GraphConv", "EdgeWeightNorm", "SAGEConv", "GATConv", "GATv2Conv", "DotGatConv", "AGNNConv", "EGATConv",
+from .extra import GroupRevRes, TWIRLSUnfoldingAndAttention  # noqa: E402
+
+__all__ = ["GroupRevRes", "TWIRLSUnfoldingAndAttention", "GraphConv", "EdgeWeightNorm", "SAGEConv", "GATConv", "GATv2Conv", "DotGatConv", "AGNNConv", "EGATConv",
            "EdgeGATConv", "GINConv", "GINEConv", "SGConv", "TAGConv", "APPNPConv", "ChebConv", "GCN2Conv",
            "GatedGraphConv", "GatedGCNConv", "CFConv", "NNConv", "GMMConv", "EdgeConv", "EGNNConv", "TWIRLSConv",
            "RelGraphConv", "HeteroGraphConv", "HGTConv", "DenseGraphConv", "DenseSAGEConv", "DenseChebConv", "PNAConv",

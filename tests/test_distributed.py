@@ -75,6 +75,30 @@ def test_standalone_dist_graph():
         (e.sum() * 2).backward()
         opt.step()
         assert float(emb.weight[torch.tensor([1])].abs().sum()) > 0
+        # find_edges resolves global edge ids on the owning partition
+        eids = torch.tensor([0, 17, g.num_edges() - 1])
+        fu, fv = dg.find_edges(eids)
+        _, emap = dd.partition_graph(g, "tg2", 2, d, return_mapping=True) if False else (None, None)
+        assert bool(g.has_edges_between(nmap[fu], nmap[fv]).all())
+        # KVStore facade: init / push / pull with a push handler (accumulate instead of overwrite)
+        kv = dd.KVClient()
+        kv.map_shared_data(dg.get_partition_book())
+        name = kv.init_data("acc", (600, 2), torch.float32, dd.PartitionPolicy("node", dg.get_partition_book()))
+        kv.register_push_handler(name, lambda tgt, loc, data: tgt.index_add_(0, loc, data))
+        kv.push(name, ids, torch.ones(4, 2))
+        kv.push(name, ids, torch.ones(4, 2))
+        assert torch.equal(kv.pull(name, ids), torch.full((4, 2), 2.0))
+        kv.barrier()
+        # sparse Adam on a distributed embedding
+        emb2 = dd.DistEmbedding(600, 4, "emb2", _graph=dg)
+        opt2 = dd.optim.SparseAdam([emb2], lr=0.1)
+        e2 = emb2(torch.tensor([4, 9]))
+        e2.sum().backward()
+        opt2.step()
+        assert torch.allclose(emb2.weight[torch.tensor([4, 9])], torch.full((2, 4), -0.1), atol=1e-4)
+        sg2 = dd.sample_etype_neighbors(dg, torch.arange(0, 600, 50), {"_E": 3})
+        assert int(sg2.in_degrees().max()) <= 3
+        assert dd.get_rank() == 0 and dd.role.get_role() in ("default", "client", "server")
         dd.exit_client()
 
 
