@@ -108,7 +108,12 @@ def partition_graph(g, graph_name, num_parts, out_path, num_hops=1, part_method=
         raise DGLError("partition_graph currently supports homogeneous graphs (use dgl.to_homogeneous first)")
     g = g.cpu() if g.device.type != "cpu" else g
     n = g.num_nodes()
-    if num_parts == 1:
+    if kwargs.get("node_part") is not None:  # precomputed assignment (tools/dispatch_data.py, ParMETIS output)
+        node_part = torch.as_tensor(kwargs["node_part"]).long()
+        if node_part.shape[0] != n or int(node_part.max()) >= num_parts:
+            raise DGLError("node_part must assign every node to a partition id < num_parts")
+        part_method = "given"
+    elif num_parts == 1:
         node_part = torch.zeros(n, dtype=torch.int64)
     elif part_method == "metis":
         node_part = metis_partition_assignment(g, num_parts, balance_ntypes=balance_ntypes, balance_edges=balance_edges)

@@ -1,0 +1,186 @@
+// Native unit tests of libdglb200_cpu.so through its C ABI (the counterpart of the reference's gtest suite
+// /root/reference/tests/cpp/: test_spmm.cc, test_partition.cc, message_queue_test.cc, socket_communicator_test.cc).
+// No gtest in this image: a 30-line harness, built and run by tests/test_cpp_native.py.
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <string>
+#include <thread>
+#include <vector>
+
+extern "C" {
+const char* dglb200_last_error();
+int dglb200_cpu_gspmm(int op, int red, int dtype, int idtype, const void* indptr, const void* indices, const void* eids,
+                      int64_t num_rows, const void* ufeat, const void* efeat, void* out, void* arg_u, void* arg_e,
+                      int64_t F, int64_t ldiv, int64_t lmod, int64_t rdiv, int64_t rmod);
+int dglb200_cache_create(int policy, int64_t capacity, int num_parts, int64_t* handle);
+int dglb200_cache_destroy(int64_t handle);
+int dglb200_cache_query(int64_t handle, const void* keys, int64_t n, void* positions, void* num_hit);
+int dglb200_cache_replace(int64_t handle, const void* keys, int64_t n, void* positions);
+int dglb200_cache_stats(int64_t handle, int64_t* hits, int64_t* queries);
+int dglb200_cpu_ldg_partition(int idtype, const void* indptr, const void* indices, int64_t n, int k, const void* vwgt,
+                              int refine_iters, double imbalance, int64_t seed, void* part);
+int dglb200_cpu_libra_partition(int idtype, const void* src, const void* dst, int64_t E, int64_t n, int k, void* edge_part);
+int dglb200_rpc_create(int rank, const char* ip, int port, int64_t* handle, int* bound_port);
+int dglb200_rpc_connect(int64_t handle, int peer, const char* ip, int port, int max_try, int retry_ms);
+int dglb200_rpc_send(int64_t handle, int peer, int tag, const void* data, int64_t n);
+int dglb200_rpc_recv_peek(int64_t handle, int timeout_ms, int* src, int* tag, int64_t* size);
+int dglb200_rpc_recv_take(void* dst);
+int dglb200_rpc_destroy(int64_t handle);
+}
+
+static int g_failed = 0, g_checks = 0;
+#define CHECK(cond)                                                                  \
+  do {                                                                               \
+    ++g_checks;                                                                      \
+    if (!(cond)) {                                                                   \
+      ++g_failed;                                                                    \
+      std::printf("FAILED %s:%d  %s   (last error: %s)\n", __FILE__, __LINE__, #cond, dglb200_last_error()); \
+    }                                                                                \
+  } while (0)
+
+static void test_spmm() {
+  // 4 destination rows, CSC: row r sums its in-neighbours' features
+  std::vector<int64_t> indptr = {0, 2, 2, 5, 6}, indices = {1, 3, 0, 1, 2, 3};
+  const int F = 3;
+  std::vector<float> x(4 * F), w(6), out(4 * F, -1.f);
+  for (int i = 0; i < 4 * F; ++i) x[i] = 0.5f * i - 1.f;
+  for (int i = 0; i < 6; ++i) w[i] = 1.f + i;
+  // copy_u sum
+  CHECK(dglb200_cpu_gspmm(4, 0, 0, 1, indptr.data(), indices.data(), nullptr, 4, x.data(), nullptr, out.data(), nullptr,
+                          nullptr, F, 1, F, 1, 1) == 0);
+  for (int r = 0; r < 4; ++r)
+    for (int f = 0; f < F; ++f) {
+      float ref = 0;
+      for (int64_t p = indptr[r]; p < indptr[r + 1]; ++p) ref += x[indices[p] * F + f];
+      CHECK(std::fabs(out[r * F + f] - ref) < 1e-6);
+    }
+  // u_mul_e sum with a scalar per edge
+  CHECK(dglb200_cpu_gspmm(2, 0, 0, 1, indptr.data(), indices.data(), nullptr, 4, x.data(), w.data(), out.data(), nullptr,
+                          nullptr, F, 1, F, 1, 1) == 0);
+  for (int r = 0; r < 4; ++r)
+    for (int f = 0; f < F; ++f) {
+      float ref = 0;
+      for (int64_t p = indptr[r]; p < indptr[r + 1]; ++p) ref += x[indices[p] * F + f] * w[p];
+      CHECK(std::fabs(out[r * F + f] - ref) < 1e-5);
+    }
+  // copy_u max with arg
+  std::vector<int64_t> arg(4 * F, -7);
+  CHECK(dglb200_cpu_gspmm(4, 1, 0, 1, indptr.data(), indices.data(), nullptr, 4, x.data(), nullptr, out.data(), arg.data(),
+                          nullptr, F, 1, F, 1, 1) == 0);
+  CHECK(arg[0] == 3 && out[0] == x[3 * F]);   // row 0: neighbours {1,3} -> node 3 has the larger feature
+  CHECK(out[1 * F] == 0.f);                   // empty row -> 0
+}
+
+static void test_cache(int policy) {
+  int64_t h = 0;
+  CHECK(dglb200_cache_create(policy, 64, 2, &h) == 0);
+  std::vector<int64_t> keys(40), pos(40);
+  for (int i = 0; i < 40; ++i) keys[i] = i * 3;
+  int64_t nhit = -1;
+  CHECK(dglb200_cache_query(h, keys.data(), 40, pos.data(), &nhit) == 0);
+  CHECK(nhit == 0);
+  CHECK(dglb200_cache_replace(h, keys.data(), 40, pos.data()) == 0);
+  std::set<int64_t> slots(pos.begin(), pos.end());
+  CHECK(slots.size() == 40);  // distinct slots
+  for (auto s : slots) CHECK(s >= 0 && s < 64);
+  std::vector<int64_t> pos2(40);
+  CHECK(dglb200_cache_query(h, keys.data(), 40, pos2.data(), &nhit) == 0);
+  CHECK(nhit == 40);
+  // the query reorders hits first; every returned slot must be one that was assigned
+  for (int i = 0; i < 40; ++i) CHECK(slots.count(pos2[i]) == 1);
+  // overflow the capacity: old keys get evicted, the structure stays consistent
+  std::vector<int64_t> more(200), mpos(200);
+  for (int i = 0; i < 200; ++i) more[i] = 1000 + i;
+  for (int b = 0; b < 200; b += 50) {
+    CHECK(dglb200_cache_query(h, more.data() + b, 50, mpos.data(), &nhit) == 0);
+    CHECK(dglb200_cache_replace(h, more.data() + b + 0, 50, mpos.data()) == 0);
+  }
+  int64_t hits = 0, queries = 0;
+  CHECK(dglb200_cache_stats(h, &hits, &queries) == 0);
+  CHECK(queries >= 280 && hits >= 40);
+  CHECK(dglb200_cache_destroy(h) == 0);
+}
+
+static void test_partitioners() {
+  // two 50-node cliques joined by one edge: a 2-way partition must separate them
+  const int n = 100;
+  std::vector<int64_t> indptr(n + 1, 0), indices;
+  for (int v = 0; v < n; ++v) {
+    const int lo = v < 50 ? 0 : 50;
+    for (int u = lo; u < lo + 50; ++u)
+      if (u != v) indices.push_back(u);
+    if (v == 49) indices.push_back(50);
+    if (v == 50) indices.push_back(49);
+    indptr[v + 1] = (int64_t)indices.size();
+  }
+  std::vector<int64_t> part(n, -1);
+  CHECK(dglb200_cpu_ldg_partition(1, indptr.data(), indices.data(), n, 2, nullptr, 10, 1.05, 7, part.data()) == 0);
+  int a = 0, cut = 0;
+  for (int v = 0; v < n; ++v) a += part[v] == part[0];
+  for (int v = 0; v < n; ++v)
+    for (int64_t p = indptr[v]; p < indptr[v + 1]; ++p) cut += part[v] != part[indices[p]];
+  CHECK(a >= 45 && a <= 55);
+  CHECK(cut <= 2 * 60);  // far below the ~2500 of a random split
+  // Libra vertex cut on a sparse pseudo-random graph: every edge gets a partition in range, loads stay balanced
+  const int64_t n2 = 2000, E2 = 16000;
+  std::vector<int64_t> src(E2), dst(E2);
+  uint64_t st = 12345;
+  for (int64_t e = 0; e < E2; ++e) {
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    src[e] = (int64_t)((st >> 33) % n2);
+    st = st * 6364136223846793005ull + 1442695040888963407ull;
+    dst[e] = (int64_t)((st >> 33) % n2);
+  }
+  std::vector<int64_t> ep(E2, -1), load(4, 0);
+  CHECK(dglb200_cpu_libra_partition(1, src.data(), dst.data(), E2, n2, 4, ep.data()) == 0);
+  for (auto p : ep) { CHECK(p >= 0 && p < 4); if (p >= 0 && p < 4) ++load[p]; }
+  for (auto l : load) CHECK(l > E2 / 8 && l < E2 / 2);
+}
+
+static void test_rpc_loopback() {
+  int64_t a = 0, b = 0;
+  int pa = 0, pb = 0;
+  CHECK(dglb200_rpc_create(0, "127.0.0.1", 0, &a, &pa) == 0);
+  CHECK(dglb200_rpc_create(1, "127.0.0.1", 0, &b, &pb) == 0);
+  CHECK(pa > 0 && pb > 0);
+  CHECK(dglb200_rpc_connect(a, 1, "127.0.0.1", pb, 50, 20) == 0);
+  std::vector<char> payload(1 << 20);
+  for (size_t i = 0; i < payload.size(); ++i) payload[i] = (char)(i * 31);
+  std::thread sender([&] {
+    for (int k = 0; k < 4; ++k) CHECK(dglb200_rpc_send(a, 1, 100 + k, payload.data(), (int64_t)payload.size() - k) == 0);
+    CHECK(dglb200_rpc_send(a, 1, 7, nullptr, 0) == 0);  // empty message
+  });
+  for (int k = 0; k < 5; ++k) {
+    int src = -1, tag = -1;
+    int64_t size = -2;
+    CHECK(dglb200_rpc_recv_peek(b, 5000, &src, &tag, &size) == 0);
+    CHECK(src == 0);
+    std::vector<char> buf(size > 0 ? size : 1);
+    CHECK(dglb200_rpc_recv_take(buf.data()) == 0);
+    if (k < 4) {
+      CHECK(tag == 100 + k && size == (int64_t)payload.size() - k);
+      CHECK(std::memcmp(buf.data(), payload.data(), (size_t)size) == 0);
+    } else {
+      CHECK(tag == 7 && size == 0);
+    }
+  }
+  sender.join();
+  int src, tag;
+  int64_t size = 0;
+  CHECK(dglb200_rpc_recv_peek(b, 50, &src, &tag, &size) == 0);
+  CHECK(size == -1);  // timeout, nothing pending
+  CHECK(dglb200_rpc_destroy(a) == 0);
+  CHECK(dglb200_rpc_destroy(b) == 0);
+}
+
+int main() {
+  test_spmm();
+  for (int policy = 0; policy < 4; ++policy) test_cache(policy);  // S3-FIFO, SIEVE, LRU, CLOCK
+  test_partitioners();
+  test_rpc_loopback();
+  std::printf("%d checks, %d failed\n", g_checks, g_failed);
+  return g_failed ? 1 : 0;
+}
