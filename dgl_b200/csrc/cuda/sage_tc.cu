@@ -192,6 +192,7 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
 #define SAGE_TRACE(slot, cond) do { if (trace && blockIdx.x == 0 && (cond)) trace[(slot)] = clock64(); } while (0)
   SAGE_TRACE(0, threadIdx.x == 0);
   const int64_t tile_stride = (int64_t)gridDim.x * R;
+  const int gmax = kStages >= 4 ? 2 : 1;  // chunks per column group: a group occupies 2 * gmax ring slots at once
 
   if (warp < kProducerWarps) {
     // ===================== producers: gather + mean -> swizzled smem A tile =====================
@@ -229,72 +230,63 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
       const int32_t* s_self = s_cnt + kTileM;
       const int32_t* s_nbr = s_self + kTileM;
       const int rows_here = (int)min((int64_t)R, n - tile0);
-      // K is walked in groups of up to two 64-column chunks: a lane group then reads 256 contiguous bytes of a
-      // feature row at once (DRAM page / sector locality) and fills two ring slots in one pass.
-      for (int half = 0; half < 2; ++half) {
-        for (int k0 = 0; k0 < KH; k0 += 2) {
-          const int nch = min(2, KH - k0);
-          const int lpr_shift = nch == 2 ? 4 : 3;  // lanes per row piece: 16 or 8
-          const int rpp = (kProducerWarps * 32) >> lpr_shift;  // rows per pass: 32 or 64
-          const int piece = tid & ((1 << lpr_shift) - 1);
-          const int r0 = tid >> lpr_shift;
-          const int kcl = piece >> 3, c = piece & 7;
-          for (int u = 0; u < nch; ++u) mbar_wait(empty0 + 8 * ((g + u) % kStages), (((g + u) / kStages) & 1) ^ 1);
-          uint8_t* sa = smem + ((g + kcl) % kStages) * stage_bytes;
-          const int col = (k0 + kcl) * kChunkK + c * 8;  // column of this lane's 16 bytes inside the half
-          const __nv_bfloat16* Xc = X + col;
-          __nv_bfloat16* Ao = A_out ? A_out + half * Fp + col : nullptr;
-          const int npass = R / rpp;  // 1..4
-          if (half == 0) {
-            uint4 val[4];
-#pragma unroll
-            for (int pass = 0; pass < 4; ++pass) {
-              const int r = pass * rpp + r0;
-              val[pass] = (pass < npass && r < rows_here) ? __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)s_self[r] * Fp))
-                                                          : make_uint4(0, 0, 0, 0);
-            }
-#pragma unroll
-            for (int pass = 0; pass < 4; ++pass) {
-              const int r = pass * rpp + r0;
-              if (pass < npass) {
-                if (Ao && r < rows_here) *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp) = val[pass];
-                *reinterpret_cast<uint4*>(sa + sw128_off(r, c)) = val[pass];
-              }
-            }
-          } else {
+      // K is walked in column groups of up to two 64-column chunks; for each group the SELF slice and the NEIGHBOUR
+      // slice of the same columns are produced together (ring order: self chunks of the group, then its neighbour
+      // chunks - the TMA warp streams W^T in the same order). A lane group reads 256 contiguous bytes of a feature row
+      // at once (DRAM page / sector locality) and the one self-row load of a pass is in flight together with the
+      // neighbour-row loads instead of costing a separate latency round trip.
+      for (int k0 = 0; k0 < KH; k0 += gmax) {
+        const int nch = min(gmax, KH - k0);
+        const int lpr_shift = nch == 2 ? 4 : 3;  // lanes per row piece: 16 or 8
+        const int rpp = (kProducerWarps * 32) >> lpr_shift;  // rows per pass: 32 or 64
+        const int piece = tid & ((1 << lpr_shift) - 1);
+        const int r0 = tid >> lpr_shift;
+        const int kcl = piece >> 3, c = piece & 7;
+        for (int u = 0; u < 2 * nch; ++u) mbar_wait(empty0 + 8 * ((g + u) % kStages), (((g + u) / kStages) & 1) ^ 1);
+        uint8_t* sa_self = smem + ((g + kcl) % kStages) * stage_bytes;
+        uint8_t* sa_nbr = smem + ((g + nch + kcl) % kStages) * stage_bytes;
+        const int col = (k0 + kcl) * kChunkK + c * 8;  // column of this lane's 16 bytes inside a half
+        const __nv_bfloat16* Xc = X + col;
+        __nv_bfloat16* Ao = A_out ? A_out + col : nullptr;
+        const int npass = R / rpp;  // 1..4
 #pragma unroll 1
-            for (int pass = 0; pass < npass; ++pass) {
-              const int r = pass * rpp + r0;
-              const int cn = s_cnt[r];  // 0 for rows past the live count
-              const int32_t* nb = s_nbr + r * fanout;
-              AccRow acc;
+        for (int pass = 0; pass < npass; ++pass) {
+          const int r = pass * rpp + r0;
+          const bool live = r < rows_here;
+          const int cn = s_cnt[r];  // 0 for rows past the live count
+          const int32_t* nb = s_nbr + r * fanout;
+          uint4 sv = make_uint4(0, 0, 0, 0);
+          if (live) sv = __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)s_self[r] * Fp));
+          AccRow acc;
 #pragma unroll
-              for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
-              for (int j0 = 0; j0 < cn; j0 += kGatherBatch) {
-                uint4 q[kGatherBatch];
+          for (int i = 0; i < 8; ++i) acc.v[i] = 0.f;
+          for (int j0 = 0; j0 < cn; j0 += kGatherBatch) {
+            uint4 q[kGatherBatch];
 #pragma unroll
-                for (int j = 0; j < kGatherBatch; ++j)
-                  q[j] = (j0 + j < cn) ? __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)max(nb[j0 + j], 0) * Fp))
-                                       : make_uint4(0, 0, 0, 0);
+            for (int j = 0; j < kGatherBatch; ++j)
+              q[j] = (j0 + j < cn) ? __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)max(nb[j0 + j], 0) * Fp))
+                                   : make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int j = 0; j < kGatherBatch; ++j) acc_add(acc, q[j]);
-              }
-              const float inv = cn > 0 ? 1.f / (float)cn : 0.f;
-              uint4 val;
-              __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
-#pragma unroll
-              for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc.v[2 * i] * inv, acc.v[2 * i + 1] * inv);
-              if (Ao && r < rows_here) *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp) = val;
-              *reinterpret_cast<uint4*>(sa + sw128_off(r, c)) = val;
-            }
+            for (int j = 0; j < kGatherBatch; ++j) acc_add(acc, q[j]);
           }
-          fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
-          __syncwarp();
-          if (lane == 0)
-            for (int u = 0; u < nch; ++u) mbar_arrive(full0 + 8 * ((g + u) % kStages));
-          SAGE_TRACE(16 + it * 16 + half * KH + k0, tid == 0 && it < 8 && half * KH + k0 < 16);
-          g += nch;
+          const float inv = cn > 0 ? 1.f / (float)cn : 0.f;
+          uint4 val;
+          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc.v[2 * i] * inv, acc.v[2 * i + 1] * inv);
+          if (Ao && live) {
+            *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp) = sv;
+            *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp + Fp) = val;
+          }
+          *reinterpret_cast<uint4*>(sa_self + sw128_off(r, c)) = sv;
+          *reinterpret_cast<uint4*>(sa_nbr + sw128_off(r, c)) = val;
         }
+        fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
+        __syncwarp();
+        if (lane == 0)
+          for (int u = 0; u < 2 * nch; ++u) mbar_arrive(full0 + 8 * ((g + u) % kStages));
+        SAGE_TRACE(16 + it * 16 + k0, tid == 0 && it < 8 && k0 < 16);
+        g += 2 * nch;
       }
     }
   } else if (warp < kTmaWarp) {
@@ -375,12 +367,16 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
     if (lane == 0) {
       uint32_t g = 0;
       for (int64_t tile0 = (int64_t)blockIdx.x * R; tile0 < n; tile0 += tile_stride) {
-        for (int kc = 0; kc < KC; ++kc, ++g) {
-          const int stage = g % kStages;
-          const uint32_t phase = (g / kStages) & 1;
-          mbar_wait(empty0 + 8 * stage, phase ^ 1);
-          mbar_arrive_expect_tx(full0 + 8 * stage, b_bytes);
-          tma_load_2d(smem_u32(smem + stage * stage_bytes + a_bytes), &tmap_w, full0 + 8 * stage, kc * kChunkK, 0);
+        for (int k0 = 0; k0 < KH; k0 += gmax) {  // ring order of the producers: [self chunks | neighbour chunks] per group
+          const int nch = min(gmax, KH - k0);
+          for (int u = 0; u < 2 * nch; ++u, ++g) {
+            const int kc = (u < nch ? 0 : KH) + k0 + (u < nch ? u : u - nch);  // K chunk carried by this ring slot
+            const int stage = g % kStages;
+            const uint32_t phase = (g / kStages) & 1;
+            mbar_wait(empty0 + 8 * stage, phase ^ 1);
+            mbar_arrive_expect_tx(full0 + 8 * stage, b_bytes);
+            tma_load_2d(smem_u32(smem + stage * stage_bytes + a_bytes), &tmap_w, full0 + 8 * stage, kc * kChunkK, 0);
+          }
         }
       }
     }

@@ -139,6 +139,7 @@ class FusedSAGETrainer:
         self._alloc_buffers()
         self.use_graph = use_cuda_graph
         self.graph = None
+        self._side_stream = torch.cuda.Stream(self.dev)
         self._probe_mm()
         self.gpu_launches_per_step = 0
 
@@ -425,13 +426,23 @@ class FusedSAGETrainer:
                          _p(self.labels), _p(self.S[L]), _p(self.n[L]), self.B, self.C, _p(self.dlogits), 0, 0,
                          _p(self.gb[L - 1]), _p(self.loss_dev), _p(self.correct_dev))
         # ---------------- backward
+        # The weight-gradient GEMM of a layer does not feed the dA -> scatter -> dReLU chain that produces the next
+        # layer's dZ, so it runs on a side stream (forked/joined with events, capturable) and overlaps with that chain.
         dZ = self.dlogits16 if self.tc_last else self.dlogits
+        main = torch.cuda.current_stream(self.dev)
+        side = self._side_stream
+        keep = [dZ]  # every dZ stays referenced until the join: the allocator must not recycle a block the side stream reads
         for l in range(L, 0, -1):
             cap, f, Fi = self.caps[l], self.fanouts[l - 1], self.in_dims[l - 1]
             A = self.A[l]
             if self.tc_layer[l - 1]:
                 # weights live as W^T [n_pad, 2*in]: dW^T = dZ^T A, dA = dZ W^T - no transposes materialised
-                self.gWt[l - 1].copy_(self._mm32(dZ.t(), A))
+                if l > 1:
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        self.gWt[l - 1].copy_(self._mm32(dZ.t(), A))
+                else:
+                    self.gWt[l - 1].copy_(self._mm32(dZ.t(), A))
                 self._launch_count += 2
                 dA = torch.mm(dZ, self.Wt[l - 1]) if l > 1 else None
                 dA_dt = dt
@@ -456,6 +467,8 @@ class FusedSAGETrainer:
                 self._launch("dglb200_engine_relu_bwd", "ippplifpp", dt, _p(dH), _p(Hs[l - 1]), _p(self.n[l - 1]),
                              self.caps[l - 1], Fi, float(scale), _p(dZn), _p(self.gb[l - 2]))
                 dZ = dZn
+                keep.append(dZn)
+        main.wait_stream(side)
         # ---------------- gradient all-reduce fused with Adam
         if self.comm is not None:
             self.comm.barrier(0)  # every rank's gradients are complete and visible
