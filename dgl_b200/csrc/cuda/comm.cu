@@ -205,6 +205,149 @@ __global__ void __launch_bounds__(256) p2p_scatter_add_kernel(Peers shards, int6
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Pipelined halo exchange + aggregation in ONE cooperative kernel (static plan, see parallel/p2p.py HaloPlan).
+//   * The plan deduplicated the remote source ids: every halo row crosses NVLink exactly once. The first
+//     `puller_warps` warps of EVERY CTA pull chunks of `chunk_rows` halo rows (taken from an atomic chunk counter) with
+//     16 B peer loads, 8 in flight per lane, and write them behind the local rows of `table`. Remote-load throughput is
+//     bounded per SM by its outstanding-request budget, so the pull is spread over all SMs instead of a few CTAs.
+//   * All other warps (and the pullers once the chunks are gone) take row groups from an atomic work counter. The row
+//     order is INTERIOR rows (all sources local) first, then BOUNDARY rows: interior aggregation overlaps the transfer,
+//     and a warp reaching a boundary group waits on a shared-memory flag that ONE warp per CTA raises after it has seen
+//     the device-wide completed-chunk counter reach n_chunks (one global poller per CTA, nobody scans flags).
+// The halo all-gather of the reference (NCCL all_gather / KVStore pull before the layer) never exists as a separate
+// phase. Cooperative launch guarantees that all pullers are resident, so the wait cannot deadlock; a cycle-count
+// timeout raises the communicator's error flag instead of hanging the GPU.
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned* addr) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(addr) : "memory");
+  return v;
+}
+
+template <typename T, typename I, int VB>
+__global__ void __launch_bounds__(256) halo_pipe_kernel(const I* __restrict__ indptr, const I* __restrict__ indices,
+                                                        const int64_t* __restrict__ order, int64_t n_order,
+                                                        int64_t n_interior, T* table, Peers shards, int64_t shard_rows,
+                                                        const I* __restrict__ halo_ids, int64_t n_halo, int chunk_rows,
+                                                        int puller_warps, unsigned* counters, int F,
+                                                        T* __restrict__ out, int mean, int sub, int group_rows,
+                                                        int* error_flag) {
+  constexpr int VE = VB / sizeof(T);
+  using V = typename std::conditional<VB == 16, uint4, typename std::conditional<VB == 8, uint2, uint32_t>::type>::type;
+  const int nvec = F / VE;
+  const int n_chunks = (int)((n_halo + chunk_rows - 1) / chunk_rows);
+  const int wid = threadIdx.x >> 5, ln = threadIdx.x & 31;
+  __shared__ volatile int halo_ready;
+  if (threadIdx.x == 0) halo_ready = n_chunks == 0 ? 1 : 0;
+  __syncthreads();
+  // ------------------------------------------------ phase A (puller warps): pull chunks over NVLink
+  if (wid < puller_warps && n_chunks > 0) {
+    V* dst_base = reinterpret_cast<V*>(table + shard_rows * (int64_t)F);
+    for (;;) {
+      unsigned c = 0;
+      if (ln == 0) c = atomicAdd(counters + 1, 1u);
+      c = __shfl_sync(0xffffffffu, c, 0);
+      if ((int)c >= n_chunks) break;
+      const int64_t h0 = (int64_t)c * chunk_rows;
+      const int hn = (int)((n_halo - h0) < chunk_rows ? (n_halo - h0) : chunk_rows);
+      const int items = hn * nvec;
+      constexpr int U = 8;
+      for (int base = ln; base < items; base += 32 * U) {
+        V v[U];
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int it = base + k * 32;
+          if (it < items) {
+            const int h = it / nvec;
+            const int vc = it - h * nvec;
+            const int64_t u = halo_ids[h0 + h];
+            const int64_t owner = u / shard_rows;
+            const int64_t lr = u - owner * shard_rows;
+            v[k] = __ldcg(reinterpret_cast<const V*>(reinterpret_cast<const T*>(shards.p[owner]) + lr * F) + vc);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < U; ++k) {
+          const int it = base + k * 32;
+          if (it < items) dst_base[h0 * nvec + it] = v[k];
+        }
+      }
+      __syncwarp();
+      if (ln == 0) {
+        __threadfence();
+        atomicAdd(counters + 2, 1u);  // completed chunks
+      }
+    }
+    if (wid == 0) {  // this CTA's poller: wait for the device-wide completion, then release the CTA's boundary work
+      if (ln == 0) {
+        const long long t0 = clock64();
+        while ((int)ld_acquire_gpu_u32(counters + 2) < n_chunks) {
+          if (clock64() - t0 > 4000000000ll) {
+            if (error_flag) atomicExch(error_flag, 2);
+            break;
+          }
+          __nanosleep(256);
+        }
+        __threadfence();
+        halo_ready = 1;
+      }
+      __syncwarp();
+    }
+  }
+  // ------------------------------------------------ phase B (all warps): aggregate row groups, warp-granular
+  const int rows_per_warp = 32 / sub;
+  const int lane = ln % sub;
+  const int sw = ln / sub;
+  const int64_t n_groups = (n_order + group_rows - 1) / group_rows;
+  bool ready = false;
+  for (;;) {
+    unsigned g32 = 0;
+    if (ln == 0) g32 = atomicAdd(counters, 1u);
+    const int64_t g = __shfl_sync(0xffffffffu, g32, 0);
+    if (g >= n_groups) break;
+    const int64_t r0 = g * group_rows;
+    const int64_t r1 = (r0 + group_rows) < n_order ? (r0 + group_rows) : n_order;
+    if (!ready && r1 > n_interior) {
+      while (!halo_ready) __nanosleep(128);
+      __threadfence();
+      ready = true;
+    }
+    for (int64_t ri = r0 + sw; ri < r1; ri += rows_per_warp) {
+      const int64_t row = order[ri];
+      const int64_t s = indptr[row], t = indptr[row + 1];
+      for (int c = lane; c < nvec; c += sub) {
+        float acc[VE];
+#pragma unroll
+        for (int i = 0; i < VE; ++i) acc[i] = 0.f;
+        int64_t p = s;
+        for (; p + 4 <= t; p += 4) {
+          V v[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) v[k] = __ldcg(reinterpret_cast<const V*>(table + (int64_t)indices[p + k] * F) + c);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const T* q = reinterpret_cast<const T*>(&v[k]);
+#pragma unroll
+            for (int i = 0; i < VE; ++i) acc[i] += to_f<T>(q[i]);
+          }
+        }
+        for (; p < t; ++p) {
+          const V v = __ldcg(reinterpret_cast<const V*>(table + (int64_t)indices[p] * F) + c);
+          const T* q = reinterpret_cast<const T*>(&v);
+#pragma unroll
+          for (int i = 0; i < VE; ++i) acc[i] += to_f<T>(q[i]);
+        }
+        const float sc = mean ? (t > s ? 1.f / (float)(t - s) : 0.f) : 1.f;
+        V o;
+        T* po = reinterpret_cast<T*>(&o);
+#pragma unroll
+        for (int i = 0; i < VE; ++i) po[i] = from_f<T>(acc[i] * sc);
+        reinterpret_cast<V*>(out + row * F)[c] = o;
+      }
+    }
+  }
+}
+
 static Peers make_peers(const void* const* ptrs, int world) {
   Peers p;
   for (int r = 0; r < kMaxPeers; ++r) p.p[r] = r < world ? const_cast<void*>(ptrs[r]) : nullptr;
@@ -319,6 +462,61 @@ DGLB_API int dglb200_comm_halo_spmm(int dtype, int idtype, const void* indptr, c
     else if (dtype == kF16) launch(__half(), I());
     else if (dtype == kF32) launch(float(), I());
     else throw std::runtime_error("halo_spmm: unsupported dtype");
+  });
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}
+
+// One-kernel halo pull + aggregation (HaloPlan). `counters`: four u32 (row-group counter, chunk counter, completed
+// chunks, pad), zeroed here on the stream.
+DGLB_API int dglb200_comm_halo_pipe(int dtype, int idtype, const void* indptr, const void* indices, const void* order,
+                                    int64_t n_order, int64_t n_interior, void* table, const void* const* shard_ptrs,
+                                    int world, int64_t shard_rows, const void* halo_ids, int64_t n_halo, int chunk_rows,
+                                    int puller_warps, void* counters, int F, void* out, int mean, void* error_flag,
+                                    void* stream) {
+  DGLB_TRY
+  cudaStream_t st = (cudaStream_t)stream;
+  if (n_order == 0) return 0;
+  DGLB_CHECK(puller_warps >= 1 && puller_warps <= 8, "halo_pipe: puller warps per CTA must be in [1, 8]");
+  Peers sh = make_peers(shard_ptrs, world);
+  static int sm_count = 0;
+  if (!sm_count) {
+    int dev = 0;
+    DGLB_CUDA_CHECK(cudaGetDevice(&dev));
+    DGLB_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  DGLB_CUDA_CHECK(cudaMemsetAsync(counters, 0, 4 * sizeof(unsigned), st));
+  auto launch = [&](auto tag, auto itag) {
+    using T = decltype(tag);
+    using I = decltype(itag);
+    const int64_t row_bytes = (int64_t)F * sizeof(T);
+    DGLB_CHECK(row_bytes % 4 == 0, "row bytes must be a multiple of 4");
+    const int vb = row_bytes % 16 == 0 ? 16 : (row_bytes % 8 == 0 ? 8 : 4);
+    const int nvec = (int)(row_bytes / vb);
+    int sub = 1;
+    while (sub < nvec && sub < 32) sub <<= 1;
+    int group_rows = (32 / sub) * 8;
+    int chunk = chunk_rows, np = puller_warps, mn = mean, Fv = F;
+    int64_t n_ord = n_order, n_int = n_interior, srows = shard_rows, nh = n_halo;
+    const void *ip = indptr, *ix = indices, *od = order, *hid = halo_ids;
+    void *tb = table, *ct = counters, *o = out, *ef = error_flag;
+    void* args[] = {&ip, &ix, &od, &n_ord, &n_int, &tb, &sh, &srows, &hid, &nh, &chunk, &np, &ct, &Fv, &o, &mn, &sub, &group_rows, &ef};
+    auto go = [&](auto kern) {
+      int per_sm = 0;
+      DGLB_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+      if (per_sm > 6) per_sm = 6;
+      const int blocks = sm_count * (per_sm < 1 ? 1 : per_sm);
+      DGLB_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kern, dim3(blocks), dim3(256), args, 0, st));
+    };
+    if (vb == 16) go(halo_pipe_kernel<T, I, 16>);
+    else if (vb == 8) go(halo_pipe_kernel<T, I, 8>);
+    else go(halo_pipe_kernel<T, I, 4>);
+  };
+  DGLB_ID_SWITCH(idtype, I, {
+    if (dtype == kBF16) launch(__nv_bfloat16(), I());
+    else if (dtype == kF16) launch(__half(), I());
+    else if (dtype == kF32) launch(float(), I());
+    else throw std::runtime_error("halo_pipe: unsupported dtype");
   });
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH

@@ -97,6 +97,10 @@ class P2PComm:
         self._grad = self.alloc(int(numel) * 4)
         return self._grad.view(torch.float32)[:numel]
 
+    def halo_plan(self, indptr, indices_global, shard_rows):
+        """Build the static halo-exchange plan of this rank's partition (see ``HaloPlan``)."""
+        return HaloPlan(self, indptr, indices_global, shard_rows)
+
     def peer_grad_ptrs(self):
         return self._grad.ptr_array
 
@@ -156,3 +160,73 @@ class P2PComm:
             self.lib.fn("dglb200_comm_p2p_scatter_add", "ipilplpip")(
                 id_code(idx.dtype), shards.ptr_table(), self.world_size, int(shard_rows), idx.data_ptr(),
                 idx.shape[0], vals.data_ptr(), int(vals.shape[1]), loader.stream_ptr())
+
+
+class HaloPlan:
+    """Static halo-exchange plan of one partition (the graph structure does not change between layers / steps).
+
+    The reference moves halo features with collectives before every layer (DistDGL pulls them through the KVStore,
+    GraphBolt's CooperativeConv does an all-to-all, python/dgl/graphbolt/impl/cooperative_conv.py:27-57); an NCCL
+    all-gather of the whole table is the dense equivalent. Here the plan
+      * deduplicates the remote source ids once: every halo row crosses NVLink exactly once per aggregation;
+      * relabels the sources into the local table ``[local rows | halo rows]``;
+      * orders the destination rows INTERIOR first (all sources local), then BOUNDARY rows,
+    and ``spmm`` runs ONE cooperative kernel (csrc/cuda/comm.cu ``halo_pipe_kernel``) in which some warps of every
+    CTA pull the halo chunks from the owners' HBM with peer loads while all other warps aggregate the interior rows;
+    boundary rows start as soon as the device-wide chunk counter says the halo is complete - no NCCL call, no second
+    launch, no host synchronisation.
+    """
+
+    MAX_CHUNKS = 2048
+
+    def __init__(self, comm: "P2PComm", indptr, indices_global, shard_rows, puller_warps=None):
+        self.comm, self.rows = comm, int(shard_rows)
+        dev = comm.device
+        self.indptr = indptr.contiguous()
+        idx = indices_global.long()
+        lo = comm.rank * self.rows
+        remote = (idx < lo) | (idx >= lo + self.rows)
+        halo = torch.unique(idx[remote])                      # sorted => grouped by owner (range partition)
+        self.halo_ids = halo.to(indices_global.dtype).contiguous()
+        self.n_halo = int(halo.shape[0])
+        ext = idx - lo
+        if self.n_halo:
+            ext[remote] = self.rows + torch.searchsorted(halo, idx[remote])
+        self.indices = ext.to(indices_global.dtype).contiguous()
+        n = int(indptr.shape[0]) - 1
+        has_remote = torch.zeros(n, dtype=torch.bool, device=dev)
+        if idx.numel():
+            deg = (indptr[1:] - indptr[:-1]).long()
+            row_of = torch.repeat_interleave(torch.arange(n, device=dev), deg)
+            has_remote[row_of[remote]] = True
+        self.order = torch.sort(has_remote.to(torch.uint8), stable=True)[1].contiguous()   # interior rows first
+        self.n_interior = n - int(has_remote.sum())
+        m = torch.tensor([self.n_halo], device=dev)
+        if comm.world_size > 1:
+            dist.all_reduce(m, op=dist.ReduceOp.MAX, group=comm.group)
+        self.halo_cap = int(m.item())
+        self.chunk_rows = max(64, -(-self.n_halo // self.MAX_CHUNKS))
+        self.counters = torch.zeros(4, dtype=torch.int32, device=dev)
+        # measured on 2xB200 (profiles/comm_2gpu.json): with (almost) no interior rows every warp should pull first
+        self.puller_warps = int(puller_warps) if puller_warps else (8 if self.n_interior * 20 < n else 4)
+
+    def alloc_features(self, feat_dim, dtype):
+        """Symmetric feature buffer with room for the halo rows behind the local shard. Returns (buffer, table);
+        ``table[:rows]`` is this rank's shard (what the peers read), ``table[rows:]`` receives the halo rows."""
+        es = torch.empty(0, dtype=dtype).element_size()
+        buf = self.comm.alloc((self.rows + self.halo_cap) * feat_dim * es)
+        table = buf.view(dtype)[: (self.rows + self.halo_cap) * feat_dim].view(self.rows + self.halo_cap, feat_dim)
+        return buf, table
+
+    def spmm(self, buf, table, out, mean=True):
+        """out[d] = sum / mean over the in-neighbours of d of the (distributed) feature rows. The caller must make sure
+        every rank has finished writing its local rows (``comm.barrier``) before calling, and must not overwrite them
+        before every rank has finished (another ``comm.barrier``)."""
+        F = int(table.shape[1])
+        self.comm.lib.fn("dglb200_comm_halo_pipe", "iipppll" "ppil" "pliip" "ipipp")(
+            dtype_code(table.dtype), id_code(self.indptr.dtype), self.indptr.data_ptr(), self.indices.data_ptr(),
+            self.order.data_ptr(), int(self.order.shape[0]), self.n_interior,
+            table.data_ptr(), buf.ptr_table(), self.comm.world_size, self.rows,
+            self.halo_ids.data_ptr(), self.n_halo, self.chunk_rows, self.puller_warps, self.counters.data_ptr(),
+            F, out.data_ptr(), 1 if mean else 0, self.comm._error.data_ptr(), loader.stream_ptr())
+        return out

@@ -61,6 +61,12 @@ def test_p2p_single_rank_kernels():
     comm.halo_spmm(indptr, indices, shard, n, F, torch.bfloat16, out, mean=True)
     ref = dgl.ops.copy_u_mean(g, x.float())
     assert (out.float() - ref).abs().max() < 0.05
+    plan = comm.halo_plan(indptr, indices, n)      # single rank: no halo, every row is interior
+    pbuf, table = plan.alloc_features(F, torch.bfloat16)
+    table[:n].copy_(x)
+    out2 = torch.empty_like(out)
+    plan.spmm(pbuf, table, out2, mean=True)
+    assert plan.n_halo == 0 and (out2.float() - ref).abs().max() < 0.05
     dsh = comm.alloc(n * F * 4)
     dx = dsh.view(torch.float32)[: n * F].view(n, F)
     dout = torch.randn(n, F, device=DEV)
