@@ -223,6 +223,15 @@ def gsddmm(coo, op, lhs, rhs, lhs_target="u", rhs_target="v"):
     out = torch.empty((E, F), dtype=ref.dtype, device=ref.device)
     if E > 0 and F > 0:
         lib, is_cuda = _dev_lib(ref)
+        if is_cuda and op == "dot" and tuple(bc) == (1, F, 1, F) and ref.element_size() <= 4:
+            # rows that are not a multiple of 16 bytes (e.g. 41 classes) would force scalar loads on E * rsz elements:
+            # zero-pad the reduce dimension of the (much smaller) node operands once and take the vector kernels
+            vec = 16 // ref.element_size()
+            if rsz % vec and rsz > vec and E >= 4 * max(l2.shape[0], r2.shape[0]):
+                pad = vec - rsz % vec
+                l2 = torch.nn.functional.pad(l2.view(l2.shape[0], F, rsz), (0, pad)).reshape(l2.shape[0], -1)
+                r2 = torch.nn.functional.pad(r2.view(r2.shape[0], F, rsz), (0, pad)).reshape(r2.shape[0], -1)
+                rsz += pad
         args = [OPS[op], dtype_code(ref.dtype), id_code(row.dtype), _p(row), _p(col), E, _p(l2), _p(r2), _p(out),
                 TARGETS[lhs_target], TARGETS[rhs_target], F, rsz, *bc]
         if is_cuda:

@@ -115,6 +115,155 @@ __global__ void __launch_bounds__(256) sddmm_dot_vec_kernel(const I* __restrict_
   }
 }
 
+// Edge-major vectorised dot (multi-head attention scores / dE of u_mul_e_sum): ONE sub-warp per edge covers all heads.
+// Each lane owns 16-byte pieces of the [F heads x rsz] rows of both endpoints (coalesced 16 B x sub loads, the edge's
+// endpoints are read once, no per-(edge, head) index arithmetic), partial products are reduced inside the lph lanes of
+// a head with xor shuffles and the F results of an edge are written by the head-leader lanes. U edges are in flight
+// per sub-warp so the dependent endpoint -> row round trips of different edges overlap.
+// Requires: rsz * sizeof(T) = lph * 16 with lph a power of two <= 32, no broadcasting (lmod == rmod == F).
+template <typename T, typename I, int U>
+__global__ void __launch_bounds__(256) sddmm_dot_edge_kernel(const I* __restrict__ row, const I* __restrict__ col,
+                                                             int64_t E, const T* __restrict__ lhs,
+                                                             const T* __restrict__ rhs, T* __restrict__ out, int lt,
+                                                             int rt, int F, int rsz, int sub, int lph) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int gpb = blockDim.x / sub;
+  const int lane = threadIdx.x % sub;
+  const int nvec = F * lph;                 // 16-byte pieces per row
+  const int64_t row_elems = (int64_t)F * rsz;
+  const int64_t ngroups = (int64_t)gridDim.x * gpb;
+  for (int64_t e0 = (int64_t)blockIdx.x * gpb + threadIdx.x / sub; e0 < E; e0 += ngroups * U) {
+    const T* lp[U];
+    const T* rp[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = e0 + u * ngroups;
+      lp[u] = nullptr;
+      if (e < E) {
+        lp[u] = lhs + sel<I>(lt, row, col, e) * row_elems;
+        rp[u] = rhs + sel<I>(rt, row, col, e) * row_elems;
+      }
+    }
+    for (int j = lane; j < nvec; j += sub) {  // sub >= lph, so a head never straddles two iterations
+      float acc[U];
+      uint4 a[U], b[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (lp[u]) {
+          a[u] = __ldg(reinterpret_cast<const uint4*>(lp[u]) + j);
+          b[u] = __ldg(reinterpret_cast<const uint4*>(rp[u]) + j);
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        acc[u] = 0.f;
+        if (lp[u]) {
+          const T* av = reinterpret_cast<const T*>(&a[u]);
+          const T* bv = reinterpret_cast<const T*>(&b[u]);
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[u] = fmaf(to_f<T>(av[q]), to_f<T>(bv[q]), acc[u]);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        for (int o = lph >> 1; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+        if (lp[u] && (j & (lph - 1)) == 0) out[(e0 + u * ngroups) * F + j / lph] = from_f<T>(acc[u]);
+      }
+    }
+  }
+}
+
+// Single-head dot with an arbitrary reduce length (rows not 16-byte sized): sub-warp per edge, scalar coalesced loads,
+// U edges in flight.
+template <typename T, typename I, int U>
+__global__ void __launch_bounds__(256) sddmm_dot1_kernel(const I* __restrict__ row, const I* __restrict__ col, int64_t E,
+                                                         const T* __restrict__ lhs, const T* __restrict__ rhs,
+                                                         T* __restrict__ out, int lt, int rt, int rsz, int sub) {
+  const int gpb = blockDim.x / sub;
+  const int lane = threadIdx.x % sub;
+  const int64_t ngroups = (int64_t)gridDim.x * gpb;
+  for (int64_t e0 = (int64_t)blockIdx.x * gpb + threadIdx.x / sub; e0 < E; e0 += ngroups * U) {
+    const T* lp[U];
+    const T* rp[U];
+    float acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = e0 + u * ngroups;
+      lp[u] = nullptr;
+      acc[u] = 0.f;
+      if (e < E) {
+        lp[u] = lhs + sel<I>(lt, row, col, e) * rsz;
+        rp[u] = rhs + sel<I>(rt, row, col, e) * rsz;
+      }
+    }
+    for (int k = lane; k < rsz; k += sub) {
+      float a[U], b[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (lp[u]) {
+          a[u] = to_f<T>(__ldg(lp[u] + k));
+          b[u] = to_f<T>(__ldg(rp[u] + k));
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (lp[u]) acc[u] = fmaf(a[u], b[u], acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      for (int o = sub >> 1; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      if (lane == 0 && lp[u]) out[e0 + u * ngroups] = from_f<T>(acc[u]);
+    }
+  }
+}
+
+// Single-head dot, rows a multiple of 16 bytes (any length): 16-byte loads, sub lanes stride over the row.
+template <typename T, typename I, int U>
+__global__ void __launch_bounds__(256) sddmm_dot1_vec_kernel(const I* __restrict__ row, const I* __restrict__ col, int64_t E,
+                                                             const T* __restrict__ lhs, const T* __restrict__ rhs,
+                                                             T* __restrict__ out, int lt, int rt, int rsz, int sub) {
+  constexpr int VEC = 16 / sizeof(T);
+  const int gpb = blockDim.x / sub;
+  const int lane = threadIdx.x % sub;
+  const int nvec = rsz / VEC;
+  const int64_t ngroups = (int64_t)gridDim.x * gpb;
+  for (int64_t e0 = (int64_t)blockIdx.x * gpb + threadIdx.x / sub; e0 < E; e0 += ngroups * U) {
+    const uint4* lp[U];
+    const uint4* rp[U];
+    float acc[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int64_t e = e0 + u * ngroups;
+      lp[u] = nullptr;
+      acc[u] = 0.f;
+      if (e < E) {
+        lp[u] = reinterpret_cast<const uint4*>(lhs + sel<I>(lt, row, col, e) * rsz);
+        rp[u] = reinterpret_cast<const uint4*>(rhs + sel<I>(rt, row, col, e) * rsz);
+      }
+    }
+    for (int j = lane; j < nvec; j += sub) {
+      uint4 a[U], b[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (lp[u]) {
+          a[u] = __ldg(lp[u] + j);
+          b[u] = __ldg(rp[u] + j);
+        }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (lp[u]) {
+          const T* av = reinterpret_cast<const T*>(&a[u]);
+          const T* bv = reinterpret_cast<const T*>(&b[u]);
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) acc[u] = fmaf(to_f<T>(av[q]), to_f<T>(bv[q]), acc[u]);
+        }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      for (int o = sub >> 1; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+      if (lane == 0 && lp[u]) out[e0 + u * ngroups] = from_f<T>(acc[u]);
+    }
+  }
+}
+
 }  // namespace dglb
 
 using namespace dglb;
@@ -128,7 +277,39 @@ DGLB_API int dglb200_cuda_gsddmm(int op, int dtype, int idtype, const void* row,
   DGLB_FLOAT_SWITCH(dtype, T, {
     DGLB_ID_SWITCH(idtype, I, {
       constexpr int kVec = 16 / (int)sizeof(T);
-      if (op == kDot && sizeof(T) <= 4 && rsz % kVec == 0 && ((uintptr_t)lhs % 16 == 0) && ((uintptr_t)rhs % 16 == 0)) {
+      const int64_t lph64 = rsz / kVec;
+      const bool plain = lmod == F && rmod == F && ldiv == 1 && rdiv == 1;  // no broadcasting between the operands
+      if (op == kDot && sizeof(T) <= 4 && plain && rsz % kVec == 0 && lph64 >= 1 && lph64 <= 32 && (lph64 & (lph64 - 1)) == 0 &&
+          F * lph64 <= 1024 && ((uintptr_t)lhs % 16 == 0) && ((uintptr_t)rhs % 16 == 0)) {
+        const int lph = (int)lph64;
+        int sub = lph;
+        while (sub < (int)(F * lph) && sub < 32) sub <<= 1;
+        const int gpb = 256 / sub;
+        int64_t blocks = (E + (int64_t)gpb * 4 - 1) / ((int64_t)gpb * 4);
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        if (blocks < 1) blocks = 1;
+        sddmm_dot_edge_kernel<T, I, 4><<<(unsigned)blocks, 256, 0, st>>>((const I*)row, (const I*)col, E, (const T*)lhs,
+                                                                         (const T*)rhs, (T*)out, lt, rt, (int)F, (int)rsz, sub, lph);
+      } else if (op == kDot && sizeof(T) <= 4 && F == 1 && lmod == 1 && rmod == 1 && rsz % kVec == 0 && rsz < (1 << 30) &&
+                 ((uintptr_t)lhs % 16 == 0) && ((uintptr_t)rhs % 16 == 0)) {
+        int sub = 1;
+        while (sub * kVec < rsz && sub < 32) sub <<= 1;
+        const int gpb = 256 / sub;
+        int64_t blocks = (E + (int64_t)gpb * 4 - 1) / ((int64_t)gpb * 4);
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        if (blocks < 1) blocks = 1;
+        sddmm_dot1_vec_kernel<T, I, 4><<<(unsigned)blocks, 256, 0, st>>>((const I*)row, (const I*)col, E, (const T*)lhs,
+                                                                         (const T*)rhs, (T*)out, lt, rt, (int)rsz, sub);
+      } else if (op == kDot && sizeof(T) <= 4 && F == 1 && lmod == 1 && rmod == 1 && rsz < (1 << 30)) {
+        int sub = 1;
+        while (sub < rsz && sub < 32) sub <<= 1;
+        const int gpb = 256 / sub;
+        int64_t blocks = (E + (int64_t)gpb * 4 - 1) / ((int64_t)gpb * 4);
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        if (blocks < 1) blocks = 1;
+        sddmm_dot1_kernel<T, I, 4><<<(unsigned)blocks, 256, 0, st>>>((const I*)row, (const I*)col, E, (const T*)lhs,
+                                                                     (const T*)rhs, (T*)out, lt, rt, (int)rsz, sub);
+      } else if (op == kDot && sizeof(T) <= 4 && rsz % kVec == 0 && ((uintptr_t)lhs % 16 == 0) && ((uintptr_t)rhs % 16 == 0)) {
         int sub = 1;
         while (sub * kVec < rsz && sub < 32) sub <<= 1;
         const int gpb = 256 / sub;

@@ -13,6 +13,11 @@ def farthest_point_sampler(pos, npoints, start_idx=None):
     """pos: [B, N, C] -> indices [B, npoints]; iterative FPS, each step one batched distance update."""
     B, N, C = pos.shape
     dev = pos.device
+    if pos.is_cuda and C <= 16 and pos.dtype in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
+        from ._graph_kernels import fps
+        start = (torch.randint(0, N, (B,), device=dev) if start_idx is None
+                 else torch.full((B,), int(start_idx), device=dev, dtype=torch.long))
+        return fps(pos, int(npoints), start)   # one CTA per cloud, whole loop in one launch
     dist = torch.full((B, N), float("inf"), device=dev, dtype=pos.dtype)
     if start_idx is None:
         cur = torch.randint(0, N, (B,), device=dev)
@@ -33,6 +38,18 @@ def neighbor_matching(graph, e_weights=None, relabel_idx=True):
     if not graph.is_homogeneous:
         raise DGLError("The graph should be homogeneous")
     n = graph.num_nodes()
+    if graph.device.type == "cuda":
+        # handshake matching rounds on the symmetrised adjacency (csrc/cuda/graph_kernels.cu match_*_kernel)
+        from . import random as dgl_random
+        from ._graph_kernels import neighbor_matching as _nm
+        from .transforms.functional import to_bidirected_coo
+        su, sv, sw = to_bidirected_coo(graph, e_weights)
+        from .graph_index import coo_to_csr
+        indptr, indices, eids = coo_to_csr(su, sv, n, graph.idtype)
+        res = _nm(indptr, indices, eids, sw, n, dgl_random.next_seed())
+        if relabel_idx:
+            res = torch.unique(res, return_inverse=True)[1].to(graph.idtype)
+        return res
     u, v = graph.edges()
     u, v = u.cpu().tolist(), v.cpu().tolist()
     w = e_weights.cpu().tolist() if e_weights is not None else None

@@ -35,10 +35,13 @@ def coo_to_csr(row, col, num_rows, idtype):
     else:
         perm = _stable_argsort(row)
         srow, scol = row[perm], col[perm]
+    eids = perm.to(idtype) if perm is not None else None
+    if row.is_cuda and row.dtype == idtype:
+        from ._graph_kernels import row_counts_to_indptr
+        return row_counts_to_indptr(srow.contiguous(), num_rows), scol.contiguous(), eids
     counts = torch.bincount(srow.long(), minlength=num_rows)
     indptr = torch.zeros(num_rows + 1, dtype=torch.int64, device=row.device)
     torch.cumsum(counts, 0, out=indptr[1:])
-    eids = perm.to(idtype) if perm is not None else None
     return indptr.to(idtype), scol.contiguous(), eids
 
 
@@ -46,7 +49,7 @@ class UnitGraph:
     """One relation's adjacency. Edge ids are positions in the COO arrays."""
 
     __slots__ = ("num_src", "num_dst", "idtype", "_coo", "_csr", "_csc", "_formats", "_pinned", "_row_sorted",
-                 "_degs")
+                 "_degs", "_rev_of", "_dst_view")
 
     def __init__(self, num_src, num_dst, idtype, coo=None, csr=None, csc=None, formats=ALL_FORMATS):
         self.num_src = int(num_src)
@@ -58,6 +61,8 @@ class UnitGraph:
         self._formats = tuple(formats)
         self._pinned = False
         self._degs = {}
+        self._dst_view = None
+        self._rev_of = None  # set on reversed views: formats they build are cached on the viewed graph too
 
     # ---- construction -------------------------------------------------
     @staticmethod
@@ -150,6 +155,8 @@ class UnitGraph:
             row, col = self.coo() if self._coo is not None or "coo" in self._formats else self._coo_temp()
             self._csr = coo_to_csr(row, col, self.num_src, self.idtype)
             self._post_create(self._csr)
+            if self._rev_of is not None and self._rev_of._csc is None and "csc" in self._rev_of._formats:
+                self._rev_of._csc = self._csr   # a format built on a reversed VIEW is cached on the graph it views
         return self._csr
 
     def csc(self):
@@ -159,6 +166,8 @@ class UnitGraph:
             row, col = self.coo() if self._coo is not None or "coo" in self._formats else self._coo_temp()
             self._csc = coo_to_csr(col, row, self.num_dst, self.idtype)
             self._post_create(self._csc)
+            if self._rev_of is not None and self._rev_of._csr is None and "csr" in self._rev_of._formats:
+                self._rev_of._csr = self._csc
         return self._csc
 
     def _coo_temp(self):
@@ -214,12 +223,28 @@ class UnitGraph:
         return d
 
     # ---- transforms -----------------------------------------------------
+    def dst_sorted_view(self):
+        """(view, eid_map): a relation with the same edges whose edge ids are the positions of this graph's CSC, i.e.
+        edges grouped by destination. g-SpMM / edge-softmax on the view need no edge-id indirection and g-SDDMM writes
+        its result already in that order, so a layer that creates AND consumes its edge data internally (attention)
+        never permutes an [E, ...] tensor. ``eid_map[i]`` = original id of view edge i (None if already ordered).
+        The view is cached; the formats it builds (its CSR for the backward pass) live as long as the graph."""
+        indptr, indices, eids = self.csc()
+        if eids is None:
+            return self, None
+        v = getattr(self, "_dst_view", None)
+        if v is None:
+            v = UnitGraph.from_csc(self.num_src, self.num_dst, indptr, indices, None, ALL_FORMATS)
+            self._dst_view = v
+        return v, eids
+
     def reverse(self):
         """Transposed relation sharing storage (CSR <-> CSC swap)."""
         g = UnitGraph(self.num_dst, self.num_src, self.idtype,
                       coo=None if self._coo is None else (self._coo[1], self._coo[0]),
                       csr=self._csc, csc=self._csr, formats=_swap_formats(self._formats))
         g._pinned = self._pinned
+        g._rev_of = self
         return g
 
     def _map(self, fn):

@@ -1029,6 +1029,19 @@ class DGLGraph:
     def local_var(self):
         return self.clone()
 
+    def dst_sorted_view(self):
+        """(graph, eid_map) for single-relation graphs: same nodes / node frames, edges re-numbered in CSC order (see
+        ``UnitGraph.dst_sorted_view``); edge frames of the view start empty. Used by attention layers so that scores,
+        softmax and the weighted aggregation all run in one edge order without permuting [E, heads] tensors."""
+        if len(self._graphs) != 1:
+            raise DGLError("dst_sorted_view needs a graph with a single relation")
+        ug, emap = self._graphs[0].dst_sorted_view()
+        if emap is None:
+            return self, None
+        from .frame import Frame
+        g = self._clone_with([ug], self._node_frames, [Frame(num_rows=ug.num_edges())])
+        return g, emap
+
     @contextmanager
     def local_scope(self):
         old_n = self._node_frames

@@ -24,6 +24,26 @@ def _zero_in_degree_check(graph, allow):
                        "and let the code run.")
 
 
+def _attention_view(graph, edge_weight=None):
+    """(graph to compute on, eid map, edge weight in that order): CUDA graphs with one relation are swapped for their
+    destination-sorted view so that scores / softmax / aggregation share one edge order (no [E, heads] permutations)."""
+    if graph.device.type != "cuda" or len(graph.canonical_etypes) != 1:
+        return graph, None, edge_weight
+    view, emap = graph.dst_sorted_view()
+    if emap is not None and edge_weight is not None:
+        edge_weight = edge_weight[emap.long()]
+    return view, emap, edge_weight
+
+
+def _attention_to_eid_order(a, emap):
+    if emap is None:
+        return a
+    out = torch.empty_like(a)
+    out[emap.long()] = a
+    return out
+
+
+
 class GATConv(nn.Module):
     r"""Graph attention layer (Velickovic et al.): e_ij = LeakyReLU(a^T [W h_i || W h_j]) (reference gatconv.py:14-365)."""
 
@@ -82,8 +102,9 @@ class GATConv(nn.Module):
         self._allow_zero_in_degree = set_value
 
     def forward(self, graph, feat, edge_weight=None, get_attention=False):
+        _zero_in_degree_check(graph, self._allow_zero_in_degree)
+        graph, emap, edge_weight = _attention_view(graph, edge_weight)
         with graph.local_scope():
-            _zero_in_degree_check(graph, self._allow_zero_in_degree)
             if isinstance(feat, tuple):
                 src_prefix_shape = feat[0].shape[:-1]
                 dst_prefix_shape = feat[1].shape[:-1]
@@ -122,7 +143,7 @@ class GATConv(nn.Module):
             if self.activation:
                 rst = self.activation(rst)
             if get_attention:
-                return rst, graph.edata["a"]
+                return rst, _attention_to_eid_order(graph.edata["a"], emap)
             return rst
 
 

@@ -10,15 +10,18 @@ import torch.nn as nn
 
 from ... import function as fn
 from ...base import DGLError
-from ...ops import edge_softmax, gather_mm, segment_mm
+from ...ops import edge_softmax, gather_mm, segment_mm, u_mul_e_sum
+from ..._graph_kernels import keyed_gather
 from ..linear import TypedLinear
 
 
 class RelGraphConv(nn.Module):
     r"""R-GCN layer: h_i' = sigma(sum_r sum_{j in N_r(i)} e_ji W_r h_j + W_0 h_i).
 
-    The typed message ``W_{etype} h_src`` is computed edge-parallel through TypedLinear (grouped GEMM) and
-    reduced with one copy_e-sum g-SpMM; with ``presorted=True`` edges grouped by type use segment_mm."""
+    Two execution plans: (i) basis regulariser -> aggregate first (``_aggregate_first``: B weighted g-SpMMs + one dense
+    GEMM, no per-edge message tensor); (ii) otherwise the typed message ``W_{etype} h_src`` is computed edge-parallel
+    through TypedLinear (tcgen05 grouped GEMM, ``segment_mm`` when ``presorted=True``) and reduced with one copy_e-sum
+    g-SpMM (reference relgraphconv.py:13-190 always runs plan (ii))."""
 
     def __init__(self, in_feat, out_feat, num_rels, regularizer=None, num_bases=None, bias=True, activation=None,
                  self_loop=True, dropout=0.0, layer_norm=False):
@@ -46,15 +49,34 @@ class RelGraphConv(nn.Module):
             m = m * edges.data["norm"]
         return {"m": m}
 
+    def _aggregate_first(self, g, feat, etypes, norm):
+        """Basis regulariser, W_r = sum_b c_rb V_b:  sum_r sum_{j in N_r(i)} e_ji W_r h_j
+        = sum_b ( sum_{(j -> i)} e_ji c_{r(ji), b} h_j ) V_b  - one weighted g-SpMM per basis over the WHOLE edge set
+        (edge weight = coefficient of the edge's relation) followed by ONE dense GEMM [N, B*in] @ [B*in, out].
+        No [E, out] message tensor exists (the reference materialises it: 42 M edges x 349 classes on ogbn-mag)."""
+        lin = self.linear_r
+        B = lin.num_bases
+        ce = keyed_gather(lin.coeff, etypes)                            # [E, B]; backward = keyed sum, not index_add
+        if norm is not None:
+            ce = ce * norm.reshape(-1, 1)
+        aggs = [u_mul_e_sum(g, feat, ce[:, b:b + 1].contiguous()) for b in range(B)]
+        return torch.cat(aggs, 1) @ lin.W.reshape(B * lin.in_size, lin.out_size)
+
     def forward(self, g, feat, etypes, norm=None, *, presorted=False):
         self.presorted = presorted
+        lin = self.linear_r
+        agg_first = (lin.regularizer == "basis" and feat.dim() == 2 and feat.is_floating_point()
+                     and lin.num_bases * lin.in_size * g.num_dst_nodes() <= 4 * lin.out_size * max(g.num_edges(), 1))
         with g.local_scope():
-            g.srcdata["h"] = feat
-            if norm is not None:
-                g.edata["norm"] = norm
-            g.edata["etype"] = etypes
-            g.update_all(self.message, fn.sum("m", "h"))
-            h = g.dstdata["h"]
+            if agg_first:
+                h = self._aggregate_first(g, feat, etypes, norm)
+            else:
+                g.srcdata["h"] = feat
+                if norm is not None:
+                    g.edata["norm"] = norm
+                g.edata["etype"] = etypes
+                g.update_all(self.message, fn.sum("m", "h"))
+                h = g.dstdata["h"]
             if self.layer_norm:
                 h = self.layer_norm_weight(h)
             if self.bias:

@@ -202,7 +202,13 @@ class NDArrayPartition:
         return idxs + int(self._ranges[part_id])
 
     def generate_permutation(self, idxs):
-        """Permutation grouping ``idxs`` by owner + per-part counts (basis of sparse all-to-all)."""
+        """Permutation grouping ``idxs`` by owner + per-part counts (basis of sparse all-to-all).
+        CUDA inputs: owner/count kernel + radix sort on ceil(log2 P) bits (csrc/cuda/graph_kernels.cu)."""
+        if idxs.is_cuda and idxs.dtype in (torch.int32, torch.int64):
+            from ._graph_kernels import partition_owner, partition_perm
+            own, counts, _ = partition_owner(idxs.contiguous(), self._num_parts,
+                                             self._ranges if self._mode == "range" else None)
+            return partition_perm(own, self._num_parts), counts
         own = self.owner(idxs)
         perm = torch.sort(own, stable=True)[1]
         counts = torch.bincount(own, minlength=self._num_parts)

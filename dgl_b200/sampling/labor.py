@@ -19,6 +19,13 @@ from .neighbor import _build_result
 def _labor_rel(ug, seeds, fanout, prob, importance_sampling, random_seed, seed2_contribution=0.0):
     indptr, indices, eids = ug.csc()
     dev = seeds.device
+    if (dev.type == "cuda" and prob is None and importance_sampling == 0 and not seed2_contribution
+            and indptr.is_cuda and seeds.dtype == indptr.dtype):
+        # LABOR-0: per-source variate r_t <= fanout / deg(s); count + fill kernels (csrc/cuda/graph_kernels.cu)
+        from .._graph_kernels import labor0
+        src, pos, eid, counts = labor0(indptr, indices, eids, seeds.contiguous(), fanout, random_seed)
+        w = 1.0 / counts[pos.long()].clamp(min=1).float()     # Hajek-normalised: equal inclusion prob inside a seed
+        return src, seeds[pos.long()], eid, w
     indptr_d, indices_d = indptr.to(dev), indices.to(dev)
     s = indptr_d[seeds.long()].long()
     deg = indptr_d[seeds.long() + 1].long() - s

@@ -14,6 +14,8 @@ def global_uniform_negative_sampling(g, num_samples, exclude_self_loops=True, re
     ns, nd = ug.num_src, ug.num_dst
     if exclude_self_loops and c[0] != c[2]:
         exclude_self_loops = False
+    if g.device.type == "cuda":
+        return _neg_cuda(g, ug, ns, nd, int(num_samples), exclude_self_loops, replace, redundancy)
     row, col = ug.coo()
     dev = row.device
     key = torch.sort(row.long() * nd + col.long())[0]
@@ -55,3 +57,33 @@ def global_uniform_negative_sampling(g, num_samples, exclude_self_loops=True, re
     u = torch.cat(got_u)[:want].to(g.idtype)
     v = torch.cat(got_v)[:want].to(g.idtype)
     return u, v
+
+
+def _neg_cuda(g, ug, ns, nd, want, exclude_self_loops, replace, redundancy):
+    """Rejection sampling on the device (csrc/cuda/graph_kernels.cu neg_sample_kernel): one trial per thread, the
+    edge test walks the CSR row of u; accepted pairs are compacted (and de-duplicated unless ``replace``)."""
+    from .. import random as dgl_random
+    from .._graph_kernels import neg_sample
+    indptr, indices, _ = ug.csr()
+    redundancy = 1.3 if redundancy is None else 1 + redundancy
+    got_u, got_v, seen, have = [], [], None, 0
+    for _ in range(8):
+        trials = int((want - have) * redundancy) + 16
+        u, v, ok = neg_sample(indptr, indices, False, ns, nd, exclude_self_loops, trials, dgl_random.next_seed())
+        u, v = u[ok], v[ok]
+        if not replace:
+            q = u.long() * nd + v.long()
+            if seen is not None:
+                fresh = ~torch.isin(q, seen)
+                u, v, q = u[fresh], v[fresh], q[fresh]
+            uq, inv = torch.unique(q, return_inverse=True)
+            first = torch.full((uq.shape[0],), q.shape[0], device=q.device, dtype=torch.long)
+            first.scatter_reduce_(0, inv, torch.arange(q.shape[0], device=q.device), reduce="amin")
+            first = torch.sort(first)[0]
+            u, v, q = u[first], v[first], q[first]
+            seen = q if seen is None else torch.cat([seen, q])
+        got_u.append(u); got_v.append(v)
+        have += u.shape[0]
+        if have >= want:
+            break
+    return torch.cat(got_u)[:want].to(g.idtype), torch.cat(got_v)[:want].to(g.idtype)

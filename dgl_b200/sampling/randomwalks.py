@@ -58,6 +58,22 @@ def random_walk(g, nodes, *, metapath=None, length=None, prob=None, restart_prob
     idt = g.idtype
     dev = g.device
     nodes = _to_tensor(nodes, idt, dev)
+    if dev.type == "cuda" and len(set(metapath)) <= 16 and len(metapath) > 0:
+        # ONE kernel for the whole walk: thread per walker, relation table in kernel parameters
+        from .._graph_kernels import random_walk as _rw
+        uniq = sorted(set(metapath))
+        rels = []
+        for etid in uniq:
+            indptr, indices, eids = g._graphs[etid].csr()
+            rels.append((indptr, indices, eids, g._edge_frames[etid][prob] if prob is not None else None))
+        step_rel = torch.tensor([uniq.index(e) for e in metapath], dtype=torch.int32, device=dev)
+        rp = None
+        if restart_prob is not None:
+            rp = (restart_prob if torch.is_tensor(restart_prob) else torch.full((len(metapath),), float(restart_prob)))
+            rp = rp.to(device=dev, dtype=torch.float32).contiguous()
+        traces, eids_t = _rw(rels, step_rel, rp, nodes.contiguous(), len(metapath), dgl_random.next_seed(), return_eids)
+        types = torch.tensor([g._src_ntid(metapath[0])] + [g._dst_ntid(e) for e in metapath], dtype=idt, device=dev)
+        return (traces, eids_t, types) if return_eids else (traces, types)
     traces = [nodes]
     eids_out = []
     cur = nodes.clone()
@@ -90,8 +106,8 @@ def pack_traces(traces, types):
 
 
 def node2vec_random_walk(g, nodes, p, q, walk_length, prob=None, return_eids=False):
-    """Second-order biased walks (node2vec). CPU native kernel (rejection sampling);
-    CUDA graphs are walked on a host copy of the CSR."""
+    """Second-order biased walks (node2vec). Rejection sampling, thread per walker: native CPU kernel or the
+    sm_100a kernel (csrc/cuda/graph_kernels.cu) depending on the graph's device."""
     if not g.is_homogeneous:
         raise DGLError("node2vec_random_walk requires a homogeneous graph")
     if prob is not None:
@@ -99,6 +115,12 @@ def node2vec_random_walk(g, nodes, p, q, walk_length, prob=None, return_eids=Fal
     idt = g.idtype
     out_dev = g.device
     ug = g._graphs[0]
+    if out_dev.type == "cuda":
+        from .._graph_kernels import node2vec_walk as _n2v
+        indptr, indices, eids = ug.csr()
+        seeds = _to_tensor(nodes, idt, out_dev).contiguous()
+        traces, te = _n2v(indptr, indices, eids, seeds, walk_length, p, q, dgl_random.next_seed(), return_eids)
+        return (traces, te) if return_eids else traces
     indptr, indices, eids = [None if t is None else t.cpu().contiguous() for t in ug.csr()]
     seeds = _to_tensor(nodes, idt, torch.device("cpu")).contiguous()
     n = seeds.shape[0]

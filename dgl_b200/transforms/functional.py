@@ -548,8 +548,27 @@ def reorder_graph(g, node_permute_algo=None, edge_permute_algo="src", store_ids=
     return new
 
 
+def to_bidirected_coo(g, e_weights=None):
+    """(u, v, w) of the symmetrised edge set without self loops (weights duplicated for both directions)."""
+    u, v = g.edges()
+    m = u != v
+    u, v = u[m], v[m]
+    w = None
+    if e_weights is not None:
+        w = e_weights.to(u.device)[m]
+        w = torch.cat([w, w])
+    return torch.cat([u, v]).contiguous(), torch.cat([v, u]).contiguous(), w
+
+
 def _pairwise_topk(x, y, k, exclude_self_offset=None, dist="euclidean", chunk=4096):
     """for each row of y find k nearest rows of x. returns idx [len(y), k]"""
+    if x.is_cuda and x.shape[1] <= 16 and k <= 64 and dist == "euclidean" and x.dtype == y.dtype \
+            and x.dtype in (torch.float32, torch.float16, torch.bfloat16):
+        # low-dimensional point clouds: shared-memory brute force, one thread per query (csrc/cuda/graph_kernels.cu)
+        from .._graph_kernels import knn_brute
+        doff = torch.tensor([0, x.shape[0]], dtype=torch.int64, device=x.device)
+        qoff = torch.tensor([0, y.shape[0]], dtype=torch.int64, device=x.device)
+        return knn_brute(x, doff, y, qoff, k)
     outs = []
     if dist == "cosine":
         x = torch.nn.functional.normalize(x, dim=-1)

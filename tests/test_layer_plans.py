@@ -1,0 +1,82 @@
+"""Execution plans of layers that differ from the reference's formulation must stay numerically equivalent:
+RelGraphConv aggregate-first (basis regulariser) and the destination-sorted edge order of attention layers."""
+import pytest
+import torch
+
+import dgl_b200 as dgl
+
+
+def _rgcn_message_plan(conv, g, x, et, norm):
+    lin = conv.linear_r
+    W = lin.get_weight()
+    u, v = g.edges()
+    m = torch.bmm(x[u.long()].unsqueeze(1), W[et.long()]).squeeze(1)
+    if norm is not None:
+        m = m * norm
+    h = torch.zeros(g.num_nodes(), W.shape[2], device=x.device, dtype=x.dtype).index_add_(0, v.long(), m)
+    return h + conv.h_bias + x @ conv.loop_weight
+
+
+@pytest.mark.parametrize("with_norm", [False, True])
+def test_relgraphconv_aggregate_first_matches_message_plan(with_norm):
+    torch.manual_seed(0)
+    g = dgl.rand_graph(200, 3000)
+    et = torch.randint(0, 5, (3000,))
+    x = torch.randn(200, 16, requires_grad=True)
+    norm = torch.rand(3000, 1) if with_norm else None
+    conv = dgl.nn.RelGraphConv(16, 24, 5, regularizer="basis", num_bases=2)
+    y = conv(g, x, et, norm)
+    y.sum().backward()
+    gx, gc, gw = x.grad.clone(), conv.linear_r.coeff.grad.clone(), conv.linear_r.W.grad.clone()
+    x.grad = None
+    conv.zero_grad()
+    ref = _rgcn_message_plan(conv, g, x, et, norm)
+    ref.sum().backward()
+    assert torch.allclose(y, ref, atol=1e-4)
+    assert torch.allclose(gx, x.grad, atol=1e-4) and torch.allclose(gc, conv.linear_r.coeff.grad, atol=1e-3)
+    assert torch.allclose(gw, conv.linear_r.W.grad, atol=1e-3)
+
+
+def test_dst_sorted_view_structure():
+    g = dgl.rand_graph(50, 400)
+    view, emap = g.dst_sorted_view()
+    u, v = g.edges()
+    vu, vv = view.edges()
+    assert torch.equal(vu, u[emap.long()]) and torch.equal(vv, v[emap.long()])
+    assert bool((vv[1:] >= vv[:-1]).all())
+    assert view.dst_sorted_view()[1] is None          # already ordered: the view of a view is itself
+    assert g.dst_sorted_view()[0]._graphs[0] is view._graphs[0]   # cached
+
+
+@pytest.mark.gpu
+def test_gatconv_cuda_view_matches_cpu():
+    torch.manual_seed(0)
+    g = dgl.add_self_loop(dgl.rand_graph(300, 5000))
+    x = torch.randn(300, 32)
+    conv = dgl.nn.GATConv(32, 8, 4)
+    y, a = conv(g, x, get_attention=True)
+    gc, xc = g.to("cuda"), x.cuda().requires_grad_()
+    convc = conv.to("cuda")
+    yc, ac = convc(gc, xc, get_attention=True)
+    assert torch.allclose(yc.cpu(), y, atol=1e-4) and torch.allclose(ac.cpu(), a, atol=1e-5)
+    yc.sum().backward()
+    x2 = x.clone().requires_grad_()
+    conv.cpu()(g, x2).sum().backward()
+    assert torch.allclose(xc.grad.cpu(), x2.grad, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_sddmm_dot_edge_kernels_match_dense():
+    g = dgl.rand_graph(400, 6000).to("cuda")
+    u, v = g.edges()
+    for shape in [(8, 8), (4, 16), (1, 41), (2, 64), (16, 4)]:
+        a = torch.randn(400, *shape, device="cuda")
+        b = torch.randn(400, *shape, device="cuda")
+        got = dgl.ops.u_dot_v(g, a, b)
+        ref = (a[u.long()] * b[v.long()]).sum(-1, keepdim=True)
+        assert torch.allclose(got, ref, atol=1e-4), shape
+    a = torch.randn(400, 8, 8, device="cuda").bfloat16()
+    b = torch.randn(400, 8, 8, device="cuda").bfloat16()
+    got = dgl.ops.u_dot_v(g, a, b).float()
+    ref = (a[u.long()].float() * b[v.long()].float()).sum(-1, keepdim=True)
+    assert torch.allclose(got, ref, atol=5e-2)
