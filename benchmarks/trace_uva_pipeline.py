@@ -1,0 +1,20 @@
+import sys, os
+sys.path.insert(0, '/root/repo/benchmarks'); sys.path.insert(0, '/root/repo')
+sys.argv = ['x']
+import torch, torch.nn.functional as F
+import bench_uva_pipeline as b
+class A: pass
+args = A(); args.batch = 1024; args.fanouts = [10, 10, 10]; args.cache_mb = 0
+n, u, v, feat, labels, train = b.make_graph(0.1)
+model, opt, it, ce, ci = b.run_ours(args, n, u, v, feat, labels, train)
+import dgl_b200 as dgl
+def step():
+    with dgl.utils.trace.range("next_batch"):
+        blocks, x, y = next(it)
+    with dgl.utils.trace.range("model_fwd_bwd_opt"):
+        loss = F.cross_entropy(model(blocks, x), y)
+        opt.zero_grad(set_to_none=True); loss.backward(); opt.step()
+for _ in range(5): step()
+with dgl.utils.trace.trace() as t:
+    for _ in range(20): step()
+print(t.report())

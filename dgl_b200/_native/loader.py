@@ -19,6 +19,7 @@ import threading
 from pathlib import Path
 
 from . import build as _build
+from ..utils import trace as _trace
 
 _LIBDIR = Path(__file__).resolve().parent.parent / "lib"
 _KIND = {"p": ctypes.c_void_p, "l": ctypes.c_int64, "i": ctypes.c_int32,
@@ -52,8 +53,11 @@ class _Lib:
             raw.argtypes = [_KIND[c] for c in sig]
             err = self._err
 
+            is_cuda = "cuda" in self.path
+            tstate = _trace._state
+
             def f(*args, _raw=raw, _name=name):
-                rc = _raw(*args)
+                rc = _trace.call(_name, _raw, args, is_cuda) if tstate["on"] else _raw(*args)
                 if rc != 0:
                     msg = err()
                     raise NativeError(f"{_name}: {msg.decode() if msg else rc}")

@@ -17,7 +17,8 @@ namespace dglb {
 template <typename I, int VB>
 __global__ void __launch_bounds__(256) gather_rows_kernel(const char* __restrict__ src, const I* __restrict__ idx,
                                                           int64_t n, char* __restrict__ dst, int64_t row_bytes,
-                                                          int64_t src_rows, int sub) {
+                                                          int64_t src_rows, int sub,
+                                                          const int64_t* __restrict__ dst_pos = nullptr) {
   using V = typename std::conditional<VB == 16, uint4, typename std::conditional<VB == 8, uint2,
             typename std::conditional<VB == 4, uint32_t, uint8_t>::type>::type>::type;
   const int rows_per_block = blockDim.x / sub;
@@ -26,14 +27,16 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const char* __restrict
   for (int64_t r = (int64_t)blockIdx.x * rows_per_block + threadIdx.x / sub; r < n;
        r += (int64_t)gridDim.x * rows_per_block) {
     int64_t s = idx[r];
+    // dst_pos: the gather walks the source in the (sorted) order of idx and writes row r to its original position
+    const int64_t orow = dst_pos ? dst_pos[r] : r;
     if (s < 0 || s >= src_rows) {  // out-of-range ids gather zeros (padding rows)
       V z;
       memset(&z, 0, sizeof(V));
-      for (int64_t c = lane; c < nvec; c += sub) reinterpret_cast<V*>(dst + r * row_bytes)[c] = z;
+      for (int64_t c = lane; c < nvec; c += sub) reinterpret_cast<V*>(dst + orow * row_bytes)[c] = z;
       continue;
     }
     const V* sp = reinterpret_cast<const V*>(src + s * row_bytes);
-    V* dp = reinterpret_cast<V*>(dst + r * row_bytes);
+    V* dp = reinterpret_cast<V*>(dst + orow * row_bytes);
     int64_t c = lane;
     for (; c + 3 * sub < nvec; c += 4 * sub) {  // 4 loads in flight per lane
       V a = sp[c], b = sp[c + sub], d = sp[c + 2 * sub], e = sp[c + 3 * sub];
@@ -70,7 +73,7 @@ static int pick_vb(int64_t row_bytes, const void* a, const void* b) {
 
 template <typename I>
 void launch_gather(const void* src, const I* idx, int64_t n, void* dst, int64_t row_bytes, int64_t src_rows,
-                   int max_blocks, cudaStream_t st) {
+                   int max_blocks, cudaStream_t st, const int64_t* dst_pos = nullptr) {
   const int vb = pick_vb(row_bytes, src, dst);
   const int64_t nvec = row_bytes / vb;
   int sub = 1;
@@ -79,7 +82,7 @@ void launch_gather(const void* src, const I* idx, int64_t n, void* dst, int64_t 
   int64_t blocks = (n + rpb - 1) / rpb;
   if (blocks > max_blocks) blocks = max_blocks;
   if (blocks < 1) blocks = 1;
-#define G(VBV) gather_rows_kernel<I, VBV><<<(unsigned)blocks, 256, 0, st>>>((const char*)src, idx, n, (char*)dst, row_bytes, src_rows, sub)
+#define G(VBV) gather_rows_kernel<I, VBV><<<(unsigned)blocks, 256, 0, st>>>((const char*)src, idx, n, (char*)dst, row_bytes, src_rows, sub, dst_pos)
   if (vb == 16) G(16); else if (vb == 8) G(8); else if (vb == 4) G(4); else G(1);
 #undef G
 }
@@ -256,7 +259,8 @@ using namespace dglb;
 
 // src may be device memory or host-pinned memory (then `uva`=1 and the device alias is resolved here)
 DGLB_API int dglb200_cuda_gather_rows(int idtype, const void* src, const void* idx, int64_t n, void* dst,
-                                      int64_t row_bytes, int64_t src_rows, int uva, int max_blocks, void* stream) {
+                                      int64_t row_bytes, int64_t src_rows, int uva, int max_blocks, const void* dst_pos,
+                                      void* stream) {
   DGLB_TRY
   const void* sp = src;
   if (uva) {
@@ -265,7 +269,7 @@ DGLB_API int dglb200_cuda_gather_rows(int idtype, const void* src, const void* i
     sp = dp;
   }
   if (max_blocks <= 0) max_blocks = 148 * 32;
-  DGLB_ID_SWITCH(idtype, I, { launch_gather<I>(sp, (const I*)idx, n, dst, row_bytes, src_rows, max_blocks, (cudaStream_t)stream); });
+  DGLB_ID_SWITCH(idtype, I, { launch_gather<I>(sp, (const I*)idx, n, dst, row_bytes, src_rows, max_blocks, (cudaStream_t)stream, (const int64_t*)dst_pos); });
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH
 }

@@ -175,6 +175,33 @@ class CopyTo(_Stage):
             yield data.to(self.device, self.non_blocking) if hasattr(data, "to") else data
 
 
+def _record_stream(obj, stream, depth=0):
+    """Best-effort ``record_stream`` over every CUDA tensor reachable from a mini-batch (tensors, graphs / blocks,
+    lists, tuples, dicts, plain objects) - the reference does the same for prefetched batches
+    (python/dgl/dataloading/dataloader.py:473-485)."""
+    if obj is None or depth > 6:
+        return
+    if torch.is_tensor(obj):
+        if obj.is_cuda:
+            obj.record_stream(stream)
+        return
+    if hasattr(obj, "record_stream") and not isinstance(obj, type):
+        try:
+            obj.record_stream(stream)
+        except Exception:  # noqa: BLE001
+            pass
+        return
+    if isinstance(obj, dict):
+        for v in obj.values():
+            _record_stream(v, stream, depth + 1)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            _record_stream(v, stream, depth + 1)
+    elif hasattr(obj, "__dict__"):
+        for v in vars(obj).values():
+            _record_stream(v, stream, depth + 1)
+
+
 class DataLoader:
     """Iterate a datapipe with optional background prefetch (``num_workers`` > 0 or ``overlap`` enables a
     producer thread with its own CUDA stream; ``max_uva_threads`` caps the UVA gather grid)."""
@@ -240,6 +267,8 @@ class DataLoader:
             if item is done:
                 break
             if ev is not None:
-                torch.cuda.current_stream().wait_event(ev)
+                cur = torch.cuda.current_stream()
+                cur.wait_event(ev)
+                _record_stream(item, cur)   # memory allocated on the producer stream is consumed on this one
             yield item
         th.join()

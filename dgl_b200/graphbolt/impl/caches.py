@@ -150,52 +150,143 @@ class GPUCache:
 
 
 class GPUGraphCache:
-    """GPU cache of hot vertices' adjacency lists: vertices whose access count reaches ``threshold`` get their
-    neighbour lists copied into device memory; ``query`` splits seeds into cached / missing."""
+    """GPU cache of hot vertices' adjacency lists (reference: graphbolt/src/cuda/extension/gpu_graph_cache.cu,
+    python/dgl/graphbolt/impl/gpu_graph_cache.py). Device-native: an open-addressing vertex table (key, access count,
+    offset, length) plus an edge pool, all plain CUDA tensors (csrc/cuda/graph_cache.cu); ``query`` / ``replace`` run
+    as kernels without host synchronisation, vertices are admitted once their access count reaches ``threshold``.
 
-    def __init__(self, num_edges, threshold, indptr_dtype, dtypes=None, device=None):
+        hit_pos, miss_pos = cache.query(seeds)
+        indptr_h, indices_h = cache.fetch_cached(seeds[hit_pos])          # compact CSC from the pool
+        indptr_m, indices_m = index_select_csc(graph_indptr, graph_indices, seeds[miss_pos])   # UVA / device graph
+        cache.replace(seeds[miss_pos], indptr_m, indices_m)
+    """
+
+    def __init__(self, num_edges, threshold, indptr_dtype=torch.int64, dtypes=None, device=None, num_slots=None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.capacity_edges = int(num_edges)
         self.threshold = int(threshold)
-        self.counts = {}
-        self.offsets = {}
-        self.indices = torch.empty(self.capacity_edges, dtype=torch.int64, device=self.device)
-        self.used = 0
-        self.total_queries = 0
-        self.total_miss = 0
+        self.idtype = (dtypes[0] if dtypes else torch.int64)
+        slots = int(num_slots) if num_slots else max(1024, 2 * self.capacity_edges // 8)
+        self.slots = 1 << (slots - 1).bit_length()
+        dev = self.device
+        self.keys = torch.full((self.slots,), -1, dtype=torch.int64, device=dev)
+        self.counts = torch.zeros(self.slots, dtype=torch.int32, device=dev)
+        self.offs = torch.zeros(self.slots, dtype=torch.int64, device=dev)
+        self.lens = torch.full((self.slots,), -1, dtype=torch.int32, device=dev)
+        self.pool = torch.empty(self.capacity_edges, dtype=self.idtype, device=dev)
+        self.used_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.stats = torch.zeros(2, dtype=torch.int64, device=dev)      # [queries, misses]
+        self._last = None
+
+    def _lib(self):
+        from ..._native import loader
+        return loader.cuda_lib(), loader
 
     def query(self, seeds):
-        keys = seeds.tolist()
-        hit_pos, miss_pos = [], []
-        for i, k in enumerate(keys):
-            self.counts[k] = self.counts.get(k, 0) + 1
-            (hit_pos if k in self.offsets else miss_pos).append(i)
-        self.total_queries += len(keys)
-        self.total_miss += len(miss_pos)
-        dev = seeds.device
-        return torch.tensor(hit_pos, dtype=torch.long, device=dev), torch.tensor(miss_pos, dtype=torch.long, device=dev)
+        """Bump the access counters of ``seeds`` and split their positions into (cached, missing)."""
+        from ...base import id_code
+        seeds = seeds.to(self.device).to(self.idtype).contiguous()
+        n = seeds.shape[0]
+        hit = torch.empty(n, dtype=torch.uint8, device=self.device)
+        off = torch.empty(n, dtype=torch.int64, device=self.device)
+        ln = torch.empty(n, dtype=torch.int32, device=self.device)
+        lib, loader = self._lib()
+        lib.fn("dglb200_graphcache_query", "ipppplplppppp")(
+            id_code(self.idtype), self.keys.data_ptr(), self.counts.data_ptr(), self.offs.data_ptr(), self.lens.data_ptr(),
+            self.slots, seeds.data_ptr(), n, hit.data_ptr(), off.data_ptr(), ln.data_ptr(), self.stats.data_ptr(),
+            loader.stream_ptr())
+        hb = hit.bool()
+        self._last = (seeds, off, ln)
+        return torch.nonzero(hb).squeeze(1), torch.nonzero(~hb).squeeze(1)
 
     def fetch_cached(self, seeds):
-        """(indptr, indices) of the cached adjacency lists of ``seeds`` (all must be cached)."""
-        lens = [self.offsets[int(k)][1] for k in seeds.tolist()]
-        indptr = torch.zeros(len(lens) + 1, dtype=torch.int64, device=self.device)
-        indptr[1:] = torch.cumsum(torch.tensor(lens, device=self.device), 0)
-        parts = [self.indices[self.offsets[int(k)][0]: self.offsets[int(k)][0] + self.offsets[int(k)][1]] for k in seeds.tolist()]
-        return indptr, (torch.cat(parts) if parts else self.indices[:0])
+        """(indptr, indices) compact CSC of cached ``seeds`` (as returned by the hit positions of ``query``)."""
+        from ...base import id_code
+        seeds = seeds.to(self.device).to(self.idtype).contiguous()
+        n = seeds.shape[0]
+        hit = torch.empty(n, dtype=torch.uint8, device=self.device)
+        off = torch.empty(n, dtype=torch.int64, device=self.device)
+        ln = torch.empty(n, dtype=torch.int32, device=self.device)
+        lib, loader = self._lib()
+        scratch = torch.zeros(2, dtype=torch.int64, device=self.device)
+        cnt = self.counts.clone()      # a pure lookup must not change the admission counters
+        lib.fn("dglb200_graphcache_query", "ipppplplppppp")(
+            id_code(self.idtype), self.keys.data_ptr(), cnt.data_ptr(), self.offs.data_ptr(), self.lens.data_ptr(),
+            self.slots, seeds.data_ptr(), n, hit.data_ptr(), off.data_ptr(), ln.data_ptr(), scratch.data_ptr(),
+            loader.stream_ptr())
+        indptr = torch.zeros(n + 1, dtype=torch.int64, device=self.device)
+        torch.cumsum(ln.long(), 0, out=indptr[1:])
+        total = int(indptr[-1])
+        indices = torch.empty(total, dtype=self.idtype, device=self.device)
+        if total:
+            lib.fn("dglb200_cuda_seg_copy", "iipplpppppp")(
+                id_code(self.idtype), 1, off.data_ptr(), 0, n, indptr.data_ptr(), self.pool.data_ptr(), indices.data_ptr(),
+                0, 0, loader.stream_ptr())
+        return indptr, indices
 
     def replace(self, seeds, indptr, indices):
-        """Offer the freshly fetched adjacency lists of ``seeds``; hot ones are admitted while space remains."""
-        for i, k in enumerate(seeds.tolist()):
-            if k in self.offsets or self.counts.get(k, 0) < self.threshold:
-                continue
-            lo, hi = int(indptr[i]), int(indptr[i + 1])
-            n = hi - lo
-            if self.used + n > self.capacity_edges:
-                continue
-            self.indices[self.used: self.used + n] = indices[lo:hi].to(self.device)
-            self.offsets[k] = (self.used, n)
-            self.used += n
+        """Offer the freshly fetched adjacency lists of ``seeds``; hot ones are admitted while the pool has room."""
+        from ...base import id_code
+        seeds = seeds.to(self.device).to(self.idtype).contiguous()
+        indptr = indptr.to(self.device).long().contiguous()
+        indices = indices.to(self.device).to(self.idtype).contiguous()
+        lib, loader = self._lib()
+        lib.fn("dglb200_graphcache_replace", "ippppliplppplpp")(
+            id_code(self.idtype), self.keys.data_ptr(), self.counts.data_ptr(), self.offs.data_ptr(), self.lens.data_ptr(),
+            self.slots, self.threshold, seeds.data_ptr(), seeds.shape[0], indptr.data_ptr(), indices.data_ptr(),
+            self.pool.data_ptr(), self.capacity_edges, self.used_dev.data_ptr(), loader.stream_ptr())
+
+    @property
+    def used(self):
+        return int(self.used_dev.item())
+
+    @property
+    def total_queries(self):
+        return int(self.stats[0].item())
+
+    @property
+    def total_miss(self):
+        return int(self.stats[1].item())
 
     @property
     def miss_rate(self):
-        return self.total_miss / self.total_queries if self.total_queries else 0.0
+        q = self.total_queries
+        return self.total_miss / q if q else 0.0
+
+
+def index_select_csc(indptr, indices, seeds, edge_ids=None):
+    """Compact CSC (indptr int64, indices[, edge ids]) of the adjacency lists of ``seeds``. ``indptr`` / ``indices`` may
+    live in host-pinned memory (UVA) or on the device; one sub-warp copies one list (reference:
+    graphbolt/src/cuda/index_select_csc_impl.cu)."""
+    from ..._native import loader
+    from ...base import id_code
+    dev = seeds.device
+    if dev.type != "cuda":
+        s = indptr[seeds.long()].long()
+        deg = indptr[seeds.long() + 1].long() - s
+        out_indptr = torch.zeros(seeds.shape[0] + 1, dtype=torch.int64)
+        torch.cumsum(deg, 0, out=out_indptr[1:])
+        pos = torch.repeat_interleave(s - out_indptr[:-1], deg) + torch.arange(int(out_indptr[-1]))
+        return (out_indptr, indices[pos]) + ((edge_ids[pos],) if edge_ids is not None else ())
+    idt = indptr.dtype
+    seeds = seeds.to(idt).contiguous()
+    n = seeds.shape[0]
+    lib = loader.cuda_lib()
+
+    def dptr(t):
+        if t.is_cuda:
+            return t.data_ptr()
+        from ...utils.pin_memory import host_device_pointer
+        return host_device_pointer(t)
+    deg = torch.empty(n, dtype=torch.int64, device=dev)
+    lib.fn("dglb200_cuda_csc_degree", "ipplpp")(id_code(idt), dptr(indptr), seeds.data_ptr(), n, deg.data_ptr(), loader.stream_ptr())
+    out_indptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(deg, 0, out=out_indptr[1:])
+    total = int(out_indptr[-1])
+    out = torch.empty(total, dtype=indices.dtype, device=dev)
+    out2 = torch.empty(total, dtype=indices.dtype, device=dev) if edge_ids is not None else None
+    if total:
+        lib.fn("dglb200_cuda_seg_copy", "iipplpppppp")(
+            id_code(idt), 0, dptr(indptr), seeds.data_ptr(), n, out_indptr.data_ptr(), dptr(indices), out.data_ptr(),
+            0 if edge_ids is None else dptr(edge_ids.to(indices.dtype)), 0 if out2 is None else out2.data_ptr(), loader.stream_ptr())
+    return (out_indptr, out) + ((out2,) if out2 is not None else ())

@@ -197,8 +197,9 @@ class GATv2Conv(nn.Module):
         self._allow_zero_in_degree = set_value
 
     def forward(self, graph, feat, get_attention=False):
+        _zero_in_degree_check(graph, self._allow_zero_in_degree)
+        graph, emap, _ = _attention_view(graph)
         with graph.local_scope():
-            _zero_in_degree_check(graph, self._allow_zero_in_degree)
             if isinstance(feat, tuple):
                 h_src = self.feat_drop(feat[0])
                 h_dst = self.feat_drop(feat[1])
@@ -228,7 +229,7 @@ class GATv2Conv(nn.Module):
             if self.activation:
                 rst = self.activation(rst)
             if get_attention:
-                return rst, graph.edata["a"]
+                return rst, _attention_to_eid_order(graph.edata["a"], emap)
             return rst
 
 

@@ -68,10 +68,18 @@ def cuda_map_ids(universe, ids):
     return out
 
 
+_uva_sort_min_rows = [1 << 14]
+
+
 def _gather(src, index, uva, max_blocks=0):
     if index.dtype not in (torch.int32, torch.int64):
         index = index.long()
     index = index.contiguous()
+    dst_pos = None
+    if uva and index.shape[0] >= _uva_sort_min_rows[0]:
+        # host reads in ascending address order (DRAM page / IOMMU-TLB locality, the reference sorts too:
+        # graphbolt/src/cuda/index_select_impl.cu:129-134); rows are written straight to their original positions
+        index, dst_pos = torch.sort(index)
     if not src.is_contiguous():
         raise DGLError("gather source must be contiguous")
     n = index.shape[0]
@@ -80,9 +88,9 @@ def _gather(src, index, uva, max_blocks=0):
     for s in src.shape[1:]:
         row_bytes *= s
     if n > 0 and row_bytes > 0:
-        loader.cuda_lib().fn("dglb200_cuda_gather_rows", "ipplpllii" + "p")(
+        loader.cuda_lib().fn("dglb200_cuda_gather_rows", "ipplpllii" + "pp")(
             id_code(index.dtype), src.data_ptr(), index.data_ptr(), n, out.data_ptr(), row_bytes, src.shape[0],
-            1 if uva else 0, max_blocks, loader.stream_ptr())
+            1 if uva else 0, max_blocks, 0 if dst_pos is None else dst_pos.data_ptr(), loader.stream_ptr())
     return out
 
 

@@ -44,3 +44,15 @@ def scatter_pinned_tensor_rows(dest, rows, source):
     """dest[rows[i]] = source[i]; ``dest`` pinned host, rows/source on GPU."""
     from ..ops.index import index_scatter
     index_scatter(dest, rows, source)
+
+
+def host_device_pointer(tensor):
+    """Device-visible address of a host-pinned tensor (UVA): what kernels dereference to read host memory directly."""
+    import ctypes
+
+    from .._native import loader
+    if not tensor.is_pinned():
+        raise DGLError("tensor must be in pinned (page-locked) host memory for UVA access")
+    out = ctypes.c_void_p()
+    loader.cuda_lib().fn("dglb200_cuda_host_device_ptr", "pp")(tensor.data_ptr(), ctypes.addressof(out))
+    return out.value

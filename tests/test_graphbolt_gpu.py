@@ -84,3 +84,30 @@ def test_p2p_single_rank_kernels():
     comm.gather(shard, n, idx, got)
     assert torch.equal(got, x[idx])
     comm.check_error()
+
+
+def test_native_gpu_graph_cache_and_index_select_csc():
+    import dgl_b200.graphbolt as gb
+    from dgl_b200.graphbolt.impl import GPUGraphCache, index_select_csc
+    g = dgl.rand_graph(2000, 40000, idtype=torch.int64)
+    indptr, indices, _ = g._graphs[0].csc()
+    indptr_p, indices_p = indptr.pin_memory(), indices.pin_memory()          # graph stays in host memory (UVA)
+    seeds = torch.randint(0, 2000, (500,), device=DEV)
+    ip, ix = index_select_csc(indptr_p, indices_p, seeds)
+    ip_ref, ix_ref = index_select_csc(indptr, indices, seeds.cpu())
+    assert torch.equal(ip.cpu(), ip_ref) and torch.equal(ix.cpu(), ix_ref)
+    cache = GPUGraphCache(20000, threshold=2, dtypes=[torch.int64])
+    hot = torch.arange(0, 300, device=DEV)
+    for rnd in range(3):
+        hit, miss = cache.query(hot)
+        if rnd == 0:
+            assert hit.numel() == 0 and miss.numel() == 300
+        ms = hot[miss]
+        mp, mi = index_select_csc(indptr_p, indices_p, ms)
+        cache.replace(ms, mp, mi)
+    hit, miss = cache.query(hot)
+    assert hit.numel() > 250                                                # admitted after reaching the threshold
+    cp, ci = cache.fetch_cached(hot[hit])
+    rp, ri = index_select_csc(indptr, indices, hot[hit].cpu())
+    assert torch.equal(cp.cpu(), rp) and torch.equal(ci.cpu(), ri)
+    assert 0.0 < cache.miss_rate < 1.0 and cache.used <= 20000

@@ -80,3 +80,15 @@ def test_sddmm_dot_edge_kernels_match_dense():
     got = dgl.ops.u_dot_v(g, a, b).float()
     ref = (a[u.long()].float() * b[v.long()].float()).sum(-1, keepdim=True)
     assert torch.allclose(got, ref, atol=5e-2)
+
+
+def test_trace_records_native_ops():
+    g = dgl.rand_graph(100, 1000)
+    x = torch.randn(100, 16, requires_grad=True)
+    with dgl.utils.trace.trace() as t:
+        with dgl.utils.trace.range("layer"):
+            y = dgl.ops.copy_u_sum(g, x)
+        y.sum().backward()
+    s = t.summary()
+    assert s["dglb200_cpu_gspmm"]["calls"] == 2 and s["range:layer"]["calls"] == 1
+    assert not dgl.utils.trace.enabled() and "dglb200_cpu_gspmm" in t.report()
