@@ -120,37 +120,41 @@ def main():
         del plan
 
     # ---------------------------------------------------------------- 2. all-reduce fused with Adam
-    from dgl_b200._native import loader
-    import ctypes
-    numel = 1 << 22  # 4 Mi fp32 parameters (16 MB of gradients)
-    lib = loader.cuda_lib()
-    gbuf = comm.grad_buffer(numel)
-    gbuf.copy_(torch.randn(numel, device=dev))
-    param = torch.randn(numel, device=dev)
-    m, v = torch.zeros_like(param), torch.zeros_like(param)
-    shadow = torch.zeros(numel, dtype=torch.bfloat16, device=dev)
-    step = torch.zeros(1, dtype=torch.int64, device=dev)
-    peers = comm.peer_grad_ptrs()
+    # two sizes: the flagship GraphSAGE (0.21 M parameters: latency-bound, one-shot) and a 4 Mi-parameter model
+    # (16 MiB of gradients: bandwidth-bound, two-shot = reduce-scatter + Adam on the slice + all-gather of the update)
+    for numel in (212_992, 1 << 22):
+        gbuf = comm.grad_buffer(numel)
+        gbuf.copy_(torch.randn(numel, device=dev))
+        param = torch.randn(numel, device=dev)
+        dist.broadcast(param, 0)
+        m, v = torch.zeros_like(param), torch.zeros_like(param)
+        shadow = torch.zeros(numel, dtype=torch.bfloat16, device=dev)
+        step = torch.zeros(1, dtype=torch.int64, device=dev)
+        p2 = torch.nn.Parameter(param.clone())
+        opt = torch.optim.Adam([p2], lr=1e-3, fused=True)
+        g2 = gbuf.clone()
+        shadow2 = torch.zeros_like(shadow)
 
-    def fused():
-        comm.barrier(0)
-        lib.fn("dglb200_engine_allreduce_adam", "ppippplfffffpp")(
-            param.data_ptr(), ctypes.cast(peers, ctypes.c_void_p), world, m.data_ptr(), v.data_ptr(), shadow.data_ptr(),
-            numel, 1e-3, 0.9, 0.999, 1e-8, 0.0, step.data_ptr(), loader.stream_ptr())
-        comm.barrier(1)
-    t_f = timed(fused)
-    p2 = torch.nn.Parameter(torch.randn(numel, device=dev))
-    opt = torch.optim.Adam([p2], lr=1e-3, fused=True)
-    g2 = torch.randn(numel, device=dev)
+        def fused():
+            comm.fused_allreduce_adam(param, m, v, shadow, step)
 
-    def nccl():
-        dist.all_reduce(g2)
-        p2.grad = g2
-        opt.step()
-        shadow.copy_(p2.data)  # the bf16 copy the fused kernel also produces
-    t_n = timed(nccl)
-    emit(bench="allreduce_adam", numel=numel, ms_fused=t_f, ms_nccl_allreduce_plus_fused_adam=t_n, speedup=t_n / t_f,
-         bytes_moved_per_gpu=numel * 4 * (world - 1), pull_GBps_per_gpu=numel * 4 * (world - 1) / t_f / 1e6)
+        def nccl():
+            g = g2.clone()
+            dist.all_reduce(g)
+            p2.grad = g.div_(world)
+            opt.step()
+            shadow2.copy_(p2.data)  # the bf16 copy the fused kernel also produces
+        fused()
+        nccl()
+        torch.cuda.synchronize()
+        err = (param - p2.data).abs().max().item()
+        t_f = timed(fused)
+        t_n = timed(nccl)
+        two = world >= 4 and numel * 4 >= comm.TWO_SHOT_MIN_BYTES
+        moved = numel * 4 * (2 * (world - 1) / world if two else (world - 1))
+        emit(bench="allreduce_adam", numel=numel, algorithm="two-shot" if two else "one-shot", ms_fused=t_f,
+             ms_nccl_allreduce_plus_fused_adam=t_n, speedup=t_n / t_f, max_abs_param_diff_after_1_step=err,
+             bytes_moved_per_gpu=moved, pull_GBps_per_gpu=moved / t_f / 1e6)
 
     # ---------------------------------------------------------------- 3. sharded-table gather
     nq = 400_000

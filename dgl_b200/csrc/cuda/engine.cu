@@ -351,12 +351,15 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(float* __restrict__
                                                              __nv_bfloat16* __restrict__ shadow, int64_t numel,
                                                              float lr, float beta1, float beta2, float eps,
                                                              float weight_decay, int64_t* __restrict__ step_dev,
-                                                             int bump_step) {
+                                                             int bump_step, int64_t lo = 0,
+                                                             float* __restrict__ param_pub = nullptr) {
+  // [lo, numel) is the element range this launch owns: the whole buffer for the one-shot all-reduce, this rank's slice
+  // for the two-shot variant (reduce-scatter + Adam on the slice, updated fp32 values published in param_pub)
   const int64_t t = *step_dev + 1;
   const float bc1 = 1.f - __powf(beta1, (float)t);
   const float bc2 = 1.f - __powf(beta2, (float)t);
   const float inv_world = 1.f / (float)world;
-  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < numel;
+  for (int64_t i = lo + ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < numel;
        i += (int64_t)gridDim.x * blockDim.x * 4) {
     float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 8
@@ -382,6 +385,7 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(float* __restrict__
       pp[k] -= lr * mh / (sqrtf(vh) + eps);
     }
     *reinterpret_cast<float4*>(param + i) = p4;
+    if (param_pub) *reinterpret_cast<float4*>(param_pub + i) = p4;
     *reinterpret_cast<float4*>(m + i) = m4;
     *reinterpret_cast<float4*>(v + i) = v4;
     if (shadow) {
@@ -553,6 +557,29 @@ DGLB_API int dglb200_engine_colsum(const void* X, int64_t rows, int N, void* out
   DGLB_CATCH
 }
 
+// second half of the two-shot all-reduce + Adam: every rank pulls the slices the OTHER ranks updated (fp32 parameters in
+// their symmetric param buffers) into its local parameters and bf16 shadow. slice r = [r * slice, min(numel, (r+1) * slice)).
+__global__ void __launch_bounds__(256) param_allgather_kernel(float* __restrict__ param, PeerPtrs pubs, int world, int rank,
+                                                              __nv_bfloat16* __restrict__ shadow, int64_t numel,
+                                                              int64_t slice) {
+  const int64_t mine_lo = (int64_t)rank * slice, mine_hi = min(numel, mine_lo + slice);
+  for (int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; i < numel;
+       i += (int64_t)gridDim.x * blockDim.x * 4) {
+    if (i >= mine_lo && i < mine_hi) continue;
+    const int r = (int)(i / slice);
+    float4 x;
+    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "l"(pubs.p[r] + i));
+    *reinterpret_cast<float4*>(param + i) = x;
+    if (shadow) {
+      __nv_bfloat162 l2 = __floats2bfloat162_rn(x.x, x.y), h2 = __floats2bfloat162_rn(x.z, x.w);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&l2);
+      pk.y = *reinterpret_cast<uint32_t*>(&h2);
+      *reinterpret_cast<uint2*>(shadow + i) = pk;
+    }
+  }
+}
+
 // peer_ptrs: host array of `world` device pointers (each rank's flat fp32 grad buffer, P2P mapped)
 DGLB_API int dglb200_engine_allreduce_adam(void* param, const void* const* peer_ptrs, int world, void* m, void* v,
                                            void* shadow, int64_t numel, float lr, float beta1, float beta2, float eps,
@@ -568,6 +595,43 @@ DGLB_API int dglb200_engine_allreduce_adam(void* param, const void* const* peer_
   if (blocks < 1) blocks = 1;
   allreduce_adam_kernel<<<(unsigned)blocks, 256, 0, st>>>((float*)param, pp, world, (float*)m, (float*)v, (__nv_bfloat16*)shadow, numel, lr, beta1, beta2, eps, weight_decay, (int64_t*)step_dev, 0);
   bump_step_kernel<<<1, 1, 0, st>>>((int64_t*)step_dev);
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}
+
+// Two-shot variant for large parameter sets (bandwidth-optimal: 2 * (world-1)/world * bytes per GPU instead of
+// (world-1) * bytes): phase 1 reduces + applies Adam on this rank's slice and publishes the new fp32 values in its
+// symmetric param buffer; after a device barrier phase 2 (dglb200_engine_param_allgather) pulls the other slices.
+DGLB_API int dglb200_engine_allreduce_adam_rs(void* param, const void* const* peer_grad_ptrs, int world, int rank, void* m,
+                                              void* v, void* shadow, int64_t numel, int64_t slice, float lr, float beta1,
+                                              float beta2, float eps, float weight_decay, void* step_dev, void* param_pub,
+                                              void* stream) {
+  DGLB_TRY
+  DGLB_CHECK(world >= 1 && world <= 8 && rank >= 0 && rank < world, "bad world / rank");
+  DGLB_CHECK(numel % 4 == 0 && slice % 4 == 0 && slice * world >= numel, "numel and slice must be multiples of 4, slice * world >= numel");
+  PeerPtrs pp;
+  for (int r = 0; r < 8; ++r) pp.p[r] = r < world ? (const float*)peer_grad_ptrs[r] : nullptr;
+  const int64_t lo = (int64_t)rank * slice, hi = std::min<int64_t>(numel, lo + slice);
+  if (hi > lo) {
+    int64_t blocks = ((hi - lo) / 4 + 255) / 256;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    allreduce_adam_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>((float*)param, pp, world, (float*)m, (float*)v, (__nv_bfloat16*)shadow, hi, lr, beta1, beta2, eps, weight_decay, (int64_t*)step_dev, 0, lo, (float*)param_pub);
+  }
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}
+
+DGLB_API int dglb200_engine_param_allgather(void* param, const void* const* peer_pub_ptrs, int world, int rank, void* shadow,
+                                            int64_t numel, int64_t slice, void* step_dev, void* stream) {
+  DGLB_TRY
+  PeerPtrs pp;
+  for (int r = 0; r < 8; ++r) pp.p[r] = r < world ? (const float*)peer_pub_ptrs[r] : nullptr;
+  cudaStream_t st = (cudaStream_t)stream;
+  int64_t blocks = (numel / 4 + 255) / 256;
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  if (blocks < 1) blocks = 1;
+  if (world > 1) param_allgather_kernel<<<(unsigned)blocks, 256, 0, st>>>((float*)param, pp, world, rank, (__nv_bfloat16*)shadow, numel, slice);
+  if (step_dev) bump_step_kernel<<<1, 1, 0, st>>>((int64_t*)step_dev);
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH
 }

@@ -131,6 +131,43 @@ class P2PComm:
         if sync:
             self.barrier(2)
 
+    TWO_SHOT_MIN_BYTES = 2 << 20
+
+    def fused_allreduce_adam(self, param, m, v, shadow, step_dev, lr=1e-3, betas=(0.9, 0.999), eps=1e-8,
+                             weight_decay=0.0, two_shot=None):
+        """Gradient all-reduce FUSED with the Adam update (+ bf16 shadow weights). Gradients must already sit in
+        ``grad_buffer``. No NCCL call, graph-capturable.
+          * one-shot (small models, latency-bound): every rank pulls all peers' gradients inside the Adam kernel;
+          * two-shot (>= 2 MiB of gradients on >= 4 ranks, bandwidth-bound): each rank reduces + updates only ITS
+            slice (reduce-scatter fused with Adam; optimizer state is effectively sharded) and publishes the new fp32
+            values in a symmetric buffer, then pulls the other ranks' slices (all-gather fused with the bf16 cast) -
+            2(W-1)/W x bytes per GPU instead of (W-1) x bytes."""
+        numel = int(param.numel())
+        W = self.world_size
+        if two_shot is None:
+            two_shot = W >= 4 and numel * 4 >= self.TWO_SHOT_MIN_BYTES
+        peers = ctypes.cast(self._grad.ptr_array, ctypes.c_void_p)
+        sh = 0 if shadow is None else shadow.data_ptr()
+        self.barrier(0)
+        if not two_shot or W == 1:
+            self.lib.fn("dglb200_engine_allreduce_adam", "ppippplfffffpp")(
+                param.data_ptr(), peers, W, m.data_ptr(), v.data_ptr(), sh, numel, lr, betas[0], betas[1], eps,
+                weight_decay, step_dev.data_ptr(), loader.stream_ptr())
+            self.barrier(1)
+            return
+        if getattr(self, "_param_pub", None) is None or self._param_pub.nbytes < numel * 4:
+            self._param_pub = self.alloc(numel * 4)
+        slice_ = -(-numel // W)
+        slice_ = (slice_ + 3) // 4 * 4
+        self.lib.fn("dglb200_engine_allreduce_adam_rs", "ppiipppllfffffppp")(
+            param.data_ptr(), peers, W, self.rank, m.data_ptr(), v.data_ptr(), sh, numel, slice_, lr, betas[0], betas[1],
+            eps, weight_decay, step_dev.data_ptr(), self._param_pub.local_ptr, loader.stream_ptr())
+        self.barrier(1)
+        self.lib.fn("dglb200_engine_param_allgather", "ppiipllpp")(
+            param.data_ptr(), self._param_pub.ptr_table(), W, self.rank, sh, numel, slice_, step_dev.data_ptr(),
+            loader.stream_ptr())
+        self.barrier(2)   # nobody overwrites its published slice / gradients before every rank has pulled them
+
     def halo_spmm(self, indptr, indices, shards: SymmetricBuffer, shard_rows, feat_dim, dtype, out, mean=True,
                   edge_weight=None):
         """Aggregation over a range-partitioned feature table with remote rows fetched over NVLink inside

@@ -179,7 +179,42 @@ def _w_trainer(rank, world, comm):
     return losses[-1]
 
 
+def _w_fused_allreduce_adam(rank, world, comm):
+    import torch.distributed as dist
+    dev = comm.device
+    for two_shot, numel in ((False, 4096), (True, 10240), (True, 4100)):
+        g = torch.Generator().manual_seed(5)
+        param = torch.randn(numel, generator=g).to(dev)
+        ref = torch.nn.Parameter(param.clone())
+        opt = torch.optim.Adam([ref], lr=1e-2, weight_decay=0.01)
+        m, v = torch.zeros_like(param), torch.zeros_like(param)
+        shadow = torch.zeros(numel, dtype=torch.bfloat16, device=dev)
+        step = torch.zeros(1, dtype=torch.int64, device=dev)
+        gbuf = comm.grad_buffer(numel)
+        for it in range(3):
+            gr = torch.Generator().manual_seed(100 * it + rank)
+            grad = torch.randn(numel, generator=gr).to(dev)
+            gbuf.copy_(grad)
+            comm.fused_allreduce_adam(param, m, v, shadow, step, lr=1e-2, weight_decay=0.01, two_shot=two_shot)
+            tot = grad.clone()
+            dist.all_reduce(tot)
+            ref.grad = tot / world
+            opt.step()
+        assert int(step.item()) == 3
+        assert torch.allclose(param, ref.data, atol=1e-5), (two_shot, (param - ref.data).abs().max())
+        assert torch.allclose(shadow.float(), ref.data, atol=2e-2)
+        chk = param.clone()
+        dist.broadcast(chk, 0)
+        assert torch.equal(chk, param)          # replicas identical
+    return True
+
+
 # ---------------------------------------------------------------------------------------------- tests
+def test_fused_allreduce_adam_one_and_two_shot():
+    _run(_w_fused_allreduce_adam)
+
+
+
 def test_p2p_allreduce_gather_scatter():
     _run(_w_allreduce_and_tables)
 
