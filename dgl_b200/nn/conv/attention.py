@@ -126,6 +126,14 @@ class GATConv(nn.Module):
                     dst_prefix_shape = (graph.number_of_dst_nodes(),) + dst_prefix_shape[1:]
             el = (feat_src * self.attn_l).sum(dim=-1).unsqueeze(-1)
             er = (feat_dst * self.attn_r).sum(dim=-1).unsqueeze(-1)
+            # per-head rows that are not a multiple of 16 bytes (e.g. 41 classes) would force 4-byte accesses on E x D
+            # elements in the aggregation and its backward: zero-pad the (small) node tensor, slice the result
+            ft_pad = 0
+            if feat_src.is_cuda and feat_src.dim() == 3 and graph.num_edges() >= 4 * feat_src.shape[0]:
+                vec = 16 // feat_src.element_size()
+                ft_pad = (-self._out_feats) % vec
+            if ft_pad:
+                feat_src = F.pad(feat_src, (0, ft_pad))
             graph.srcdata.update({"ft": feat_src, "el": el})
             graph.dstdata.update({"er": er})
             graph.apply_edges(fn.u_add_v("el", "er", "e"))
@@ -135,6 +143,8 @@ class GATConv(nn.Module):
                 graph.edata["a"] = graph.edata["a"] * edge_weight.tile(1, self._num_heads, 1).transpose(0, 2)
             graph.update_all(fn.u_mul_e("ft", "a", "m"), fn.sum("m", "ft"))
             rst = graph.dstdata["ft"]
+            if ft_pad:
+                rst = rst[..., : self._out_feats]
             if self.res_fc is not None:
                 resval = self.res_fc(h_dst).view(*dst_prefix_shape, -1, self._out_feats)
                 rst = rst + resval
