@@ -132,6 +132,19 @@ class GATConv(nn.Module):
             if feat_src.is_cuda and feat_src.dim() == 3 and graph.num_edges() >= 4 * feat_src.shape[0]:
                 vec = 16 // feat_src.element_size()
                 ft_pad = (-self._out_feats) % vec
+            if (feat_src.is_cuda and feat_src.dim() == 3 and edge_weight is None and not get_attention
+                    and (self.attn_drop.p == 0 or not self.training) and len(graph.canonical_etypes) == 1):
+                # whole attention block in two kernels (online-softmax forward, recomputing backward)
+                from ...ops import gat_fused
+                vec = 16 // feat_src.element_size()
+                pad = (-self._out_feats) % vec
+                if gat_fused.supported(el, feat_src, self._num_heads, self._out_feats + pad):
+                    ftp = F.pad(feat_src, (0, pad)) if pad else feat_src
+                    rst = gat_fused.fused_gat(graph._graphs[0], el.squeeze(-1), er.squeeze(-1), ftp,
+                                              self.leaky_relu.negative_slope)
+                    if pad:
+                        rst = rst[..., : self._out_feats]
+                    return self._finish(rst, h_dst, dst_prefix_shape)
             if ft_pad:
                 feat_src = F.pad(feat_src, (0, ft_pad))
             graph.srcdata.update({"ft": feat_src, "el": el})
@@ -145,16 +158,20 @@ class GATConv(nn.Module):
             rst = graph.dstdata["ft"]
             if ft_pad:
                 rst = rst[..., : self._out_feats]
-            if self.res_fc is not None:
-                resval = self.res_fc(h_dst).view(*dst_prefix_shape, -1, self._out_feats)
-                rst = rst + resval
-            if self.has_explicit_bias:
-                rst = rst + self.bias.view(*((1,) * len(dst_prefix_shape)), self._num_heads, self._out_feats)
-            if self.activation:
-                rst = self.activation(rst)
+            rst = self._finish(rst, h_dst, dst_prefix_shape)
             if get_attention:
                 return rst, _attention_to_eid_order(graph.edata["a"], emap)
             return rst
+
+    def _finish(self, rst, h_dst, dst_prefix_shape):
+        if self.res_fc is not None:
+            resval = self.res_fc(h_dst).view(*dst_prefix_shape, -1, self._out_feats)
+            rst = rst + resval
+        if self.has_explicit_bias:
+            rst = rst + self.bias.view(*((1,) * len(dst_prefix_shape)), self._num_heads, self._out_feats)
+        if self.activation:
+            rst = self.activation(rst)
+        return rst
 
 
 class GATv2Conv(nn.Module):

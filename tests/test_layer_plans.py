@@ -92,3 +92,33 @@ def test_trace_records_native_ops():
     s = t.summary()
     assert s["dglb200_cpu_gspmm"]["calls"] == 2 and s["range:layer"]["calls"] == 1
     assert not dgl.utils.trace.enabled() and "dglb200_cpu_gspmm" in t.report()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("H,D,dtype", [(8, 8, torch.float32), (1, 41, torch.float32), (4, 16, torch.bfloat16), (2, 32, torch.float32)])
+def test_fused_gat_matches_unfused(H, D, dtype):
+    from dgl_b200.ops import gat_fused
+    torch.manual_seed(0)
+    g = dgl.add_self_loop(dgl.rand_graph(500, 9000)).to("cuda")
+    view, _ = g.dst_sorted_view()
+    ug = view._graphs[0]
+    vec = 16 // torch.empty(0, dtype=dtype).element_size()
+    Dp = D + (-D) % vec
+    el = torch.randn(500, H, device="cuda").to(dtype).requires_grad_()
+    er = torch.randn(500, H, device="cuda").to(dtype).requires_grad_()
+    ft = torch.randn(500, H, Dp, device="cuda").to(dtype).requires_grad_()
+    assert gat_fused.supported(el, ft, H, Dp)
+    out = gat_fused.fused_gat(ug, el, er, ft, 0.2)
+    go = torch.randn_like(out)
+    out.backward(go)
+    # oracle: dense fp32 formulation on the same edges
+    u, v = view.edges()
+    el32, er32, ft32 = (t.detach().float().requires_grad_() for t in (el, er, ft))
+    e = torch.nn.functional.leaky_relu(el32[u.long()] + er32[v.long()], 0.2)              # [E, H]
+    a = dgl.ops.edge_softmax(view, e.unsqueeze(-1)).squeeze(-1)
+    ref = torch.zeros(500, H, Dp, device="cuda").index_add_(0, v.long(), a.unsqueeze(-1) * ft32[u.long()])
+    ref.backward(go.float())
+    tol = 2e-4 if dtype == torch.float32 else 6e-2
+    assert torch.allclose(out.float(), ref, atol=tol)
+    assert torch.allclose(ft.grad.float(), ft32.grad, atol=tol * 5)
+    assert torch.allclose(el.grad.float(), el32.grad, atol=tol * 20) and torch.allclose(er.grad.float(), er32.grad, atol=tol * 20)
