@@ -209,7 +209,54 @@ def _w_fused_allreduce_adam(rank, world, comm):
     return True
 
 
+def _w_partitioned_sage(rank, world, comm):
+    """Vertex-partitioned full-graph SAGE must reproduce the single-process model: same logits, same gradients."""
+    import dgl_b200 as dgl
+    from dgl_b200.parallel import PartitionedSAGE
+    dev = comm.device
+    rows, Fin, C = 1200, 32, 5
+    N = rows * world
+    gen = torch.Generator().manual_seed(4)
+    u = torch.randint(0, N, (30000,), generator=gen).int()
+    v = torch.randint(0, N, (30000,), generator=gen).int()
+    g = dgl.graph((u, v), num_nodes=N, idtype=torch.int32)
+    x = torch.randn(N, Fin, generator=gen)
+    y = torch.randint(0, C, (N,), generator=gen)
+    indptr, indices, _ = g._graphs[0].csc()
+    lo, hi = rank * rows, (rank + 1) * rows
+    ip = (indptr[lo:hi + 1] - indptr[lo]).to(dev)
+    ix = indices[int(indptr[lo]): int(indptr[hi])].to(dev)
+    torch.manual_seed(0)
+    model = PartitionedSAGE(comm, ip, ix, rows, Fin, 16, C, num_layers=2).to(dev)
+    logits = model(x[lo:hi].to(dev))
+    loss = torch.nn.functional.cross_entropy(logits, y[lo:hi].to(dev), reduction="sum") / N
+    loss.backward()
+    model.allreduce_gradients()
+    # single-process oracle with the same weights on the whole graph (the all-reduce averages: oracle grads / world)
+    import copy
+    sl, nl = copy.deepcopy(model.self_lin).cpu(), copy.deepcopy(model.neigh_lin).cpu()
+    for p_ in list(sl.parameters()) + list(nl.parameters()):
+        p_.grad = None
+    h = x
+    for i in range(2):
+        h = sl[i](h) + nl[i](dgl.ops.copy_u_mean(g, h))
+        if i == 0:
+            h = torch.relu(h)
+    ref_loss = torch.nn.functional.cross_entropy(h, y, reduction="sum") / N
+    ref_loss.backward()
+    assert torch.allclose(logits.cpu(), h[lo:hi], atol=1e-4)
+    for a, b in zip(list(model.self_lin.parameters()) + list(model.neigh_lin.parameters()),
+                    list(sl.parameters()) + list(nl.parameters())):
+        assert torch.allclose(a.grad.cpu() * world, b.grad, atol=1e-4), (a.grad.cpu() * world - b.grad).abs().max()
+    return float(loss)
+
+
 # ---------------------------------------------------------------------------------------------- tests
+def test_partitioned_fullgraph_sage_matches_single_process():
+    _run(_w_partitioned_sage)
+
+
+
 def test_fused_allreduce_adam_one_and_two_shot():
     _run(_w_fused_allreduce_adam)
 
