@@ -95,7 +95,13 @@ class FusedSAGETrainer:
         # tensor-core path (tcgen05 fused gather+GEMM kernel): bf16, hidden % 32 == 0, feature rows padded to a
         # multiple of 64 elements (zero columns: mathematically identical, their weights receive zero gradient)
         if use_tc is None:
+            from ..global_config import get_gemm_path
+            path = get_gemm_path()                      # DGLB200_GEMM = auto | tc | cublas
             use_tc = dtype == torch.bfloat16 and hidden % 64 == 0 and hidden <= 256
+            if path == "cublas":
+                use_tc = False
+            elif path == "tc" and not use_tc:
+                raise ValueError("DGLB200_GEMM=tc needs bf16 and a hidden size that is a multiple of 64 (<= 256)")
         self.use_tc = bool(use_tc)
         self.F_orig = feat.shape[1]
         if self.use_tc and feat.shape[1] % 64:
