@@ -145,15 +145,37 @@ class FusedCSCSamplingGraph:
         fan = torch.as_tensor(fanouts).reshape(-1).tolist()
         prob = self.edge_attributes[probs_name] if probs_name else None
         rs = dgl_random.next_seed() if random_seed is None else int(torch.as_tensor(random_seed).reshape(-1)[0])
+        def regroup(sd, src, dst, eid):
+            # group the kept edges by seed position (LABOR returns them per edge, the CSC wants them per seed)
+            order = torch.argsort(sd, stable=True)
+            key = order[torch.searchsorted(sd[order], dst)] if dst.numel() else dst.long()
+            perm = torch.argsort(key, stable=True)
+            return src[perm], torch.bincount(key, minlength=sd.shape[0]), eid[perm]
+
         if self.node_type_offset is None:
             src, dst, eid, w = _labor_rel(self._unit(), seeds.to(self.csc_indptr.dtype), fan[0], prob, 0, rs, seed2_contribution)
-            # regroup by seed position
-            order = torch.argsort(seeds, stable=True)
-            key = order[torch.searchsorted(seeds[order], dst)] if dst.numel() else dst.long()
-            perm = torch.argsort(key, stable=True)
-            cnt = torch.bincount(key, minlength=seeds.shape[0])
-            return self._convert(seeds, {None: (src[perm], cnt, eid[perm])})
-        raise NotImplementedError("hetero LABOR sampling: use sample_neighbors")
+            return self._convert(seeds, {None: regroup(seeds, src, dst, eid)})
+        if not isinstance(seeds, dict):
+            raise DGLError("heterogeneous graph: seeds must be a dict of node type -> ids")
+        # one LABOR pass per edge type with the SAME random seed: the variate of a source vertex is a function of
+        # (seed, global vertex id), so a vertex is kept / dropped consistently across relations (reference
+        # fused_csc_sampling_graph.cc labor path with per-etype fanouts)
+        off = self.node_type_offset
+        units = self._etype_units()
+        if len(fan) == 1:
+            fan = fan * len(self.edge_type_to_id)
+        results = {}
+        for et, tid in self.edge_type_to_id.items():
+            s_, _, d = etype_str_to_tuple(et)
+            if d not in seeds or fan[tid] == 0:
+                continue
+            ug, eid_map = units[et]
+            g_seeds = (seeds[d] + int(off[self.node_type_to_id[d]])).to(self.csc_indptr.dtype)
+            p = prob[eid_map] if prob is not None else None
+            src, dst, eid, w = _labor_rel(ug, g_seeds, fan[tid], p, 0, rs, seed2_contribution)
+            src, cnt, eid = regroup(g_seeds, src, dst, eid)
+            results[et] = (src, cnt, eid_map.to(eid.device)[eid.long()])
+        return self._convert(seeds, results)
 
     def temporal_sample_neighbors(self, seeds, seeds_timestamp, fanouts, replace=False, seeds_pre_time_window=None,
                                   probs_name=None, node_timestamp_attr_name=None, edge_timestamp_attr_name=None):

@@ -122,3 +122,24 @@ def test_fused_gat_matches_unfused(H, D, dtype):
     assert torch.allclose(out.float(), ref, atol=tol)
     assert torch.allclose(ft.grad.float(), ft32.grad, atol=tol * 5)
     assert torch.allclose(el.grad.float(), el32.grad, atol=tol * 20) and torch.allclose(er.grad.float(), er32.grad, atol=tol * 20)
+
+
+def test_graphbolt_hetero_labor_sampling():
+    import dgl_b200.graphbolt as gb
+    torch.manual_seed(0)
+    u1, i1 = torch.randint(0, 50, (600,)), torch.randint(0, 30, (600,))
+    i2, u2 = torch.randint(0, 30, (600,)), torch.randint(0, 50, (600,))
+    hg = dgl.heterograph({("u", "r1", "i"): (u1, i1), ("i", "r2", "u"): (i2, u2)})
+    fg = gb.from_dglgraph(hg)
+    seeds = {"i": torch.arange(10), "u": torch.arange(5)}
+    sub = fg.sample_layer_neighbors(seeds, [3], random_seed=5)
+    sub2 = fg.sample_layer_neighbors(seeds, [3], random_seed=5)
+    e1 = set(zip(u1.tolist(), i1.tolist()))
+    csc = sub.sampled_csc["u:r1:i"]
+    assert torch.equal(csc.indices, sub2.sampled_csc["u:r1:i"].indices)          # same seed -> same sample
+    assert csc.indptr.shape[0] == 11
+    for d in range(10):
+        for s in csc.indices[int(csc.indptr[d]): int(csc.indptr[d + 1])].tolist():
+            assert (s, d) in e1
+    full = fg.sample_layer_neighbors(seeds, [-1])
+    assert int(full.sampled_csc["u:r1:i"].indptr[-1]) == int(sum((i1 == d).sum() for d in range(10)))
