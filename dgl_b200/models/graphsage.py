@@ -84,6 +84,7 @@ class FusedSAGETrainer:
         self.dev = feat.device
         self.lib = loader.cuda_lib()
         indptr, indices, _ = graph._graphs[0].csc()
+        self._graph_ref = graph                    # used by predict() (generic sampler + module path)
         E = indices.shape[0]
         N = graph.num_nodes()
         if E >= 2 ** 31 or N >= 2 ** 31:
@@ -603,8 +604,19 @@ class FusedSAGETrainer:
         return tot
 
     @torch.no_grad()
-    def predict(self, seeds):
-        """Sampled-neighbourhood inference for ``seeds`` (no dropout): returns logits [len(seeds), C]."""
-        mod = GraphSAGE(self.F_in, self.H, self.C, self.L, 0.0).to(self.dev)
+    def predict(self, seeds, fanouts=None, batch_size=4096):
+        """Sampled-neighbourhood inference for ``seeds`` (no dropout): returns fp32 logits [len(seeds), C].
+        The trained weights are exported into a ``GraphSAGE`` module and evaluated on blocks drawn by the generic
+        ``NeighborSampler`` (``fanouts`` defaults to the training fan-outs; pass ``[-1] * L`` for full neighbourhoods)."""
+        from ..dataloading import NeighborSampler
+        mod = GraphSAGE(self.F_orig, self.H, self.C, self.L, 0.0).to(self.dev).eval()
         self.export_to_module(mod)
-        raise NotImplementedError("use export_to_module() + DataLoader for inference")
+        sampler = NeighborSampler(list(fanouts) if fanouts is not None else list(self.fanouts))
+        g = self._graph_ref
+        seeds = torch.as_tensor(seeds).to(self.dev).to(g.idtype)
+        outs = []
+        for chunk in seeds.split(int(batch_size)):
+            inp, _, blocks = sampler.sample(g, chunk)
+            x = self.feat[inp.long(), : self.F_orig].float()
+            outs.append(mod(blocks, x).float())
+        return torch.cat(outs) if outs else torch.empty((0, self.C), device=self.dev)

@@ -126,3 +126,6 @@ def test_engine_cuda_graph_trains():
             pred = mod(blocks, feat[inp.long()]).argmax(1)
             correct += int((pred == tr.labels[out.long()].long()).sum()); tot += out.numel()
     assert correct / tot > 0.3
+    # the trainer's own inference entry point
+    logits = tr.predict(torch.arange(2000), fanouts=[-1, -1, -1], batch_size=512)
+    assert logits.shape == (2000, 5) and float((logits.argmax(1) == tr.labels[:2000].long()).float().mean()) > 0.3
