@@ -46,9 +46,13 @@ def run_ours(args, n, u, v, feat, labels, train):
     from dgl_b200.models import GraphSAGE
     dev = "cuda"
     g = dgl.graph((u.int(), v.int()), num_nodes=n, idtype=torch.int32)
-    fg = gb.from_dglgraph(g).pin_memory_()
-    feature = gb.TorchBasedFeature(feat).pin_memory_()
-    if args.cache_mb:
+    if args.resident == "device":          # graph + features in HBM: the generic (non-fused) GPU pipeline
+        fg = gb.from_dglgraph(g).to(dev)
+        feature = gb.TorchBasedFeature(feat.to(dev))
+    else:
+        fg = gb.from_dglgraph(g).pin_memory_()
+        feature = gb.TorchBasedFeature(feat).pin_memory_()
+    if args.cache_mb and args.resident != "device":
         feature = gb.GPUCachedFeature(feature, args.cache_mb << 20)
     store = gb.BasicFeatureStore({("node", None, "feat"): feature})
     items = gb.ItemSet((train.int(), labels[train]), names=("seeds", "labels"))
@@ -75,12 +79,18 @@ def run_reference(args, n, u, v, feat, labels, train):
     dev = torch.device("cuda")
     g = dgl.graph((u.int(), v.int()), num_nodes=n, idtype=torch.int32)
     g.create_formats_()
-    g.pin_memory_()
-    nfeat = dgl.utils.pin_memory_inplace(feat)
+    device_resident = args.resident == "device"
+    if device_resident:
+        g = g.to(dev)
+        feat_d = feat.to(dev)
+    else:
+        g.pin_memory_()
+        nfeat = dgl.utils.pin_memory_inplace(feat)
+        _KEEP.append(nfeat)   # the holder un-pins the tensor when it is collected
     labels_d = labels.to(dev)
     sampler = dgl.dataloading.NeighborSampler(args.fanouts)
     dl = dgl.dataloading.DataLoader(g, train.int().to(dev), sampler, device=dev, batch_size=args.batch, shuffle=True,
-                                    drop_last=False, num_workers=0, use_uva=True)
+                                    drop_last=False, num_workers=0, use_uva=not device_resident)
 
     class SAGE(nn.Module):
         def __init__(self):
@@ -103,10 +113,9 @@ def run_reference(args, n, u, v, feat, labels, train):
     def batches():
         while True:
             for input_nodes, output_nodes, blocks in dl:
-                x = dgl.utils.gather_pinned_tensor_rows(feat, input_nodes)
+                x = feat_d[input_nodes.long()] if device_resident else dgl.utils.gather_pinned_tensor_rows(feat, input_nodes)
                 yield blocks, x, labels_d[output_nodes.long()]
 
-    _KEEP.append(nfeat)   # the holder un-pins the tensor when it is collected
     return model, opt, batches(), lambda blocks: sum(b.num_edges() for b in blocks), lambda blocks: blocks[0].num_src_nodes()
 
 
@@ -119,6 +128,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--cache-mb", type=int, default=0)
     ap.add_argument("--workers", type=int, default=1, help="ours: 1 = prefetch thread + side stream (gb.DataLoader)")
+    ap.add_argument("--resident", default="host", choices=["host", "device"],
+                    help="host: graph + features pinned in host memory (UVA, config 5); device: both in HBM")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     args.fanouts = [10, 10, 10]
@@ -148,7 +159,7 @@ def main():
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / args.steps
-    rec = dict(bench="sage_uva_pipeline", impl=args.impl, scale=args.scale, nodes=n, edges=int(u.shape[0]), feat_dim=128,
+    rec = dict(bench="sage_uva_pipeline" if args.resident == "host" else "sage_generic_pipeline_device_resident", impl=args.impl, scale=args.scale, nodes=n, edges=int(u.shape[0]), feat_dim=128,
                batch=args.batch, fanouts=args.fanouts, ms_per_step=ms, sampled_edges_per_s=edges / args.steps / ms * 1e3,
                input_rows_per_step=inputs / args.steps, uva_feature_GBps=inputs / args.steps * 512 / ms / 1e6,
                gpu_cache_mb=args.cache_mb, workers=args.workers, final_loss=loss, steps=args.steps, warmup=args.warmup, graph_build_s=gen_s)

@@ -65,7 +65,20 @@ def unique_and_compact_csc_formats(csc_formats, unique_dst_nodes, rank=0, world_
 def compact_csc_format(csc_formats, dst_nodes, dst_timestamps=None):
     """Relabel WITHOUT deduplication: every sampled edge gets its own source slot after the dst nodes."""
     if isinstance(csc_formats, dict):
-        raise NotImplementedError("heterogeneous compact_csc_format is not implemented")
+        # per source node type: [dst nodes of that type | one fresh slot per sampled edge, relation after relation]
+        rows = {nt: [ids] for nt, ids in dst_nodes.items()}
+        nxt = {nt: int(ids.shape[0]) for nt, ids in dst_nodes.items()}
+        compacted = {}
+        for et, csc in csc_formats.items():
+            s, _, _ = etype_str_to_tuple(et)
+            n = csc.indices.shape[0]
+            start = nxt.get(s, 0)
+            rows.setdefault(s, []).append(csc.indices)
+            nxt[s] = start + n
+            compacted[et] = CSCFormatBase(indptr=csc.indptr,
+                                          indices=torch.arange(start, start + n, device=csc.indices.device,
+                                                               dtype=csc.indices.dtype))
+        return {nt: torch.cat(v) for nt, v in rows.items()}, compacted
     n_dst = dst_nodes.shape[0]
     n = csc_formats.indices.shape[0]
     original_row_ids = torch.cat([dst_nodes, csc_formats.indices])
