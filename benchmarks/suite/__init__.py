@@ -39,4 +39,4 @@ def grid(param_grid):
         yield dict(zip(keys, vals))
 
 
-from . import api, kernel, model_speed  # noqa: E402,F401
+from . import api, kernel, model_acc, model_speed, multigpu  # noqa: E402,F401
