@@ -135,6 +135,13 @@ def _gather_mm_torch(a, b, idx_b):
 
 def segment_mm(a, b, seglen_a):
     """out[seg_r] = a[seg_r] @ b[r];  a:[N,K] b:[R,K,M] seglen_a:[R] (host or device tensor)."""
+    from ..ops.sparse_autograd import _autocast_args
+    (a, b), ctx = _autocast_args(a, b)       # under autocast both operands run in the autocast dtype -> tcgen05 path
+    with ctx:
+        return _segment_mm(a, b, seglen_a)
+
+
+def _segment_mm(a, b, seglen_a):
     if a.shape[0] == 0:
         return a.new_zeros((0, b.shape[-1]))
     if _tc_ok(a, b):
@@ -145,6 +152,13 @@ def segment_mm(a, b, seglen_a):
 def gather_mm(a, b, idx_b):
     """out[i] = a[i] @ b[idx_b[i]];  a:[N,K] b:[R,K,M]. Unsorted relation ids: rows are bucketed by relation on the
     device (stable sort + bincount), the A rows are gathered inside the GEMM kernel, and the result is scattered back."""
+    from ..ops.sparse_autograd import _autocast_args
+    (a, b), ctx = _autocast_args(a, b)
+    with ctx:
+        return _gather_mm(a, b, idx_b)
+
+
+def _gather_mm(a, b, idx_b):
     N, K = a.shape
     R, _, M = b.shape
     if N == 0:

@@ -63,4 +63,7 @@ class _FusedGAT(torch.autograd.Function):
 
 def fused_gat(ug, el, er, ft, negative_slope):
     """el: [N_src, H], er: [N_dst, H], ft: [N_src, H, D] -> [N_dst, H, D]."""
-    return _FusedGAT.apply(ug, el, er, ft, negative_slope)
+    from .sparse_autograd import _autocast_args
+    (el, er, ft), ctx = _autocast_args(el, er, ft)
+    with ctx:
+        return _FusedGAT.apply(ug, el, er, ft, negative_slope)

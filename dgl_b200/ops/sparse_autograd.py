@@ -227,21 +227,49 @@ class SegmentReduce(torch.autograd.Function):
         return None, dx, None
 
 
+def _autocast_args(*tensors):
+    """Under ``torch.autocast`` cast the floating CUDA operands of a sparse op to the autocast dtype (the reference does
+    the same: backend/pytorch/sparse.py:146-159 ``_cast_if_autocast_enabled``), so a bf16 activation meeting an fp32
+    edge weight does not raise a dtype mismatch. Returns (cast tensors, context that disables autocast inside the op)."""
+    if not (torch.is_autocast_enabled() and any(t is not None and torch.is_tensor(t) and t.is_cuda for t in tensors)):
+        return tensors, _NullCtx()
+    dt = torch.get_autocast_dtype("cuda") if hasattr(torch, "get_autocast_dtype") else torch.get_autocast_gpu_dtype()
+    cast = tuple(t.to(dt) if (t is not None and torch.is_tensor(t) and t.is_cuda and t.is_floating_point()
+                              and t.dtype != torch.float64) else t for t in tensors)
+    return cast, torch.autocast("cuda", enabled=False)
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
 def gspmm(gidx, op, reduce_op, lhs_data, rhs_data):
     if op == "sub":
         op, rhs_data = "add", -rhs_data
     elif op == "div":
         op, rhs_data = "mul", 1.0 / rhs_data
-    return GSpMM.apply(gidx, op, reduce_op, lhs_data, rhs_data)
+    (lhs_data, rhs_data), ctx = _autocast_args(lhs_data, rhs_data)
+    with ctx:
+        return GSpMM.apply(gidx, op, reduce_op, lhs_data, rhs_data)
 
 
 def gsddmm(gidx, op, lhs_data, rhs_data, lhs_target="u", rhs_target="v"):
-    return GSDDMM.apply(gidx, op, lhs_data, rhs_data, lhs_target, rhs_target)
+    (lhs_data, rhs_data), ctx = _autocast_args(lhs_data, rhs_data)
+    with ctx:
+        return GSDDMM.apply(gidx, op, lhs_data, rhs_data, lhs_target, rhs_target)
 
 
 def edge_softmax(gidx, logits, eids=None, norm_by="dst"):
-    return EdgeSoftmax.apply(gidx, logits, eids, norm_by)
+    (logits,), ctx = _autocast_args(logits)
+    with ctx:
+        return EdgeSoftmax.apply(gidx, logits, eids, norm_by)
 
 
 def segment_reduce(op, x, offsets):
-    return SegmentReduce.apply(op, x, offsets)
+    (x,), ctx = _autocast_args(x)
+    with ctx:
+        return SegmentReduce.apply(op, x, offsets)

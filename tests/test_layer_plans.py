@@ -143,3 +143,27 @@ def test_graphbolt_hetero_labor_sampling():
             assert (s, d) in e1
     full = fg.sample_layer_neighbors(seeds, [-1])
     assert int(full.sampled_csc["u:r1:i"].indptr[-1]) == int(sum((i1 == d).sum() for d in range(10)))
+
+
+@pytest.mark.gpu
+def test_sparse_ops_under_autocast():
+    g = dgl.add_self_loop(dgl.rand_graph(300, 4000)).to("cuda")
+    x = torch.randn(300, 32, device="cuda")
+    w = torch.rand(g.num_edges(), 1, device="cuda")                       # fp32 edge weights meet bf16 activations
+    lin = torch.nn.Linear(32, 64).cuda()
+    conv = dgl.nn.GATConv(64, 8, 4).cuda()
+    rel = dgl.nn.RelGraphConv(32, 16, 3, regularizer="basis", num_bases=2).cuda()
+    et = torch.randint(0, 3, (g.num_edges(),), device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        h = lin(x)
+        assert h.dtype == torch.bfloat16
+        agg = dgl.ops.u_mul_e_sum(g, h, w)
+        assert agg.dtype == torch.bfloat16
+        out = conv(g, h)
+        out2 = rel(g, x, et)
+        tl = dgl.nn.TypedLinear(32, 16, 3).cuda()
+        y = tl(x, torch.sort(torch.randint(0, 3, (300,), device="cuda"))[0], sorted_by_type=True)
+        assert y.dtype == torch.bfloat16                                  # tcgen05 grouped GEMM under autocast
+    (agg.float().sum() + out.float().sum() + out2.float().sum() + y.float().sum()).backward()
+    ref = dgl.ops.u_mul_e_sum(g, lin(x), w)
+    assert (agg.float() - ref).abs().max() < 0.15 and lin.weight.grad is not None

@@ -251,7 +251,42 @@ def _w_partitioned_sage(rank, world, comm):
     return float(loss)
 
 
+def _w_p2p_cooperative(rank, world, comm):
+    import torch.distributed as dist
+    from dgl_b200.graphbolt.impl.cooperative import P2PCooperativeConv
+    dev = comm.device
+    cap, F = 700, 32
+    n_local = 500 + 100 * rank                                  # ranks own different numbers of rows
+    gen = torch.Generator().manual_seed(10 + rank)
+    h = torch.randn(n_local, F, generator=gen).to(dev).requires_grad_()
+    sizes = [500 + 100 * r for r in range(world)]
+    owner = torch.randint(0, world, (2000,), generator=gen)
+    local = (torch.rand(2000, generator=gen) * torch.tensor(sizes, dtype=torch.float)[owner]).long()
+    ex = P2PCooperativeConv(comm, cap)
+    need = ex.address(owner, local, cap).to(dev)
+    out = ex(h, need)
+    wgt = torch.randn(2000, F, generator=gen).to(dev)
+    (out * wgt).sum().backward()
+    # oracle through NCCL: gather every rank's rows, index; gradient = sum over ranks of the scattered weights
+    allh = [torch.zeros(cap, F, device=dev) for _ in range(world)]
+    pad = torch.zeros(cap, F, device=dev)
+    pad[:n_local] = h.detach()
+    dist.all_gather(allh, pad)
+    ref = torch.stack(allh)[owner.to(dev), local.to(dev)]
+    assert torch.allclose(out, ref)
+    gfull = torch.zeros(world, cap, F, device=dev)
+    gfull.index_put_((owner.to(dev), local.to(dev)), wgt, accumulate=True)
+    dist.all_reduce(gfull)
+    assert torch.allclose(h.grad, gfull[rank, :n_local], atol=1e-4)
+    return True
+
+
 # ---------------------------------------------------------------------------------------------- tests
+def test_p2p_cooperative_exchange():
+    _run(_w_p2p_cooperative)
+
+
+
 def test_partitioned_fullgraph_sage_matches_single_process():
     _run(_w_partitioned_sage)
 
