@@ -54,6 +54,25 @@ class SymmetricBuffer:
         self._raw = _RawCuda(self.local_ptr, self.nbytes)
         self.local_bytes = torch.as_tensor(self._raw, device=comm.device)
 
+    def _close_peer_mappings(self):
+        for r, p in enumerate(self.ptrs):
+            if r != self.comm.rank and p:
+                try:
+                    self.comm.lib.fn("dglb200_comm_ipc_close", "p")(p)
+                except Exception:  # noqa: BLE001 - best effort during teardown
+                    pass
+        self.ptrs = [p if r == self.comm.rank else None for r, p in enumerate(self.ptrs)]
+
+    def _free_local(self):
+        if self.local_ptr:
+            self.local_bytes = None
+            self._raw = None
+            try:
+                self.comm.lib.fn("dglb200_comm_free", "p")(self.local_ptr)
+            except Exception:  # noqa: BLE001
+                pass
+            self.local_ptr = 0
+
     def view(self, dtype, shape=None):
         t = self.local_bytes.view(dtype)
         return t if shape is None else t[: int(torch.tensor(shape).prod())].view(*shape)
@@ -86,6 +105,24 @@ class P2PComm:
         self._bufs = []
         if self.world_size > 1:
             dist.barrier(group=self.group)
+
+    def close(self):
+        """Collective teardown: every rank unmaps its peers' buffers, then (after a barrier) frees its own allocations.
+        Views handed out by ``SymmetricBuffer.view`` must not be used afterwards."""
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        torch.cuda.synchronize(self.device)
+        if self.world_size > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        bufs = list(self._bufs) + [self._flags]
+        for b in bufs:
+            b._close_peer_mappings()
+        if self.world_size > 1 and dist.is_initialized():
+            dist.barrier(group=self.group)
+        for b in bufs:
+            b._free_local()
+        self._bufs = []
 
     # ------------------------------------------------------------------ memory
     def alloc(self, nbytes):

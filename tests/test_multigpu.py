@@ -31,6 +31,7 @@ def _entry(rank, world, port, fn, q):
         res = fn(rank, world, comm)
         torch.cuda.synchronize()
         comm.check_error()
+        comm.close()                      # collective teardown of the symmetric buffers (unmap peers, then free)
         dist.barrier()
         q.put((rank, "ok", res))
         dist.destroy_process_group()
