@@ -130,6 +130,7 @@ def main():
     ap.add_argument("--workers", type=int, default=1, help="ours: 1 = prefetch thread + side stream (gb.DataLoader)")
     ap.add_argument("--resident", default="host", choices=["host", "device"],
                     help="host: graph + features pinned in host memory (UVA, config 5); device: both in HBM")
+    ap.add_argument("--amp", action="store_true", help="bf16 autocast (ours: SAGEConv takes the tcgen05 fused layer)")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     args.fanouts = [10, 10, 10]
@@ -140,7 +141,9 @@ def main():
 
     def step():
         blocks, x, y = next(it)
-        loss = F.cross_entropy(model(blocks, x), y)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.amp):
+            logits = model(blocks, x)
+        loss = F.cross_entropy(logits.float(), y)
         opt.zero_grad(set_to_none=True)
         loss.backward()
         opt.step()
@@ -162,7 +165,7 @@ def main():
     rec = dict(bench="sage_uva_pipeline" if args.resident == "host" else "sage_generic_pipeline_device_resident", impl=args.impl, scale=args.scale, nodes=n, edges=int(u.shape[0]), feat_dim=128,
                batch=args.batch, fanouts=args.fanouts, ms_per_step=ms, sampled_edges_per_s=edges / args.steps / ms * 1e3,
                input_rows_per_step=inputs / args.steps, uva_feature_GBps=inputs / args.steps * 512 / ms / 1e6,
-               gpu_cache_mb=args.cache_mb, workers=args.workers, final_loss=loss, steps=args.steps, warmup=args.warmup, graph_build_s=gen_s)
+               gpu_cache_mb=args.cache_mb, workers=args.workers, amp=args.amp, final_loss=loss, steps=args.steps, warmup=args.warmup, graph_build_s=gen_s)
     print(json.dumps(rec), flush=True)
     if args.out:
         with open(args.out, "a") as f:

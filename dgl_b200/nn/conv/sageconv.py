@@ -57,6 +57,17 @@ class SAGEConv(nn.Module):
         return {"neigh": rst.squeeze(0)}
 
     def forward(self, graph, feat, edge_weight=None):
+        if self._aggre_type == "mean" and self.norm is None:
+            from .. import fused_sage
+            if fused_sage.usable(graph, feat, self._out_feats, edge_weight):
+                # one tcgen05 kernel: gather + mean + concat + [W_self | W_neigh] GEMM + bias (+ ReLU)
+                relu = self.activation is torch.nn.functional.relu or isinstance(self.activation, torch.nn.ReLU)
+                rst = fused_sage.fused_sage_mean(graph, self.feat_drop(feat), self.fc_self.weight, self.fc_neigh.weight,
+                                                 self.fc_self.bias, relu=relu)
+                if rst is not None:
+                    if self.activation is not None and not relu:
+                        rst = self.activation(rst)
+                    return rst
         with graph.local_scope():
             if isinstance(feat, tuple):
                 feat_src = self.feat_drop(feat[0])

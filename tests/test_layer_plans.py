@@ -167,3 +167,34 @@ def test_sparse_ops_under_autocast():
     (agg.float().sum() + out.float().sum() + out2.float().sum() + y.float().sum()).backward()
     ref = dgl.ops.u_mul_e_sum(g, lin(x), w)
     assert (agg.float() - ref).abs().max() < 0.15 and lin.weight.grad is not None
+
+
+@pytest.mark.gpu
+def test_sageconv_block_uses_tcgen05_path_and_matches_unfused():
+    from dgl_b200.dataloading import NeighborSampler
+    from dgl_b200.nn import fused_sage
+    torch.manual_seed(0)
+    g = dgl.rand_graph(5000, 100000, idtype=torch.int32).to("cuda")
+    feat = torch.randn(5000, 100, device="cuda")
+    inp, out, blocks = NeighborSampler([10]).sample(g, torch.arange(700, device="cuda", dtype=torch.int32))
+    blk = blocks[0]
+    conv = dgl.nn.SAGEConv(100, 48, "mean", activation=torch.nn.functional.relu).cuda()
+    x = feat[inp.long()].requires_grad_()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert fused_sage.usable(blk, x, 48, None)
+        y = conv(blk, x)
+    assert y.dtype == torch.bfloat16 and y.shape == (700, 48)
+    gy = torch.randn_like(y)
+    y.backward(gy)
+    gx, gws, gwn, gb = x.grad.clone(), conv.fc_self.weight.grad.clone(), conv.fc_neigh.weight.grad.clone(), conv.fc_self.bias.grad.clone()
+    # fp32 unfused oracle (plain formulation of the layer)
+    x2 = x.detach().clone().requires_grad_()
+    conv.zero_grad()
+    hn = dgl.ops.copy_u_mean(blk, x2)
+    ref = torch.relu(x2[:700] @ conv.fc_self.weight.t() + conv.fc_self.bias + hn @ conv.fc_neigh.weight.t())
+    ref.backward(gy.float())
+    assert (y.float() - ref).abs().max() < 0.08
+    assert (gx - x2.grad).abs().max() < 0.08
+    assert (gws - conv.fc_self.weight.grad).abs().max() / conv.fc_self.weight.grad.abs().max() < 0.03
+    assert (gwn - conv.fc_neigh.weight.grad).abs().max() / conv.fc_neigh.weight.grad.abs().max() < 0.03
+    assert (gb - conv.fc_self.bias.grad).abs().max() / conv.fc_self.bias.grad.abs().max() < 0.03
