@@ -12,12 +12,15 @@ max in-degree <= 28, out_feats <= 256, no edge weights.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from .._native import loader
 from ..base import dtype_code, id_code
 
 MAX_FANOUT = 28
+ENABLED = [os.environ.get("DGLB200_FUSED_SAGECONV", "1") != "0"]   # switch for A/B measurements
 
 
 def _pad_to(n, m):
@@ -92,7 +95,7 @@ class _FusedSAGETC(torch.autograd.Function):
 
 
 def usable(block, feat, out_feats, edge_weight):
-    if edge_weight is not None or not torch.is_tensor(feat) or not feat.is_cuda or feat.dim() != 2:
+    if not ENABLED[0] or edge_weight is not None or not torch.is_tensor(feat) or not feat.is_cuda or feat.dim() != 2:
         return False
     if not getattr(block, "is_block", False) or len(block.canonical_etypes) != 1 or out_feats > 256:
         return False

@@ -178,12 +178,16 @@ def test_sageconv_block_uses_tcgen05_path_and_matches_unfused():
     feat = torch.randn(5000, 100, device="cuda")
     inp, out, blocks = NeighborSampler([10]).sample(g, torch.arange(700, device="cuda", dtype=torch.int32))
     blk = blocks[0]
-    conv = dgl.nn.SAGEConv(100, 48, "mean", activation=torch.nn.functional.relu).cuda()
+    conv = dgl.nn.SAGEConv(100, 48, "mean").cuda()      # linear layer: gradients comparable without ReLU-mask flips
     x = feat[inp.long()].requires_grad_()
     with torch.autocast("cuda", dtype=torch.bfloat16):
         assert fused_sage.usable(blk, x, 48, None)
         y = conv(blk, x)
+        conv_r = dgl.nn.SAGEConv(100, 48, "mean", activation=torch.nn.functional.relu).cuda()
+        conv_r.load_state_dict(conv.state_dict())
+        yr = conv_r(blk, x.detach())                     # fused ReLU epilogue
     assert y.dtype == torch.bfloat16 and y.shape == (700, 48)
+    assert (yr.float() - torch.relu(y.float())).abs().max() < 0.02
     gy = torch.randn_like(y)
     y.backward(gy)
     gx, gws, gwn, gb = x.grad.clone(), conv.fc_self.weight.grad.clone(), conv.fc_neigh.weight.grad.clone(), conv.fc_self.bias.grad.clone()
@@ -191,7 +195,7 @@ def test_sageconv_block_uses_tcgen05_path_and_matches_unfused():
     x2 = x.detach().clone().requires_grad_()
     conv.zero_grad()
     hn = dgl.ops.copy_u_mean(blk, x2)
-    ref = torch.relu(x2[:700] @ conv.fc_self.weight.t() + conv.fc_self.bias + hn @ conv.fc_neigh.weight.t())
+    ref = x2[:700] @ conv.fc_self.weight.t() + conv.fc_self.bias + hn @ conv.fc_neigh.weight.t()
     ref.backward(gy.float())
     assert (y.float() - ref).abs().max() < 0.08
     assert (gx - x2.grad).abs().max() < 0.08
