@@ -3,3 +3,5 @@ from .graphsage import FusedSAGETrainer, GraphSAGE  # noqa: F401
 from .gcn import GCN  # noqa: F401
 from .gat import GAT  # noqa: F401
 from .rgcn import RGCN  # noqa: F401
+from .zoo import (APPNP, DGI, GATv2, GCNII, GIN, HGT, SGC, TAGCN, ChebNet, HeteroRGCN, JKNet, LabelPropagationModel,  # noqa: F401
+                  LinkPredictor)

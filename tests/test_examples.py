@@ -35,3 +35,11 @@ def test_graphsage_graphbolt_cpu():
 
 def test_graphsage_dist_standalone(tmp_path):
     _run("graphsage_dist.py", "--epochs", "1", "--out", str(tmp_path))
+
+
+def test_gin_graph_classification_cpu():
+    _run("gin_graph_classification.py", "--epochs", "2")
+
+
+def test_link_prediction_sage_cpu():
+    _run("link_prediction_sage.py", "--steps", "3")
