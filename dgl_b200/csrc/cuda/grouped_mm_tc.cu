@@ -27,7 +27,8 @@ namespace gmm {
 
 constexpr int kTileM = 128;
 constexpr int kChunkK = 64;
-constexpr int kStages = 4;
+constexpr int kStages = 4;      // dW kernel ring depth
+constexpr int kMaxStages = 8;   // forward kernel: as many stages as fit (deeper prefetch for small K / N tiles)
 constexpr int kProducerWarps = 16;
 constexpr int kEpilogueWarps = 8;
 constexpr int kTmaWarp = kProducerWarps + kEpilogueWarps;
@@ -58,7 +59,7 @@ seg_mm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
                  const int tma_a, const uint16_t* __restrict__ A, int64_t lda,
                  const int64_t* __restrict__ idx_a, const int64_t* __restrict__ seg_off,
                  const int64_t* __restrict__ tile_off, int R, int K, int Nout, int NB, void* __restrict__ out,
-                 int out_f32) {
+                 int out_f32, const int nst) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int64_t n_row_tiles = tile_off[R];
   const int64_t n_tiles = n_row_tiles * NB;
@@ -70,12 +71,12 @@ seg_mm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t b_bytes = (uint32_t)Np_full * 128;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
-  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
-  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages);
-  const uint32_t accf0 = smem_u32(bars + 2 * kStages), acce0 = smem_u32(bars + 2 * kStages + 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
+  uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
+  const uint32_t accf0 = smem_u32(bars + 2 * kMaxStages), acce0 = smem_u32(bars + 2 * kMaxStages + 2);
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < nst; ++s) {
       mbar_init(full0 + 8 * s, tma_a ? 1 : kProducerWarps + 1);  // contiguous A: the TMA thread brings both operands
       mbar_init(empty0 + 8 * s, 1);
     }
@@ -131,8 +132,8 @@ seg_mm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           if (kc0 + u < KC) {
-            const int stage = g % kStages;
-            mbar_wait(empty0 + 8 * stage, ((g / kStages) & 1) ^ 1);
+            const int stage = g % nst;
+            mbar_wait(empty0 + 8 * stage, ((g / nst) & 1) ^ 1);
             uint8_t* sa = smem + stage * stage_bytes;
 #pragma unroll
             for (int h = 0; h < 2; ++h) *reinterpret_cast<uint4*>(sa + sw128_off((tid >> 3) + h * 64, c)) = v[u][h];
@@ -209,8 +210,8 @@ seg_mm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         locate_tile(t / NB, tile_off, R, seg_off, kTileM, r, row0, rows);
         const int nb = (int)(t % NB);
         for (int kc = 0; kc < KC; ++kc, ++g) {
-          const int stage = g % kStages;
-          mbar_wait(empty0 + 8 * stage, ((g / kStages) & 1) ^ 1);
+          const int stage = g % nst;
+          mbar_wait(empty0 + 8 * stage, ((g / nst) & 1) ^ 1);
           mbar_arrive_expect_tx(full0 + 8 * stage, tma_a ? a_bytes + b_bytes : b_bytes);
           if (tma_a) tma_load_2d(smem_u32(smem + stage * stage_bytes), &tmap_a, full0 + 8 * stage, kc * kChunkK, (int)row0);
           tma_load_3d(smem_u32(smem + stage * stage_bytes + a_bytes), &tmap_b, full0 + 8 * stage, kc * kChunkK, nb * 256, r);
@@ -229,8 +230,8 @@ seg_mm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const uint32_t tmem_d = tmem_base + (uint32_t)(acc * acc_cols);
       for (int kc = 0; kc < KC; ++kc, ++g) {
-        const int stage = g % kStages;
-        mbar_wait(full0 + 8 * stage, (g / kStages) & 1);
+        const int stage = g % nst;
+        mbar_wait(full0 + 8 * stage, (g / nst) & 1);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a0 = smem_u32(smem + stage * stage_bytes), b0 = a0 + a_bytes;
@@ -472,15 +473,17 @@ DGLB_API int dglb200_cuda_segment_mm_tc(int dtype, const void* A, int64_t n_a_ro
     if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(A) failed with code " + std::to_string((int)rc));
   }
   const size_t stage_bytes = kTileM * 128 + (size_t)Np_full * 128;
-  const size_t smem = kStages * stage_bytes + 1024 + 256;
+  // 4 stages measured best (profiles/README.md: 6-8 stages were 5-10 % slower on the memory-bound shapes)
+  const int nst = (int)std::max<size_t>(2, std::min<size_t>(4, (size_t)(200 * 1024) / stage_bytes));
+  const size_t smem = nst * stage_bytes + 1024 + 256;
   const unsigned grid = (unsigned)std::min<int64_t>(max_tiles * NB, sm_count());
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == kBF16) {
     DGLB_CUDA_CHECK(cudaFuncSetAttribute(seg_mm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    seg_mm_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmap_a, tmap, tma_a, (const uint16_t*)A, lda, (const int64_t*)idx_a, (const int64_t*)seg_off, (const int64_t*)tile_off, R, K, Nout, NB, out, out_f32);
+    seg_mm_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmap_a, tmap, tma_a, (const uint16_t*)A, lda, (const int64_t*)idx_a, (const int64_t*)seg_off, (const int64_t*)tile_off, R, K, Nout, NB, out, out_f32, nst);
   } else {
     DGLB_CUDA_CHECK(cudaFuncSetAttribute(seg_mm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    seg_mm_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmap_a, tmap, tma_a, (const uint16_t*)A, lda, (const int64_t*)idx_a, (const int64_t*)seg_off, (const int64_t*)tile_off, R, K, Nout, NB, out, out_f32);
+    seg_mm_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmap_a, tmap, tma_a, (const uint16_t*)A, lda, (const int64_t*)idx_a, (const int64_t*)seg_off, (const int64_t*)tile_off, R, K, Nout, NB, out, out_f32, nst);
   }
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH
