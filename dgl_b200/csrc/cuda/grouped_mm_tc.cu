@@ -56,7 +56,8 @@ __device__ __forceinline__ void locate_tile(int64_t t, const int64_t* __restrict
 template <bool IS_BF16>
 __global__ void __launch_bounds__(kThreads, 1)
 seg_mm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const int tma_a, const uint16_t* __restrict__ A, int64_t lda,
+                 const __grid_constant__ CUtensorMap tmap_o, const int tma_a, const int tma_out,
+                 const uint16_t* __restrict__ A, int64_t lda,
                  const int64_t* __restrict__ idx_a, const int64_t* __restrict__ seg_off,
                  const int64_t* __restrict__ tile_off, int R, int K, int Nout, int NB, void* __restrict__ out,
                  int out_f32, const int nst) {
@@ -73,6 +74,8 @@ seg_mm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  // output staging for the TMA-store epilogue: Np/64 panels of [128 rows x 128 B], SWIZZLE_128B (1024-byte aligned)
+  uint8_t* stage_out = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(bars) + 256 + 1023) & ~(uintptr_t)1023);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
   const uint32_t accf0 = smem_u32(bars + 2 * kMaxStages), acce0 = smem_u32(bars + 2 * kMaxStages + 2);
   if (threadIdx.x == 0) {
@@ -162,6 +165,48 @@ seg_mm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       tc_fence_after();
       const bool live = row < rows;
       const int64_t grow = row0 + row;
+      // full tiles leave through shared memory + TMA store (coalesced 128-byte rows, no partial-sector stores);
+      // partial tiles (segment tails) keep the masked direct stores below
+      const bool via_tma = tma_out && rows == kTileM && (ncols & 63) == 0;
+      if (via_tma) {
+        if (ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // staging is free again
+        asm volatile("bar.sync 3, %0;" ::"n"(kEpilogueWarps * 32) : "memory");
+        for (int n0 = (ew >> 2) * 32; n0 < ncols; n0 += 32 * (kEpilogueWarps / 4)) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + n0), v);
+          uint8_t* panel = stage_out + (n0 >> 6) * (kTileM * 128);
+          const int c0 = (n0 & 63) >> 3;
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t pk[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float x0 = __uint_as_float(v[j + 2 * q]), x1 = __uint_as_float(v[j + 2 * q + 1]);
+              if (IS_BF16) {
+                __nv_bfloat162 hh = __floats2bfloat162_rn(x0, x1);
+                pk[q] = *reinterpret_cast<uint32_t*>(&hh);
+              } else {
+                __half2 hh = __floats2half2_rn(x0, x1);
+                pk[q] = *reinterpret_cast<uint32_t*>(&hh);
+              }
+            }
+            *reinterpret_cast<uint4*>(panel + sw128_off(row, c0 + (j >> 3))) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acce0 + 8 * acc);  // TMEM accumulator is free as soon as it has been read
+        fence_proxy_async();
+        asm volatile("bar.sync 3, %0;" ::"n"(kEpilogueWarps * 32) : "memory");
+        if (ew == 0 && lane == 0) {
+          for (int pn = 0; pn < (ncols >> 6); ++pn)
+            asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&tmap_o),
+                         "r"(nb * 256 + pn * 64), "r"((int)row0), "r"(smem_u32(stage_out + pn * (kTileM * 128)))
+                         : "memory");
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+        continue;
+      }
       for (int n0 = (ew >> 2) * 32; n0 < ncols; n0 += 32 * (kEpilogueWarps / 4)) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + n0), v);
@@ -200,6 +245,7 @@ seg_mm_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       __syncwarp();
       if (lane == 0) mbar_arrive(acce0 + 8 * acc);
     }
+    if (tma_out && ew == 0 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (warp == kTmaWarp) {
     // ===================== TMA producer for the B[r] chunks =====================
     if (lane == 0) {
@@ -440,7 +486,7 @@ using namespace dglb::gmm;
 // A: [*, lda] 16-bit (bf16: dtype kBF16, fp16: kF16), rows addressed as idx_a[i] (int64, optional) or i, i in [0, n_rows)
 // Bt: [R, Nout, K] contiguous (K-major), seg_off: [R+1] int64 row offsets, tile_off: [R+1] int64 prefix of ceil(len/128)
 // out: [n_rows, Nout] same 16-bit type, or fp32 when out_f32
-DGLB_API int dglb200_cuda_segment_mm_tc(int dtype, const void* A, int64_t n_a_rows, int64_t lda, const void* idx_a, const void* Bt,
+DGLB_API int dglb200_cuda_segment_mm_tc(int dtype, const void* A, int64_t n_a_rows, int64_t n_out_rows, int64_t lda, const void* idx_a, const void* Bt,
                                         const void* seg_off, const void* tile_off, int64_t max_tiles, int R, int K,
                                         int Nout, void* out, int out_f32, void* stream) {
   DGLB_TRY
@@ -472,18 +518,31 @@ DGLB_API int dglb200_cuda_segment_mm_tc(int dtype, const void* A, int64_t n_a_ro
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(A) failed with code " + std::to_string((int)rc));
   }
+  // TMA-store epilogue for 16-bit outputs whose width is a multiple of 64 columns
+  const int tma_out = (!out_f32 && Nout % 64 == 0) ? 1 : 0;
+  CUtensorMap tmap_o = tmap;
+  if (tma_out) {
+    const cuuint64_t odim[2] = {(cuuint64_t)Nout, (cuuint64_t)n_out_rows};
+    const cuuint64_t ostride[1] = {(cuuint64_t)Nout * 2};
+    const cuuint32_t obox[2] = {64, (cuuint32_t)kTileM};
+    rc = get_encode()(&tmap_o, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, out, odim,
+                      ostride, obox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(out) failed with code " + std::to_string((int)rc));
+  }
+  const size_t out_stage_bytes = tma_out ? (size_t)Np_full * 256 + 1024 : 0;
   const size_t stage_bytes = kTileM * 128 + (size_t)Np_full * 128;
   // 4 stages measured best (profiles/README.md: 6-8 stages were 5-10 % slower on the memory-bound shapes)
-  const int nst = (int)std::max<size_t>(2, std::min<size_t>(4, (size_t)(200 * 1024) / stage_bytes));
-  const size_t smem = nst * stage_bytes + 1024 + 256;
+  const int nst = (int)std::max<size_t>(2, std::min<size_t>(4, ((size_t)(224 * 1024) - out_stage_bytes - 2048) / stage_bytes));
+  const size_t smem = nst * stage_bytes + 1024 + 256 + out_stage_bytes;
   const unsigned grid = (unsigned)std::min<int64_t>(max_tiles * NB, sm_count());
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == kBF16) {
     DGLB_CUDA_CHECK(cudaFuncSetAttribute(seg_mm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    seg_mm_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmap_a, tmap, tma_a, (const uint16_t*)A, lda, (const int64_t*)idx_a, (const int64_t*)seg_off, (const int64_t*)tile_off, R, K, Nout, NB, out, out_f32, nst);
+    seg_mm_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmap_a, tmap, tmap_o, tma_a, tma_out, (const uint16_t*)A, lda, (const int64_t*)idx_a, (const int64_t*)seg_off, (const int64_t*)tile_off, R, K, Nout, NB, out, out_f32, nst);
   } else {
     DGLB_CUDA_CHECK(cudaFuncSetAttribute(seg_mm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    seg_mm_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmap_a, tmap, tma_a, (const uint16_t*)A, lda, (const int64_t*)idx_a, (const int64_t*)seg_off, (const int64_t*)tile_off, R, K, Nout, NB, out, out_f32, nst);
+    seg_mm_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmap_a, tmap, tmap_o, tma_a, tma_out, (const uint16_t*)A, lda, (const int64_t*)idx_a, (const int64_t*)seg_off, (const int64_t*)tile_off, R, K, Nout, NB, out, out_f32, nst);
   }
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH

@@ -48,8 +48,8 @@ def _seg_mm_tc(a, idx_a, n_rows, bt, seg_off, tile_off, out_f32=False):
     R, Nout, K = bt.shape
     out = torch.empty((n_rows, Nout), dtype=torch.float32 if out_f32 else a.dtype, device=a.device)
     max_tiles = (n_rows + _TILE_M - 1) // _TILE_M + R
-    loader.cuda_lib().fn("dglb200_cuda_segment_mm_tc", "ipllppppliiipip")(
-        dtype_code(a.dtype), a.data_ptr(), a.shape[0], a.stride(0), 0 if idx_a is None else idx_a.data_ptr(), bt.data_ptr(),
+    loader.cuda_lib().fn("dglb200_cuda_segment_mm_tc", "iplllppppliiipip")(
+        dtype_code(a.dtype), a.data_ptr(), a.shape[0], n_rows, a.stride(0), 0 if idx_a is None else idx_a.data_ptr(), bt.data_ptr(),
         seg_off.data_ptr(), tile_off.data_ptr(), max_tiles, R, K, Nout, out.data_ptr(), 1 if out_f32 else 0,
         loader.stream_ptr())
     return out
