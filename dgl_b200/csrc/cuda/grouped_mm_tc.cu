@@ -303,7 +303,8 @@ done:
 // block, 256-wide n block); item_off[r] = number of row chunks of relations < r.
 template <bool IS_BF16>
 __global__ void __launch_bounds__(kThreads, 1)
-seg_mm_dw_tc_kernel(const uint16_t* __restrict__ A, int64_t lda, const int64_t* __restrict__ idx_a,
+seg_mm_dw_tc_kernel(const __grid_constant__ CUtensorMap tmap_do, const int tma_do,
+                    const uint16_t* __restrict__ A, int64_t lda, const int64_t* __restrict__ idx_a,
                     const uint16_t* __restrict__ dO, int64_t ldo, const int64_t* __restrict__ seg_off,
                     const int64_t* __restrict__ item_off, int R, int K, int Nout, int KB, int NB,
                     float* __restrict__ dW) {
@@ -324,7 +325,7 @@ seg_mm_dw_tc_kernel(const uint16_t* __restrict__ A, int64_t lda, const int64_t* 
   const uint32_t accf0 = smem_u32(bars + 2 * kStages), acce0 = smem_u32(bars + 2 * kStages + 2);
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(full0 + 8 * s, kProducerWarps);
+      mbar_init(full0 + 8 * s, kProducerWarps + (tma_do ? 1 : 0));  // + the TMA thread that brings the dO boxes
       mbar_init(empty0 + 8 * s, 1);
     }
     for (int a = 0; a < 2; ++a) {
@@ -374,14 +375,14 @@ seg_mm_dw_tc_kernel(const uint16_t* __restrict__ A, int64_t lda, const int64_t* 
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int col = nb * 256 + b * 64 + c * 8;
-          vb[b] = (b < n_boxes && live && col < Nout) ? __ldg(reinterpret_cast<const uint4*>(dO + orow * ldo + col))
-                                                      : make_uint4(0, 0, 0, 0);
+          vb[b] = (!tma_do && b < n_boxes && live && col < Nout) ? __ldg(reinterpret_cast<const uint4*>(dO + orow * ldo + col))
+                                                                 : make_uint4(0, 0, 0, 0);
         }
 #pragma unroll
         for (int b = 0; b < 2; ++b) *reinterpret_cast<uint4*>(sa + b * box_bytes + sw128_off(rr, c)) = va[b];
 #pragma unroll
         for (int b = 0; b < 4; ++b)
-          if (b < n_boxes) *reinterpret_cast<uint4*>(sb + b * box_bytes + sw128_off(rr, c)) = vb[b];
+          if (!tma_do && b < n_boxes) *reinterpret_cast<uint4*>(sb + b * box_bytes + sw128_off(rr, c)) = vb[b];
         fence_proxy_async();
         __syncwarp();
         if (lane == 0) mbar_arrive(full0 + 8 * stage);
@@ -427,6 +428,27 @@ seg_mm_dw_tc_kernel(const uint16_t* __restrict__ A, int64_t lda, const int64_t* 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acce0 + 8 * acc);
+    }
+  } else if (warp == kTmaWarp) {
+    // dO boxes by TMA (contiguous rows, unmasked: rows outside the segment meet zeroed A rows, rows / columns outside the
+    // tensor are zero-filled); the A operand stays with the producers because its out-of-segment rows must be zero
+    if (tma_do && lane == 0) {
+      uint32_t g = 0;
+      for (int64_t t = blockIdx.x; t < n_items; t += gridDim.x) {
+        int r, rows;
+        int64_t row0;
+        locate_tile(t / per_chunk, item_off, R, seg_off, kDwRowChunk, r, row0, rows);
+        const int nb = (int)(t % NB);
+        const int n_sub = (rows + kChunkK - 1) / kChunkK;
+        for (int sc = 0; sc < n_sub; ++sc, ++g) {
+          const int stage = g % kStages;
+          mbar_wait(empty0 + 8 * stage, ((g / kStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(full0 + 8 * stage, b_bytes);
+          const uint32_t sb = smem_u32(smem + stage * stage_bytes + a_bytes);
+          for (int b = 0; b < n_boxes; ++b)
+            tma_load_2d(sb + b * box_bytes, &tmap_do, full0 + 8 * stage, nb * 256 + b * 64, (int)(row0 + (int64_t)sc * kChunkK));
+        }
+      }
     }
   } else if (warp == kMmaWarp) {
     const uint32_t fmt = IS_BF16 ? 1u : 0u;
@@ -550,7 +572,7 @@ DGLB_API int dglb200_cuda_segment_mm_tc(int dtype, const void* A, int64_t n_a_ro
 
 // dW: [R, K, Nout] fp32, accumulated into (caller zeroes it). item_off: [R+1] int64 prefix of ceil(len / 2048).
 DGLB_API int dglb200_cuda_segment_mm_dw_tc(int dtype, const void* A, int64_t lda, const void* idx_a, const void* dO,
-                                           int64_t ldo, const void* seg_off, const void* item_off, int64_t max_items,
+                                           int64_t n_do_rows, int64_t ldo, const void* seg_off, const void* item_off, int64_t max_items,
                                            int R, int K, int Nout, void* dW, void* stream) {
   DGLB_TRY
   DGLB_CHECK(dtype == kBF16 || dtype == kF16, "segment_mm_dw_tc: bf16 / fp16 inputs only");
@@ -562,14 +584,27 @@ DGLB_API int dglb200_cuda_segment_mm_dw_tc(int dtype, const void* A, int64_t lda
   const int n_boxes = (Np_full + 63) / 64;
   const size_t stage_bytes = (size_t)(2 + n_boxes) * kChunkK * 128;
   const size_t smem = kStages * stage_bytes + 1024 + 256;
+  // dO through TMA: needs a dense row stride that is a multiple of 16 bytes (always true here) - boxes of [64 rows x 64 cols]
+  const int tma_do = 1;
+  CUtensorMap tmap_do;
+  {
+    const cuuint64_t ddim[2] = {(cuuint64_t)Nout, (cuuint64_t)n_do_rows};
+    const cuuint64_t dstride[1] = {(cuuint64_t)ldo * 2};
+    const cuuint32_t dbox[2] = {64, (cuuint32_t)kChunkK};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult rc = get_encode()(&tmap_do, dtype == kBF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2,
+                               const_cast<void*>(dO), ddim, dstride, dbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (rc != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled(dO) failed with code " + std::to_string((int)rc));
+  }
   const unsigned grid = (unsigned)std::min<int64_t>(max_items * NB * KB, sm_count());
   cudaStream_t st = (cudaStream_t)stream;
   if (dtype == kBF16) {
     DGLB_CUDA_CHECK(cudaFuncSetAttribute(seg_mm_dw_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    seg_mm_dw_tc_kernel<true><<<grid, kThreads, smem, st>>>((const uint16_t*)A, lda, (const int64_t*)idx_a, (const uint16_t*)dO, ldo, (const int64_t*)seg_off, (const int64_t*)item_off, R, K, Nout, KB, NB, (float*)dW);
+    seg_mm_dw_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmap_do, tma_do, (const uint16_t*)A, lda, (const int64_t*)idx_a, (const uint16_t*)dO, ldo, (const int64_t*)seg_off, (const int64_t*)item_off, R, K, Nout, KB, NB, (float*)dW);
   } else {
     DGLB_CUDA_CHECK(cudaFuncSetAttribute(seg_mm_dw_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    seg_mm_dw_tc_kernel<false><<<grid, kThreads, smem, st>>>((const uint16_t*)A, lda, (const int64_t*)idx_a, (const uint16_t*)dO, ldo, (const int64_t*)seg_off, (const int64_t*)item_off, R, K, Nout, KB, NB, (float*)dW);
+    seg_mm_dw_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmap_do, tma_do, (const uint16_t*)A, lda, (const int64_t*)idx_a, (const uint16_t*)dO, ldo, (const int64_t*)seg_off, (const int64_t*)item_off, R, K, Nout, KB, NB, (float*)dW);
   }
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH

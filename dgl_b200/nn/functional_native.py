@@ -60,9 +60,9 @@ def _seg_mm_dw_tc(a, idx_a, dout, seg_off, item_off, R):
     K = a.shape[1]
     dw = torch.zeros((R, K, Nout), dtype=torch.float32, device=a.device)
     max_items = (n_rows + _DW_ROWS - 1) // _DW_ROWS + R
-    loader.cuda_lib().fn("dglb200_cuda_segment_mm_dw_tc", "iplpplppliiipp")(
+    loader.cuda_lib().fn("dglb200_cuda_segment_mm_dw_tc", "iplppllppliiipp")(
         dtype_code(a.dtype), a.data_ptr(), a.stride(0), 0 if idx_a is None else idx_a.data_ptr(), dout.data_ptr(),
-        dout.stride(0), seg_off.data_ptr(), item_off.data_ptr(), max_items, R, K, Nout, dw.data_ptr(),
+        n_rows, dout.stride(0), seg_off.data_ptr(), item_off.data_ptr(), max_items, R, K, Nout, dw.data_ptr(),
         loader.stream_ptr())
     return dw
 
