@@ -202,3 +202,34 @@ def test_sageconv_block_uses_tcgen05_path_and_matches_unfused():
     assert (gws - conv.fc_self.weight.grad).abs().max() / conv.fc_self.weight.grad.abs().max() < 0.03
     assert (gwn - conv.fc_neigh.weight.grad).abs().max() / conv.fc_neigh.weight.grad.abs().max() < 0.03
     assert (gb - conv.fc_self.bias.grad).abs().max() / conv.fc_self.bias.grad.abs().max() < 0.03
+
+
+@pytest.mark.gpu
+def test_fused_gat_on_blocks_and_zero_in_degree():
+    from dgl_b200.dataloading import NeighborSampler
+    torch.manual_seed(0)
+    g = dgl.rand_graph(3000, 30000, idtype=torch.int32)                   # some vertices have no in-edges
+    x = torch.randn(3000, 24)
+    conv = dgl.nn.GATConv(24, 8, 4, allow_zero_in_degree=True)
+    y = conv(g, x)
+    yc = conv.cuda()(g.to("cuda"), x.cuda())
+    assert torch.allclose(yc.cpu(), y, atol=1e-4)
+    zero = (g.in_degrees() == 0)
+    assert int(zero.sum()) > 0
+    bias = conv.bias.detach().cpu().view(4, 8)
+    assert torch.allclose(yc.cpu()[zero], bias.expand(int(zero.sum()), 4, 8), atol=1e-5)   # nothing aggregated: bias only
+    # message-flow graph (num_src != num_dst)
+    gc = g.to("cuda")
+    inp, out, blocks = NeighborSampler([8]).sample(gc, torch.arange(500, device="cuda", dtype=torch.int32))
+    blk = blocks[0]
+    xb = x.cuda()[inp.long()].requires_grad_()
+    yb = conv(blk, xb)
+    yb.sum().backward()
+    blk_cpu = blk.to("cpu")
+    xb2 = xb.detach().cpu().requires_grad_()
+    conv_cpu = dgl.nn.GATConv(24, 8, 4, allow_zero_in_degree=True)
+    conv_cpu.load_state_dict({k: v.cpu() for k, v in conv.state_dict().items()})
+    yr = conv_cpu(blk_cpu, xb2)
+    yr.sum().backward()
+    assert yb.shape == (500, 4, 8) and torch.allclose(yb.detach().cpu(), yr.detach(), atol=1e-4)
+    assert torch.allclose(xb.grad.cpu(), xb2.grad, atol=1e-4)
