@@ -19,7 +19,13 @@ def rank_assignment(ids, world_size, seed=0):
 def rank_sort(ids, rank, world_size, seed=0):
     """Sort ids by owner; returns (sorted_ids, permutation, offsets[world+1])."""
     owner = rank_assignment(ids, world_size, seed)
-    perm = torch.sort(owner, stable=True)[1]
+    if ids.is_cuda:
+        # radix sort on ceil(log2 world) key bits (csrc/cuda/graph_kernels.cu, reference
+        # cooperative_minibatching_utils.cu:56-113 uses a segmented radix sort by rank)
+        from ..._graph_kernels import partition_perm
+        perm = partition_perm(owner.to(torch.int32).contiguous(), world_size)
+    else:
+        perm = torch.sort(owner, stable=True)[1]
     counts = torch.bincount(owner, minlength=world_size)
     offsets = torch.zeros(world_size + 1, dtype=torch.int64, device=ids.device)
     offsets[1:] = torch.cumsum(counts, 0)

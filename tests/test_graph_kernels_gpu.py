@@ -165,3 +165,11 @@ def test_structure_helpers_native(idtype):
     assert torch.equal(rows.cpu(), torch.sort(row)[0])
     ids = torch.arange(300, device=DEV, dtype=idtype) * 3
     assert torch.equal(gk.expand_indptr(ip_g, node_ids=ids).cpu(), torch.sort(row)[0] * 3)
+
+
+def test_cooperative_rank_sort_native():
+    from dgl_b200.graphbolt.impl.cooperative import rank_sort
+    ids = torch.randint(0, 100000, (5000,))
+    s_c, p_c, o_c = rank_sort(ids, 0, 8, seed=3)
+    s_g, p_g, o_g = rank_sort(ids.to(DEV), 0, 8, seed=3)
+    assert torch.equal(s_g.cpu(), s_c) and torch.equal(p_g.cpu(), p_c) and torch.equal(o_g.cpu(), o_c)
