@@ -9,7 +9,8 @@ from . import function  # noqa: F401
 from .base import ALL, EID, ETYPE, NID, NTYPE, DGLError, dgl_warning  # noqa: F401
 from .batch import batch, batch_hetero, slice_batch, unbatch, unbatch_hetero  # noqa: F401
 from .convert import (bipartite_from_networkx, bipartite_from_scipy, block_to_graph, create_block,  # noqa: F401
-                      from_networkx, from_scipy, graph, heterograph, rand_bipartite, rand_graph,
+                      from_cugraph, from_networkx, from_scipy, graph, hetero_from_shared_memory, heterograph,
+                      rand_bipartite, rand_graph, to_cugraph,
                       to_heterogeneous, to_homogeneous, to_networkx)
 from .frame import LazyFeature  # noqa: F401
 from .heterograph import DGLBlock, DGLGraph, DGLHeteroGraph  # noqa: F401

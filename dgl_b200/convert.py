@@ -17,7 +17,7 @@ from .graph_index import UnitGraph
 from .heterograph import DGLBlock, DGLGraph, combine_names
 
 __all__ = ["graph", "heterograph", "create_block", "block_to_graph", "to_heterogeneous", "to_homogeneous",
-           "from_scipy", "bipartite_from_scipy", "from_networkx", "bipartite_from_networkx", "to_networkx",
+           "from_scipy", "bipartite_from_scipy", "hetero_from_shared_memory", "to_cugraph", "from_cugraph", "from_networkx", "bipartite_from_networkx", "to_networkx",
            "rand_graph", "rand_bipartite", "from_cugraph", "to_cugraph"]
 
 
@@ -424,3 +424,36 @@ def from_cugraph(cugraph_graph):
 
 def to_cugraph(g):
     raise DGLError("cugraph is not available in this build")
+
+
+def hetero_from_shared_memory(name):
+    """Graph structure (no features) previously published with ``g.shared_memory(name)`` (reference convert.py:187)."""
+    from .utils.shared_mem import graph_from_shared_memory
+    return graph_from_shared_memory(name)
+
+
+def to_cugraph(g):
+    """cuGraph interop (reference convert.py to_cugraph) - needs the optional ``cugraph`` / ``cudf`` packages."""
+    try:
+        import cudf
+        import cugraph
+    except ImportError as e:  # pragma: no cover - optional dependency
+        raise DGLError("to_cugraph requires the cugraph and cudf packages") from e
+    if not g.is_homogeneous:
+        raise DGLError("dgl_graph is not Homogeneous")
+    u, v = g.edges()
+    df = cudf.DataFrame({"source": cudf.from_dlpack(torch.utils.dlpack.to_dlpack(u.contiguous())),
+                         "destination": cudf.from_dlpack(torch.utils.dlpack.to_dlpack(v.contiguous()))})
+    cg = cugraph.Graph(directed=True)
+    cg.from_cudf_edgelist(df)
+    return cg
+
+
+def from_cugraph(cugraph_graph):
+    """Create a graph from a cuGraph graph on the same device (reference convert.py from_cugraph)."""
+    if not cugraph_graph.is_directed():
+        cugraph_graph = cugraph_graph.to_directed()
+    edges = cugraph_graph.edges()
+    src = torch.utils.dlpack.from_dlpack(edges["src"].to_dlpack())
+    dst = torch.utils.dlpack.from_dlpack(edges["dst"].to_dlpack())
+    return graph((src, dst))

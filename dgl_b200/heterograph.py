@@ -1088,6 +1088,25 @@ class DGLGraph:
     def int(self):
         return self.astype(torch.int32)
 
+    def adjacency_matrix(self, etype=None):
+        """Alias of :meth:`adj` (reference heterograph.py:3759)."""
+        return self.adj(etype)
+
+    def get_node_storage(self, key, ntype=None):
+        """Storage object (column) of node feature ``key`` (reference heterograph.py:1769): supports ``fetch``."""
+        return self._node_frames[self.get_ntype_id(ntype)]._columns[key]
+
+    def get_edge_storage(self, key, etype=None):
+        """Storage object (column) of edge feature ``key`` (reference heterograph.py:1773)."""
+        return self._edge_frames[self.get_etype_id(etype)]._columns[key]
+
+    def materialize_data(self):
+        """Resolve every lazily indexed feature column on the current device (reference heterograph.py:5758)."""
+        for frame in list(self._node_frames) + list(self._edge_frames):
+            for col in frame._columns.values():
+                col.data  # noqa: B018 - touching the property materialises the column
+        return self
+
     def shared_memory(self, name, formats=("coo", "csr", "csc")):
         from .utils.shared_mem import graph_to_shared_memory
         return graph_to_shared_memory(self, name, formats)

@@ -28,7 +28,7 @@ __all__ = [
     "compact_graphs", "khop_adj", "khop_graph", "line_graph", "add_nodes", "add_edges", "remove_nodes",
     "remove_edges", "laplacian_lambda_max", "metapath_reachable_graph", "reorder_graph", "sort_csr_by_tag",
     "sort_csc_by_tag", "knn_graph", "segmented_knn_graph", "radius_graph", "random_walk_pe", "lap_pe",
-    "laplacian_pe", "double_radius_node_labeling", "shortest_dist", "svd_pe", "to_half", "to_float", "to_double",
+    "laplacian_pe", "double_radius_node_labeling", "shortest_dist", "svd_pe", "to_half", "to_bfloat16", "to_float", "to_double",
     "adj_product_graph", "adj_sum_graph", "out_subgraph_like", "unique_and_compact", "norm_by_dst",
     "reverse_heterograph", "to_simple_graph", "to_bidirected_stale", "laplacian_lambda_max",
     "metis_partition", "metis_partition_assignment", "partition_graph_with_halo",
@@ -791,6 +791,11 @@ def _cast_feats(g, dtype):
 
 def to_half(g):
     return _cast_feats(g, torch.float16)
+
+
+def to_bfloat16(g):
+    """Shallow copy whose floating-point node / edge features are bfloat16 (reference functional.py:3729)."""
+    return _cast_feats(g, torch.bfloat16)
 
 
 def to_float(g):
