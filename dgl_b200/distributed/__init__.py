@@ -10,3 +10,34 @@ from .partition import (GraphPartitionBook, RangePartitionBook, load_partition, 
                         load_partition_feats, partition_graph)
 from . import rpc  # noqa: F401
 from .rpc import DistConnectError  # noqa: F401
+from .partition import dgl_partition_to_graphbolt, gb_convert_single_dgl_partition  # noqa: F401,E402
+from .rpc import connect_to_server, start_server  # noqa: F401,E402
+
+
+class NodeCollator:
+    """Legacy collator kept for API parity (reference distributed/dist_dataloader.py NodeCollator): turns a list of seed
+    nodes into (input_nodes, output_nodes, blocks) with a block sampler."""
+
+    def __init__(self, g, nids, graph_sampler):
+        self.g, self.nids, self.graph_sampler = g, nids, graph_sampler
+
+    @property
+    def dataset(self):
+        return self.nids
+
+    def collate(self, items):
+        import torch
+        items = torch.as_tensor(items) if not isinstance(items, dict) else items
+        return self.graph_sampler.sample(self.g, items)
+
+
+class EdgeCollator(NodeCollator):
+    """Legacy edge collator (reference EdgeCollator): seeds are edge ids; the sampler must be an edge-prediction sampler."""
+
+    def __init__(self, g, eids, graph_sampler, g_sampling=None, exclude=None, reverse_eids=None, reverse_etypes=None,
+                 negative_sampler=None):
+        super().__init__(g, eids, graph_sampler)
+        from ..dataloading import as_edge_prediction_sampler
+        if not hasattr(graph_sampler, "sample_blocks_for_edges") and (negative_sampler is not None or exclude is not None):
+            self.graph_sampler = as_edge_prediction_sampler(graph_sampler, exclude=exclude, reverse_eids=reverse_eids,
+                                                            reverse_etypes=reverse_etypes, negative_sampler=negative_sampler)

@@ -230,3 +230,44 @@ def load_partition_feats(part_config, part_id, load_nodes=True, load_edges=True)
     nf = torch.load(os.path.join(base, info["node_feats"]), weights_only=False) if load_nodes else None
     ef = torch.load(os.path.join(base, info["edge_feats"]), weights_only=False) if load_edges else None
     return nf, ef
+
+
+def gb_convert_single_dgl_partition(part_id, graph_formats, part_config, store_eids=True, store_inner_node=False,
+                                    store_inner_edge=False):
+    """Convert ONE partition written by ``partition_graph`` into a GraphBolt ``FusedCSCSamplingGraph`` saved next to it as
+    ``fused_csc_sampling_graph.pt`` (reference distributed/partition.py:1844). Returns the path."""
+    from ..base import EID, NID
+    from ..graphbolt import fused_csc_sampling_graph as make_fused
+    g, _, _, gpb, _, ntypes, etypes = load_partition(part_config, part_id, load_feats=False)
+    indptr, indices, eids = g._graphs[0].csc()
+    node_attrs, edge_attrs = {}, {}
+    if NID in g.ndata:
+        node_attrs[NID] = g.ndata[NID]
+    if store_inner_node and "inner_node" in g.ndata:
+        node_attrs["inner_node"] = g.ndata["inner_node"]
+    perm = eids.long() if eids is not None else None
+    if store_eids and EID in g.edata:
+        edge_attrs[EID] = g.edata[EID] if perm is None else g.edata[EID][perm]
+    if store_inner_edge and "inner_edge" in g.edata:
+        edge_attrs["inner_edge"] = g.edata["inner_edge"] if perm is None else g.edata["inner_edge"][perm]
+    fg = make_fused(indptr.long(), indices.long(), node_attributes=node_attrs or None, edge_attributes=edge_attrs or None)
+    with open(part_config) as f:
+        meta = json.load(f)
+    base = os.path.dirname(part_config)
+    rel = os.path.join(os.path.dirname(meta[f"part-{part_id}"]["part_graph"]), "fused_csc_sampling_graph.pt")
+    path = os.path.join(base, rel)
+    torch.save(fg, path)
+    return rel
+
+
+def dgl_partition_to_graphbolt(part_config, *, store_eids=True, store_inner_node=False, store_inner_edge=False,
+                               graph_formats=None, n_jobs=1):
+    """Convert every partition of ``part_config`` to GraphBolt and record the files in the config
+    (``part_graph_graphbolt``), as the reference does (distributed/partition.py:1965)."""
+    with open(part_config) as f:
+        meta = json.load(f)
+    for pid in range(meta["num_parts"]):
+        rel = gb_convert_single_dgl_partition(pid, graph_formats, part_config, store_eids, store_inner_node, store_inner_edge)
+        meta[f"part-{pid}"]["part_graph_graphbolt"] = rel
+    with open(part_config, "w") as f:
+        json.dump(meta, f, sort_keys=True, indent=4)

@@ -170,3 +170,25 @@ class RPCClient:
             except Exception:  # noqa: BLE001
                 pass
         self.ep.close()
+
+
+def start_server(server_id, ip_config, num_servers, num_clients, server_state, max_queue_size=None, net_type="socket"):
+    """Run the RPC server loop of ``server_id`` until every client has disconnected (reference rpc_server.py:20)."""
+    servers = read_ip_config(ip_config) if isinstance(ip_config, str) else list(ip_config)
+    ip, port = servers[server_id][:2]
+    RPCServer(server_id, ip, int(port), num_clients, server_state).serve_forever()
+
+
+_DEFAULT_CLIENT = [None]
+
+
+def connect_to_server(ip_config, num_servers=1, max_queue_size=None, net_type="socket", group_id=0):
+    """Connect this process to every server of ``ip_config`` and keep the client as the process default
+    (reference rpc_client.py:104). Retries are bounded by ``DGL_DIST_MAX_TRY_TIMES`` inside the transport."""
+    servers = read_ip_config(ip_config) if isinstance(ip_config, str) else list(ip_config)
+    _DEFAULT_CLIENT[0] = RPCClient([(s[0], int(s[1])) for s in servers])
+    return _DEFAULT_CLIENT[0]
+
+
+def get_default_client():
+    return _DEFAULT_CLIENT[0]

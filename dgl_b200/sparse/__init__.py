@@ -19,7 +19,7 @@ from ..ops import sparse_autograd as SA
 __all__ = ["SparseMatrix", "spmatrix", "from_coo", "from_csr", "from_csc", "diag", "identity", "val_like", "spmm",
            "bspmm", "spspmm", "sddmm", "bsddmm", "softmax", "sum", "smax", "smin", "smean", "sprod", "add", "sub",
            "mul", "div", "power", "neg", "inv", "matmul", "sp_broadcast_v", "sp_add_v", "sp_sub_v", "sp_mul_v",
-           "sp_div_v", "to_torch_sparse_coo", "from_torch_sparse"]
+           "sp_div_v", "to_torch_sparse_coo", "to_torch_sparse_csr", "to_torch_sparse_csc", "from_torch_sparse", "reduce"]
 
 
 class SparseMatrix:
@@ -307,6 +307,20 @@ def from_torch_sparse(t):
     return from_coo(idx[0], idx[1], t.values(), tuple(t.shape[:2]))
 
 
+def to_torch_sparse_csr(mat):
+    """torch sparse CSR tensor of ``mat`` (the order of the non-zeros may change; reference sparse_matrix.py:1373)."""
+    indptr, indices, eids = mat.csr()
+    val = mat.val if eids is None else mat.val[eids.long()]
+    return torch.sparse_csr_tensor(indptr.long(), indices.long(), val, size=tuple(mat.shape) + tuple(mat.val.shape[1:]))
+
+
+def to_torch_sparse_csc(mat):
+    """torch sparse CSC tensor of ``mat`` (reference sparse_matrix.py:1411)."""
+    indptr, indices, eids = mat.csc()
+    val = mat.val if eids is None else mat.val[eids.long()]
+    return torch.sparse_csc_tensor(indptr.long(), indices.long(), val, size=tuple(mat.shape) + tuple(mat.val.shape[1:]))
+
+
 def to_torch_sparse_coo(mat):
     r, c = mat.coo()
     return torch.sparse_coo_tensor(torch.stack([r.long(), c.long()]), mat.val, mat.shape + tuple(mat.val.shape[1:]))
@@ -407,6 +421,16 @@ def _reduce(A, dim, op):
     red = "amax" if op == "max" else "amin"
     out = torch.zeros(shape, dtype=v.dtype, device=v.device).scatter_reduce(0, idx, v, reduce=red, include_self=False)
     return out
+
+
+def reduce(A, dim=None, rtype="sum"):  # noqa: A001
+    """Reduce the non-zeros along ``dim`` with ``rtype`` in sum / smin / smax / smean / sprod (reference
+    sparse/reduction.py:reduce)."""
+    op = {"sum": "sum", "smin": "min", "smax": "max", "smean": "mean", "sprod": "prod",
+          "min": "min", "max": "max", "mean": "mean", "prod": "prod"}.get(rtype)
+    if op is None:
+        raise ValueError(f"unknown reduce type {rtype}")
+    return _reduce(A, dim, op)
 
 
 def sum(A, dim=None):  # noqa: A001

@@ -155,3 +155,21 @@ def test_multiprocess_servers():
         assert n == 600
         assert torch.equal(feat, g.ndata["feat"][nmap[torch.tensor([3, 250, 590])]])
         assert bool(g.has_edges_between(nmap[su], nmap[sv]).all())
+
+
+def test_partition_to_graphbolt_conversion():
+    import json
+    g = dgl.rand_graph(300, 3000)
+    g.ndata["feat"] = torch.randn(300, 4)
+    with tempfile.TemporaryDirectory() as d:
+        dd.partition_graph(g, "tg", 2, d)
+        cfg = os.path.join(d, "tg.json")
+        dd.dgl_partition_to_graphbolt(cfg, store_eids=True, store_inner_node=True)
+        meta = json.load(open(cfg))
+        for pid in range(2):
+            rel = meta[f"part-{pid}"]["part_graph_graphbolt"]
+            fg = torch.load(os.path.join(d, rel), weights_only=False)
+            pg = dd.load_partition(cfg, pid, load_feats=False)[0]
+            assert fg.total_num_nodes == pg.num_nodes() and fg.total_num_edges == pg.num_edges()
+            sub = fg.sample_neighbors(torch.arange(10), [3])
+            assert int(sub.sampled_csc.indptr[-1]) <= 30
