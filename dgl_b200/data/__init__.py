@@ -5,7 +5,7 @@ from .synthetic import SHAPES, rmat_edges, rmat_graph, shaped_dataset  # noqa: F
 
 def __getattr__(name):
     import importlib
-    for modname in ("dgl_dataset", "graph_serialize", "more", "builtin", "csv_dataset", "utils"):
+    for modname in ("dgl_dataset", "graph_serialize", "more", "builtin", "csv_dataset", "utils", "extra"):
         mod = importlib.import_module(f"{__name__}.{modname}")
         if hasattr(mod, name):
             return getattr(mod, name)
