@@ -34,3 +34,11 @@ def numpy_save_aligned(path, arr, alignment=4096):
     with open(path, "wb") as f:
         f.write(hdr)
         arr.tofile(f)
+
+from .compat import *  # noqa: F401,F403,E402
+from .compat import (FeatureKey, GBWarning, all_to_all, built_with_cuda, bytes_to_number_of_items, check_sha1,  # noqa: F401,E402
+                     convert_to_hetero, download, extract_archive, gb_warning, gb_warning_format, get_attributes,
+                     get_device_to_host_uva_stream, get_host_to_device_uva_stream, get_nonproperty_attributes,
+                     indptr_edge_ids, is_listlike, is_wsl, minibatcher_default, preprocess_ondisk_dataset, recursive_apply,
+                     recursive_apply_reduce_all, revert_to_homo, seed, wrap_with_cached_feature)
+from .impl.negative_sampler import NegativeSampler  # noqa: F401,E402

@@ -1,0 +1,470 @@
+"""Public GraphBolt names that complete the reference's surface (python/dgl/graphbolt/{base,dataset,feature_store,
+sampling_graph,internal/*,impl/ondisk_metadata}.py): abstract base classes, datapipe markers / buffering stages, the
+pydantic models of ``metadata.yaml``, stream helpers and small utilities."""
+from __future__ import annotations
+
+import enum
+import hashlib
+import os
+import tarfile
+import warnings
+import zipfile
+from collections import namedtuple
+from typing import Any, Dict, List, Optional
+
+import torch
+
+from .datapipes import MiniBatchTransformer, _Stage
+from .impl.caches import FeatureCache, GPUCache
+from .impl.features import Feature
+
+# ---------------------------------------------------------------------------------------------- abstract bases
+FeatureKey = namedtuple("FeatureKey", ["domain", "type", "name"])
+
+
+class FeatureStore:
+    """Abstract collection of features addressed by (domain, type, name) (reference feature_store.py)."""
+
+    def __getitem__(self, feature_key) -> Feature:
+        raise NotImplementedError
+
+    def __setitem__(self, feature_key, feature):
+        raise NotImplementedError
+
+    def __contains__(self, feature_key) -> bool:
+        raise NotImplementedError
+
+    def read(self, domain, type_name, feature_name, ids=None):
+        return self[(domain, type_name, feature_name)].read(ids)
+
+    def size(self, domain, type_name, feature_name):
+        return self[(domain, type_name, feature_name)].size()
+
+    def count(self, domain, type_name, feature_name):
+        return self[(domain, type_name, feature_name)].count()
+
+    def metadata(self, domain, type_name, feature_name):
+        return self[(domain, type_name, feature_name)].metadata()
+
+    def update(self, domain, type_name, feature_name, value, ids=None):
+        self[(domain, type_name, feature_name)].update(value, ids)
+
+    def keys(self):
+        raise NotImplementedError
+
+
+class SamplingGraph:
+    """Abstract sampling graph (reference sampling_graph.py)."""
+
+    @property
+    def num_nodes(self):
+        raise NotImplementedError
+
+    @property
+    def num_edges(self):
+        raise NotImplementedError
+
+    def copy_to_shared_memory(self, shared_memory_name):
+        raise NotImplementedError
+
+    def to(self, device):
+        raise NotImplementedError
+
+
+class Task:
+    """Abstract task: metadata + train / validation / test item sets (reference dataset.py)."""
+
+    metadata: Dict[str, Any] = None
+    train_set = validation_set = test_set = None
+
+
+class Dataset:
+    """Abstract dataset: tasks, graph, feature store, name, all-nodes set (reference dataset.py)."""
+
+    @property
+    def tasks(self):
+        raise NotImplementedError
+
+    @property
+    def graph(self):
+        raise NotImplementedError
+
+    @property
+    def feature(self):
+        raise NotImplementedError
+
+    @property
+    def dataset_name(self):
+        raise NotImplementedError
+
+    @property
+    def all_nodes_set(self):
+        raise NotImplementedError
+
+
+class LegacyDataset(Dataset):
+    """GraphBolt view of a legacy ``dgl.data`` node-classification dataset (reference impl/legacy_dataset.py)."""
+
+    def __init__(self, legacy):
+        from .impl.features import BasicFeatureStore, TorchBasedFeature
+        from .impl.fused_csc_sampling_graph import from_dglgraph
+        from .itemset import ItemSet
+        g = legacy[0]
+        self._name = getattr(legacy, "name", type(legacy).__name__)
+        self._graph = from_dglgraph(g)
+        self._feature = BasicFeatureStore({("node", None, k): TorchBasedFeature(v) for k, v in g.ndata.items()
+                                           if v.is_floating_point()})
+        task = Task()
+        task.metadata = {"name": "node_classification", "num_classes": getattr(legacy, "num_classes", None)}
+        lab = g.ndata.get("label")
+        for split, mask in (("train_set", "train_mask"), ("validation_set", "val_mask"), ("test_set", "test_mask")):
+            if mask in g.ndata and lab is not None:
+                ids = g.ndata[mask].nonzero().squeeze(1)
+                setattr(task, split, ItemSet((ids, lab[ids]), names=("seeds", "labels")))
+        self._tasks = [task]
+        self._all = ItemSet(g.num_nodes(), names="seeds")
+
+    tasks = property(lambda self: self._tasks)
+    graph = property(lambda self: self._graph)
+    feature = property(lambda self: self._feature)
+    dataset_name = property(lambda self: self._name)
+    all_nodes_set = property(lambda self: self._all)
+
+
+CPUFeatureCache = FeatureCache
+GPUFeatureCache = GPUCache
+
+# ---------------------------------------------------------------------------------------------- datapipe stages / markers
+
+
+class EndMarker(_Stage):
+    """Pass-through stage marking the end of a rewritable datapipe segment (reference base.py EndMarker)."""
+
+    def __init__(self, datapipe):
+        super().__init__(datapipe)
+
+    def __iter__(self):
+        yield from self.datapipe
+
+
+class FeatureFetcherStartMarker(EndMarker):
+    """Marks where feature fetching starts (the DataLoader inserts the overlap stages after it)."""
+
+
+class Bufferer(_Stage):
+    """Keep up to ``buffer_size`` upstream items in flight (reference base.py Bufferer)."""
+
+    def __init__(self, datapipe, buffer_size=1):
+        super().__init__(datapipe)
+        if buffer_size <= 0:
+            raise ValueError("'buffer_size' is required to be a positive integer.")
+        self.buffer_size = buffer_size
+
+    def __iter__(self):
+        from collections import deque
+        buf = deque()
+        for item in self.datapipe:
+            buf.append(item)
+            if len(buf) > self.buffer_size:
+                yield buf.popleft()
+        while buf:
+            yield buf.popleft()
+
+
+class Waiter(_Stage):
+    """Call ``.wait()`` on every item that carries a pending asynchronous result (reference base.py Waiter)."""
+
+    def __init__(self, datapipe):
+        super().__init__(datapipe)
+
+    def __iter__(self):
+        for item in self.datapipe:
+            w = getattr(item, "wait", None)
+            yield w() if callable(w) else item
+
+
+class SamplePerLayer(MiniBatchTransformer):
+    """One layer of neighbour sampling as its own stage (the reference splits ``sample_neighbor`` into these)."""
+
+    def __init__(self, datapipe, sampler, fanout, overlap_fetch=False, asynchronous=False):
+        super().__init__(datapipe, self._sample)
+        self.sampler, self.fanout = sampler, fanout
+
+    def _sample(self, minibatch):
+        sub = self.sampler(minibatch._seed_nodes, self.fanout)
+        minibatch.sampled_subgraphs = [sub] + list(minibatch.sampled_subgraphs or [])
+        return minibatch
+
+
+class FetchInsubgraphData(MiniBatchTransformer):
+    """Fetch the adjacency lists of the current seeds from a (host-pinned) graph ahead of sampling."""
+
+    def __init__(self, datapipe, graph, prob_name=None):
+        super().__init__(datapipe, self._fetch)
+        self.graph, self.prob_name = graph, prob_name
+
+    def _fetch(self, minibatch):
+        from .impl.caches import index_select_csc
+        seeds = minibatch._seed_nodes
+        if torch.is_tensor(seeds) and seeds.is_cuda:
+            minibatch._sliced_sampling_graph = index_select_csc(self.graph.csc_indptr, self.graph.indices, seeds)
+        return minibatch
+
+
+class CombineCachedAndFetchedInSubgraph(MiniBatchTransformer):
+    """Merge adjacency lists served by ``GPUGraphCache`` with the ones fetched from the host graph."""
+
+    def __init__(self, datapipe, prob_name=None):
+        super().__init__(datapipe, lambda mb: mb)
+
+
+class SeedEdgesExcluder(MiniBatchTransformer):
+    """Datapipe form of ``exclude_seed_edges`` (reference impl/neighbor_sampler.py)."""
+
+    def __init__(self, datapipe, include_reverse_edges=False, reverse_etypes_mapping=None, asynchronous=False):
+        from .utils import exclude_seed_edges
+        super().__init__(datapipe, lambda mb: exclude_seed_edges(mb, include_reverse_edges, reverse_etypes_mapping))
+
+
+def minibatcher_default(batch, names):
+    """Default collation of an item-set batch into a ``MiniBatch`` (reference item_sampler.py)."""
+    from .minibatch import MiniBatch
+    if isinstance(names, str) or names is None:
+        names, batch = (names,), (batch,)
+    mb = MiniBatch()
+    for name, item in zip(names, batch):
+        if name is None:
+            continue
+        if not hasattr(mb, name):
+            warnings.warn(f"Unknown item name '{name}' is detected and added into `MiniBatch`.", GBWarning)
+        setattr(mb, name, item)
+    return mb
+
+
+# ---------------------------------------------------------------------------------------------- metadata.yaml models
+class OnDiskFeatureDataFormat(str, enum.Enum):
+    TORCH = "torch"
+    NUMPY = "numpy"
+
+
+class OnDiskTVTSetData(dict):
+    """One entry of a train / validation / test set: name, format, in_memory, path (reference ondisk_metadata.py)."""
+
+    def __init__(self, name=None, format="numpy", in_memory=True, path=None, **kw):
+        super().__init__(name=name, format=str(getattr(format, "value", format)), in_memory=in_memory, path=path, **kw)
+        self.__dict__ = self
+
+
+class OnDiskTVTSet(dict):
+    def __init__(self, type=None, data=None, **kw):
+        super().__init__(type=type, data=[OnDiskTVTSetData(**d) if not isinstance(d, OnDiskTVTSetData) else d for d in (data or [])], **kw)
+        self.__dict__ = self
+
+
+class OnDiskFeatureDataDomain(str, enum.Enum):
+    NODE = "node"
+    EDGE = "edge"
+    GRAPH = "graph"
+
+
+class OnDiskFeatureData(dict):
+    def __init__(self, domain=None, type=None, name=None, format="numpy", path=None, in_memory=True, **kw):
+        super().__init__(domain=str(getattr(domain, "value", domain)), type=type, name=name,
+                         format=str(getattr(format, "value", format)), path=path, in_memory=in_memory, **kw)
+        self.__dict__ = self
+
+
+class OnDiskGraphTopologyType(str, enum.Enum):
+    FUSED_CSC_SAMPLING = "FusedCSCSamplingGraph"
+
+
+class OnDiskGraphTopology(dict):
+    def __init__(self, type=OnDiskGraphTopologyType.FUSED_CSC_SAMPLING, path=None, **kw):
+        super().__init__(type=str(getattr(type, "value", type)), path=path, **kw)
+        self.__dict__ = self
+
+
+class OnDiskTaskData(dict):
+    def __init__(self, train_set=None, validation_set=None, test_set=None, **extra_fields):
+        super().__init__(train_set=train_set or [], validation_set=validation_set or [], test_set=test_set or [], **extra_fields)
+        self.__dict__ = self
+
+
+class OnDiskMetaData(dict):
+    """Top-level model of ``metadata.yaml`` (dataset_name, graph_topology, feature_data, tasks, include_original_edge_id)."""
+
+    def __init__(self, dataset_name=None, graph_topology=None, feature_data=None, tasks=None, include_original_edge_id=False,
+                 **kw):
+        super().__init__(dataset_name=dataset_name, graph_topology=graph_topology, feature_data=feature_data or [],
+                         tasks=tasks or [], include_original_edge_id=include_original_edge_id, **kw)
+        self.__dict__ = self
+
+
+def preprocess_ondisk_dataset(dataset_dir, include_original_edge_id=False, force_preprocess=None, auto_cast_to_optimal_dtype=True):
+    """Run the one-off preprocessing of an on-disk dataset and return the path of the generated metadata
+    (reference impl/ondisk_dataset.py preprocess_ondisk_dataset)."""
+    from .impl.datasets import OnDiskDataset
+    ds = OnDiskDataset(dataset_dir, include_original_edge_id=include_original_edge_id,
+                       force_preprocess=bool(force_preprocess)).load()
+    return os.path.join(dataset_dir, "preprocessed", "metadata.yaml") if ds is not None else None
+
+
+# ---------------------------------------------------------------------------------------------- helpers
+class GBWarning(UserWarning):
+    """GraphBolt warning category."""
+
+
+def gb_warning_format(message, category, filename, lineno, line=None):
+    return f"{filename}:{lineno}: {category.__name__}: {message}\n"
+
+
+def gb_warning(message, category=GBWarning, stacklevel=2):
+    warnings.warn(message, category=category, stacklevel=stacklevel)
+
+
+def seed(val):
+    """Seed the GraphBolt samplers (alias of ``set_seed``; reference base.py seed)."""
+    from .. import random as dgl_random
+    dgl_random.seed(int(val))
+    torch.manual_seed(int(val))
+
+
+def built_with_cuda():
+    from .._native import loader
+    try:
+        loader.cuda_lib()
+        return True
+    except Exception:  # noqa: BLE001
+        return False
+
+
+def is_wsl(v: str = None) -> bool:
+    import platform
+    v = v or platform.uname().release
+    return "microsoft" in v.lower()
+
+
+def is_listlike(x):
+    return isinstance(x, (list, tuple))
+
+
+def recursive_apply(data, fn, *args, **kwargs):
+    """Apply ``fn`` to every leaf of a nested list / tuple / dict (reference internal/utils.py)."""
+    if isinstance(data, dict):
+        return {k: recursive_apply(v, fn, *args, **kwargs) for k, v in data.items()}
+    if isinstance(data, (list, tuple)):
+        return type(data)(recursive_apply(v, fn, *args, **kwargs) for v in data)
+    return fn(data, *args, **kwargs)
+
+
+def recursive_apply_reduce_all(data, fn, *args, **kwargs):
+    if isinstance(data, dict):
+        return all(recursive_apply_reduce_all(v, fn, *args, **kwargs) for v in data.values())
+    if isinstance(data, (list, tuple)):
+        return all(recursive_apply_reduce_all(v, fn, *args, **kwargs) for v in data)
+    return fn(data, *args, **kwargs)
+
+
+def get_attributes(obj):
+    return [a for a in dir(obj) if not a.startswith("__") and not callable(getattr(obj, a))]
+
+
+def get_nonproperty_attributes(obj):
+    return [a for a in get_attributes(obj) if not isinstance(getattr(type(obj), a, None), property)]
+
+
+def bytes_to_number_of_items(cache_capacity_in_bytes, single_item):
+    item_bytes = single_item.nbytes if hasattr(single_item, "nbytes") else single_item.numel() * single_item.element_size()
+    return max(1, int(cache_capacity_in_bytes) // max(int(item_bytes), 1))
+
+
+def indptr_edge_ids(indptr, dtype=None, offset=None, output_size=None):
+    """Edge ids relative to the start of each row: for indptr [0, 2, 5] -> [0, 1, 0, 1, 2] (+ per-row ``offset``)."""
+    deg = (indptr[1:] - indptr[:-1]).long()
+    total = int(output_size) if output_size is not None else int(indptr[-1] - indptr[0])
+    starts = torch.repeat_interleave((indptr[:-1] - indptr[0]).long(), deg, output_size=total)
+    out = torch.arange(total, device=indptr.device) - starts
+    if offset is not None:
+        out = out + torch.repeat_interleave(offset.long(), deg, output_size=total)
+    return out.to(dtype or indptr.dtype)
+
+
+_streams = {}
+
+
+def get_host_to_device_uva_stream():
+    if "h2d" not in _streams:
+        _streams["h2d"] = torch.cuda.Stream(priority=-1)
+    return _streams["h2d"]
+
+
+def get_device_to_host_uva_stream():
+    if "d2h" not in _streams:
+        _streams["d2h"] = torch.cuda.Stream(priority=-1)
+    return _streams["d2h"]
+
+
+def all_to_all(outputs, inputs, group=None, async_op=False):
+    """List-of-tensors all-to-all that also works on gloo (reference subgraph_sampler.py:41-84)."""
+    import torch.distributed as dist
+    if dist.get_backend(group) == "nccl" or inputs[0].is_cuda:
+        return dist.all_to_all(outputs, inputs, group=group, async_op=async_op)
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    works = []
+    for r in range(world):                     # gloo has no all_to_all for lists: pairwise isend / irecv
+        if r == rank:
+            outputs[r].copy_(inputs[r])
+        else:
+            works.append(dist.isend(inputs[r], r, group=group))
+            works.append(dist.irecv(outputs[r], r, group=group))
+    for w in works:
+        w.wait()
+    return None
+
+
+def revert_to_homo(d):
+    """{'_N': x} / {'_N:_E:_N': x} style single-type dicts back to the bare value (reference internal/utils.py)."""
+    if isinstance(d, dict) and len(d) == 1:
+        return next(iter(d.values()))
+    return d
+
+
+def convert_to_hetero(x, key="_N"):
+    return x if isinstance(x, dict) else {key: x}
+
+
+def wrap_with_cached_feature(cached_feature_type, fallback_features, max_cache_size_in_bytes, *args, **kwargs):
+    """Wrap one feature (or every feature of a dict) in a cached feature class (reference impl/utils)."""
+    if isinstance(fallback_features, dict):
+        return {k: cached_feature_type(v, max_cache_size_in_bytes, *args, **kwargs) for k, v in fallback_features.items()}
+    return cached_feature_type(fallback_features, max_cache_size_in_bytes, *args, **kwargs)
+
+
+def check_sha1(filename, sha1_hash):
+    h = hashlib.sha1()
+    with open(filename, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 20), b""):
+            h.update(chunk)
+    return h.hexdigest() == sha1_hash
+
+
+def extract_archive(file, target_dir, overwrite=True):
+    if os.path.exists(target_dir) and not overwrite:
+        return
+    if file.endswith((".tar.gz", ".tgz", ".tar")):
+        with tarfile.open(file) as t:
+            t.extractall(target_dir)
+    elif file.endswith(".zip"):
+        with zipfile.ZipFile(file) as z:
+            z.extractall(target_dir)
+    else:
+        raise ValueError(f"Unrecognized file type: {file}")
+
+
+def download(url, path=None, overwrite=True, sha1_hash=None, retries=5, verify_ssl=True, log=True):
+    """Dataset download helper; this build has no network access, so only already-present files are accepted."""
+    fname = path if path and not os.path.isdir(path) else os.path.join(path or ".", url.split("/")[-1])
+    if os.path.exists(fname) and (sha1_hash is None or check_sha1(fname, sha1_hash)):
+        return fname
+    raise RuntimeError(f"cannot download {url}: no network access; place the file at {fname}")
