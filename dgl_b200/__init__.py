@@ -22,6 +22,8 @@ from . import nn  # noqa: F401
 from .version import __version__  # noqa: F401
 
 from .random import seed  # noqa: F401
+from . import backend  # noqa: F401,E402
+from .logging import enable_verbose_logging  # noqa: F401,E402
 
 _LAZY = {"sampling", "dataloading", "graphbolt", "sparse", "distributed", "optim", "data", "parallel", "models",
          "utils", "multiprocessing", "cuda", "geometry", "partition", "traversal", "propagate", "storages",
