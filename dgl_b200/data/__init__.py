@@ -4,6 +4,8 @@ from .synthetic import SHAPES, rmat_edges, rmat_graph, shaped_dataset  # noqa: F
 
 
 def __getattr__(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
     import importlib
     for modname in ("dgl_dataset", "graph_serialize", "more", "builtin", "csv_dataset", "utils", "extra"):
         mod = importlib.import_module(f"{__name__}.{modname}")

@@ -10,6 +10,8 @@ from .utils import (Identity, JumpingKnowledge, KNNGraph, LabelPropagation, Radi
 
 
 def __getattr__(name):
+    if name.startswith("__"):
+        raise AttributeError(name)
     import importlib
     for modname in ("sparse_emb", "network_emb", "gt", "explain"):
         mod = importlib.import_module(f"{__name__}.{modname}")
