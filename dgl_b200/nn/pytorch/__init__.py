@@ -5,3 +5,11 @@ from .. import *  # noqa: F401,F403
 from .. import conv  # noqa: F401
 from . import explain, factory, glob, gt, hetero, linear, link, network_emb, softmax, sparse_emb, utils  # noqa: F401
 from .softmax import edge_softmax  # noqa: F401
+
+
+def __getattr__(name):
+    # names dgl_b200.nn resolves lazily (NodeEmbedding, DeepWalk, GNNExplainer, graph-transformer blocks, ...)
+    if name.startswith("__"):
+        raise AttributeError(name)
+    from .. import __getattr__ as _parent_getattr
+    return _parent_getattr(name)
