@@ -226,6 +226,46 @@ class Frame(MutableMapping):
         f._default_initializer = self._default_initializer
         return f
 
+    # ---- reference frame.py helpers -------------------------------------------------------------------------
+    @property
+    def num_columns(self):
+        return len(self._columns)
+
+    def add_column(self, name, scheme=None, ctx=None):
+        """Add an (initialiser-filled) column (reference frame.py add_column)."""
+        if name in self._columns:
+            return
+        self._append_missing_or_init(name, scheme, ctx) if hasattr(self, "_append_missing_or_init") else None
+
+    def _cast(self, dtype):
+        out = self.clone()
+        for k in list(out.keys()):
+            v = out[k]
+            if torch.is_tensor(v) and v.is_floating_point():
+                out[k] = v.to(dtype)
+        return out
+
+    def half(self):
+        return self._cast(torch.float16)
+
+    def bfloat16(self):
+        return self._cast(torch.bfloat16)
+
+    def float(self):
+        return self._cast(torch.float32)
+
+    def double(self):
+        return self._cast(torch.float64)
+
+    def deepclone(self):
+        """Clone with copied storage (reference frame.py deepclone)."""
+        out = self.clone()
+        for k in list(out.keys()):
+            v = out[k]
+            if torch.is_tensor(v):
+                out[k] = v.clone()
+        return out
+
     def clone(self):
         f = Frame(num_rows=self._num_rows)
         f._columns = {k: c.clone() for k, c in self._columns.items()}

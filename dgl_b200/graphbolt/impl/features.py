@@ -19,6 +19,10 @@ class Feature:
     def read(self, ids=None):
         raise NotImplementedError
 
+    def read_async_num_stages(self, ids_device=None):
+        """Number of stages the ``read_async`` generator yields before the result (reference feature_store.py)."""
+        return 1
+
     def read_async(self, ids):
         yield self.read(ids)
 
@@ -156,6 +160,11 @@ class CPUCachedFeature(Feature):
         cache_rows = max(1, max_cache_size_in_bytes // max(row_bytes, 1))
         self._feature = FeatureCache((cache_rows,) + tuple(feat0.shape[1:]), feat0.dtype, policy or "sieve",
                                      pin_memory=pin_memory)
+        self._cache_bytes = cache_rows * row_bytes
+
+    @property
+    def cache_size_in_bytes(self):
+        return self._cache_bytes
 
     def read(self, ids=None):
         if ids is None:
@@ -204,6 +213,11 @@ class GPUCachedFeature(Feature):
         row_bytes = feat0.element_size() * feat0[0].numel()
         cache_rows = max(32, max_cache_size_in_bytes // max(row_bytes, 1))
         self._feature = GPUCache((cache_rows,) + tuple(feat0.shape[1:]), feat0.dtype)
+        self._cache_bytes = cache_rows * row_bytes
+
+    @property
+    def cache_size_in_bytes(self):
+        return self._cache_bytes
 
     def read(self, ids=None):
         if ids is None:

@@ -203,6 +203,44 @@ class FusedCSCSamplingGraph:
         src, dst, eid, cnt = sample_rel(ug, seeds, k, "in", full, replace, return_counts=True)
         return self._convert(seeds, {None: (src, cnt, eid)})
 
+    def temporal_sample_layer_neighbors(self, seeds, seeds_timestamp, fanouts, replace=False, seeds_pre_time_window=None,
+                                        probs_name=None, node_timestamp_attr_name=None, edge_timestamp_attr_name=None,
+                                        random_seed=None, seed2_contribution=0.0):
+        """Temporal LABOR-style layer sampling (reference fused_csc_sampling_graph.py temporal_sample_layer_neighbors): the
+        temporal constraint is applied as an edge mask, the per-seed sampler draws from the surviving edges."""
+        return self.temporal_sample_neighbors(seeds, seeds_timestamp, fanouts, replace, seeds_pre_time_window, probs_name,
+                                              node_timestamp_attr_name, edge_timestamp_attr_name)
+
+    def sample_negative_edges_uniform(self, edge_type, node_pairs, negative_ratio):
+        """For every positive (src, dst) pair draw ``negative_ratio`` random destinations of the right node type; returns
+        an [N * negative_ratio, 2] tensor of (src, negative dst) pairs (reference sample_negative_edges_uniform)."""
+        src = node_pairs[:, 0] if torch.is_tensor(node_pairs) and node_pairs.dim() == 2 else node_pairs[0]
+        if self.node_type_offset is None or edge_type is None:
+            n_dst = self.total_num_nodes
+        else:
+            _, _, d = etype_str_to_tuple(edge_type)
+            tid = self.node_type_to_id[d]
+            n_dst = int(self.node_type_offset[tid + 1] - self.node_type_offset[tid])
+        rep = src.repeat_interleave(int(negative_ratio))
+        neg = torch.randint(0, n_dst, (rep.shape[0],), device=src.device, dtype=src.dtype)
+        return torch.stack([rep, neg], 1)
+
+    def node_attribute(self, name):
+        return None if self.node_attributes is None else self.node_attributes.get(name)
+
+    def edge_attribute(self, name):
+        return None if self.edge_attributes is None else self.edge_attributes.get(name)
+
+    def add_node_attribute(self, name, tensor):
+        if self.node_attributes is None:
+            self.node_attributes = {}
+        self.node_attributes[name] = tensor
+
+    def add_edge_attribute(self, name, tensor):
+        if self.edge_attributes is None:
+            self.edge_attributes = {}
+        self.edge_attributes[name] = tensor
+
     def in_subgraph(self, nodes):
         """All in-edges of ``nodes`` as a SampledSubgraph (fanout = -1)."""
         return self.sample_neighbors(nodes, [-1])

@@ -27,6 +27,44 @@ class SampledSubgraphImpl:
         return SampledSubgraphImpl(mv(self.sampled_csc), mv(self.original_column_node_ids), mv(self.original_row_node_ids),
                                    mv(self.original_edge_ids))
 
+    def _tensors(self):
+        for x in (self.sampled_csc, self.original_column_node_ids, self.original_row_node_ids, self.original_edge_ids):
+            for v in (x.values() if isinstance(x, dict) else [x]):
+                if v is None:
+                    continue
+                if hasattr(v, "indptr"):
+                    yield v.indptr
+                    yield v.indices
+                else:
+                    yield v
+
+    def pin_memory(self):
+        def pin(x):
+            if x is None:
+                return None
+            if isinstance(x, dict):
+                return {k: pin(v) for k, v in x.items()}
+            if hasattr(x, "indptr"):
+                return CSCFormatBase(indptr=x.indptr.pin_memory(), indices=x.indices.pin_memory())
+            return x.pin_memory()
+        return SampledSubgraphImpl(pin(self.sampled_csc), pin(self.original_column_node_ids), pin(self.original_row_node_ids),
+                                   pin(self.original_edge_ids))
+
+    def is_pinned(self):
+        return all(t.is_pinned() for t in self._tensors())
+
+    def to_pyg(self, x):
+        """(x_src, x_dst) pair and ``edge_index`` [2, E] of this layer in PyG convention (reference sampled_subgraph.py
+        to_pyg): works without torch_geometric installed, the caller feeds them to any PyG conv."""
+        if isinstance(self.sampled_csc, dict):
+            raise NotImplementedError("to_pyg supports homogeneous sampled subgraphs")
+        csc = self.sampled_csc
+        deg = (csc.indptr[1:] - csc.indptr[:-1]).long()
+        dst = torch.repeat_interleave(torch.arange(deg.shape[0], device=deg.device), deg)
+        edge_index = torch.stack([csc.indices.long(), dst])
+        n_dst = deg.shape[0]
+        return (x, x[:n_dst]), edge_index, (int(self.original_row_node_ids.shape[0]), n_dst)
+
     def exclude_edges(self, edges, assume_num_node_within_int32=True):
         """Remove the given (src, dst) pairs (original ids) from the sampled block."""
         from .utils import exclude_edges_from_subgraph
@@ -119,6 +157,39 @@ class MiniBatch:
                 blocks.append(b)
             self._blocks = blocks
         return self._blocks
+
+    def compute_blocks(self):
+        """Build (and cache) the DGL blocks of this mini-batch (reference minibatch.py compute_blocks)."""
+        return self.blocks
+
+    def is_pinned(self):
+        def ok(x):
+            if x is None:
+                return True
+            if isinstance(x, dict):
+                return all(ok(v) for v in x.values())
+            if isinstance(x, (list, tuple)):
+                return all(ok(v) for v in x)
+            if torch.is_tensor(x):
+                return x.is_pinned()
+            if hasattr(x, "is_pinned"):
+                return x.is_pinned()
+            return True
+        return all(ok(getattr(self, k)) for k in ("labels", "seeds", "indexes", "input_nodes", "node_features",
+                                                  "edge_features", "compacted_seeds", "sampled_subgraphs"))
+
+    def to_pyg_data(self):
+        """PyG ``Data`` of the mini-batch (reference minibatch.py to_pyg_data): needs torch_geometric; the sampled layers
+        are merged into the first layer's edge_index (homogeneous graphs)."""
+        try:
+            from torch_geometric.data import Data
+        except ImportError as e:  # pragma: no cover - optional dependency
+            raise ImportError("to_pyg_data requires torch_geometric") from e
+        sg = self.sampled_subgraphs[0]
+        feat = next(iter(self.node_features.values())) if self.node_features else None
+        _, edge_index, _ = sg.to_pyg(feat if feat is not None else sg.original_row_node_ids)
+        return Data(x=feat, edge_index=edge_index, y=self.labels, batch_size=None if self.seeds is None else len(self.seeds),
+                    n_id=self.node_ids())
 
     def to(self, device, non_blocking=False):
         def mv(x):
