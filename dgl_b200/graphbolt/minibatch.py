@@ -63,7 +63,8 @@ class SampledSubgraphImpl:
         dst = torch.repeat_interleave(torch.arange(deg.shape[0], device=deg.device), deg)
         edge_index = torch.stack([csc.indices.long(), dst])
         n_dst = deg.shape[0]
-        return (x, x[:n_dst]), edge_index, (int(self.original_row_node_ids.shape[0]), n_dst)
+        n_src = int(self.original_row_node_ids.shape[0]) if self.original_row_node_ids is not None else int(x.shape[0])
+        return (x, x[:n_dst]), edge_index, (n_src, n_dst)
 
     def exclude_edges(self, edges, assume_num_node_within_int32=True):
         """Remove the given (src, dst) pairs (original ids) from the sampled block."""
