@@ -204,6 +204,14 @@ class DistTensor:
     def __init__(self, shape, dtype, name=None, init_func=None, part_policy=None, persistent=False, is_gdata=True,
                  attach=True, _existing=False, _graph=None, _dom="node", _typ="_N"):
         self._shape, self._dtype = tuple(shape), dtype
+        if _graph is None:
+            # user-created tensor: attach to the process's DistGraph and pick the partition policy by length, as the
+            # reference does when ``part_policy`` is omitted (dist_tensor.py:141-165)
+            _graph = getattr(_CTX, "graph", None)
+            if part_policy is not None and getattr(part_policy, "policy_str", "").startswith("edge"):
+                _dom = "edge"
+            elif _graph is not None and shape[0] == _graph.num_edges() and shape[0] != _graph.num_nodes():
+                _dom = "edge"
         self._g = _graph
         self._dom, self._typ = _dom, _typ
         self._name = name if _existing else f"{_dom}~{_typ}~{name}"
@@ -226,6 +234,37 @@ class DistTensor:
 
     def __len__(self):
         return self._shape[0]
+
+    @property
+    def tensor_name(self):
+        """User-facing name (without the kvstore prefix)."""
+        return self._name.split("~", 2)[-1]
+
+    @property
+    def kvstore_key(self):
+        return self._name
+
+    @property
+    def part_policy(self):
+        from .kvstore import PartitionPolicy
+        gpb = self._g.gpb if self._g is not None else None
+        return PartitionPolicy(f"{self._dom}~{self._typ}", gpb)
+
+    @property
+    def local_partition(self):
+        """Rows of this tensor stored on the local server (standalone / co-located), else None."""
+        if _CTX.mode == "standalone" and _CTX.local_servers:
+            store = getattr(_CTX.local_servers[0], "data", None) or getattr(_CTX.local_servers[0], "store", None)
+            if isinstance(store, dict) and self._name in store:
+                return store[self._name]
+        return None
+
+    def count_nonzero(self):
+        """Number of non-zero entries over all shards."""
+        tot, step = 0, 1 << 20
+        for lo in range(0, self._shape[0], step):
+            tot += int((self[torch.arange(lo, min(lo + step, self._shape[0]))] != 0).sum())
+        return tot
 
     def _owner(self, ids):
         gpb = self._g.gpb
@@ -283,6 +322,24 @@ class _DistDataView:
         self._g._tensors[val.name] = (val.shape[1:], val.dtype)
 
 
+ALL_NODES = "__ALL__"
+
+
+class _DistTypeView:
+    """``g.nodes[ntype].data`` / ``g.edges[etype].data`` views of a DistGraph."""
+
+    def __init__(self, g, dom):
+        self._g, self._dom = g, dom
+
+    def __getitem__(self, typ):
+        view = _DistDataView(self._g, self._dom)
+        return type("_TypedView", (), {"data": view})()
+
+    def __call__(self, typ=None):
+        n = self._g.num_nodes() if self._dom == "node" else self._g.num_edges()
+        return torch.arange(n)
+
+
 class DistGraph:
     """Client handle of a partitioned graph served by DistGraphServer processes (or in-process when standalone)."""
 
@@ -305,6 +362,7 @@ class DistGraph:
         self.canonical_etypes = [("_N", "_E", "_N")]
         self.idtype = torch.int64
         self.device = torch.device("cpu")
+        _CTX.graph = self
 
     def get_partition_book(self):
         return self.gpb
@@ -353,6 +411,97 @@ class DistGraph:
 
     def get_num_client(self):
         return get_num_client()
+
+    # ---- type / schema queries (reference dist_graph.py DistGraph) ----------------------------------------
+    def get_ntype_id(self, ntype=None):
+        if ntype is None:
+            if len(self.ntypes) != 1:
+                raise DGLError("Node type name must be specified if there are more than one node types.")
+            return 0
+        return self.ntypes.index(ntype)
+
+    def to_canonical_etype(self, etype=None):
+        if etype is None:
+            if len(self.canonical_etypes) != 1:
+                raise DGLError("Edge type name must be specified if there are more than one edge types.")
+            return self.canonical_etypes[0]
+        if isinstance(etype, tuple):
+            return etype
+        for c in self.canonical_etypes:
+            if c[1] == etype:
+                return c
+        raise DGLError(f'Edge type "{etype}" does not exist.')
+
+    def get_etype_id(self, etype=None):
+        return self.canonical_etypes.index(self.to_canonical_etype(etype))
+
+    @property
+    def nodes(self):
+        return _DistTypeView(self, "node")
+
+    @property
+    def edges(self):
+        return _DistTypeView(self, "edge")
+
+    def node_attr_schemes(self):
+        return {k.split("~", 2)[2]: v for k, v in self._tensors.items() if k.startswith("node~")}
+
+    def edge_attr_schemes(self):
+        return {k.split("~", 2)[2]: v for k, v in self._tensors.items() if k.startswith("edge~")}
+
+    def is_pinned(self):
+        return False
+
+    def get_node_partition_policy(self, ntype="_N"):
+        from .kvstore import PartitionPolicy
+        return PartitionPolicy("node~" + ntype, self.gpb)
+
+    def get_edge_partition_policy(self, etype="_E"):
+        from .kvstore import PartitionPolicy
+        et = etype[1] if isinstance(etype, tuple) else etype
+        return PartitionPolicy("edge~" + et, self.gpb)
+
+    def add_edge_attribute(self, name):
+        """Make edge data ``name`` available to the distributed samplers as an edge attribute (GraphBolt partitions
+        keep attributes inside the sampling graph; here samplers read edge data through the servers directly)."""
+        if "edge~_E~" + name not in self._tensors and name not in self.edge_attr_schemes():
+            raise DGLError(f"Fail to find data of {name}.")
+
+    def in_degrees(self, u=ALL_NODES):
+        return self._degrees(u, "in")
+
+    def out_degrees(self, u=ALL_NODES):
+        return self._degrees(u, "out")
+
+    def _degrees(self, u, direction):
+        """Degrees of (global) node ids, answered by the owning partitions (standalone: the local partition)."""
+        lp = self.local_partition
+        if lp is None:
+            raise DGLError("in_degrees / out_degrees need the local partition (standalone mode or co-located server)")
+        from ..base import NID
+        deg = lp.in_degrees() if direction == "in" else lp.out_degrees()
+        full = torch.zeros(self._num_nodes, dtype=deg.dtype)
+        full[lp.ndata[NID].long()] = deg if NID in lp.ndata else deg
+        if isinstance(u, str):
+            return full
+        return full[torch.as_tensor(u).long()]
+
+    def edge_subgraph(self, edges, relabel_nodes=True, store_ids=True):
+        """Subgraph induced by (global) edge ids, built from ``find_edges`` (reference DistGraph.edge_subgraph)."""
+        from ..convert import graph as make_graph
+        from ..base import EID, NID
+        eids = torch.as_tensor(edges).long()
+        u, v = self.find_edges(eids)
+        if relabel_nodes:
+            nodes, inv = torch.unique(torch.cat([u, v]), return_inverse=True)
+            sg = make_graph((inv[: u.shape[0]], inv[u.shape[0]:]), num_nodes=nodes.shape[0])
+            if store_ids:
+                sg.ndata[NID] = nodes
+        else:
+            sg = make_graph((u, v), num_nodes=self._num_nodes)
+        if store_ids:
+            sg.edata[EID] = eids
+        return sg
 
 
 def _merge(g, results):

@@ -48,6 +48,76 @@ class RangePartitionBook:
 
     canonical_etypes = etypes
 
+    # ---- reference graph_partition_book.py RangePartitionBook extras ------------------------------------------
+    @property
+    def global_nid_dtype(self):
+        return torch.int64
+
+    @property
+    def global_eid_dtype(self):
+        return torch.int64
+
+    def to_canonical_etype(self, etype):
+        return etype
+
+    def shared_memory(self, graph_name):
+        """Publish the book's range tables in POSIX shared memory under ``graph_name`` (server -> trainers)."""
+        from ..utils.shared_mem import tensors_to_shared_memory
+        tensors = {f"node~{k}": v for k, v in self._node_map.items()}
+        tensors.update({f"edge~{k}": v for k, v in self._edge_map.items()})
+        return tensors_to_shared_memory(graph_name + "_gpb", tensors,
+                                        meta={"part_id": self._partid, "num_parts": self._num_partitions,
+                                              "ntypes": self._ntypes, "etypes": self._etypes})
+
+    def _homo_offsets(self, maps, order):
+        """Start of every type's block in the homogeneous id space of every partition: ids are laid out partition by
+        partition, type by type inside a partition (the layout ``partition_graph`` writes)."""
+        types = sorted(order, key=order.get)
+        P = self._num_partitions
+        sizes = torch.stack([maps[t][:, 1] - maps[t][:, 0] for t in types], 1)            # [P, T]
+        flat = sizes.reshape(-1)
+        starts = (torch.cumsum(flat, 0) - flat).reshape(P, len(types))
+        return types, sizes, starts
+
+    def _to_homo(self, ids, typ, maps, order):
+        types, sizes, starts = self._homo_offsets(maps, order)
+        t = types.index(typ)
+        ids = torch.as_tensor(ids).long()
+        rng = maps[typ]
+        part = torch.searchsorted(rng[:, 1].contiguous(), ids, right=True)
+        return starts[part, t] + (ids - rng[part, 0])
+
+    def _to_per_type(self, ids, maps, order):
+        types, sizes, starts = self._homo_offsets(maps, order)
+        ids = torch.as_tensor(ids).long()
+        ends = (starts + sizes).reshape(-1)
+        slot = torch.searchsorted(ends.contiguous(), ids, right=True)
+        p, t = slot // len(types), slot % len(types)
+        base = torch.stack([maps[x][:, 0] for x in types], 1)                              # [P, T]
+        return t, base[p, t] + (ids - starts.reshape(-1)[slot])
+
+    def map_to_homo_nid(self, ids, ntype):
+        return self._to_homo(ids, ntype, self._node_map, self._ntypes)
+
+    def map_to_homo_eid(self, ids, etype):
+        return self._to_homo(ids, etype, self._edge_map, self._etypes)
+
+    def map_to_per_ntype(self, ids):
+        return self._to_per_type(ids, self._node_map, self._ntypes)
+
+    def map_to_per_etype(self, ids):
+        return self._to_per_type(ids, self._edge_map, self._etypes)
+
+    @property
+    def local_ntype_offset(self):
+        types, sizes, _ = self._homo_offsets(self._node_map, self._ntypes)
+        return [0] + torch.cumsum(sizes[self._partid], 0).tolist()
+
+    @property
+    def local_etype_offset(self):
+        types, sizes, _ = self._homo_offsets(self._edge_map, self._etypes)
+        return [0] + torch.cumsum(sizes[self._partid], 0).tolist()
+
     def _num(self, m):
         return int((m[:, 1] - m[:, 0]).sum())
 
