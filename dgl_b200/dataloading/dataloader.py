@@ -158,6 +158,14 @@ class DataLoader:
         self.num_workers = num_workers
         self.kwargs = kwargs
 
+    def attach_data(self, name, data):
+        """Add a data source other than node / edge features for prefetching (reference dataloader.py:1258): samplers can
+        request rows of it through ``LazyFeature`` and the loader resolves them alongside the graph features."""
+        if not hasattr(self, "other_storages"):
+            self.other_storages = {}
+        from ..storages import wrap_storage
+        self.other_storages[name] = wrap_storage(data)
+
     def set_epoch(self, epoch):
         self.batcher.set_epoch(epoch)
 

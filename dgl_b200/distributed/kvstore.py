@@ -157,6 +157,68 @@ class KVClient:
     def barrier(self):
         self._dg._call_many([(sid, self._dg.SVC_BARRIER, None) for sid in range(self.num_servers)])
 
+    # ---- reference kvstore.py KVClient extras ------------------------------------------------------------------
+    @property
+    def client_id(self):
+        c = self._dg._CTX.client
+        return 0 if c is None else c.client_id
+
+    @property
+    def machine_id(self):
+        return 0 if self._gpb is None else self._gpb.partid
+
+    @property
+    def role(self):
+        return "default"
+
+    @property
+    def all_possible_part_policy(self):
+        doms = sorted({n.rsplit("~", 1)[0] for n in self._meta})
+        return {d: PartitionPolicy(d, self._gpb) for d in doms}
+
+    def gdata_name_list(self):
+        return self.data_name_list()
+
+    def get_partid(self, name, id_tensor):
+        """Owning partition of every id of tensor ``name``."""
+        return self._owner(name, torch.as_tensor(id_tensor).long().reshape(-1))
+
+    def count_nonzero(self, name):
+        tail, dtype = self._meta[name]
+        dom = name.split("~", 1)[0]
+        n = self._gpb._num_nodes() if dom == "node" and hasattr(self._gpb, "_num_nodes") else None
+        if n is None:
+            m = self._gpb._node_map if dom == "node" else self._gpb._edge_map
+            n = int(sum(int((v[:, 1] - v[:, 0]).sum()) for v in m.values()))
+        tot = 0
+        for lo in range(0, n, 1 << 20):
+            tot += int((self.pull(name, torch.arange(lo, min(n, lo + (1 << 20)))) != 0).sum())
+        return tot
+
+    def delete_data(self, name):
+        """Forget tensor ``name`` on this client (servers keep non-persistent data until shutdown)."""
+        self._meta.pop(name, None)
+
+    def union(self, operand1_name, operand2_name, output_name):
+        """output = operand1 | operand2 (element-wise OR of two boolean / integer masks stored in the KVStore)."""
+        tail, dtype = self._meta[operand1_name]
+        dom = operand1_name.split("~", 1)[0]
+        m = self._gpb._node_map if dom == "node" else self._gpb._edge_map
+        n = int(sum(int((v[:, 1] - v[:, 0]).sum()) for v in m.values()))
+        if output_name not in self._meta:
+            self.init_data(output_name, (n,) + tuple(tail), dtype,
+                           PartitionPolicy(operand1_name.rsplit("~", 1)[0], self._gpb))
+        for lo in range(0, n, 1 << 20):
+            ids = torch.arange(lo, min(n, lo + (1 << 20)))
+            self.push(output_name if "~" in output_name else [k for k in self._meta if k.endswith("~" + output_name)][0], ids,
+                      self.pull(operand1_name, ids) | self.pull(operand2_name, ids))
+
+    def register_pull_handler(self, name, func):
+        if self._dg._CTX.mode != "standalone":
+            raise DGLError("pull handlers must be registered on the servers")
+        for st in self._dg._CTX.local_servers:
+            getattr(st, "pull_handlers", st.handlers)[("pull", name)] = func
+
     def register_push_handler(self, name, func):
         if self._dg._CTX.mode != "standalone":
             raise DGLError("push handlers must be registered on the servers (KVServer.register_push_handler)")

@@ -118,6 +118,27 @@ class SparseMatrix:
         r, c = self.coo()
         return bool((r == c).all())
 
+    def compact(self, dim, leading_indices=None):
+        """Drop empty rows (``dim=0``) / columns (``dim=1``) and relabel that dimension; ``leading_indices`` are placed
+        first (like ``include_dst_in_src`` of ``to_block``). Returns (matrix, new index -> original index)
+        (reference sparse_matrix.py:683)."""
+        r, c = self.coo()
+        ids = (r if dim == 0 else c).long()
+        if leading_indices is not None:
+            lead = torch.as_tensor(leading_indices, device=ids.device).long()
+            present = torch.unique(ids)
+            rest = present[~torch.isin(present, lead)]
+            original = torch.cat([lead, rest])
+        else:
+            original = torch.unique(ids)
+        lookup = torch.full((int(max(self.shape[dim], int(original.max()) + 1 if original.numel() else 0)),), -1,
+                            dtype=torch.long, device=ids.device)
+        lookup[original] = torch.arange(original.shape[0], device=ids.device)
+        new = lookup[ids]
+        shape = (original.shape[0], self.shape[1]) if dim == 0 else (self.shape[0], original.shape[0])
+        rows, cols = (new, c.long()) if dim == 0 else (r.long(), new)
+        return from_coo(rows, cols, self.val, shape), original
+
     def has_duplicate(self):
         r, c = self.coo()
         key = r.long() * max(self._shape[1], 1) + c.long()
