@@ -36,3 +36,91 @@ def test_chunk_partition_dispatch_verify(tmp_path):
     dg = dd.DistGraph("toy")
     assert dg.num_nodes() == 500 and dg.num_edges() == 4000
     dd.exit_client()
+
+
+def _dist_worker(rank, world, port, chunked, parts, out, q):
+    import traceback
+    try:
+        os.environ.update({"MASTER_ADDR": "127.0.0.1", "MASTER_PORT": str(port), "RANK": str(rank), "WORLD_SIZE": str(world)})
+        sys.path.insert(0, ROOT)
+        import torch.distributed as dist
+        dist.init_process_group("gloo", rank=rank, world_size=world)
+        from tools.distpartitioning.data_shuffle import gen_dist_partitions
+        path = gen_dist_partitions(rank, world, chunked, parts, out)
+        dist.destroy_process_group()
+        q.put((rank, "ok", path))
+    except Exception:  # noqa: BLE001
+        q.put((rank, "error", traceback.format_exc()))
+
+
+def test_distributed_partition_pipeline_gloo(tmp_path):
+    """One gloo process per partition; the result must equal partition_graph(node_part=...) run in one process."""
+    import socket
+    import torch.multiprocessing as mp
+    from chunk_graph import chunk_graph
+    from random_partition import random_partition
+    from dgl_b200 import distributed as dd
+    g = dgl.rand_graph(400, 3000, idtype=torch.int64)
+    g.ndata["feat"] = torch.randn(400, 5)
+    g.edata["w"] = torch.rand(3000)
+    chunked, parts, out = str(tmp_path / "chunked"), str(tmp_path / "parts"), str(tmp_path / "out")
+    chunk_graph(g, "toy", num_chunks=3, output_path=chunked)
+    random_partition(chunked, 2, parts)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_dist_worker, args=(r, 2, port, chunked, parts, out, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in range(2)]
+    for p in procs:
+        p.join(30)
+    assert all(st == "ok" for _, st, _ in res), [m for _, st, m in res if st != "ok"]
+    cfg = os.path.join(out, "toy.json")
+    import numpy as np
+    node_part = torch.from_numpy(np.loadtxt(os.path.join(parts, "_N.txt"), dtype=np.int64))
+    ref_dir = str(tmp_path / "ref")
+    dd.partition_graph(g, "toy", 2, ref_dir, node_part=node_part)
+    u, v = g.edges()
+    for p in range(2):
+        pg, nf, ef, gpb, *_ = dd.load_partition(cfg, p)
+        rg, rnf, ref_, rgpb, *_ = dd.load_partition(os.path.join(ref_dir, "toy.json"), p)
+        assert gpb._node_map["_N"].tolist() == rgpb._node_map["_N"].tolist()
+        assert gpb._edge_map["_N:_E:_N"].tolist() == rgpb._edge_map["_N:_E:_N"].tolist()
+        inner = pg.ndata["inner_node"].bool()
+        orig = pg.ndata["orig_id"]
+        assert torch.equal(torch.sort(orig[inner])[0], torch.nonzero(node_part == p).squeeze(1))
+        assert torch.equal(nf["_N/feat"], g.ndata["feat"][orig[inner]])                 # features follow the shuffle
+        ps, pd = pg.edges()
+        eo = pg.edata["orig_id"]
+        assert torch.equal(orig[ps.long()], u[eo]) and torch.equal(orig[pd.long()], v[eo])   # edges map back exactly
+        assert torch.equal(torch.sort(eo)[0], torch.nonzero(node_part[v] == p).squeeze(1))
+        assert torch.allclose(ef["_N:_E:_N/w"], g.edata["w"][eo])
+        # same inner node numbering as the single-process partitioner
+        assert torch.equal(pg.ndata["orig_id"][inner], rg.ndata["orig_id"][rg.ndata["inner_node"].bool()])
+    # consumable by the runtime
+    os.environ["DGL_DIST_MODE"] = "standalone"
+    dd.initialize(part_config=cfg)
+    dg = dd.DistGraph("toy")
+    assert dg.num_nodes() == 400 and dg.num_edges() == 3000
+    dd.exit_client()
+
+
+def test_parmetis_pre_post_process(tmp_path):
+    import numpy as np
+    from chunk_graph import chunk_graph
+    sys.path.insert(0, ROOT)
+    from tools.distpartitioning.parmetis_postprocess import post_process
+    from tools.distpartitioning.parmetis_preprocess import gen_parmetis_input
+    hg = dgl.heterograph({("a", "r", "b"): (torch.randint(0, 30, (100,)), torch.randint(0, 20, (100,))),
+                          ("b", "q", "a"): (torch.randint(0, 20, (80,)), torch.randint(0, 30, (80,)))})
+    chunked = str(tmp_path / "c")
+    chunk_graph(hg, "h", num_chunks=2, output_path=chunked)
+    nfiles, efiles = gen_parmetis_input(chunked, str(tmp_path / "pm"))
+    n = sum(np.loadtxt(f, dtype=np.int64).reshape(-1, 4).shape[0] for f in nfiles)
+    e = sum(np.loadtxt(f, dtype=np.int64).reshape(-1, 2).shape[0] for f in efiles)
+    assert n == 50 and e == 180
+    out = str(tmp_path / "pm" / "h_part.2")
+    np.savetxt(out, np.stack([np.arange(50), np.arange(50) % 2], 1), fmt="%d")
+    pdir = post_process(chunked, out, str(tmp_path / "parts"))
+    assert np.loadtxt(os.path.join(pdir, "a.txt")).shape[0] == 30 and np.loadtxt(os.path.join(pdir, "b.txt")).shape[0] == 20

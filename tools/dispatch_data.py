@@ -5,7 +5,9 @@
 The reference shuffles node/edge data between ranks with gloo all-to-all because no single host can hold the graph; this
 build targets 8 x 180 GB GPUs per host with TBs of host RAM, so the dispatcher re-assembles the chunks and emits every
 partition from one process (``--num-workers`` parallelises the per-partition writes over processes that each own a
-subset of the partition ids). Output layout == ``dgl.distributed.partition_graph``."""
+subset of the partition ids). Output layout == ``dgl.distributed.partition_graph``.
+For graphs that must not be assembled on one host use the gloo pipeline ``tools/distpartitioning/data_proc_pipeline.py``
+(one process per partition, all-to-all shuffle) - it produces the same partitions."""
 import argparse
 import json
 import os
