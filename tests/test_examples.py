@@ -43,3 +43,14 @@ def test_gin_graph_classification_cpu():
 
 def test_link_prediction_sage_cpu():
     _run("link_prediction_sage.py", "--steps", "3")
+
+
+@pytest.mark.parametrize("script", ["1_node_classification.py", "2_message_passing.py", "3_minibatch_training.py",
+                                    "4_sparse_and_graphbolt.py"])
+def test_tutorials_run(script):
+    old = sys.argv
+    sys.argv = [script]
+    try:
+        runpy.run_path(os.path.join(ROOT, "docs", "tutorials", script), run_name="__main__")
+    finally:
+        sys.argv = old
