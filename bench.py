@@ -202,7 +202,8 @@ def run_ours(args):
     n, u, v, feat, labels, train_idx = make_data(dev, args.scale)
     g = dgl.graph((u, v), num_nodes=n, idtype=torch.int32, device=dev)
     del u, v
-    comm = P2PComm() if world > 1 else None
+    # --comm nccl: BASELINE communication path (NCCL all-reduce + the same Adam kernel) for A/B against the fused P2P path
+    comm = ("nccl" if args.comm == "nccl" else P2PComm()) if world > 1 else None
     dtype = torch.bfloat16 if args.dtype == "bf16" else torch.float32
     tr = FusedSAGETrainer(g, feat, labels, CLASSES, hidden=HIDDEN, fanouts=FANOUTS, batch_size=BATCH, lr=1e-3,
                           weight_decay=5e-4, dropout=0.5, dtype=dtype, seed=1234, comm=comm,
@@ -241,7 +242,7 @@ def run_ours(args):
     ms_e2e = timed(dev, loop_e2e)
     edges_e2e = sum_over_ranks(float(tr.total_sampled_edges() - e_before), dev)
     loss = tr.last_loss()
-    if comm is not None:
+    if comm is not None and not isinstance(comm, str):
         comm.check_error()
     if rank == 0:
         steps_per_epoch = -(-TRAIN_NODES // (BATCH * world))
@@ -392,6 +393,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--scale", type=float, default=1.0, help="shrink the graph (testing only; 1.0 = named config)")
+    ap.add_argument("--comm", default="p2p", choices=["p2p", "nccl"], help="gradient all-reduce: fused P2P kernel or NCCL baseline")
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay (debug)")
     ap.add_argument("--no-tc", action="store_true", help="use the unfused cuBLAS layer path (A/B debug)")
     args = ap.parse_args()

@@ -134,7 +134,10 @@ def _split_meta(indptr):
 
 def _gspmm_balanced(csr, ufeat2d, ew, num_dst, F, heads=1):
     indptr, indices, eids = csr
-    meta = _split_meta(indptr)
+    from .global_config import is_deterministic
+    # deterministic mode (USE_DETERMINISTIC_ALG=1 / dgl.global_config.set_deterministic): long rows are NOT split into
+    # work items that meet in fp32 red.add scratch, so every output element is reduced by one sub-warp in a fixed order
+    meta = {"n_long": 0} if is_deterministic() else _split_meta(indptr)
     if ew is not None and eids is not None:
         # bring the per-edge scalars into CSC order once (sequential reads in the kernel instead of
         # one random 32-byte sector per edge)
@@ -151,7 +154,7 @@ def _gspmm_balanced(csr, ufeat2d, ew, num_dst, F, heads=1):
         args = (0, 0, 0, 0, 0, 0, 0)
     lib.fn("dglb200_cuda_gspmm_balanced", "iiippplppp" + "ll" + "ppp" + "l" + "p" + "l" + "pp")(
         (max(1, int(heads)) if ew is not None else 0), dtype_code(ufeat2d.dtype), id_code(indptr.dtype), _p(indptr), _p(indices), _p(eids),
-        num_dst, _p(ufeat2d), _p(ew), _p(out), F, SPLIT_DEG, *args, loader.stream_ptr())
+        num_dst, _p(ufeat2d), _p(ew), _p(out), F, SPLIT_DEG if meta["n_long"] else (1 << 40), *args, loader.stream_ptr())
     return out
 
 

@@ -33,3 +33,13 @@ def set_gemm_path(path):
 
 def get_gemm_path():
     return _cfg["gemm_path"]
+
+
+def set_deterministic(flag):
+    """Bit-reproducible sparse reductions (reference env ``USE_DETERMINISTIC_ALG``, src/array/cuda/spmm.cu:33-35):
+    g-SpMM stops splitting long rows across work items (no floating-point atomics in the forward aggregation)."""
+    _cfg["deterministic"] = bool(flag)
+
+
+def is_deterministic():
+    return _cfg["deterministic"]

@@ -123,11 +123,30 @@ class FusedSAGETrainer:
         self.lr, self.wd, self.p_drop = lr, weight_decay, dropout
         self.betas, self.eps = betas, eps
         self.seed = seed
+        # comm = P2PComm            -> gradients averaged by the peer-memory kernel fused with Adam (the product path)
+        # comm = "nccl"             -> BASELINE: torch.distributed all_reduce (NCCL) of the flat gradient, then the same
+        #                              Adam kernel on the local buffer (also selected by DGLB200_COMM=nccl when the
+        #                              process group is initialised and no P2PComm is given)
+        self.nccl_group = None
+        if comm is None:
+            from ..global_config import get_comm_path
+            import torch.distributed as _dist
+            if get_comm_path() == "nccl" and _dist.is_available() and _dist.is_initialized() and _dist.get_world_size() > 1:
+                comm = "nccl"
+        if isinstance(comm, str):
+            if comm != "nccl":
+                raise DGLError("comm must be a P2PComm, 'nccl' or None")
+            import torch.distributed as _dist
+            self.nccl_group = _dist.group.WORLD
+            self._nccl_world, self._nccl_rank = _dist.get_world_size(), _dist.get_rank()
+            comm = None
         self.comm = comm
         if dtype not in (torch.bfloat16, torch.float32):
             raise DGLError("FusedSAGETrainer supports dtype bfloat16 (tensor-core path) or float32")
         self.world = 1 if comm is None else comm.world_size
         self.rank = 0 if comm is None else comm.rank
+        if self.nccl_group is not None:
+            self.rank = self._nccl_rank
         if self.F_in % 2 or hidden % 8:
             raise DGLError("feature sizes must be even (F_in) / multiples of 8 (hidden)")
         # ---- layer dims: layer l (1-based) maps in_dims[l-1] -> out_dims[l-1]
@@ -483,6 +502,12 @@ class FusedSAGETrainer:
             self._my_kernels += 1
             peers = self.comm.peer_grad_ptrs()
         else:
+            if self.nccl_group is not None:
+                # baseline communication path: NCCL all-reduce (capturable), pre-scaled so the kernel's 1/world is a no-op
+                import torch.distributed as _dist
+                self.grad.mul_(1.0 / self._nccl_world)
+                _dist.all_reduce(self.grad, group=self.nccl_group)
+                self._launch_count += 2
             peers = (ctypes.c_void_p * 1)(self.grad.data_ptr())
         self._peers_keepalive = peers
         self._launch("dglb200_engine_allreduce_adam", "ppippplfffffp", _p(self.param), ctypes.cast(peers, ctypes.c_void_p),

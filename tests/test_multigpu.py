@@ -282,7 +282,35 @@ def _w_p2p_cooperative(rank, world, comm):
     return True
 
 
+def _w_trainer_nccl_baseline(rank, world, comm):
+    """comm='nccl' (baseline path) must give the same parameters as the fused P2P path."""
+    import dgl_b200 as dgl
+    from dgl_b200.models import FusedSAGETrainer
+    dev = comm.device
+    gen = torch.Generator().manual_seed(3)
+    n = 8000
+    g = dgl.graph((torch.randint(0, n, (100000,), generator=gen).int(), torch.randint(0, n, (100000,), generator=gen).int()),
+                  num_nodes=n, idtype=torch.int32).to(dev)
+    feat = torch.randn(n, 64, generator=gen).to(dev)
+    labels = torch.randint(0, 7, (n,), generator=gen).to(dev)
+    params = []
+    for c in (comm, "nccl"):
+        tr = FusedSAGETrainer(g, feat, labels, 7, hidden=64, fanouts=[5, 5], batch_size=256, lr=1e-2, dropout=0.0, comm=c,
+                              seed=11, use_cuda_graph=False)
+        for step in range(4):
+            gs = torch.Generator().manual_seed(1000 + step * world + rank)
+            tr.train_step(torch.randint(0, n, (256,), generator=gs))
+        params.append(tr.param.clone())
+    assert torch.allclose(params[0], params[1], atol=2e-3), (params[0] - params[1]).abs().max()
+    return True
+
+
 # ---------------------------------------------------------------------------------------------- tests
+def test_trainer_nccl_baseline_matches_p2p():
+    _run(_w_trainer_nccl_baseline)
+
+
+
 def test_p2p_cooperative_exchange():
     _run(_w_p2p_cooperative)
 
