@@ -233,3 +233,19 @@ def test_fused_gat_on_blocks_and_zero_in_degree():
     yr.sum().backward()
     assert yb.shape == (500, 4, 8) and torch.allclose(yb.detach().cpu(), yr.detach(), atol=1e-4)
     assert torch.allclose(xb.grad.cpu(), xb2.grad, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_deterministic_spmm_mode_is_bit_reproducible():
+    from dgl_b200 import global_config as gc
+    g = dgl.data.rmat_graph(20000, 600000, seed=1).to("cuda")                # power-law: hub rows far above the split degree
+    x = torch.randn(20000, 64, device="cuda")
+    assert int(g.in_degrees().max()) > 128
+    ref = dgl.ops.copy_u_sum(g, x)
+    gc.set_deterministic(True)
+    try:
+        a = dgl.ops.copy_u_sum(g, x)
+        b = dgl.ops.copy_u_sum(g, x)
+    finally:
+        gc.set_deterministic(False)
+    assert torch.equal(a, b) and torch.allclose(a, ref, atol=1e-3, rtol=1e-4)
