@@ -63,6 +63,31 @@ def gat_reddit(dgl, scale, dev, dtype):
     return model, (lambda: model(g, feat)), labels, train, dict(nodes=n, edges=g.num_edges(), feats=f, classes=c, heads=8, hidden=8)
 
 
+def gcn_cora(dgl, scale, dev, dtype):
+    """BASELINE config 1: 2-layer GCN (16 hidden) on a Cora-sized random graph (2,708 nodes / 10,556 edges / 1,433 feats /
+    7 classes) - the CPU plumbing configuration."""
+    n, e, f, c = int(2708 * scale), int(10556 * scale), 1433, 7
+    gen = torch.Generator().manual_seed(0)
+    u = torch.randint(0, n, (e,), generator=gen, dtype=torch.int32)
+    v = torch.randint(0, n, (e,), generator=gen, dtype=torch.int32)
+    g = dgl.add_self_loop(dgl.graph((u, v), num_nodes=n, idtype=torch.int32)).to(dev)
+    feat = (torch.rand(n, f, generator=gen) < 0.0127).float().to(dev).to(dtype)      # Cora's bag-of-words sparsity
+    labels = torch.randint(0, c, (n,), generator=gen).to(dev)
+    train = torch.arange(140).to(dev)
+
+    class GCN(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.l1 = dgl.nn.GraphConv(f, 16, activation=F.relu)
+            self.l2 = dgl.nn.GraphConv(16, c)
+
+        def forward(self, g, x):
+            return self.l2(g, F.dropout(self.l1(g, x), 0.5, self.training))
+
+    model = GCN().to(dev).to(dtype)
+    return model, (lambda: model(g, feat)), labels, train, dict(nodes=n, edges=g.num_edges(), feats=f, classes=c, hidden=16)
+
+
 def rgcn_mag(dgl, scale, dev, dtype):
     gen = torch.Generator().manual_seed(0)
     nn_ = {k: max(8, int(v * scale)) for k, v in MAG_NODES.items()}
@@ -106,7 +131,8 @@ def rgcn_mag(dgl, scale, dev, dtype):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="gat_reddit", choices=["gat_reddit", "rgcn_mag"])
+    ap.add_argument("--config", default="gat_reddit", choices=["gat_reddit", "rgcn_mag", "gcn_cora"])
+    ap.add_argument("--device", default="cuda", choices=["cuda", "cpu"])
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--scale", type=float, default=1.0)
     ap.add_argument("--epochs", type=int, default=10)
@@ -114,10 +140,10 @@ def main():
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
-    dev = torch.device("cuda")
+    dev = torch.device(args.device)
     dgl = load_impl(args.impl)
     dtype = torch.float32 if args.dtype == "fp32" else torch.bfloat16
-    model, fwd, labels, idx, cfg = (gat_reddit if args.config == "gat_reddit" else rgcn_mag)(dgl, args.scale, dev, dtype)
+    model, fwd, labels, idx, cfg = {"gat_reddit": gat_reddit, "rgcn_mag": rgcn_mag, "gcn_cora": gcn_cora}[args.config](dgl, args.scale, dev, dtype)
     opt = torch.optim.Adam(model.parameters(), lr=5e-3)
 
     def step():
@@ -130,16 +156,23 @@ def main():
 
     for _ in range(args.warmup):
         loss = step()
-    torch.cuda.synchronize()
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s.record()
-    for _ in range(args.epochs):
-        loss = step()
-    e.record()
-    torch.cuda.synchronize()
-    ms = s.elapsed_time(e) / args.epochs
+    if dev.type == "cuda":
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(args.epochs):
+            loss = step()
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / args.epochs
+    else:
+        import time
+        t0 = time.perf_counter()
+        for _ in range(args.epochs):
+            loss = step()
+        ms = (time.perf_counter() - t0) * 1e3 / args.epochs
     rec = dict(bench=args.config, impl=args.impl, dtype=args.dtype, scale=args.scale, ms_per_epoch=ms,
-               edges_per_s=cfg["edges"] / ms * 1e3, final_loss=float(loss), peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30,
+               edges_per_s=cfg["edges"] / ms * 1e3, final_loss=float(loss), peak_mem_gb=(torch.cuda.max_memory_allocated() / 2 ** 30) if dev.type == "cuda" else None, device=dev.type,
                config=cfg, epochs=args.epochs, warmup=args.warmup)
     print(json.dumps(rec), flush=True)
     if args.out:
