@@ -76,8 +76,19 @@ class _Lib:
         return hasattr(self.cdll, name)
 
 
-def _need_build(path: Path) -> bool:
-    return not path.exists()
+def _need_build(path: Path, kind: str = "") -> bool:
+    """Missing library, or (cheap mtime test) a source newer than it; the build itself is incremental."""
+    if not path.exists():
+        return True
+    if not kind:
+        return False
+    src = Path(__file__).resolve().parent.parent / "csrc"
+    try:
+        built = path.stat().st_mtime
+        files = list((src / kind).glob("*")) + list(src.glob("*.h"))
+        return any(f.stat().st_mtime > built for f in files)
+    except OSError:
+        return False
 
 
 def cpu_lib() -> _Lib:
@@ -86,8 +97,12 @@ def cpu_lib() -> _Lib:
         with _lock:
             if _cpu is None:
                 p = _LIBDIR / "libdglb200_cpu.so"
-                if _need_build(p) or os.environ.get("DGLB200_REBUILD"):
+                if _need_build(p, "cpu") or os.environ.get("DGLB200_REBUILD"):
                     _build.build_cpu(verbose=bool(os.environ.get("DGLB200_VERBOSE")))
+                    try:
+                        os.utime(p)  # nothing changed (hash-cached): stop the mtime test from firing again
+                    except OSError:
+                        pass
                 _cpu = _Lib(p)
     return _cpu
 

@@ -15,6 +15,7 @@ import torch
 from ..base import DGLError
 from ..graph_index import UnitGraph
 from ..ops import sparse_autograd as SA
+from ..ops import cpu_struct as _cpu_struct
 
 __all__ = ["SparseMatrix", "spmatrix", "from_coo", "from_csr", "from_csc", "diag", "identity", "val_like", "spmm",
            "bspmm", "spspmm", "sddmm", "bsddmm", "softmax", "sum", "smax", "smin", "smean", "sprod", "add", "sub",
@@ -370,7 +371,13 @@ def spspmm(A, B):
     """Sparse @ sparse (SpGEMM via torch.sparse / cuSPARSE); differentiable w.r.t. both value vectors."""
     if A.shape[1] != B.shape[0]:
         raise DGLError(f"shape mismatch for spspmm: {A.shape} @ {B.shape}")
-    ta, tb = to_torch_sparse_coo(A.coalesce() if A.has_duplicate() else A), to_torch_sparse_coo(B.coalesce() if B.has_duplicate() else B)
+    A = A.coalesce() if A.has_duplicate() else A
+    B = B.coalesce() if B.has_duplicate() else B
+    if _cpu_struct.usable(A, B):
+        # host matrices: native two-pass Gustavson SpGEMM with a masked row-dot backward (csrc/cpu/structure.cc)
+        cp, ci, cv = _cpu_struct.spspmm(A, B)
+        return from_csr(cp, ci, cv, (A.shape[0], B.shape[1]))
+    ta, tb = to_torch_sparse_coo(A), to_torch_sparse_coo(B)
     tc = torch.sparse.mm(ta, tb).coalesce()
     idx = tc.indices()
     return from_coo(idx[0].to(A.row.dtype), idx[1].to(A.row.dtype), tc.values(), (A.shape[0], B.shape[1]))
@@ -478,6 +485,10 @@ def sprod(A, dim=None):
 def _binary_sp(A, B, fn):
     if A.shape != B.shape:
         raise DGLError(f"shape mismatch: {A.shape} vs {B.shape}")
+    if _cpu_struct.usable(A, B) and not A.has_duplicate() and not B.has_duplicate():
+        # host matrices: per-row sorted merge in native code instead of concat + unique
+        cp, ci, cv = _cpu_struct.spadd(A, B, beta=float(fn(1.0)))
+        return from_csr(cp, ci, cv, A.shape)
     ra, ca = A.coo()
     rb, cb = B.coo()
     r, c = torch.cat([ra, rb.to(ra.dtype)]), torch.cat([ca, cb.to(ca.dtype)])

@@ -23,6 +23,18 @@ int dglb200_cache_stats(int64_t handle, int64_t* hits, int64_t* queries);
 int dglb200_cpu_ldg_partition(int idtype, const void* indptr, const void* indices, int64_t n, int k, const void* vwgt,
                               int refine_iters, double imbalance, int64_t seed, void* part);
 int dglb200_cpu_libra_partition(int idtype, const void* src, const void* dst, int64_t E, int64_t n, int k, void* edge_part);
+int dglb200_cpu_csr_mm_count(int idtype, int64_t n_rows, const void* ap, const void* ai, const void* bp, const void* bi,
+                             int64_t n_cols, int64_t* row_nnz);
+int dglb200_cpu_csr_mm_fill(int idtype, int dtype, int64_t n_rows, const void* ap, const void* ai, const void* av,
+                            const void* bp, const void* bi, const void* bv, int64_t n_cols, const int64_t* cp, void* ci,
+                            void* cv);
+int dglb200_cpu_csr_sum_count(int idtype, int64_t n_rows, const void* ap, const void* ai, const void* bp, const void* bi,
+                              int64_t* row_nnz);
+int dglb200_cpu_csr_sum_fill(int idtype, int dtype, int64_t n_rows, const void* ap, const void* ai, const void* av,
+                             double alpha, const void* bp, const void* bi, const void* bv, double beta, const int64_t* cp,
+                             void* ci, void* cv, void* src_a, void* src_b);
+int dglb200_cpu_csr_rowdot(int idtype, int dtype, int64_t nnz, const void* rows, const void* cols, const void* xp,
+                           const void* xi, const void* xv, const void* yp, const void* yi, const void* yv, void* out);
 int dglb200_rpc_create(int rank, const char* ip, int port, int64_t* handle, int* bound_port);
 int dglb200_rpc_connect(int64_t handle, int peer, const char* ip, int port, int max_try, int retry_ms);
 int dglb200_rpc_send(int64_t handle, int peer, int tag, const void* data, int64_t n);
@@ -176,8 +188,75 @@ static void test_rpc_loopback() {
   CHECK(dglb200_rpc_destroy(b) == 0);
 }
 
+// csr_mm / csr_sum / masked row-dot against a dense evaluation (reference tests/cpp/test_csrmm.cc)
+static void test_csr_arith() {
+  const int M = 5, K = 4, N = 6;
+  // A (5x4) and B (4x6) with sorted rows; row 3 of A is empty
+  std::vector<int64_t> ap = {0, 2, 3, 5, 5, 7}, ai = {0, 2, 1, 0, 3, 1, 2};
+  std::vector<float> av = {1, 2, 3, 4, 5, 6, 7};
+  std::vector<int64_t> bp = {0, 2, 4, 5, 7}, bi = {1, 4, 0, 4, 5, 2, 3};
+  std::vector<float> bv = {1, -1, 2, 3, 4, 5, 6};
+  auto dense = [](int rows, int cols, const std::vector<int64_t>& p, const std::vector<int64_t>& i,
+                  const std::vector<float>& v) {
+    std::vector<float> d(rows * cols, 0.f);
+    for (int r = 0; r < rows; ++r)
+      for (int64_t e = p[r]; e < p[r + 1]; ++e) d[r * cols + i[e]] += v[e];
+    return d;
+  };
+  std::vector<float> da = dense(M, K, ap, ai, av), db = dense(K, N, bp, bi, bv), dc(M * N, 0.f);
+  for (int r = 0; r < M; ++r)
+    for (int k = 0; k < K; ++k)
+      for (int c = 0; c < N; ++c) dc[r * N + c] += da[r * K + k] * db[k * N + c];
+  std::vector<int64_t> nnz(M), cp(M + 1, 0);
+  CHECK(dglb200_cpu_csr_mm_count(1, M, ap.data(), ai.data(), bp.data(), bi.data(), N, nnz.data()) == 0);
+  for (int r = 0; r < M; ++r) cp[r + 1] = cp[r] + nnz[r];
+  CHECK(nnz[3] == 0);
+  std::vector<int64_t> ci(cp[M]);
+  std::vector<float> cv(cp[M]);
+  CHECK(dglb200_cpu_csr_mm_fill(1, 0, M, ap.data(), ai.data(), av.data(), bp.data(), bi.data(), bv.data(), N, cp.data(),
+                                ci.data(), cv.data()) == 0);
+  std::vector<float> got = dense(M, N, cp, ci, cv);
+  for (int i = 0; i < M * N; ++i) CHECK(std::fabs(got[i] - dc[i]) < 1e-5);
+  for (int r = 0; r < M; ++r)
+    for (int64_t e = cp[r] + 1; e < cp[r + 1]; ++e) CHECK(ci[e - 1] < ci[e]);  // sorted, unique
+  // structural product (null values = all ones) counts paths
+  CHECK(dglb200_cpu_csr_mm_fill(1, 0, M, ap.data(), ai.data(), nullptr, bp.data(), bi.data(), nullptr, N, cp.data(),
+                                ci.data(), cv.data()) == 0);
+  for (int64_t e = 0; e < cp[M]; ++e) CHECK(cv[e] >= 1.f && cv[e] == std::floor(cv[e]));
+
+  // C2 = 2*A - A' where A' shares the shape of A
+  std::vector<int64_t> a2p = {0, 1, 3, 3, 4, 6}, a2i = {2, 0, 1, 3, 0, 2};
+  std::vector<float> a2v = {10, 20, 30, 40, 50, 60};
+  std::vector<int64_t> sn(M), sp(M + 1, 0);
+  CHECK(dglb200_cpu_csr_sum_count(1, M, ap.data(), ai.data(), a2p.data(), a2i.data(), sn.data()) == 0);
+  for (int r = 0; r < M; ++r) sp[r + 1] = sp[r] + sn[r];
+  std::vector<int64_t> si(sp[M]), sa(sp[M]), sb(sp[M]);
+  std::vector<float> sv(sp[M]);
+  CHECK(dglb200_cpu_csr_sum_fill(1, 0, M, ap.data(), ai.data(), av.data(), 2.0, a2p.data(), a2i.data(), a2v.data(), -1.0,
+                                 sp.data(), si.data(), sv.data(), sa.data(), sb.data()) == 0);
+  std::vector<float> ds = dense(M, K, sp, si, sv), d2 = dense(M, K, a2p, a2i, a2v);
+  for (int i = 0; i < M * K; ++i) CHECK(std::fabs(ds[i] - (2 * da[i] - d2[i])) < 1e-5);
+  for (int64_t e = 0; e < sp[M]; ++e) {
+    CHECK(sa[e] >= 0 || sb[e] >= 0);
+    if (sa[e] >= 0) CHECK(ai[sa[e]] == si[e]);
+    if (sb[e] >= 0) CHECK(a2i[sb[e]] == si[e]);
+  }
+
+  // row-dot: <A[r,:], A'[c,:]> for a few (r, c) pairs
+  std::vector<int64_t> rows = {0, 1, 4, 3, 2}, cols = {0, 1, 4, 2, 4};
+  std::vector<float> out(rows.size());
+  CHECK(dglb200_cpu_csr_rowdot(1, 0, (int64_t)rows.size(), rows.data(), cols.data(), ap.data(), ai.data(), av.data(),
+                               a2p.data(), a2i.data(), a2v.data(), out.data()) == 0);
+  for (size_t t = 0; t < rows.size(); ++t) {
+    float ref = 0;
+    for (int k = 0; k < K; ++k) ref += da[rows[t] * K + k] * d2[cols[t] * K + k];
+    CHECK(std::fabs(out[t] - ref) < 1e-4);
+  }
+}
+
 int main() {
   test_spmm();
+  test_csr_arith();
   for (int policy = 0; policy < 4; ++policy) test_cache(policy);  // S3-FIFO, SIEVE, LRU, CLOCK
   test_partitioners();
   test_rpc_loopback();
