@@ -4,7 +4,8 @@ from __future__ import annotations
 
 import torch
 
-from .base import DGLError
+from ._native import loader
+from .base import DGLError, id_code
 from .heterograph import _to_tensor
 
 __all__ = ["bfs_nodes_generator", "bfs_edges_generator", "topological_nodes_generator", "dfs_edges_generator",
@@ -16,8 +17,29 @@ def _csr(g, reverse):
     return ug.csc() if reverse else ug.csr()
 
 
+def _split(ids, sections):
+    return list(torch.split(ids, sections.tolist())) if sections.numel() else []
+
+
+def _native_bfs(graph, source, reverse, want_edges):
+    """Host graphs: one native pass (csrc/cpu/traversal.cc); frontiers are in discovery order like the reference."""
+    indptr, indices, eids = _csr(graph, reverse)
+    n = graph.num_nodes()
+    src = _to_tensor(source, graph.idtype, graph.device).contiguous()
+    out = torch.empty(n, dtype=graph.idtype)
+    sections = torch.empty(n + 1, dtype=torch.int64)
+    counts = torch.zeros(2, dtype=torch.int64)
+    loader.cpu_lib().fn("dglb200_cpu_bfs", "ippplplipppp")(
+        id_code(graph.idtype), indptr.data_ptr(), indices.data_ptr(), 0 if eids is None else eids.data_ptr(), n,
+        src.data_ptr(), src.shape[0], int(want_edges), out.data_ptr(), sections.data_ptr(), counts.data_ptr(),
+        counts[1:].data_ptr())
+    return _split(out[:int(counts[1])], sections[:int(counts[0])])
+
+
 def bfs_nodes_generator(graph, source, reverse=False):
-    """Frontiers of a BFS from ``source`` (vectorised level-synchronous expansion)."""
+    """Frontiers of a BFS from ``source`` (native on the host, vectorised level-synchronous expansion on the GPU)."""
+    if graph.device.type == "cpu":
+        return _native_bfs(graph, source, reverse, False)
     indptr, indices, _ = _csr(graph, reverse)
     n = graph.num_nodes()
     frontier = _to_tensor(source, graph.idtype, graph.device)
@@ -40,6 +62,8 @@ def bfs_nodes_generator(graph, source, reverse=False):
 
 def bfs_edges_generator(graph, source, reverse=False):
     """Edge frontiers of a BFS tree (one tree edge per newly discovered node)."""
+    if graph.device.type == "cpu":
+        return _native_bfs(graph, source, reverse, True)
     indptr, indices, eids = _csr(graph, reverse)
     n = graph.num_nodes()
     frontier = _to_tensor(source, graph.idtype, graph.device)
@@ -69,6 +93,16 @@ def topological_nodes_generator(graph, reverse=False):
     """Kahn levels of a DAG."""
     indptr, indices, _ = _csr(graph, reverse)
     n = graph.num_nodes()
+    if graph.device.type == "cpu":
+        out = torch.empty(n, dtype=graph.idtype)
+        sections = torch.empty(n + 1, dtype=torch.int64)
+        counts = torch.zeros(2, dtype=torch.int64)
+        loader.cpu_lib().fn("dglb200_cpu_topological", "ipplpppp")(
+            id_code(graph.idtype), indptr.data_ptr(), indices.data_ptr(), n, out.data_ptr(), sections.data_ptr(),
+            counts.data_ptr(), counts[1:].data_ptr())
+        if int(counts[1]) != n:
+            raise DGLError("The graph has cycles; topological traversal requires a DAG.")
+        return _split(out, sections[:int(counts[0])])
     deg = (graph.out_degrees() if reverse else graph.in_degrees()).clone().long()
     frontier = torch.nonzero(deg == 0).squeeze(1).to(graph.idtype)
     out, visited = [], 0
@@ -88,48 +122,45 @@ def topological_nodes_generator(graph, reverse=False):
 
 
 def _dfs(graph, source, reverse, has_reverse_edge, has_nontree_edge):
-    FORWARD, REVERSE, NONTREE = 0, 1, 2
-    indptr, indices, eids = [t.cpu() if t is not None else None for t in _csr(graph, reverse)]
-    ip, ix = indptr.tolist(), indices.tolist()
-    ei = eids.tolist() if eids is not None else list(range(len(ix)))
-    src_list = _to_tensor(source, graph.idtype, torch.device("cpu")).tolist()
+    """Per-source labelled edge streams (FORWARD=0, REVERSE=1, NONTREE=2), native (csrc/cpu/traversal.cc)."""
+    indptr, indices, eids = [t.cpu().contiguous() if t is not None else None for t in _csr(graph, reverse)]
+    n = graph.num_nodes()
+    cap = int(indices.shape[0]) + 2 * n + 1
+    fn = loader.cpu_lib().fn("dglb200_cpu_dfs", "ippplliipplp")
     all_edges, all_labels = [], []
-    for src in src_list:
-        visited = {src}
-        stack = [(src, ip[src])]
-        edges, labels = [], []
-        while stack:
-            u, p = stack[-1]
-            if p < ip[u + 1]:
-                stack[-1] = (u, p + 1)
-                v = ix[p]
-                if v not in visited:
-                    visited.add(v)
-                    edges.append(ei[p]); labels.append(FORWARD)
-                    stack.append((v, ip[v]))
-                elif has_nontree_edge:
-                    edges.append(ei[p]); labels.append(NONTREE)
-            else:
-                stack.pop()
-                if has_reverse_edge and stack:
-                    pu, pp = stack[-1]
-                    edges.append(ei[pp - 1]); labels.append(REVERSE)
-        all_edges.append(edges)
-        all_labels.append(labels)
+    for src in _to_tensor(source, graph.idtype, torch.device("cpu")).tolist():
+        edges = torch.empty(cap, dtype=indptr.dtype)
+        labels = torch.empty(cap, dtype=torch.int64)
+        count = torch.zeros(1, dtype=torch.int64)
+        fn(id_code(indptr.dtype), indptr.data_ptr(), indices.data_ptr(), 0 if eids is None else eids.data_ptr(), n,
+           int(src), int(has_reverse_edge), int(has_nontree_edge), edges.data_ptr(), labels.data_ptr(), cap,
+           count.data_ptr())
+        k = int(count)
+        all_edges.append(edges[:k].to(graph.idtype))
+        all_labels.append(labels[:k])
     return all_edges, all_labels
+
+
+def _merge_traversals(streams):
+    """Frontier i holds the i-th element of every stream that is long enough (reference
+    src/graph/traversal.cc MergeMultipleTraversals / ComputeMergedSections)."""
+    if not streams:
+        return []
+    if len(streams) == 1:
+        return list(streams[0].split(1))
+    longest = max(int(t.shape[0]) for t in streams)
+    return [torch.stack([t[i] for t in streams if t.shape[0] > i]) for i in range(longest)]
 
 
 def dfs_edges_generator(graph, source, reverse=False):
     edges, _ = _dfs(graph, source, reverse, False, False)
-    flat = [e for es in edges for e in es]
-    return [torch.tensor([e], dtype=graph.idtype) for e in flat]
+    return _merge_traversals(edges)
 
 
 def dfs_labeled_edges_generator(graph, source, reverse=False, has_reverse_edge=False, has_nontree_edge=False,
                                 return_labels=True):
     edges, labels = _dfs(graph, source, reverse, has_reverse_edge, has_nontree_edge)
-    fe = [torch.tensor([e], dtype=graph.idtype) for es in edges for e in es]
-    fl = [torch.tensor([l], dtype=torch.int64) for ls in labels for l in ls]
+    fe = _merge_traversals(edges)
     if return_labels:
-        return fe, fl
+        return fe, _merge_traversals(labels)
     return fe
