@@ -18,6 +18,16 @@ def farthest_point_sampler(pos, npoints, start_idx=None):
         start = (torch.randint(0, N, (B,), device=dev) if start_idx is None
                  else torch.full((B,), int(start_idx), device=dev, dtype=torch.long))
         return fps(pos, int(npoints), start)   # one CTA per cloud, whole loop in one launch
+    if dev.type == "cpu" and pos.dtype in (torch.float32, torch.float64):
+        # host clouds: native loop, threads over clouds (or over points of a single large cloud) — csrc/cpu/spatial.cc
+        from ._native import loader
+        from .base import dtype_code
+        start = (torch.randint(0, N, (B,)) if start_idx is None else torch.full((B,), int(start_idx), dtype=torch.long))
+        out = torch.empty((B, npoints), dtype=torch.long)
+        p = pos.contiguous()
+        loader.cpu_lib().fn("dglb200_cpu_fps", "ipllllpp")(dtype_code(p.dtype), p.data_ptr(), B, N, C, int(npoints),
+                                                           start.data_ptr(), out.data_ptr())
+        return out
     dist = torch.full((B, N), float("inf"), device=dev, dtype=pos.dtype)
     if start_idx is None:
         cur = torch.randint(0, N, (B,), device=dev)
@@ -50,28 +60,20 @@ def neighbor_matching(graph, e_weights=None, relabel_idx=True):
         if relabel_idx:
             res = torch.unique(res, return_inverse=True)[1].to(graph.idtype)
         return res
-    u, v = graph.edges()
-    u, v = u.cpu().tolist(), v.cpu().tolist()
-    w = e_weights.cpu().tolist() if e_weights is not None else None
-    adj = [[] for _ in range(n)]
-    for i, (a, b) in enumerate(zip(u, v)):
-        if a != b:
-            adj[a].append((b, w[i] if w else 1.0))
-            adj[b].append((a, w[i] if w else 1.0))
-    match = [-1] * n
-    order = torch.randperm(n).tolist()
-    for a in order:
-        if match[a] >= 0:
-            continue
-        best, bw = -1, -1.0
-        for b, ww in adj[a]:
-            if match[b] < 0 and b != a and ww > bw:
-                best, bw = b, ww
-        if best >= 0:
-            match[a] = match[best] = min(a, best)
-        else:
-            match[a] = a
-    res = torch.tensor(match, dtype=graph.idtype, device=graph.device)
+    # host graphs: one native greedy sweep over a random node order (csrc/cpu/spatial.cc)
+    from ._native import loader
+    from .base import id_code
+    from .graph_index import coo_to_csr
+    from .transforms.functional import to_bidirected_coo
+    su, sv, sw = to_bidirected_coo(graph, e_weights)
+    indptr, indices, eids = coo_to_csr(su, sv, n, graph.idtype)
+    if sw is not None:
+        sw = (sw if eids is None else sw[eids.long()]).float().contiguous()
+    order = torch.randperm(n)
+    res = torch.full((n,), -1, dtype=graph.idtype)
+    loader.cpu_lib().fn("dglb200_cpu_neighbor_matching", "ippplpp")(
+        id_code(graph.idtype), indptr.data_ptr(), indices.data_ptr(), 0 if sw is None else sw.data_ptr(), n,
+        order.data_ptr(), res.data_ptr())
     if relabel_idx:
         _, res = torch.unique(res, return_inverse=True)
         res = res.to(graph.idtype)

@@ -560,6 +560,23 @@ def to_bidirected_coo(g, e_weights=None):
     return torch.cat([u, v]).contiguous(), torch.cat([v, u]).contiguous(), w
 
 
+def kdtree_knn(x, y, k, x_offsets=None, y_offsets=None, return_distance=False):
+    """k nearest rows of ``x`` for every row of ``y`` with a native kd-tree (host tensors, float32/64). With offsets the
+    search is segmented: queries of segment s only see data points of segment s. Returns (idx [len(y), k], dist|None);
+    rows with fewer than k candidates are padded with -1 (reference src/graph/transform/cpu/knn.cc KdTreeKNN)."""
+    from .._native import loader
+    from ..base import dtype_code
+    x, y = x.contiguous(), y.contiguous()
+    xo = torch.tensor([0, x.shape[0]], dtype=torch.int64) if x_offsets is None else torch.as_tensor(x_offsets).long().contiguous()
+    yo = torch.tensor([0, y.shape[0]], dtype=torch.int64) if y_offsets is None else torch.as_tensor(y_offsets).long().contiguous()
+    idx = torch.empty((y.shape[0], k), dtype=torch.int64)
+    dist = torch.empty((y.shape[0], k), dtype=x.dtype) if return_distance else None
+    loader.cpu_lib().fn("dglb200_cpu_knn_kdtree", "ipppplllpp")(
+        dtype_code(x.dtype), x.data_ptr(), xo.data_ptr(), y.data_ptr(), yo.data_ptr(), xo.shape[0] - 1, x.shape[1], int(k),
+        idx.data_ptr(), 0 if dist is None else dist.data_ptr())
+    return idx, dist
+
+
 def _pairwise_topk(x, y, k, exclude_self_offset=None, dist="euclidean", chunk=4096):
     """for each row of y find k nearest rows of x. returns idx [len(y), k]"""
     if x.is_cuda and x.shape[1] <= 16 and k <= 64 and dist == "euclidean" and x.dtype == y.dtype \
@@ -569,10 +586,14 @@ def _pairwise_topk(x, y, k, exclude_self_offset=None, dist="euclidean", chunk=40
         doff = torch.tensor([0, x.shape[0]], dtype=torch.int64, device=x.device)
         qoff = torch.tensor([0, y.shape[0]], dtype=torch.int64, device=x.device)
         return knn_brute(x, doff, y, qoff, k)
-    outs = []
     if dist == "cosine":
         x = torch.nn.functional.normalize(x, dim=-1)
         y = torch.nn.functional.normalize(y, dim=-1)
+    if x.device.type == "cpu" and x.shape[1] <= 16 and x.dtype == y.dtype and x.dtype in (torch.float32, torch.float64) \
+            and x.shape[0] > 256:
+        # host point clouds: kd-tree (csrc/cpu/spatial.cc); on unit vectors Euclidean order == cosine order
+        return kdtree_knn(x, y, k)[0]
+    outs = []
     for s in range(0, y.shape[0], chunk):
         yc = y[s:s + chunk]
         if dist == "cosine":
@@ -614,6 +635,23 @@ def knn_graph(x, k, algorithm="bruteforce-blas", dist="euclidean", exclude_self=
 
 
 def segmented_knn_graph(x, k, segs, algorithm="bruteforce-blas", dist="euclidean", exclude_self=False):
+    segs = [int(n) for n in segs]
+    kk = k + 1 if exclude_self else k
+    if x.device.type == "cpu" and x.shape[1] <= 16 and x.dtype in (torch.float32, torch.float64) and segs \
+            and min(segs) >= kk:
+        # one native call: a kd-tree per segment, queries confined to their own segment
+        pts = torch.nn.functional.normalize(x, dim=-1) if dist == "cosine" else x
+        offs = torch.tensor([0] + segs).cumsum(0)
+        idx, _ = kdtree_knn(pts, pts, kk, offs, offs)
+        n = x.shape[0]
+        dst = torch.arange(n).view(-1, 1).expand_as(idx)
+        if exclude_self:
+            keep = torch.ones_like(idx, dtype=torch.bool)
+            is_self = idx == dst
+            keep[is_self] = False
+            keep[~is_self.any(1), -1] = False
+            return make_graph((idx[keep], dst[keep]), num_nodes=n)
+        return make_graph((idx.reshape(-1), dst.reshape(-1)), num_nodes=n)
     off = 0
     srcs, dsts = [], []
     for n in segs:
