@@ -101,6 +101,84 @@ class Column:
     def clone(self):
         return Column(self.storage, self.index, self.device)
 
+    # ---- reference Column surface (python/dgl/frame.py:306-560) --------------------------------
+    def astype(self, new_dtype):
+        """Column of another dtype; the lazy index / device move are kept lazy."""
+        if new_dtype == self.dtype:
+            return self
+        return Column(self.storage.to(new_dtype), self.index, self.device)
+
+    def __getitem__(self, rowids):
+        return self.data[rowids.long() if torch.is_tensor(rowids) and rowids.dtype != torch.bool else rowids]
+
+    def __setitem__(self, rowids, feats):
+        self.update(rowids, feats)
+
+    def update(self, rowids, feats):
+        """Write rows; the column is materialised and copied first so views sharing the storage are unaffected."""
+        data = self.data.clone()
+        data[rowids.long() if torch.is_tensor(rowids) else rowids] = feats.to(data.dtype).to(data.device)
+        self.storage = data
+
+    def extend(self, feats, feat_scheme=None):
+        """Append rows."""
+        feats = torch.as_tensor(feats)
+        if tuple(feats.shape[1:]) != tuple(self.storage.shape[1:]):
+            raise DGLError(f"Cannot append rows of shape {tuple(feats.shape[1:])} to a column of shape "
+                           f"{tuple(self.storage.shape[1:])}.")
+        data = self.data
+        self.storage = torch.cat([data, feats.to(data.dtype).to(data.device)], 0)
+
+    def deepclone(self):
+        return Column(self.data.clone())
+
+    @staticmethod
+    def create(data):
+        """Wrap a tensor (or pass a Column through)."""
+        return data.clone() if isinstance(data, Column) else Column(torch.as_tensor(data))
+
+    def fetch(self, indices, device, pin_memory=False, **kwargs):
+        """Rows ``indices`` on ``device`` (the FeatureStorage protocol the dataloader uses); pinned host storage with a
+        CUDA target goes through the UVA gather."""
+        sub = self.subcolumn(torch.as_tensor(indices))
+        out = sub.data
+        if pin_memory and not out.is_cuda and not out.is_pinned():
+            out = out.pin_memory()
+        return out.to(device, **kwargs)
+
+    def pin_memory_(self):
+        """Page-lock the materialised storage in place (remembered so :meth:`unpin_memory_` only undoes our own pin)."""
+        from .utils.pin_memory import pin_memory_inplace
+        data = self.data
+        if not data.is_cuda and not data.is_pinned():
+            pin_memory_inplace(data)
+            self._pinned = True
+
+    def unpin_memory_(self):
+        from .utils.pin_memory import unpin_memory_inplace
+        if self._pinned and self.index is None and self.device is None:
+            unpin_memory_inplace(self.storage)
+            self._pinned = False
+
+    def record_stream(self, stream):
+        if torch.is_tensor(self.storage) and self.storage.is_cuda:
+            self.storage.record_stream(stream)
+        if self.index is not None and self.index.is_cuda:
+            self.index.record_stream(stream)
+
+    def __repr__(self):
+        return repr(self.data)
+
+    def __getstate__(self):
+        # materialise: a pickled column never drags the full parent storage along
+        return self.data
+
+    def __setstate__(self, state):
+        self.storage, self.index, self.device, self._pinned = state, None, None, False
+
+    def __copy__(self):
+        return self.clone()
+
 
 class Frame(MutableMapping):
     """name -> Column with a common row count."""

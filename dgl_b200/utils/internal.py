@@ -5,8 +5,8 @@ import torch
 
 from ..base import DGLError
 
-__all__ = ["expand_as_pair", "check_eq_shape", "toindex", "prepare_tensor", "prepare_tensor_dict", "recursive_apply",
-           "context_of", "dtype_of", "Index", "extract_node_subframes", "extract_edge_subframes", "set_new_frames"]
+__all__ = ["expand_as_pair", "check_eq_shape", "prepare_tensor", "prepare_tensor_dict", "recursive_apply",
+           "context_of", "dtype_of", "extract_node_subframes", "extract_edge_subframes", "set_new_frames"]
 
 
 def expand_as_pair(input_, g=None):
@@ -40,13 +40,6 @@ def prepare_tensor(g, data, name):
 
 def prepare_tensor_dict(g, data, name):
     return {k: prepare_tensor(g, v, f"{name}[{k}]") for k, v in data.items()}
-
-
-def toindex(data, dtype=torch.int64):
-    return torch.as_tensor(data, dtype=dtype)
-
-
-Index = toindex
 
 
 def recursive_apply(data, fn, *args, **kwargs):

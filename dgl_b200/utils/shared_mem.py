@@ -100,3 +100,13 @@ def graph_from_shared_memory(name):
     nn = {nt: n for nt, n in zip(meta["ntypes"], meta["num_nodes"])}
     graphs = [UnitGraph.from_coo(nn[c[0]], nn[c[2]], t[f"row{i}"], t[f"col{i}"]) for i, c in enumerate(cet)]
     return DGLGraph(graphs, meta["ntypes"], cet, meta["num_nodes"])
+
+
+def create_shared_mem_array(name, shape, dtype):
+    """Reference spelling (python/dgl/ndarray.py:create_shared_mem_array) of :func:`create_shared_tensor`."""
+    return create_shared_tensor(name, tuple(shape), dtype)
+
+
+def get_shared_mem_array(name, shape, dtype):
+    """Reference spelling (python/dgl/ndarray.py:get_shared_mem_array) of :func:`open_shared_tensor`."""
+    return open_shared_tensor(name, tuple(shape), dtype)
