@@ -27,7 +27,9 @@ from .logging import enable_verbose_logging  # noqa: F401,E402
 
 _LAZY = {"sampling", "dataloading", "graphbolt", "sparse", "distributed", "optim", "data", "parallel", "models",
          "utils", "multiprocessing", "cuda", "geometry", "partition", "traversal", "propagate", "storages",
-         "distgnn", "mpops", "generators", "merge", "homophily", "label_informativeness", "logging", "global_config"}
+         "distgnn", "mpops", "generators", "merge", "homophily", "label_informativeness", "logging", "global_config",
+         "init", "random", "frame", "view", "core", "convert", "batch", "subgraph", "readout", "contrib", "graph_index",
+         "heterograph_index", "heterograph", "base", "transforms"}
 
 
 def __getattr__(name):

@@ -9,7 +9,7 @@ import warnings
 
 import torch
 
-__all__ = ["ALL", "NID", "EID", "NTYPE", "ETYPE", "DGLError", "dgl_warning", "is_all"]
+__all__ = ["ALL", "NID", "EID", "NTYPE", "ETYPE", "DGLError", "DGLWarning", "dgl_warning", "dgl_warning_format", "is_all"]
 
 
 class DGLError(Exception):
@@ -44,8 +44,21 @@ class DGLWarning(UserWarning):
     pass
 
 
+_default_formatwarning = warnings.formatwarning
+
+
+def dgl_warning_format(message, category, filename, lineno, line=None):
+    """``warnings.formatwarning`` replacement: DGL warnings print as one short line, everything else as usual."""
+    if isinstance(category, type) and issubclass(category, DGLWarning):
+        return f"DGL Warning: {message}\n"
+    return _default_formatwarning(message, category, filename, lineno, line)
+
+
 def dgl_warning(message, category=DGLWarning, stacklevel=2):
     warnings.warn(message, category=category, stacklevel=stacklevel)
+
+
+warnings.formatwarning = dgl_warning_format
 
 
 _DTYPE_CODE = {torch.float32: 0, torch.float64: 1, torch.float16: 2, torch.bfloat16: 3}

@@ -144,6 +144,17 @@ def graph(data, *, num_nodes=None, idtype=None, device=None, row_sorted=False, c
     return DGLGraph([ug], ["_N"], [("_N", "_E", "_N")], [ug.num_src])
 
 
+def create_from_edges(sparse_fmt, arrays, utype, etype, vtype, urange, vrange, row_sorted=False, col_sorted=False):
+    """One-relation graph from typed incident arrays (reference convert.py:1990). ``utype == vtype`` gives a
+    homogeneous-style relation over one node set, otherwise a bipartite one. ``row_sorted`` / ``col_sorted`` are
+    accepted for parity: sortedness is detected when a compressed format is first built (graph_index.coo_to_csr)."""
+    same = utype == vtype
+    ug = _make_unit((sparse_fmt, tuple(arrays)), urange, vrange, None, None, same)
+    if same:
+        return DGLGraph([ug], [utype], [(utype, etype, vtype)], [ug.num_src])
+    return DGLGraph([ug], [utype, vtype], [(utype, etype, vtype)], [ug.num_src, ug.num_dst])
+
+
 def heterograph(data_dict, num_nodes_dict=None, idtype=None, device=None):
     """Create a heterogeneous graph from {(stype, etype, dtype): data} (reference convert.py:207)."""
     if not data_dict:

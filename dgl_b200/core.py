@@ -86,6 +86,40 @@ class NodeBatch:
         return self._ntype
 
 
+def data_dict_to_list(graph, data_dict, func, target):
+    """Per-type list of the operand a builtin message function reads (reference core.py:207).
+
+    ``target`` is 'u', 'v' or 'e'. For node targets the list is indexed by node-type id, for edges by edge-type id;
+    types that do not take part stay ``None``. With a single source type ``data_dict`` may be a bare tensor."""
+    if isinstance(func, fn.BinaryMessageFunction):
+        if target in ("u", "v"):
+            out = [None] * len(graph.ntypes)
+            if not isinstance(data_dict, dict):
+                s, _, d = graph.canonical_etypes[0]
+                out[graph.get_ntype_id(s if target == "u" else d)] = data_dict
+            else:
+                for s, _, d in graph.canonical_etypes:
+                    t = s if target == "u" else d
+                    out[graph.get_ntype_id(t)] = data_dict[t]
+            return out
+        out = [None] * len(graph.canonical_etypes)
+        for rel in graph.canonical_etypes:
+            out[graph.get_etype_id(rel)] = data_dict[rel]
+        return out
+    if target == "u":  # copy_u
+        out = [None] * len(graph.ntypes)
+        if not isinstance(data_dict, dict):
+            out[graph.get_ntype_id(graph.canonical_etypes[0][0])] = data_dict
+        else:
+            for s, _, _ in graph.canonical_etypes:
+                out[graph.get_ntype_id(s)] = data_dict[s]
+        return out
+    out = [None] * len(graph.canonical_etypes)  # copy_e
+    for rel in graph.canonical_etypes:
+        out[graph.get_etype_id(rel)] = data_dict[rel]
+    return out
+
+
 def is_builtin(func):
     return isinstance(func, fn.BuiltinFunction)
 

@@ -346,3 +346,349 @@ def _unpin_inplace(t):
         return
     if torch.cuda.is_available():
         torch.cuda.cudart().cudaHostUnregister(t.data_ptr())
+
+
+# ======================================================================================================
+# Legacy homogeneous index (reference python/dgl/graph_index.py: GraphIndex / SubgraphIndex and creators).
+# The pre-0.5 API addressed one homogeneous graph through a ``GraphIndex`` handle. Here it is the same
+# adapter as ``heterograph_index.HeteroGraphIndex`` pinned to the single relation, with the legacy
+# singular method names (``has_node``, ``edge_id``, ``in_degree`` ...) and in-place mutation.
+# ======================================================================================================
+class BoolFlag:
+    """Tri-state flag of the legacy C API."""
+    BOOL_UNKNOWN = -1
+    BOOL_FALSE = 0
+    BOOL_TRUE = 1
+
+
+class GraphIndex:
+    """Structure-only handle on a homogeneous graph. Mutable unless created ``readonly``."""
+
+    def __init__(self, graph=None, readonly=False):
+        if graph is None:
+            from .convert import graph as make_graph
+            graph = make_graph(([], []))
+        self._g = graph
+        self._readonly = bool(readonly)
+
+    # pickling keeps only structure
+    def __getstate__(self):
+        u, v = self._g.edges()
+        return self._g.num_nodes(), self._readonly, u, v
+
+    def __setstate__(self, state):
+        from .convert import graph as make_graph
+        n, self._readonly, u, v = state
+        self._g = make_graph((u, v), num_nodes=n)
+
+    @property
+    def graph(self):
+        return self._g
+
+    # ---- mutation ------------------------------------------------------------------------------------
+    def _writable(self):
+        if self._readonly:
+            raise DGLError("The graph index is read-only; create it with readonly=False to mutate it.")
+
+    def add_nodes(self, num):
+        self._writable()
+        self._g.add_nodes(int(num))
+
+    def add_edge(self, u, v):
+        self.add_edges([u], [v])
+
+    def add_edges(self, u, v):
+        self._writable()
+        u, v = torch.as_tensor(u).reshape(-1), torch.as_tensor(v).reshape(-1)
+        if u.numel() == 1 and v.numel() > 1:
+            u = u.expand_as(v)
+        if v.numel() == 1 and u.numel() > 1:
+            v = v.expand_as(u)
+        self._g.add_edges(u, v)
+
+    def clear(self):
+        self._writable()
+        self.__init__(None, False)
+
+    def clear_cache(self):
+        """Cached compressed formats are dropped and rebuilt on demand."""
+        ug = self._g._graphs[0]
+        u, v = ug.coo()
+        self._g._graphs[0] = UnitGraph.from_coo(ug.num_src, ug.num_dst, u, v)
+
+    def readonly(self, readonly_state=True):
+        self._readonly = bool(readonly_state)
+        return self
+
+    def is_readonly(self):
+        return self._readonly
+
+    def is_multigraph(self):
+        return bool(self._g.is_multigraph)
+
+    # ---- queries --------------------------------------------------------------------------------------
+    def num_nodes(self):
+        return self._g.num_nodes()
+
+    number_of_nodes = num_nodes
+
+    def num_edges(self):
+        return self._g.num_edges()
+
+    number_of_edges = num_edges
+
+    def has_node(self, vid):
+        return 0 <= int(vid) < self._g.num_nodes()
+
+    def has_nodes(self, vids):
+        return self._g.has_nodes(torch.as_tensor(vids)).long()
+
+    def has_edge_between(self, u, v):
+        return bool(self._g.has_edges_between(torch.tensor([u]), torch.tensor([v]))[0])
+
+    def has_edges_between(self, u, v):
+        return self._g.has_edges_between(torch.as_tensor(u), torch.as_tensor(v)).long()
+
+    def predecessors(self, v, radius=1):
+        if radius != 1:
+            raise DGLError("only radius 1 is supported")
+        return self._g.predecessors(int(v))
+
+    def successors(self, v, radius=1):
+        if radius != 1:
+            raise DGLError("only radius 1 is supported")
+        return self._g.successors(int(v))
+
+    def edge_id(self, u, v):
+        """Ids of every edge u -> v."""
+        _, _, e = self._g.edge_ids(torch.tensor([u]), torch.tensor([v]), return_uv=True)
+        return e
+
+    def edge_ids(self, u, v):
+        return self._g.edge_ids(torch.as_tensor(u), torch.as_tensor(v), return_uv=True)
+
+    def find_edge(self, eid):
+        u, v = self._g.find_edges(torch.tensor([eid]))
+        return int(u[0]), int(v[0])
+
+    def find_edges(self, eid):
+        eid = torch.as_tensor(eid)
+        u, v = self._g.find_edges(eid)
+        return u, v, eid
+
+    def in_edges(self, v):
+        return self._g.in_edges(torch.as_tensor(v).reshape(-1), form="all")
+
+    def out_edges(self, v):
+        return self._g.out_edges(torch.as_tensor(v).reshape(-1), form="all")
+
+    def edges(self, order=None):
+        return self._g.edges(form="all", order=order or "eid")
+
+    def sort_csr(self):
+        """Column-sort the rows of the cached CSR (a no-op contract here: queries never depend on in-row order)."""
+        self._g._graphs[0].csr()
+
+    def in_degree(self, v):
+        return int(self._g.in_degrees(int(v)))
+
+    def in_degrees(self, v):
+        return self._g.in_degrees(torch.as_tensor(v))
+
+    def out_degree(self, v):
+        return int(self._g.out_degrees(int(v)))
+
+    def out_degrees(self, v):
+        return self._g.out_degrees(torch.as_tensor(v))
+
+    # ---- subgraphs ---------------------------------------------------------------------------------------
+    def node_subgraph(self, v):
+        from .base import EID
+        v = torch.as_tensor(v)
+        sg = self._g.subgraph(v, store_ids=True)
+        return SubgraphIndex(GraphIndex(sg, True), self, v, sg.edata[EID])
+
+    def node_subgraphs(self, vs_arr):
+        return [self.node_subgraph(v) for v in vs_arr]
+
+    def node_halo_subgraph(self, v, num_hops):
+        """Subgraph induced by ``v`` plus everything within ``num_hops`` in-hops (the halo)."""
+        from .base import EID, NID
+        v = torch.as_tensor(v)
+        frontier, nodes = v, v
+        for _ in range(int(num_hops)):
+            frontier = torch.unique(self._g.in_edges(frontier)[0])
+            nodes = torch.unique(torch.cat([nodes, frontier]))
+        rest = nodes[~torch.isin(nodes, v)]
+        order = torch.cat([v, rest])
+        sg = self._g.subgraph(order, store_ids=True)
+        return SubgraphIndex(GraphIndex(sg, True), self, sg.ndata[NID], sg.edata[EID])
+
+    def edge_subgraph(self, e, preserve_nodes=False):
+        from .base import NID
+        e = torch.as_tensor(e)
+        sg = self._g.edge_subgraph(e, relabel_nodes=not preserve_nodes, store_ids=True)
+        nodes = sg.ndata[NID] if NID in sg.ndata else torch.arange(sg.num_nodes())
+        return SubgraphIndex(GraphIndex(sg, True), self, nodes, e)
+
+    # ---- matrices / conversion ------------------------------------------------------------------------------
+    def adjacency_matrix_scipy(self, transpose, fmt, return_edge_ids=None):
+        return self._g._graph.adjacency_matrix_scipy(0, transpose, fmt, return_edge_ids)
+
+    def adjacency_matrix(self, transpose, ctx):
+        return self._g._graph.adjacency_matrix(0, transpose, ctx)
+
+    def incidence_matrix(self, typestr, ctx):
+        return self._g._graph.incidence_matrix(0, typestr, ctx)
+
+    def get_csr_shuffle_order(self):
+        return self._g._graph.get_csr_shuffle_order(0)
+
+    def get_immutable_gidx(self, ctx):
+        return GraphIndex(self._g.to(ctx), True)
+
+    def to_immutable(self):
+        return GraphIndex(self._g, True)
+
+    def to_networkx(self):
+        import networkx as nx
+        u, v, e = [t.tolist() for t in self.edges()]
+        G = nx.MultiDiGraph() if self.is_multigraph() else nx.DiGraph()
+        G.add_nodes_from(range(self.num_nodes()))
+        for a, b, i in zip(u, v, e):
+            G.add_edge(a, b, id=i)
+        return G
+
+    def line_graph(self, backtracking=True):
+        from .transforms import line_graph
+        return GraphIndex(line_graph(self._g, backtracking=backtracking), True)
+
+    @property
+    def ctx(self):
+        return self._g.device
+
+    @property
+    def dtype(self):
+        return "int32" if self._g.idtype == torch.int32 else "int64"
+
+    def nbits(self):
+        return 32 if self._g.idtype == torch.int32 else 64
+
+    def bits_needed(self):
+        return self._g._graph.bits_needed(0)
+
+    def asbits(self, bits):
+        return GraphIndex(self._g.int() if int(bits) == 32 else self._g.long(), self._readonly)
+
+    def copy_to(self, ctx):
+        return GraphIndex(self._g.to(ctx), self._readonly)
+
+    def copyto_shared_mem(self, shared_mem_name):
+        return GraphIndex(self._g.shared_memory(shared_mem_name), True)
+
+
+class SubgraphIndex:
+    """A subgraph's index together with its parent and the induced parent ids."""
+
+    def __init__(self, graph, parent, induced_nodes, induced_edges):
+        self.graph, self.parent = graph, parent
+        self.induced_nodes, self.induced_edges = induced_nodes, induced_edges
+
+
+def from_coo(num_nodes, src, dst, readonly):
+    from .convert import graph as make_graph
+    return GraphIndex(make_graph((torch.as_tensor(src), torch.as_tensor(dst)), num_nodes=int(num_nodes)), readonly)
+
+
+def from_csr(indptr, indices, direction):
+    """``direction='out'``: rows are sources; ``'in'``: rows are destinations."""
+    from .convert import graph as make_graph
+    fmt = "csr" if direction == "out" else "csc"
+    return GraphIndex(make_graph((fmt, (torch.as_tensor(indptr), torch.as_tensor(indices), []))), True)
+
+
+def from_shared_mem_graph_index(shared_mem_name):
+    from .convert import hetero_from_shared_memory
+    return GraphIndex(hetero_from_shared_memory(shared_mem_name), True)
+
+
+def from_networkx(nx_graph, readonly):
+    from .convert import from_networkx as conv
+    import networkx as nx
+    if not isinstance(nx_graph, nx.Graph):
+        nx_graph = nx.DiGraph(nx_graph)
+    has_id = nx_graph.number_of_edges() > 0 and "id" in next(iter(nx_graph.edges(data=True)))[-1]
+    return GraphIndex(conv(nx_graph, edge_id_attr_name="id" if has_id else None), readonly)
+
+
+def from_scipy_sparse_matrix(adj, readonly):
+    from .convert import from_scipy
+    return GraphIndex(from_scipy(adj), readonly)
+
+
+def from_edge_list(elist, readonly):
+    from .convert import graph as make_graph
+    if isinstance(elist, tuple) and len(elist) == 2 and not isinstance(elist[0], (tuple, list)) or (
+            isinstance(elist, tuple) and len(elist) == 2 and len(elist[0]) != 2):
+        src, dst = elist
+    else:
+        src, dst = ([e[0] for e in elist], [e[1] for e in elist]) if len(elist) else ([], [])
+    return GraphIndex(make_graph((torch.as_tensor(src, dtype=torch.int64), torch.as_tensor(dst, dtype=torch.int64))),
+                      readonly)
+
+
+def map_to_subgraph_nid(induced_nodes, parent_nids):
+    """Positions of ``parent_nids`` inside ``induced_nodes`` (parent id -> subgraph id)."""
+    induced = torch.as_tensor(induced_nodes).long()
+    parent_nids = torch.as_tensor(parent_nids).long()
+    order = torch.argsort(induced)
+    pos = torch.searchsorted(induced[order], parent_nids)
+    if pos.numel() and (bool((pos >= induced.numel()).any()) or not torch.equal(induced[order][pos], parent_nids)):
+        raise DGLError("some parent node ids are not part of the subgraph")
+    return order[pos]
+
+
+def transform_ids(mapping, ids):
+    """``mapping[ids]``."""
+    return torch.as_tensor(mapping)[torch.as_tensor(ids).long()]
+
+
+def disjoint_union(graphs):
+    from .batch import batch
+    return GraphIndex(batch([x.graph for x in graphs]), True)
+
+
+def disjoint_partition(graph, num_or_size_splits):
+    """Inverse of :func:`disjoint_union`: an int splits into that many equal parts, a list gives node counts."""
+    from .batch import unbatch
+    g = graph.graph
+    if isinstance(num_or_size_splits, int):
+        k = num_or_size_splits
+        if g.num_nodes() % k:
+            raise DGLError("graph cannot be split into equally sized parts")
+        sizes = torch.full((k,), g.num_nodes() // k, dtype=torch.int64)
+    else:
+        sizes = torch.as_tensor(num_or_size_splits, dtype=torch.int64)
+    bounds = torch.cumsum(sizes, 0)
+    u, _ = g.edges()
+    owner = torch.searchsorted(bounds, u.long(), right=True)
+    esizes = torch.bincount(owner, minlength=sizes.shape[0])
+    return [GraphIndex(x, True) for x in unbatch(g, node_split=sizes, edge_split=esizes)]
+
+
+def create_graph_index(graph_data, readonly):
+    """Anything networkx-like, a scipy matrix, an edge list, another index or ``None`` (empty mutable index)."""
+    if isinstance(graph_data, GraphIndex):
+        return graph_data
+    if graph_data is None:
+        if readonly:
+            raise DGLError("can't create an empty immutable graph")
+        return GraphIndex(None, False)
+    if isinstance(graph_data, (list, tuple)):
+        return from_edge_list(graph_data, readonly)
+    if hasattr(graph_data, "tocoo"):
+        return from_scipy_sparse_matrix(graph_data, readonly)
+    try:
+        return from_networkx(graph_data, readonly)
+    except Exception as exc:  # noqa: BLE001
+        raise DGLError(f'Error while creating graph from input of type "{type(graph_data)}".') from exc

@@ -581,6 +581,12 @@ class DGLGraph:
         # multiple relations: flatten to one homogenised relation
         return self._flatten(etids)
 
+    @property
+    def _graph(self):
+        """Id-based index view (the reference's ``g._graph`` handle; see :mod:`dgl_b200.heterograph_index`)."""
+        from .heterograph_index import HeteroGraphIndex
+        return HeteroGraphIndex(self)
+
     def _single_relation_graph(self, etid):
         s, e, d = self._canonical_etypes[etid]
         sid, did = self._src_ntid(etid), self._dst_ntid(etid)

@@ -8,6 +8,17 @@ from . import function as fn
 __all__ = ["node_homophily", "edge_homophily", "linkx_homophily", "adjusted_homophily"]
 
 
+def check_pytorch():
+    """The measures are written against torch tensors (the reference guards on its backend switch here)."""
+    return True
+
+
+def get_long_edges(graph):
+    """(src, dst) of every edge as int64 tensors."""
+    src, dst = graph.edges()
+    return src.long(), dst.long()
+
+
 def node_homophily(graph, y):
     with graph.local_scope():
         src, dst = graph.edges()

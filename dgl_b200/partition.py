@@ -11,6 +11,34 @@ from .convert import graph as make_graph
 from .subgraph import node_subgraph
 
 
+def reorder_nodes(g, new_node_ids):
+    """Graph whose node ``v`` of ``g`` is renamed ``new_node_ids[v]`` (a permutation of 0..N-1); edge order is kept and
+    ``ndata['orig_id']`` maps new ids back (reference partition.py:22)."""
+    new_node_ids = torch.as_tensor(new_node_ids, device=g.device).to(g.idtype)
+    if new_node_ids.shape[0] != g.num_nodes():
+        raise DGLError("The number of new node ids must match #nodes in the graph.")
+    sorted_ids, idx = torch.sort(new_node_ids)
+    if g.num_nodes() and not torch.equal(sorted_ids, torch.arange(g.num_nodes(), dtype=g.idtype, device=g.device)):
+        raise DGLError("The new node IDs are incorrect.")
+    u, v = g.edges()
+    out = make_graph((new_node_ids[u.long()], new_node_ids[v.long()]), num_nodes=g.num_nodes(), idtype=g.idtype,
+                     device=g.device)
+    out.ndata["orig_id"] = idx.to(g.idtype)
+    return out
+
+
+def get_peak_mem():
+    """Peak virtual memory of this process in GB (``VmPeak`` of /proc/self/status; 0.0 where unavailable)."""
+    try:
+        with open("/proc/self/status") as f:
+            for line in f:
+                if line.startswith("VmPeak"):
+                    return int(line.split()[1]) / 1024 / 1024
+    except OSError:
+        pass
+    return 0.0
+
+
 def _sym_csr(g):
     """CSR of the symmetrised homogeneous view of g (CPU int64)."""
     from .convert import to_homogeneous
