@@ -7,7 +7,7 @@ def __getattr__(name):
     if name.startswith("__"):
         raise AttributeError(name)
     import importlib
-    for modname in ("dgl_dataset", "graph_serialize", "more", "builtin", "csv_dataset", "utils", "extra"):
+    for modname in ("dgl_dataset", "graph_serialize", "more", "builtin", "csv_dataset", "utils", "extra", "compat"):
         mod = importlib.import_module(f"{__name__}.{modname}")
         if hasattr(mod, name):
             return getattr(mod, name)

@@ -1,91 +1,95 @@
-"""CSVDataset (parity: /root/reference/python/dgl/data/csv_dataset.py): a directory with ``meta.yaml`` +
-nodes_*.csv / edges_*.csv (+ optional graphs.csv)."""
+"""CSVDataset (parity: /root/reference/python/dgl/data/csv_dataset.py): a directory holding ``meta.yaml`` plus
+nodes_*.csv / edges_*.csv and an optional graphs.csv becomes one or many (hetero)graphs.
+
+Parsing is split in ``csv_dataset_base``: YAML validation, one table object per CSV, graph construction. Feature
+columns go through a *data parser* — a callable ``DataFrame -> {name: ndarray}`` — which can be given per node type /
+edge type (dict) or as one callable; :class:`~.csv_dataset_base.DefaultDataParser` is the default. Processed graphs
+are cached next to the CSVs (``<name>.bin``) and reloaded unless ``force_reload``."""
 from __future__ import annotations
 
 import os
 
-import numpy as np
-import pandas as pd
 import torch
-import yaml
 
 from ..base import DGLError
-from ..convert import heterograph
 from .dgl_dataset import DGLDataset
-
-
-def _parse_feats(df, skip):
-    out = {}
-    for col in df.columns:
-        if col in skip:
-            continue
-        vals = df[col].to_numpy()
-        if vals.dtype == object:
-            arr = np.stack([np.array([float(x) for x in str(v).split(",")]) for v in vals])
-            out[col] = torch.from_numpy(arr).float() if arr.dtype.kind == "f" else torch.from_numpy(arr)
-        else:
-            t = torch.from_numpy(vals)
-            out[col] = t.float() if t.dtype == torch.float64 else t
-    return out
+from .graph_serialize import load_graphs, save_graphs
+from .utils import Subset
 
 
 class CSVDataset(DGLDataset):
+    META_YAML_NAME = "meta.yaml"
+
     def __init__(self, data_path, force_reload=False, verbose=True, ndata_parser=None, edata_parser=None,
                  gdata_parser=None, transform=None):
+        from .csv_dataset_base import DefaultDataParser, load_yaml_with_sanity_check
+        self.graphs, self.data = None, None
+        self.ndata_parser = {} if ndata_parser is None else ndata_parser
+        self.edata_parser = {} if edata_parser is None else edata_parser
+        self.gdata_parser = gdata_parser
+        self.default_data_parser = DefaultDataParser()
         self.data_path = data_path
-        meta_path = os.path.join(data_path, "meta.yaml")
+        meta_path = os.path.join(data_path, self.META_YAML_NAME)
         if not os.path.exists(meta_path):
-            raise DGLError(f"'meta.yaml' cannot be found under {data_path}.")
-        with open(meta_path) as f:
-            self.meta = yaml.safe_load(f)
-        self.graphs, self.data = [], {}
-        super().__init__(self.meta.get("dataset_name", "csv_dataset"), raw_dir=os.path.dirname(data_path),
-                         force_reload=force_reload, verbose=verbose, transform=transform)
+            raise DGLError(f"'{self.META_YAML_NAME}' cannot be found under {data_path}.")
+        self.meta_yaml = load_yaml_with_sanity_check(meta_path)
+        super().__init__(self.meta_yaml.dataset_name, raw_dir=os.path.dirname(meta_path), force_reload=force_reload,
+                         verbose=verbose, transform=transform)
+
+    # the CSVs live in the directory itself, not under <raw_dir>/<name>
+    @property
+    def raw_path(self):
+        return self.data_path
+
+    @property
+    def save_path(self):
+        return self.data_path
+
+    def _parser(self, table, key):
+        if callable(table):
+            return table
+        return table.get(key, self.default_data_parser)
 
     def process(self):
-        sep = self.meta.get("separator", ",")
-        node_frames, edge_frames = {}, {}
-        for nd in self.meta.get("node_data", []):
-            node_frames[nd.get("ntype", "_V")] = pd.read_csv(os.path.join(self.data_path, nd["file_name"]), sep=sep)
-        for ed in self.meta.get("edge_data", []):
-            et = tuple(ed.get("etype", ["_V", "_E", "_V"]))
-            edge_frames[et] = pd.read_csv(os.path.join(self.data_path, ed["file_name"]), sep=sep)
-        gids = set()
-        for df in list(node_frames.values()) + list(edge_frames.values()):
-            if "graph_id" in df.columns:
-                gids.update(df["graph_id"].unique().tolist())
-        gids = sorted(gids) if gids else [None]
-        for gid in gids:
-            data, nn, nfeat, efeat = {}, {}, {}, {}
-            idmaps = {}
-            for nt, df in node_frames.items():
-                d = df if gid is None else df[df["graph_id"] == gid]
-                ids = d["node_id"].to_numpy()
-                idmaps[nt] = {v: i for i, v in enumerate(ids)}
-                nn[nt] = len(ids)
-                nfeat[nt] = _parse_feats(d, {"node_id", "graph_id"})
-            for et, df in edge_frames.items():
-                d = df if gid is None else df[df["graph_id"] == gid]
-                s = [idmaps[et[0]][x] for x in d["src_id"].to_numpy()] if et[0] in idmaps else d["src_id"].to_numpy()
-                t = [idmaps[et[2]][x] for x in d["dst_id"].to_numpy()] if et[2] in idmaps else d["dst_id"].to_numpy()
-                data[et] = (torch.as_tensor(np.asarray(s, dtype=np.int64)), torch.as_tensor(np.asarray(t, dtype=np.int64)))
-                efeat[et] = _parse_feats(d, {"src_id", "dst_id", "graph_id"})
-            g = heterograph(data, nn or None)
-            for nt, fs in nfeat.items():
-                for k, v in fs.items():
-                    g.nodes[nt].data[k] = v
-            for et, fs in efeat.items():
-                for k, v in fs.items():
-                    g.edges[et].data[k] = v
-            self.graphs.append(g)
-        gd = self.meta.get("graph_data")
-        if gd:
-            df = pd.read_csv(os.path.join(self.data_path, gd["file_name"]), sep=sep)
-            self.data = _parse_feats(df, {"graph_id"})
+        from .csv_dataset_base import DGLGraphConstructor, EdgeData, GraphData, NodeData
+        meta, base, sep = self.meta_yaml, self.data_path, self.meta_yaml.separator
+        nodes = [NodeData.load_from_csv(m, self._parser(self.ndata_parser, m.ntype), base_dir=base, separator=sep)
+                 for m in meta.node_data]
+        edges = [EdgeData.load_from_csv(m, self._parser(self.edata_parser, tuple(m.etype)), base_dir=base, separator=sep)
+                 for m in meta.edge_data]
+        graph_data = None
+        if meta.graph_data is not None:
+            graph_data = GraphData.load_from_csv(meta.graph_data, self.gdata_parser or self.default_data_parser,
+                                                 base_dir=base, separator=sep)
+        self.graphs, self.data = DGLGraphConstructor.construct_graphs(nodes, edges, graph_data)
+        self._set_labels()
+
+    def _set_labels(self):
+        if len(self.data) == 1:
+            self.labels = next(iter(self.data.values()))
+
+    def _cache_file(self):
+        return os.path.join(self.save_path, self.name + ".bin")
+
+    def has_cache(self):
+        return os.path.exists(self._cache_file())
+
+    def save(self):
+        if self.graphs is None:
+            raise DGLError("No graphs available in dataset")
+        save_graphs(self._cache_file(), self.graphs, labels=self.data)
+
+    def load(self):
+        self.graphs, self.data = load_graphs(self._cache_file())
+        self._set_labels()
 
     def __getitem__(self, i):
+        if torch.is_tensor(i) and i.dim() == 1:
+            return Subset(self, i.cpu())
         g = self.graphs[i] if self._transform is None else self._transform(self.graphs[i])
-        if self.data:
+        if len(self.data) == 1:
+            return g, self.labels[i]
+        if len(self.data) > 0:
             return g, {k: v[i] for k, v in self.data.items()}
         return g
 
