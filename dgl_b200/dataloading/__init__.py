@@ -18,3 +18,14 @@ from .capped_neighbor_sampler import CappedNeighborSampler  # noqa: F401
 from .spot_target import SpotTarget  # noqa: F401
 
 from .dataloader import GraphCollator  # noqa: F401,E402
+from .tensorized import (CollateWrapper, DDPTensorizedDataset, EdgeCollator, NodeCollator, TensorizedDataset,  # noqa: F401,E402
+                         WorkerInitWrapper, create_tensorized_dataset, find_exclude_eids,
+                         remove_parent_storage_columns, restore_parent_storage_columns)
+
+
+def __getattr__(name):
+    # distributed loaders are also reachable from here, as in the reference's dataloading/dist_dataloader.py
+    if name in ("DistDataLoader", "DistNodeDataLoader", "DistEdgeDataLoader"):
+        from ..distributed import dist_graph
+        return getattr(dist_graph, name)
+    raise AttributeError(name)
