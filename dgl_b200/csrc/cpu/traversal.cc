@@ -6,6 +6,7 @@
 // frontier ("sections"); the Python side splits.  Everything here is a single pass over the edges
 // that the traversal reaches, so these are serial by design (frontier order is part of the
 // contract: discovery order, ties by adjacency order).
+#include <algorithm>
 #include <vector>
 
 #include "common.h"
@@ -114,10 +115,88 @@ int64_t dfs(const I* indptr, const I* indices, const I* eids, int64_t n, I sourc
   return w;
 }
 
+// Reverse Cuthill-McKee on a symmetric adjacency: per connected component start from a
+// pseudo-peripheral vertex (George-Liu: repeat BFS from a minimum-degree vertex of the last level
+// until the eccentricity stops growing), number vertices breadth-first visiting neighbours by
+// increasing degree, and finally reverse the whole numbering.
+template <typename I>
+void rcmk(const I* indptr, const I* indices, int64_t n, int64_t* perm) {
+  std::vector<int64_t> deg(n);
+  for (int64_t v = 0; v < n; ++v) deg[v] = indptr[v + 1] - indptr[v];
+  std::vector<int64_t> by_degree(n);
+  for (int64_t v = 0; v < n; ++v) by_degree[v] = v;
+  std::stable_sort(by_degree.begin(), by_degree.end(), [&](int64_t a, int64_t b) { return deg[a] < deg[b]; });
+  std::vector<uint8_t> placed(n, 0);
+  std::vector<int64_t> level(n, -1), queue, touched;
+  std::vector<I> nbrs;
+  int64_t w = 0;
+
+  // BFS over the not-yet-placed component of `root`; returns (eccentricity, min-degree vertex of last level)
+  auto probe = [&](int64_t root) {
+    for (int64_t v : touched) level[v] = -1;
+    touched.clear();
+    queue.clear();
+    queue.push_back(root);
+    level[root] = 0;
+    touched.push_back(root);
+    int64_t last = root, ecc = 0;
+    for (size_t h = 0; h < queue.size(); ++h) {
+      const int64_t u = queue[h];
+      if (level[u] > ecc || (level[u] == ecc && deg[u] < deg[last])) {
+        if (level[u] > ecc) last = u;
+        ecc = level[u];
+        if (deg[u] < deg[last]) last = u;
+      }
+      for (I p = indptr[u]; p < indptr[u + 1]; ++p) {
+        const int64_t v = indices[p];
+        if (placed[v] || level[v] >= 0) continue;
+        level[v] = level[u] + 1;
+        touched.push_back(v);
+        queue.push_back(v);
+      }
+    }
+    return std::make_pair(ecc, last);
+  };
+
+  for (int64_t seed : by_degree) {
+    if (placed[seed]) continue;
+    int64_t root = seed;
+    auto cur = probe(root);
+    for (int iter = 0; iter < 8; ++iter) {
+      auto nxt = probe(cur.second);
+      if (nxt.first <= cur.first) break;
+      root = cur.second;
+      cur = nxt;
+    }
+    // Cuthill-McKee numbering of this component
+    const int64_t first = w;
+    perm[w++] = root;
+    placed[root] = 1;
+    for (int64_t h = first; h < w; ++h) {
+      const int64_t u = perm[h];
+      nbrs.clear();
+      for (I p = indptr[u]; p < indptr[u + 1]; ++p)
+        if (!placed[indices[p]]) {
+          placed[indices[p]] = 1;
+          nbrs.push_back(indices[p]);
+        }
+      std::stable_sort(nbrs.begin(), nbrs.end(), [&](I a, I b) { return deg[a] < deg[b]; });
+      for (I v : nbrs) perm[w++] = v;
+    }
+  }
+  std::reverse(perm, perm + n);
+}
+
 }  // namespace
 }  // namespace dglb
 
 using namespace dglb;
+
+DGLB_API int dglb200_cpu_rcmk(int idtype, const void* indptr, const void* indices, int64_t n, int64_t* perm) {
+  DGLB_TRY
+  DGLB_ID_SWITCH(idtype, I, rcmk<I>((const I*)indptr, (const I*)indices, n, perm));
+  DGLB_CATCH
+}
 
 DGLB_API int dglb200_cpu_bfs(int idtype, const void* indptr, const void* indices, const void* eids, int64_t n,
                              const void* src, int64_t n_src, int want_edges, void* out_ids, int64_t* sections,

@@ -32,6 +32,7 @@ __all__ = [
     "adj_product_graph", "adj_sum_graph", "out_subgraph_like", "unique_and_compact", "norm_by_dst",
     "reverse_heterograph", "to_simple_graph", "to_bidirected_stale", "laplacian_lambda_max",
     "metis_partition", "metis_partition_assignment", "partition_graph_with_halo",
+    "knn", "metis_perm", "rcmk_perm", "pairwise_squared_distance",
 ]
 
 
@@ -499,6 +500,83 @@ def _sort_by_tag(g, tag, name, tag_type, fmt):
     return new
 
 
+def metis_perm(g, k):
+    """Node permutation grouping the ``k`` partitions of :func:`metis_partition_assignment` (reference
+    functional.py:3347); returns a numpy array like the reference."""
+    from ..partition import metis_partition_assignment
+    part = metis_partition_assignment(g if g.device.type == "cpu" else g.to("cpu"), k)
+    return torch.sort(part, stable=True)[1].numpy().copy()
+
+
+def rcmk_perm(g):
+    """Reverse Cuthill-McKee node permutation (bandwidth reduction) of the symmetrised graph, computed natively
+    (csrc/cpu/traversal.cc rcmk: pseudo-peripheral start per component, degree-ordered BFS) — reference
+    functional.py:3371 calls scipy's ``reverse_cuthill_mckee``."""
+    from .._native import loader
+    from ..base import id_code
+    from ..graph_index import coo_to_csr
+    cg = g if g.device.type == "cpu" else g.to("cpu")
+    su, sv, _ = to_bidirected_coo(cg)
+    n = cg.num_nodes()
+    indptr, indices, _ = coo_to_csr(su, sv, n, cg.idtype)
+    perm = torch.empty(n, dtype=torch.int64)
+    loader.cpu_lib().fn("dglb200_cpu_rcmk", "ipplp")(id_code(cg.idtype), indptr.data_ptr(), indices.data_ptr(), n,
+                                                     perm.data_ptr())
+    return perm.numpy().copy()
+
+
+def pairwise_squared_distance(x):
+    """x: (n_samples, n_points, dims) -> (n_samples, n_points, n_points) squared Euclidean distances."""
+    x2 = (x * x).sum(-1, keepdim=True)
+    return x2 + x2.transpose(-1, -2) - 2 * x @ x.transpose(-1, -2)
+
+
+def knn(k, x, x_segs, y=None, y_segs=None, algorithm="bruteforce", dist="euclidean"):
+    """For every point of every segment of ``y`` the ``k`` nearest points of the same segment of ``x`` (self query when
+    ``y`` is None). Returns a ``[2, k * len(y)]`` id tensor: row 0 indexes ``y``, row 1 indexes ``x`` (reference
+    functional.py:641). 'kd-tree' (host) uses the native tree; the brute-force names use the shared-memory kernel on
+    the GPU and the tree / GEMM path on the host; 'nn-descent' is served exactly."""
+    if algorithm == "nn-descent" and y is not None:
+        raise DGLError("Currently 'nn-descent' only supports self-query cases.")
+    if y is None:
+        y, y_segs = x, x_segs
+    if x.device != y.device:
+        raise DGLError("x and y must be on the same device")
+    x_segs = torch.as_tensor(x_segs).long().cpu()
+    y_segs = torch.as_tensor(y_segs).long().cpu()
+    if x_segs.numel() != y_segs.numel():
+        raise DGLError("x_segs and y_segs must describe the same number of point sets")
+    lo = int(x_segs.min()) if x_segs.numel() else 0
+    if k > lo:
+        dgl_warning(f"'k' should be less than or equal to the number of points in 'x'expect k <= {lo}, got k = {k}, "
+                    f"use k = {lo}")
+        k = lo
+    if k <= 0:
+        raise DGLError(f"Invalid k value. expect k > 0, got k = {k}")
+    if x.shape[0] == 0 or y.shape[0] == 0:
+        raise DGLError("Find empty point set")
+    dist = dist.lower()
+    if dist not in ("euclidean", "cosine"):
+        raise DGLError(f"Only ['euclidean', 'cosine'] are supported for distancecomputation, got {dist}")
+    if dist == "cosine":
+        x = x / (x.norm(dim=1, keepdim=True) + 1e-5)
+        y = y / (y.norm(dim=1, keepdim=True) + 1e-5)
+    xo = torch.cat([torch.zeros(1, dtype=torch.long), x_segs.cumsum(0)])
+    yo = torch.cat([torch.zeros(1, dtype=torch.long), y_segs.cumsum(0)])
+    if x.device.type == "cpu" and x.dtype == y.dtype and x.dtype in (torch.float32, torch.float64) and \
+            (algorithm == "kd-tree" or x.shape[1] <= 16):
+        idx = kdtree_knn(x, y, k, xo, yo)[0]
+    elif x.is_cuda and x.shape[1] <= 16 and k <= 64 and x.dtype == y.dtype and x.dtype in (
+            torch.float32, torch.float16, torch.bfloat16):
+        from .._graph_kernels import knn_brute
+        idx = knn_brute(x, xo.to(x.device), y, yo.to(x.device), k)
+    else:
+        idx = torch.cat([_pairwise_topk(x[xo[s]:xo[s + 1]], y[yo[s]:yo[s + 1]], k) + int(xo[s])
+                         for s in range(x_segs.numel())])
+    rows = torch.arange(y.shape[0], device=idx.device).view(-1, 1).expand_as(idx)
+    return torch.stack([rows.reshape(-1), idx.reshape(-1)]).to(torch.int64)
+
+
 def reorder_graph(g, node_permute_algo=None, edge_permute_algo="src", store_ids=True, permute_config=None):
     """Reorder nodes ('rcmk', 'metis', 'custom') and edges ('src', 'dst', 'custom')
     (reference reorder_graph)."""
@@ -509,15 +587,12 @@ def reorder_graph(g, node_permute_algo=None, edge_permute_algo="src", store_ids=
     if node_permute_algo is None:
         perm = torch.arange(n, device=g.device)
     elif node_permute_algo == "rcmk":
-        from scipy.sparse.csgraph import reverse_cuthill_mckee
-        perm = torch.from_numpy(reverse_cuthill_mckee(_scipy_adj(g)).astype(np.int64)).to(g.device)
+        perm = torch.as_tensor(rcmk_perm(g)).to(g.device)
     elif node_permute_algo == "metis":
         k = permute_config.get("k")
         if k is None:
             raise DGLError("Partition parts 'k' is required for metis.")
-        from ..partition import metis_partition_assignment
-        part = metis_partition_assignment(g, k)
-        perm = torch.sort(part, stable=True)[1]
+        perm = torch.as_tensor(metis_perm(g, k)).to(g.device)
     elif node_permute_algo == "custom":
         perm = _to_tensor(permute_config["nodes_perm"], torch.int64, g.device)
         if perm.shape[0] != n:
