@@ -20,7 +20,8 @@ from ..ops import cpu_struct as _cpu_struct
 __all__ = ["SparseMatrix", "spmatrix", "from_coo", "from_csr", "from_csc", "diag", "identity", "val_like", "spmm",
            "bspmm", "spspmm", "sddmm", "bsddmm", "softmax", "sum", "smax", "smin", "smean", "sprod", "add", "sub",
            "mul", "div", "power", "neg", "inv", "matmul", "sp_broadcast_v", "sp_add_v", "sp_sub_v", "sp_mul_v",
-           "sp_div_v", "to_torch_sparse_coo", "to_torch_sparse_csr", "to_torch_sparse_csc", "from_torch_sparse", "reduce"]
+           "sp_div_v", "to_torch_sparse_coo", "to_torch_sparse_csr", "to_torch_sparse_csc", "from_torch_sparse", "reduce", "sp_add", "sp_sub", "sp_mul", "sp_div", "sp_power",
+           "spsp_add", "spsp_mul", "spsp_div", "is_scalar", "load_dgl_sparse"]
 
 
 class SparseMatrix:
@@ -508,11 +509,65 @@ def sub(A, B):
     raise DGLError("SparseMatrix can only be subtracted by another SparseMatrix")
 
 
+def is_scalar(x):
+    """Python number or 0-dim tensor (reference sparse/utils.py)."""
+    import numbers
+    return isinstance(x, numbers.Number) or (torch.is_tensor(x) and x.dim() == 0)
+
+
+def _match_nonzeros(A, B):
+    """Positions (ia, ib) of the coordinates that A and B share (both coalesced); order follows A's non-zeros."""
+    ra, ca = A.coo()
+    rb, cb = B.coo()
+    ncol = max(A.shape[1], 1)
+    ka = ra.long() * ncol + ca.long()
+    kb = rb.long() * ncol + cb.long()
+    if kb.numel() == 0 or ka.numel() == 0:
+        e = torch.empty(0, dtype=torch.long, device=ka.device)
+        return e, e
+    skb, order = torch.sort(kb)
+    pos = torch.searchsorted(skb, ka).clamp(max=skb.numel() - 1)
+    hit = skb[pos] == ka
+    ia = torch.nonzero(hit).view(-1)
+    return ia, order[pos[hit]]
+
+
+def spsp_add(A, B):
+    return _binary_sp(A, B, lambda x: x)
+
+
+def spsp_mul(A, B):
+    """Elementwise product of two sparse matrices: non-zero only where both are (reference elementwise_op_sp.py:17)."""
+    if A.shape != B.shape:
+        raise DGLError(f"shape mismatch: {A.shape} vs {B.shape}")
+    A = A.coalesce() if A.has_duplicate() else A
+    B = B.coalesce() if B.has_duplicate() else B
+    ia, ib = _match_nonzeros(A, B)
+    r, c = A.coo()
+    return from_coo(r[ia], c[ia], A.val[ia] * B.val[ib], A.shape)
+
+
+def spsp_div(A, B):
+    """Elementwise quotient; both operands must have the same sparsity and the result keeps A's non-zero order
+    (reference elementwise_op_sp.py:24)."""
+    if A.shape != B.shape:
+        raise DGLError(f"shape mismatch: {A.shape} vs {B.shape}")
+    if A.has_duplicate() or B.has_duplicate():
+        raise DGLError("sp_div requires both matrices to be coalesced (no duplicate entries)")
+    ia, ib = _match_nonzeros(A, B)
+    if not (ia.numel() == A.nnz == B.nnz):
+        raise DGLError("Cannot divide two COO matrices with different sparsities.")
+    return val_like(A, A.val / B.val[ib])
+
+
 def mul(A, B):
     if isinstance(A, SparseMatrix) and isinstance(B, SparseMatrix):
-        if A.is_diag() and B.is_diag() and A.nnz == B.nnz:
-            return val_like(A, A.val * B.val)
-        raise DGLError("elementwise mul of two general sparse matrices is not supported (as in the reference)")
+        if A.is_diag() and B.is_diag() and A.nnz == B.nnz and A.shape == B.shape and not A.has_duplicate():
+            ra, _ = A.coo()
+            rb, _ = B.coo()
+            if torch.equal(ra, rb):
+                return val_like(A, A.val * B.val)
+        return spsp_mul(A, B)
     if isinstance(B, SparseMatrix):
         A, B = B, A
     return val_like(A, A.val * B)
@@ -520,10 +575,44 @@ def mul(A, B):
 
 def div(A, B):
     if isinstance(B, SparseMatrix):
-        if isinstance(A, SparseMatrix) and A.is_diag() and B.is_diag():
-            return val_like(A, A.val / B.val)
-        raise DGLError("division by a sparse matrix is only defined for diagonal matrices")
+        if not isinstance(A, SparseMatrix):
+            raise DGLError("Only a sparse matrix can be divided by a sparse matrix.")
+        return spsp_div(A, B)
     return val_like(A, A.val / B)
+
+
+def sp_add(A, B):
+    """``A + B`` for two sparse matrices (operator form; other operand types are rejected)."""
+    return spsp_add(A, B) if isinstance(B, SparseMatrix) else NotImplemented
+
+
+def sp_sub(A, B):
+    return sub(A, B) if isinstance(B, SparseMatrix) else NotImplemented
+
+
+def sp_mul(A, B):
+    """``A * B``: scalar scaling, or the intersection product of two sparse matrices."""
+    if is_scalar(B):
+        return val_like(A, A.val * B)
+    return spsp_mul(A, B) if isinstance(B, SparseMatrix) else NotImplemented
+
+
+def sp_div(A, B):
+    """``A / B``: scalar, or a sparse matrix with identical sparsity."""
+    if is_scalar(B):
+        return val_like(A, A.val / B)
+    return spsp_div(A, B) if isinstance(B, SparseMatrix) else NotImplemented
+
+
+def sp_power(A, scalar):
+    return val_like(A, A.val ** scalar) if is_scalar(scalar) else NotImplemented
+
+
+def load_dgl_sparse():
+    """The reference dlopens libdgl_sparse here; the sparse kernels of this package live in the two native libraries
+    loaded by ``dgl_b200._native.loader`` — make sure the host one is present."""
+    from .._native import loader
+    loader.cpu_lib()
 
 
 def power(A, scalar):
