@@ -468,3 +468,151 @@ def download(url, path=None, overwrite=True, sha1_hash=None, retries=5, verify_s
     if os.path.exists(fname) and (sha1_hash is None or check_sha1(fname, sha1_hash)):
         return fname
     raise RuntimeError(f"cannot download {url}: no network access; place the file at {fname}")
+
+
+# ---------------------------------------------------------------------------------------------- late additions
+from typing import Dict as _Dict, NamedTuple as _NamedTuple, Tuple as _Tuple  # noqa: E402
+
+from . import datapipes as _dp  # noqa: E402
+
+
+class PyGLayerData(_NamedTuple):
+    """Homogeneous inputs of one PyG layer: ``x`` = (source features, destination features), ``edge_index`` [2, E],
+    ``size`` = (num src, num dst) — reference sampled_subgraph.py:44."""
+    x: _Tuple
+    edge_index: torch.Tensor
+    size: _Tuple[int, int]
+
+
+class PyGLayerHeteroData(_NamedTuple):
+    """Heterogeneous counterpart: every field is a dict (features by node type, the rest by edge type) —
+    reference sampled_subgraph.py:55."""
+    x: _Tuple
+    edge_index: _Dict[str, torch.Tensor]
+    size: _Dict[str, _Tuple[int, int]]
+
+
+def get_feature_key_list(feature_keys, domain):
+    """[(domain, type or None, name)] from a list (homogeneous) or ``{type: [names]}`` (reference feature_fetcher.py:22)."""
+    if isinstance(feature_keys, dict):
+        return [(domain, t, n) for t, names in feature_keys.items() for n in names]
+    if feature_keys is not None:
+        return [(domain, None, n) for n in feature_keys]
+    return []
+
+
+def is_object_pinned(obj):
+    """True iff every tensor reachable from the object's plain attributes is in pinned memory (reference base.py:323)."""
+    for attr in get_nonproperty_attributes(obj):
+        if not recursive_apply_reduce_all(getattr(obj, attr), lambda x: x is None or not hasattr(x, "is_pinned") or x.is_pinned()):
+            return False
+    return True
+
+
+def is_scalar(x):
+    """0-dim tensor or Python number (reference itemset.py:is_scalar)."""
+    import numbers
+    return (torch.is_tensor(x) and x.dim() == 0) or isinstance(x, numbers.Number)
+
+
+def load_graphbolt():
+    """The reference dlopens ``libgraphbolt`` here. The native pieces of this package (samplers, caches, disk reader)
+    are part of ``libdglb200_{cpu,cuda}``; loading the host library is the equivalent readiness check."""
+    from .._native import loader
+    loader.cpu_lib()
+
+
+class MultiprocessingWrapper(_dp.MiniBatchTransformer):
+    """Reference dataloader.py:MultiprocessingWrapper moves the upstream stages into torch worker processes. The
+    sampling stages here are GPU (or OpenMP) kernels, so the wrapper runs them in a prefetching thread instead:
+    ``num_workers == 0`` is a pass-through, otherwise up to ``2 * num_workers`` batches are produced ahead."""
+
+    def __init__(self, datapipe, num_workers=0, persistent_workers=True):
+        from .datapipes.utils import PrefetcherIterDataPipe
+        self.num_workers = num_workers
+        inner = datapipe if num_workers <= 0 else PrefetcherIterDataPipe(datapipe, 2 * num_workers)
+        super().__init__(inner, None)
+
+    def __iter__(self):
+        return iter(self.datapipe)
+
+
+class NeighborSamplerImpl(_dp.SubgraphSampler):
+    """Common base of the neighbour samplers (reference impl/neighbor_sampler.py:NeighborSamplerImpl): subclasses of it
+    here are ``impl.neighbor_sampler.NeighborSampler`` / ``LayerNeighborSampler``; constructing it directly gives the
+    sampler selected by ``layer`` (False: per-node fanout, True: LABOR layer sampling)."""
+
+    def __new__(cls, datapipe, graph, fanouts, replace=False, prob_name=None, deduplicate=True, sampler=None,
+                overlap_fetch=None, num_gpu_cached_edges=None, gpu_cache_threshold=None, cooperative=None,
+                asynchronous=None, layer_dependency=None, batch_dependency=None, layer=False):
+        from .impl.neighbor_sampler import LayerNeighborSampler, NeighborSampler
+        if layer:
+            return LayerNeighborSampler(datapipe, graph, fanouts, replace=replace, prob_name=prob_name,
+                                        deduplicate=deduplicate, layer_dependency=bool(layer_dependency))
+        return NeighborSampler(datapipe, graph, fanouts, replace=replace, prob_name=prob_name, deduplicate=deduplicate)
+
+
+class TemporalNeighborSamplerImpl(_dp.SubgraphSampler):
+    """Common base of the temporal samplers (reference impl/temporal_neighbor_sampler.py)."""
+
+    def __new__(cls, datapipe, graph, fanouts, replace=False, prob_name=None, node_timestamp_attr_name=None,
+                edge_timestamp_attr_name=None, sampler=None, layer=False):
+        from .impl.neighbor_sampler import TemporalLayerNeighborSampler, TemporalNeighborSampler
+        kind = TemporalLayerNeighborSampler if layer else TemporalNeighborSampler
+        return kind(datapipe, graph, fanouts, replace=replace, prob_name=prob_name,
+                    node_timestamp_attr_name=node_timestamp_attr_name, edge_timestamp_attr_name=edge_timestamp_attr_name)
+
+
+class CompactPerLayer(_dp.MiniBatchTransformer):
+    """Second half of a sampling layer as its own stage: relabel the freshly sampled block against the unique node set
+    and make that set the seeds of the next layer (reference impl/neighbor_sampler.py:CompactPerLayer)."""
+
+    def __init__(self, datapipe, deduplicate=True, cooperative=False, asynchronous=False):
+        super().__init__(datapipe, self._compact)
+        self.deduplicate = deduplicate
+
+    def _compact(self, minibatch):
+        from .utils import compact_csc_format, unique_and_compact_csc_formats
+        sub = minibatch.sampled_subgraphs[0]
+        seeds = minibatch._seed_nodes
+        if getattr(sub, "original_row_node_ids", None) is not None:
+            minibatch._seed_nodes = sub.original_row_node_ids     # layer already compacted by the sampler
+            return minibatch
+        if self.deduplicate:
+            row_ids, csc = unique_and_compact_csc_formats(sub.sampled_csc, seeds)
+        else:
+            row_ids, csc = compact_csc_format(sub.sampled_csc, seeds)
+        sub.sampled_csc, sub.original_row_node_ids, sub.original_column_node_ids = csc, row_ids, seeds
+        minibatch._seed_nodes = row_ids
+        return minibatch
+
+
+class FetchCachedInsubgraphData(_dp.MiniBatchTransformer):
+    """Query the GPU graph cache for the seeds' adjacency lists; misses are left for :class:`FetchInsubgraphData`
+    (reference impl/neighbor_sampler.py:FetchCachedInsubgraphData)."""
+
+    def __init__(self, datapipe, gpu_graph_cache):
+        super().__init__(datapipe, self._query)
+        self.cache = gpu_graph_cache
+
+    def _query(self, minibatch):
+        seeds = minibatch._seed_nodes
+        if torch.is_tensor(seeds) and seeds.is_cuda:
+            minibatch._cache_query = self.cache.query(seeds)
+        return minibatch
+
+
+class CombineCachedAndFetchedInSubgraph(_dp.MiniBatchTransformer):
+    """Merge cache hits with the lists fetched for the misses and insert the latter into the cache (reference
+    impl/neighbor_sampler.py:CombineCachedAndFetchedInSubgraph)."""
+
+    def __init__(self, datapipe, prob_name=None):
+        super().__init__(datapipe, self._combine)
+
+    def _combine(self, minibatch):
+        q = getattr(minibatch, "_cache_query", None)
+        fetched = getattr(minibatch, "_sliced_sampling_graph", None)
+        if q is not None and fetched is not None and hasattr(q, "replace"):
+            minibatch._sliced_sampling_graph = q.replace(*fetched)
+        return minibatch
+

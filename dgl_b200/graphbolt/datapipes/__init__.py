@@ -12,8 +12,8 @@ import threading
 
 import torch
 
-from .base import etype_str_to_tuple
-from .minibatch import MiniBatch
+from ..base import etype_str_to_tuple
+from ..minibatch import MiniBatch
 
 
 class _Stage:
@@ -26,19 +26,19 @@ class _Stage:
         return len(self.datapipe)
 
     def sample_neighbor(self, graph, fanouts, **kw):
-        from .impl.neighbor_sampler import NeighborSampler
+        from ..impl.neighbor_sampler import NeighborSampler
         return NeighborSampler(self, graph, fanouts, **kw)
 
     def sample_layer_neighbor(self, graph, fanouts, **kw):
-        from .impl.neighbor_sampler import LayerNeighborSampler
+        from ..impl.neighbor_sampler import LayerNeighborSampler
         return LayerNeighborSampler(self, graph, fanouts, **kw)
 
     def sample_in_subgraph(self, graph):
-        from .impl.in_subgraph_sampler import InSubgraphSampler
+        from ..impl.in_subgraph_sampler import InSubgraphSampler
         return InSubgraphSampler(self, graph)
 
     def sample_uniform_negative(self, graph, negative_ratio):
-        from .impl.negative_sampler import UniformNegativeSampler
+        from ..impl.negative_sampler import UniformNegativeSampler
         return UniformNegativeSampler(self, graph, negative_ratio)
 
     def fetch_feature(self, feature_store, node_feature_keys=None, edge_feature_keys=None, **kw):
@@ -52,7 +52,7 @@ class _Stage:
 
     def exclude_seed_edges(self, include_reverse_edges=False, reverse_etypes_mapping=None, asynchronous=False):
         from functools import partial
-        from .utils import exclude_seed_edges
+        from ..utils import exclude_seed_edges
         return MiniBatchTransformer(self, partial(exclude_seed_edges, include_reverse_edges=include_reverse_edges,
                                                   reverse_etypes_mapping=reverse_etypes_mapping))
 
@@ -78,7 +78,7 @@ class SubgraphSampler(MiniBatchTransformer):
 
     @staticmethod
     def _seeds_preprocess(minibatch):
-        from .utils import unique_and_compact
+        from ..utils import unique_and_compact
         seeds = minibatch.seeds
         if isinstance(seeds, dict):
             nodes = {}
@@ -212,7 +212,7 @@ class DataLoader:
         self.prefetch = prefetch
         if max_uva_threads:
             try:
-                from ..ops.cuda_struct import set_max_uva_threads
+                from ...ops.cuda_struct import set_max_uva_threads
                 set_max_uva_threads(max_uva_threads)
             except Exception:  # noqa: BLE001
                 pass

@@ -54,17 +54,29 @@ class SampledSubgraphImpl:
         return all(t.is_pinned() for t in self._tensors())
 
     def to_pyg(self, x):
-        """(x_src, x_dst) pair and ``edge_index`` [2, E] of this layer in PyG convention (reference sampled_subgraph.py
-        to_pyg): works without torch_geometric installed, the caller feeds them to any PyG conv."""
-        if isinstance(self.sampled_csc, dict):
-            raise NotImplementedError("to_pyg supports homogeneous sampled subgraphs")
-        csc = self.sampled_csc
-        deg = (csc.indptr[1:] - csc.indptr[:-1]).long()
-        dst = torch.repeat_interleave(torch.arange(deg.shape[0], device=deg.device), deg)
-        edge_index = torch.stack([csc.indices.long(), dst])
-        n_dst = deg.shape[0]
-        n_src = int(self.original_row_node_ids.shape[0]) if self.original_row_node_ids is not None else int(x.shape[0])
-        return (x, x[:n_dst]), edge_index, (n_src, n_dst)
+        """This layer in PyG convention (reference sampled_subgraph.py:286): ``x`` is the source-side feature tensor (or
+        ``{ntype: tensor}`` for heterogeneous layers). Returns :class:`PyGLayerData` /
+        :class:`PyGLayerHeteroData` with x = (source features, destination features = first ``num_dst`` rows),
+        ``edge_index`` [2, E] and ``size`` = (num src, num dst). Works without torch_geometric installed."""
+        from .base import etype_str_to_tuple
+        from .compat import PyGLayerData, PyGLayerHeteroData
+
+        def one(csc):
+            deg = (csc.indptr[1:] - csc.indptr[:-1]).long()
+            dst = torch.repeat_interleave(torch.arange(deg.shape[0], device=deg.device), deg)
+            return torch.stack([csc.indices.long(), dst]), int(deg.shape[0])
+
+        if not isinstance(self.sampled_csc, dict):
+            edge_index, n_dst = one(self.sampled_csc)
+            return PyGLayerData((x, x[:n_dst]), edge_index, (int(x.shape[0]), n_dst))
+        x_dst, edge_index, sizes = {}, {}, {}
+        for etype, csc in self.sampled_csc.items():
+            ei, n_dst = one(csc)
+            s_t, _, d_t = etype_str_to_tuple(etype)
+            x_dst[d_t] = x[d_t][:n_dst]
+            edge_index[etype] = ei
+            sizes[etype] = (int(x[s_t].shape[0]), n_dst)
+        return PyGLayerHeteroData((x, x_dst), edge_index, sizes)
 
     def exclude_edges(self, edges, assume_num_node_within_int32=True):
         """Remove the given (src, dst) pairs (original ids) from the sampled block."""
