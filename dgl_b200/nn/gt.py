@@ -13,6 +13,11 @@ __all__ = ["BiasedMHA", "BiasedMultiheadAttention", "GraphormerLayer", "EGTLayer
            "SpatialEncoder", "SpatialEncoder3d", "LapPosEncoder"]
 
 
+def gaussian(x, mean, std):
+    """Gaussian basis function ``N(x; mean, std)`` (reference gt/spatial_encoder.py:8, constant pi = 3.14159)."""
+    return torch.exp(-0.5 * ((x - mean) / std) ** 2) / ((2 * 3.14159) ** 0.5 * std)
+
+
 class BiasedMHA(nn.Module):
     def __init__(self, feat_size, num_heads, bias=True, attn_bias_type="add", attn_drop=0.1):
         super().__init__()
