@@ -29,7 +29,7 @@ _LAZY = {"sampling", "dataloading", "graphbolt", "sparse", "distributed", "optim
          "utils", "multiprocessing", "cuda", "geometry", "partition", "traversal", "propagate", "storages",
          "distgnn", "mpops", "generators", "merge", "homophily", "label_informativeness", "logging", "global_config",
          "init", "random", "frame", "view", "core", "convert", "batch", "subgraph", "readout", "contrib", "graph_index",
-         "heterograph_index", "heterograph", "base", "transforms"}
+         "heterograph_index", "heterograph", "base", "transforms", "udf", "ndarray", "container"}
 
 
 def __getattr__(name):

@@ -14,6 +14,34 @@ import torch
 from .base import DGLError
 
 
+class Scheme(tuple):
+    """(shape, dtype) of one column: ``shape`` excludes the row dimension (reference frame.py:125). A plain tuple
+    subclass so it compares equal to the ``(shape, dtype)`` pairs of :attr:`Frame.schemes` and pickles by value."""
+    __slots__ = ()
+
+    def __new__(cls, shape, dtype):
+        return super().__new__(cls, (tuple(shape), dtype))
+
+    @property
+    def shape(self):
+        return self[0]
+
+    @property
+    def dtype(self):
+        return self[1]
+
+    def __reduce__(self):
+        return Scheme, (self[0], self[1])
+
+    def __repr__(self):
+        return f"Scheme(shape={self[0]}, dtype={self[1]})"
+
+
+def infer_scheme(tensor):
+    """Scheme of the column a tensor would make."""
+    return Scheme(tuple(tensor.shape[1:]), tensor.dtype)
+
+
 class LazyFeature:
     """Placeholder for a feature fetched later by the DataLoader
     (reference: python/dgl/frame.py:class LazyFeature)."""
@@ -226,7 +254,7 @@ class Frame(MutableMapping):
 
     @property
     def schemes(self):
-        return {k: (tuple(c.shape[1:]), c.dtype) for k, c in self._columns.items()
+        return {k: Scheme(tuple(c.shape[1:]), c.dtype) for k, c in self._columns.items()
                 if not isinstance(c.storage, LazyFeature)}
 
     def set_initializer(self, initializer, column=None):

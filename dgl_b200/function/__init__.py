@@ -9,8 +9,16 @@ from __future__ import annotations
 import sys
 from itertools import product
 
-__all__ = ["BuiltinFunction", "MessageFunction", "ReduceFunction", "BinaryMessageFunction", "CopyMessageFunction",
+__all__ = ["TargetCode", "BuiltinFunction", "MessageFunction", "ReduceFunction", "BinaryMessageFunction", "CopyMessageFunction",
            "SimpleReduceFunction", "copy_u", "copy_e", "copy_src", "copy_edge", "sum", "max", "min", "mean"]
+
+
+class TargetCode:
+    """Numeric codes of the three message-passing targets (reference function/base.py:7)."""
+    SRC = 0
+    DST = 1
+    EDGE = 2
+    CODE2STR = {0: "u", 1: "v", 2: "e"}
 
 
 class BuiltinFunction:

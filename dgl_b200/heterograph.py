@@ -1183,6 +1183,70 @@ def combine_names(names, ids=None):
     return "+".join(selected)
 
 
+def make_canonical_etypes(etypes, ntypes, metagraph):
+    """[(srctype, etype, dsttype)] from parallel type-name lists and a metagraph whose edge i connects the node-type
+    ids of relation i (reference heterograph.py:6407)."""
+    if len(etypes) != metagraph.num_edges():
+        raise DGLError(f"Length of edge type list must match the number of edges in the metagraph. "
+                       f"{len(etypes)} vs {metagraph.num_edges()}")
+    if len(ntypes) != metagraph.num_nodes():
+        raise DGLError(f"Length of nodes type list must match the number of nodes in the metagraph. "
+                       f"{len(ntypes)} vs {metagraph.num_nodes()}")
+    if len(etypes) == 1 and len(ntypes) == 1:
+        return [(ntypes[0], etypes[0], ntypes[0])]
+    out = []
+    for i, name in enumerate(etypes):
+        s, d = metagraph.find_edge(i)
+        out.append((ntypes[int(s)], name, ntypes[int(d)]))
+    return out
+
+
+def find_src_dst_ntypes(ntypes, metagraph):
+    """({src type: id}, {dst type: id}) when no node type is both a source and a destination (uni-bipartite
+    metagraph), else ``None``. Isolated types count as sources (reference heterograph.py:6448)."""
+    src, dst = set(), set()
+    for i in range(metagraph.num_edges()):
+        s, d = metagraph.find_edge(i)
+        src.add(int(s))
+        dst.add(int(d))
+    if src & dst:
+        return None
+    src |= set(range(metagraph.num_nodes())) - dst
+    return {ntypes[t]: t for t in sorted(src)}, {ntypes[t]: t for t in sorted(dst)}
+
+
+def pad_tuple(tup, length, pad_val=None):
+    """Tuple of exactly ``length`` (non-tuples are wrapped first); ``None`` when it is already longer."""
+    if not isinstance(tup, tuple):
+        tup = (tup,)
+    if len(tup) > length:
+        return None
+    return tup + (pad_val,) * (length - len(tup))
+
+
+def combine_frames(frames, ids, col_names=None):
+    """Concatenate ``frames[i] for i in ids`` over their common columns (optionally restricted to ``col_names``);
+    columns whose schemes disagree raise, no common column gives ``None`` (reference heterograph.py:6561)."""
+    from .frame import Frame
+    schemes = None
+    for i in ids:
+        fr = frames[i]
+        if fr.num_rows == 0:
+            continue
+        if schemes is None:
+            schemes = dict(fr.schemes) if col_names is None else {k: fr.schemes[k] for k in col_names}
+            continue
+        for key, scheme in list(schemes.items()):
+            if key not in fr.schemes:
+                del schemes[key]
+            elif fr.schemes[key] != scheme:
+                raise DGLError(f"Cannot concatenate column {key} with shape {scheme} and shape {fr.schemes[key]}")
+    if not schemes:
+        return None
+    cols = {k: torch.cat([frames[i][k] for i in ids if frames[i].num_rows > 0], 0) for k in schemes}
+    return Frame(cols)
+
+
 def reduce_dict_data(frames, reducer, order=None):
     """Merge per-relation results for one dst type (reference heterograph.py:6500+)."""
     if len(frames) == 1 and reducer != "stack":

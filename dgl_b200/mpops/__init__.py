@@ -14,3 +14,6 @@ def fused_gat(g, feat_src, el, er, slope=0.2):
     e = F.leaky_relu(ops.u_add_v(g, el, er), slope)
     a = edge_softmax(g, e)
     return ops.u_mul_e_sum(g, feat_src, a)
+
+from .edgewise import *  # noqa: F401,F403,E402
+from . import edgewise  # noqa: F401,E402

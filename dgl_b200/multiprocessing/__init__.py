@@ -33,3 +33,43 @@ def shared_tensor(shape, dtype=torch.float32):
 
 
 from torch.multiprocessing import *  # noqa: F401,F403,E402
+
+
+def thread_wrapped_func(func):
+    """Run a process entry point on a fresh thread and hand back its result (reference multiprocessing/pytorch.py:13).
+    OpenMP runtimes keep per-thread state that does not survive ``fork``; entering through a new thread gives the
+    child a clean OpenMP team. Exceptions are re-raised in the caller with the worker's traceback as message."""
+    import functools
+    import threading
+    import traceback
+
+    @functools.wraps(func)
+    def decorated(*args, **kwargs):
+        box = {}
+
+        def run():
+            try:
+                box["res"] = func(*args, **kwargs)
+            except Exception as exc:  # noqa: BLE001
+                box["exc"], box["trace"] = exc, traceback.format_exc()
+
+        t = threading.Thread(target=run)
+        t.start()
+        t.join()
+        if "exc" in box:
+            try:
+                raise box["exc"].__class__(box["trace"])
+            except TypeError:
+                raise RuntimeError(box["trace"]) from box["exc"]
+        return box.get("res")
+
+    return decorated
+
+
+class Process(torch.multiprocessing.Process):
+    """``torch.multiprocessing.Process`` whose target is wrapped by :func:`thread_wrapped_func`."""
+
+    def __init__(self, group=None, target=None, name=None, args=(), kwargs=None, *, daemon=None):
+        if target is not None:
+            target = thread_wrapped_func(target)
+        super().__init__(group, target, name, args, kwargs or {}, daemon=daemon)

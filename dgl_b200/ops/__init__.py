@@ -178,3 +178,15 @@ for _l, _r in product("uve", "uve"):
         _n, _f = _gen_sddmm(_l, _op, _r)
         setattr(_mod, _n, _f)
         __all__.append(_n)
+
+
+def reshape_lhs_rhs(lhs_data, rhs_data):
+    """Insert singleton feature dims after the row dim so both operands have the same rank, e.g. (N, 3, 1) and
+    (E, 5, 3, 4) -> (N, 1, 3, 1) and (E, 5, 3, 4); broadcasting then lines up from the right
+    (reference ops/spmm.py:13, ops/sddmm.py)."""
+    ls, rs = tuple(lhs_data.shape), tuple(rhs_data.shape)
+    if len(ls) != len(rs):
+        nd = max(len(ls), len(rs))
+        lhs_data = lhs_data.reshape((ls[0],) + (1,) * (nd - len(ls)) + ls[1:])
+        rhs_data = rhs_data.reshape((rs[0],) + (1,) * (nd - len(rs)) + rs[1:])
+    return lhs_data, rhs_data
