@@ -192,3 +192,14 @@ def connect_to_server(ip_config, num_servers=1, max_queue_size=None, net_type="s
 
 def get_default_client():
     return _DEFAULT_CLIENT[0]
+
+
+def __getattr__(name):
+    # the class-based API of the reference (Request/Response, send_request, remote_call, context accessors ...)
+    # lives in rpc_api.py and is reachable from this namespace as in the reference's single rpc.py
+    if name.startswith("__"):
+        raise AttributeError(name)
+    from . import rpc_api
+    if hasattr(rpc_api, name):
+        return getattr(rpc_api, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
