@@ -283,3 +283,59 @@ def load_labels_v2(filename):
 def check_pytorch():
     """Datasets that need torch ops in the reference (MovieLens) guard on the backend here."""
     return True
+
+
+# ---- superpixel graph construction (superpixel.py:15-75) ----------------------------------------------------------
+def sigma(dists, kth=8):
+    """Per-row kernel width: mean of the ``kth`` smallest non-self distances (1 for graphs smaller than ``kth``)."""
+    n = dists.shape[0]
+    if kth > n:
+        s = np.ones((n, 1))
+    else:
+        s = np.partition(dists, kth, axis=-1)[:, :kth + 1].sum(axis=1, keepdims=True) / kth
+    return s + 1e-8
+
+
+def compute_adjacency_matrix_images(coord, feat, use_feat=True):
+    """Dense Gaussian affinity between superpixels from their coordinates (and mean colours): symmetric, zero
+    diagonal."""
+    from scipy.spatial.distance import cdist
+    coord = np.asarray(coord).reshape(-1, 2)
+    c = cdist(coord, coord)
+    expo = -((c / sigma(c)) ** 2)
+    if use_feat:
+        f = cdist(feat, feat)
+        expo = expo - (f / sigma(f)) ** 2
+    A = np.exp(expo)
+    A = 0.5 * (A + A.T)
+    np.fill_diagonal(A, 0)
+    return A
+
+
+def compute_edges_list(A, kth=9):
+    """(neighbour ids [N, kth-1], affinities) of the ``kth - 1`` strongest non-self affinities per row; graphs with at
+    most ``kth`` nodes become fully connected."""
+    n = A.shape[0]
+    if n > kth:
+        cut = n - (kth - 1)
+        idx = np.argpartition(A, cut - 1, axis=-1)[:, cut:]
+        return idx, np.take_along_axis(A, idx, axis=-1)
+    ids = np.tile(np.arange(n), n).reshape(n, n)
+    if n == 1:
+        return ids, A
+    off = ids != np.arange(n)[:, None]
+    return ids[off].reshape(n, -1), A[off].reshape(n, -1)
+
+
+class SuperPixelDataset:
+    """Name-dispatching base of the superpixel image-graph datasets (MNIST / CIFAR10 superpixels)."""
+
+    def __new__(cls, raw_dir=None, name="MNIST", split="train", use_feature=False, **kwargs):
+        from . import extra
+        table = {"MNIST": extra.MNISTSuperPixelDataset, "CIFAR10": extra.CIFAR10SuperPixelDataset}
+        if name not in table:
+            raise DGLError(f"Unknown superpixel dataset {name!r}; expected MNIST or CIFAR10")
+        return table[name](raw_dir=raw_dir, split=split, use_feature=use_feature, **kwargs)
+
+
+__all__ += ["sigma", "compute_adjacency_matrix_images", "compute_edges_list", "SuperPixelDataset"]

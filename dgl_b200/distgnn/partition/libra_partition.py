@@ -1,0 +1,6 @@
+"""Reference module path ``dgl.distgnn.partition.libra_partition``: the names below are implemented in
+dgl_b200.distgnn, dgl_b200.partition, dgl_b200 ... and re-exported lazily."""
+from ..._pathshim import reexport
+
+__getattr__, __dir__, __all__ = reexport(__name__, ['dgl_b200.distgnn', 'dgl_b200.partition', 'dgl_b200'],
+                                          ['libra_partition', 'partition_graph'])

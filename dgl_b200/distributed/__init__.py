@@ -41,3 +41,17 @@ class EdgeCollator(NodeCollator):
         if not hasattr(graph_sampler, "sample_blocks_for_edges") and (negative_sampler is not None or exclude is not None):
             self.graph_sampler = as_edge_prediction_sampler(graph_sampler, exclude=exclude, reverse_eids=reverse_eids,
                                                             reverse_etypes=reverse_etypes, negative_sampler=negative_sampler)
+
+from . import compat, rpc_api  # noqa: F401,E402
+from .compat import *  # noqa: F401,F403,E402
+from .rpc_api import Request, Response  # noqa: F401,E402
+
+
+_COMPAT_LAZY = ("SubgraphResponse", "FindEdgeResponse", "InDegreeResponse", "OutDegreeResponse", "SamplingRequest",
+                "SamplingRequestEtype", "InSubgraphRequest", "EdgesRequest", "InDegreeRequest", "OutDegreeRequest")
+
+
+def __getattr__(name):
+    if name in _COMPAT_LAZY:
+        return getattr(compat, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

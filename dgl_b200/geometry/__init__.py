@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import torch
 
-from .base import DGLError
+from ..base import DGLError
 
 __all__ = ["farthest_point_sampler", "neighbor_matching"]
 
@@ -14,14 +14,14 @@ def farthest_point_sampler(pos, npoints, start_idx=None):
     B, N, C = pos.shape
     dev = pos.device
     if pos.is_cuda and C <= 16 and pos.dtype in (torch.float32, torch.float16, torch.bfloat16, torch.float64):
-        from ._graph_kernels import fps
+        from .._graph_kernels import fps
         start = (torch.randint(0, N, (B,), device=dev) if start_idx is None
                  else torch.full((B,), int(start_idx), device=dev, dtype=torch.long))
         return fps(pos, int(npoints), start)   # one CTA per cloud, whole loop in one launch
     if dev.type == "cpu" and pos.dtype in (torch.float32, torch.float64):
         # host clouds: native loop, threads over clouds (or over points of a single large cloud) — csrc/cpu/spatial.cc
-        from ._native import loader
-        from .base import dtype_code
+        from .._native import loader
+        from ..base import dtype_code
         start = (torch.randint(0, N, (B,)) if start_idx is None else torch.full((B,), int(start_idx), dtype=torch.long))
         out = torch.empty((B, npoints), dtype=torch.long)
         p = pos.contiguous()
@@ -50,21 +50,21 @@ def neighbor_matching(graph, e_weights=None, relabel_idx=True):
     n = graph.num_nodes()
     if graph.device.type == "cuda":
         # handshake matching rounds on the symmetrised adjacency (csrc/cuda/graph_kernels.cu match_*_kernel)
-        from . import random as dgl_random
-        from ._graph_kernels import neighbor_matching as _nm
-        from .transforms.functional import to_bidirected_coo
+        from .. import random as dgl_random
+        from .._graph_kernels import neighbor_matching as _nm
+        from ..transforms.functional import to_bidirected_coo
         su, sv, sw = to_bidirected_coo(graph, e_weights)
-        from .graph_index import coo_to_csr
+        from ..graph_index import coo_to_csr
         indptr, indices, eids = coo_to_csr(su, sv, n, graph.idtype)
         res = _nm(indptr, indices, eids, sw, n, dgl_random.next_seed())
         if relabel_idx:
             res = torch.unique(res, return_inverse=True)[1].to(graph.idtype)
         return res
     # host graphs: one native greedy sweep over a random node order (csrc/cpu/spatial.cc)
-    from ._native import loader
-    from .base import id_code
-    from .graph_index import coo_to_csr
-    from .transforms.functional import to_bidirected_coo
+    from .._native import loader
+    from ..base import id_code
+    from ..graph_index import coo_to_csr
+    from ..transforms.functional import to_bidirected_coo
     su, sv, sw = to_bidirected_coo(graph, e_weights)
     indptr, indices, eids = coo_to_csr(su, sv, n, graph.idtype)
     if sw is not None:

@@ -290,6 +290,21 @@ class OnDiskTaskData(dict):
         self.__dict__ = self
 
 
+class ExtraMetaData(dict):
+    """Base of the metadata models: unknown keys are kept and grouped under ``extra_fields`` (reference
+    impl/ondisk_metadata.py:24)."""
+
+    _known = ()
+
+    def __init__(self, **kw):
+        extra = dict(kw.pop("extra_fields", None) or {})
+        for k in list(kw):
+            if self._known and k not in self._known:
+                extra[k] = kw.pop(k)
+        super().__init__(extra_fields=extra, **kw)
+        self.__dict__ = self
+
+
 class OnDiskMetaData(dict):
     """Top-level model of ``metadata.yaml`` (dataset_name, graph_topology, feature_data, tasks, include_original_edge_id)."""
 

@@ -15,7 +15,7 @@ CuGraphRelGraphConv = RelGraphConv
 from .extra import GroupRevRes, TWIRLSUnfoldingAndAttention  # noqa: E402
 from .parts import (AX, MLP, Attention, CuGraphBaseConv, D_power_bias_X, D_power_X, InvertibleCheckpoint,  # noqa: E402,F401
                     Propagate, PropagateNoPrecond, normalized_AX)
-from .misc import (DGNConvTower, PNAConvTower, RadialPooling, aggregate_dir_av, aggregate_dir_dx, aggregate_max,  # noqa: E402,F401
+from .misc import (DGNConvTower, PNAConvTower, RadialPooling, msg_func, reduce_func, aggregate_dir_av, aggregate_dir_dx, aggregate_max,  # noqa: E402,F401
                    aggregate_mean, aggregate_min, aggregate_moment_3, aggregate_moment_4, aggregate_moment_5,
                    aggregate_std, aggregate_sum, aggregate_var, scale_amplification, scale_attenuation,
                    scale_identity)

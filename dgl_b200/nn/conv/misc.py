@@ -345,6 +345,12 @@ def msg_func(edges):
     return {"ev": edges.data["he"], "hv": edges.src["hv"], "uv": edges.src["hv"] * 0 + edges.dst["hv"]}
 
 
+def reduce_func(nodes):
+    """UDF counterpart of the AtomicConv aggregation: sum the per-edge radial messages of each node (the layer itself
+    uses the fused ``u_mul_e`` + ``sum`` kernel)."""
+    return {"hv_new": nodes.mailbox["m"].sum(1)}
+
+
 class RadialPooling(nn.Module):
     def __init__(self, interaction_cutoffs, rbf_kernel_means, rbf_kernel_scaling):
         super().__init__()

@@ -13,7 +13,8 @@ import torch.nn.functional as F
 from ..base import EID, NID
 from ..subgraph import khop_in_subgraph, node_subgraph
 
-__all__ = ["GNNExplainer", "HeteroGNNExplainer", "PGExplainer", "HeteroPGExplainer", "SubgraphX", "HeteroSubgraphX"]
+__all__ = ["GNNExplainer", "HeteroGNNExplainer", "PGExplainer", "HeteroPGExplainer", "SubgraphX", "HeteroSubgraphX",
+           "MCTSNode"]
 
 
 class GNNExplainer(nn.Module):
@@ -332,7 +333,7 @@ class HeteroPGExplainer(PGExplainer):
         return (probs, hetero_edge_mask)
 
 
-class _MCTSNode:
+class MCTSNode:
     def __init__(self, nodes):
         self.nodes = nodes
         self.num_visit = 0
@@ -410,7 +411,7 @@ class SubgraphX(nn.Module):
             new_nodes = subg.ndata[NID][new_subg.ndata[NID].long()[keep]] if NID in subg.ndata else keep
             str_nodes = str(sorted(new_nodes.tolist()))
             if str_nodes not in self.mcts_node_maps:
-                child_mcts_node = _MCTSNode(new_nodes)
+                child_mcts_node = MCTSNode(new_nodes)
                 self.mcts_node_maps[str_nodes] = child_mcts_node
             else:
                 child_mcts_node = self.mcts_node_maps[str_nodes]
@@ -442,7 +443,7 @@ class SubgraphX(nn.Module):
         assert graph.num_nodes() > self.node_min, f"The number of nodes in the graph {graph.num_nodes()} should be bigger than {self.node_min}."
         self.graph, self.feat, self.target_class, self.kwargs = graph, feat, target_class, kwargs
         self.mcts_node_maps = dict()
-        root = _MCTSNode(graph.nodes())
+        root = MCTSNode(graph.nodes())
         self.mcts_node_maps[str(root)] = root
         for _ in range(self.num_rollouts):
             self.mcts_rollout(root)

@@ -1,0 +1,6 @@
+"""Reference module path ``dgl.sparse.broadcast``: the names below are implemented in
+dgl_b200.sparse, dgl_b200 ... and re-exported lazily."""
+from .._pathshim import reexport
+
+__getattr__, __dir__, __all__ = reexport(__name__, ['dgl_b200.sparse', 'dgl_b200'],
+                                          ['sp_add_v', 'sp_broadcast_v', 'sp_div_v', 'sp_mul_v', 'sp_sub_v'])
