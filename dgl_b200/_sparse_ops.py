@@ -336,3 +336,65 @@ def edge_softmax_backward(csc, out, grad_out, num_dst):
         else:
             lib.fn("dglb200_cpu_edge_softmax_bwd", "iipplpppl")(*args)
     return gs.reshape(out.shape)
+
+
+# ---- names of the reference's _sparse_ops.py that have no kernel of their own here ------------------------------------
+def to_dgl_nd(x):
+    """The reference converts a framework tensor to its NDArray before every kernel call; kernels here take tensors."""
+    return x
+
+
+def to_dgl_nd_for_write(x):
+    return x
+
+
+def get_typeid_by_target(gidx, etid, target):
+    """Node-type id of relation ``etid``'s source (target 0 / 'u') or destination (1 / 'v'); edges return ``etid``."""
+    src, dst = gidx.metagraph.find_edge(etid)
+    if target in (0, "u"):
+        return int(src)
+    if target in (1, "v"):
+        return int(dst)
+    return int(etid)
+
+
+def libra_vertex_cut(nc, node_degree, edgenum_unassigned, community_weights, u, v, w, out, N, N_e, dataset):
+    """Libra vertex-cut edge assignment written into ``out`` (reference _CAPI_DGLLibraVertexCut); see
+    ``dgl_b200.partition.libra_partition_assignment`` for the graph-level entry point."""
+    from ._native import loader
+    from .base import id_code
+    u64, v64 = u.long().contiguous(), v.long().contiguous()
+    res = out if out.dtype == torch.int64 and out.is_contiguous() else torch.empty(int(N_e), dtype=torch.int64)
+    loader.cpu_lib().fn("dglb200_cpu_libra_partition", "ippllip")(
+        id_code(torch.int64), u64.data_ptr(), v64.data_ptr(), int(N_e), int(N), int(nc), res.data_ptr())
+    if res is not out:
+        out.copy_(res.to(out.dtype))
+    community_weights.zero_()
+    community_weights += torch.bincount(res, minlength=int(nc)).to(community_weights.dtype)
+
+
+def libra2dgl_build_dict(a, b, indices, ldt_key, gdt_key, gdt_value, node_map, offset, nc, c, fsize, dataset):
+    """Per-partition global->local dictionary of the Libra conversion: returns the number of distinct vertices touched
+    by partition ``c``'s edges (``a`` -> ``b``) and fills ``ldt_key`` with them in first-seen order."""
+    verts = torch.unique(torch.cat([a, b]), sorted=False)
+    n = int(verts.shape[0])
+    ldt_key[:n] = verts.to(ldt_key.dtype)
+    return n
+
+
+def libra2dgl_build_adjlist(feat, gfeat, adj, inner_node, ldt, gdt_key, gdt_value, node_map, lr, lrtensor, num_nodes,
+                            nc, c, feat_size, labels, trainm, testm, valm, glabels, gtrainm, gtestm, gvalm, feat_shape):
+    """Gather the features / labels / masks of partition ``c``'s vertices (``ldt`` = their global ids) from the global
+    arrays into the partition-local ones."""
+    ids = ldt[:num_nodes].long()
+    gfeat[:num_nodes] = feat[ids]
+    glabels[:num_nodes] = labels[ids]
+    gtrainm[:num_nodes], gtestm[:num_nodes], gvalm[:num_nodes] = trainm[ids], testm[ids], valm[ids]
+
+
+def libra2dgl_set_lr(gdt_key, gdt_value, lrtensor, nc, Nn):
+    """Pick, for every replicated vertex, one owning partition uniformly among the partitions holding a copy."""
+    gen = torch.Generator().manual_seed(0)
+    counts = gdt_key[:Nn].long().clamp(min=1)
+    pick = (torch.rand(Nn, generator=gen) * counts).long()
+    lrtensor[:Nn] = gdt_value.view(Nn, -1)[torch.arange(Nn), pick].to(lrtensor.dtype)

@@ -265,8 +265,8 @@ def _service_classes():
             self.seed_nodes, self.fan_out, self.edge_dir, self.prob, self.replace = nodes, fan_out, edge_dir, prob, replace
 
         def process_request(self, server_state):
-            return _triple(dg._h_sample(server_state, (self.seed_nodes, self.fan_out, self.edge_dir, self.prob,
-                                                       self.replace)))
+            return _triple(dg._h_sample(server_state, (self.seed_nodes, self.fan_out, self.prob, self.replace,
+                                                       self.edge_dir)))
 
     class SamplingRequestEtype(SamplingRequest):
         def __init__(self, nodes, fan_out, edge_dir="in", prob=None, replace=False, etype_sorted=True,

@@ -766,3 +766,17 @@ class DistSparseAdam(DistSparseGradOptimizer):
 
 SparseAdagrad = DistSparseAdagrad
 SparseAdam = DistSparseAdam
+
+
+NodeDataView = EdgeDataView = _DistDataView          # reference names of the ndata / edata views
+HeteroNodeView = HeteroEdgeView = _DistTypeView      # reference names of g.nodes[...] / g.edges[...] views
+
+
+def __getattr__(name):
+    # class-based request / response types of this service live in messages.py (lazy: avoids an import cycle)
+    if name.startswith("__"):
+        raise AttributeError(name)
+    from . import messages
+    if name in messages.__all__:
+        return getattr(messages, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

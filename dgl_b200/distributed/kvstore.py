@@ -224,3 +224,13 @@ class KVClient:
             raise DGLError("push handlers must be registered on the servers (KVServer.register_push_handler)")
         for st in self._dg._CTX.local_servers:
             st.handlers[name] = func
+
+
+def __getattr__(name):
+    # class-based request / response types of this service live in messages.py (lazy: avoids an import cycle)
+    if name.startswith("__"):
+        raise AttributeError(name)
+    from . import messages
+    if name in messages.__all__:
+        return getattr(messages, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -32,3 +32,13 @@ def get_global_rank():
 
 def get_num_trainers():
     return _ROLE["num"]
+
+
+def __getattr__(name):
+    # class-based request / response types of this service live in messages.py (lazy: avoids an import cycle)
+    if name.startswith("__"):
+        raise AttributeError(name)
+    from . import messages
+    if name in messages.__all__:
+        return getattr(messages, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -111,3 +111,15 @@ class TemporalNeighborSampler(SubgraphSampler):
 
 class TemporalLayerNeighborSampler(TemporalNeighborSampler):
     """Layer-wise (LABOR-style) variant; the temporal constraint dominates, so it shares the per-seed sampler."""
+
+
+_COMPAT_NAMES = ("NeighborSamplerImpl", "SamplePerLayer", "CompactPerLayer", "FetchInsubgraphData",
+                 "FetchCachedInsubgraphData", "CombineCachedAndFetchedInSubgraph")
+
+
+def __getattr__(name):
+    # per-stage classes of the reference's split pipeline are defined in graphbolt/compat.py
+    if name in _COMPAT_NAMES:
+        from .. import compat
+        return getattr(compat, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

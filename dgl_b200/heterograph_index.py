@@ -14,7 +14,7 @@ from .graph_index import UnitGraph
 
 __all__ = ["HeteroGraphIndex", "HeteroSubgraphIndex", "create_metagraph_index", "create_unitgraph_from_coo",
            "create_unitgraph_from_csr", "create_heterograph_from_relations", "create_heterograph_from_shared_memory",
-           "joint_union", "disjoint_union", "disjoint_partition", "slice_gidx"]
+           "joint_union", "disjoint_union", "disjoint_partition", "slice_gidx", "FlattenedHeteroGraph", "HeteroPickleStates"]
 
 
 class _MetaGraph:
@@ -357,3 +357,55 @@ def slice_gidx(graph, num_nodes, start_nid, num_edges, start_eid):
              for i, t in enumerate(g.ntypes)}
     sg = g.subgraph(nodes, store_ids=False)
     return HeteroGraphIndex(sg)
+
+
+class FlattenedHeteroGraph:
+    """Result of flattening several relations into one homogeneous relation (reference FlattenedHeteroGraph): the
+    merged graph plus, per node / edge, the type it came from and its id within that type."""
+
+    def __init__(self, graph, induced_srctype, induced_srctype_set, induced_srcid, induced_etype, induced_etype_set,
+                 induced_eid, induced_dsttype, induced_dsttype_set, induced_dstid):
+        self.graph = graph
+        self.induced_srctype, self.induced_srctype_set, self.induced_srcid = induced_srctype, induced_srctype_set, induced_srcid
+        self.induced_etype, self.induced_etype_set, self.induced_eid = induced_etype, induced_etype_set, induced_eid
+        self.induced_dsttype, self.induced_dsttype_set, self.induced_dstid = induced_dsttype, induced_dsttype_set, induced_dstid
+
+
+class HeteroPickleStates:
+    """Picklable structure snapshot of a heterograph index: version, (metagraph pairs, node counts) and the COO arrays
+    of every relation (reference HeteroPickleStates; the features are pickled by the frames, not here)."""
+
+    def __init__(self, version=2, meta=None, arrays=None):
+        self._version, self._meta, self._arrays = version, meta, list(arrays or [])
+
+    @staticmethod
+    def from_index(gidx):
+        g = gidx.graph
+        meta = (gidx.metagraph._pairs, [g.num_nodes(t) for t in g.ntypes], list(g.ntypes), list(g.canonical_etypes))
+        arrays = [t for ug in g._graphs for t in ug.coo()]
+        return HeteroPickleStates(2, meta, arrays)
+
+    def to_index(self):
+        pairs, counts, ntypes, cet = self._meta
+        rels = [UnitGraph.from_coo(counts[s], counts[d], self._arrays[2 * i], self._arrays[2 * i + 1])
+                for i, (s, d) in enumerate(pairs)]
+        return create_heterograph_from_relations(_MetaGraph(len(ntypes), pairs), rels, counts, ntypes,
+                                                 [tuple(c) for c in cet])
+
+    @property
+    def version(self):
+        return self._version
+
+    @property
+    def meta(self):
+        return self._meta
+
+    @property
+    def arrays(self):
+        return self._arrays
+
+    def __getstate__(self):
+        return self._version, self._meta, self._arrays
+
+    def __setstate__(self, state):
+        self._version, self._meta, self._arrays = state

@@ -95,3 +95,52 @@ def test_kvstore_handlers_and_misc_functions():
     dd.finalize_worker()
     dd.join_finalize_worker()
     assert dd.MpCommand.FINALIZE_POOL == 6
+
+
+def test_message_classes_run_the_server_handlers():
+    """Request objects executed directly against a partition's ServerState (no network needed)."""
+    from dgl_b200.distributed import dist_graph, kvstore, role
+    from dgl_b200.distributed.rpc_api import get_service_property
+    g = dgl.rand_graph(300, 1500)
+    g.ndata["feat"] = torch.randn(300, 4)
+    g.edata["w"] = torch.rand(1500)
+    with tempfile.TemporaryDirectory() as d:
+        dd.partition_graph(g, "mg", 2, d)
+        st = dist_graph.ServerState(os.path.join(d, "mg.json"), 0)
+        lo = st.nid_start
+        ids = torch.arange(lo, lo + 3)
+        res = kvstore.PullRequest("node~_N~feat", ids).process_request(st)
+        assert res.server_id == 0 and torch.equal(res.data_tensor, st.kv["node~_N~feat"][:3])
+        assert kvstore.PushRequest("node~_N~feat", ids, torch.ones(3, 4)).process_request(st) is None
+        assert torch.equal(st.kv["node~_N~feat"][:3], torch.ones(3, 4))
+        kvstore.RegisterPushHandlerRequest("node~_N~feat", lambda t, loc, x: t.index_add_(0, loc, x)).process_request(st)
+        kvstore.PushRequest("node~_N~feat", ids, torch.ones(3, 4)).process_request(st)
+        assert torch.equal(st.kv["node~_N~feat"][:3], torch.full((3, 4), 2.0))
+        assert kvstore.InitDataRequest("node~_N~acc", (300, 2), torch.float32, "node:_N").process_request(st).msg == "ok"
+        assert kvstore.GetPartShapeRequest("node~_N~acc").process_request(st).shape == (st.n_inner, 2)
+        meta = kvstore.GetSharedDataRequest().process_request(st).meta
+        assert meta["node~_N~acc"][2] == "node:_N" and "node~_N~feat" in meta
+        assert kvstore.CountLocalNonzeroRequest("node~_N~acc").process_request(st).num_local_nonzero == 0
+        kvstore.DeleteDataRequest("node~_N~acc").process_request(st)
+        assert "node~_N~acc" not in st.kv
+        assert kvstore.BarrierRequest().process_request(st).msg == "ok"
+        kvstore.SendMetaToBackupRequest("x", torch.float32, (1,), "node:_N").process_request(st)
+        role.RegisterRoleRequest(3, 0, "trainer").process_request(st)
+        role.RegisterRoleRequest(4, 1, "trainer").process_request(st)
+        assert role.GetRoleRequest().process_request(st).role == {"trainer": [(3, 0), (4, 1)]}
+        assert dist_graph.InitGraphRequest("mg").process_request(st).msg == "mg"
+        with pytest.raises(RuntimeError):
+            dist_graph.InitGraphRequest("other").process_request(st)
+        assert dist_graph.QueryIfUseGraphBoltRequest().process_request(st).use_graphbolt is False
+        dist_graph.AddEdgeAttributeFromSharedMemRequest("w").process_request(st)
+        assert st.g.edata["w"].shape[0] == st.g.num_edges()
+        sub = dd.SamplingRequest(ids, 2).process_request(st)
+        assert sub.global_dst.numel() <= 6 and torch.isin(sub.global_dst, ids).all()
+        ins = dd.InSubgraphRequest(ids).process_request(st)
+        assert torch.isin(ins.global_dst, ids).all()
+        e = dd.EdgesRequest(torch.tensor([st.eid_start]), 5).process_request(st)
+        assert e.order_id == 5 and e.global_src.numel() == 1
+        # every class is registered as a service with a response class (or None for one-way pushes)
+        assert get_service_property(kvstore.PullRequest("a", ids).service_id) == (kvstore.PullRequest, kvstore.PullResponse)
+        assert get_service_property(kvstore.PushRequest("a", ids, ids).service_id)[1] is None
+    assert dist_graph.NodeDataView is dist_graph.EdgeDataView

@@ -180,3 +180,24 @@ def test_small_module_helpers(hg):
     assert "UserWarning" in dgl.base.dgl_warning_format("hi", UserWarning, "f.py", 1)
     s, d = dgl.homophily.get_long_edges(dgl.graph(([0], [1]), idtype=torch.int32))
     assert s.dtype == torch.int64 and d.tolist() == [1]
+
+
+def test_pickle_states_and_sparse_ops_leftovers(hg):
+    st = pickle.loads(pickle.dumps(H.HeteroPickleStates.from_index(hg._graph)))
+    assert st.version == 2 and len(st.arrays) == 4
+    back = st.to_index().graph
+    assert back.canonical_etypes == hg.canonical_etypes and back.num_edges() == hg.num_edges()
+    assert back.num_nodes("b") == hg.num_nodes("b")
+    f = H.FlattenedHeteroGraph(hg, *range(9))
+    assert f.induced_srctype == 0 and f.induced_dstid == 8
+    from dgl_b200 import _sparse_ops as S
+    assert S.get_typeid_by_target(hg._graph, 0, "u") == 0 and S.get_typeid_by_target(hg._graph, 0, "v") == 1
+    assert S.get_typeid_by_target(hg._graph, 1, "e") == 1 and S.to_dgl_nd(3) == 3 and S.to_dgl_nd_for_write(4) == 4
+    g = dgl.rand_graph(30, 90)
+    u, v = g.edges()
+    out, cw = torch.zeros(90, dtype=torch.int64), torch.zeros(3)
+    S.libra_vertex_cut(3, None, None, cw, u, v, None, out, 30, 90, "x")
+    assert int(cw.sum()) == 90 and set(out.tolist()) <= {0, 1, 2} and cw.max() - cw.min() <= 3
+    key = torch.zeros(10, dtype=torch.int64)
+    assert S.libra2dgl_build_dict(torch.tensor([5, 5, 7]), torch.tensor([7, 9, 5]), None, key, None, None, None, 0, 3, 0, 1, "x") == 3
+    assert sorted(key[:3].tolist()) == [5, 7, 9]
