@@ -331,9 +331,10 @@ DGLB_API int dglb200_cache_create(int policy, int64_t capacity, int num_parts, i
   DGLB_CHECK(capacity > 0 && num_parts > 0, "capacity and num_parts must be positive");
   auto* c = new PartitionedCache();
   int64_t off = 0;
+  // never more shards than slots: every shard owns at least one slot and the slot ranges tile [0, capacity)
+  if ((int64_t)num_parts > capacity) num_parts = (int)capacity;
   for (int p = 0; p < num_parts; ++p) {
     int64_t cap = capacity / num_parts + (p < capacity % num_parts ? 1 : 0);
-    if (cap == 0) cap = 1;
     c->parts.push_back(make_policy(policy, cap));
     c->offsets.push_back(off);
     off += cap;

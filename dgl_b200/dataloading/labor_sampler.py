@@ -25,6 +25,13 @@ class LaborSampler(BlockSampler):
         self.batch_dependency = batch_dependency
         self.random_seed = dgl_random.next_seed()
 
+    def set_seed(self, random_seed=None):
+        """Re-seed the shared per-vertex variates (reference labor_sampler.py:set_seed). With ``batch_dependency`` > 1
+        consecutive batches interpolate between successive seeds; calling this restarts that schedule so that every
+        rank / worker given the same ``random_seed`` draws identical neighbourhoods."""
+        self.random_seed = dgl_random.next_seed() if random_seed is None else int(random_seed)
+        self.cnt = 0
+
     def sample_blocks(self, g, seed_nodes, exclude_eids=None):
         output_nodes = seed_nodes
         blocks = []

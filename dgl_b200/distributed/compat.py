@@ -49,6 +49,10 @@ class IdMap:
         if bool((self._start[1:] < self._end[:-1]).any()):
             raise DGLError("id ranges overlap")
 
+    @property
+    def torch_dtype(self):
+        return torch.int64
+
     def __call__(self, ids):
         ids = torch.as_tensor(ids)
         if self.num_types == 0:

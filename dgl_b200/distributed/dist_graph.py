@@ -364,6 +364,18 @@ class DistGraph:
         self.device = torch.device("cpu")
         _CTX.graph = self
 
+    @property
+    def idtype(self):
+        return torch.int64
+
+    @property
+    def device(self):
+        return torch.device("cpu")
+
+    @property
+    def canonical_etypes(self):
+        return [tuple(e.split(":")) if ":" in e else ("_N", e, "_N") for e in self.etypes]
+
     def get_partition_book(self):
         return self.gpb
 
@@ -689,6 +701,29 @@ class DistEmbedding:
     def weight(self):
         return self._tensor
 
+    @property
+    def name(self):
+        return self._name
+
+    @property
+    def data_name(self):
+        """KVStore key of the embedding table."""
+        return self._tensor.name
+
+    @property
+    def part_policy(self):
+        return self._tensor.part_policy
+
+    @property
+    def kvstore(self):
+        from .compat import get_kvstore
+        return get_kvstore()
+
+    @property
+    def optm_state(self):
+        """State tensor(s) a sparse optimizer attached to this embedding (``None`` before an optimizer is created)."""
+        return getattr(self, "_optm_state", None)
+
 
 class DistSparseGradOptimizer:
     def __init__(self, params, lr):
@@ -716,11 +751,80 @@ class DistSparseGradOptimizer:
     def update(self, emb, idx, grad):
         raise NotImplementedError
 
-    def save(self, path):
-        torch.save({"lr": self._lr}, path)
+    # ---- checkpointing (reference distributed/optim/pytorch/sparse_optim.py:56-260) ---------------------------
+    @staticmethod
+    def _world():
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(), dist.get_world_size()
+        return 0, 1
 
-    def load(self, path):
-        self._lr = torch.load(path)["lr"]
+    def _hyper(self):
+        return {k: v for k, v in vars(self).items() if k.startswith("_") and isinstance(v, (int, float, tuple))}
+
+    def _state_tensors(self, emb):
+        st = self._state[emb._name]
+        return list(st) if isinstance(st, tuple) else [st]
+
+    def local_state_dict(self):
+        """This rank's share of the optimizer state: hyper-parameters plus, per embedding, a contiguous 1/world slice of
+        global row ids and the state rows for them: ``{"params": {...}, "emb_states": {emb: {"ids": t, "states":
+        {state name: rows}}}}``. Rows are addressed by *global* id, so a checkpoint can be restored under a different
+        number of trainers."""
+        rank, world = self._world()
+        out = {"params": dict(self._hyper(), world_size=world), "emb_states": {}}
+        for emb in self._params:
+            n = emb.num_embeddings
+            ids = torch.arange(rank * n // world, (rank + 1) * n // world)
+            out["emb_states"][emb._name] = {"ids": ids, "states": {t.name: t[ids] for t in self._state_tensors(emb)}}
+        return out
+
+    def load_local_state_dict(self, local_state_dict):
+        """Write the rows of a :meth:`local_state_dict` back into the distributed state tensors."""
+        by_name = {emb._name: emb for emb in self._params}
+        for emb_name, emb_state in local_state_dict["emb_states"].items():
+            if emb_name not in by_name:
+                raise ValueError(f"loaded state dict contains an unknown embedding {emb_name}")
+            tensors = {t.name: t for t in self._state_tensors(by_name[emb_name])}
+            if len(emb_state["states"]) != len(tensors):
+                raise ValueError(f"loaded state dict has a different number of states of embedding {emb_name}")
+            ids = emb_state["ids"]
+            for name, rows in emb_state["states"].items():
+                if name not in tensors:
+                    raise ValueError(f"loaded state dict contains a state {name} that can't be found in the optimizer states")
+                if ids.numel():
+                    tensors[name][ids] = rows.to(tensors[name].dtype)
+        for k, v in local_state_dict.get("params", {}).items():
+            if k != "world_size" and hasattr(self, k):
+                setattr(self, k, v)
+
+    def save(self, f):
+        """Collective: every rank writes ``<f>_<rank>``."""
+        import torch.distributed as dist
+        rank, world = self._world()
+        if world > 1:
+            dist.barrier()
+        torch.save(self.local_state_dict(), f"{f}_{rank}")
+        if world > 1:
+            dist.barrier()
+
+    def load(self, f):
+        """Collective: restore from the files of a :meth:`save`, whatever world size wrote them — file ``i`` is read by
+        rank ``i % world`` (covers scale-in and scale-out); a missing own file is a warning, not an error."""
+        import glob
+        import warnings
+        import torch.distributed as dist
+        rank, world = self._world()
+        if world > 1:
+            dist.barrier()
+        files = {int(p.rsplit("_", 1)[1]): p for p in glob.glob(f"{f}_*") if p.rsplit("_", 1)[1].isdigit()}
+        if rank not in files and not any(i % world == rank for i in files):
+            warnings.warn(f"File {f}_{rank} can't be found, load nothing.")
+        for i in sorted(files):
+            if i % world == rank:
+                self.load_local_state_dict(torch.load(files[i], weights_only=False))
+        if world > 1:
+            dist.barrier()
 
 
 class DistSparseAdagrad(DistSparseGradOptimizer):
@@ -730,6 +834,7 @@ class DistSparseAdagrad(DistSparseGradOptimizer):
         for emb in params:
             self._state[emb._name] = DistTensor((emb.num_embeddings, emb.embedding_dim), torch.float32,
                                                 emb._name + "_sum", _graph=emb._tensor._g)
+            emb._optm_state = (self._state[emb._name],)
 
     def update(self, emb, idx, grad):
         st = self._state[emb._name]
@@ -751,6 +856,7 @@ class DistSparseAdam(DistSparseGradOptimizer):
                 DistTensor((emb.num_embeddings, 1), torch.float32, emb._name + "_step", _graph=g),
                 DistTensor((emb.num_embeddings, emb.embedding_dim), torch.float32, emb._name + "_m", _graph=g),
                 DistTensor((emb.num_embeddings, emb.embedding_dim), torch.float32, emb._name + "_v", _graph=g))
+            emb._optm_state = self._state[emb._name]
 
     def update(self, emb, idx, grad):
         st, m, v = self._state[emb._name]

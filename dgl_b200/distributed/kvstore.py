@@ -39,6 +39,19 @@ class PartitionPolicy:
     def partition_book(self):
         return self._gpb
 
+    @property
+    def type_name(self):
+        """Node type name, or the canonical edge type as a tuple."""
+        return self._typ if self._dom == NODE_PART_POLICY else tuple(self._typ.split(":"))
+
+    def is_node(self):
+        return self._dom == NODE_PART_POLICY
+
+    def get_data_name(self, name):
+        """KVStore key of tensor ``name`` under this policy (a ``HeteroDataName``)."""
+        from .compat import HeteroDataName
+        return HeteroDataName(self.is_node(), self.type_name, name)
+
     def to_partid(self, id_tensor):
         return self._gpb.nid2partid(id_tensor) if self._dom == NODE_PART_POLICY else self._gpb.eid2partid(id_tensor)
 
@@ -72,6 +85,34 @@ class KVServer:
 
     def is_backup_server(self):
         return False
+
+    @property
+    def part_id(self):
+        return self._state.part_id if self._state is not None else self.server_id
+
+    @property
+    def barrier_count(self):
+        return self._barrier_count if hasattr(self, "_barrier_count") else {}
+
+    @barrier_count.setter
+    def barrier_count(self, value):
+        self._barrier_count = value
+
+    @property
+    def orig_data(self):
+        """Names of tensors created by this server (all of them: there are no backup servers sharing them)."""
+        return set(self._state.kv) if self._state is not None else set()
+
+    @property
+    def push_handlers(self):
+        return {k: v for k, v in self._state.handlers.items() if k != "__pull__"} if self._state is not None else {}
+
+    @property
+    def pull_handlers(self):
+        return dict(self._state.handlers.get("__pull__", {})) if self._state is not None else {}
+
+    def count_local_nonzero(self, name):
+        return int(torch.count_nonzero(self._state.kv[name]))
 
     def add_part_policy(self, policy):
         self.part_policy[policy.policy_str] = policy
@@ -113,6 +154,23 @@ class KVClient:
     @property
     def num_servers(self):
         return self._dg._CTX.num_servers
+
+    @property
+    def group_count(self):
+        """Servers per machine (one per partition here)."""
+        return 1
+
+    @property
+    def data_store(self):
+        """Local shard store in standalone mode (``{}`` when the shards live in server processes)."""
+        st = getattr(self._dg._CTX, "local_state", None)
+        return st.kv if st is not None else {}
+
+    def add_data(self, name, tensor, part_policy=None):
+        """Standalone-mode helper of the reference's SA KVClient: register an existing full tensor under ``name``."""
+        full = self.init_data(name, tuple(tensor.shape), tensor.dtype, part_policy)
+        self.push(full, torch.arange(tensor.shape[0]), tensor)
+        return full
 
     def data_name_list(self):
         return list(self._meta)

@@ -57,6 +57,9 @@ class RangePartitionBook:
     def global_eid_dtype(self):
         return torch.int64
 
+    def is_homogeneous(self):
+        return len(self._ntypes) == 1 and len(self._etypes) == 1
+
     def to_canonical_etype(self, etype):
         return etype
 

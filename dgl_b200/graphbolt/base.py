@@ -78,5 +78,11 @@ class CSCFormatBase:
     def to(self, device, non_blocking=False):
         return CSCFormatBase(self.indptr.to(device, non_blocking=non_blocking), self.indices.to(device, non_blocking=non_blocking))
 
+    def pin_memory(self):
+        return CSCFormatBase(self.indptr.pin_memory(), self.indices.pin_memory())
+
+    def is_pinned(self):
+        return self.indptr.is_pinned() and self.indices.is_pinned()
+
     def __repr__(self):
         return f"CSCFormatBase(indptr={self.indptr},\n              indices={self.indices},\n)"

@@ -21,6 +21,16 @@ class Node:
         self.parents.add(parent)
         parent.childs.add(self)
 
+    def add_child(self, child):
+        child.add_parent(self)
+
+    def remove_parent(self, parent):
+        self.parents.discard(parent)
+        parent.childs.discard(self)
+
+    def remove_child(self, child):
+        child.remove_parent(self)
+
     def __repr__(self):
         return f"<Node {self.name} parents={sorted(p.name for p in self.parents)}>"
 

@@ -53,6 +53,25 @@ class FeatureCache:
         except Exception:  # noqa: BLE001
             pass
 
+    def is_pinned(self):
+        return self.tensor.is_pinned()
+
+    @property
+    def max_size_in_bytes(self):
+        return self.capacity * self.row_bytes
+
+    def query_and_replace(self, keys, reader_fn):
+        """Rows of ``keys``: hits come from the cache, misses are read with ``reader_fn(missing_keys)`` and inserted
+        (reference impl/cpu_feature_cache.py:query_and_replace)."""
+        values, hit_pos, miss_pos, miss_keys = self.query(keys)
+        out = torch.empty((keys.shape[0],) + tuple(self.tensor.shape[1:]), dtype=self.tensor.dtype)
+        out[hit_pos] = values
+        if miss_keys.numel():
+            fresh = reader_fn(miss_keys)
+            out[miss_pos] = fresh.to(out.dtype)
+            self.replace(miss_keys, fresh)
+        return out
+
     def query(self, keys):
         """Returns (values_of_hits, hit_positions_in_keys, missing_positions_in_keys, missing_keys)."""
         keys = keys.to(torch.int64).cpu().contiguous()

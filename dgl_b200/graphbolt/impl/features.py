@@ -128,6 +128,20 @@ class DiskBasedFeature(Feature):
                                                           idx.shape[0], out.data_ptr(), self._threads)
         return out.to(dev, non_blocking=True) if dev.type == "cuda" else out
 
+    def to(self, device):
+        """Disk-backed features stay on disk; only an explicit "cpu"/"pinned" target is accepted (reference
+        torch_based_feature_store.py: DiskBasedFeature.to raises for GPUs — wrap it with a GPU cache instead)."""
+        if str(device) not in ("cpu", "pinned"):
+            raise DGLError("`DiskBasedFeature` does not support `to()` with a non-CPU device: reads land in (pinned) "
+                           "host memory; put a GPU cache in front of it instead.")
+        return self
+
+    def pin_memory_(self):
+        raise DGLError("`DiskBasedFeature` does not support `pin_memory_()`: there is no resident host copy to pin.")
+
+    def is_pinned(self):
+        return False
+
     def size(self):
         return torch.Size(self._shape[1:])
 
@@ -326,6 +340,10 @@ class TorchBasedFeatureStore(BasicFeatureStore):
             if hasattr(f, "pin_memory_"):
                 f.pin_memory_()
         return self
+
+    def is_pinned(self):
+        """True iff every in-memory feature is pinned (disk-backed features have no host copy to pin)."""
+        return all(f.is_pinned() for f in self._features.values() if hasattr(f, "is_pinned"))
 
     def to(self, device):
         return TorchBasedFeatureStore({k: (f.to(device) if hasattr(f, "to") else f) for k, f in self._features.items()})

@@ -43,6 +43,16 @@ class RelGraphConv(nn.Module):
             nn.init.xavier_uniform_(self.loop_weight, gain=nn.init.calculate_gain("relu"))
         self.dropout = nn.Dropout(dropout)
 
+    def reset_parameters(self):
+        """Re-draw the relation weights, zero the bias and re-draw the self-loop weight (Xavier, ReLU gain)."""
+        self.linear_r.reset_parameters()
+        if self.bias:
+            nn.init.zeros_(self.h_bias)
+        if self.self_loop:
+            nn.init.xavier_uniform_(self.loop_weight, gain=nn.init.calculate_gain("relu"))
+        if self.layer_norm:
+            self.layer_norm_weight.reset_parameters()
+
     def message(self, edges):
         m = self.linear_r(edges.src["h"], edges.data["etype"], self.presorted)
         if "norm" in edges.data:

@@ -334,6 +334,11 @@ class GatedGraphConv(nn.Module):
             nn.init.xavier_normal_(linear.weight, gain=gain)
             nn.init.zeros_(linear.bias)
 
+    def set_allow_zero_in_degree(self, set_value):
+        """Kept for API parity: the GRU update of this layer is well defined for nodes without in-edges (their
+        aggregated message is zero), so nothing is checked either way (reference gatedgraphconv.py:98)."""
+        self._allow_zero_in_degree = set_value
+
     def forward(self, graph, feat, etypes=None):
         with graph.local_scope():
             assert graph.is_homogeneous, "not a homogeneous graph; convert it with to_homogeneous and pass in the edge type as argument"
@@ -519,6 +524,9 @@ class GMMConv(nn.Module):
         nn.init.constant_(self.inv_sigma.data, 1)
         if self.bias is not None:
             nn.init.zeros_(self.bias.data)
+
+    def set_allow_zero_in_degree(self, set_value):
+        self._allow_zero_in_degree = set_value
 
     def forward(self, graph, feat, pseudo):
         with graph.local_scope():

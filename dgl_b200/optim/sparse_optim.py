@@ -81,6 +81,21 @@ class SparseGradOptimizer(abc.ABC):
     def _state(self, emb):
         raise NotImplementedError
 
+    def setup(self, params):
+        """Allocate the optimizer state of every embedding (idempotent; the constructors call the same path)."""
+        for emb in params:
+            self._state(emb)
+
+    def update(self, idx, grad, emb):
+        """Apply one update to rows ``idx`` of ``emb`` with gradient ``grad`` (reference sparse_optim.py:update):
+        duplicates in ``idx`` are averaged first, exactly as :meth:`step` does."""
+        with torch.no_grad():
+            table = emb.weight if emb._shards is None else emb._tensor[:, : emb.embedding_dim]
+            idx, grad = idx.to(table.device), grad.to(table.device)
+            uniq, inv, cnt = torch.unique(idx, return_inverse=True, return_counts=True)
+            gsum = torch.zeros((uniq.shape[0], grad.shape[1]), device=table.device, dtype=grad.dtype).index_add_(0, inv, grad)
+            self.update_rows(emb, uniq, gsum / cnt.unsqueeze(1), table)
+
     @abc.abstractmethod
     def update_rows(self, emb, rows, grad, table):
         """apply the optimizer update to table[rows] with averaged gradient ``grad``"""

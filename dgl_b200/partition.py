@@ -198,6 +198,10 @@ class NDArrayPartition:
         else:
             raise DGLError(f"Unknown partition mode {mode}")
 
+    def get(self):
+        """The partition object itself (the reference returns its C++ handle here)."""
+        return self
+
     def num_parts(self):
         return self._num_parts
 

@@ -317,14 +317,27 @@ def _sparsify(mat, eps, avg_degree):
     return mat
 
 
-class PPR(BaseTransform):
-    def __init__(self, alpha=0.15, eweight_name="w", eps=None, avg_degree=5):
-        self.alpha, self.eweight_name, self.eps, self.avg_degree = alpha, eweight_name, eps, avg_degree
+class _Diffusion(BaseTransform):
+    """Shared sparsification rule of PPR / HeatKernel / GDC."""
+    eps, avg_degree = None, 5
 
     def get_eps(self, num_nodes, mat):
-        if self.eps is None and self.avg_degree is not None:
-            return None
-        return self.eps
+        """Threshold below which diffused weights are dropped: the explicit ``eps``, or the value that keeps
+        ``avg_degree * num_nodes`` entries of ``mat`` (midpoint between the last kept and the first dropped value, as
+        in the reference module.py:get_eps)."""
+        if self.eps is not None:
+            return self.eps
+        vals = torch.sort(torch.as_tensor(mat).flatten(), descending=True)[0]
+        k = self.avg_degree * num_nodes
+        if k >= vals.numel():
+            return float("-inf")
+        left = vals[k - 1] if k > 0 else vals[0]
+        return float((left + vals[k]) / 2.0)
+
+
+class PPR(_Diffusion):
+    def __init__(self, alpha=0.15, eweight_name="w", eps=None, avg_degree=5):
+        self.alpha, self.eweight_name, self.eps, self.avg_degree = alpha, eweight_name, eps, avg_degree
 
     def __call__(self, g):
         a = _dense_adj(g, self.eweight_name)
@@ -334,7 +347,7 @@ class PPR(BaseTransform):
         return _graph_from_dense(g, ppr, self.eweight_name)
 
 
-class HeatKernel(BaseTransform):
+class HeatKernel(_Diffusion):
     def __init__(self, t=2.0, eweight_name="w", eps=None, avg_degree=5):
         self.t, self.eweight_name, self.eps, self.avg_degree = t, eweight_name, eps, avg_degree
 
@@ -346,7 +359,7 @@ class HeatKernel(BaseTransform):
         return _graph_from_dense(g, hk, self.eweight_name)
 
 
-class GDC(BaseTransform):
+class GDC(_Diffusion):
     def __init__(self, coefs, eweight_name="w", eps=None, avg_degree=5):
         self.coefs, self.eweight_name, self.eps, self.avg_degree = coefs, eweight_name, eps, avg_degree
 

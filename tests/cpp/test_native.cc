@@ -114,6 +114,16 @@ static void test_cache(int policy) {
   CHECK(dglb200_cache_stats(h, &hits, &queries) == 0);
   CHECK(queries >= 280 && hits >= 40);
   CHECK(dglb200_cache_destroy(h) == 0);
+  // fewer slots than requested shards: slot ids must still stay inside the cache tensor
+  int64_t tiny = 0;
+  CHECK(dglb200_cache_create(policy, 3, 8, &tiny) == 0);
+  std::vector<int64_t> tk(100), tp(100);
+  for (int i = 0; i < 100; ++i) tk[i] = 7 * i + 1;
+  for (int b = 0; b < 100; b += 2) {
+    CHECK(dglb200_cache_replace(tiny, tk.data() + b, 2, tp.data() + b) == 0);
+    for (int j = b; j < b + 2; ++j) CHECK(tp[j] >= -1 && tp[j] < 3);
+  }
+  CHECK(dglb200_cache_destroy(tiny) == 0);
 }
 
 static void test_partitioners() {

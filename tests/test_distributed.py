@@ -96,6 +96,26 @@ def test_standalone_dist_graph():
         e2.sum().backward()
         opt2.step()
         assert torch.allclose(emb2.weight[torch.tensor([4, 9])], torch.full((2, 4), -0.1), atol=1e-4)
+        # optimizer checkpoint: state rows are saved by global id and restored into a fresh optimizer
+        assert emb2.name == "emb2" and emb2.data_name.endswith("emb2") and len(emb2.optm_state) == 3
+        ck = os.path.join(d, "opt_ck")
+        opt2.save(ck)
+        assert os.path.exists(ck + "_0")
+        sd = opt2.local_state_dict()
+        assert sd["params"]["world_size"] == 1 and sd["params"]["_lr"] == 0.1
+        m_before = opt2._state["emb2"][1][torch.tensor([4, 9])].clone()
+        assert float(m_before.abs().sum()) > 0
+        opt2._state["emb2"][1][torch.tensor([4, 9])] = torch.zeros(2, 4)          # corrupt, then restore
+        opt2._lr = 5.0
+        opt2.load(ck)
+        assert torch.equal(opt2._state["emb2"][1][torch.tensor([4, 9])], m_before) and opt2._lr == 0.1
+        assert float(opt2._state["emb2"][0][torch.tensor([4])]) == 1.0             # step counter restored too
+        with pytest.warns(UserWarning):
+            opt2.load(os.path.join(d, "no_such_ck"))
+        bad = opt2.local_state_dict()
+        bad["emb_states"]["emb2"]["states"]["bogus"] = bad["emb_states"]["emb2"]["states"].pop(next(iter(bad["emb_states"]["emb2"]["states"])))
+        with pytest.raises(ValueError):
+            opt2.load_local_state_dict(bad)
         sg2 = dd.sample_etype_neighbors(dg, torch.arange(0, 600, 50), {"_E": 3})
         assert int(sg2.in_degrees().max()) <= 3
         assert dd.get_rank() == 0 and dd.role.get_role() in ("default", "client", "server")

@@ -138,3 +138,58 @@ def test_reshape_lhs_rhs_and_storage_registry():
     with pytest.raises(AssertionError):
         storages.wrap_storage("nope")
     assert storages.BaseTensorStorage(torch.arange(4)).fetch(torch.tensor([1]), "cpu").tolist() == [1]
+
+
+def test_method_level_additions():
+    from dgl_b200 import graphbolt as gb
+    from dgl_b200.transforms import module as TM
+    from dgl_b200.graphbolt.datapipes.visualization import Node
+    m = torch.rand(20, 20)
+    eps = TM.GDC([0.5, 0.3], avg_degree=5).get_eps(20, m)
+    assert int((m >= eps).sum()) == 100 and TM.PPR(eps=0.1).get_eps(20, m) == 0.1
+    assert TM.HeatKernel(avg_degree=50).get_eps(20, m) == float("-inf")
+    s = dgl.dataloading.LaborSampler([2, 2])
+    g = dgl.rand_graph(100, 1000)
+    s.set_seed(7)
+    a = s.sample(g, torch.arange(10))[2][0].edata[dgl.EID]
+    s.set_seed(7)
+    b = s.sample(g, torch.arange(10))[2][0].edata[dgl.EID]
+    assert torch.equal(a, b) and s.cnt == 1
+    csc = gb.CSCFormatBase(indptr=torch.tensor([0, 1]), indices=torch.tensor([0]))
+    assert csc.is_pinned() is False
+    cache = gb.CPUFeatureCache((4, 2), torch.float32)
+    table = torch.arange(20.0).view(10, 2)
+    reads = []
+
+    def reader(keys):
+        reads.append(keys.tolist())
+        return table[keys]
+
+    assert torch.equal(cache.query_and_replace(torch.tensor([1, 3]), reader), table[[1, 3]])
+    assert torch.equal(cache.query_and_replace(torch.tensor([3, 5]), reader), table[[3, 5]])
+    assert reads == [[1, 3], [5]] and cache.max_size_in_bytes == 4 * 8 and cache.is_pinned() is False
+    a_, b_ = Node(object(), "a"), Node(object(), "b")
+    a_.add_child(b_)
+    assert a_ in b_.parents and b_ in a_.childs
+    a_.remove_child(b_)
+    assert not b_.parents and not a_.childs
+    conv = dgl.nn.RelGraphConv(4, 3, 2)
+    before = conv.loop_weight.clone()
+    conv.reset_parameters()
+    assert not torch.equal(before, conv.loop_weight)
+    mm = dgl.nn.GMMConv(3, 2, 2, 2)
+    mm.set_allow_zero_in_degree(True)
+    assert mm._allow_zero_in_degree is True
+    dgl.nn.GatedGraphConv(3, 3, 1, 1).set_allow_zero_in_degree(True)
+    part = dgl.partition.NDArrayPartition(10, 2)
+    assert part.get() is part
+    emb = dgl.nn.NodeEmbedding(6, 2, "mm_emb")
+    opt = dgl.optim.SparseAdagrad([emb], lr=1.0)
+    opt.setup([emb])
+    w0 = emb.weight.clone()
+    opt.update(torch.tensor([1, 1, 4]), torch.ones(3, 2), emb)
+    assert not torch.equal(emb.weight[1], w0[1]) and torch.equal(emb.weight[0], w0[0])
+    from dgl_b200.distributed import kvstore
+    pol = kvstore.PartitionPolicy("edge:a:r:b", None)
+    assert pol.type_name == ("a", "r", "b") and not pol.is_node() and str(pol.get_data_name("w")) == "edge~a:r:b~w"
+    assert kvstore.PartitionPolicy("node:user", None).type_name == "user"
