@@ -372,10 +372,6 @@ class DistGraph:
     def device(self):
         return torch.device("cpu")
 
-    @property
-    def canonical_etypes(self):
-        return [tuple(e.split(":")) if ":" in e else ("_N", e, "_N") for e in self.etypes]
-
     def get_partition_book(self):
         return self.gpb
 
