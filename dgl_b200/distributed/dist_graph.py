@@ -364,14 +364,6 @@ class DistGraph:
         self.device = torch.device("cpu")
         _CTX.graph = self
 
-    @property
-    def idtype(self):
-        return torch.int64
-
-    @property
-    def device(self):
-        return torch.device("cpu")
-
     def get_partition_book(self):
         return self.gpb
 
