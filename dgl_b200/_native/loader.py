@@ -21,7 +21,9 @@ from pathlib import Path
 from . import build as _build
 from ..utils import trace as _trace
 
-_LIBDIR = Path(__file__).resolve().parent.parent / "lib"
+# DGLB200_LIBDIR points the loader at an alternative build of the native libraries (e.g. the sanitizer build
+# produced by script/run_sanitizers.sh --python)
+_LIBDIR = Path(os.environ["DGLB200_LIBDIR"]) if os.environ.get("DGLB200_LIBDIR") else Path(__file__).resolve().parent.parent / "lib"
 _KIND = {"p": ctypes.c_void_p, "l": ctypes.c_int64, "i": ctypes.c_int32,
          "f": ctypes.c_float, "d": ctypes.c_double, "s": ctypes.c_char_p}
 

@@ -1,6 +1,7 @@
 // Native unit tests of libdglb200_cpu.so through its C ABI (the counterpart of the reference's gtest suite
 // /root/reference/tests/cpp/: test_spmm.cc, test_partition.cc, message_queue_test.cc, socket_communicator_test.cc).
 // No gtest in this image: a 30-line harness, built and run by tests/test_cpp_native.py.
+#include <atomic>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -43,7 +44,7 @@ int dglb200_rpc_recv_take(void* dst);
 int dglb200_rpc_destroy(int64_t handle);
 }
 
-static int g_failed = 0, g_checks = 0;
+static std::atomic<int> g_failed{0}, g_checks{0};  // CHECK is used from helper threads too
 #define CHECK(cond)                                                                  \
   do {                                                                               \
     ++g_checks;                                                                      \
@@ -270,6 +271,6 @@ int main() {
   for (int policy = 0; policy < 4; ++policy) test_cache(policy);  // S3-FIFO, SIEVE, LRU, CLOCK
   test_partitioners();
   test_rpc_loopback();
-  std::printf("%d checks, %d failed\n", g_checks, g_failed);
+  std::printf("%d checks, %d failed\n", g_checks.load(), g_failed.load());
   return g_failed ? 1 : 0;
 }
