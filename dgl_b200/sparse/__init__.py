@@ -396,11 +396,12 @@ def sddmm(A, X1, X2):
 
 
 def bsddmm(A, X1, X2):
-    """Batched sddmm: X1 [M, K, B], X2 [K, N, B], A.val [nnz, B]."""
+    """Batched sddmm: X1 [M, K, B], X2 [K, N, B]; A.val is [nnz] (shared by the batch) or [nnz, B]; result val [nnz, B]."""
     x1 = X1.permute(0, 2, 1).contiguous()  # [M, B, K]
     x2 = X2.permute(1, 2, 0).contiguous()  # [N, B, K]
     dots = SA.gsddmm(A._g, "dot", x1, x2, "v", "u").squeeze(-1)  # [nnz, B]
-    return val_like(A, A.val * dots)
+    scale = A.val if A.val.dim() > 1 else A.val.unsqueeze(-1)
+    return val_like(A, scale * dots)
 
 
 def matmul(A, B):

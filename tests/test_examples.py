@@ -45,6 +45,36 @@ def test_link_prediction_sage_cpu():
     _run("link_prediction_sage.py", "--steps", "3")
 
 
+def _main_of(script, *argv):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(script[:-3], os.path.join(ROOT, "examples", script))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    old = sys.argv
+    sys.argv = [script, *argv]
+    try:
+        return mod.main()
+    finally:
+        sys.argv = old
+
+
+def test_tree_lstm_learns_with_topological_propagation():
+    assert _main_of("tree_lstm.py", "--epochs", "8", "--trees", "128") > 0.9
+
+
+def test_deepwalk_embeddings_separate_communities():
+    assert _main_of("deepwalk_embedding.py", "--epochs", "6") > 0.85
+
+
+def test_sparse_graph_transformer_learns():
+    assert _main_of("sparse_graph_transformer.py", "--epochs", "30") > 0.7
+
+
+@pytest.mark.parametrize("sampler", ["cluster", "saint"])
+def test_subgraph_sampling_training(sampler):
+    assert _main_of("subgraph_sampling_training.py", "--sampler", sampler, "--epochs", "20") > 0.55
+
+
 @pytest.mark.parametrize("script", ["1_node_classification.py", "2_message_passing.py", "3_minibatch_training.py",
                                     "4_sparse_and_graphbolt.py"])
 def test_tutorials_run(script):

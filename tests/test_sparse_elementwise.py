@@ -61,3 +61,15 @@ def test_operator_forms_and_scalars():
     assert dglsp.sp_power(A, 2).val.tolist() == [1.0, 4.0, 9.0]
     assert dglsp.is_scalar(3) and dglsp.is_scalar(torch.tensor(1.0)) and not dglsp.is_scalar(torch.ones(1))
     dglsp.load_dgl_sparse()
+
+
+def test_bsddmm_broadcasts_scalar_values_over_the_batch():
+    A = dglsp.from_coo(torch.tensor([0, 1, 2]), torch.tensor([1, 2, 0]), torch.tensor([1.0, 2.0, 3.0]), (3, 3))
+    X1, X2 = torch.randn(3, 4, 5), torch.randn(4, 3, 5)
+    out = dglsp.bsddmm(A, X1, X2)
+    dense = torch.einsum("mkb,knb->mnb", X1, X2)
+    r, c = A.coo()
+    assert out.val.shape == (3, 5) and torch.allclose(out.val, A.val[:, None] * dense[r.long(), c.long()], atol=1e-5)
+    B = dglsp.val_like(A, torch.rand(3, 5))
+    out2 = dglsp.bsddmm(B, X1, X2)
+    assert torch.allclose(out2.val, B.val * dense[r.long(), c.long()], atol=1e-5)
