@@ -75,6 +75,20 @@ def test_subgraph_sampling_training(sampler):
     assert _main_of("subgraph_sampling_training.py", "--sampler", sampler, "--epochs", "20") > 0.55
 
 
+def test_hgt_on_homogenised_heterograph_learns():
+    assert _main_of("hgt_hetero.py", "--epochs", "30") > 0.6
+
+
+def test_dgi_and_label_propagation_beat_raw_features():
+    raw, dgi, lp = _main_of("unsupervised_and_propagation.py", "--epochs", "50")
+    assert dgi > raw and lp > raw and lp > 0.6
+
+
+def test_gnn_explainer_prefers_motif_edges():
+    acc, ratio = _main_of("gnn_explainer.py", "--epochs", "250")
+    assert acc > 0.9 and ratio > 1.1
+
+
 @pytest.mark.parametrize("script", ["1_node_classification.py", "2_message_passing.py", "3_minibatch_training.py",
                                     "4_sparse_and_graphbolt.py"])
 def test_tutorials_run(script):
