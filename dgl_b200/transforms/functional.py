@@ -514,14 +514,12 @@ def rcmk_perm(g):
     functional.py:3371 calls scipy's ``reverse_cuthill_mckee``."""
     from .._native import loader
     from ..base import id_code
-    from ..graph_index import coo_to_csr
     cg = g if g.device.type == "cpu" else g.to("cpu")
-    su, sv, _ = to_bidirected_coo(cg)
+    u, v = [t.contiguous() for t in cg.edges()]
     n = cg.num_nodes()
-    indptr, indices, _ = coo_to_csr(su, sv, n, cg.idtype)
     perm = torch.empty(n, dtype=torch.int64)
-    loader.cpu_lib().fn("dglb200_cpu_rcmk", "ipplp")(id_code(cg.idtype), indptr.data_ptr(), indices.data_ptr(), n,
-                                                     perm.data_ptr())
+    loader.cpu_lib().fn("dglb200_cpu_rcmk_coo", "ippllp")(id_code(cg.idtype), u.data_ptr(), v.data_ptr(), u.shape[0], n,
+                                                          perm.data_ptr())
     return perm.numpy().copy()
 
 
