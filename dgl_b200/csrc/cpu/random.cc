@@ -30,10 +30,22 @@ struct Stream {
   inline double unit() { return ((next() >> 11) + 0.5) * (1.0 / 9007199254740992.0); }  // (0, 1)
 };
 
+// Draws are generated in fixed blocks of kBlock outputs, block j always using stream j: the result is a pure function of
+// (seed, num) and does not depend on how many threads happen to run the blocks.
+constexpr int64_t kBlock = 4096;
+
+template <typename F>
+void for_each_block(int64_t num, F&& body) {
+  const int64_t nblocks = (num + kBlock - 1) / kBlock;
+  parallel_for_dynamic(0, nblocks, 4, [&](int64_t b, int64_t e) {
+    for (int64_t j = b; j < e; ++j) body(j, j * kBlock, std::min(num, (j + 1) * kBlock));
+  });
+}
+
 void uniform_replace(int64_t num, int64_t population, uint64_t seed, int64_t* out) {
-  parallel_for(0, num, 1 << 14, [&](int64_t b, int64_t e) {
-    Stream rng(seed, (uint64_t)b);
-    for (int64_t i = b; i < e; ++i) out[i] = (int64_t)rng.below((uint64_t)population);
+  for_each_block(num, [&](int64_t block, int64_t lo, int64_t hi) {
+    Stream rng(seed, (uint64_t)block);
+    for (int64_t i = lo; i < hi; ++i) out[i] = (int64_t)rng.below((uint64_t)population);
   });
 }
 
@@ -74,8 +86,8 @@ void weighted_replace(int64_t num, int64_t population, const T* prob, uint64_t s
     cdf[i] = acc;
   }
   DGLB_CHECK(acc > 0, "probabilities must not all be zero");
-  parallel_for(0, num, 1 << 13, [&](int64_t b, int64_t e) {
-    Stream rng(seed, (uint64_t)b);
+  for_each_block(num, [&](int64_t block, int64_t b, int64_t e) {
+    Stream rng(seed, (uint64_t)block);
     for (int64_t i = b; i < e; ++i) {
       const double u = rng.unit() * acc;
       int64_t p = std::upper_bound(cdf.begin(), cdf.end(), u) - cdf.begin();

@@ -2,7 +2,10 @@
 # Memory-safety / data-race gate for the host native code (csrc/cpu). The reference ships no sanitizer configuration
 # (SURVEY 5.2).
 #   script/run_sanitizers.sh             C++ unit tests under AddressSanitizer + UndefinedBehaviorSanitizer
-#   script/run_sanitizers.sh --tsan      C++ unit tests under ThreadSanitizer
+#   script/run_sanitizers.sh --tsan      C++ unit tests under ThreadSanitizer. Meaningful for the pthread code (RPC
+#                                        transport, caches): libgomp is not instrumented, so OpenMP regions report
+#                                        fork/join false positives — those kernels are checked for races by
+#                                        tests/test_thread_invariance.py (bit-identical results for 1 / 3 / 8 threads)
 #   script/run_sanitizers.sh --python [pytest args]
 #                                        build libdglb200_cpu.so with ASan+UBSan into a scratch directory and run the
 #                                        CPU pytest suite against it (DGLB200_LIBDIR), with libasan and libstdc++

@@ -36,6 +36,14 @@ int dglb200_cpu_csr_sum_fill(int idtype, int dtype, int64_t n_rows, const void* 
                              void* ci, void* cv, void* src_a, void* src_b);
 int dglb200_cpu_csr_rowdot(int idtype, int dtype, int64_t nnz, const void* rows, const void* cols, const void* xp,
                            const void* xi, const void* xv, const void* yp, const void* yi, const void* yv, void* out);
+int dglb200_cpu_knn_kdtree(int dtype, const void* data, const int64_t* data_off, const void* query, const int64_t* query_off,
+                           int64_t n_seg, int64_t dim, int64_t k, int64_t* out_idx, void* out_dist);
+int dglb200_cpu_fps(int dtype, const void* pos, int64_t B, int64_t N, int64_t C, int64_t npoints, const int64_t* start,
+                    int64_t* out);
+int dglb200_cpu_choice(int64_t num, int64_t population, int dtype, const void* prob, int replace, int64_t seed, int64_t* out);
+int dglb200_cpu_bfs(int idtype, const void* indptr, const void* indices, const void* eids, int64_t n, const void* src,
+                    int64_t n_src, int want_edges, void* out_ids, int64_t* sections, int64_t* n_sections, int64_t* n_ids);
+int dglb200_cpu_rcmk_coo(int idtype, const void* u, const void* v, int64_t E, int64_t n, int64_t* perm);
 int dglb200_rpc_create(int rank, const char* ip, int port, int64_t* handle, int* bound_port);
 int dglb200_rpc_connect(int64_t handle, int peer, const char* ip, int port, int max_try, int retry_ms);
 int dglb200_rpc_send(int64_t handle, int peer, int tag, const void* data, int64_t n);
@@ -265,8 +273,71 @@ static void test_csr_arith() {
   }
 }
 
+// Larger inputs so the OpenMP paths (dynamic chunks, per-thread scratch) really run multi-threaded; this is what the
+// ThreadSanitizer build of script/run_sanitizers.sh --tsan looks at.
+static void test_parallel_paths() {
+  const int64_t n = 3000;
+  // random sparse matrix with ~8 nnz per row, sorted rows
+  std::vector<int64_t> ap(n + 1, 0), ai;
+  std::vector<float> av;
+  uint64_t s = 88172645463325252ull;
+  auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+  for (int64_t r = 0; r < n; ++r) {
+    std::set<int64_t> cols;
+    while (cols.size() < 8) cols.insert((int64_t)(rnd() % n));
+    for (auto c : cols) { ai.push_back(c); av.push_back(1.f + (float)(rnd() % 7)); }
+    ap[r + 1] = (int64_t)ai.size();
+  }
+  std::vector<int64_t> nnz(n), cp(n + 1, 0);
+  CHECK(dglb200_cpu_csr_mm_count(1, n, ap.data(), ai.data(), ap.data(), ai.data(), n, nnz.data()) == 0);
+  for (int64_t r = 0; r < n; ++r) cp[r + 1] = cp[r] + nnz[r];
+  std::vector<int64_t> ci(cp[n]);
+  std::vector<float> cv(cp[n]);
+  CHECK(dglb200_cpu_csr_mm_fill(1, 0, n, ap.data(), ai.data(), av.data(), ap.data(), ai.data(), av.data(), n, cp.data(),
+                                ci.data(), cv.data()) == 0);
+  // spot-check a few rows against a direct evaluation
+  for (int64_t r = 0; r < n; r += 997) {
+    std::vector<double> acc(n, 0.0);
+    for (int64_t x = ap[r]; x < ap[r + 1]; ++x)
+      for (int64_t y = ap[ai[x]]; y < ap[ai[x] + 1]; ++y) acc[ai[y]] += (double)av[x] * av[y];
+    for (int64_t e = cp[r]; e < cp[r + 1]; ++e) CHECK(std::fabs(cv[e] - acc[ci[e]]) < 1e-3);
+  }
+  // kNN: every point's nearest neighbour is itself
+  std::vector<float> pts(3 * 5000);
+  for (auto& p : pts) p = (float)(rnd() % 100000) / 1000.f;
+  std::vector<int64_t> off = {0, 5000}, idx(5000 * 4);
+  CHECK(dglb200_cpu_knn_kdtree(0, pts.data(), off.data(), pts.data(), off.data(), 1, 3, 4, idx.data(), nullptr) == 0);
+  for (int64_t i = 0; i < 5000; i += 13) CHECK(idx[i * 4] == i || (pts[3 * i] == pts[3 * idx[i * 4]]));
+  // FPS over many clouds (thread per cloud) and one big cloud (threads inside the cloud)
+  std::vector<int64_t> start(64, 0), out(64 * 8);
+  std::vector<float> clouds(64 * 200 * 3);
+  for (auto& p : clouds) p = (float)(rnd() % 1000) / 10.f;
+  CHECK(dglb200_cpu_fps(0, clouds.data(), 64, 200, 3, 8, start.data(), out.data()) == 0);
+  for (int b = 0; b < 64; ++b) { std::set<int64_t> u(out.begin() + b * 8, out.begin() + b * 8 + 8); CHECK(u.size() == 8); }
+  std::vector<float> big(40000 * 3);
+  for (auto& p : big) p = (float)(rnd() % 100000) / 100.f;
+  std::vector<int64_t> bout(16), bstart(1, 0);
+  CHECK(dglb200_cpu_fps(0, big.data(), 1, 40000, 3, 16, bstart.data(), bout.data()) == 0);
+  { std::set<int64_t> u(bout.begin(), bout.end()); CHECK(u.size() == 16); }
+  // parallel uniform draws
+  std::vector<int64_t> draws(200000);
+  CHECK(dglb200_cpu_choice(200000, 1000, 0, nullptr, 1, 7, draws.data()) == 0);
+  for (int64_t i = 0; i < 200000; i += 101) CHECK(draws[i] >= 0 && draws[i] < 1000);
+  // BFS + RCM on the matrix above viewed as a graph
+  std::vector<int64_t> ids(n), sections(n + 1), counts(2, 0), src = {0};
+  CHECK(dglb200_cpu_bfs(1, ap.data(), ai.data(), nullptr, n, src.data(), 1, 0, ids.data(), sections.data(), &counts[0],
+                        &counts[1]) == 0);
+  CHECK(counts[1] > n / 2);
+  std::vector<int64_t> eu, ev, perm(n);
+  for (int64_t r = 0; r < n; ++r)
+    for (int64_t e = ap[r]; e < ap[r + 1]; ++e) { eu.push_back(r); ev.push_back(ai[e]); }
+  CHECK(dglb200_cpu_rcmk_coo(1, eu.data(), ev.data(), (int64_t)eu.size(), n, perm.data()) == 0);
+  { std::set<int64_t> u(perm.begin(), perm.end()); CHECK((int64_t)u.size() == n); }
+}
+
 int main() {
   test_spmm();
+  test_parallel_paths();
   test_csr_arith();
   for (int policy = 0; policy < 4; ++policy) test_cache(policy);  // S3-FIFO, SIEVE, LRU, CLOCK
   test_partitioners();
