@@ -1,7 +1,6 @@
 """DeepWalk and MetaPath2Vec embedding models (parity: /root/reference/python/dgl/nn/pytorch/network_emb.py)."""
 from __future__ import annotations
 
-import random
 
 import torch
 import torch.nn as nn
@@ -44,32 +43,29 @@ class DeepWalk(nn.Module):
         return random_walk(self.g, indices, length=self.walk_length - 1)[0]
 
     def forward(self, batch_walk):
-        batch_size = len(batch_walk)
-        device = batch_walk.device
-        batch_node_embed = self.node_embed(batch_walk).view(-1, self.emb_dim)
-        batch_context_embed = self.context_embed(batch_walk).view(-1, self.emb_dim)
-        batch_idx_list_offset = torch.arange(batch_size) * self.walk_length
-        batch_idx_list_offset = batch_idx_list_offset.unsqueeze(1)
-        idx_list_src = (batch_idx_list_offset + self.idx_list_src.unsqueeze(0)).view(-1).to(device)
-        idx_list_dst = (batch_idx_list_offset + self.idx_list_dst.unsqueeze(0)).view(-1).to(device)
-        pos_src_emb = batch_node_embed[idx_list_src]
-        pos_dst_emb = batch_context_embed[idx_list_dst]
-        neg_idx_list_src = idx_list_dst.unsqueeze(1) + torch.zeros(self.negative_size, dtype=torch.long, device=device).unsqueeze(0)
-        neg_idx_list_src = neg_idx_list_src.view(-1)
-        neg_src_emb = batch_node_embed[neg_idx_list_src]
+        """Skip-gram loss of a batch of walks ``[B, walk_length]``: every (centre, context) pair inside the window is a
+        positive; each positive gets ``negative_size`` negatives — with ``fast_neg`` they are context vectors of random
+        positions of the same batch (no extra embedding lookups), otherwise nodes drawn from degree^0.75. All draws use
+        torch's generator, so a seeded run is reproducible."""
+        n_walks, length = batch_walk.shape
+        dev = batch_walk.device
+        centre = self.node_embed(batch_walk)                       # [B, L, D]
+        context = self.context_embed(batch_walk)                   # [B, L, D]
+        src, dst = self.idx_list_src.to(dev), self.idx_list_dst.to(dev)
+        pos = (centre[:, src] * context[:, dst]).sum(-1).clamp(-6, 6)              # [B, P]
+        pos_loss = -F.logsigmoid(pos).mean()
+        anchor = centre[:, dst].unsqueeze(2)                                        # [B, P, 1, D]
+        n_pairs = src.shape[0]
         if self.fast_neg:
-            neg_idx_list_dst = list(range(batch_size * self.walk_length)) * (self.negative_size * self.window_size * 2)
-            random.shuffle(neg_idx_list_dst)
-            neg_idx_list_dst = neg_idx_list_dst[: len(neg_idx_list_src)]
-            neg_dst_emb = batch_context_embed[torch.as_tensor(neg_idx_list_dst, device=device)]
+            flat = context.reshape(n_walks * length, self.emb_dim)
+            pick = torch.randint(0, n_walks * length, (n_walks, n_pairs, self.negative_size), device=dev)
+            neg_ctx = flat[pick]                                                    # [B, P, K, D]
         else:
-            neg_dst = torch.multinomial(self.neg_prob, len(neg_src_emb), replacement=True).to(device)
-            neg_dst_emb = self.context_embed(neg_dst)
-        pos_score = torch.clamp(torch.sum(pos_src_emb * pos_dst_emb, dim=1), max=6, min=-6)
-        pos_score = torch.mean(-F.logsigmoid(pos_score))
-        neg_score = torch.clamp(torch.sum(neg_src_emb * neg_dst_emb, dim=1), max=6, min=-6)
-        neg_score = torch.mean(-F.logsigmoid(-neg_score)) * self.negative_size * self.neg_weight
-        return torch.mean(pos_score + neg_score)
+            pick = torch.multinomial(self.neg_prob, n_walks * n_pairs * self.negative_size, replacement=True).to(dev)
+            neg_ctx = self.context_embed(pick).view(n_walks, n_pairs, self.negative_size, self.emb_dim)
+        neg = (anchor * neg_ctx).sum(-1).clamp(-6, 6)
+        neg_loss = -F.logsigmoid(-neg).mean() * self.negative_size * self.neg_weight
+        return pos_loss + neg_loss
 
 
 class MetaPath2Vec(nn.Module):
