@@ -173,7 +173,8 @@ __global__ void __launch_bounds__(256) ce_loss2_kernel(const float* __restrict__
                                                        const int64_t* __restrict__ n_dev, int64_t n_cap, int C,
                                                        float* __restrict__ dlog32, __nv_bfloat16* __restrict__ dlog16,
                                                        int ldd, float* __restrict__ db, float* __restrict__ loss_out,
-                                                       int32_t* __restrict__ correct_out) {
+                                                       int32_t* __restrict__ correct_out, float* __restrict__ dlog_hi,
+                                                       float* __restrict__ dlog_lo) {
   __shared__ float s_db[8][64];
   const int64_t n = min(*n_dev, n_cap);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -216,7 +217,20 @@ __global__ void __launch_bounds__(256) ce_loss2_kernel(const float* __restrict__
 #pragma unroll
     for (int q = 0; q < 2; ++q) {
       const int c = lane + 32 * q;
-      if (dlog32 && c < C) dlog32[r * C + c] = g[q];
+      if (dlog_lo) {
+        // fp32 tensor-core path: the gradient in full ([n_cap, ldd], padding zeroed: operand of the dW kernel, which
+        // splits on the fly) and as the hi / lo planes of its TF32 split (TMA operands of the dA kernel)
+        if (c < ldd) {
+          uint32_t h;
+          asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(g[q]));
+          const float hi = __uint_as_float(h & 0xFFFFE000u);
+          dlog32[r * ldd + c] = g[q];
+          dlog_hi[r * ldd + c] = hi;
+          dlog_lo[r * ldd + c] = g[q] - hi;
+        }
+      } else if (dlog32 && c < C) {
+        dlog32[r * C + c] = g[q];
+      }
       if (dlog16 && c < ldd) dlog16[r * ldd + c] = __float2bfloat16(g[q]);
     }
   }
@@ -352,7 +366,9 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(float* __restrict__
                                                              float lr, float beta1, float beta2, float eps,
                                                              float weight_decay, int64_t* __restrict__ step_dev,
                                                              int bump_step, int64_t lo = 0,
-                                                             float* __restrict__ param_pub = nullptr) {
+                                                             float* __restrict__ param_pub = nullptr,
+                                                             float* __restrict__ shadow_hi = nullptr,
+                                                             float* __restrict__ shadow_lo = nullptr) {
   // [lo, numel) is the element range this launch owns: the whole buffer for the one-shot all-reduce, this rank's slice
   // for the two-shot variant (reduce-scatter + Adam on the slice, updated fp32 values published in param_pub)
   const int64_t t = *step_dev + 1;
@@ -395,6 +411,21 @@ __global__ void __launch_bounds__(256) allreduce_adam_kernel(float* __restrict__
       pk.x = *reinterpret_cast<uint32_t*>(&lo);
       pk.y = *reinterpret_cast<uint32_t*>(&hi);
       *reinterpret_cast<uint2*>(shadow + i) = pk;
+    }
+    if (shadow_hi) {
+      // fp32 tensor-core operands: x = hi + lo, hi exactly representable in TF32 (see tc_common.cuh: tf32_split)
+      float4 h4, l4;
+      float* hp = reinterpret_cast<float*>(&h4);
+      float* lp = reinterpret_cast<float*>(&l4);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        uint32_t h;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(pp[k]));
+        hp[k] = __uint_as_float(h & 0xFFFFE000u);
+        lp[k] = pp[k] - hp[k];
+      }
+      *reinterpret_cast<float4*>(shadow_hi + i) = h4;
+      *reinterpret_cast<float4*>(shadow_lo + i) = l4;
     }
   }
   if (bump_step && blockIdx.x == 0 && threadIdx.x == 0) {
@@ -490,14 +521,15 @@ DGLB_API int dglb200_engine_ce_loss(const void* logits, const void* bias, const 
 
 DGLB_API int dglb200_engine_ce_loss2(const void* logits, int ldl, const void* bias, const void* labels_all,
                                      const void* seeds, const void* n_dev, int64_t n_cap, int C, void* dlog32,
-                                     void* dlog16, int ldd, void* db, void* loss_out, void* correct_out, void* stream) {
+                                     void* dlog16, int ldd, void* db, void* loss_out, void* correct_out, void* dlog_hi,
+                                     void* dlog_lo, void* stream) {
   DGLB_TRY
   DGLB_CHECK(C >= 1 && C <= 64 && ldd <= 64, "ce_loss2 supports up to 64 classes");
   if (n_cap == 0) return 0;
   ce_loss2_kernel<<<(unsigned)((n_cap + 7) / 8), 256, 0, (cudaStream_t)stream>>>(
       (const float*)logits, ldl, (const float*)bias, (const int32_t*)labels_all, (const int32_t*)seeds,
       (const int64_t*)n_dev, n_cap, C, (float*)dlog32, (__nv_bfloat16*)dlog16, ldd, (float*)db, (float*)loss_out,
-      (int32_t*)correct_out);
+      (int32_t*)correct_out, (float*)dlog_hi, (float*)dlog_lo);
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH
 }
@@ -583,7 +615,8 @@ __global__ void __launch_bounds__(256) param_allgather_kernel(float* __restrict_
 // peer_ptrs: host array of `world` device pointers (each rank's flat fp32 grad buffer, P2P mapped)
 DGLB_API int dglb200_engine_allreduce_adam(void* param, const void* const* peer_ptrs, int world, void* m, void* v,
                                            void* shadow, int64_t numel, float lr, float beta1, float beta2, float eps,
-                                           float weight_decay, void* step_dev, void* stream) {
+                                           float weight_decay, void* step_dev, void* shadow_hi, void* shadow_lo,
+                                           void* stream) {
   DGLB_TRY
   DGLB_CHECK(world >= 1 && world <= 8, "world must be in [1, 8]");
   DGLB_CHECK(numel % 4 == 0, "flat parameter buffer must be padded to a multiple of 4 elements");
@@ -593,7 +626,7 @@ DGLB_API int dglb200_engine_allreduce_adam(void* param, const void* const* peer_
   int64_t blocks = (numel / 4 + 255) / 256;
   if (blocks > 148 * 4) blocks = 148 * 4;
   if (blocks < 1) blocks = 1;
-  allreduce_adam_kernel<<<(unsigned)blocks, 256, 0, st>>>((float*)param, pp, world, (float*)m, (float*)v, (__nv_bfloat16*)shadow, numel, lr, beta1, beta2, eps, weight_decay, (int64_t*)step_dev, 0);
+  allreduce_adam_kernel<<<(unsigned)blocks, 256, 0, st>>>((float*)param, pp, world, (float*)m, (float*)v, (__nv_bfloat16*)shadow, numel, lr, beta1, beta2, eps, weight_decay, (int64_t*)step_dev, 0, 0, nullptr, (float*)shadow_hi, (float*)shadow_lo);
   bump_step_kernel<<<1, 1, 0, st>>>((int64_t*)step_dev);
   DGLB_LAUNCH_CHECK();
   DGLB_CATCH

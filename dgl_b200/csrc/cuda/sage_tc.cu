@@ -24,20 +24,28 @@
 namespace dglb {
 
 constexpr int kTileM = 128;
-constexpr int kChunkK = 64;  // bf16 elements per K chunk = 128 bytes = one swizzle atom row
 constexpr int kMaxStages = 4;
+// One K chunk is one 128-byte swizzle-atom row: 64 bf16 or 32 fp32 elements (TcT<T>::kRowElems). With T = float the
+// operands are split x = hi + lo on the fly (producers for A, the optimizer epilogue for W) and every K step issues the
+// three TF32 products lo*hi + hi*lo + hi*hi (tc_common.cuh), so an fp32 model keeps fp32-level accuracy on tcgen05.
 
 struct AccRow {
   float v[8];
 };
 
+template <typename T>
 __device__ __forceinline__ void acc_add(AccRow& a, const uint4& q) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
+  if constexpr (sizeof(T) == 2) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&q);
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float2 f = __bfloat1622float2(h[i]);
-    a.v[2 * i] += f.x;
-    a.v[2 * i + 1] += f.y;
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = __bfloat1622float2(h[i]);
+      a.v[2 * i] += f.x;
+      a.v[2 * i + 1] += f.y;
+    }
+  } else {
+    a.v[0] += __uint_as_float(q.x); a.v[1] += __uint_as_float(q.y);
+    a.v[2] += __uint_as_float(q.z); a.v[3] += __uint_as_float(q.w);
   }
 }
 
@@ -55,14 +63,18 @@ __device__ __forceinline__ uint32_t fmix32(uint32_t x) {
   return x;
 }
 
-template <bool RELU>
+template <bool RELU, typename T>
 __global__ void __launch_bounds__(kThreads, 1)
-sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bfloat16* __restrict__ X,
+sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_wlo,
+                     const T* __restrict__ X,
                      const int32_t* __restrict__ self_ids, const int32_t* __restrict__ nbr,
                      const int32_t* __restrict__ cnt, const int64_t* __restrict__ n_dev, int64_t n_cap, int fanout,
-                     int Fp, int Np, const float* __restrict__ bias, __nv_bfloat16* __restrict__ out,
-                     __nv_bfloat16* __restrict__ A_out, float p_drop, uint64_t seed,
+                     int Fp, int Np, const float* __restrict__ bias, T* __restrict__ out,
+                     T* __restrict__ A_out, float p_drop, uint64_t seed,
                      const int64_t* __restrict__ step_dev, int kStages, int R, int out_f32, long long* __restrict__ trace) {
+  constexpr int kChunkK = TcT<T>::kRowElems;   // elements per 128-byte K chunk
+  constexpr int kPlanes = TcT<T>::kPlanes;     // 1 (bf16) or 2 (fp32: hi | lo)
+  constexpr int kVecE = 16 / (int)sizeof(T);   // elements per 16-byte lane vector
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int64_t n = min(*n_dev, n_cap);
   if ((int64_t)blockIdx.x * R >= n) return;  // device-side M: CTAs past the live row count do no work at all
@@ -74,7 +86,8 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
   const uint32_t a_bytes = kTileM * 128;
   const uint32_t b_bytes = (uint32_t)Np * 128;
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  const uint32_t stage_bytes = a_bytes + b_bytes;  // stage s: A tile at smem + s*stage_bytes, B tile right after it
+  // stage s: [A plane 0 | (A lo) | B plane 0 | (B lo)] at smem + s*stage_bytes
+  const uint32_t stage_bytes = kPlanes * (a_bytes + b_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * stage_bytes);
   // bars: full[4] | empty[4] | acc_full[2] | acc_empty[2] ; tmem base holder ; 2 x index lists (cnt | self | nbr)
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
@@ -162,9 +175,9 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
         for (int u = 0; u < 2 * nch; ++u) mbar_wait(empty0 + 8 * ((g + u) % kStages), (((g + u) / kStages) & 1) ^ 1);
         uint8_t* sa_self = smem + ((g + kcl) % kStages) * stage_bytes;
         uint8_t* sa_nbr = smem + ((g + nch + kcl) % kStages) * stage_bytes;
-        const int col = (k0 + kcl) * kChunkK + c * 8;  // column of this lane's 16 bytes inside a half
-        const __nv_bfloat16* Xc = X + col;
-        __nv_bfloat16* Ao = A_out ? A_out + col : nullptr;
+        const int col = (k0 + kcl) * kChunkK + c * kVecE;  // column of this lane's 16 bytes inside a half
+        const T* Xc = X + col;
+        T* Ao = A_out ? A_out + col : nullptr;
         const int npass = R / rpp;  // 1..4
 #pragma unroll 1
         for (int pass = 0; pass < npass; ++pass) {
@@ -184,19 +197,34 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
               q[j] = (j0 + j < cn) ? __ldg(reinterpret_cast<const uint4*>(Xc + (int64_t)max(nb[j0 + j], 0) * Fp))
                                    : make_uint4(0, 0, 0, 0);
 #pragma unroll
-            for (int j = 0; j < kGatherBatch; ++j) acc_add(acc, q[j]);
+            for (int j = 0; j < kGatherBatch; ++j) acc_add<T>(acc, q[j]);
           }
           const float inv = cn > 0 ? 1.f / (float)cn : 0.f;
           uint4 val;
-          __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
+          if constexpr (sizeof(T) == 2) {
+            __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc.v[2 * i] * inv, acc.v[2 * i + 1] * inv);
+            for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(acc.v[2 * i] * inv, acc.v[2 * i + 1] * inv);
+          } else {
+            val = make_uint4(__float_as_uint(acc.v[0] * inv), __float_as_uint(acc.v[1] * inv),
+                             __float_as_uint(acc.v[2] * inv), __float_as_uint(acc.v[3] * inv));
+          }
           if (Ao && live) {
             *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp) = sv;
             *reinterpret_cast<uint4*>(Ao + (tile0 + r) * Kp + Fp) = val;
           }
-          *reinterpret_cast<uint4*>(sa_self + sw128_off(r, c)) = sv;
-          *reinterpret_cast<uint4*>(sa_nbr + sw128_off(r, c)) = val;
+          if constexpr (kPlanes == 1) {
+            *reinterpret_cast<uint4*>(sa_self + sw128_off(r, c)) = sv;
+            *reinterpret_cast<uint4*>(sa_nbr + sw128_off(r, c)) = val;
+          } else {
+            float4 hi, lo;
+            tf32_split4(*reinterpret_cast<const float4*>(&sv), hi, lo);
+            *reinterpret_cast<float4*>(sa_self + sw128_off(r, c)) = hi;
+            *reinterpret_cast<float4*>(sa_self + a_bytes + sw128_off(r, c)) = lo;
+            tf32_split4(*reinterpret_cast<const float4*>(&val), hi, lo);
+            *reinterpret_cast<float4*>(sa_nbr + sw128_off(r, c)) = hi;
+            *reinterpret_cast<float4*>(sa_nbr + a_bytes + sw128_off(r, c)) = lo;
+          }
         }
         fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy
         __syncwarp();
@@ -246,6 +274,26 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
               if (RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
               dst[j >> 2] = x;
             }
+          } else if (live && sizeof(T) == 4) {
+            // fp32 activations: bias + ReLU + dropout (same per-element hash as the bf16 path), 16-byte stores
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + grow * Np + n0);
+            const uint32_t e0 = (uint32_t)(((uint64_t)grow * (uint64_t)Np + (uint64_t)n0) >> 2);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 sb = *reinterpret_cast<const float4*>(s_bias + n0 + j);
+              float4 x = make_float4(fmaf(__uint_as_float(v[j]), keep_scale, sb.x), fmaf(__uint_as_float(v[j + 1]), keep_scale, sb.y),
+                                     fmaf(__uint_as_float(v[j + 2]), keep_scale, sb.z), fmaf(__uint_as_float(v[j + 3]), keep_scale, sb.w));
+              if (RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f); }
+              if (thresh) {
+                const uint32_t rb = fmix32(((e0 + (uint32_t)(j >> 2)) * 0x9E3779B9u) ^ sd_row);
+                const uint32_t drop = __vcmpltu4(rb, thresh4);
+                if (drop & 0x000000ffu) x.x = 0.f;
+                if (drop & 0x0000ff00u) x.y = 0.f;
+                if (drop & 0x00ff0000u) x.z = 0.f;
+                if (drop & 0xff000000u) x.w = 0.f;
+              }
+              dst[j >> 2] = x;
+            }
           } else if (live) {
             uint32_t packed[16];
             const uint32_t e0 = (uint32_t)(((uint64_t)grow * (uint64_t)Np + (uint64_t)n0) >> 2);
@@ -268,7 +316,7 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
               packed[j >> 1] = p01;
               packed[(j >> 1) + 1] = p23;
             }
-            uint4* dst = reinterpret_cast<uint4*>(out + grow * Np + n0);
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(out) + grow * Np + n0);
 #pragma unroll
             for (int q = 0; q < 4; ++q) dst[q] = make_uint4(packed[4 * q], packed[4 * q + 1], packed[4 * q + 2], packed[4 * q + 3]);
           }
@@ -291,8 +339,10 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
             const int stage = g % kStages;
             const uint32_t phase = (g / kStages) & 1;
             mbar_wait(empty0 + 8 * stage, phase ^ 1);
-            mbar_arrive_expect_tx(full0 + 8 * stage, b_bytes);
-            tma_load_2d(smem_u32(smem + stage * stage_bytes + a_bytes), &tmap_w, full0 + 8 * stage, kc * kChunkK, 0);
+            mbar_arrive_expect_tx(full0 + 8 * stage, kPlanes * b_bytes);
+            const uint32_t sb = smem_u32(smem + stage * stage_bytes + kPlanes * a_bytes);
+            tma_load_2d(sb, &tmap_w, full0 + 8 * stage, kc * kChunkK, 0);
+            if constexpr (kPlanes == 2) tma_load_2d(sb + b_bytes, &tmap_wlo, full0 + 8 * stage, kc * kChunkK, 0);
           }
         }
       }
@@ -300,7 +350,9 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
   } else {
     // ===================== MMA issuer (one elected thread) =====================
     // instruction descriptor: D=F32, A=B=BF16, both K-major, N = Np, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    const uint32_t idesc = (1u << 4) | ((uint32_t)TcT<T>::kFmt << 7) | ((uint32_t)TcT<T>::kFmt << 10) |
+                           ((uint32_t)(Np >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+    auto kdesc = [](uint32_t a) { return make_sw128_kmajor_desc(a); };
     uint32_t g = 0;
     int it = 0;
     for (int64_t tile0 = (int64_t)blockIdx.x * R; tile0 < n; tile0 += tile_stride, ++it) {
@@ -314,12 +366,10 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
         mbar_wait(full0 + 8 * stage, phase);
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t a0 = smem_u32(smem + stage * stage_bytes), b0 = a0 + a_bytes;
+          const uint32_t a0 = smem_u32(smem + stage * stage_bytes), b0 = a0 + kPlanes * a_bytes;
 #pragma unroll
-          for (int k = 0; k < kChunkK / 16; ++k) {
-            umma_bf16(tmem_d, make_sw128_kmajor_desc(a0 + k * 32), make_sw128_kmajor_desc(b0 + k * 32), idesc,
-                      (kc | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 0; k < 4; ++k)  // 4 K steps of 32 bytes per 128-byte chunk
+            umma_step<T>(tmem_d, a0 + k * 32, a_bytes, kdesc, b0 + k * 32, b_bytes, kdesc, idesc, (kc | k) != 0);
           umma_commit(empty0 + 8 * stage);                    // smem slot reusable once these MMAs retire
           if (kc == KC - 1) umma_commit(accf0 + 8 * acc);     // accumulator complete -> epilogue
           SAGE_TRACE(160 + it * 16 + kc, it < 8 && kc < 16);
@@ -340,28 +390,30 @@ sage_layer_tc_kernel(const __grid_constant__ CUtensorMap tmap_w, const __nv_bflo
 
 using namespace dglb;
 
-// X: [rows, Fp] bf16, Wt: [Np, 2*Fp] bf16 (K contiguous), out: [n_cap, Np] bf16 (fp32 when out_f32),
-// A_out: [n_cap, 2*Fp] bf16 or null
-DGLB_API int dglb200_engine_sage_layer_tc(const void* X, const void* self_ids, const void* nbr, const void* cnt,
-                                          const void* n_dev, int64_t n_cap, int fanout, int Fp, int Np,
-                                          const void* Wt, const void* bias, void* out, void* A_out, int relu,
-                                          float p_drop, int64_t seed, const void* step_dev, int out_f32, void* trace, void* stream) {
-  DGLB_TRY
-  DGLB_CHECK(Fp % 64 == 0 && Fp >= 64, "Fp must be a multiple of 64");
-  DGLB_CHECK(Np % 32 == 0 && Np >= 32 && Np <= 256, "Np must be a multiple of 32 in [32, 256]");
-  DGLB_CHECK(((uintptr_t)X % 16 == 0) && ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)out % 16 == 0), "16-byte alignment required");
-  DGLB_CHECK(!out_f32 || p_drop == 0.f, "fp32 output does not support dropout");
-  if (n_cap == 0) return 0;
-  CUtensorMap tmap;
+namespace {
+
+template <typename T>
+void launch_sage_layer(const void* X, const void* self_ids, const void* nbr, const void* cnt, const void* n_dev,
+                       int64_t n_cap, int fanout, int Fp, int Np, const void* Wt, const void* Wt_lo, const void* bias,
+                       void* out, void* A_out, int relu, float p_drop, int64_t seed, const void* step_dev, int out_f32,
+                       void* trace, cudaStream_t st) {
+  constexpr int kChunkK = TcT<T>::kRowElems;
+  constexpr int kPlanes = TcT<T>::kPlanes;
+  DGLB_CHECK(Fp % kChunkK == 0 && Fp >= kChunkK, "Fp must be a multiple of one 128-byte K chunk");
+  DGLB_CHECK(kPlanes == 1 || Wt_lo != nullptr, "fp32 layers need the lo plane of the split weights");
+  CUtensorMap tmap, tmap_lo;
   const cuuint64_t gdim[2] = {(cuuint64_t)(2 * Fp), (cuuint64_t)Np};
-  const cuuint64_t gstride[1] = {(cuuint64_t)(2 * Fp) * 2};
+  const cuuint64_t gstride[1] = {(cuuint64_t)(2 * Fp) * sizeof(T)};
   const cuuint32_t box[2] = {(cuuint32_t)kChunkK, (cuuint32_t)Np};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = get_encode()(&tmap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(Wt), gdim, gstride, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-  const size_t stage_bytes = kTileM * 128 + (size_t)Np * 128;
+  for (int pl = 0; pl < kPlanes; ++pl) {
+    CUresult r = get_encode()(pl ? &tmap_lo : &tmap, TcT<T>::kTmap, 2, const_cast<void*>(pl ? Wt_lo : Wt), gdim, gstride, box,
+                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  }
+  if (kPlanes == 1) tmap_lo = tmap;
+  const size_t stage_bytes = kPlanes * (kTileM * 128 + (size_t)Np * 128);
   const size_t fixed = 1024 + 256 + 1024 + 2 * (size_t)kTileM * 4 * (2 + fanout);
   DGLB_CHECK(fixed + 2 * stage_bytes <= 227 * 1024, "fanout too large for the fused layer kernel");
   const int stages = (int)std::min<size_t>(kMaxStages, (227 * 1024 - fixed) / stage_bytes);
@@ -376,14 +428,40 @@ DGLB_API int dglb200_engine_sage_layer_tc(const void* X, const void* self_ids, c
   const int64_t tiles128 = (n_cap + kTileM - 1) / kTileM;
   const int R = tiles128 < 8 * (int64_t)num_sms ? 64 : 128;
   const unsigned grid = (unsigned)std::min<int64_t>((n_cap + R - 1) / R, num_sms);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (relu) {
-    DGLB_CUDA_CHECK(cudaFuncSetAttribute(sage_layer_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sage_layer_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmap, (const __nv_bfloat16*)X, (const int32_t*)self_ids, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np, (const float*)bias, (__nv_bfloat16*)out, (__nv_bfloat16*)A_out, p_drop, (uint64_t)seed, (const int64_t*)step_dev, stages, R, out_f32, (long long*)trace);
-  } else {
-    DGLB_CUDA_CHECK(cudaFuncSetAttribute(sage_layer_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sage_layer_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmap, (const __nv_bfloat16*)X, (const int32_t*)self_ids, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np, (const float*)bias, (__nv_bfloat16*)out, (__nv_bfloat16*)A_out, p_drop, (uint64_t)seed, (const int64_t*)step_dev, stages, R, out_f32, (long long*)trace);
-  }
+  auto go = [&](auto kern) {
+    DGLB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, kThreads, smem, st>>>(tmap, tmap_lo, (const T*)X, (const int32_t*)self_ids, (const int32_t*)nbr,
+                                       (const int32_t*)cnt, (const int64_t*)n_dev, n_cap, fanout, Fp, Np,
+                                       (const float*)bias, (T*)out, (T*)A_out, p_drop, (uint64_t)seed,
+                                       (const int64_t*)step_dev, stages, R, out_f32, (long long*)trace);
+  };
+  if (relu) go(sage_layer_tc_kernel<true, T>);
+  else go(sage_layer_tc_kernel<false, T>);
   DGLB_LAUNCH_CHECK();
+}
+
+}  // namespace
+
+// dtype kBF16: X [rows, Fp] bf16, Wt [Np, 2*Fp] bf16 (K contiguous), out [n_cap, Np] bf16 (fp32 when out_f32),
+//              A_out [n_cap, 2*Fp] bf16 or null.
+// dtype kF32 : the same tensors in fp32; Wt / Wt_lo are the hi / lo planes of the TF32 split of the weights.
+DGLB_API int dglb200_engine_sage_layer_tc(int dtype, const void* X, const void* self_ids, const void* nbr, const void* cnt,
+                                          const void* n_dev, int64_t n_cap, int fanout, int Fp, int Np,
+                                          const void* Wt, const void* Wt_lo, const void* bias, void* out, void* A_out,
+                                          int relu, float p_drop, int64_t seed, const void* step_dev, int out_f32,
+                                          void* trace, void* stream) {
+  DGLB_TRY
+  DGLB_CHECK(dtype == kBF16 || dtype == kF32, "sage_layer_tc: bf16 or fp32");
+  DGLB_CHECK(Np % 32 == 0 && Np >= 32 && Np <= 256, "Np must be a multiple of 32 in [32, 256]");
+  DGLB_CHECK(((uintptr_t)X % 16 == 0) && ((uintptr_t)Wt % 16 == 0) && ((uintptr_t)out % 16 == 0), "16-byte alignment required");
+  DGLB_CHECK(!out_f32 || p_drop == 0.f, "fp32 logits output does not support dropout");
+  if (n_cap == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dtype == kBF16)
+    launch_sage_layer<__nv_bfloat16>(X, self_ids, nbr, cnt, n_dev, n_cap, fanout, Fp, Np, Wt, Wt_lo, bias, out, A_out, relu,
+                                     p_drop, seed, step_dev, out_f32, trace, st);
+  else
+    launch_sage_layer<float>(X, self_ids, nbr, cnt, n_dev, n_cap, fanout, Fp, Np, Wt, Wt_lo, bias, out, A_out, relu, p_drop,
+                             seed, step_dev, out_f32, trace, st);
   DGLB_CATCH
 }

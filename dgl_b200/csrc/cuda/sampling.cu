@@ -227,27 +227,39 @@ __global__ void __launch_bounds__(128) sample_fill_kernel(const I* __restrict__ 
         emit(c, pick);
       }
     } else {
-      // keep the cnt smallest exponential-race keys (insertion into a sorted local buffer)
+      // Exponential race (Efraimidis-Spirakis): keep the cnt smallest keys -log(u_k) / w_k. The keys are a pure function
+      // of (seed, row, k), so rows that need more than KMAX picks (fanout = -1 or fanout > 128 on a hub) are served in
+      // several passes: each pass collects the next KMAX smallest (key, k) pairs above the last emitted pair in a
+      // sorted register/local buffer. Every slot [0, cnt) of the output is therefore written for any cnt.
       constexpr int KMAX = 128;
       float keys[KMAX];
       int32_t idx[KMAX];
-      const int kk = (int)min(cnt, (int64_t)KMAX);
-      int m = 0;
-      for (int64_t k = 0; k < deg; ++k) {
-        const float wk = w(k);
-        if (wk <= 0.f) continue;
-        const float key = -__logf(rng_uniform(seed, stream, k)) / wk;
-        if (m < kk) {
-          int p = m++;
-          while (p > 0 && keys[p - 1] > key) { keys[p] = keys[p - 1]; idx[p] = idx[p - 1]; --p; }
-          keys[p] = key; idx[p] = (int32_t)k;
-        } else if (key < keys[kk - 1]) {
-          int p = kk - 1;
-          while (p > 0 && keys[p - 1] > key) { keys[p] = keys[p - 1]; idx[p] = idx[p - 1]; --p; }
-          keys[p] = key; idx[p] = (int32_t)k;
+      float last_key = -1.f;
+      int64_t last_k = -1, emitted = 0;
+      while (emitted < cnt) {
+        const int kk = (int)min(cnt - emitted, (int64_t)KMAX);
+        int m = 0;
+        for (int64_t k = 0; k < deg; ++k) {
+          const float wk = w(k);
+          if (wk <= 0.f) continue;
+          const float key = -__logf(rng_uniform(seed, stream, k)) / wk;
+          if (key < last_key || (key == last_key && k <= last_k)) continue;  // emitted by an earlier pass
+          if (m < kk) {
+            int p = m++;
+            while (p > 0 && keys[p - 1] > key) { keys[p] = keys[p - 1]; idx[p] = idx[p - 1]; --p; }
+            keys[p] = key; idx[p] = (int32_t)k;
+          } else if (key < keys[kk - 1]) {
+            int p = kk - 1;
+            while (p > 0 && keys[p - 1] > key) { keys[p] = keys[p - 1]; idx[p] = idx[p - 1]; --p; }
+            keys[p] = key; idx[p] = (int32_t)k;
+          }
         }
+        if (m == 0) break;  // cannot happen: cnt <= number of positive-probability edges (sample_count_kernel)
+        for (int c = 0; c < m; ++c) emit(emitted + c, idx[c]);
+        emitted += m;
+        last_key = keys[m - 1];
+        last_k = idx[m - 1];
       }
-      for (int c = 0; c < kk && c < m; ++c) emit(c, idx[c]);
     }
   }
 }

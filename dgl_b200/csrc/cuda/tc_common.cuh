@@ -101,6 +101,24 @@ __device__ __forceinline__ uint64_t make_sw128_mnmajor_desc(uint32_t smem_addr, 
   return d;
 }
 
+// MN-major operands of 32-bit element types (kind::tf32) have ONE legal swizzled layout: SWIZZLE_128B with a 32-byte
+// base ("128B_BASE32B", layout type 1): the 32-byte chunks of a 128-byte row are XOR-swizzled by (k-row & 3), an atom is
+// 4 k-rows x 128 B (512 B) and atoms repeat along K with SBO = 512 B. TMA writes the same image with
+// CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B. (16-byte-base SWIZZLE_128B is only legal for K-major tf32.)
+__device__ __forceinline__ uint64_t make_sw128b32_mnmajor_desc(uint32_t smem_addr, uint32_t box_stride_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((box_stride_bytes >> 4) & 0x3FFF) << 16;  // leading byte offset: next 128-byte-wide box along MN
+  d |= (uint64_t)(512 >> 4) << 32;                          // stride byte offset: next 4-row atom along K
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;                                   // SWIZZLE_128B_BASE32B
+  return d;
+}
+// byte offset of (k-row r, 16-byte chunk c) inside a [rows x 128 B] box of that layout
+__device__ __forceinline__ uint32_t sw128b32_off(int r, int c) {
+  return (uint32_t)(r * 128 + ((((c >> 1) ^ (r & 3)) << 5) | ((c & 1) << 4)));
+}
+
 // swizzled byte offset of (row r, 16-byte chunk c) inside a [rows x 128 B] K-major SW128 tile
 __device__ __forceinline__ uint32_t sw128_off(int r, int c) { return (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4); }
 
@@ -108,6 +126,86 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Operand-type traits shared by the engine kernels (sage_tc.cu, sage_bwd_tc.cu).
+//   bf16 : kind::f16, one operand plane, 64 elements per 128-byte swizzle row, K = 16 per instruction.
+//   fp32 : kind::tf32 on an error-compensated split x = hi + lo (hi = x rounded to TF32, lo = x - hi, exact in fp32).
+//          Every product is issued as lo*hi + hi*lo + hi*hi into the same fp32 TMEM accumulator, which restores
+//          fp32-level accuracy (relative error ~2^-21 per product, below the fp32 accumulation noise of K >= 64) on the
+//          tensor cores - the "3xTF32" scheme. Two operand planes, 32 elements per 128-byte row, K = 8 per instruction.
+template <typename T>
+struct TcT;
+template <>
+struct TcT<__nv_bfloat16> {
+  static constexpr int kPlanes = 1, kRowElems = 64, kMmaK = 16, kFmt = 1, kProducts = 1;
+  static constexpr CUtensorMapDataType kTmap = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+};
+template <>
+struct TcT<float> {
+  static constexpr int kPlanes = 2, kRowElems = 32, kMmaK = 8, kFmt = 2, kProducts = 3;
+  static constexpr CUtensorMapDataType kTmap = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+};
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+// One logical MMA step on operand planes laid out `a_plane` / `b_plane` bytes apart (fp32: plane 0 = hi, plane 1 = lo).
+// DescFn turns a shared-memory byte address into the (K-major or MN-major) matrix descriptor.
+template <typename T, typename DA, typename DB>
+__device__ __forceinline__ void umma_step(uint32_t tmem_d, uint32_t a_addr, uint32_t a_plane, DA da, uint32_t b_addr,
+                                          uint32_t b_plane, DB db, uint32_t idesc, bool accumulate) {
+  if constexpr (TcT<T>::kPlanes == 1) {
+    umma_bf16(tmem_d, da(a_addr), db(b_addr), idesc, accumulate ? 1u : 0u);
+  } else {
+    // small terms first: lo*hi, hi*lo, then hi*hi
+    umma_tf32(tmem_d, da(a_addr + a_plane), db(b_addr), idesc, accumulate ? 1u : 0u);
+    umma_tf32(tmem_d, da(a_addr), db(b_addr + b_plane), idesc, 1u);
+    umma_tf32(tmem_d, da(a_addr), db(b_addr), idesc, 1u);
+  }
+}
+
+// MN-major operand helpers selected by the element type (see make_sw128b32_mnmajor_desc for the 32-bit case)
+template <typename T>
+__device__ __forceinline__ uint64_t make_mnmajor_desc(uint32_t smem_addr, uint32_t box_stride_bytes) {
+  if constexpr (sizeof(T) == 4) return make_sw128b32_mnmajor_desc(smem_addr, box_stride_bytes);
+  else return make_sw128_mnmajor_desc(smem_addr, box_stride_bytes);
+}
+template <typename T>
+__device__ __forceinline__ uint32_t mn_box_off(int r, int c) {
+  if constexpr (sizeof(T) == 4) return sw128b32_off(r, c);
+  else return sw128_off(r, c);
+}
+
+// x = hi + lo with hi exactly representable in TF32 (round-to-nearest on the 10-bit mantissa)
+__device__ __forceinline__ void tf32_split(float x, float& hi, float& lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h & 0xFFFFE000u);
+  lo = x - hi;
+}
+__device__ __forceinline__ void tf32_split4(const float4& x, float4& hi, float4& lo) {
+  tf32_split(x.x, hi.x, lo.x); tf32_split(x.y, hi.y, lo.y); tf32_split(x.z, hi.z, lo.z); tf32_split(x.w, hi.w, lo.w);
+}
+
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// row-granular bulk copy global -> shared (the TMA engine without a tensor map; SASS: UBLKCP), completion on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(bar)
+               : "memory");
+}
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

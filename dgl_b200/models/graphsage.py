@@ -95,15 +95,24 @@ class FusedSAGETrainer:
         self.dtype = dtype
         # tensor-core path (tcgen05 fused gather+GEMM kernel): bf16, hidden % 32 == 0, feature rows padded to a
         # multiple of 64 elements (zero columns: mathematically identical, their weights receive zero gradient)
+        tc_ok = dtype in (torch.bfloat16, torch.float32) and hidden in (128, 256) and num_classes <= 64
         if use_tc is None:
             from ..global_config import get_gemm_path
             path = get_gemm_path()                      # DGLB200_GEMM = auto | tc | cublas
-            use_tc = dtype == torch.bfloat16 and hidden % 64 == 0 and hidden <= 256
+            use_tc = tc_ok
             if path == "cublas":
                 use_tc = False
             elif path == "tc" and not use_tc:
-                raise ValueError("DGLB200_GEMM=tc needs bf16 and a hidden size that is a multiple of 64 (<= 256)")
+                raise ValueError("DGLB200_GEMM=tc needs hidden in {128, 256} and <= 64 classes")
+        elif use_tc and not tc_ok:
+            raise ValueError("the tcgen05 engine needs hidden in {128, 256} and <= 64 classes")
         self.use_tc = bool(use_tc)
+        # bf16: kind::f16 MMAs on bf16 storage. fp32: fp32 storage + 3xTF32 split products (fp32-level accuracy, see
+        # csrc/cuda/tc_common.cuh) - the engine never drops below the precision the caller asked for.
+        self.precision_note = (
+            ("bf16 storage/operands, fp32 accumulate (tcgen05 kind::f16)" if dtype == torch.bfloat16 else
+             "fp32 storage, fp32 accumulate, 3xTF32 error-compensated tcgen05 products (fp32-equivalent)")
+            if self.use_tc else ("bf16 operands via cuBLAS" if dtype == torch.bfloat16 else "fp32 via cuBLAS (TF32 off)"))
         self.F_orig = feat.shape[1]
         if self.use_tc and feat.shape[1] % 64:
             Fp = (feat.shape[1] + 63) // 64 * 64
@@ -166,6 +175,7 @@ class FusedSAGETrainer:
         self.use_graph = use_cuda_graph
         self.graph = None
         self._side_stream = torch.cuda.Stream(self.dev)
+        self._zero_stream = torch.cuda.Stream(self.dev)
         self._probe_mm()
         self.gpu_launches_per_step = 0
 
@@ -193,6 +203,10 @@ class FusedSAGETrainer:
         self.adam_m = torch.zeros_like(self.param)
         self.adam_v = torch.zeros_like(self.param)
         self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+        # fp32 tensor-core operands: hi / lo planes of the TF32 split, refreshed by the optimizer epilogue
+        split = self.use_tc and self.dtype == torch.float32
+        self.shadow_hi = torch.zeros(off, dtype=torch.float32, device=dev) if split else None
+        self.shadow_lo = torch.zeros(off, dtype=torch.float32, device=dev) if split else None
         # flat gradient + 8 trailing words (loss, accuracy counter): one memset per step clears all of it
         self.zero_block = (torch.zeros(off + 8, dtype=torch.float32, device=dev) if self.comm is None
                            else self.comm.grad_buffer(off + 8))
@@ -203,7 +217,8 @@ class FusedSAGETrainer:
         gen.manual_seed(self.seed)
         gain = math.sqrt(2.0)
         self.W, self.b, self.Wb, self.gW, self.gb = [], [], [], [], []
-        self.Wt = [None] * self.L      # [n_pad, 2*in] bf16 K-major operand of the fused layer kernel
+        self.Wt = [None] * self.L      # [n_pad, 2*in] K-major operand of the fused layer kernel (bf16, or fp32 hi plane)
+        self.Wt_lo = [None] * self.L   # fp32 only: lo plane
         self.gWt = [None] * self.L     # gradient in the same layout
         self.b_pad = [None] * self.L   # bias incl. padding entries
         for kind, l, o, shape in segs:
@@ -231,14 +246,28 @@ class FusedSAGETrainer:
                 self.Wb.append(wview(self.shadow) if self.dtype == torch.bfloat16 else view)
                 self.gW.append(wview(self.grad))
                 if self.tc_layer[l]:
-                    self.Wt[l] = self.shadow[o:o + n].view(npad, k2)
+                    if split:
+                        self.Wt[l] = self.shadow_hi[o:o + n].view(npad, k2)
+                        self.Wt_lo[l] = self.shadow_lo[o:o + n].view(npad, k2)
+                    else:
+                        self.Wt[l] = self.shadow[o:o + n].view(npad, k2)
                     self.gWt[l] = self.grad[o:o + n].view(npad, k2)
             else:
                 self.b.append(self.param[o:o + n][:n_out])
                 self.gb.append(self.grad[o:o + n][:n_out])
                 self.b_pad[l] = self.param[o:o + n]
-        self.shadow.copy_(self.param)
+                self.gb_pad = getattr(self, "gb_pad", [None] * self.L)
+                self.gb_pad[l] = self.grad[o:o + n]
+        self._refresh_shadows()
         self.step_dev = torch.zeros(1, dtype=torch.int64, device=dev)
+
+    def _refresh_shadows(self):
+        """Operand copies of the fp32 master weights: bf16 shadow, or the TF32 hi / lo planes."""
+        self.shadow.copy_(self.param)
+        if self.shadow_hi is not None:
+            hi = (self.param.view(torch.int32) + 0x1000).bitwise_and(-8192).view(torch.float32)  # round-to-nearest TF32
+            self.shadow_hi.copy_(hi)
+            self.shadow_lo.copy_(self.param - hi)
 
     def state_dict(self):
         return {"param": self.param.clone(), "m": self.adam_m.clone(), "v": self.adam_v.clone(),
@@ -246,7 +275,7 @@ class FusedSAGETrainer:
 
     def load_state_dict(self, sd):
         self.param.copy_(sd["param"]); self.adam_m.copy_(sd["m"]); self.adam_v.copy_(sd["v"])
-        self.step_dev.copy_(sd["step"]); self.shadow.copy_(self.param)
+        self.step_dev.copy_(sd["step"]); self._refresh_shadows()
 
     def export_to_module(self, module: GraphSAGE):
         """Copy the trained weights into a ``GraphSAGE`` module (fc_self / fc_neigh / bias)."""
@@ -267,7 +296,7 @@ class FusedSAGETrainer:
                 self.W[l][:ko].copy_(layer.fc_self.weight.t())
                 self.W[l][k:k + ko].copy_(layer.fc_neigh.weight.t())
                 self.b[l].copy_(layer.fc_self.bias)
-            self.shadow.copy_(self.param)
+            self._refresh_shadows()
 
     # ------------------------------------------------------------------ capacity calibration
     def _calibrate_caps(self, margin, trials=24):
@@ -351,8 +380,10 @@ class FusedSAGETrainer:
                 self.nbr[l] = torch.empty((cap, f), dtype=i32, device=dev)
             else:
                 self.nbr[l] = self.nbr_g[l]
-        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.edges_total = torch.zeros(16, dtype=torch.int64, device=dev)  # running count of sampled edges
+        if not hasattr(self, "overflow"):   # survive a re-allocation after a capacity overflow
+            self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.edges_total = torch.zeros(16, dtype=torch.int64, device=dev)  # running count of sampled edges
+            self.overflow_steps = 0
         # activations
         self.A = [None] * (L + 1)
         self.dH = [None] * (L + 1)
@@ -367,7 +398,31 @@ class FusedSAGETrainer:
                 self.Hbuf[l] = torch.zeros((self.caps[l], self.out_dims[l - 1]), dtype=self.dtype, device=dev)
         if self.tc_last:
             self.logits_pad = torch.zeros((self.B, 64), dtype=torch.float32, device=dev)
-            self.dlogits16 = torch.zeros((self.B, 64), dtype=torch.bfloat16, device=dev)
+            # CE gradient in the operand format of the backward kernels: bf16, or the fp32 hi / lo planes
+            self.dlogits16 = torch.zeros((self.B, 64), dtype=self.dtype, device=dev)
+            self.dlogits_lo = torch.zeros((self.B, 64), dtype=torch.float32, device=dev) if self.shadow_hi is not None else None
+            # fp32: dlogits16 / dlogits_lo are the TF32 hi / lo planes (TMA operands of the dA kernel), dlogits_full the
+            # unsplit value (the dW kernel splits its operands itself)
+            self.dlogits_full = (torch.zeros((self.B, 64), dtype=torch.float32, device=dev)
+                                 if self.shadow_hi is not None else self.dlogits16)
+        # dZ of the hidden layers that feed a dA kernel (layers 2..L-1), written once by the dW kernel's producers
+        self.dZ = [None] * (L + 1)
+        self.dZ_lo = [None] * (L + 1)
+        if self.use_tc:
+            for l in range(2, L):
+                self.dZ[l] = torch.zeros((self.caps[l], self.out_dims[l - 1]), dtype=self.dtype, device=dev)
+                if self.shadow_hi is not None:
+                    self.dZ_lo[l] = torch.zeros((self.caps[l], self.out_dims[l - 1]), dtype=torch.float32, device=dev)
+            # all dH buffers in one allocation: ONE memset node per step clears them (side stream, off the critical path)
+            tot = sum(self.caps[l] * self.out_dims[l - 1] for l in range(1, L))
+            self.dH_all = torch.zeros(max(tot, 1), dtype=torch.float32, device=dev)
+            o = 0
+            for l in range(1, L):
+                k = self.caps[l] * self.out_dims[l - 1]
+                self.dH[l] = self.dH_all[o:o + k].view(self.caps[l], self.out_dims[l - 1])
+                o += k
+        thresh = min(255, int(min(self.p_drop, 1.0) * 256.0 + 0.5)) if self.p_drop > 0 else 0
+        self.keep_scale = 256.0 / (256.0 - thresh)  # the kernels quantise the drop probability to 1/256
 
     def _probe_mm(self):
         """Can torch.mm emit an fp32 result from bf16 operands (keeps dW in full precision)?"""
@@ -396,6 +451,13 @@ class FusedSAGETrainer:
         L, dt, it = self.L, dtype_code(self.dtype), id_code(torch.int32)
         self._launch_count = 0
         self._my_kernels = 0
+        if self.use_tc and L > 1:
+            # the fp32 gradient buffers the dA kernels scatter into: cleared by one memset that overlaps sampling + forward
+            zs = self._zero_stream
+            zs.wait_stream(torch.cuda.current_stream(self.dev))
+            with torch.cuda.stream(zs):
+                self.dH_all.zero_()
+            self._launch_count += 1
         # ---------------- sampling + compaction, output layer first
         for l in range(L, 0, -1):
             cap, f = self.caps[l], self.fanouts[l - 1]
@@ -417,9 +479,9 @@ class FusedSAGETrainer:
                 # gather + mean + concat + GEMM + bias (+ ReLU + dropout) in ONE tcgen05 kernel; the output layer
                 # emits fp32 logits (bias included) into a 64-column padded buffer
                 last = l == L
-                self._launch("dglb200_engine_sage_layer_tc", "ppppp" + "l" + "iii" + "pppp" + "iflpip", _p(X),
+                self._launch("dglb200_engine_sage_layer_tc", "ippppp" + "l" + "iii" + "ppppp" + "iflpip", dt, _p(X),
                              _p(self.S[1]) if l == 1 else 0, _p(self.nbr[l]), _p(self.cnt[l]), _p(self.n[l]), cap, f, Fi,
-                             self.n_pad[l - 1], _p(self.Wt[l - 1]), _p(self.b_pad[l - 1]),
+                             self.n_pad[l - 1], _p(self.Wt[l - 1]), _p(self.Wt_lo[l - 1]), _p(self.b_pad[l - 1]),
                              _p(self.logits_pad if last else self.Hbuf[l]), _p(self.A[l]), 0 if last else 1,
                              0.0 if last else float(self.p_drop), self.seed * 104729 + l, _p(self.step_dev),
                              1 if last else 0, 0)
@@ -444,19 +506,25 @@ class FusedSAGETrainer:
         self.zero_block.zero_()
         self._launch_count += 1
         if self.tc_last:
-            self._launch("dglb200_engine_ce_loss2", "pipppplippipp" + "p", _p(self.logits_pad), 64, 0, _p(self.labels),
-                         _p(self.S[L]), _p(self.n[L]), self.B, self.C, 0, _p(self.dlogits16), 64, _p(self.gb[L - 1]),
-                         _p(self.loss_dev), _p(self.correct_dev))
+            split = self.dlogits_lo is not None
+            self._launch("dglb200_engine_ce_loss2", "pipppplippipp" + "ppp", _p(self.logits_pad), 64, 0, _p(self.labels),
+                         _p(self.S[L]), _p(self.n[L]), self.B, self.C, _p(self.dlogits_full) if split else 0,
+                         0 if split else _p(self.dlogits16), 64, _p(self.gb[L - 1]),
+                         _p(self.loss_dev), _p(self.correct_dev), _p(self.dlogits16) if split else 0, _p(self.dlogits_lo))
         else:
-            self._launch("dglb200_engine_ce_loss2", "pipppplippipp" + "p", _p(logits), self.C, _p(self.b[L - 1]),
+            self._launch("dglb200_engine_ce_loss2", "pipppplippipp" + "ppp", _p(logits), self.C, _p(self.b[L - 1]),
                          _p(self.labels), _p(self.S[L]), _p(self.n[L]), self.B, self.C, _p(self.dlogits), 0, 0,
-                         _p(self.gb[L - 1]), _p(self.loss_dev), _p(self.correct_dev))
+                         _p(self.gb[L - 1]), _p(self.loss_dev), _p(self.correct_dev), 0, 0)
         # ---------------- backward
         # The weight-gradient GEMM of a layer does not feed the dA -> scatter -> dReLU chain that produces the next
         # layer's dZ, so it runs on a side stream (forked/joined with events, capturable) and overlaps with that chain.
-        dZ = self.dlogits16 if self.tc_last else self.dlogits
         main = torch.cuda.current_stream(self.dev)
         side = self._side_stream
+        if self.use_tc:
+            self._backward_tc(main, side)
+            self._finish_step()
+            return
+        dZ = self.dlogits
         keep = [dZ]  # every dZ stays referenced until the join: the allocator must not recycle a block the side stream reads
         for l in range(L, 0, -1):
             cap, f, Fi = self.caps[l], self.fanouts[l - 1], self.in_dims[l - 1]
@@ -495,6 +563,39 @@ class FusedSAGETrainer:
                 dZ = dZn
                 keep.append(dZn)
         main.wait_stream(side)
+        self._finish_step()
+
+    def _backward_tc(self, main, side):
+        """Backward on tcgen05: per layer one weight-gradient kernel (dZ built on the fly from the incoming fp32
+        gradient + ReLU/dropout mask, bias gradient in the same pass) and one input-gradient kernel whose epilogue IS
+        the scatter into the layer below. No cuBLAS, no elementwise kernels."""
+        L, dt = self.L, dtype_code(self.dtype)
+        sig_dw = "ipppiifpiipl" + "pllpppi"
+        sig_da = "ipppppppliiip"
+        # layer L: dZ = dlogits (CE kernel). Swapped roles (M side = A columns) because n_pad = 64 < one MMA M tile.
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            k2 = 2 * self.in_dims[L - 1]
+            self._launch("dglb200_engine_sage_bwd_dw", sig_dw, dt, 0, 0, _p(self.A[L]), k2, k2, 1.0,
+                         _p(self.dlogits_full), 64, 64, _p(self.n[L]), self.caps[L], _p(self.gWt[L - 1]), 1, k2, 0, 0, 0, 0)
+        dz, dz_lo = self.dlogits16, self.dlogits_lo
+        for l in range(L, 1, -1):
+            Fi = self.in_dims[l - 1]
+            if l == L:
+                main.wait_stream(self._zero_stream)  # dH buffers were cleared off the critical path (see _step_impl)
+            self._launch("dglb200_engine_sage_bwd_da", sig_da, dt, _p(dz), _p(dz_lo), _p(self.Wt[l - 1]),
+                         _p(self.Wt_lo[l - 1]), _p(self.nbr[l]), _p(self.cnt[l]), _p(self.n[l]), self.caps[l],
+                         self.fanouts[l - 1], self.n_pad[l - 1], Fi, _p(self.dH[l - 1]))
+            lo = l - 1  # weight gradient of the layer below; its dZ feeds the next dA kernel
+            k2 = 2 * self.in_dims[lo - 1]
+            self._launch("dglb200_engine_sage_bwd_dw", sig_dw, dt, _p(self.dH[lo]), _p(self.Hbuf[lo]), 0,
+                         self.out_dims[lo - 1], self.out_dims[lo - 1], float(self.keep_scale), _p(self.A[lo]), k2, k2,
+                         _p(self.n[lo]), self.caps[lo], _p(self.gWt[lo - 1]), k2, 1, _p(self.gb_pad[lo - 1]),
+                         _p(self.dZ[lo]), _p(self.dZ_lo[lo]), 0)
+            dz, dz_lo = self.dZ[lo], self.dZ_lo[lo]
+        main.wait_stream(side)
+
+    def _finish_step(self):
         # ---------------- gradient all-reduce fused with Adam
         if self.comm is not None:
             self.comm.barrier(0)  # every rank's gradients are complete and visible
@@ -510,9 +611,10 @@ class FusedSAGETrainer:
                 self._launch_count += 2
             peers = (ctypes.c_void_p * 1)(self.grad.data_ptr())
         self._peers_keepalive = peers
-        self._launch("dglb200_engine_allreduce_adam", "ppippplfffffp", _p(self.param), ctypes.cast(peers, ctypes.c_void_p),
+        self._launch("dglb200_engine_allreduce_adam", "ppippplfffffppp", _p(self.param), ctypes.cast(peers, ctypes.c_void_p),
                      self.world, _p(self.adam_m), _p(self.adam_v), _p(self.shadow) if self.dtype == torch.bfloat16 else 0, self.numel, float(self.lr),
-                     float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd), _p(self.step_dev), kernels=2)
+                     float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd), _p(self.step_dev),
+                     _p(self.shadow_hi), _p(self.shadow_lo), kernels=2)
         if self.comm is not None:
             self.comm.barrier(1)  # all ranks finished reading before anyone rewrites its gradients
             self._launch_count += 1
@@ -577,40 +679,65 @@ class FusedSAGETrainer:
         torch.cuda.current_stream(self.dev).synchronize()
         return float(self.loss_pinned[0])
 
+    def check_step_overflow(self):
+        """Synchronous variant for ``train_step`` loops: True if any step since the last check overflowed the
+        calibrated frontier capacities (the engine then switches to worst-case capacities)."""
+        if self.check_overflow():
+            self.overflow_steps += 1
+            return True
+        return False
+
     def last_loss(self):
         return float(self.loss_pinned[0])
 
     def fit(self, batches, on_step=None):
         """Pipelined training over an iterable of seed batches; returns the list of per-step losses.
 
-        Every step still copies its seeds from pinned host memory to the device and its loss back into pinned host
-        memory, but the host reads the loss of step ``i`` only after it has enqueued step ``i + RING - 1``, so the
-        CPU never idles the GPU (the reference's loop reads ``loss.item()`` synchronously,
-        examples/multigpu/node_classification_sage.py:229-256). ``on_step(i, loss)`` is called as losses arrive."""
+        Every step still copies its seeds from pinned host memory to the device and its loss (plus the frontier
+        overflow flag) back into pinned host memory, but the host reads the result of step ``i`` only after it has
+        enqueued step ``i + RING - 1``, so the CPU never idles the GPU (the reference's loop reads ``loss.item()``
+        synchronously, examples/multigpu/node_classification_sage.py:229-256). ``on_step(i, loss)`` is called as losses
+        arrive. A step whose sampled frontier exceeded the calibrated capacities trained on a truncated neighbourhood:
+        it is counted in ``overflow_steps`` and the engine falls back to worst-case capacities before the next step."""
         import collections
         if not hasattr(self, "loss_ring"):
             self.loss_ring = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(self.RING)]
+            self.ovf_ring = [torch.zeros(1, dtype=torch.int32).pin_memory() for _ in range(self.RING)]
         pending = collections.deque()
         losses = []
+        state = {"overflow": False}
 
         def drain_one():
             k, ev = pending.popleft()
             ev.synchronize()
             losses.append(float(self.loss_ring[k][0]))
+            if int(self.ovf_ring[k][0]) != 0:
+                state["overflow"] = True
             if on_step is not None:
                 on_step(len(losses) - 1, losses[-1])
 
         for i, seeds in enumerate(batches):
             if len(pending) == self.RING:
                 drain_one()
+            if state["overflow"]:
+                while pending:
+                    drain_one()
+                torch.cuda.synchronize(self.dev)
+                self.overflow_steps += 1
+                self.check_overflow()          # worst-case capacities, buffers re-allocated, graph re-captured lazily
+                state["overflow"] = False
             self.step_async(seeds)
             k = i % self.RING
             self.loss_ring[k].copy_(self.loss_dev, non_blocking=True)
+            self.ovf_ring[k].copy_(self.overflow, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record()
             pending.append((k, ev))
         while pending:
             drain_one()
+        if state["overflow"]:
+            self.overflow_steps += 1
+            self.check_overflow()
         return losses
 
     def total_sampled_edges(self):

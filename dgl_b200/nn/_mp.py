@@ -1,0 +1,139 @@
+"""Tensor-level message-passing vocabulary of ``dgl_b200.nn``.
+
+Every layer of this package is written as a short composition of the functions below, which call the framework's own
+sm_100a operators (``ops.gspmm`` / ``gsddmm`` / ``edge_softmax`` / fused kernels) on plain tensors: no node/edge frames
+are touched, nothing is stored on the graph, no ``local_scope`` is needed, and - unlike the frame-based formulation of
+the reference's layers (python/dgl/nn/pytorch/conv/*.py) - no step synchronises with the host.
+
+Conventions: ``g`` is a homogeneous graph, a bipartite graph or a block (single edge type); ``x_src`` lives on source
+nodes, results on destination nodes; edge tensors follow the graph's edge order.
+"""
+from __future__ import annotations
+
+import torch
+
+from .. import ops
+from ..base import DGLError
+
+__all__ = ["src_dst", "gather_sum", "gather_mean", "gather_max", "gather_min", "gather", "edge_reduce", "pair_op",
+           "attend", "degrees", "sym_norm_propagate", "require_in_edges", "hop", "edge_softmax_agg"]
+
+
+def src_dst(g, feat):
+    """Split a layer input into (source features, destination features).
+
+    A pair is returned as is; on a block the destination nodes are the leading rows of the source nodes."""
+    if isinstance(feat, (tuple, list)):
+        return feat[0], feat[1]
+    if getattr(g, "is_block", False):
+        return feat, feat[: g.number_of_dst_nodes()]
+    return feat, feat
+
+
+def _flat(x):
+    """[N, a, b, ...] -> ([N, a*b*...], tail) so the operators see 2-D operands."""
+    if x.dim() <= 2:
+        return x, None
+    return x.reshape(x.shape[0], -1), tuple(x.shape[1:])
+
+
+def _unflat(y, tail):
+    return y if tail is None else y.reshape(y.shape[0], *tail)
+
+
+def gather(g, x_src, how="sum", w=None):
+    """out[v] = reduce_{u -> v} (w[e] * x_src[u]); ``how`` in sum | mean | max | min; ``w`` is [E] or broadcastable
+    to the message shape (None = unweighted copy)."""
+    if w is None:
+        return ops.gspmm(g, "copy_lhs", how, x_src, None)
+    if w.dim() < x_src.dim():
+        w = w.reshape(w.shape + (1,) * (x_src.dim() - w.dim()))
+    return ops.gspmm(g, "mul", how, x_src, w)
+
+
+def gather_sum(g, x_src, w=None):
+    return gather(g, x_src, "sum", w)
+
+
+def gather_mean(g, x_src, w=None):
+    return gather(g, x_src, "mean", w)
+
+
+def gather_max(g, x_src):
+    return gather(g, x_src, "max")
+
+
+def gather_min(g, x_src):
+    return gather(g, x_src, "min")
+
+
+def edge_reduce(g, e, how="sum"):
+    """out[v] = reduce over the in-edges of v of the edge tensor ``e``."""
+    return ops.gspmm(g, "copy_rhs", how, None, e)
+
+
+def pair_op(g, op, x_src, x_dst):
+    """Per-edge binary op between the source and the destination endpoint: add | sub | mul | div | dot."""
+    return ops.gsddmm(g, op, x_src, x_dst, "u", "v")
+
+
+def degrees(g, side="in", dtype=torch.float32, floor=1.0):
+    """Clamped node degrees as a float column-free vector (``side`` = in | out)."""
+    d = g.in_degrees() if side == "in" else g.out_degrees()
+    d = d.to(dtype)
+    return d.clamp(min=floor) if floor is not None else d
+
+
+def require_in_edges(g, allow, layer):
+    """Raise if a destination node has no in-edge (its output would silently be zero / the softmax undefined).
+    The verdict is cached per graph structure, so a training loop pays the reduction + host read ONCE instead of
+    every forward (the reference layers re-check, and synchronise, on every call)."""
+    if allow:
+        return
+    key = "_no_isolated_dst"
+    ok = getattr(g, key, None)
+    if ok is None:
+        ok = not bool((g.in_degrees() == 0).any()) if g.number_of_edges() or g.number_of_dst_nodes() else True
+        try:
+            setattr(g, key, ok)
+        except AttributeError:
+            pass
+    if not ok:
+        raise DGLError(
+            f"There are 0-in-degree nodes in the graph, output for those nodes will be invalid. Add self-loops with "
+            f"`g = dgl.add_self_loop(g)` or construct {layer} with `allow_zero_in_degree=True` to suppress this check.")
+
+
+def sym_norm_propagate(g, x_src, mode="both", w=None):
+    """Degree-normalised aggregation of GCN-style layers.
+
+    both : D_in^-1/2 A D_out^-1/2 x      right : D_in^-1 A x      left : A D_out^-1 x      none : A x
+    With edge weights ``w`` the structural degrees are still used (weights are expected to be pre-normalised, e.g. by
+    ``EdgeWeightNorm``)."""
+    if mode in ("both", "left"):
+        s = degrees(g, "out", x_src.dtype).pow(-0.5 if mode == "both" else -1.0)
+        x_src = x_src * s.reshape((-1,) + (1,) * (x_src.dim() - 1))
+    y = gather_sum(g, x_src, w)
+    if mode in ("both", "right"):
+        s = degrees(g, "in", y.dtype).pow(-0.5 if mode == "both" else -1.0)
+        y = y * s.reshape((-1,) + (1,) * (y.dim() - 1))
+    return y
+
+
+def hop(g, x, norm=None, w=None):
+    """One propagation step on a homogeneous graph with an optional symmetric pre/post scaling vector ``norm``
+    (already shaped [N, 1]): norm * A (norm * x)."""
+    if norm is not None:
+        x = x * norm
+    y = gather_sum(g, x, w)
+    return y * norm if norm is not None else y
+
+
+def attend(g, scores):
+    """Softmax of per-edge scores over the in-edges of every destination node."""
+    return ops.edge_softmax(g, scores)
+
+
+def edge_softmax_agg(g, scores, values_src):
+    """softmax(scores) over in-edges, then the attention-weighted sum of source values: the GAT aggregation."""
+    return gather_sum(g, values_src, attend(g, scores))

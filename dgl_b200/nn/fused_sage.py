@@ -2,13 +2,15 @@
 
 The block's CSC (every destination has at most ``fanout`` in-edges) is turned into the ELL layout of the engine kernel
 and the layer runs as ONE kernel (csrc/cuda/sage_tc.cu): gather + mean + [self | neigh] concat in shared memory ->
-tcgen05.mma against [W_self | W_neigh]^T (TMA) -> bias (+ReLU) epilogue. The backward reuses the engine's pieces: two
-cuBLAS GEMMs (dW, dA) and the vector-``red.add`` scatter of the mean aggregation. This is the same kernel
-``FusedSAGETrainer`` replays inside its CUDA graph, made available to models written against ``dgl.nn``.
+tcgen05.mma against [W_self | W_neigh]^T (TMA) -> bias (+ReLU) epilogue. The backward is two more tcgen05 kernels
+(csrc/cuda/sage_bwd_tc.cu): the split-K weight gradient with MN-major operands and the input gradient whose epilogue
+scatters through the block (``red.global.add.v4.f32``). These are the kernels ``FusedSAGETrainer`` replays inside its
+CUDA graph, made available to models written against ``dgl.nn``.
 
-Requirements (otherwise SAGEConv keeps its g-SpMM + cuBLAS formulation): CUDA, bf16 activations (e.g. under
-``torch.autocast(dtype=torch.bfloat16)``), block whose destination nodes are the first rows of the source nodes,
-max in-degree <= 28, out_feats <= 256, no edge weights.
+Requirements (otherwise SAGEConv keeps its g-SpMM formulation): CUDA, bf16 activations (e.g. under
+``torch.autocast(dtype=torch.bfloat16)``) or fp32 activations (3xTF32 split products, fp32-level accuracy), block whose
+destination nodes are the first rows of the source nodes, max in-degree <= 28, out_feats <= 256, in_feats <= 256,
+no edge weights.
 """
 from __future__ import annotations
 
@@ -16,8 +18,7 @@ import os
 
 import torch
 
-from .._native import loader
-from ..base import dtype_code, id_code
+from ..ops import fused as fused_ops
 
 MAX_FANOUT = 28
 ENABLED = [os.environ.get("DGLB200_FUSED_SAGECONV", "1") != "0"]   # switch for A/B measurements
@@ -50,48 +51,55 @@ def block_to_ell(block):
     return res
 
 
+def _np_pad(out_f):
+    """Output width padded to a size every engine kernel accepts as an MMA N (and the dW kernel as an N-side block)."""
+    return 64 if out_f <= 64 else (128 if out_f <= 128 else 256)
+
+
 class _FusedSAGETC(torch.autograd.Function):
+    """Forward: ONE sage_layer_tc launch. Backward: sage_bwd_dw (weight gradient, MN-major tcgen05 split-K) and
+    sage_bwd_da (input gradient whose epilogue scatters through the ELL block) - no cuBLAS call in either direction."""
+
     @staticmethod
     def forward(ctx, x, w_self, w_neigh, bias, nbr, cnt, fan, relu):
         n_dst = nbr.shape[0]
         F = x.shape[1]
         out_f = w_self.shape[0]
-        Np = _pad_to(out_f, 32)
-        dev = x.device
-        Wt = torch.zeros((Np, 2 * F), dtype=torch.bfloat16, device=dev)          # [W_self | W_neigh], K-major
+        Np = _np_pad(out_f)
+        dev, dt = x.device, x.dtype
+        Wt = torch.zeros((Np, 2 * F), dtype=dt, device=dev)                      # [W_self | W_neigh], K-major
         Wt[:out_f, :F] = w_self
         Wt[:out_f, F:] = w_neigh
         b_pad = torch.zeros(Np, dtype=torch.float32, device=dev)
         if bias is not None:
             b_pad[:out_f] = bias.float()
-        out = torch.empty((n_dst, Np), dtype=torch.bfloat16, device=dev)
-        A = torch.empty((n_dst, 2 * F), dtype=torch.bfloat16, device=dev)        # [x_self | mean x_nbr], kept for dW
         n_dev = torch.tensor([n_dst], dtype=torch.int64, device=dev)
-        loader.cuda_lib().fn("dglb200_engine_sage_layer_tc", "ppppp" + "l" + "iii" + "pppp" + "iflpipp")(
-            x.data_ptr(), 0, nbr.data_ptr(), cnt.data_ptr(), n_dev.data_ptr(), n_dst, fan, F, Np, Wt.data_ptr(),
-            b_pad.data_ptr(), out.data_ptr(), A.data_ptr(), 1 if relu else 0, 0.0, 0, 0, 0, 0, loader.stream_ptr())
-        ctx.save_for_backward(Wt, A, nbr, cnt, n_dev, out if relu else torch.empty(0))
+        planes = fused_ops.tf32_split(Wt) if dt == torch.float32 else (Wt, None)
+        out, A = fused_ops.sage_layer_tc(x, None, nbr, cnt, n_dev, planes[0], b_pad, relu=relu, save_A=True,
+                                         Wt_lo=planes[1])                        # A = [x_self | mean x_nbr], kept for dW
+        ctx.save_for_backward(planes[0], planes[1] if planes[1] is not None else torch.empty(0), A, nbr, cnt, n_dev,
+                              out if relu else torch.empty(0))
         ctx.meta = (x.shape[0], F, out_f, Np, fan, relu, bias is not None)
         return out[:, :out_f]
 
     @staticmethod
     def backward(ctx, dout):
-        Wt, A, nbr, cnt, n_dev, out = ctx.saved_tensors
+        Wt, Wt_lo, A, nbr, cnt, n_dev, out = ctx.saved_tensors
         n_src, F, out_f, Np, fan, relu, has_bias = ctx.meta
         n_dst = nbr.shape[0]
-        dZ = torch.zeros((n_dst, Np), dtype=torch.bfloat16, device=dout.device)
+        dt = A.dtype
+        dZ = torch.zeros((n_dst, Np), dtype=dt, device=dout.device)
         dZ[:, :out_f] = dout
         if relu:
             dZ = dZ * (out > 0)
-        dWt = torch.mm(dZ.t(), A).float()                                        # [Np, 2F]
-        dA = torch.mm(dZ, Wt)                                                    # [n_dst, 2F] bf16
+        # dWt [Np, 2F] = dZ^T A. The M side of the MMA must be a multiple of 128: A's columns (2F, F % 64 == 0) always are.
+        dWt = torch.zeros((Np, 2 * F), dtype=torch.float32, device=dout.device)
+        fused_ops.sage_bwd_dw(dWt, dZ, n_dev, P=A, transposed_out=True)
         dX = torch.zeros((n_src, F), dtype=torch.float32, device=dout.device)
-        loader.cuda_lib().fn("dglb200_engine_scatter_grad", "iippppliipp")(
-            dtype_code(torch.bfloat16), id_code(torch.int32), dA.data_ptr(), nbr.data_ptr(), cnt.data_ptr(),
-            n_dev.data_ptr(), n_dst, fan, F, dX.data_ptr(), loader.stream_ptr())
+        if ctx.needs_input_grad[0]:
+            fused_ops.sage_bwd_da(dZ, Wt, nbr, cnt, n_dev, dX, Wt_lo=Wt_lo if Wt_lo.numel() else None)
         d_bias = dZ.float().sum(0)[:out_f] if has_bias else None
-        return (dX.to(torch.bfloat16), dWt[:out_f, :F].to(torch.bfloat16), dWt[:out_f, F:].to(torch.bfloat16),
-                d_bias, None, None, None, None)
+        return (dX.to(dt), dWt[:out_f, :F].to(dt), dWt[:out_f, F:].to(dt), d_bias, None, None, None, None)
 
 
 def usable(block, feat, out_feats, edge_weight):
@@ -102,7 +110,7 @@ def usable(block, feat, out_feats, edge_weight):
     dt = feat.dtype
     if torch.is_autocast_enabled():
         dt = torch.get_autocast_dtype("cuda") if hasattr(torch, "get_autocast_dtype") else torch.get_autocast_gpu_dtype()
-    return dt == torch.bfloat16 and block.num_src_nodes() >= block.num_dst_nodes() > 0
+    return dt in (torch.bfloat16, torch.float32) and feat.shape[1] <= 256 and block.num_src_nodes() >= block.num_dst_nodes() > 0
 
 
 def fused_sage_mean(block, x, w_self, w_neigh, bias, relu=False):
@@ -112,8 +120,9 @@ def fused_sage_mean(block, x, w_self, w_neigh, bias, relu=False):
         return None
     F = x.shape[1]
     Fp = _pad_to(F, 64)
-    x = x.to(torch.bfloat16)
-    ws, wn = w_self.to(torch.bfloat16), w_neigh.to(torch.bfloat16)
+    dt = torch.bfloat16 if (x.dtype == torch.bfloat16 or torch.is_autocast_enabled()) else torch.float32
+    x = x.to(dt)
+    ws, wn = w_self.to(dt), w_neigh.to(dt)
     if Fp != F:                                                   # zero columns: mathematically identical
         x = torch.nn.functional.pad(x, (0, Fp - F))
         ws = torch.nn.functional.pad(ws, (0, Fp - F))

@@ -1,45 +1,46 @@
-"""Link / edge predictors (parity: /root/reference/python/dgl/nn/pytorch/link/{edgepred,transe,transr}.py)."""
+"""Link / edge scoring heads (API parity: /root/reference/python/dgl/nn/pytorch/link/{edgepred,transe,transr}.py)."""
 from __future__ import annotations
 
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+_PAIR_OPS = {
+    "dot": lambda a, b: (a * b).sum(-1, keepdim=True),
+    "cos": lambda a, b: F.cosine_similarity(a, b).unsqueeze(-1),
+    "ele": lambda a, b: a * b,
+    "cat": lambda a, b: torch.cat((a, b), dim=-1),
+}
+_PAIR_WIDTH = {"dot": lambda d: 1, "cos": lambda d: 1, "ele": lambda d: d, "cat": lambda d: 2 * d}
+
 
 class EdgePredictor(nn.Module):
+    """Combine the two endpoint embeddings of an edge (dot | cos | ele | cat), optionally followed by a linear map."""
+
     def __init__(self, op, in_feats=None, out_feats=None, bias=False):
         super().__init__()
-        assert op in ["dot", "cos", "ele", "cat"], "Expect op to be in ['dot', 'cos', 'ele', 'cat'], got {}".format(op)
+        if op not in _PAIR_OPS:
+            raise AssertionError(f"Expect op to be in ['dot', 'cos', 'ele', 'cat'], got {op}")
         self.op = op
-        if (in_feats is not None) and (out_feats is not None):
-            if op in ["dot", "cos"]:
-                in_feats = 1
-            elif op == "cat":
-                in_feats = 2 * in_feats
-            self.linear = nn.Linear(in_feats, out_feats, bias=bias)
-        else:
-            self.linear = None
+        project = in_feats is not None and out_feats is not None
+        self.linear = nn.Linear(_PAIR_WIDTH[op](in_feats), out_feats, bias=bias) if project else None
 
     def reset_parameters(self):
         if self.linear is not None:
             self.linear.reset_parameters()
 
     def forward(self, h_src, h_dst):
-        if self.op == "dot":
-            N, D = h_src.shape
-            h = torch.bmm(h_src.view(N, 1, D), h_dst.view(N, D, 1)).squeeze(-1)
-        elif self.op == "cos":
-            h = F.cosine_similarity(h_src, h_dst).unsqueeze(-1)
-        elif self.op == "ele":
-            h = h_src * h_dst
-        else:
-            h = torch.cat([h_src, h_dst], dim=-1)
-        if self.linear is not None:
-            h = self.linear(h)
-        return h
+        z = _PAIR_OPS[self.op](h_src, h_dst)
+        return z if self.linear is None else self.linear(z)
+
+
+def _translation_score(head, rel, tail, p):
+    return -(head + rel - tail).norm(p=p, dim=-1)
 
 
 class TransE(nn.Module):
+    """``-|| h + r - t ||_p`` with one learned translation per relation."""
+
     def __init__(self, num_rels, feats, p=1):
         super().__init__()
         self.rel_emb = nn.Embedding(num_rels, feats)
@@ -49,11 +50,12 @@ class TransE(nn.Module):
         self.rel_emb.reset_parameters()
 
     def forward(self, h_head, h_tail, rels):
-        h_rel = self.rel_emb(rels)
-        return -torch.norm(h_head + h_rel - h_tail, p=self.p, dim=-1)
+        return _translation_score(h_head, self.rel_emb(rels), h_tail, self.p)
 
 
 class TransR(nn.Module):
+    """TransE in a relation-specific space: both entities are projected by ``M_r`` [nfeats, rfeats] first."""
+
     def __init__(self, num_rels, rfeats, nfeats, p=1):
         super().__init__()
         self.rel_emb = nn.Embedding(num_rels, rfeats)
@@ -65,8 +67,6 @@ class TransR(nn.Module):
         self.rel_project.reset_parameters()
 
     def forward(self, h_head, h_tail, rels):
-        h_rel = self.rel_emb(rels)
-        proj_rel = self.rel_project(rels).reshape(-1, self.nfeats, self.rfeats)
-        h_head = (h_head.unsqueeze(1) @ proj_rel).squeeze(1)
-        h_tail = (h_tail.unsqueeze(1) @ proj_rel).squeeze(1)
-        return -torch.norm(h_head + h_rel - h_tail, p=self.p, dim=-1)
+        M = self.rel_project(rels).view(-1, self.nfeats, self.rfeats)
+        into_rel = lambda h: torch.einsum("nd,ndr->nr", h, M)  # noqa: E731
+        return _translation_score(into_rel(h_head), self.rel_emb(rels), into_rel(h_tail), self.p)

@@ -4,35 +4,80 @@ from __future__ import annotations
 import torch
 
 from .._native import loader
-from ..base import DGLError
+from ..base import DGLError, dtype_code
 
 
 def _p(t):
     return 0 if t is None else t.data_ptr()
 
 
+def tf32_split(t):
+    """x = hi + lo with hi exactly representable in TF32 (round-to-nearest on the 10-bit mantissa) - the operand
+    planes of the fp32 tensor-core kernels (csrc/cuda/tc_common.cuh: tf32_split)."""
+    t = t.contiguous().float()
+    hi = (t.view(torch.int32) + 0x1000).bitwise_and(-8192).view(torch.float32)
+    return hi, t - hi
+
+
 def sage_layer_tc(X, self_ids, nbr, cnt, n_dev, Wt, bias, relu=True, p_drop=0.0, seed=0, step_dev=None, out=None,
-                  save_A=False, A_out=None, trace=None, out_f32=False):
+                  save_A=False, A_out=None, trace=None, out_f32=False, Wt_lo=None):
     """out[d] = act([X[self(d)] | mean_k X[nbr[d,k]]] @ Wt^T + bias) for d < n_dev (tcgen05 + TMA + TMEM kernel).
 
-    X: [rows, Fp] bf16 (Fp % 64 == 0); self_ids: int32 [n_cap] or None (identity); nbr: int32 [n_cap, fanout];
-    cnt: int32 [n_cap]; n_dev: int64 [1] device tensor; Wt: [Np, 2*Fp] bf16 (K-major); bias: fp32 [Np].
-    Returns (out [n_cap, Np] bf16, A or None)."""
-    if X.dtype != torch.bfloat16 or Wt.dtype != torch.bfloat16:
-        raise DGLError("sage_layer_tc needs bf16 operands")
+    X: [rows, Fp] bf16 (Fp % 64 == 0) or fp32 (Fp % 32 == 0); self_ids: int32 [n_cap] or None (identity);
+    nbr: int32 [n_cap, fanout]; cnt: int32 [n_cap]; n_dev: int64 [1] device tensor; Wt: [Np, 2*Fp] in X's dtype
+    (K-major); bias: fp32 [Np]. fp32 operands run as 3xTF32 split products: pass the unsplit ``Wt`` (the planes are
+    derived here) or the hi plane as ``Wt`` together with ``Wt_lo``.
+    Returns (out [n_cap, Np] in X's dtype (fp32 if out_f32), A or None)."""
+    if X.dtype not in (torch.bfloat16, torch.float32) or Wt.dtype != X.dtype:
+        raise DGLError("sage_layer_tc needs bf16 or fp32 operands of one dtype")
+    if X.dtype == torch.float32 and Wt_lo is None:
+        Wt, Wt_lo = tf32_split(Wt)
     n_cap, fanout = nbr.shape
     Fp = X.shape[1]
     Np = Wt.shape[0]
     if Wt.shape[1] != 2 * Fp:
         raise DGLError("Wt must be [Np, 2*Fp]")
     if out is None:
-        out = torch.empty((n_cap, Np), dtype=torch.float32 if out_f32 else torch.bfloat16, device=X.device)
+        out = torch.empty((n_cap, Np), dtype=torch.float32 if out_f32 else X.dtype, device=X.device)
     if save_A and A_out is None:
-        A_out = torch.zeros((n_cap, 2 * Fp), dtype=torch.bfloat16, device=X.device)
-    loader.cuda_lib().fn("dglb200_engine_sage_layer_tc", "ppppp" + "l" + "iii" + "pppp" + "iflpipp")(
-        _p(X), _p(self_ids), _p(nbr), _p(cnt), _p(n_dev), n_cap, fanout, Fp, Np, _p(Wt), _p(bias), _p(out), _p(A_out),
-        1 if relu else 0, float(p_drop), int(seed), _p(step_dev), 1 if out_f32 else 0, _p(trace), loader.stream_ptr())
+        A_out = torch.zeros((n_cap, 2 * Fp), dtype=X.dtype, device=X.device)
+    loader.cuda_lib().fn("dglb200_engine_sage_layer_tc", "ippppp" + "l" + "iii" + "ppppp" + "iflpipp")(
+        dtype_code(X.dtype), _p(X), _p(self_ids), _p(nbr), _p(cnt), _p(n_dev), n_cap, fanout, Fp, Np, _p(Wt), _p(Wt_lo),
+        _p(bias), _p(out), _p(A_out), 1 if relu else 0, float(p_drop), int(seed), _p(step_dev), 1 if out_f32 else 0,
+        _p(trace), loader.stream_ptr())
     return out, A_out
+
+
+def sage_bwd_dw(out, Q, n_dev, P=None, dH=None, Hmask=None, scale=1.0, transposed_out=False, gb=None, dz_out=None,
+                dz_out_lo=None, nbs=0):
+    """Weight gradient on tcgen05 (csrc/cuda/sage_bwd_tc.cu): ``out += P^T @ Q`` over the first ``n_dev`` rows.
+
+    P [n_cap, CP] (CP % 128 == 0) is given, or built on the fly as ``(Hmask > 0) * dH * scale`` from the incoming fp32
+    gradient ``dH`` and the layer output ``Hmask`` (then ``gb`` += column sums and ``dz_out`` (+ ``dz_out_lo`` for fp32)
+    receive dZ). Q [n_cap, CQ]. ``out`` fp32 [CP, CQ], or [CQ, CP] when ``transposed_out``."""
+    src = Hmask if P is None else P
+    n_cap, CP = src.shape
+    CQ = Q.shape[1]
+    ldi, ldj = (1, CP) if transposed_out else (CQ, 1)
+    loader.cuda_lib().fn("dglb200_engine_sage_bwd_dw", "ipppiifpiipl" + "pllpppi" + "p")(
+        dtype_code(Q.dtype), _p(dH), _p(Hmask), _p(P), src.stride(0), CP, float(scale), _p(Q), Q.stride(0), CQ, _p(n_dev),
+        n_cap, _p(out), ldi, ldj, _p(gb), _p(dz_out), _p(dz_out_lo), int(nbs), loader.stream_ptr())
+    return out
+
+
+def sage_bwd_da(dz, Wt, nbr, cnt, n_dev, dH_below, dz_lo=None, Wt_lo=None):
+    """Input gradient with the scatter in the epilogue: dA = dz [n_cap, Np] @ Wt [Np, 2F];
+    ``dH_below[d] += dA[d, :F]``, ``dH_below[nbr[d, k]] += dA[d, F:] / cnt[d]`` (fp32 [*, F], caller zeroes it)."""
+    n_cap, fanout = nbr.shape
+    Np, F2 = Wt.shape
+    if dz.dtype == torch.float32 and dz_lo is None:
+        dz, dz_lo = tf32_split(dz)
+    if Wt.dtype == torch.float32 and Wt_lo is None:
+        Wt, Wt_lo = tf32_split(Wt)
+    loader.cuda_lib().fn("dglb200_engine_sage_bwd_da", "ipppppppliiip" + "p")(
+        dtype_code(dz.dtype), _p(dz), _p(dz_lo), _p(Wt), _p(Wt_lo), _p(nbr), _p(cnt), _p(n_dev), n_cap, fanout, Np, F2 // 2,
+        _p(dH_below), loader.stream_ptr())
+    return dH_below
 
 
 def sample_ell(indptr, indices, seeds, fanout, seed=0, n_dev=None, step_dev=None, return_eids=False, pad_rows=True):

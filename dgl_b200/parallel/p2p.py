@@ -187,9 +187,9 @@ class P2PComm:
         sh = 0 if shadow is None else shadow.data_ptr()
         self.barrier(0)
         if not two_shot or W == 1:
-            self.lib.fn("dglb200_engine_allreduce_adam", "ppippplfffffpp")(
+            self.lib.fn("dglb200_engine_allreduce_adam", "ppippplfffffpppp")(
                 param.data_ptr(), peers, W, m.data_ptr(), v.data_ptr(), sh, numel, lr, betas[0], betas[1], eps,
-                weight_decay, step_dev.data_ptr(), loader.stream_ptr())
+                weight_decay, step_dev.data_ptr(), 0, 0, loader.stream_ptr())
             self.barrier(1)
             return
         if getattr(self, "_param_pub", None) is None or self._param_pub.nbytes < numel * 4:

@@ -93,3 +93,33 @@ def test_frontier_compact(first_cap, nf, fan, universe):
     fc2 = FrontierCompactor(first_cap, fan, nf + 5, DEV)
     nodes, loc, count, ovf = fc2.compact(first, n_dev, nbr)
     assert int(count.item()) == nf + 5 and int(ovf.item()) == 1
+
+
+@pytest.mark.parametrize("fanout", [-1, 200, 300])
+def test_weighted_sampling_above_128_picks(fanout):
+    """Weighted sampling without replacement on a hub with > 128 positive-probability in-edges:
+    every output slot must be a real, distinct, positive-probability in-edge - no uninitialised ids."""
+    import dgl_b200 as dgl
+    torch.manual_seed(0)
+    n, hub_deg = 2000, 700
+    src = torch.cat([torch.randint(1, n, (hub_deg,)), torch.randint(0, n, (5000,))])
+    dst = torch.cat([torch.zeros(hub_deg, dtype=torch.int64), torch.randint(1, n, (5000,))])
+    g = dgl.graph((src, dst), num_nodes=n)
+    p = torch.rand(g.num_edges())
+    p[torch.rand(g.num_edges()) < 0.3] = 0.0          # a third of the edges can never be picked
+    g.edata["p"] = p
+    gg = g.to(DEV)
+    seeds = torch.tensor([0, 5, 17], device=DEV)
+    sg = dgl.sampling.sample_neighbors(gg, seeds, fanout, prob="p")
+    u, v = sg.edges()
+    eid = sg.edata[dgl.EID]
+    su, sv = gg.edges()
+    assert torch.equal(su[eid], u) and torch.equal(sv[eid], v)          # edge ids point at real edges
+    assert torch.unique(eid).numel() == eid.numel()                      # without replacement
+    assert bool((gg.edata["p"][eid] > 0).all())
+    nz_hub = int(((dst == 0) & (p > 0)).sum())
+    want = nz_hub if fanout < 0 else min(fanout, nz_hub)
+    assert int((v == 0).sum()) == want
+    if fanout < 0:                                                       # everything eligible is returned
+        cpu = dgl.sampling.sample_neighbors(g, seeds.cpu(), -1, prob="p")
+        assert sorted(cpu.edata[dgl.EID].tolist()) == sorted(eid.cpu().tolist())
