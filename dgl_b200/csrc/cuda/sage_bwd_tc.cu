@@ -72,6 +72,8 @@ sage_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmap_q, const float* __re
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 2);
   float* s_gb = reinterpret_cast<float*>(bars + 2 * kMaxStages + 4);  // [128] bias-gradient partials
+  constexpr int kScrStride = 20;                                       // epilogue transpose scratch: 8 warps x [32 x 20] fp32
+  float* s_scr = s_gb + 128;
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages), accf = smem_u32(bars + 2 * kMaxStages);
   if (threadIdx.x == 0) {
     for (int s = 0; s < nst; ++s) {
@@ -227,22 +229,42 @@ sage_bwd_dw_kernel(const __grid_constant__ CUtensorMap tmap_q, const float* __re
     }
   } else if (warp < kTmaWarp) {
     // ===================== epilogue: D block (TMEM) -> red.add into the fp32 gradient =====================
+    // A TMEM lane is one ROW i of D. With a row-major destination (ldj == 1) a warp would touch 32 rows x 16 bytes per
+    // reduction, so each [32 x 16] piece is transposed through a per-warp smem scratch and leaves as 8 rows x 64
+    // contiguous bytes; with a column-major destination (ldi == 1) lanes are already contiguous in memory.
     const int ew = warp - kProducerWarps;
     const int quarter = ew & 3;
-    const int i = mb * 128 + quarter * 32 + lane;
+    const int i0 = mb * 128 + quarter * 32;
+    float* scr = s_scr + ew * (32 * kScrStride);
+    const int sub = lane >> 2, c4 = lane & 3;
     mbar_wait(accf, 0);
     tc_fence_after();
-    for (int n0 = (ew >> 2) * 32; n0 < NBS; n0 += 32 * (kEpilogueWarps / 4)) {
-      uint32_t v[32];
-      tmem_ld32(tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)n0, v);
-      float* dst = out + (int64_t)i * ldi + (int64_t)(nb * NBS + n0) * ldj;
+    for (int n0 = (ew >> 2) * 16; n0 < NBS; n0 += 16 * (kEpilogueWarps / 4)) {
+      uint32_t v[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)n0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int64_t j0 = (int64_t)nb * NBS + n0;
       if (ldj == 1) {
+        __syncwarp();
 #pragma unroll
-        for (int j = 0; j < 32; j += 4)
-          red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<uint4*>(scr + lane * kScrStride + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+#pragma unroll
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+          const float4 x = *reinterpret_cast<const float4*>(scr + (r0 + sub) * kScrStride + c4 * 4);
+          red_add_v4(out + (int64_t)(i0 + r0 + sub) * ldi + j0 + c4 * 4, x.x, x.y, x.z, x.w);
+        }
       } else {
+        float* dst = out + (int64_t)(i0 + lane) * ldi + j0 * ldj;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) atomicAdd(dst + (int64_t)j * ldj, __uint_as_float(v[j]));
+        for (int j = 0; j < 16; ++j) atomicAdd(dst + (int64_t)j * ldj, __uint_as_float(v[j]));
       }
     }
     tc_fence_before();
@@ -301,22 +323,27 @@ __global__ void __launch_bounds__(kDaThreads, 1)
 sage_bwd_da_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_constant__ CUtensorMap tmap_dz_lo,
                    const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_w_lo,
                    const int32_t* __restrict__ nbr, const int32_t* __restrict__ cnt, const int64_t* __restrict__ n_dev,
-                   int64_t n_cap, int fanout, int Np, int F, float* __restrict__ dH_below, int nst) {
+                   int64_t n_cap, int fanout, int Np, int F, int CB, float* __restrict__ dH_below, int nst) {
   using G = Geo<T>;
   constexpr int kPlanes = TcT<T>::kPlanes;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int64_t n = min(*n_dev, n_cap);
-  const int64_t n_tiles = ((n + 127) / 128) * 2;  // (row tile, column block) : block 0 = self half, 1 = neighbour half
+  const int ncb = 2 * F / CB;                      // column blocks of a row tile: the first F/CB are the self half
+  const int64_t n_tiles = ((n + 127) / 128) * ncb;
   if ((int64_t)blockIdx.x >= n_tiles) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KC = Np / G::kBC;                      // K chunks (Np is a multiple of one 128-byte row)
   const uint32_t a_bytes = 128 * 128;              // dZ tile [128 rows x 128 B], K-major
-  const uint32_t b_bytes = (uint32_t)F * 128;      // F/kBC boxes of [kBC k-rows x 128 B], MN-major
+  const uint32_t b_bytes = (uint32_t)CB * 128;     // CB/kBC boxes of [kBC k-rows x 128 B], MN-major
   const uint32_t kbox_bytes = G::kBC * 128;        // one Wt box: kBC reduce rows x 128 B
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t stage_bytes = kPlanes * (a_bytes + b_bytes);  // [A hi | (A lo) | B hi | (B lo)]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nst * stage_bytes);
   uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  // per-warp transpose scratch of the epilogue: 32 rows x 16 columns fp32, row stride 20 floats (conflict-free 16-byte
+  // stores by row, 64-byte segment loads by 8 rows)
+  constexpr int kScrStride = 20;
+  float* scratch = reinterpret_cast<float*>(bars + 2 * kMaxStages + 6) + warp * (32 * kScrStride);
   const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kMaxStages);
   const uint32_t accf0 = smem_u32(bars + 2 * kMaxStages), acce0 = smem_u32(bars + 2 * kMaxStages + 2);
   if (threadIdx.x == 0) {
@@ -330,7 +357,7 @@ sage_bwd_da_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_con
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const uint32_t acc_cols = F <= 32 ? 32 : (F <= 64 ? 64 : (F <= 128 ? 128 : 256));
+  const uint32_t acc_cols = CB <= 32 ? 32 : (CB <= 64 ? 64 : (CB <= 128 ? 128 : 256));
   const uint32_t tmem_cols = 2 * acc_cols;
   if (warp == kDaMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_holder)), "r"(tmem_cols) : "memory");
@@ -343,25 +370,23 @@ sage_bwd_da_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_con
 
   if (warp < kDaEpiWarps) {
     // ===================== epilogue: accumulator -> scatter into the gradient of the layer below =====================
-    const int quarter = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter
-    const int cols_per = F / 4;                    // F is a multiple of 64: 16 / 32 / 48 / 64 columns per warp
+    // A TMEM lane is a ROW of the tile, so a warp reading the accumulator holds 32 different rows: reductions issued
+    // straight from those registers would touch 32 destination rows with 16 bytes each. Every [32 rows x 16 cols] piece
+    // therefore takes one trip through a per-warp shared-memory scratch and leaves as 8 rows x 64 contiguous bytes per
+    // warp instruction (lane -> row r0 + lane/4, 16-byte column group lane%4).
+    const int quarter = warp & 3, cq = warp >> 2;  // TMEM lane quarter, column quarter of the block
+    const int cols_per = CB / 4;                   // CB is a multiple of 64: 16 / 32 / 64 columns per warp
+    const int sub = lane >> 2, c4 = lane & 3;
     int it = 0;
     for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
-      const int64_t row = (t >> 1) * 128 + quarter * 32 + lane;
-      const int blk = (int)(t & 1);
+      const int64_t row0 = (t / ncb) * 128 + quarter * 32;
+      const int cb = (int)(t % ncb);
+      const bool nbr_half = cb * CB >= F;
+      const int colbase = cb * CB - (nbr_half ? F : 0) + cq * cols_per;  // column inside dH_below
       const int acc = it & 1;
       mbar_wait(accf0 + 8 * acc, (it >> 1) & 1);
       tc_fence_after();
-      const bool live = row < n;
-      int cn = 0;
-      float w = 1.f;
-      const int32_t* nb = nbr + row * fanout;
-      if (live && blk == 1) {
-        cn = cnt[row];
-        w = cn > 0 ? 1.f / (float)cn : 0.f;
-      }
       for (int c0 = 0; c0 < cols_per; c0 += 16) {
-        // 16 columns per pass keep the register footprint small enough for 16 resident epilogue warps
         uint32_t v[16];
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * acc_cols + cq * cols_per + c0);
         asm volatile(
@@ -371,20 +396,25 @@ sage_bwd_da_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_con
               "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (!live) continue;
-        const int col = cq * cols_per + c0;
-        if (blk == 0) {
-          float* dst = dH_below + row * F + col;
+        __syncwarp();  // previous piece fully consumed
 #pragma unroll
-          for (int j = 0; j < 16; j += 4)
-            red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
-        } else {
-          for (int k = 0; k < cn; ++k) {
-            float* dst = dH_below + (int64_t)max(nb[k], 0) * F + col;
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<uint4*>(scratch + lane * kScrStride + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        __syncwarp();
+        const int col = colbase + c0 + c4 * 4;
 #pragma unroll
-            for (int j = 0; j < 16; j += 4)
-              red_add_v4(dst + j, __uint_as_float(v[j]) * w, __uint_as_float(v[j + 1]) * w, __uint_as_float(v[j + 2]) * w,
-                         __uint_as_float(v[j + 3]) * w);
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+          const int64_t row = row0 + r0 + sub;
+          if (row >= n) continue;
+          const float4 x = *reinterpret_cast<const float4*>(scratch + (r0 + sub) * kScrStride + c4 * 4);
+          if (!nbr_half) {
+            red_add_v4(dH_below + row * F + col, x.x, x.y, x.z, x.w);
+          } else {
+            const int cn = cnt[row];
+            const float w = cn > 0 ? 1.f / (float)cn : 0.f;
+            const int32_t* nb = nbr + row * fanout;
+            for (int k = 0; k < cn; ++k)
+              red_add_v4(dH_below + (int64_t)max(nb[k], 0) * F + col, x.x * w, x.y * w, x.z * w, x.w * w);
           }
         }
       }
@@ -395,10 +425,10 @@ sage_bwd_da_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_con
   } else if (warp == kDaTmaWarp) {
     if (lane == 0) {
       uint32_t g = 0;
-      const int nboxes = F / G::kBC;
+      const int nboxes = CB / G::kBC;
       for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-        const int row0 = (int)((t >> 1) * 128);
-        const int blk = (int)(t & 1);
+        const int row0 = (int)((t / ncb) * 128);
+        const int cb = (int)(t % ncb);
         for (int kc = 0; kc < KC; ++kc, ++g) {
           const int stage = g % nst;
           mbar_wait(empty0 + 8 * stage, ((g / nst) & 1) ^ 1);
@@ -407,9 +437,9 @@ sage_bwd_da_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_con
           tma_load_2d(sa, &tmap_dz, full0 + 8 * stage, kc * G::kBC, row0);
           if constexpr (kPlanes == 2) tma_load_2d(sa + a_bytes, &tmap_dz_lo, full0 + 8 * stage, kc * G::kBC, row0);
           for (int b = 0; b < nboxes; ++b) {
-            tma_load_2d(sb + b * kbox_bytes, &tmap_w, full0 + 8 * stage, blk * F + b * G::kBC, kc * G::kBC);
+            tma_load_2d(sb + b * kbox_bytes, &tmap_w, full0 + 8 * stage, cb * CB + b * G::kBC, kc * G::kBC);
             if constexpr (kPlanes == 2)
-              tma_load_2d(sb + b_bytes + b * kbox_bytes, &tmap_w_lo, full0 + 8 * stage, blk * F + b * G::kBC, kc * G::kBC);
+              tma_load_2d(sb + b_bytes + b * kbox_bytes, &tmap_w_lo, full0 + 8 * stage, cb * CB + b * G::kBC, kc * G::kBC);
           }
         }
       }
@@ -417,7 +447,7 @@ sage_bwd_da_kernel(const __grid_constant__ CUtensorMap tmap_dz, const __grid_con
   } else {
     // ===================== MMA issuer: A K-major (dZ), B MN-major (Wt rows are the reduce index) =====================
     const uint32_t fmt = (uint32_t)TcT<T>::kFmt;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(F >> 3) << 17) |
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (1u << 16) | ((uint32_t)(CB >> 3) << 17) |
                            ((uint32_t)(128 >> 4) << 24);
     auto kdesc = [](uint32_t a) { return make_sw128_kmajor_desc(a); };
     auto mdesc = [kbox_bytes](uint32_t a) { return make_mnmajor_desc<T>(a, kbox_bytes); };
@@ -490,8 +520,9 @@ static void launch_dw(const void* dH, const void* Hmask, const void* P, int ldp,
   DGLB_CHECK(kPlanes == 1 || dz_out == nullptr || dz_out_lo != nullptr, "fp32 dZ write-out needs both planes");
   const int MB = CP / 128, NB = CQ / NBS;
   const size_t stage_bytes = kPlanes * ((size_t)G::kPBytes + (size_t)NBS * 128);
-  const int nst = (int)std::max<size_t>(1, std::min<size_t>(kMaxStages, (size_t)(220 * 1024) / stage_bytes));
-  const size_t smem = nst * stage_bytes + 1024 + 1024;
+  const size_t fixed_dw = 1024 + 1024 + (size_t)kEpilogueWarps * 32 * 20 * 4;  // slack + barriers/bias + transpose scratch
+  const int nst = (int)std::max<size_t>(1, std::min<size_t>(kMaxStages, ((size_t)(226 * 1024) - fixed_dw) / stage_bytes));
+  const size_t smem = nst * stage_bytes + fixed_dw;
   const int64_t chunks = (n_cap + G::kKR - 1) / G::kKR;
   const int Qn = MB * NB;
   const int groups = (int)std::max<int64_t>(1, std::min<int64_t>(sm_count() / Qn, chunks));
@@ -508,12 +539,21 @@ static void launch_dw(const void* dH, const void* Hmask, const void* P, int ldp,
 
 template <typename T>
 static void launch_da(const void* dz, const void* dz_lo, const void* Wt, const void* Wt_lo, const void* nbr, const void* cnt,
-                      const void* n_dev, int64_t n_cap, int fanout, int Np, int F, void* dH_below, cudaStream_t st) {
+                      const void* n_dev, int64_t n_cap, int fanout, int Np, int F, void* dH_below, int cb_hint, cudaStream_t st) {
   using G = Geo<T>;
   constexpr int kPlanes = TcT<T>::kPlanes;
   DGLB_CHECK(F % 64 == 0 && F >= 64 && F <= 256, "dA: F must be a multiple of 64 in [64, 256]");
   DGLB_CHECK(Np % G::kBC == 0 && Np >= G::kBC, "dA: Np must be a multiple of one 128-byte row");
   DGLB_CHECK(kPlanes == 1 || (dz_lo && Wt_lo), "fp32 dA needs the lo planes");
+  // column block of a tile: the scatter epilogue is the expensive part, so prefer enough (row tile x column block)
+  // work items to occupy every SM a few times over; the dZ tile re-read per block comes from L2
+  const int64_t row_tiles = (n_cap + 127) / 128;
+  int CB = cb_hint;
+  if (CB <= 0) {
+    CB = F % 256 == 0 ? 256 : (F % 128 == 0 ? 128 : 64);
+    while (CB > 64 && row_tiles * (2 * F / CB) < 3 * (int64_t)sm_count() && F % (CB / 2) == 0) CB /= 2;
+  }
+  DGLB_CHECK(CB % 64 == 0 && CB <= 256 && F % CB == 0, "dA: unsupported column block");
   CUtensorMap tdz, tdzl, tw, twl;
   encode_2d<T>(&tdz, dz, (uint64_t)Np, (uint64_t)n_cap, (uint64_t)Np, G::kBC, 128);
   encode_2d<T>(&tw, Wt, (uint64_t)(2 * F), (uint64_t)Np, (uint64_t)(2 * F), G::kBC, G::kBC, true);
@@ -524,15 +564,16 @@ static void launch_da(const void* dz, const void* dz_lo, const void* Wt, const v
     tdzl = tdz;
     twl = tw;
   }
-  const size_t stage_bytes = kPlanes * ((size_t)128 * 128 + (size_t)F * 128);
-  const int nst = (int)std::max<size_t>(1, std::min<size_t>(kMaxStages, (size_t)(220 * 1024) / stage_bytes));
-  const size_t smem = nst * stage_bytes + 1024 + 256;
-  const int64_t tiles = ((n_cap + 127) / 128) * 2;
+  const size_t stage_bytes = kPlanes * ((size_t)128 * 128 + (size_t)CB * 128);
+  const size_t fixed = 1024 + 256 + (size_t)kDaEpiWarps * 32 * 20 * 4;  // alignment slack + barriers + transpose scratch
+  const int nst = (int)std::max<size_t>(1, std::min<size_t>(kMaxStages, ((size_t)(226 * 1024) - fixed) / stage_bytes));
+  const size_t smem = nst * stage_bytes + fixed;
+  const int64_t tiles = row_tiles * (2 * F / CB);
   const unsigned grid = (unsigned)std::min<int64_t>(tiles, sm_count());
   auto kern = sage_bwd_da_kernel<T>;
   DGLB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, kDaThreads, smem, st>>>(tdz, tdzl, tw, twl, (const int32_t*)nbr, (const int32_t*)cnt, (const int64_t*)n_dev,
-                                      n_cap, fanout, Np, F, (float*)dH_below, nst);
+                                      n_cap, fanout, Np, F, CB, (float*)dH_below, nst);
   DGLB_LAUNCH_CHECK();
 }
 
@@ -565,14 +606,15 @@ DGLB_API int dglb200_engine_sage_bwd_dw(int dtype, const void* dH, const void* H
 
 // Input gradient of one fused layer, scattered:  dA = dz [n_cap, Np] @ Wt [Np, 2F];
 //   dH_below[d] += dA[d, :F];  dH_below[nbr[d, k]] += dA[d, F:] / cnt[d]  (k < cnt[d]);  dH_below fp32 [*, F], pre-zeroed.
+//   cb: column block of a work item (64 | 128 | 256, 0 = chosen from the tile count).
 DGLB_API int dglb200_engine_sage_bwd_da(int dtype, const void* dz, const void* dz_lo, const void* Wt, const void* Wt_lo,
                                         const void* nbr, const void* cnt, const void* n_dev, int64_t n_cap, int fanout,
-                                        int Np, int F, void* dH_below, void* stream) {
+                                        int Np, int F, void* dH_below, int cb, void* stream) {
   DGLB_TRY
   DGLB_CHECK(dtype == kBF16 || dtype == kF32, "sage_bwd_da: bf16 or fp32");
   if (n_cap == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  if (dtype == kBF16) sbw::launch_da<__nv_bfloat16>(dz, dz_lo, Wt, Wt_lo, nbr, cnt, n_dev, n_cap, fanout, Np, F, dH_below, st);
-  else sbw::launch_da<float>(dz, dz_lo, Wt, Wt_lo, nbr, cnt, n_dev, n_cap, fanout, Np, F, dH_below, st);
+  if (dtype == kBF16) sbw::launch_da<__nv_bfloat16>(dz, dz_lo, Wt, Wt_lo, nbr, cnt, n_dev, n_cap, fanout, Np, F, dH_below, cb, st);
+  else sbw::launch_da<float>(dz, dz_lo, Wt, Wt_lo, nbr, cnt, n_dev, n_cap, fanout, Np, F, dH_below, cb, st);
   DGLB_CATCH
 }

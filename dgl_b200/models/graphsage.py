@@ -562,7 +562,8 @@ class FusedSAGETrainer:
                              self.caps[l - 1], Fi, float(scale), _p(dZn), _p(self.gb[l - 2]))
                 dZ = dZn
                 keep.append(dZn)
-        main.wait_stream(side)
+        if any(self.tc_layer[1:]):  # the side stream only carries work (and joined the capture) on that branch
+            main.wait_stream(side)
         self._finish_step()
 
     def _backward_tc(self, main, side):
@@ -571,7 +572,7 @@ class FusedSAGETrainer:
         the scatter into the layer below. No cuBLAS, no elementwise kernels."""
         L, dt = self.L, dtype_code(self.dtype)
         sig_dw = "ipppiifpiipl" + "pllpppi"
-        sig_da = "ipppppppliiip"
+        sig_da = "ipppppppliiipi"
         # layer L: dZ = dlogits (CE kernel). Swapped roles (M side = A columns) because n_pad = 64 < one MMA M tile.
         side.wait_stream(main)
         with torch.cuda.stream(side):
@@ -585,7 +586,7 @@ class FusedSAGETrainer:
                 main.wait_stream(self._zero_stream)  # dH buffers were cleared off the critical path (see _step_impl)
             self._launch("dglb200_engine_sage_bwd_da", sig_da, dt, _p(dz), _p(dz_lo), _p(self.Wt[l - 1]),
                          _p(self.Wt_lo[l - 1]), _p(self.nbr[l]), _p(self.cnt[l]), _p(self.n[l]), self.caps[l],
-                         self.fanouts[l - 1], self.n_pad[l - 1], Fi, _p(self.dH[l - 1]))
+                         self.fanouts[l - 1], self.n_pad[l - 1], Fi, _p(self.dH[l - 1]), 0)
             lo = l - 1  # weight gradient of the layer below; its dZ feeds the next dA kernel
             k2 = 2 * self.in_dims[lo - 1]
             self._launch("dglb200_engine_sage_bwd_dw", sig_dw, dt, _p(self.dH[lo]), _p(self.Hbuf[lo]), 0,

@@ -16,7 +16,8 @@ from .. import ops
 from ..base import DGLError
 
 __all__ = ["src_dst", "gather_sum", "gather_mean", "gather_max", "gather_min", "gather", "edge_reduce", "pair_op",
-           "attend", "degrees", "sym_norm_propagate", "require_in_edges", "hop", "edge_softmax_agg"]
+           "attend", "degrees", "sym_norm_propagate", "require_in_edges", "hop", "edge_softmax_agg", "norm_coefficients",
+           "structure_cache"]
 
 
 def src_dst(g, feat):
@@ -84,20 +85,27 @@ def degrees(g, side="in", dtype=torch.float32, floor=1.0):
     return d.clamp(min=floor) if floor is not None else d
 
 
+def structure_cache(g):
+    """Per-STRUCTURE scratch dict: it lives on the immutable adjacency object (mutating a graph creates a new one), so
+    anything derived from the topology alone - degree vectors, normalisation coefficients, the isolated-node verdict -
+    is computed once per graph, not once per forward."""
+    units = getattr(g, "_graphs", None)
+    if units is None or len(units) != 1:
+        return {}
+    return units[0]._degs
+
+
 def require_in_edges(g, allow, layer):
     """Raise if a destination node has no in-edge (its output would silently be zero / the softmax undefined).
     The verdict is cached per graph structure, so a training loop pays the reduction + host read ONCE instead of
     every forward (the reference layers re-check, and synchronise, on every call)."""
     if allow:
         return
-    key = "_no_isolated_dst"
-    ok = getattr(g, key, None)
+    cache = structure_cache(g)
+    ok = cache.get("no_isolated_dst")
     if ok is None:
-        ok = not bool((g.in_degrees() == 0).any()) if g.number_of_edges() or g.number_of_dst_nodes() else True
-        try:
-            setattr(g, key, ok)
-        except AttributeError:
-            pass
+        ok = not bool((g.in_degrees() == 0).any()) if g.number_of_dst_nodes() else True
+        cache["no_isolated_dst"] = ok
     if not ok:
         raise DGLError(
             f"There are 0-in-degree nodes in the graph, output for those nodes will be invalid. Add self-loops with "
@@ -105,19 +113,36 @@ def require_in_edges(g, allow, layer):
 
 
 def sym_norm_propagate(g, x_src, mode="both", w=None):
-    """Degree-normalised aggregation of GCN-style layers.
+    """Degree-normalised aggregation of GCN-style layers as ONE weighted g-SpMM.
 
     both : D_in^-1/2 A D_out^-1/2 x      right : D_in^-1 A x      left : A D_out^-1 x      none : A x
     With edge weights ``w`` the structural degrees are still used (weights are expected to be pre-normalised, e.g. by
     ``EdgeWeightNorm``)."""
-    if mode in ("both", "left"):
-        s = degrees(g, "out", x_src.dtype).pow(-0.5 if mode == "both" else -1.0)
-        x_src = x_src * s.reshape((-1,) + (1,) * (x_src.dim() - 1))
-    y = gather_sum(g, x_src, w)
-    if mode in ("both", "right"):
-        s = degrees(g, "in", y.dtype).pow(-0.5 if mode == "both" else -1.0)
-        y = y * s.reshape((-1,) + (1,) * (y.dim() - 1))
-    return y
+    return gather_sum(g, x_src, norm_coefficients(g, mode, x_src.dtype, w))
+
+
+def norm_coefficients(g, mode, dtype, w=None):
+    """Per-edge coefficient that folds the degree normalisation of ``sym_norm_propagate`` into ONE weighted g-SpMM:
+    both: d_out(u)^-1/2 d_in(v)^-1/2, right: 1/d_in(v), left: 1/d_out(u) (times ``w`` when given). The structural part
+    is cached per graph, so full-graph training computes it once; the two N x F row scalings of the textbook
+    formulation disappear from every forward and backward."""
+    if mode == "none":
+        return w
+    cache = structure_cache(g)
+    key = ("norm_coeff", mode, dtype)
+    c = cache.get(key)
+    if c is None:
+        one_src = degrees(g, "out", dtype).pow(-0.5 if mode == "both" else -1.0) if mode in ("both", "left") else None
+        one_dst = degrees(g, "in", dtype).pow(-0.5 if mode == "both" else -1.0) if mode in ("both", "right") else None
+        if one_src is not None and one_dst is not None:
+            c = pair_op(g, "mul", one_src.unsqueeze(-1), one_dst.unsqueeze(-1)).reshape(-1)
+        elif one_src is not None:
+            c = ops.gsddmm(g, "copy_lhs", one_src.unsqueeze(-1), None, "u", "v").reshape(-1)
+        else:
+            c = ops.gsddmm(g, "copy_rhs", None, one_dst.unsqueeze(-1), "u", "v").reshape(-1)
+        c = c.detach()
+        cache[key] = c
+    return c if w is None else c * w
 
 
 def hop(g, x, norm=None, w=None):

@@ -65,7 +65,7 @@ def sage_bwd_dw(out, Q, n_dev, P=None, dH=None, Hmask=None, scale=1.0, transpose
     return out
 
 
-def sage_bwd_da(dz, Wt, nbr, cnt, n_dev, dH_below, dz_lo=None, Wt_lo=None):
+def sage_bwd_da(dz, Wt, nbr, cnt, n_dev, dH_below, dz_lo=None, Wt_lo=None, cb=0):
     """Input gradient with the scatter in the epilogue: dA = dz [n_cap, Np] @ Wt [Np, 2F];
     ``dH_below[d] += dA[d, :F]``, ``dH_below[nbr[d, k]] += dA[d, F:] / cnt[d]`` (fp32 [*, F], caller zeroes it)."""
     n_cap, fanout = nbr.shape
@@ -74,9 +74,9 @@ def sage_bwd_da(dz, Wt, nbr, cnt, n_dev, dH_below, dz_lo=None, Wt_lo=None):
         dz, dz_lo = tf32_split(dz)
     if Wt.dtype == torch.float32 and Wt_lo is None:
         Wt, Wt_lo = tf32_split(Wt)
-    loader.cuda_lib().fn("dglb200_engine_sage_bwd_da", "ipppppppliiip" + "p")(
+    loader.cuda_lib().fn("dglb200_engine_sage_bwd_da", "ipppppppliiipi" + "p")(
         dtype_code(dz.dtype), _p(dz), _p(dz_lo), _p(Wt), _p(Wt_lo), _p(nbr), _p(cnt), _p(n_dev), n_cap, fanout, Np, F2 // 2,
-        _p(dH_below), loader.stream_ptr())
+        _p(dH_below), int(cb), loader.stream_ptr())
     return dH_below
 
 

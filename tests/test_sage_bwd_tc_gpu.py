@@ -93,9 +93,10 @@ def test_sage_bwd_dw(dt, n_cap, n, CP, CQ, transform, transposed, nbs):
 
 
 @pytest.mark.parametrize("dt", [torch.bfloat16, torch.float32])
-@pytest.mark.parametrize("n_cap,n,Np,F,fan,rows_below", [(1024, 1000, 64, 256, 10, 9000), (11000, 10500, 256, 256, 10, 90000),
-                                                       (300, 300, 128, 128, 5, 2000), (129, 1, 256, 64, 3, 500)])
-def test_sage_bwd_da(dt, n_cap, n, Np, F, fan, rows_below):
+@pytest.mark.parametrize("n_cap,n,Np,F,fan,rows_below,cb", [
+    (1024, 1000, 64, 256, 10, 9000, 0), (11000, 10500, 256, 256, 10, 90000, 0), (11000, 10500, 256, 256, 10, 90000, 256),
+    (5000, 4999, 256, 256, 10, 40000, 128), (300, 300, 128, 128, 5, 2000, 0), (129, 1, 256, 64, 3, 500, 0)])
+def test_sage_bwd_da(dt, n_cap, n, Np, F, fan, rows_below, cb):
     from dgl_b200.ops.fused import sage_bwd_da
     torch.manual_seed(2)
     nbr, cnt = _ell(n_cap, fan, rows_below, seed=3)
@@ -103,7 +104,7 @@ def test_sage_bwd_da(dt, n_cap, n, Np, F, fan, rows_below):
     dz = (torch.randn(n_cap, Np, device=DEV) * 0.5).to(dt)
     Wt = (torch.randn(Np, 2 * F, device=DEV) * 0.1).to(dt)
     dH = torch.zeros(rows_below, F, device=DEV)
-    sage_bwd_da(dz, Wt, nbr, cnt, n_dev, dH)
+    sage_bwd_da(dz, Wt, nbr, cnt, n_dev, dH, cb=cb)
     torch.cuda.synchronize()
     dA = dz[:n].double() @ Wt.double()
     ref = torch.zeros(rows_below, F, device=DEV, dtype=torch.float64)
