@@ -123,7 +123,8 @@ def sym_norm_propagate(g, x_src, mode="both", w=None):
 
 def norm_coefficients(g, mode, dtype, w=None):
     """Per-edge coefficient that folds the degree normalisation of ``sym_norm_propagate`` into ONE weighted g-SpMM:
-    both: d_out(u)^-1/2 d_in(v)^-1/2, right: 1/d_in(v), left: 1/d_out(u) (times ``w`` when given). The structural part
+    both: d_out(u)^-1/2 d_in(v)^-1/2, right: 1/d_in(v), left: 1/d_out(u), in_both: d_in(u)^-1/2 d_in(v)^-1/2 (the
+    convention of the spectral filters, which read one degree vector for both ends) - times ``w`` when given. The structural part
     is cached per graph, so full-graph training computes it once; the two N x F row scalings of the textbook
     formulation disappear from every forward and backward."""
     if mode == "none":
@@ -132,8 +133,11 @@ def norm_coefficients(g, mode, dtype, w=None):
     key = ("norm_coeff", mode, dtype)
     c = cache.get(key)
     if c is None:
-        one_src = degrees(g, "out", dtype).pow(-0.5 if mode == "both" else -1.0) if mode in ("both", "left") else None
-        one_dst = degrees(g, "in", dtype).pow(-0.5 if mode == "both" else -1.0) if mode in ("both", "right") else None
+        if mode == "in_both":
+            one_src = one_dst = degrees(g, "in", dtype).pow(-0.5)
+        else:
+            one_src = degrees(g, "out", dtype).pow(-0.5 if mode == "both" else -1.0) if mode in ("both", "left") else None
+            one_dst = degrees(g, "in", dtype).pow(-0.5 if mode == "both" else -1.0) if mode in ("both", "right") else None
         if one_src is not None and one_dst is not None:
             c = pair_op(g, "mul", one_src.unsqueeze(-1), one_dst.unsqueeze(-1)).reshape(-1)
         elif one_src is not None:

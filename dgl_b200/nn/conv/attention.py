@@ -1,7 +1,16 @@
-"""Attention-style graph convolutions: GATConv, GATv2Conv, DotGatConv, AGNNConv, EGATConv, EdgeGATConv.
+"""Attention convolutions: GATConv, GATv2Conv, DotGatConv, AGNNConv, EGATConv, EdgeGATConv.
 
-Parity: /root/reference/python/dgl/nn/pytorch/conv/{gatconv,gatv2conv,dotgatconv,agnnconv,egatconv,edgegatconv}.py.
-All of them lower to g-SDDMM (u_add_v / u_dot_v) + the fused edge-softmax kernel + g-SpMM (u_mul_e_sum).
+API parity: /root/reference/python/dgl/nn/pytorch/conv/{gatconv,gatv2conv,dotgatconv,agnnconv,egatconv,edgegatconv}.py
+(constructor signatures, parameter names; values checked by tests/test_nn_reference_parity.py).
+
+Execution plan shared by the layers (``_HeadedAttention``):
+
+* on CUDA the graph is swapped for its destination-sorted view so scores, softmax and aggregation share one edge order
+  (no [E, heads] permutation between the COO-ordered g-SDDMM and the CSC-ordered g-SpMM);
+* GAT's additive scores go through the FUSED attention kernels (csrc/cuda/gat_fused.cu: online-softmax forward over CSC
+  rows, recomputing backward) - no [E, heads] tensor exists in either direction - whenever no per-edge output is asked;
+* otherwise: one g-SDDMM for the logits, the fused edge-softmax kernel, one weighted g-SpMM;
+* the isolated-node check is evaluated once per graph structure (``_mp.require_in_edges``), not once per forward.
 """
 from __future__ import annotations
 
@@ -9,487 +18,334 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ... import function as fn
+from ... import ops
 from ...base import DGLError
-from ...ops import edge_softmax
-from ...utils import expand_as_pair
+from .. import _mp
 
 
-def _zero_in_degree_check(graph, allow):
-    if not allow and bool((graph.in_degrees() == 0).any()):
-        raise DGLError("There are 0-in-degree nodes in the graph, output for those nodes will be invalid. This is "
-                       "harmful for some applications, causing silent performance regression. Adding self-loop on "
-                       "the input graph by calling `g = dgl.add_self_loop(g)` will resolve the issue. Setting "
-                       "``allow_zero_in_degree`` to be `True` when constructing this module will suppress the check "
-                       "and let the code run.")
+def _pair(width):
+    return tuple(width) if isinstance(width, (tuple, list)) else (width, width)
 
 
-def _attention_view(graph, edge_weight=None):
-    """(graph to compute on, eid map, edge weight in that order): CUDA graphs with one relation are swapped for their
-    destination-sorted view so that scores / softmax / aggregation share one edge order (no [E, heads] permutations)."""
+def _attention_view(graph, *edge_tensors):
+    """(graph to compute on, eid map, edge tensors permuted into that graph's edge order)."""
     if graph.device.type != "cuda" or len(graph.canonical_etypes) != 1:
-        return graph, None, edge_weight
+        return (graph, None) + edge_tensors
     view, emap = graph.dst_sorted_view()
-    if emap is not None and edge_weight is not None:
-        edge_weight = edge_weight[emap.long()]
-    return view, emap, edge_weight
-
-
-def _attention_to_eid_order(a, emap):
     if emap is None:
-        return a
-    out = torch.empty_like(a)
-    out[emap.long()] = a
+        return (view, None) + edge_tensors
+    idx = emap.long()
+    return (view, emap) + tuple(None if t is None else t[idx] for t in edge_tensors)
+
+
+def _to_eid_order(per_edge, emap):
+    if emap is None:
+        return per_edge
+    out = torch.empty_like(per_edge)
+    out[emap.long()] = per_edge
     return out
 
 
+class _HeadedAttention(nn.Module):
+    """Plumbing common to the multi-head layers: endpoint projections, residual / bias / activation epilogue."""
 
-class GATConv(nn.Module):
-    r"""Graph attention layer (Velickovic et al.): e_ij = LeakyReLU(a^T [W h_i || W h_j]) (reference gatconv.py:14-365)."""
+    _layer_name = "attention layer"
+
+    def _make_projections(self, in_feats, width, bias=False):
+        """``fc`` shared by both endpoints, or ``fc_src`` / ``fc_dst`` when the two sides have different widths."""
+        self._in_src_feats, self._in_dst_feats = _pair(in_feats)
+        if isinstance(in_feats, (tuple, list)):
+            self.fc_src = nn.Linear(self._in_src_feats, width, bias=bias)
+            self.fc_dst = nn.Linear(self._in_dst_feats, width, bias=bias)
+        else:
+            self.fc = nn.Linear(self._in_src_feats, width, bias=bias)
+
+    def _make_residual(self, residual, width, bias=False):
+        if not residual:
+            self.register_buffer("res_fc", None)
+        elif self._in_dst_feats != width:
+            self.res_fc = nn.Linear(self._in_dst_feats, width, bias=bias)
+        else:
+            self.res_fc = nn.Identity()
+
+    def set_allow_zero_in_degree(self, set_value):
+        self._allow_zero_in_degree = set_value
+
+    def _inputs(self, graph, feat, drop=None):
+        """(h_src, h_dst) after feature dropout; a block's destination rows are the prefix of its source rows."""
+        if isinstance(feat, (tuple, list)):
+            h_src, h_dst = feat
+            return (h_src, h_dst) if drop is None else (drop(h_src), drop(h_dst))
+        h = feat if drop is None else drop(feat)
+        return h, (h[: graph.number_of_dst_nodes()] if graph.is_block else h)
+
+    def _project(self, graph, h_src, h_dst, shared_input):
+        """[.., heads, out] projections of both endpoints; one GEMM when the endpoints share input and weights."""
+        H, D = self._num_heads, self._out_feats
+        if hasattr(self, "fc"):
+            z_src = self.fc(h_src).view(*h_src.shape[:-1], H, D)
+            z_dst = z_src[: graph.number_of_dst_nodes()] if shared_input else self.fc(h_dst).view(*h_dst.shape[:-1], H, D)
+            return z_src, z_dst
+        return (self.fc_src(h_src).view(*h_src.shape[:-1], H, D), self.fc_dst(h_dst).view(*h_dst.shape[:-1], H, D))
+
+    def _epilogue(self, out, h_dst, bias=None):
+        H, D = self._num_heads, self._out_feats
+        if self.res_fc is not None:
+            out = out + self.res_fc(h_dst).view(*h_dst.shape[:-1], -1, D)
+        if bias is not None:
+            out = out + bias.view(*((1,) * (out.dim() - 2)), H, D)
+        return out if not self.activation else self.activation(out)
+
+
+# =====================================================================================================================
+class GATConv(_HeadedAttention):
+    r"""Graph attention (Velickovic et al.): ``e_ij = LeakyReLU(a_l . W h_j + a_r . W h_i)``, softmax over in-edges."""
+
+    _layer_name = "GATConv"
 
     def __init__(self, in_feats, out_feats, num_heads, feat_drop=0.0, attn_drop=0.0, negative_slope=0.2, residual=False,
                  activation=None, allow_zero_in_degree=False, bias=True):
         super().__init__()
-        self._num_heads = num_heads
-        self._in_src_feats, self._in_dst_feats = expand_as_pair(in_feats)
-        self._out_feats = out_feats
-        self._allow_zero_in_degree = allow_zero_in_degree
-        if isinstance(in_feats, tuple):
-            self.fc_src = nn.Linear(self._in_src_feats, out_feats * num_heads, bias=False)
-            self.fc_dst = nn.Linear(self._in_dst_feats, out_feats * num_heads, bias=False)
-        else:
-            self.fc = nn.Linear(self._in_src_feats, out_feats * num_heads, bias=False)
-        self.attn_l = nn.Parameter(torch.FloatTensor(size=(1, num_heads, out_feats)))
-        self.attn_r = nn.Parameter(torch.FloatTensor(size=(1, num_heads, out_feats)))
-        self.feat_drop = nn.Dropout(feat_drop)
-        self.attn_drop = nn.Dropout(attn_drop)
+        self._num_heads, self._out_feats, self._allow_zero_in_degree = num_heads, out_feats, allow_zero_in_degree
+        width = out_feats * num_heads
+        self._make_projections(in_feats, width)
+        self.attn_l = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.attn_r = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.feat_drop, self.attn_drop = nn.Dropout(feat_drop), nn.Dropout(attn_drop)
         self.leaky_relu = nn.LeakyReLU(negative_slope)
-        self.has_linear_res = False
-        self.has_explicit_bias = False
-        if residual:
-            if self._in_dst_feats != out_feats * num_heads:
-                self.res_fc = nn.Linear(self._in_dst_feats, num_heads * out_feats, bias=bias)
-                self.has_linear_res = True
-            else:
-                self.res_fc = nn.Identity()
-        else:
-            self.register_buffer("res_fc", None)
-        if bias and not self.has_linear_res:
-            self.bias = nn.Parameter(torch.FloatTensor(size=(num_heads * out_feats,)))
-            self.has_explicit_bias = True
+        self.has_linear_res = bool(residual) and self._in_dst_feats != width
+        self._make_residual(residual, width, bias=bias)            # a linear residual carries the bias itself
+        self.has_explicit_bias = bool(bias) and not self.has_linear_res
+        if self.has_explicit_bias:
+            self.bias = nn.Parameter(torch.empty(width))
         else:
             self.register_buffer("bias", None)
-        self.reset_parameters()
         self.activation = activation
+        self.reset_parameters()
 
     def reset_parameters(self):
         gain = nn.init.calculate_gain("relu")
-        if hasattr(self, "fc"):
-            nn.init.xavier_normal_(self.fc.weight, gain=gain)
-        else:
-            nn.init.xavier_normal_(self.fc_src.weight, gain=gain)
-            nn.init.xavier_normal_(self.fc_dst.weight, gain=gain)
+        for lin in (getattr(self, n) for n in ("fc", "fc_src", "fc_dst") if hasattr(self, n)):
+            nn.init.xavier_normal_(lin.weight, gain=gain)
         nn.init.xavier_normal_(self.attn_l, gain=gain)
         nn.init.xavier_normal_(self.attn_r, gain=gain)
         if self.has_explicit_bias:
-            nn.init.constant_(self.bias, 0)
+            nn.init.zeros_(self.bias)
         if isinstance(self.res_fc, nn.Linear):
             nn.init.xavier_normal_(self.res_fc.weight, gain=gain)
             if self.res_fc.bias is not None:
-                nn.init.constant_(self.res_fc.bias, 0)
+                nn.init.zeros_(self.res_fc.bias)
 
-    def set_allow_zero_in_degree(self, set_value):
-        self._allow_zero_in_degree = set_value
+    def _fused(self, g, z_src, s_src, s_dst):
+        """Scores + softmax + aggregation in the fused kernels; None when the shape is not covered."""
+        from ...ops import gat_fused
+        pad = (-self._out_feats) % (16 // z_src.element_size())   # per-head rows padded to 16 bytes
+        if not gat_fused.supported(s_src.unsqueeze(-1), z_src, self._num_heads, self._out_feats + pad):
+            return None
+        z = F.pad(z_src, (0, pad)) if pad else z_src
+        out = gat_fused.fused_gat(g._graphs[0], s_src, s_dst, z, self.leaky_relu.negative_slope)
+        return out[..., : self._out_feats] if pad else out
 
     def forward(self, graph, feat, edge_weight=None, get_attention=False):
-        _zero_in_degree_check(graph, self._allow_zero_in_degree)
-        graph, emap, edge_weight = _attention_view(graph, edge_weight)
-        with graph.local_scope():
-            if isinstance(feat, tuple):
-                src_prefix_shape = feat[0].shape[:-1]
-                dst_prefix_shape = feat[1].shape[:-1]
-                h_src = self.feat_drop(feat[0])
-                h_dst = self.feat_drop(feat[1])
-                if not hasattr(self, "fc_src"):
-                    feat_src = self.fc(h_src).view(*src_prefix_shape, self._num_heads, self._out_feats)
-                    feat_dst = self.fc(h_dst).view(*dst_prefix_shape, self._num_heads, self._out_feats)
-                else:
-                    feat_src = self.fc_src(h_src).view(*src_prefix_shape, self._num_heads, self._out_feats)
-                    feat_dst = self.fc_dst(h_dst).view(*dst_prefix_shape, self._num_heads, self._out_feats)
-            else:
-                src_prefix_shape = dst_prefix_shape = feat.shape[:-1]
-                h_src = h_dst = self.feat_drop(feat)
-                feat_src = feat_dst = self.fc(h_src).view(*src_prefix_shape, self._num_heads, self._out_feats)
-                if graph.is_block:
-                    feat_dst = feat_src[: graph.number_of_dst_nodes()]
-                    h_dst = h_dst[: graph.number_of_dst_nodes()]
-                    dst_prefix_shape = (graph.number_of_dst_nodes(),) + dst_prefix_shape[1:]
-            el = (feat_src * self.attn_l).sum(dim=-1).unsqueeze(-1)
-            er = (feat_dst * self.attn_r).sum(dim=-1).unsqueeze(-1)
-            # per-head rows that are not a multiple of 16 bytes (e.g. 41 classes) would force 4-byte accesses on E x D
-            # elements in the aggregation and its backward: zero-pad the (small) node tensor, slice the result
-            ft_pad = 0
-            if feat_src.is_cuda and feat_src.dim() == 3 and graph.num_edges() >= 4 * feat_src.shape[0]:
-                vec = 16 // feat_src.element_size()
-                ft_pad = (-self._out_feats) % vec
-            if (feat_src.is_cuda and feat_src.dim() == 3 and edge_weight is None and not get_attention
-                    and (self.attn_drop.p == 0 or not self.training) and len(graph.canonical_etypes) == 1):
-                # whole attention block in two kernels (online-softmax forward, recomputing backward)
-                from ...ops import gat_fused
-                vec = 16 // feat_src.element_size()
-                pad = (-self._out_feats) % vec
-                if gat_fused.supported(el, feat_src, self._num_heads, self._out_feats + pad):
-                    ftp = F.pad(feat_src, (0, pad)) if pad else feat_src
-                    rst = gat_fused.fused_gat(graph._graphs[0], el.squeeze(-1), er.squeeze(-1), ftp,
-                                              self.leaky_relu.negative_slope)
-                    if pad:
-                        rst = rst[..., : self._out_feats]
-                    return self._finish(rst, h_dst, dst_prefix_shape)
-            if ft_pad:
-                feat_src = F.pad(feat_src, (0, ft_pad))
-            graph.srcdata.update({"ft": feat_src, "el": el})
-            graph.dstdata.update({"er": er})
-            graph.apply_edges(fn.u_add_v("el", "er", "e"))
-            e = self.leaky_relu(graph.edata.pop("e"))
-            graph.edata["a"] = self.attn_drop(edge_softmax(graph, e))
-            if edge_weight is not None:
-                graph.edata["a"] = graph.edata["a"] * edge_weight.tile(1, self._num_heads, 1).transpose(0, 2)
-            graph.update_all(fn.u_mul_e("ft", "a", "m"), fn.sum("m", "ft"))
-            rst = graph.dstdata["ft"]
-            if ft_pad:
-                rst = rst[..., : self._out_feats]
-            rst = self._finish(rst, h_dst, dst_prefix_shape)
-            if get_attention:
-                return rst, _attention_to_eid_order(graph.edata["a"], emap)
-            return rst
-
-    def _finish(self, rst, h_dst, dst_prefix_shape):
-        if self.res_fc is not None:
-            resval = self.res_fc(h_dst).view(*dst_prefix_shape, -1, self._out_feats)
-            rst = rst + resval
-        if self.has_explicit_bias:
-            rst = rst + self.bias.view(*((1,) * len(dst_prefix_shape)), self._num_heads, self._out_feats)
-        if self.activation:
-            rst = self.activation(rst)
-        return rst
+        _mp.require_in_edges(graph, self._allow_zero_in_degree, self._layer_name)
+        g, emap, edge_weight = _attention_view(graph, edge_weight)
+        h_src, h_dst = self._inputs(g, feat, self.feat_drop)
+        z_src, z_dst = self._project(g, h_src, h_dst, shared_input=not isinstance(feat, (tuple, list)))
+        s_src = (z_src * self.attn_l).sum(-1)                      # [N_src, H]
+        s_dst = (z_dst * self.attn_r).sum(-1)
+        plain = edge_weight is None and not get_attention and not (self.training and self.attn_drop.p > 0)
+        if plain and z_src.is_cuda and z_src.dim() == 3 and len(g.canonical_etypes) == 1:
+            out = self._fused(g, z_src, s_src, s_dst)
+            if out is not None:
+                return self._epilogue(out, h_dst, self.bias)
+        logits = self.leaky_relu(_mp.pair_op(g, "add", s_src.unsqueeze(-1), s_dst.unsqueeze(-1)))
+        attn = self.attn_drop(_mp.attend(g, logits))               # [E, H, 1]
+        if edge_weight is not None:
+            attn = attn * edge_weight.reshape(-1, 1, 1)
+        # 4-byte accesses on E x D elements are avoided by padding per-head rows to 16 bytes on dense graphs
+        pad = 0
+        if z_src.is_cuda and z_src.dim() == 3 and g.num_edges() >= 4 * z_src.shape[0]:
+            pad = (-self._out_feats) % (16 // z_src.element_size())
+        out = _mp.gather_sum(g, F.pad(z_src, (0, pad)) if pad else z_src, attn)
+        out = self._epilogue(out[..., : self._out_feats] if pad else out, h_dst, self.bias)
+        return (out, _to_eid_order(attn, emap)) if get_attention else out
 
 
-class GATv2Conv(nn.Module):
-    r"""GATv2: e_ij = a^T LeakyReLU(W_l h_i + W_r h_j) (reference gatv2conv.py)."""
+class GATv2Conv(_HeadedAttention):
+    r"""GATv2 (dynamic attention): ``e_ij = a . LeakyReLU(W_l h_j + W_r h_i)``."""
+
+    _layer_name = "GATv2Conv"
 
     def __init__(self, in_feats, out_feats, num_heads, feat_drop=0.0, attn_drop=0.0, negative_slope=0.2, residual=False,
                  activation=None, allow_zero_in_degree=False, bias=True, share_weights=False):
         super().__init__()
-        self._num_heads = num_heads
-        self._in_src_feats, self._in_dst_feats = expand_as_pair(in_feats)
-        self._out_feats = out_feats
-        self._allow_zero_in_degree = allow_zero_in_degree
-        self.fc_src = nn.Linear(self._in_src_feats, out_feats * num_heads, bias=bias)
-        if share_weights:
-            self.fc_dst = self.fc_src
-        else:
-            self.fc_dst = nn.Linear(self._in_dst_feats, out_feats * num_heads, bias=bias)
-        self.attn = nn.Parameter(torch.FloatTensor(size=(1, num_heads, out_feats)))
-        self.feat_drop = nn.Dropout(feat_drop)
-        self.attn_drop = nn.Dropout(attn_drop)
+        self._num_heads, self._out_feats, self._allow_zero_in_degree = num_heads, out_feats, allow_zero_in_degree
+        self._in_src_feats, self._in_dst_feats = _pair(in_feats)
+        width = out_feats * num_heads
+        self.fc_src = nn.Linear(self._in_src_feats, width, bias=bias)
+        self.fc_dst = self.fc_src if share_weights else nn.Linear(self._in_dst_feats, width, bias=bias)
+        self.attn = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.feat_drop, self.attn_drop = nn.Dropout(feat_drop), nn.Dropout(attn_drop)
         self.leaky_relu = nn.LeakyReLU(negative_slope)
-        if residual:
-            if self._in_dst_feats != out_feats * num_heads:
-                self.res_fc = nn.Linear(self._in_dst_feats, num_heads * out_feats, bias=bias)
-            else:
-                self.res_fc = nn.Identity()
-        else:
-            self.register_buffer("res_fc", None)
-        self.activation = activation
-        self.share_weights = share_weights
-        self.bias = bias
+        self._make_residual(residual, width, bias=bias)
+        self.activation, self.share_weights, self.bias = activation, share_weights, bias
         self.reset_parameters()
 
     def reset_parameters(self):
         gain = nn.init.calculate_gain("relu")
-        nn.init.xavier_normal_(self.fc_src.weight, gain=gain)
-        if self.bias:
-            nn.init.constant_(self.fc_src.bias, 0)
-        if not self.share_weights:
-            nn.init.xavier_normal_(self.fc_dst.weight, gain=gain)
-            if self.bias:
-                nn.init.constant_(self.fc_dst.bias, 0)
+        for lin in {self.fc_src, self.fc_dst} | ({self.res_fc} if isinstance(self.res_fc, nn.Linear) else set()):
+            nn.init.xavier_normal_(lin.weight, gain=gain)
+            if lin.bias is not None:
+                nn.init.zeros_(lin.bias)
         nn.init.xavier_normal_(self.attn, gain=gain)
-        if isinstance(self.res_fc, nn.Linear):
-            nn.init.xavier_normal_(self.res_fc.weight, gain=gain)
-            if self.bias:
-                nn.init.constant_(self.res_fc.bias, 0)
-
-    def set_allow_zero_in_degree(self, set_value):
-        self._allow_zero_in_degree = set_value
 
     def forward(self, graph, feat, get_attention=False):
-        _zero_in_degree_check(graph, self._allow_zero_in_degree)
-        graph, emap, _ = _attention_view(graph)
-        with graph.local_scope():
-            if isinstance(feat, tuple):
-                h_src = self.feat_drop(feat[0])
-                h_dst = self.feat_drop(feat[1])
-                feat_src = self.fc_src(h_src).view(-1, self._num_heads, self._out_feats)
-                feat_dst = self.fc_dst(h_dst).view(-1, self._num_heads, self._out_feats)
-            else:
-                h_src = h_dst = self.feat_drop(feat)
-                feat_src = self.fc_src(h_src).view(-1, self._num_heads, self._out_feats)
-                if self.share_weights:
-                    feat_dst = feat_src
-                else:
-                    feat_dst = self.fc_dst(h_src).view(-1, self._num_heads, self._out_feats)
-                if graph.is_block:
-                    feat_dst = feat_dst[: graph.number_of_dst_nodes()]
-                    h_dst = h_dst[: graph.number_of_dst_nodes()]
-            graph.srcdata.update({"el": feat_src})
-            graph.dstdata.update({"er": feat_dst})
-            graph.apply_edges(fn.u_add_v("el", "er", "e"))
-            e = self.leaky_relu(graph.edata.pop("e"))
-            e = (e * self.attn).sum(dim=-1).unsqueeze(dim=2)
-            graph.edata["a"] = self.attn_drop(edge_softmax(graph, e))
-            graph.update_all(fn.u_mul_e("el", "a", "m"), fn.sum("m", "ft"))
-            rst = graph.dstdata["ft"]
-            if self.res_fc is not None:
-                resval = self.res_fc(h_dst).view(h_dst.shape[0], -1, self._out_feats)
-                rst = rst + resval
-            if self.activation:
-                rst = self.activation(rst)
-            if get_attention:
-                return rst, _attention_to_eid_order(graph.edata["a"], emap)
-            return rst
+        _mp.require_in_edges(graph, self._allow_zero_in_degree, self._layer_name)
+        g, emap = _attention_view(graph)
+        h_src, h_dst = self._inputs(g, feat, self.feat_drop)
+        H, D = self._num_heads, self._out_feats
+        z_src = self.fc_src(h_src).view(-1, H, D)
+        if self.share_weights and not isinstance(feat, (tuple, list)):
+            z_dst = z_src[: g.number_of_dst_nodes()]
+        else:
+            z_dst = self.fc_dst(h_dst).view(-1, H, D)
+        hidden = self.leaky_relu(_mp.pair_op(g, "add", z_src, z_dst))                    # [E, H, D]
+        attn = self.attn_drop(_mp.attend(g, (hidden * self.attn).sum(-1, keepdim=True)))
+        out = self._epilogue(_mp.gather_sum(g, z_src, attn), h_dst)
+        return (out, _to_eid_order(attn, emap)) if get_attention else out
 
 
-class DotGatConv(nn.Module):
-    r"""Dot-product attention: e_ij = (W h_i)^T (W h_j) (reference dotgatconv.py) — g-SDDMM u_dot_v path."""
+class DotGatConv(_HeadedAttention):
+    r"""Scaled dot-product attention ``e_ij = (W h_i) . (W h_j) / sqrt(d)`` (g-SDDMM u_dot_v)."""
+
+    _layer_name = "DotGatConv"
 
     def __init__(self, in_feats, out_feats, num_heads, allow_zero_in_degree=False):
         super().__init__()
-        self._in_src_feats, self._in_dst_feats = expand_as_pair(in_feats)
-        self._out_feats = out_feats
-        self._allow_zero_in_degree = allow_zero_in_degree
-        self._num_heads = num_heads
-        if isinstance(in_feats, tuple):
-            self.fc_src = nn.Linear(self._in_src_feats, self._out_feats * self._num_heads, bias=False)
-            self.fc_dst = nn.Linear(self._in_dst_feats, self._out_feats * self._num_heads, bias=False)
-        else:
-            self.fc = nn.Linear(self._in_src_feats, self._out_feats * self._num_heads, bias=False)
+        self._num_heads, self._out_feats, self._allow_zero_in_degree = num_heads, out_feats, allow_zero_in_degree
+        self._make_projections(in_feats, out_feats * num_heads)
 
     def forward(self, graph, feat, get_attention=False):
-        graph = graph.local_var()
-        _zero_in_degree_check(graph, self._allow_zero_in_degree)
-        if isinstance(feat, tuple):
-            h_src, h_dst = feat
-            feat_src = self.fc_src(h_src).view(-1, self._num_heads, self._out_feats)
-            feat_dst = self.fc_dst(h_dst).view(-1, self._num_heads, self._out_feats)
-        else:
-            h_src = feat
-            feat_src = feat_dst = self.fc(h_src).view(-1, self._num_heads, self._out_feats)
-            if graph.is_block:
-                feat_dst = feat_src[: graph.number_of_dst_nodes()]
-        graph.srcdata.update({"ft": feat_src})
-        graph.dstdata.update({"ft": feat_dst})
-        graph.apply_edges(fn.u_dot_v("ft", "ft", "a"))
-        graph.edata["sa"] = edge_softmax(graph, graph.edata["a"] / self._out_feats ** 0.5)
-        graph.update_all(fn.u_mul_e("ft", "sa", "attn"), fn.sum("attn", "agg_u"))
-        rst = graph.dstdata["agg_u"]
-        if get_attention:
-            return rst, graph.edata["sa"]
-        return rst
+        _mp.require_in_edges(graph, self._allow_zero_in_degree, self._layer_name)
+        h_src, h_dst = self._inputs(graph, feat)
+        z_src, z_dst = self._project(graph, h_src, h_dst, shared_input=not isinstance(feat, (tuple, list)))
+        attn = _mp.attend(graph, _mp.pair_op(graph, "dot", z_src, z_dst) / self._out_feats ** 0.5)
+        out = _mp.gather_sum(graph, z_src, attn)
+        return (out, attn) if get_attention else out
 
 
 class AGNNConv(nn.Module):
-    r"""Attention-based GNN: P_ij = softmax(beta * cos(h_i, h_j)) (reference agnnconv.py)."""
+    r"""Attention-based propagation ``P_ij = softmax_j( beta * cos(h_i, h_j) )``, ``H' = P H`` (no weights)."""
 
     def __init__(self, init_beta=1.0, learn_beta=True, allow_zero_in_degree=False):
         super().__init__()
         self._allow_zero_in_degree = allow_zero_in_degree
+        beta = torch.tensor([float(init_beta)])
         if learn_beta:
-            self.beta = nn.Parameter(torch.Tensor([init_beta]))
+            self.beta = nn.Parameter(beta)
         else:
-            self.register_buffer("beta", torch.Tensor([init_beta]))
+            self.register_buffer("beta", beta)
 
     def set_allow_zero_in_degree(self, set_value):
         self._allow_zero_in_degree = set_value
 
     def forward(self, graph, feat):
-        with graph.local_scope():
-            _zero_in_degree_check(graph, self._allow_zero_in_degree)
-            feat_src, feat_dst = expand_as_pair(feat, graph)
-            graph.srcdata["h"] = feat_src
-            graph.srcdata["norm_h"] = F.normalize(feat_src, p=2, dim=-1)
-            if isinstance(feat, tuple) or graph.is_block:
-                graph.dstdata["norm_h"] = F.normalize(feat_dst, p=2, dim=-1)
-            graph.apply_edges(fn.u_dot_v("norm_h", "norm_h", "cos"))
-            cos = graph.edata.pop("cos")
-            e = self.beta * cos
-            graph.edata["p"] = edge_softmax(graph, e)
-            graph.update_all(fn.u_mul_e("h", "p", "m"), fn.sum("m", "h"))
-            return graph.dstdata.pop("h")
+        _mp.require_in_edges(graph, self._allow_zero_in_degree, "AGNNConv")
+        x_src, x_dst = _mp.src_dst(graph, feat)
+        unit_src = F.normalize(x_src, p=2, dim=-1)
+        unit_dst = unit_src if x_dst is x_src else F.normalize(x_dst, p=2, dim=-1)
+        cos = _mp.pair_op(graph, "dot", unit_src, unit_dst)
+        return _mp.gather_sum(graph, x_src, _mp.attend(graph, self.beta * cos))
 
 
 class EGATConv(nn.Module):
-    r"""GAT with edge features, returns new node and edge features (reference egatconv.py)."""
+    r"""GAT with edge features: returns new node features [N, H, out_node] and edge features [E, H, out_edge]."""
 
     def __init__(self, in_node_feats, in_edge_feats, out_node_feats, out_edge_feats, num_heads, bias=True):
         super().__init__()
-        self._num_heads = num_heads
-        self._in_src_node_feats, self._in_dst_node_feats = expand_as_pair(in_node_feats)
-        self._out_node_feats = out_node_feats
-        self._out_edge_feats = out_edge_feats
-        if isinstance(in_node_feats, tuple):
-            self.fc_node_src = nn.Linear(self._in_src_node_feats, out_node_feats * num_heads, bias=False)
-            self.fc_ni = nn.Linear(self._in_src_node_feats, out_edge_feats * num_heads, bias=False)
-            self.fc_nj = nn.Linear(self._in_dst_node_feats, out_edge_feats * num_heads, bias=False)
-        else:
-            self.fc_node_src = nn.Linear(self._in_src_node_feats, out_node_feats * num_heads, bias=False)
-            self.fc_ni = nn.Linear(self._in_src_node_feats, out_edge_feats * num_heads, bias=False)
-            self.fc_nj = nn.Linear(self._in_src_node_feats, out_edge_feats * num_heads, bias=False)
+        self._num_heads, self._out_node_feats, self._out_edge_feats = num_heads, out_node_feats, out_edge_feats
+        self._in_src_node_feats, self._in_dst_node_feats = _pair(in_node_feats)
+        dst_width = self._in_dst_node_feats if isinstance(in_node_feats, (tuple, list)) else self._in_src_node_feats
+        self.fc_node_src = nn.Linear(self._in_src_node_feats, out_node_feats * num_heads, bias=False)
+        self.fc_ni = nn.Linear(self._in_src_node_feats, out_edge_feats * num_heads, bias=False)
+        self.fc_nj = nn.Linear(dst_width, out_edge_feats * num_heads, bias=False)
         self.fc_fij = nn.Linear(in_edge_feats, out_edge_feats * num_heads, bias=False)
-        self.attn = nn.Parameter(torch.FloatTensor(size=(1, num_heads, out_edge_feats)))
+        self.attn = nn.Parameter(torch.empty(1, num_heads, out_edge_feats))
         if bias:
-            self.bias = nn.Parameter(torch.FloatTensor(size=(num_heads * out_edge_feats,)))
+            self.bias = nn.Parameter(torch.empty(num_heads * out_edge_feats))
         else:
             self.register_buffer("bias", None)
         self.reset_parameters()
 
     def reset_parameters(self):
         gain = nn.init.calculate_gain("relu")
-        for m in (self.fc_node_src, self.fc_ni, self.fc_fij, self.fc_nj):
-            nn.init.xavier_normal_(m.weight, gain=gain)
+        for lin in (self.fc_node_src, self.fc_ni, self.fc_fij, self.fc_nj):
+            nn.init.xavier_normal_(lin.weight, gain=gain)
         nn.init.xavier_normal_(self.attn, gain=gain)
         if self.bias is not None:
-            nn.init.constant_(self.bias, 0)
+            nn.init.zeros_(self.bias)
 
     def forward(self, graph, nfeats, efeats, get_attention=False):
-        with graph.local_scope():
-            if bool((graph.in_degrees() == 0).any()):
-                raise DGLError("There are 0-in-degree nodes in the graph, output for those nodes will be invalid. "
-                               "Adding self-loop on the input graph by calling `g = dgl.add_self_loop(g)` will resolve "
-                               "the issue.")
-            if isinstance(nfeats, tuple):
-                nfeats_src, nfeats_dst = nfeats
-            else:
-                nfeats_src = nfeats_dst = nfeats
-                if graph.is_block:
-                    nfeats_dst = nfeats[: graph.number_of_dst_nodes()]
-            f_ni = self.fc_ni(nfeats_src)
-            f_nj = self.fc_nj(nfeats_dst)
-            f_fij = self.fc_fij(efeats)
-            graph.srcdata.update({"f_ni": f_ni})
-            graph.dstdata.update({"f_nj": f_nj})
-            graph.apply_edges(fn.u_add_v("f_ni", "f_nj", "f_tmp"))
-            f_out = graph.edata.pop("f_tmp") + f_fij
-            if self.bias is not None:
-                f_out = f_out + self.bias
-            f_out = F.leaky_relu(f_out)
-            f_out = f_out.view(-1, self._num_heads, self._out_edge_feats)
-            e = (f_out * self.attn).sum(dim=-1).unsqueeze(-1)
-            graph.edata["a"] = edge_softmax(graph, e)
-            graph.srcdata["h_out"] = self.fc_node_src(nfeats_src).view(-1, self._num_heads, self._out_node_feats)
-            graph.update_all(fn.u_mul_e("h_out", "a", "m"), fn.sum("m", "h_out"))
-            h_out = graph.dstdata["h_out"].view(-1, self._num_heads, self._out_node_feats)
-            if get_attention:
-                return h_out, f_out, graph.edata.pop("a")
-            return h_out, f_out
+        _mp.require_in_edges(graph, False, "EGATConv")
+        x_src, x_dst = _mp.src_dst(graph, nfeats)
+        H = self._num_heads
+        f = _mp.pair_op(graph, "add", self.fc_ni(x_src), self.fc_nj(x_dst)) + self.fc_fij(efeats)
+        if self.bias is not None:
+            f = f + self.bias
+        f_out = F.leaky_relu(f).view(-1, H, self._out_edge_feats)
+        attn = _mp.attend(graph, (f_out * self.attn).sum(-1, keepdim=True))
+        h_out = _mp.gather_sum(graph, self.fc_node_src(x_src).view(-1, H, self._out_node_feats), attn)
+        return (h_out, f_out, attn) if get_attention else (h_out, f_out)
 
 
-class EdgeGATConv(nn.Module):
-    r"""GAT whose attention logits and messages include edge features (reference edgegatconv.py)."""
+class EdgeGATConv(_HeadedAttention):
+    r"""GAT whose logits and messages both include a projection of the edge features:
+    ``e_ij = LeakyReLU(a_l . W h_j + a_r . W h_i + a_e . W_e f_ij)``, message ``alpha_ij (W h_j + W_e f_ij)``."""
+
+    _layer_name = "EdgeGATConv"
 
     def __init__(self, in_feats, edge_feats, out_feats, num_heads, feat_drop=0.0, attn_drop=0.0, negative_slope=0.2,
                  residual=True, activation=None, allow_zero_in_degree=False, bias=True):
         super().__init__()
-        self._num_heads = num_heads
-        self._in_src_feats, self._in_dst_feats = expand_as_pair(in_feats)
-        self._out_feats = out_feats
-        self._allow_zero_in_degree = allow_zero_in_degree
-        if isinstance(in_feats, tuple):
-            self.fc_src = nn.Linear(self._in_src_feats, out_feats * num_heads, bias=False)
-            self.fc_dst = nn.Linear(self._in_dst_feats, out_feats * num_heads, bias=False)
-        else:
-            self.fc = nn.Linear(self._in_src_feats, out_feats * num_heads, bias=False)
-        self.attn_l = nn.Parameter(torch.FloatTensor(size=(1, num_heads, out_feats)))
-        self.attn_r = nn.Parameter(torch.FloatTensor(size=(1, num_heads, out_feats)))
-        self.feat_drop = nn.Dropout(feat_drop)
-        self.attn_drop = nn.Dropout(attn_drop)
+        self._num_heads, self._out_feats, self._allow_zero_in_degree = num_heads, out_feats, allow_zero_in_degree
+        width = out_feats * num_heads
+        self._make_projections(in_feats, width)
+        self.attn_l = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.attn_r = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.feat_drop, self.attn_drop = nn.Dropout(feat_drop), nn.Dropout(attn_drop)
         self.leaky_relu = nn.LeakyReLU(negative_slope)
-        self.fc_edge = nn.Linear(edge_feats, out_feats * num_heads, bias=False)
-        self.attn_edge = nn.Parameter(torch.FloatTensor(size=(1, num_heads, out_feats)))
+        self.fc_edge = nn.Linear(edge_feats, width, bias=False)
+        self.attn_edge = nn.Parameter(torch.empty(1, num_heads, out_feats))
         if bias:
-            self.bias = nn.Parameter(torch.FloatTensor(size=(num_heads * out_feats,)))
+            self.bias = nn.Parameter(torch.empty(width))
         else:
             self.register_buffer("bias", None)
-        if residual:
-            if self._in_dst_feats != out_feats * num_heads:
-                self.res_fc = nn.Linear(self._in_dst_feats, num_heads * out_feats, bias=False)
-            else:
-                self.res_fc = nn.Identity()
-        else:
-            self.register_buffer("res_fc", None)
-        self.reset_parameters()
+        self._make_residual(residual, width)
         self.activation = activation
+        self.reset_parameters()
 
     def reset_parameters(self):
         gain = nn.init.calculate_gain("relu")
-        if hasattr(self, "fc"):
-            nn.init.xavier_normal_(self.fc.weight, gain=gain)
-        else:
-            nn.init.xavier_normal_(self.fc_src.weight, gain=gain)
-            nn.init.xavier_normal_(self.fc_dst.weight, gain=gain)
-        nn.init.xavier_normal_(self.attn_l, gain=gain)
-        nn.init.xavier_normal_(self.attn_r, gain=gain)
-        nn.init.xavier_normal_(self.fc_edge.weight, gain=gain)
-        nn.init.xavier_normal_(self.attn_edge, gain=gain)
-        if self.bias is not None:
-            nn.init.constant_(self.bias, 0)
+        lins = [getattr(self, n) for n in ("fc", "fc_src", "fc_dst") if hasattr(self, n)] + [self.fc_edge]
         if isinstance(self.res_fc, nn.Linear):
-            nn.init.xavier_normal_(self.res_fc.weight, gain=gain)
-
-    def set_allow_zero_in_degree(self, set_value):
-        self._allow_zero_in_degree = set_value
+            lins.append(self.res_fc)
+        for lin in lins:
+            nn.init.xavier_normal_(lin.weight, gain=gain)
+        for a in (self.attn_l, self.attn_r, self.attn_edge):
+            nn.init.xavier_normal_(a, gain=gain)
+        if self.bias is not None:
+            nn.init.zeros_(self.bias)
 
     def forward(self, graph, feat, edge_feat, get_attention=False):
-        with graph.local_scope():
-            _zero_in_degree_check(graph, self._allow_zero_in_degree)
-            if isinstance(feat, tuple):
-                h_src = self.feat_drop(feat[0])
-                h_dst = self.feat_drop(feat[1])
-                if not hasattr(self, "fc_src"):
-                    feat_src = self.fc(h_src).view(-1, self._num_heads, self._out_feats)
-                    feat_dst = self.fc(h_dst).view(-1, self._num_heads, self._out_feats)
-                else:
-                    feat_src = self.fc_src(h_src).view(-1, self._num_heads, self._out_feats)
-                    feat_dst = self.fc_dst(h_dst).view(-1, self._num_heads, self._out_feats)
-            else:
-                h_src = h_dst = self.feat_drop(feat)
-                feat_src = feat_dst = self.fc(h_src).view(-1, self._num_heads, self._out_feats)
-                if graph.is_block:
-                    feat_dst = feat_src[: graph.number_of_dst_nodes()]
-                    h_dst = h_dst[: graph.number_of_dst_nodes()]
-            n_edges = edge_feat.shape[:-1]
-            feat_edge = self.fc_edge(edge_feat).view(*n_edges, self._num_heads, self._out_feats)
-            ee = (feat_edge * self.attn_edge).sum(dim=-1).unsqueeze(-1)
-            graph.edata.update({"ft_edge": feat_edge, "ee": ee})
-            el = (feat_src * self.attn_l).sum(dim=-1).unsqueeze(-1)
-            er = (feat_dst * self.attn_r).sum(dim=-1).unsqueeze(-1)
-            graph.srcdata.update({"ft": feat_src, "el": el})
-            graph.dstdata.update({"er": er})
-            graph.apply_edges(fn.u_add_v("el", "er", "e_tmp"))
-            e = self.leaky_relu(graph.edata.pop("e_tmp") + graph.edata["ee"])
-            graph.edata["a"] = self.attn_drop(edge_softmax(graph, e))
-            # message = a * (ft_src + ft_edge)
-            graph.update_all(fn.u_mul_e("ft", "a", "m"), fn.sum("m", "ft_n"))
-            graph.edata["m_e"] = graph.edata["ft_edge"] * graph.edata["a"]
-            graph.update_all(fn.copy_e("m_e", "m"), fn.sum("m", "ft_e"))
-            rst = graph.dstdata["ft_n"] + graph.dstdata["ft_e"]
-            if self.res_fc is not None:
-                resval = self.res_fc(h_dst).view(h_dst.shape[0], -1, self._out_feats)
-                rst = rst + resval
-            if self.bias is not None:
-                rst = rst + self.bias.view(1, self._num_heads, self._out_feats)
-            if self.activation:
-                rst = self.activation(rst)
-            if get_attention:
-                return rst, graph.edata["a"]
-            return rst
+        _mp.require_in_edges(graph, self._allow_zero_in_degree, self._layer_name)
+        H, D = self._num_heads, self._out_feats
+        h_src, h_dst = self._inputs(graph, feat, self.feat_drop)
+        z_src, z_dst = self._project(graph, h_src, h_dst, shared_input=not isinstance(feat, (tuple, list)))
+        z_edge = self.fc_edge(edge_feat).view(*edge_feat.shape[:-1], H, D)
+        s_src = (z_src * self.attn_l).sum(-1, keepdim=True)
+        s_dst = (z_dst * self.attn_r).sum(-1, keepdim=True)
+        s_edge = (z_edge * self.attn_edge).sum(-1, keepdim=True)
+        attn = self.attn_drop(_mp.attend(graph, self.leaky_relu(_mp.pair_op(graph, "add", s_src, s_dst) + s_edge)))
+        out = _mp.gather_sum(graph, z_src, attn) + _mp.edge_reduce(graph, z_edge * attn, "sum")
+        out = self._epilogue(out, h_dst, self.bias)
+        return (out, attn) if get_attention else out

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 
 from ... import function as fn
 
-__all__ = ["AX", "normalized_AX", "D_power_X", "D_power_bias_X", "Propagate", "PropagateNoPrecond", "Attention", "MLP",
+__all__ = ["TWIRLSUnfoldingAndAttention", "AX", "normalized_AX", "D_power_X", "D_power_bias_X", "Propagate", "PropagateNoPrecond", "Attention", "MLP",
            "InvertibleCheckpoint", "CuGraphBaseConv"]
 
 
@@ -194,3 +194,34 @@ class CuGraphBaseConv(nn.Module):
         buf[: offsets.numel()] = offsets
         buf[offsets.numel(): size] = offsets[-1]
         return buf[:size]
+
+
+class TWIRLSUnfoldingAndAttention(nn.Module):
+    """The unfolded optimiser of TWIRLS: ``prop_step`` descent steps on the graph-regularised energy (pre-conditioned
+    eq. 28 or plain eq. 30), with one IRLS attention re-weighting before the first step (``init_att``) and / or after step
+    ``attn_aft``. Edge weights and weighted degrees travel in ``edata['w']`` / ``ndata['deg']`` of a private copy."""
+
+    def __init__(self, d, alp, lam, prop_step, attn_aft=-1, tau=0.2, T=-1, p=1, use_eta=False, init_att=False,
+                 attn_dropout=0, precond=True):
+        super().__init__()
+        self.d, self.lam, self.tau, self.p = d, lam, tau, p
+        self.alp = alp if alp > 0 else 1 / (lam + 1)          # default step size
+        self.prop_step, self.attn_aft, self.use_eta, self.init_att = prop_step, attn_aft, use_eta, init_att
+        step = Propagate if precond else PropagateNoPrecond
+        self.prop_layers = nn.ModuleList([step() for _ in range(prop_step)])
+        self.init_attn = Attention(tau, T, p, attn_dropout) if init_att else None
+        self.attn_layer = Attention(tau, T, p, attn_dropout) if attn_aft >= 0 else None
+        self.etas = nn.Parameter(torch.ones(d)) if use_eta else None
+
+    def forward(self, g, X):
+        g = g.local_var()
+        g.edata["w"] = torch.ones(g.num_edges(), 1, device=X.device, dtype=X.dtype)
+        g.ndata["deg"] = g.in_degrees().to(X)
+        Y = X
+        if self.init_att:
+            g = self.init_attn(g, Y, self.etas)
+        for k, step in enumerate(self.prop_layers):
+            Y = step(g, Y, X, self.alp, self.lam)
+            if k == self.attn_aft - 1:
+                g = self.attn_layer(g, Y, self.etas)
+        return Y

@@ -1,8 +1,19 @@
-"""Sum/mean-aggregation and spectral convolutions: GINConv, GINEConv, SGConv, TAGConv, APPNPConv, ChebConv,
-GCN2Conv, GatedGraphConv, GatedGCNConv, CFConv, NNConv, GMMConv, TWIRLSConv, EdgeConv, EGNNConv.
+"""Propagation-filter, isomorphism and edge-conditioned convolutions.
 
-Parity: the like-named files under /root/reference/python/dgl/nn/pytorch/conv/. Every layer lowers to the
-g-SpMM / g-SDDMM primitives.
+GINConv / GINEConv, SGConv / TAGConv / APPNPConv / ChebConv / GCN2Conv (polynomial filters of the normalised adjacency),
+GatedGraphConv / GatedGCNConv, CFConv / NNConv / GMMConv / EdgeConv / EGNNConv, TWIRLSConv.
+
+Constructor signatures and parameter names follow /root/reference/python/dgl/nn/pytorch/conv/<layer>.py (checkpoints
+interchange; ``tests/test_nn_reference_parity.py`` checks values and gradients against the unmodified reference). The
+forward passes are written on the tensor-level operators of ``nn/_mp.py``:
+
+* every degree normalisation is folded into cached per-edge coefficients, so one propagation step is ONE weighted
+  g-SpMM (``_mp.sym_norm_propagate``) instead of scale -> SpMM -> scale;
+* linear maps that the reference applies per EDGE are hoisted to the nodes whenever the message is linear in an
+  endpoint (EdgeConv: ``Theta (x_v - x_u)`` = ``(Theta x)_v - (Theta x)_u``, EGNN: the first edge-MLP layer splits into
+  per-endpoint GEMMs), which turns E x d GEMMs into N x d ones and removes [E, in] intermediates;
+* typed per-edge transforms (GatedGraphConv) run as one grouped GEMM (``ops.gather_mm``) instead of a Python loop of
+  ``send_and_recv`` over edge-type subsets.
 """
 from __future__ import annotations
 
@@ -12,84 +23,81 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from ... import function as fn
+from ... import ops
 from ...base import DGLError
-from ...ops import edge_softmax
-from ...utils import expand_as_pair
+from .. import _mp
+from .graphconv import EdgeWeightNorm
+from .parts import MLP, TWIRLSUnfoldingAndAttention
+
+_REDUCERS = ("sum", "max", "mean")
 
 
+def _eps_holder(module, init_eps, learn_eps):
+    value = torch.tensor([float(init_eps)])
+    if learn_eps:
+        module.eps = nn.Parameter(value)
+    else:
+        module.register_buffer("eps", value)
+
+
+def _both_norm_or_weights(g, dtype, edge_weight, mode="in_both"):
+    """Edge coefficients of one propagation step: the structural symmetric normalisation (``in_both``: the in-degree
+    vector on both ends, as these filters are defined on undirected graphs; ``both``: out-degree of the source), or the
+    caller's weights symmetric-normalised by their weighted degrees."""
+    if edge_weight is None:
+        return _mp.norm_coefficients(g, mode, dtype)
+    return EdgeWeightNorm("both")(g, edge_weight)
+
+
+# =====================================================================================================================
+#  isomorphism networks
+# =====================================================================================================================
 class GINConv(nn.Module):
-    r"""h_i' = f((1 + eps) h_i + aggregate_j(e_ji h_j)) (reference ginconv.py)."""
+    r"""``h_i' = f( (1 + eps) h_i + aggregate_j w_ji h_j )`` with aggregate in sum | max | mean."""
 
     def __init__(self, apply_func=None, aggregator_type="sum", init_eps=0, learn_eps=False, activation=None):
         super().__init__()
-        self.apply_func = apply_func
-        self._aggregator_type = aggregator_type
-        self.activation = activation
-        if aggregator_type not in ("sum", "max", "mean"):
-            raise KeyError("Aggregator type {} not recognized.".format(aggregator_type))
-        if learn_eps:
-            self.eps = nn.Parameter(torch.FloatTensor([init_eps]))
-        else:
-            self.register_buffer("eps", torch.FloatTensor([init_eps]))
+        if aggregator_type not in _REDUCERS:
+            raise KeyError(f"Aggregator type {aggregator_type} not recognized.")
+        self.apply_func, self._aggregator_type, self.activation = apply_func, aggregator_type, activation
+        _eps_holder(self, init_eps, learn_eps)
 
     def forward(self, graph, feat, edge_weight=None):
-        _reducer = getattr(fn, self._aggregator_type)
-        with graph.local_scope():
-            aggregate_fn = fn.copy_u("h", "m")
-            if edge_weight is not None:
-                assert edge_weight.shape[0] == graph.num_edges()
-                graph.edata["_edge_weight"] = edge_weight
-                aggregate_fn = fn.u_mul_e("h", "_edge_weight", "m")
-            feat_src, feat_dst = expand_as_pair(feat, graph)
-            graph.srcdata["h"] = feat_src
-            graph.update_all(aggregate_fn, _reducer("m", "neigh"))
-            rst = (1 + self.eps) * feat_dst + graph.dstdata["neigh"]
-            if self.apply_func is not None:
-                rst = self.apply_func(rst)
-            if self.activation is not None:
-                rst = self.activation(rst)
-            return rst
+        x_src, x_dst = _mp.src_dst(graph, feat)
+        if edge_weight is not None and edge_weight.shape[0] != graph.num_edges():
+            raise DGLError("edge_weight must have one entry per edge")
+        pooled = _mp.gather(graph, x_src, self._aggregator_type, edge_weight)
+        out = torch.addcmul(pooled, x_dst, (1 + self.eps).to(x_dst.dtype))
+        if self.apply_func is not None:
+            out = self.apply_func(out)
+        return out if self.activation is None else self.activation(out)
 
 
 class GINEConv(nn.Module):
-    r"""h_i' = f((1+eps) h_i + sum_j ReLU(h_j + e_ji)) (reference gineconv.py)."""
+    r"""``h_i' = f( (1 + eps) h_i + sum_j relu(h_j + e_ji) )``."""
 
     def __init__(self, apply_func=None, init_eps=0, learn_eps=False):
         super().__init__()
         self.apply_func = apply_func
-        if learn_eps:
-            self.eps = nn.Parameter(torch.FloatTensor([init_eps]))
-        else:
-            self.register_buffer("eps", torch.FloatTensor([init_eps]))
-
-    def message(self, edges):
-        return {"m": F.relu(edges.src["hn"] + edges.data["he"])}
+        _eps_holder(self, init_eps, learn_eps)
 
     def forward(self, graph, node_feat, edge_feat):
-        with graph.local_scope():
-            feat_src, feat_dst = expand_as_pair(node_feat, graph)
-            graph.srcdata["hn"] = feat_src
-            graph.edata["he"] = edge_feat
-            graph.apply_edges(fn.u_add_e("hn", "he", "m0"))
-            graph.edata["m"] = F.relu(graph.edata.pop("m0"))
-            graph.update_all(fn.copy_e("m", "m"), fn.sum("m", "neigh"))
-            rst = (1 + self.eps) * feat_dst + graph.dstdata["neigh"]
-            if self.apply_func is not None:
-                rst = self.apply_func(rst)
-            return rst
+        x_src, x_dst = _mp.src_dst(graph, node_feat)
+        msg = F.relu(ops.gsddmm(graph, "add", x_src, edge_feat, "u", "e"))
+        out = torch.addcmul(_mp.edge_reduce(graph, msg, "sum"), x_dst, (1 + self.eps).to(x_dst.dtype))
+        return out if self.apply_func is None else self.apply_func(out)
 
 
+# =====================================================================================================================
+#  polynomial filters of the normalised adjacency
+# =====================================================================================================================
 class SGConv(nn.Module):
-    r"""Simplified GCN: H = S^K X Theta (reference sgconv.py)."""
+    r"""Simplified GCN: ``H = (D^-1/2 A D^-1/2)^k X Theta`` (optionally cached after the first call)."""
 
     def __init__(self, in_feats, out_feats, k=1, cached=False, bias=True, norm=None, allow_zero_in_degree=False):
         super().__init__()
         self.fc = nn.Linear(in_feats, out_feats, bias=bias)
-        self._cached = cached
-        self._cached_h = None
-        self._k = k
-        self.norm = norm
+        self._cached, self._cached_h, self._k, self.norm = cached, None, k, norm
         self._allow_zero_in_degree = allow_zero_in_degree
         self.reset_parameters()
 
@@ -102,76 +110,46 @@ class SGConv(nn.Module):
         self._allow_zero_in_degree = set_value
 
     def forward(self, graph, feat, edge_weight=None):
-        with graph.local_scope():
-            if not self._allow_zero_in_degree and bool((graph.in_degrees() == 0).any()):
-                raise DGLError("There are 0-in-degree nodes in the graph, output for those nodes will be invalid. "
-                               "Adding self-loop on the input graph by calling `g = dgl.add_self_loop(g)` will "
-                               "resolve the issue.")
-            msg_func = fn.copy_u("h", "m")
-            if edge_weight is not None:
-                graph.edata["_edge_weight"] = edge_weight
-                msg_func = fn.u_mul_e("h", "_edge_weight", "m")
-            if self._cached_h is not None:
-                feat = self._cached_h
-            else:
-                if edge_weight is None:
-                    degs = graph.in_degrees().to(feat).clamp(min=1)
-                    norm = torch.pow(degs, -0.5).unsqueeze(1)
-                for _ in range(self._k):
-                    if edge_weight is None:
-                        feat = feat * norm
-                    graph.ndata["h"] = feat
-                    graph.update_all(msg_func, fn.sum("m", "h"))
-                    feat = graph.ndata.pop("h")
-                    if edge_weight is None:
-                        feat = feat * norm
-                if self.norm is not None:
-                    feat = self.norm(feat)
-                if self._cached:
-                    self._cached_h = feat
-            return self.fc(feat)
+        _mp.require_in_edges(graph, self._allow_zero_in_degree, "SGConv")
+        if self._cached_h is not None:
+            h = self._cached_h
+        else:
+            coeff = _both_norm_or_weights(graph, feat.dtype, edge_weight)
+            h = feat
+            for _ in range(self._k):
+                h = _mp.gather_sum(graph, h, coeff)
+            if self.norm is not None:
+                h = self.norm(h)
+            if self._cached:
+                self._cached_h = h
+        return self.fc(h)
 
 
 class TAGConv(nn.Module):
-    r"""Topology adaptive GCN: H = sum_k A^k X Theta_k (reference tagconv.py)."""
+    r"""Topology-adaptive GCN: ``H = [X | ÂX | ... | Â^k X] Theta``."""
 
     def __init__(self, in_feats, out_feats, k=2, bias=True, activation=None):
         super().__init__()
-        self._in_feats, self._out_feats, self._k = in_feats, out_feats, k
-        self._activation = activation
-        self.lin = nn.Linear(in_feats * (self._k + 1), out_feats, bias=bias)
+        self._in_feats, self._out_feats, self._k, self._activation = in_feats, out_feats, k, activation
+        self.lin = nn.Linear(in_feats * (k + 1), out_feats, bias=bias)
         self.reset_parameters()
 
     def reset_parameters(self):
         nn.init.xavier_normal_(self.lin.weight, gain=nn.init.calculate_gain("relu"))
 
     def forward(self, graph, feat, edge_weight=None):
-        with graph.local_scope():
-            assert graph.is_homogeneous, "Graph is not homogeneous"
-            if edge_weight is None:
-                norm = torch.pow(graph.in_degrees().to(feat).clamp(min=1), -0.5)
-                norm = norm.view(-1, *([1] * (feat.dim() - 1)))
-            msg_func = fn.copy_u("h", "m")
-            if edge_weight is not None:
-                graph.edata["_edge_weight"] = edge_weight
-                msg_func = fn.u_mul_e("h", "_edge_weight", "m")
-            fstack = [feat]
-            for _ in range(self._k):
-                rst = fstack[-1] if edge_weight is not None else fstack[-1] * norm
-                graph.ndata["h"] = rst
-                graph.update_all(msg_func, fn.sum(msg="m", out="h"))
-                rst = graph.ndata["h"]
-                if edge_weight is None:
-                    rst = rst * norm
-                fstack.append(rst)
-            rst = self.lin(torch.cat(fstack, dim=-1))
-            if self._activation is not None:
-                rst = self._activation(rst)
-            return rst
+        if graph.is_block or not graph.is_homogeneous:
+            raise DGLError("Graph is not homogeneous")
+        coeff = _both_norm_or_weights(graph, feat.dtype, edge_weight)
+        hops = [feat]
+        for _ in range(self._k):
+            hops.append(_mp.gather_sum(graph, hops[-1], coeff))
+        out = self.lin(torch.cat(hops, dim=-1))
+        return out if self._activation is None else self._activation(out)
 
 
 class APPNPConv(nn.Module):
-    r"""Approximate personalised propagation: H^{t+1} = (1-a) A_hat H^t + a H^0 (reference appnpconv.py)."""
+    r"""Approximate personalised PageRank propagation ``H_{t+1} = (1 - alpha) Â H_t + alpha H_0`` for k steps."""
 
     def __init__(self, k, alpha, edge_drop=0.0):
         super().__init__()
@@ -179,146 +157,102 @@ class APPNPConv(nn.Module):
         self.edge_drop = nn.Dropout(edge_drop)
 
     def forward(self, graph, feat, edge_weight=None):
-        with graph.local_scope():
-            if edge_weight is None:
-                src_norm = torch.pow(graph.out_degrees().to(feat).clamp(min=1), -0.5)
-                src_norm = src_norm.view(-1, *([1] * (feat.dim() - 1)))
-                dst_norm = torch.pow(graph.in_degrees().to(feat).clamp(min=1), -0.5)
-                dst_norm = dst_norm.view(-1, *([1] * (feat.dim() - 1)))
-            else:
-                edge_weight = EdgeWeightNormHelper.both(graph, edge_weight)
-            feat_0 = feat
-            for _ in range(self._k):
-                if edge_weight is None:
-                    feat = feat * src_norm
-                graph.ndata["h"] = feat
-                w = torch.ones(graph.num_edges(), 1, device=feat.device, dtype=feat.dtype) if edge_weight is None \
-                    else edge_weight.view(-1, 1).to(feat.dtype)
-                graph.edata["w"] = self.edge_drop(w).to(feat.device)
-                graph.update_all(fn.u_mul_e("h", "w", "m"), fn.sum("m", "h"))
-                feat = graph.ndata.pop("h")
-                if edge_weight is None:
-                    feat = feat * dst_norm
-                feat = (1 - self._alpha) * feat + self._alpha * feat_0
-            return feat
-
-
-class EdgeWeightNormHelper:
-    @staticmethod
-    def both(graph, w):
-        from .graphconv import EdgeWeightNorm
-        return EdgeWeightNorm("both")(graph, w)
+        coeff = _both_norm_or_weights(graph, feat.dtype, edge_weight, mode="both")
+        h, teleport = feat, self._alpha * feat
+        for _ in range(self._k):
+            w = self.edge_drop(coeff) if self.training and self.edge_drop.p > 0 else coeff
+            h = (1 - self._alpha) * _mp.gather_sum(graph, h, w) + teleport
+        return h
 
 
 class ChebConv(nn.Module):
-    r"""Chebyshev spectral convolution (reference chebconv.py)."""
+    r"""Chebyshev spectral convolution of order k on the rescaled Laplacian ``L~ = 2 L / lambda_max - I``."""
 
     def __init__(self, in_feats, out_feats, k, activation=F.relu, bias=True):
         super().__init__()
-        self._k, self._in_feats, self._out_feats = k, in_feats, out_feats
-        self.activation = activation
+        self._k, self._in_feats, self._out_feats, self.activation = k, in_feats, out_feats, activation
         self.linear = nn.Linear(k * in_feats, out_feats, bias)
 
-    def forward(self, graph, feat, lambda_max=None):
-        def unnLaplacian(feat, D_invsqrt, graph):
-            graph.ndata["h"] = feat * D_invsqrt
-            graph.update_all(fn.copy_u("h", "m"), fn.sum("m", "h"))
-            return graph.ndata.pop("h") * D_invsqrt
+    def _node_scale(self, graph, lambda_max, like):
+        if lambda_max is None:
+            from ...transforms import laplacian_lambda_max
+            lambda_max = laplacian_lambda_max(graph)
+        if not torch.is_tensor(lambda_max):
+            lambda_max = torch.as_tensor(lambda_max, dtype=like.dtype)
+        lambda_max = lambda_max.to(like)
+        if lambda_max.dim() == 1:
+            lambda_max = lambda_max.unsqueeze(-1)
+        from ...readout import broadcast_nodes
+        return 2.0 / broadcast_nodes(graph, lambda_max)          # one rescaling factor per node of a batched graph
 
-        with graph.local_scope():
-            D_invsqrt = torch.pow(graph.in_degrees().to(feat).clamp(min=1), -0.5).unsqueeze(-1)
-            if lambda_max is None:
-                from ...transforms import laplacian_lambda_max
-                lambda_max = laplacian_lambda_max(graph)
-            if isinstance(lambda_max, list):
-                lambda_max = torch.Tensor(lambda_max).to(feat)
-            if lambda_max.dim() == 1:
-                lambda_max = lambda_max.unsqueeze(-1)
-            from ...readout import broadcast_nodes
-            lambda_max = broadcast_nodes(graph, lambda_max)
-            re_norm = 2.0 / lambda_max
-            X_0 = feat
-            Xt = X_0
-            if self._k > 1:
-                h = unnLaplacian(X_0, D_invsqrt, graph)
-                X_1 = -re_norm * h + X_0 * (re_norm - 1)
-                Xt = torch.cat((Xt, X_1), 1)
-            for _ in range(2, self._k):
-                h = unnLaplacian(X_1, D_invsqrt, graph)
-                X_i = -2 * re_norm * h + X_1 * 2 * (re_norm - 1) - X_0
-                Xt = torch.cat((Xt, X_i), 1)
-                X_1, X_0 = X_i, X_1
-            h = self.linear(Xt)
-            if self.activation:
-                h = self.activation(h)
-            return h
+    def forward(self, graph, feat, lambda_max=None):
+        s = self._node_scale(graph, lambda_max, feat)
+        coeff = _mp.norm_coefficients(graph, "in_both", feat.dtype)
+
+        def rescaled_laplacian(x):                                # L~ x = s (x - Â x) - x
+            return (s - 1) * x - s * _mp.gather_sum(graph, x, coeff)
+
+        terms = [feat]
+        if self._k > 1:
+            terms.append(rescaled_laplacian(feat))
+        for _ in range(2, self._k):                               # T_i = 2 L~ T_{i-1} - T_{i-2}
+            terms.append(2 * rescaled_laplacian(terms[-1]) - terms[-2])
+        out = self.linear(torch.cat(terms, dim=1))
+        return out if self.activation is None else self.activation(out)
 
 
 class GCN2Conv(nn.Module):
-    r"""GCNII layer with initial residual and identity mapping (reference gcn2conv.py)."""
+    r"""GCNII layer: initial residual (alpha) + identity mapping (beta = log(lambda / layer + 1))."""
 
     def __init__(self, in_feats, layer, alpha=0.1, lambda_=1, project_initial_features=True,
                  allow_zero_in_degree=False, bias=True, activation=None):
         super().__init__()
-        self._in_feats = in_feats
-        self._project_initial_features = project_initial_features
-        self.alpha = alpha
-        self.beta = math.log(lambda_ / layer + 1)
-        self._bias = bias
-        self._activation = activation
-        self._allow_zero_in_degree = allow_zero_in_degree
-        self.weight1 = nn.Parameter(torch.Tensor(in_feats, in_feats))
-        if self._project_initial_features:
-            self.register_parameter("weight2", None)
-        else:
-            self.weight2 = nn.Parameter(torch.Tensor(in_feats, in_feats))
-        if self._bias:
-            self.bias = nn.Parameter(torch.Tensor(in_feats))
-        else:
-            self.register_parameter("bias", None)
+        self._in_feats, self._project_initial_features = in_feats, project_initial_features
+        self.alpha, self.beta = alpha, math.log(lambda_ / layer + 1)
+        self._bias, self._activation, self._allow_zero_in_degree = bias, activation, allow_zero_in_degree
+        self.weight1 = nn.Parameter(torch.empty(in_feats, in_feats))
+        self.weight2 = None if project_initial_features else nn.Parameter(torch.empty(in_feats, in_feats))
+        self.bias = nn.Parameter(torch.empty(in_feats)) if bias else None
         self.reset_parameters()
 
     def reset_parameters(self):
         nn.init.normal_(self.weight1)
-        if not self._project_initial_features:
+        if self.weight2 is not None:
             nn.init.normal_(self.weight2)
-        if self._bias:
+        if self.bias is not None:
             nn.init.zeros_(self.bias)
 
     def set_allow_zero_in_degree(self, set_value):
         self._allow_zero_in_degree = set_value
 
+    def _identity_map(self, x, w):
+        return torch.addmm(x, x, w, beta=1 - self.beta, alpha=self.beta)   # (1 - beta) x + beta x W
+
     def forward(self, graph, feat, feat_0, edge_weight=None):
-        with graph.local_scope():
-            if not self._allow_zero_in_degree and bool((graph.in_degrees() == 0).any()):
-                raise DGLError("There are 0-in-degree nodes in the graph; add self-loops or set allow_zero_in_degree.")
-            if edge_weight is None:
-                degs = graph.in_degrees().to(feat).clamp(min=1)
-                norm = torch.pow(degs, -0.5).unsqueeze(-1)
-                feat = feat * norm
-                graph.ndata["h"] = feat
-                graph.update_all(fn.copy_u("h", "m"), fn.sum("m", "h"))
-                feat = graph.ndata.pop("h") * norm
-            else:
-                graph.ndata["h"] = feat
-                graph.edata["_w"] = edge_weight
-                graph.update_all(fn.u_mul_e("h", "_w", "m"), fn.sum("m", "h"))
-                feat = graph.ndata.pop("h")
-            if self._project_initial_features:
-                rst = (1 - self.alpha) * feat + self.alpha * feat_0
-                rst = torch.addmm(rst, rst, self.weight1, beta=(1 - self.beta), alpha=self.beta)
-            else:
-                rst = torch.addmm(feat, feat, self.weight1, beta=(1 - self.beta), alpha=self.beta * (1 - self.alpha))
-                rst = rst + torch.addmm(feat_0, feat_0, self.weight2, beta=(1 - self.beta), alpha=self.beta * self.alpha)
-            if self._bias:
-                rst = rst + self.bias
-            if self._activation is not None:
-                rst = self._activation(rst)
-            return rst
+        _mp.require_in_edges(graph, self._allow_zero_in_degree, "GCN2Conv")
+        coeff = _both_norm_or_weights(graph, feat.dtype, edge_weight)
+        smooth = (1 - self.alpha) * _mp.gather_sum(graph, feat, coeff)
+        init = self.alpha * feat_0[: smooth.shape[0]]
+        if self._project_initial_features:
+            out = self._identity_map(smooth + init, self.weight1)
+        else:
+            out = self._identity_map(smooth, self.weight1) + self._identity_map(init, self.weight2)
+        if self.bias is not None:
+            out = out + self.bias
+        return out if self._activation is None else self._activation(out)
+
+    def extra_repr(self):
+        s = f"in={self._in_feats}, alpha={self.alpha}, beta={self.beta}"
+        if self._activation is not None:
+            s += f", activation={self._activation}"
+        return s
 
 
+# =====================================================================================================================
+#  gated recurrences
+# =====================================================================================================================
 class GatedGraphConv(nn.Module):
-    r"""Gated graph conv with GRU update and per-etype linear maps (reference gatedgraphconv.py)."""
+    r"""GGNN: ``a_i = sum_j W_{e_ji} h_j``, ``h_i <- GRU(a_i, h_i)`` repeated ``n_steps`` times."""
 
     def __init__(self, in_feats, out_feats, n_steps, n_etypes, bias=True):
         super().__init__()
@@ -330,86 +264,68 @@ class GatedGraphConv(nn.Module):
     def reset_parameters(self):
         gain = nn.init.calculate_gain("relu")
         self.gru.reset_parameters()
-        for linear in self.linears:
-            nn.init.xavier_normal_(linear.weight, gain=gain)
-            nn.init.zeros_(linear.bias)
+        for lin in self.linears:
+            nn.init.xavier_normal_(lin.weight, gain=gain)
+            nn.init.zeros_(lin.bias)
 
     def set_allow_zero_in_degree(self, set_value):
-        """Kept for API parity: the GRU update of this layer is well defined for nodes without in-edges (their
-        aggregated message is zero), so nothing is checked either way (reference gatedgraphconv.py:98)."""
         self._allow_zero_in_degree = set_value
 
+    def _incoming(self, graph, h, etypes):
+        if self._n_etypes == 1 and etypes is None:
+            return _mp.gather_sum(graph, self.linears[0](h))
+        # one grouped GEMM for all edge types: message_e = W_{t(e)} h_src(e) + b_{t(e)}
+        W = torch.stack([lin.weight.t() for lin in self.linears])              # [T, in, out]
+        b = torch.stack([lin.bias for lin in self.linears])                    # [T, out]
+        t = etypes.long()
+        msg = ops.gather_mm(ops.copy_u(graph, h), W, idx_b=t) + b[t]
+        return _mp.edge_reduce(graph, msg, "sum")
+
     def forward(self, graph, feat, etypes=None):
-        with graph.local_scope():
-            assert graph.is_homogeneous, "not a homogeneous graph; convert it with to_homogeneous and pass in the edge type as argument"
-            if self._n_etypes != 1:
-                assert etypes.min() >= 0 and etypes.max() < self._n_etypes, "edge type indices out of range"
-            zero_pad = feat.new_zeros((feat.shape[0], self._out_feats - feat.shape[1]))
-            feat = torch.cat([feat, zero_pad], -1)
-            for _ in range(self._n_steps):
-                if self._n_etypes == 1 and etypes is None:
-                    graph.ndata["h"] = self.linears[0](feat)
-                    graph.update_all(fn.copy_u("h", "m"), fn.sum("m", "a"))
-                    a = graph.ndata.pop("a")
-                else:
-                    graph.ndata["h"] = feat
-                    a = 0
-                    for i in range(self._n_etypes):
-                        eids = torch.nonzero(etypes == i, as_tuple=False).view(-1).type(graph.idtype)
-                        if len(eids) > 0:
-                            sub = graph.edge_subgraph(eids, relabel_nodes=False)
-                            sub.ndata["hh"] = self.linears[i](feat)
-                            sub.update_all(fn.copy_u("hh", "m"), fn.sum("m", "a"))
-                            a = a + sub.ndata["a"]
-                feat = self.gru(a, feat)
-            return feat
+        if not graph.is_homogeneous:
+            raise DGLError("not a homograph; convert it with to_homogeneous and pass in the edge type as argument")
+        h = F.pad(feat, (0, self._out_feats - feat.shape[1]))
+        for _ in range(self._n_steps):
+            h = self.gru(self._incoming(graph, h, etypes), h)
+        return h
 
 
 class GatedGCNConv(nn.Module):
-    r"""Gated GCN (Bresson & Laurent) with edge features (reference gatedgcnconv.py)."""
+    r"""Residual gated GCN (Bresson & Laurent): edge gates ``sigma(D h_u + E h_v + C e)`` weight the ``B h_u`` messages."""
 
     def __init__(self, input_feats, edge_feats, output_feats, dropout=0, batch_norm=True, residual=True,
                  activation=F.relu):
         super().__init__()
         self.dropout = nn.Dropout(dropout)
-        self.batch_norm = batch_norm
-        self.residual = residual
-        if input_feats != output_feats or edge_feats != output_feats:
-            self.residual = False
-        self.A = nn.Linear(input_feats, output_feats, bias=True)
-        self.B = nn.Linear(input_feats, output_feats, bias=True)
-        self.C = nn.Linear(edge_feats, output_feats, bias=True)
-        self.D = nn.Linear(input_feats, output_feats, bias=True)
-        self.E = nn.Linear(input_feats, output_feats, bias=True)
+        self.batch_norm, self.activation = batch_norm, activation
+        self.residual = residual and input_feats == output_feats
+        for name, width in (("A", input_feats), ("B", input_feats), ("C", edge_feats), ("D", input_feats), ("E", input_feats)):
+            setattr(self, name, nn.Linear(width, output_feats, bias=True))
         self.bn_node = nn.BatchNorm1d(output_feats)
         self.bn_edge = nn.BatchNorm1d(output_feats)
-        self.activation = activation
 
     def forward(self, graph, feat, edge_feat):
-        with graph.local_scope():
-            h_in, e_in = feat, edge_feat
-            graph.ndata["Ah"] = self.A(feat)
-            graph.ndata["Bh"] = self.B(feat)
-            graph.ndata["Dh"] = self.D(feat)
-            graph.ndata["Eh"] = self.E(feat)
-            graph.edata["Ce"] = self.C(edge_feat)
-            graph.apply_edges(fn.u_add_v("Dh", "Eh", "DEh"))
-            graph.edata["e"] = graph.edata["DEh"] + graph.edata["Ce"]
-            graph.edata["sigma"] = torch.sigmoid(graph.edata["e"])
-            graph.update_all(fn.u_mul_e("Bh", "sigma", "m"), fn.sum("m", "sum_sigma_h"))
-            graph.update_all(fn.copy_e("sigma", "m"), fn.sum("m", "sum_sigma"))
-            graph.ndata["h"] = graph.ndata["Ah"] + graph.ndata["sum_sigma_h"] / (graph.ndata["sum_sigma"] + 1e-6)
-            h, e = graph.ndata["h"], graph.edata["e"]
-            if self.batch_norm:
-                h, e = self.bn_node(h), self.bn_edge(e)
-            if self.activation:
-                h, e = self.activation(h), self.activation(e)
-            if self.residual:
-                h, e = h_in + h, e_in + e
-            return self.dropout(h), self.dropout(e)
+        h_in, e_in = feat, edge_feat
+        gate_logit = _mp.pair_op(graph, "add", self.D(feat), self.E(feat)) + self.C(edge_feat)
+        gate = torch.sigmoid(gate_logit)
+        num = _mp.gather_sum(graph, self.B(feat), gate)                         # sum_e gate * (B h)_u
+        den = _mp.edge_reduce(graph, gate, "sum")
+        h, e = self.A(feat) + num / (den + 1e-6), gate_logit
+        if self.batch_norm:
+            h, e = self.bn_node(h), self.bn_edge(e)
+        if self.activation is not None:
+            h, e = self.activation(h), self.activation(e)
+        if self.residual:
+            h, e = h_in + h, e_in + e
+        return self.dropout(h), self.dropout(e)
 
 
+# =====================================================================================================================
+#  edge-conditioned filters
+# =====================================================================================================================
 class ShiftedSoftplus(nn.Module):
+    r"""``softplus(x) - log(shift)``."""
+
     def __init__(self, beta=1, shift=2, threshold=20):
         super().__init__()
         self.shift = shift
@@ -420,7 +336,7 @@ class ShiftedSoftplus(nn.Module):
 
 
 class CFConv(nn.Module):
-    r"""SchNet continuous-filter convolution (reference cfconv.py)."""
+    r"""SchNet continuous-filter convolution: ``h_i' = f_out( sum_j f_node(h_j) * f_edge(e_ji) )``."""
 
     def __init__(self, node_in_feats, edge_in_feats, hidden_feats, out_feats):
         super().__init__()
@@ -430,89 +346,68 @@ class CFConv(nn.Module):
         self.project_out = nn.Sequential(nn.Linear(hidden_feats, out_feats), ShiftedSoftplus())
 
     def forward(self, g, node_feats, edge_feats):
-        with g.local_scope():
-            if isinstance(node_feats, tuple):
-                node_feats_src, _ = node_feats
-            else:
-                node_feats_src = node_feats
-            g.srcdata["hv"] = self.project_node(node_feats_src)
-            g.edata["he"] = self.project_edge(edge_feats)
-            g.update_all(fn.u_mul_e("hv", "he", "m"), fn.sum("m", "h"))
-            return self.project_out(g.dstdata["h"])
+        x_src, _ = _mp.src_dst(g, node_feats)
+        return self.project_out(_mp.gather_sum(g, self.project_node(x_src), self.project_edge(edge_feats)))
+
+
+def _residual_and_bias(module, in_dst, out_feats, residual, bias):
+    if not residual:
+        module.register_buffer("res_fc", None)
+    elif in_dst != out_feats:
+        module.res_fc = nn.Linear(in_dst, out_feats, bias=False)
+    else:
+        module.res_fc = nn.Identity()
+    if bias:
+        module.bias = nn.Parameter(torch.zeros(out_feats))
+    else:
+        module.register_buffer("bias", None)
 
 
 class NNConv(nn.Module):
-    r"""Edge-conditioned convolution (MPNN): W_e = f(e) (reference nnconv.py)."""
+    r"""Edge-conditioned convolution (MPNN): every edge owns a matrix ``Theta(e_ji)`` produced by ``edge_func``."""
 
     def __init__(self, in_feats, out_feats, edge_func, aggregator_type="mean", residual=False, bias=True):
         super().__init__()
-        self._in_src_feats, self._in_dst_feats = expand_as_pair(in_feats)
-        self._out_feats = out_feats
-        self.edge_func = edge_func
-        if aggregator_type not in ("sum", "mean", "max"):
-            raise KeyError("Aggregator type {} not recognized: ".format(aggregator_type))
-        self.reducer = getattr(fn, aggregator_type)
+        self._in_src_feats, self._in_dst_feats = (in_feats, in_feats) if isinstance(in_feats, int) else in_feats
+        self._out_feats, self.edge_func = out_feats, edge_func
+        if aggregator_type not in _REDUCERS:
+            raise KeyError(f"Aggregator type {aggregator_type} not recognized: ")
         self._aggre_type = aggregator_type
-        if residual:
-            if self._in_dst_feats != out_feats:
-                self.res_fc = nn.Linear(self._in_dst_feats, out_feats, bias=False)
-            else:
-                self.res_fc = nn.Identity()
-        else:
-            self.register_buffer("res_fc", None)
-        if bias:
-            self.bias = nn.Parameter(torch.Tensor(out_feats))
-        else:
-            self.register_buffer("bias", None)
+        _residual_and_bias(self, self._in_dst_feats, out_feats, residual, bias)
         self.reset_parameters()
 
     def reset_parameters(self):
-        gain = nn.init.calculate_gain("relu")
         if self.bias is not None:
             nn.init.zeros_(self.bias)
         if isinstance(self.res_fc, nn.Linear):
-            nn.init.xavier_normal_(self.res_fc.weight, gain=gain)
+            nn.init.xavier_normal_(self.res_fc.weight, gain=nn.init.calculate_gain("relu"))
 
     def forward(self, graph, feat, efeat):
-        with graph.local_scope():
-            feat_src, feat_dst = expand_as_pair(feat, graph)
-            graph.srcdata["h"] = feat_src.unsqueeze(-1)
-            graph.edata["w"] = self.edge_func(efeat).view(-1, self._in_src_feats, self._out_feats)
-            graph.update_all(fn.u_mul_e("h", "w", "m"), self.reducer("m", "neigh"))
-            rst = graph.dstdata["neigh"].sum(dim=1)
-            if self.res_fc is not None:
-                rst = rst + self.res_fc(feat_dst)
-            if self.bias is not None:
-                rst = rst + self.bias
-            return rst
+        x_src, x_dst = _mp.src_dst(graph, feat)
+        theta = self.edge_func(efeat).view(-1, self._in_src_feats, self._out_feats)
+        msg = torch.bmm(ops.copy_u(graph, x_src).unsqueeze(1), theta).squeeze(1)   # per-edge vector-matrix product
+        out = _mp.edge_reduce(graph, msg, self._aggre_type)
+        if self.res_fc is not None:
+            out = out + self.res_fc(x_dst)
+        return out if self.bias is None else out + self.bias
 
 
 class GMMConv(nn.Module):
-    r"""Gaussian mixture model convolution (MoNet) (reference gmmconv.py)."""
+    r"""MoNet: Gaussian mixture kernels on pseudo-coordinates weight per-kernel projections of the neighbours."""
 
     def __init__(self, in_feats, out_feats, dim, n_kernels, aggregator_type="sum", residual=False, bias=True,
                  allow_zero_in_degree=False):
         super().__init__()
-        self._in_src_feats, self._in_dst_feats = expand_as_pair(in_feats)
+        self._in_src_feats, self._in_dst_feats = (in_feats, in_feats) if isinstance(in_feats, int) else in_feats
         self._out_feats, self._dim, self._n_kernels = out_feats, dim, n_kernels
         self._allow_zero_in_degree = allow_zero_in_degree
-        if aggregator_type not in ("sum", "mean", "max"):
-            raise KeyError("Aggregator type {} not recognized.".format(aggregator_type))
-        self._reducer = getattr(fn, aggregator_type)
-        self.mu = nn.Parameter(torch.Tensor(n_kernels, dim))
-        self.inv_sigma = nn.Parameter(torch.Tensor(n_kernels, dim))
+        if aggregator_type not in _REDUCERS:
+            raise KeyError(f"Aggregator type {aggregator_type} not recognized.")
+        self._reducer = aggregator_type
+        self.mu = nn.Parameter(torch.empty(n_kernels, dim))
+        self.inv_sigma = nn.Parameter(torch.empty(n_kernels, dim))
         self.fc = nn.Linear(self._in_src_feats, n_kernels * out_feats, bias=False)
-        if residual:
-            if self._in_dst_feats != out_feats:
-                self.res_fc = nn.Linear(self._in_dst_feats, out_feats, bias=False)
-            else:
-                self.res_fc = nn.Identity()
-        else:
-            self.register_buffer("res_fc", None)
-        if bias:
-            self.bias = nn.Parameter(torch.Tensor(out_feats))
-        else:
-            self.register_buffer("bias", None)
+        _residual_and_bias(self, self._in_dst_feats, out_feats, residual, bias)
         self.reset_parameters()
 
     def reset_parameters(self):
@@ -520,41 +415,35 @@ class GMMConv(nn.Module):
         nn.init.xavier_normal_(self.fc.weight, gain=gain)
         if isinstance(self.res_fc, nn.Linear):
             nn.init.xavier_normal_(self.res_fc.weight, gain=gain)
-        nn.init.normal_(self.mu.data, 0, 0.1)
-        nn.init.constant_(self.inv_sigma.data, 1)
+        nn.init.normal_(self.mu, 0, 0.1)
+        nn.init.constant_(self.inv_sigma, 1)
         if self.bias is not None:
-            nn.init.zeros_(self.bias.data)
+            nn.init.zeros_(self.bias)
 
     def set_allow_zero_in_degree(self, set_value):
         self._allow_zero_in_degree = set_value
 
     def forward(self, graph, feat, pseudo):
-        with graph.local_scope():
-            if not self._allow_zero_in_degree and bool((graph.in_degrees() == 0).any()):
-                raise DGLError("There are 0-in-degree nodes in the graph; add self-loops or set allow_zero_in_degree.")
-            feat_src, feat_dst = expand_as_pair(feat, graph)
-            graph.srcdata["h"] = self.fc(feat_src).view(-1, self._n_kernels, self._out_feats)
-            E = graph.num_edges()
-            gaussian = -0.5 * ((pseudo.view(E, 1, self._dim) - self.mu.view(1, self._n_kernels, self._dim)) ** 2)
-            gaussian = gaussian * (self.inv_sigma.view(1, self._n_kernels, self._dim) ** 2)
-            gaussian = torch.exp(gaussian.sum(dim=-1, keepdim=True))
-            graph.edata["w"] = gaussian
-            graph.update_all(fn.u_mul_e("h", "w", "m"), self._reducer("m", "h"))
-            rst = graph.dstdata["h"].sum(1)
-            if self.res_fc is not None:
-                rst = rst + self.res_fc(feat_dst)
-            if self.bias is not None:
-                rst = rst + self.bias
-            return rst
+        _mp.require_in_edges(graph, self._allow_zero_in_degree, "GMMConv")
+        x_src, x_dst = _mp.src_dst(graph, feat)
+        proj = self.fc(x_src).view(-1, self._n_kernels, self._out_feats)
+        z = (pseudo.unsqueeze(1) - self.mu.unsqueeze(0)) * self.inv_sigma.unsqueeze(0)       # [E, K, dim]
+        kernel_w = torch.exp(-0.5 * z.square().sum(-1))                                       # [E, K]
+        out = _mp.gather(graph, proj, self._reducer, kernel_w.unsqueeze(-1)).sum(1)
+        if self.res_fc is not None:
+            out = out + self.res_fc(x_dst)
+        return out if self.bias is None else out + self.bias
 
 
 class EdgeConv(nn.Module):
-    r"""DGCNN EdgeConv: h_i' = max_j (Theta (h_j - h_i) + Phi h_i) (reference edgeconv.py)."""
+    r"""DGCNN edge convolution ``h_i' = max_j [ Theta (h_i - h_j) + Phi h_i ]`` over the in-edges j -> i.
+
+    ``Theta`` is applied to the NODES: without batch norm the layer needs no per-edge tensor at all,
+    ``max_j [(Theta h)_i - (Theta h)_j] = (Theta h)_i - min_j (Theta h)_j``."""
 
     def __init__(self, in_feat, out_feat, batch_norm=False, allow_zero_in_degree=False):
         super().__init__()
-        self.batch_norm = batch_norm
-        self._allow_zero_in_degree = allow_zero_in_degree
+        self.batch_norm, self._allow_zero_in_degree = batch_norm, allow_zero_in_degree
         self.theta = nn.Linear(in_feat, out_feat)
         self.phi = nn.Linear(in_feat, out_feat)
         if batch_norm:
@@ -564,26 +453,19 @@ class EdgeConv(nn.Module):
         self._allow_zero_in_degree = set_value
 
     def forward(self, g, feat):
-        with g.local_scope():
-            if not self._allow_zero_in_degree and bool((g.in_degrees() == 0).any()):
-                raise DGLError("There are 0-in-degree nodes in the graph; add self-loops or set allow_zero_in_degree.")
-            h_src, h_dst = expand_as_pair(feat, g)
-            g.srcdata["x"] = h_src
-            g.dstdata["x"] = h_dst
-            g.apply_edges(fn.v_sub_u("x", "x", "theta"))
-            g.edata["theta"] = self.theta(g.edata["theta"])
-            g.dstdata["phi"] = self.phi(g.dstdata["x"])
-            if not self.batch_norm:
-                g.update_all(fn.e_add_v("theta", "phi", "e"), fn.max("e", "x"))
-            else:
-                g.apply_edges(fn.e_add_v("theta", "phi", "e"))
-                g.edata["e"] = self.bn(g.edata["e"])
-                g.update_all(fn.copy_e("e", "e"), fn.max("e", "x"))
-            return g.dstdata["x"]
+        _mp.require_in_edges(g, self._allow_zero_in_degree, "EdgeConv")
+        x_src, x_dst = _mp.src_dst(g, feat)
+        t_src = F.linear(x_src, self.theta.weight)                       # (Theta h)_j, bias cancels in the difference
+        centre = F.linear(x_dst, self.theta.weight) + self.theta.bias + self.phi(x_dst)
+        if not self.batch_norm:
+            has_nbr = (g.in_degrees() > 0).to(centre.dtype).unsqueeze(-1)  # the max over an empty set is 0
+            return (centre - _mp.gather_min(g, t_src)) * has_nbr
+        e = ops.gsddmm(g, "sub", centre, t_src, "v", "u")
+        return _mp.edge_reduce(g, self.bn(e), "max")
 
 
 class EGNNConv(nn.Module):
-    r"""E(n)-equivariant GNN layer (reference egnnconv.py)."""
+    r"""E(n)-equivariant layer: messages from (h_i, h_j, ||x_i - x_j||^2, e_ij); coordinates move along x_i - x_j."""
 
     def __init__(self, in_size, hidden_size, out_size, edge_feat_size=0):
         super().__init__()
@@ -595,88 +477,65 @@ class EGNNConv(nn.Module):
                                       nn.Linear(hidden_size, out_size))
         self.coord_mlp = nn.Sequential(nn.Linear(hidden_size, hidden_size), act_fn, nn.Linear(hidden_size, 1, bias=False))
 
-    def message(self, edges):
+    def _first_edge_layer(self, graph, h, radial, edge_feat):
+        """edge_mlp[0]([h_u | h_v | radial | e]) with the endpoint blocks of the weight applied per NODE."""
+        lin, d = self.edge_mlp[0], self.in_size
+        W = lin.weight
+        z = _mp.pair_op(graph, "add", F.linear(h, W[:, :d]), F.linear(h, W[:, d:2 * d]))
+        z = z + radial * W[:, 2 * d].unsqueeze(0) + lin.bias
         if self.edge_feat_size > 0:
-            f = torch.cat([edges.src["h"], edges.dst["h"], edges.data["radial"], edges.data["a"]], dim=-1)
-        else:
-            f = torch.cat([edges.src["h"], edges.dst["h"], edges.data["radial"]], dim=-1)
-        msg_h = self.edge_mlp(f)
-        msg_x = self.coord_mlp(msg_h) * edges.data["x_diff"]
-        return {"msg_x": msg_x, "msg_h": msg_h}
+            z = z + F.linear(edge_feat, W[:, 2 * d + 1:])
+        return z
 
     def forward(self, graph, node_feat, coord_feat, edge_feat=None):
-        with graph.local_scope():
-            graph.ndata["h"] = node_feat
-            graph.ndata["x"] = coord_feat
-            if self.edge_feat_size > 0:
-                assert edge_feat is not None, "Edge features must be provided."
-                graph.edata["a"] = edge_feat
-            graph.apply_edges(fn.u_sub_v("x", "x", "x_diff"))
-            graph.edata["radial"] = graph.edata["x_diff"].square().sum(dim=1).unsqueeze(-1)
-            graph.edata["x_diff"] = graph.edata["x_diff"] / (graph.edata["radial"].sqrt() + 1e-30)
-            graph.apply_edges(self.message)
-            graph.update_all(fn.copy_e("msg_x", "m"), fn.mean("m", "x_neigh"))
-            graph.update_all(fn.copy_e("msg_h", "m"), fn.sum("m", "h_neigh"))
-            h_neigh, x_neigh = graph.ndata["h_neigh"], graph.ndata["x_neigh"]
-            h = self.node_mlp(torch.cat([node_feat, h_neigh], dim=-1))
-            x = coord_feat + x_neigh
-            return h, x
+        if self.edge_feat_size > 0 and edge_feat is None:
+            raise AssertionError("Edge features must be provided.")
+        diff = _mp.pair_op(graph, "sub", coord_feat, coord_feat)                       # x_u - x_v
+        radial = diff.square().sum(dim=1, keepdim=True)
+        direction = diff / (radial.sqrt() + 1e-30)
+        msg_h = self.edge_mlp[1:](self._first_edge_layer(graph, node_feat, radial, edge_feat))
+        msg_x = self.coord_mlp(msg_h) * direction
+        h = self.node_mlp(torch.cat([node_feat, _mp.edge_reduce(graph, msg_h, "sum")], dim=-1))
+        return h, coord_feat + _mp.edge_reduce(graph, msg_x, "mean")
 
 
+# =====================================================================================================================
+#  TWIRLS
+# =====================================================================================================================
 class TWIRLSConv(nn.Module):
-    r"""Together-with-IRLS unfolding layer (reference twirlsconv.py), simplified to the propagation +
-    optional attention reweighting steps: Y <- (1-alpha*...) iterations of normalised propagation."""
+    r"""TWIRLS (graph networks from unfolded iteratively-reweighted least squares): MLP -> ``prop_step`` unfolded
+    energy-descent steps with an optional IRLS attention re-weighting half-way -> MLP."""
 
     def __init__(self, input_d, output_d, hidden_d, prop_step, num_mlp_before=1, num_mlp_after=1, norm="none",
                  precond=True, alp=0, lam=1, attention=False, tau=0.2, T=-1, p=1, use_eta=False, attn_bef=False,
                  dropout=0.0, attn_dropout=0.0, inp_dropout=0.0):
         super().__init__()
-        self.input_d, self.output_d, self.hidden_d = input_d, output_d, hidden_d
-        self.prop_step, self.lam, self.precond = prop_step, lam, precond
-        self.alp = alp if alp > 0 else 1.0 / (lam + 1)
-        self.attention, self.tau, self.T, self.p = attention, tau, T, p
-        self.attn_step = prop_step // 2 if attention else -1
-
-        def mlp(i, o, n):
-            if n == 0:
-                return nn.Identity()
-            layers = []
-            d = i
-            for k in range(n):
-                od = o if k == n - 1 else hidden_d
-                layers.append(nn.Linear(d, od))
-                if k != n - 1:
-                    layers += [nn.ReLU(), nn.Dropout(dropout)]
-                d = od
-            return nn.Sequential(*layers)
-
-        self.size_bef = hidden_d if num_mlp_after > 0 else output_d
-        self.mlp_bef = mlp(input_d, self.size_bef, num_mlp_before)
-        self.mlp_aft = mlp(self.size_bef if num_mlp_before > 0 else input_d, output_d, num_mlp_after)
-        self.inp_dropout = nn.Dropout(inp_dropout)
-        self.attn_dropout = nn.Dropout(attn_dropout)
+        self.input_d, self.output_d, self.hidden_d, self.prop_step = input_d, output_d, hidden_d, prop_step
+        self.num_mlp_before, self.num_mlp_after, self.norm, self.precond = num_mlp_before, num_mlp_after, norm, precond
+        self.attention, self.alp, self.lam, self.tau, self.T, self.p = attention, alp, lam, tau, T, p
+        self.use_eta, self.init_att = use_eta, attn_bef
+        self.dropout, self.attn_dropout, self.inp_dropout = dropout, attn_dropout, inp_dropout
+        self.attn_aft = prop_step // 2 if attention else -1
+        # without learned pre-processing and attention the unfolding depends on the input only: compute it once
+        self.cacheable = (not attention) and num_mlp_before == 0 and inp_dropout <= 0
+        if self.cacheable:
+            self.cached_unfolding = None
+        width_in = input_d if num_mlp_before == 0 else hidden_d       # what mlp_aft receives
+        width_mid = output_d if num_mlp_after == 0 else hidden_d      # what mlp_bef emits
+        self.size_bef_unf, self.size_aft_unf = width_mid, width_in
+        self.mlp_bef = MLP(input_d, hidden_d, width_mid, num_mlp_before, dropout, norm, init_activate=False)
+        self.unfolding = TWIRLSUnfoldingAndAttention(hidden_d, alp, lam, prop_step, self.attn_aft, tau, T, p, use_eta,
+                                                     attn_bef, attn_dropout, precond)
+        self.mlp_aft = MLP(width_in, hidden_d, output_d, num_mlp_after, dropout, norm,
+                           init_activate=num_mlp_before > 0 and num_mlp_after > 0)
 
     def forward(self, graph, feat):
-        with graph.local_scope():
-            x = self.mlp_bef(self.inp_dropout(feat))
-            deg = graph.in_degrees().to(x).clamp(min=1).unsqueeze(-1)
-            Y = x
-            w = torch.ones(graph.num_edges(), 1, device=x.device, dtype=x.dtype)
-            for k in range(self.prop_step):
-                if k == self.attn_step:
-                    graph.ndata["_y"] = Y
-                    graph.apply_edges(fn.u_sub_v("_y", "_y", "_d"))
-                    d2 = graph.edata["_d"].square().sum(-1, keepdim=True)
-                    w = (d2.clamp(min=self.tau ** 2)) ** (self.p / 2 - 1)
-                    if self.T > 0:
-                        w = torch.where(d2 > self.T ** 2, torch.zeros_like(w), w)
-                    w = self.attn_dropout(w)
-                graph.ndata["_y"] = Y / torch.sqrt(deg) if not self.precond else Y
-                graph.edata["_w"] = w
-                graph.update_all(fn.u_mul_e("_y", "_w", "m"), fn.sum("m", "_ay"))
-                AY = graph.ndata["_ay"]
-                if self.precond:
-                    Y = (1 - self.alp) * Y + self.alp * self.lam * AY / (self.lam * deg + 1) + self.alp * x / (self.lam * deg + 1)
-                else:
-                    Y = (1 - self.alp) * Y + self.alp * self.lam * AY / torch.sqrt(deg) + self.alp * x
-            return self.mlp_aft(Y)
+        graph = graph.remove_self_loop().add_self_loop()
+        if self.cacheable:
+            if self.cached_unfolding is None:
+                self.cached_unfolding = self.unfolding(graph, feat)
+            mid = self.cached_unfolding
+        else:
+            x = F.dropout(feat, self.inp_dropout, training=self.training) if self.inp_dropout > 0 else feat
+            mid = self.unfolding(graph, self.mlp_bef(x))
+        return self.mlp_aft(mid)

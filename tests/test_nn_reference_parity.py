@@ -72,11 +72,11 @@ def run_pair(ours, ref, og, rg, *inputs, extra_o=(), extra_r=(), tol=2e-4, kwarg
     for a, b in zip(xo, xr):
         if torch.is_tensor(a) and a.requires_grad and a.grad is not None:
             close(a.grad, b.grad, tol * 5)
-    for (n1, p1), (n2, p2) in zip(ours.named_parameters(), ref.named_parameters()):
-        assert n1 == n2
+    mine = dict(ours.named_parameters())
+    for name, p2 in ref.named_parameters():
         if p2.grad is not None:
-            assert p1.grad is not None, n1
-            close(p1.grad, p2.grad, tol * 5)
+            assert mine[name].grad is not None, name
+            close(mine[name].grad, p2.grad, tol * 5)
 
 
 X = torch.randn(N, 12, generator=torch.Generator().manual_seed(7))
@@ -195,7 +195,8 @@ def test_twirls_and_dense():
     A[v, u] = 1.0
     for name, args in (("DenseGraphConv", (12, 8)), ("DenseSAGEConv", (12, 8)), ("DenseChebConv", (12, 8, 3))):
         ours, ref = build(name, *args)
-        close(ours(A, X), ref(A, X))
+        extra = (2.0,) if name == "DenseChebConv" else ()   # the reference's default calls the removed torch.eig
+        close(ours(A, X, *extra), ref(A, X, *extra))
 
 
 def test_relgraphconv_and_typed_linear():
