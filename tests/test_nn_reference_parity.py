@@ -275,3 +275,59 @@ def test_readout_and_utils():
     close(ours(X, X.flip(0), rels), ref(X, X.flip(0), rels))
     ours, ref = build("TransR", 3, 5, 12)
     close(ours(X, X.flip(0), rels), ref(X, X.flip(0), rels))
+
+
+def test_graph_transformer_blocks():
+    import dgl.nn.pytorch.gt as rgt
+    import dgl_b200.nn.gt as ogt
+    g = torch.Generator().manual_seed(0)
+    B, n, d, H = 2, 6, 16, 4
+    x = torch.randn(B, n, d, generator=g)
+    bias = torch.randn(B, n, n, H, generator=g)
+    mask = torch.zeros(B, n, n, dtype=torch.bool)
+    mask[1, :, 4:] = True
+
+    def pair(name, *a, **kw):
+        torch.manual_seed(0)
+        ref = getattr(rgt, name)(*a, **kw)
+        ours = getattr(ogt, name)(*a, **kw)
+        ours.load_state_dict(ref.state_dict(), strict=True)
+        return ours.eval(), ref.eval()
+
+    for btype in ("add", "mul"):
+        ours, ref = pair("BiasedMHA", d, H, attn_bias_type=btype, attn_drop=0.0)
+        close(ours(x, bias, mask), ref(x, bias, mask))
+    for norm_first in (False, True):
+        ours, ref = pair("GraphormerLayer", d, 32, H, norm_first=norm_first, dropout=0.0, attn_dropout=0.0)
+        close(ours(x, bias, mask), ref(x, bias, mask))
+    e = torch.randn(B, n, n, 8, generator=g)
+    ours, ref = pair("EGTLayer", d, 8, H, 1)
+    close(ours(x, e), ref(x, e))
+    fmask = torch.zeros(B, n, n)
+    fmask[1, :, 5:] = -1e9
+    close(ours(x, e, fmask), ref(x, e, fmask))
+    ours, ref = pair("EGTLayer", d, 8, H, 0, edge_update=False)
+    close(ours(x, e), ref(x, e))
+    deg = torch.randint(0, 9, (2, B, n), generator=g)
+    ours, ref = pair("DegreeEncoder", 5, d, "both")
+    close(ours(deg), ref(deg))
+    ours, ref = pair("DegreeEncoder", 5, d, "in")
+    close(ours(deg[0]), ref(deg[0]))
+    dist = torch.randint(-1, 6, (B, n, n), generator=g)
+    ours, ref = pair("SpatialEncoder", 4, H)
+    close(ours(dist), ref(dist))
+    path = torch.randn(B, n, n, 3, 5, generator=g)
+    ours, ref = pair("PathEncoder", 3, 5, H)
+    close(ours(dist, path), ref(dist, path))
+    coord = torch.randn(B, n, 3, generator=g)
+    ntype = torch.randint(0, 3, (B, n), generator=g)
+    ours, ref = pair("SpatialEncoder3d", 4, H, 3)
+    close(ours(coord), ref(coord))
+    close(ours(coord, ntype), ref(coord, ntype))
+    ev = torch.randn(n, 5, generator=g)
+    ea = torch.rand(n, 5, generator=g)
+    ev[:, 4] = float("nan")
+    ea[:, 4] = float("nan")
+    for model, kw in (("Transformer", {"n_head": 2}), ("DeepSet", {"num_post_layer": 2}), ("DeepSet", {"batch_norm": True})):
+        ours, ref = pair("LapPosEncoder", model, 3 if model == "DeepSet" else 1, 5, 8, **kw)
+        close(ours(ea.clone(), ev.clone()), ref(ea.clone(), ev.clone()), 1e-3)
