@@ -199,17 +199,37 @@ class FusedSAGETrainer:
             off += _pad8(n)
         self.numel = off
         self.segs = segs
-        self.param = torch.zeros(off, dtype=torch.float32, device=dev)
-        self.adam_m = torch.zeros_like(self.param)
-        self.adam_v = torch.zeros_like(self.param)
-        self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=dev)
         # fp32 tensor-core operands: hi / lo planes of the TF32 split, refreshed by the optimizer epilogue
         split = self.use_tc and self.dtype == torch.float32
-        self.shadow_hi = torch.zeros(off, dtype=torch.float32, device=dev) if split else None
-        self.shadow_lo = torch.zeros(off, dtype=torch.float32, device=dev) if split else None
-        # flat gradient + 8 trailing words (loss, accuracy counter): one memset per step clears all of it
-        self.zero_block = (torch.zeros(off + 8, dtype=torch.float32, device=dev) if self.comm is None
-                           else self.comm.grad_buffer(off + 8))
+        self._nvls = None
+        if self.comm is not None and getattr(self.comm, "nvls", False):
+            # NVLS: gradients, parameters and their operand copies live in ONE multicast-mapped symmetric allocation:
+            # the optimizer kernel reduces gradients in the switch (multimem.ld_reduce) and multicasts the update
+            pad = lambda nbytes: (nbytes + 255) // 256 * 256  # noqa: E731
+            o_grad, o_param = 0, pad(4 * (off + 8))
+            o_sh = o_param + pad(4 * off)
+            o_hi = o_sh + pad(2 * off)
+            o_lo = o_hi + (pad(4 * off) if split else 0)
+            total = o_lo + (pad(4 * off) if split else 0)
+            buf = self.comm.heap.alloc(total)
+            if buf.mc_ptr:
+                self._nvls = dict(buf=buf, grad=buf.mc_ptr + o_grad, param=buf.mc_ptr + o_param, shadow=buf.mc_ptr + o_sh,
+                                  hi=buf.mc_ptr + o_hi if split else 0, lo=buf.mc_ptr + o_lo if split else 0)
+                self.zero_block = buf.view(torch.float32, o_grad, off + 8)
+                self.param = buf.view(torch.float32, o_param, off)
+                self.shadow = buf.view(torch.bfloat16, o_sh, off)
+                self.shadow_hi = buf.view(torch.float32, o_hi, off) if split else None
+                self.shadow_lo = buf.view(torch.float32, o_lo, off) if split else None
+        if self._nvls is None:
+            self.param = torch.zeros(off, dtype=torch.float32, device=dev)
+            self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=dev)
+            self.shadow_hi = torch.zeros(off, dtype=torch.float32, device=dev) if split else None
+            self.shadow_lo = torch.zeros(off, dtype=torch.float32, device=dev) if split else None
+            # flat gradient + 8 trailing words (loss, accuracy counter): one memset per step clears all of it
+            self.zero_block = (torch.zeros(off + 8, dtype=torch.float32, device=dev) if self.comm is None
+                               else self.comm.grad_buffer(off + 8))
+        self.adam_m = torch.zeros_like(self.param)
+        self.adam_v = torch.zeros_like(self.param)
         self.grad = self.zero_block[:off]
         self.loss_dev = self.zero_block[off:off + 1]
         self.correct_dev = self.zero_block[off + 1:off + 2].view(torch.int32)
@@ -598,6 +618,22 @@ class FusedSAGETrainer:
 
     def _finish_step(self):
         # ---------------- gradient all-reduce fused with Adam
+        if self._nvls is not None:
+            # NVLS two-shot: in-switch reduction of this rank's slice, Adam on the slice, multicast of the new values
+            nv = self._nvls
+            self.comm.nvls_barrier(0)   # every rank's gradients are complete and visible
+            self._launch("dglb200_symm_allreduce_adam", "pppppppp" + "lii" + "fffff" + "p", nv["grad"], nv["param"],
+                         _p(self.param), _p(self.adam_m), _p(self.adam_v),
+                         nv["shadow"] if self.dtype == torch.bfloat16 else 0, nv["hi"], nv["lo"], self.numel, self.world,
+                         self.rank, float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps),
+                         float(self.wd), _p(self.step_dev), kernels=2)
+            self.comm.nvls_barrier(1)   # every slice has landed everywhere before the next forward reads the weights
+            self._launch_count += 2
+            self._my_kernels += 2
+            self.loss_pinned.copy_(self.loss_dev, non_blocking=True)
+            self.gpu_launches_per_step = self._my_kernels
+            self.total_launches_per_step = self._launch_count
+            return
         if self.comm is not None:
             self.comm.barrier(0)  # every rank's gradients are complete and visible
             self._launch_count += 1

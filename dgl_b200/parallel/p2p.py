@@ -103,8 +103,35 @@ class P2PComm:
         self._error = torch.zeros(1, dtype=torch.int32, device=self.device)
         self._grad = None
         self._bufs = []
+        # NVLS path (VMM symmetric heap + multicast, parallel/symm.py): in-switch reduction for the gradient all-reduce,
+        # multicast stores for the parameter broadcast, one-round-trip barrier. DGLB200_NVLS=0 keeps the CUDA-IPC path.
+        self.heap = None
         if self.world_size > 1:
+            import os as _os
+            if _os.environ.get("DGLB200_NVLS", "1") != "0":
+                try:
+                    from .symm import SymmetricHeap
+                    heap = SymmetricHeap(group=self.group, device=self.device)
+                    if heap.vmm_ok and heap.mc_ok:
+                        flags = heap.alloc(256)
+                        if flags.mc_ptr:
+                            self.heap, self._mc_flags = heap, flags
+                            self._mc_epoch = torch.zeros(8, dtype=torch.int64, device=self.device)
+                except Exception as e:  # noqa: BLE001 - any bootstrap problem: stay on the IPC path
+                    self.heap, self._nvls_error = None, str(e)
             dist.barrier(group=self.group)
+
+    @property
+    def nvls(self):
+        """True when gradient / parameter buffers can live in multicast-mapped symmetric memory."""
+        return self.heap is not None
+
+    def nvls_barrier(self, channel=0):
+        """Barrier through the multicast counter: one ``multimem.red`` per rank + local spinning (graph-capturable)."""
+        self.lib.fn("dglb200_symm_barrier", "pppipdp")(
+            self._mc_flags.mc_ptr + 4 * channel, self._mc_flags.local_ptr + 4 * channel,
+            self._mc_epoch.data_ptr() + 8 * channel, self.world_size, self._error.data_ptr(), self.timeout_s,
+            loader.stream_ptr())
 
     def close(self):
         """Collective teardown: every rank unmaps its peers' buffers, then (after a barrier) frees its own allocations.

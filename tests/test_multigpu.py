@@ -305,7 +305,98 @@ def _w_trainer_nccl_baseline(rank, world, comm):
     return True
 
 
+def _w_nvls(rank, world, comm):
+    """Multicast path (VMM symmetric heap + multimem): barrier, in-switch all-reduce fused with Adam, replicas identical.
+    Returns 'nvls' or 'unavailable: ...' so the log shows which path the box offers."""
+    import ctypes
+    import torch.distributed as dist
+    from dgl_b200._native import loader
+    dev = comm.device
+    if not comm.nvls:
+        return "unavailable: " + str(getattr(comm, "_nvls_error", getattr(getattr(comm, "heap", None), "_why", "no multicast support")))
+    lib = loader.cuda_lib()
+    numel = 10240 + 4
+    pad = lambda b: (b + 255) // 256 * 256  # noqa: E731
+    o_param, o_sh = pad(4 * numel), pad(4 * numel) * 2
+    buf = comm.heap.alloc(o_sh + pad(2 * numel))
+    assert buf.mc_ptr
+    grad, param = buf.view(torch.float32, 0, numel), buf.view(torch.float32, o_param, numel)
+    shadow = buf.view(torch.bfloat16, o_sh, numel)
+    g = torch.Generator().manual_seed(5)
+    init = torch.randn(numel, generator=g).to(dev)
+    param.copy_(init)
+    ref = torch.nn.Parameter(init.clone())
+    opt = torch.optim.Adam([ref], lr=1e-2, weight_decay=0.01)
+    m, v = torch.zeros(numel, device=dev), torch.zeros(numel, device=dev)
+    step = torch.zeros(1, dtype=torch.int64, device=dev)
+    for it in range(3):
+        gr = torch.Generator().manual_seed(100 * it + rank)
+        mine = torch.randn(numel, generator=gr).to(dev)
+        grad.copy_(mine)
+        comm.nvls_barrier(0)
+        lib.fn("dglb200_symm_allreduce_adam", "pppppppp" + "lii" + "fffff" + "pp")(
+            buf.mc_ptr, buf.mc_ptr + o_param, param.data_ptr(), m.data_ptr(), v.data_ptr(), buf.mc_ptr + o_sh, 0, 0, numel,
+            world, rank, 1e-2, 0.9, 0.999, 1e-8, 0.01, step.data_ptr(), loader.stream_ptr())
+        comm.nvls_barrier(1)
+        tot = mine.clone()
+        dist.all_reduce(tot)
+        ref.grad = tot / world
+        opt.step()
+        torch.cuda.synchronize()
+        assert torch.allclose(param, ref.detach(), atol=1e-5, rtol=1e-5), (it, (param - ref.detach()).abs().max())
+        assert torch.equal(shadow.float(), param.bfloat16().float())
+        other = param.clone()
+        dist.broadcast(other, 0)
+        assert torch.equal(other, param)            # one writer per element: replicas bit-identical
+    assert int(step.item()) == 3
+    return "nvls"
+
+
+def _w_trainer_tc(rank, world, comm):
+    """Data-parallel tcgen05 engine (bf16 and fp32) over the communicator (NVLS when available): replicas bit-identical,
+    parameters equal to the NCCL-baseline run."""
+    import dgl_b200 as dgl
+    import torch.distributed as dist
+    from dgl_b200.models import FusedSAGETrainer
+    dev = comm.device
+    gen = torch.Generator().manual_seed(3)
+    n = 12000
+    g = dgl.graph((torch.randint(0, n, (200000,), generator=gen).int(), torch.randint(0, n, (200000,), generator=gen).int()),
+                  num_nodes=n, idtype=torch.int32).to(dev)
+    feat = torch.randn(n, 64, generator=gen).to(dev)
+    labels = torch.randint(0, 7, (n,), generator=gen).to(dev)
+    out = {}
+    for dtype in (torch.bfloat16, torch.float32):
+        params = []
+        for c in (comm, "nccl"):
+            tr = FusedSAGETrainer(g, feat, labels, 7, hidden=128, fanouts=[5, 5], batch_size=256, lr=1e-2, dropout=0.0,
+                                  dtype=dtype, comm=c, seed=11, use_cuda_graph=(c is comm))
+            assert tr.use_tc
+            for step in range(6):
+                gs = torch.Generator().manual_seed(1000 + step * world + rank)
+                tr.train_step(torch.randint(0, n, (256,), generator=gs))
+            mine = tr.param.clone()
+            ref = mine.clone()
+            dist.broadcast(ref, 0)
+            assert torch.equal(mine, ref), (dtype, (mine - ref).abs().max())
+            params.append(mine)
+        assert torch.allclose(params[0], params[1], atol=2e-3), (dtype, (params[0] - params[1]).abs().max())
+        out[str(dtype)] = "nvls" if tr is not None and comm.nvls else "ipc"
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- tests
+def test_nvls_multicast_allreduce_adam():
+    res = _run(_w_nvls)
+    print("NVLS status:", res)
+    assert len(set(res.values())) == 1
+
+
+def test_trainer_tc_data_parallel():
+    res = _run(_w_trainer_tc)
+    print("trainer comm path:", res)
+
+
 def test_trainer_nccl_baseline_matches_p2p():
     _run(_w_trainer_nccl_baseline)
 
