@@ -32,6 +32,11 @@ def coo_to_csr(row, col, num_rows, idtype):
     if E > 1 and bool((row[1:] >= row[:-1]).all()):
         perm = None
         srow, scol = row, col
+    elif row.is_cuda and row.dtype == idtype and E < 2 ** 31:
+        # native build: stable radix sort on the row bits with the edge-id permutation + binary-search row bounds
+        # (csrc/cuda/structure_build.cu) - no torch.sort, one pass over the edge list per radix digit
+        from .ops.cuda_struct import cuda_coo_to_csr
+        return cuda_coo_to_csr(row.contiguous(), col, num_rows)
     else:
         perm = _stable_argsort(row)
         srow, scol = row[perm], col[perm]

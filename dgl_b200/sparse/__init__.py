@@ -378,6 +378,15 @@ def spspmm(A, B):
         # host matrices: native two-pass Gustavson SpGEMM with a masked row-dot backward (csrc/cpu/structure.cc)
         cp, ci, cv = _cpu_struct.spspmm(A, B)
         return from_csr(cp, ci, cv, (A.shape[0], B.shape[1]))
+    if A.val.is_cuda and A.val.dim() == 1 and B.val.dim() == 1 and not (A.val.requires_grad or B.val.requires_grad):
+        # device matrices: hash-table SpGEMM of this framework (csrc/cuda/structure_build.cu), no cuSPARSE
+        from ..ops.cuda_struct import cuda_spgemm
+        ap, ai, ae = A.csr()
+        bp, bi, be = B.csr()
+        av = A.val if ae is None else A.val[ae.long()]
+        bv = B.val if be is None else B.val[be.long()]
+        r, c, v = cuda_spgemm(ap, ai, av, bp, bi, bv, A.shape[0], B.shape[1])
+        return from_coo(r, c, v.to(A.val.dtype), (A.shape[0], B.shape[1]))
     ta, tb = to_torch_sparse_coo(A), to_torch_sparse_coo(B)
     tc = torch.sparse.mm(ta, tb).coalesce()
     idx = tc.indices()

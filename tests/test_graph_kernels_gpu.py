@@ -173,3 +173,73 @@ def test_cooperative_rank_sort_native():
     s_c, p_c, o_c = rank_sort(ids, 0, 8, seed=3)
     s_g, p_g, o_g = rank_sort(ids.to(DEV), 0, 8, seed=3)
     assert torch.equal(s_g.cpu(), s_c) and torch.equal(p_g.cpu(), p_c) and torch.equal(o_g.cpu(), o_c)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# structure construction kernels (csrc/cuda/structure_build.cu)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("idtype", [torch.int32, torch.int64])
+@pytest.mark.parametrize("n,m", [(1, 5), (1000, 50000), (70000, 2000000)])
+def test_native_coo_to_csr_and_transpose(idtype, n, m):
+    from dgl_b200.ops.cuda_struct import cuda_coo_to_csr, cuda_csr_transpose
+    g = torch.Generator().manual_seed(n + m)
+    row = torch.randint(0, n, (m,), generator=g).to(idtype).cuda()
+    col = torch.randint(0, n + 3, (m,), generator=g).to(idtype).cuda()
+    indptr, indices, eids = cuda_coo_to_csr(row, col, n)
+    torch.cuda.synchronize()
+    # reference: stable sort by row
+    perm = torch.sort(row.long(), stable=True)[1]
+    assert torch.equal(eids.long(), perm)
+    assert torch.equal(indices, col[perm])
+    counts = torch.bincount(row.long(), minlength=n)
+    assert torch.equal(indptr.long(), torch.cat([counts.new_zeros(1), counts.cumsum(0)]))
+    tp, ti, te = cuda_csr_transpose(indptr, indices, n, n + 3)
+    torch.cuda.synchronize()
+    srow = row[perm]
+    perm2 = torch.sort(indices.long(), stable=True)[1]
+    assert torch.equal(te.long(), perm2) and torch.equal(ti, srow[perm2])
+    c2 = torch.bincount(indices.long(), minlength=n + 3)
+    assert torch.equal(tp.long(), torch.cat([c2.new_zeros(1), c2.cumsum(0)]))
+
+
+def test_native_coalesce_and_graph_formats():
+    from dgl_b200.ops.cuda_struct import cuda_coalesce
+    g = torch.Generator().manual_seed(0)
+    n, m = 500, 40000
+    row = torch.randint(0, n, (m,), generator=g).int().cuda()
+    col = torch.randint(0, 60, (m,), generator=g).int().cuda()
+    val = torch.randn(m, 3, generator=g).cuda()
+    r, c, v, first = cuda_coalesce(row, col, val, n, 60, want_first=True)
+    dense = torch.zeros(n, 60, 3, device="cuda").index_put_((row.long(), col.long()), val, accumulate=True)
+    key = r.long() * 60 + c.long()
+    assert bool((key[1:] > key[:-1]).all())                                  # sorted, distinct
+    assert torch.allclose(dense[r.long(), c.long()], v, atol=1e-4)
+    assert int((dense.abs().sum(-1) > 0).sum()) <= r.shape[0]
+    assert torch.equal(row[first], r) and torch.equal(col[first], c)
+    # the graph index builds its formats with the native kernels on CUDA
+    import dgl_b200 as dgl
+    u = torch.randint(0, 3000, (100000,), generator=g)
+    w = torch.randint(0, 3000, (100000,), generator=g)
+    gg = dgl.graph((u, w), num_nodes=3000).to("cuda").formats(["coo", "csr", "csc"])
+    gg.create_formats_()
+    gc = dgl.graph((u, w), num_nodes=3000)
+    assert torch.equal(gg.in_degrees().cpu(), gc.in_degrees()) and torch.equal(gg.out_degrees().cpu(), gc.out_degrees())
+    x = torch.randn(3000, 8, generator=g)
+    assert torch.allclose(dgl.ops.copy_u_sum(gg, x.cuda()).cpu(), dgl.ops.copy_u_sum(gc, x), atol=1e-4)
+
+
+@pytest.mark.parametrize("shape,nnz", [((300, 200, 250), 3000), ((5000, 4000, 3000), 60000), ((50, 50, 50), 2000)])
+def test_native_spgemm_matches_cpu_gustavson(shape, nnz):
+    import dgl_b200.sparse as dglsp
+    g = torch.Generator().manual_seed(nnz)
+    M, K, N = shape
+    ai = torch.stack([torch.randint(0, M, (nnz,), generator=g), torch.randint(0, K, (nnz,), generator=g)])
+    bi = torch.stack([torch.randint(0, K, (nnz,), generator=g), torch.randint(0, N, (nnz,), generator=g)])
+    av, bv = torch.randn(nnz, generator=g), torch.randn(nnz, generator=g)
+    A, B = dglsp.spmatrix(ai, av, (M, K)).coalesce(), dglsp.spmatrix(bi, bv, (K, N)).coalesce()
+    C_cpu = dglsp.spspmm(A, B)
+    Ag = dglsp.spmatrix(A.indices().cuda(), A.val.cuda(), (M, K))
+    Bg = dglsp.spmatrix(B.indices().cuda(), B.val.cuda(), (K, N))
+    C_gpu = dglsp.spspmm(Ag, Bg)
+    assert C_gpu.nnz == C_cpu.nnz
+    assert torch.allclose(C_gpu.to_dense().cpu(), C_cpu.to_dense(), atol=1e-3)
