@@ -5,7 +5,11 @@ Layer map: native kernels (csrc/cpu OpenMP, csrc/cuda sm_100a) -
 ``_sparse_ops`` dispatch -> ``ops`` autograd -> DGLGraph/``core`` message passing ->
 ``nn``/``optim`` -> ``sampling``/``dataloading``/``graphbolt`` -> ``parallel``/``distributed``.
 """
-from . import function  # noqa: F401
+from . import _pathshim as _pathshim
+
+_pathshim.install()   # reference module paths without a file of their own (see _alias_table.py)
+
+from . import function  # noqa: F401,E402
 from .base import ALL, EID, ETYPE, NID, NTYPE, DGLError, dgl_warning  # noqa: F401
 from .batch import batch, batch_hetero, slice_batch, unbatch, unbatch_hetero  # noqa: F401
 from .convert import (bipartite_from_networkx, bipartite_from_scipy, block_to_graph, create_block,  # noqa: F401

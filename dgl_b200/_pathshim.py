@@ -1,31 +1,72 @@
-"""Lazy re-export helper for reference module paths.
+"""Reference module paths without a file of their own.
 
-The reference spreads one package over many files (``dgl.graphbolt.dataloader``, ``dgl.optim.pytorch.sparse_optim``
-...); this package groups the same names differently. A shim module created with :func:`reexport` makes
-``from dgl_b200.<reference path> import Name`` work by resolving ``Name`` in the module(s) that define it here, on
-first access (module ``__getattr__``), so no import cycles and no eager loading are introduced."""
+The reference spreads one package over many small modules (``dgl.graphbolt.feature_fetcher``,
+``dgl.nn.pytorch.conv.gatconv``, ``dgl.optim.pytorch.sparse_optim`` ...); this package groups the same names differently.
+``from dgl_b200.<reference path> import Name`` keeps working through ONE import hook: :class:`AliasFinder` sits at the end
+of ``sys.meta_path`` (so real modules always win), recognises the paths listed in ``_alias_table.ALIASES`` and builds a
+module whose attributes resolve lazily (module ``__getattr__``) in the modules that actually define them - no stub files,
+no eager imports, no import cycles."""
 from __future__ import annotations
 
 import importlib
+import importlib.abc
+import importlib.machinery
+import sys
+
+_PKG = __name__.rsplit(".", 1)[0]
 
 
-def reexport(shim_name, sources, names):
-    """Return ``(__getattr__, __dir__, __all__)`` for the shim module ``shim_name``: ``names`` are looked up in each
-    module of ``sources`` (dotted paths) in order."""
-    names = list(names)
+def _table():
+    from ._alias_table import ALIASES, SOURCE_GROUPS
+    return ALIASES, SOURCE_GROUPS
 
-    def __getattr__(name):
-        if name.startswith("__"):
-            raise AttributeError(name)
-        for src in sources:
-            mod = importlib.import_module(src)
-            try:
-                return getattr(mod, name)
-            except AttributeError:
-                continue
-        raise AttributeError(f"module {shim_name!r} has no attribute {name!r}")
 
-    def __dir__():
-        return names
+class _AliasLoader(importlib.abc.Loader):
+    def __init__(self, sources, names):
+        self.sources, self.names = list(sources), list(names)
 
-    return __getattr__, __dir__, names
+    def create_module(self, spec):
+        return None
+
+    def exec_module(self, module):
+        sources, names, modname = self.sources, self.names, module.__name__
+
+        def __getattr__(name):
+            if name.startswith("__"):
+                raise AttributeError(name)
+            for src in sources:
+                try:
+                    return getattr(importlib.import_module(src), name)
+                except AttributeError:
+                    continue
+            raise AttributeError(f"module {modname!r} has no attribute {name!r}")
+
+        module.__getattr__ = __getattr__
+        module.__dir__ = lambda: list(names)
+        module.__all__ = list(names)
+        module.__doc__ = (f"Reference module path ``{modname.replace(_PKG, 'dgl', 1)}``: its names are implemented in "
+                          f"{', '.join(sources[:3])} ... and resolved lazily.")
+
+
+class AliasFinder(importlib.abc.MetaPathFinder):
+    """Resolves ``dgl_b200.<alias>`` for the aliases of ``_alias_table`` when no real module of that name exists."""
+
+    def find_spec(self, fullname, path=None, target=None):
+        if not fullname.startswith(_PKG + "."):
+            return None
+        aliases, groups = _table()
+        entry = aliases.get(fullname[len(_PKG) + 1:])
+        if entry is None:
+            return None
+        group, names = entry
+        return importlib.machinery.ModuleSpec(fullname, _AliasLoader(groups[group], names))
+
+
+def install():
+    if not any(isinstance(f, AliasFinder) for f in sys.meta_path):
+        sys.meta_path.append(AliasFinder())
+
+
+def alias_modules():
+    """Dotted names of every synthesised module (for tests and documentation)."""
+    return sorted(f"{_PKG}.{k}" for k in _table()[0])

@@ -1,5 +1,5 @@
-"""Every reference module path that has no same-named module here is a lazy re-export shim (tools/gen_path_shims.py);
-all of their names must resolve. Also covers the last batch of small helpers those shims point at."""
+"""Every reference module path that has no same-named module here is synthesised by the alias import hook
+(dgl_b200/_pathshim.py + _alias_table.py); all of their names must resolve. Also covers the last batch of small helpers those shims point at."""
 import importlib
 import os
 
@@ -15,11 +15,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _shims():
-    for dp, _, files in os.walk(os.path.join(ROOT, "dgl_b200")):
-        for f in files:
-            p = os.path.join(dp, f)
-            if f.endswith(".py") and "_pathshim import reexport" in open(p).read():
-                yield os.path.relpath(p, ROOT)[:-3].replace(os.sep, ".")
+    from dgl_b200 import _pathshim
+    yield from _pathshim.alias_modules()
 
 
 def test_every_shim_name_resolves():

@@ -1,4 +1,4 @@
-"""Generate shim modules for reference module paths that have no same-named module in dgl_b200.
+"""Generate the alias table (dgl_b200/_alias_table.py) for reference module paths that have no same-named module in dgl_b200.
 
 Usage: python tools/gen_path_shims.py /root/reference/python/dgl [--write]
 
@@ -36,6 +36,26 @@ def public_names(path):
     return sorted(n.name for n in tree.body if isinstance(n, (ast.FunctionDef, ast.ClassDef)) and not n.name.startswith("_"))
 
 
+def write_table(path, table):
+    """One generated module instead of one stub file per path: groups of source modules + {alias: (group, names)}."""
+    groups = {}
+    for mod, (sources, _) in table.items():
+        groups.setdefault(tuple(sources), []).append(mod)
+    gid = {s: f"g{i}" for i, (s, _) in enumerate(sorted(groups.items(), key=lambda kv: -len(kv[1])))}
+    with open(path, "w") as fh:
+        fh.write('"""Reference module paths that this package does not lay out as files: ``dgl_b200.<key>`` is synthesised on '
+                 'import by\n``_pathshim.AliasFinder`` and resolves each listed name lazily in the modules of its source group. '
+                 'Generated from the\nreference tree by tools/gen_path_shims.py (names only); checked by '
+                 'tests/test_reference_paths.py."""\n\nSOURCE_GROUPS = {\n')
+        for s, g in sorted(gid.items(), key=lambda kv: int(kv[1][1:])):
+            fh.write(f"    {g!r}: {list(s)!r},\n")
+        fh.write("}\n\nALIASES = {\n")
+        for mod in sorted(table):
+            sources, names = table[mod]
+            fh.write(f"    {mod!r}: ({gid[tuple(sources)]!r}, {names!r}),\n")
+        fh.write("}\n")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("reference_pkg")
@@ -46,6 +66,7 @@ def main():
     sys.path.insert(0, here)
     unresolved = {}
     written = []
+    table = {}
     for dp, _, files in os.walk(args.reference_pkg):
         for f in sorted(files):
             if not f.endswith(".py") or f == "__init__.py" or f.startswith("_"):
@@ -102,21 +123,18 @@ def main():
                 unresolved[rel] = ["<parent is a module>"]
                 continue
             if args.write:
-                for m in reversed(to_make):
+                for m in reversed(to_make):          # intermediate PACKAGES stay real directories
                     os.makedirs(m, exist_ok=True)
                     init = os.path.join(m, "__init__.py")
                     if not os.path.exists(init):
                         relpkg = os.path.relpath(m, os.path.join(here, "dgl_b200")).replace(os.sep, ".")
                         with open(init, "w") as fh:
-                            fh.write(f'"""Reference package path ``dgl.{relpkg}`` (contents are lazy re-exports)."""\n')
-                with open(target, "w") as fh:
-                    fh.write(f'"""Reference module path ``dgl.{dotted}``: the names below are implemented in\n'
-                             f'{", ".join(good_homes[:3])} ... and re-exported lazily."""\n'
-                             f"from {'.' * (dotted.count('.') + 1)}_pathshim import reexport\n\n"
-                             f"__getattr__, __dir__, __all__ = reexport(__name__, {good_homes!r},\n"
-                             f"                                          {names!r})\n")
+                            fh.write(f'"""Reference package path ``dgl.{relpkg}`` (modules are synthesised, see _pathshim)."""\n')
+            table[dotted] = (good_homes, names)
             written.append(rel)
-    print("shims:", len(written))
+    if args.write:
+        write_table(os.path.join(here, "dgl_b200", "_alias_table.py"), table)
+    print("aliases:", len(written))
     for r in written:
         print("  ", r)
     print("unresolved:")
