@@ -148,3 +148,41 @@ DGLB_API int dglb200_frontier_compact(const void* first, const void* n_first_dev
                                               (cudaStream_t)stream));
   DGLB_CATCH
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// ELL block -> CSC arrays: out[indptr[d] + k] = nbr[d, k] for k < cnt[d]. indptr is the exclusive scan of cnt (computed
+// by the caller); optional second payload (edge ids, any integer width through a byte copy of `esize` bytes).
+namespace dglb {
+template <typename I>
+__global__ void __launch_bounds__(256) ell_to_csc_kernel(const int32_t* __restrict__ nbr, const int32_t* __restrict__ eid,
+                                                         const int32_t* __restrict__ cnt, const int64_t* __restrict__ indptr,
+                                                         int64_t n, int fanout, I* __restrict__ out_idx, I* __restrict__ out_eid,
+                                                         const I* __restrict__ eid_map) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n * fanout; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t d = i / fanout;
+    const int k = (int)(i - d * fanout);
+    if (k < cnt[d]) {
+      const int64_t p = indptr[d] + k;
+      out_idx[p] = (I)nbr[i];
+      if (out_eid) {
+        const int64_t e = eid[i];
+        out_eid[p] = eid_map ? eid_map[e] : (I)e;
+      }
+    }
+  }
+}
+}  // namespace dglb
+
+DGLB_API int dglb200_ell_to_csc(int idtype, const void* nbr, const void* eid, const void* cnt, const void* indptr, int64_t n,
+                                int fanout, void* out_idx, void* out_eid, const void* eid_map, void* stream) {
+  DGLB_TRY
+  if (n == 0) return 0;
+  const unsigned grid = (unsigned)std::min<int64_t>((n * fanout + 255) / 256, 148 * 16);
+  DGLB_ID_SWITCH(idtype, I, {
+    ell_to_csc_kernel<I><<<grid, 256, 0, (cudaStream_t)stream>>>((const int32_t*)nbr, (const int32_t*)eid, (const int32_t*)cnt,
+                                                                 (const int64_t*)indptr, n, fanout, (I*)out_idx, (I*)out_eid,
+                                                                 (const I*)eid_map);
+  });
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}

@@ -1,4 +1,6 @@
-"""NeighborSampler (parity: /root/reference/python/dgl/dataloading/neighbor_sampler.py:152-206)."""
+"""NeighborSampler (API parity: /root/reference/python/dgl/dataloading/neighbor_sampler.py:152-206). On a GPU-resident
+homogeneous graph the layers are sampled by the one-synchronisation pipeline of ``sampling/fused_blocks.py``; everything
+else (heterographs, weights, replacement, CPU) takes the layer-by-layer ``sample_neighbors`` + ``to_block`` route."""
 from __future__ import annotations
 
 import torch
@@ -26,8 +28,18 @@ class NeighborSampler(BlockSampler):
         self.replace = replace
         self.fused = fused
         self.mapping = {}
+        self._fast = None
 
     def sample_blocks(self, g, seed_nodes, exclude_eids=None):
+        # GPU fast path: all layers enqueued back to back on capacity buffers, ONE host synchronisation per batch
+        # (sampling/fused_blocks.py); blocks carry their ELL form for the tcgen05 SAGE layer
+        if self.fused and torch.is_tensor(seed_nodes) and not isinstance(self.fanouts, dict):
+            from ..sampling import fused_blocks
+            if fused_blocks.usable(g, self.fanouts, self.prob, self.replace, self.edge_dir, exclude_eids) and \
+                    seed_nodes.device == g.device and self.output_device in (None, g.device):
+                if self._fast is None:
+                    self._fast = fused_blocks.FusedBlockSampler(self.fanouts)
+                return self._fast(g, seed_nodes)
         output_nodes = seed_nodes
         blocks = []
         for fanout in reversed(self.fanouts):

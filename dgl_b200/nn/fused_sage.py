@@ -31,8 +31,8 @@ def _pad_to(n, m):
 def block_to_ell(block):
     """(nbr int32 [n_dst, fanout], cnt int32 [n_dst], fanout) of a single-relation block, cached on the block."""
     cached = getattr(block, "_ell_cache", None)
-    if cached is not None:
-        return cached
+    if cached is not None:                                         # attached by the one-sync sampler, or computed below
+        return cached if cached[0] is None or cached[2] <= MAX_FANOUT else (None, None, cached[2])
     indptr, indices, _ = block._graphs[0].csc()
     deg = (indptr[1:] - indptr[:-1]).to(torch.int32)
     n_dst = deg.shape[0]

@@ -1,0 +1,146 @@
+"""One-synchronisation multi-layer neighbour sampling into message-flow graphs.
+
+The layer-by-layer formulation (``sample_neighbors`` -> ``to_block`` per layer, the reference's
+python/dgl/dataloading/neighbor_sampler.py:152-206 over src/array/cuda/rowwise_sampling.cu + cuda_to_block.cu) reads
+sizes back to the host after every kernel family: >= 2 host synchronisations per layer before the next layer can even be
+sized. Here ALL layers are enqueued back to back on capacity-sized buffers with device-side counts - the same
+``sample_ell`` (sub-warp Floyd sampling into a dense ELL block) and cooperative ``frontier_compact`` kernels the fused
+training engine replays in its CUDA graph - and the host reads every count ONCE at the end (L + 1 node counts and L edge
+counts in one copy). Blocks are then cut out of the capacity buffers as views: CSC arrays by one ``ell_to_csc`` launch per
+layer, and the ELL form is attached to the block so ``SAGEConv`` can feed the tcgen05 fused layer without re-deriving it.
+
+Requirements: homogeneous graph on the GPU, uniform sampling without replacement, fan-outs in [1, 64] (or -1 handled by
+the caller's fallback), < 2^31 nodes and edges.
+"""
+from __future__ import annotations
+
+import torch
+
+from .._native import loader
+from ..base import EID, NID, id_code
+from ..graph_index import UnitGraph
+from ..heterograph import DGLBlock
+from ..ops.fused import FrontierCompactor
+
+
+def _p(t):
+    return 0 if t is None else t.data_ptr()
+
+
+def _csc_int32(g):
+    """int32 CSC of the graph's single relation (cached on the structure) + its edge-id map (None = identity)."""
+    ug = g._graphs[0]
+    cache = ug._degs
+    hit = cache.get("csc_i32")
+    if hit is None:
+        indptr, indices, eids = ug.csc()
+        hit = (indptr.to(torch.int32).contiguous(), indices.to(torch.int32).contiguous(), eids)
+        cache["csc_i32"] = hit
+    return hit
+
+
+def usable(g, fanouts, prob, replace, edge_dir, exclude_eids):
+    if not (g.device.type == "cuda" and len(g.canonical_etypes) == 1 and len(g.ntypes) == 1):
+        return False
+    if prob is not None or replace or edge_dir != "in" or exclude_eids is not None:
+        return False
+    if not all(isinstance(f, int) and 1 <= f <= 64 for f in fanouts):
+        return False
+    return g.num_nodes() < 2 ** 31 and g.num_edges() < 2 ** 31
+
+
+class _Workspace:
+    """Capacity buffers of one (batch capacity, fan-outs) shape: worst case ``cap[l-1] = cap[l] * (1 + fanout_l)``."""
+
+    def __init__(self, batch_cap, fanouts, device):
+        L = len(fanouts)
+        self.batch_cap, self.fanouts, self.L = batch_cap, list(fanouts), L
+        caps = [0] * (L + 1)
+        caps[L] = batch_cap
+        for l in range(L, 0, -1):
+            caps[l - 1] = caps[l] * (1 + fanouts[l - 1])
+        self.caps = caps
+        i32 = torch.int32
+        self.seeds = torch.full((batch_cap,), -1, dtype=i32, device=device)
+        self.n = [torch.zeros(1, dtype=torch.int64, device=device) for _ in range(L + 1)]
+        self.nbr_g = [None] + [torch.empty((caps[l], fanouts[l - 1]), dtype=i32, device=device) for l in range(1, L + 1)]
+        self.eid = [None] + [torch.empty((caps[l], fanouts[l - 1]), dtype=i32, device=device) for l in range(1, L + 1)]
+        self.cnt = [None] + [torch.empty(caps[l], dtype=i32, device=device) for l in range(1, L + 1)]
+        self.totals = [None] + [torch.zeros(16, dtype=torch.int64, device=device) for _ in range(1, L + 1)]
+        self.compactors = [None] + [FrontierCompactor(caps[l], fanouts[l - 1], caps[l - 1], device) for l in range(1, L + 1)]
+        self.counts_host = torch.zeros(2 * L + 1, dtype=torch.int64).pin_memory()
+
+
+class FusedBlockSampler:
+    """Callable ``(g, seeds) -> (input_nodes, output_nodes, blocks)`` for fixed fan-outs; workspaces are cached per batch
+    capacity (rounded up to a power of two) and reused across calls."""
+
+    def __init__(self, fanouts, seed=0):
+        self.fanouts = [int(f) for f in fanouts]
+        self.seed = int(seed)
+        self._ws = {}
+        self._step = 0
+
+    def _workspace(self, n_seeds, device):
+        cap = 64
+        while cap < n_seeds:
+            cap <<= 1
+        key = (cap, device.index)
+        ws = self._ws.get(key)
+        if ws is None:
+            ws = self._ws[key] = _Workspace(cap, self.fanouts, device)
+        return ws
+
+    def __call__(self, g, seeds):
+        lib = loader.cuda_lib()
+        dev = g.device
+        idt = g.idtype
+        indptr, indices, csc_eids = _csc_int32(g)
+        L = len(self.fanouts)
+        n_seeds = int(seeds.shape[0])
+        ws = self._workspace(n_seeds, dev)
+        ws.seeds[:n_seeds] = seeds.to(torch.int32)
+        if n_seeds < ws.batch_cap:
+            ws.seeds[n_seeds:] = -1
+        ws.n[L].fill_(n_seeds)
+        self._step += 1
+        S = [None] * (L + 1)
+        nbr_local = [None] * (L + 1)
+        S[L] = ws.seeds
+        it = id_code(torch.int32)
+        # ---- every layer enqueued without looking at a size
+        for l in range(L, 0, -1):
+            f = self.fanouts[l - 1]
+            ws.totals[l].zero_()
+            lib.fn("dglb200_cuda_sample_ell", "ippiplpilpppppi" + "p")(
+                it, _p(indptr), _p(indices), 0, _p(S[l]), ws.caps[l], _p(ws.n[l]), f, self.seed * 7919 + l + 131 * self._step, 0,
+                _p(ws.nbr_g[l]), _p(ws.eid[l]), _p(ws.cnt[l]), _p(ws.totals[l]), 1, loader.stream_ptr())
+            S[l - 1], nbr_local[l], n_prev, _ = ws.compactors[l].compact(S[l], ws.n[l], ws.nbr_g[l])
+            ws.n[l - 1] = n_prev
+        # ---- ONE host read: node counts of S_L .. S_0 and the edge count of every layer
+        packed = torch.cat([ws.n[l].view(1) for l in range(L, -1, -1)] + [ws.totals[l].sum().view(1) for l in range(L, 0, -1)])
+        ws.counts_host.copy_(packed, non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        counts = ws.counts_host.tolist()
+        n_nodes = {l: int(counts[L - l]) for l in range(L, -1, -1)}
+        n_edges = {l: int(counts[L + 1 + (L - l)]) for l in range(L, 0, -1)}
+        blocks = []
+        for l in range(1, L + 1):
+            f = self.fanouts[l - 1]
+            nd, ns, ne = n_nodes[l], n_nodes[l - 1], n_edges[l]
+            cnt = ws.cnt[l][:nd]
+            ptr64 = torch.zeros(nd + 1, dtype=torch.int64, device=dev)
+            torch.cumsum(cnt, 0, out=ptr64[1:])
+            idx = torch.empty(ne, dtype=idt, device=dev)
+            eids = torch.empty(ne, dtype=idt, device=dev)
+            lib.fn("dglb200_ell_to_csc", "ipppplipppp")(id_code(idt), _p(nbr_local[l]), _p(ws.eid[l]), _p(cnt), _p(ptr64), nd, f,
+                                                       _p(idx), _p(eids), _p(csc_eids), loader.stream_ptr())
+            ug = UnitGraph.from_csc(ns, nd, ptr64.to(idt), idx)
+            block = DGLBlock([ug], None, g.canonical_etypes, [ns, nd], srctypes=list(g.ntypes), dsttypes=list(g.ntypes))
+            block.srcdata[NID] = S[l - 1][:ns].to(idt)
+            block.dstdata[NID] = S[l][:nd].to(idt) if l < L else S[l][:nd].to(idt).clone()   # seeds live in the workspace
+            block.edata[EID] = eids
+            # the dense ELL form of the same block (rows = destination nodes): consumed by nn/fused_sage.py
+            block._ell_cache = (nbr_local[l][:nd], cnt.clone(), f)
+            blocks.append(block)
+        return blocks[0].srcdata[NID], blocks[-1].dstdata[NID], blocks

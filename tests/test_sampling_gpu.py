@@ -123,3 +123,47 @@ def test_weighted_sampling_above_128_picks(fanout):
     if fanout < 0:                                                       # everything eligible is returned
         cpu = dgl.sampling.sample_neighbors(g, seeds.cpu(), -1, prob="p")
         assert sorted(cpu.edata[dgl.EID].tolist()) == sorted(eid.cpu().tolist())
+
+
+@pytest.mark.parametrize("idtype", [torch.int32, torch.int64])
+def test_fused_block_sampler_matches_block_contract(idtype):
+    """One-sync multi-layer sampler: blocks obey the MFG contract (dst prefix, NID/EID maps, real in-edges, fan-out)."""
+    import dgl_b200 as dgl
+    from dgl_b200.dataloading import NeighborSampler
+    torch.manual_seed(0)
+    n, m = 5000, 120000
+    u, v = torch.randint(0, n, (m,)), torch.randint(0, n, (m,))
+    g = dgl.graph((u, v), num_nodes=n, idtype=idtype).to(DEV)
+    sampler = NeighborSampler([7, 5, 3])
+    seeds = torch.randperm(n)[:300].to(idtype).to(DEV)
+    for _ in range(2):                                   # second call reuses the cached workspace
+        inp, out, blocks = sampler.sample_blocks(g, seeds)
+        assert sampler._fast is not None and torch.equal(out, seeds)
+        gu, gv = g.edges()
+        deg = g.in_degrees()
+        cur = seeds
+        for blk, fan in zip(reversed(blocks), [3, 5, 7]):
+            nd, ns = blk.num_dst_nodes(), blk.num_src_nodes()
+            src_ids, dst_ids = blk.srcdata[dgl.NID], blk.dstdata[dgl.NID]
+            assert torch.equal(dst_ids, cur) and torch.equal(src_ids[:nd], dst_ids)
+            assert torch.unique(src_ids).numel() == ns
+            bu, bv = blk.edges()
+            eid = blk.edata[dgl.EID]
+            assert torch.equal(gu[eid.long()], src_ids[bu.long()]) and torch.equal(gv[eid.long()], dst_ids[bv.long()])
+            assert torch.unique(eid).numel() == eid.numel()                     # without replacement
+            assert torch.equal(blk.in_degrees().long(), deg[dst_ids.long()].clamp(max=fan).long())
+            nbr, cnt, f = blk._ell_cache
+            assert f == fan and torch.equal(cnt.long(), blk.in_degrees().long())
+            cur = src_ids
+        assert torch.equal(inp, cur)
+    # the fused SAGE layer consumes the attached ELL form; result equals the g-SpMM formulation
+    from dgl_b200.nn import fused_sage
+    conv = dgl.nn.SAGEConv(16, 8, "mean").to(DEV)
+    x = torch.randn(blocks[0].num_src_nodes(), 16, device=DEV)
+    y_fused = conv(blocks[0], x)
+    fused_sage.ENABLED[0] = False
+    try:
+        y_ref = conv(blocks[0], x)
+    finally:
+        fused_sage.ENABLED[0] = True
+    assert torch.allclose(y_fused, y_ref, atol=1e-4)
