@@ -26,6 +26,7 @@ class NeighborSampler(SubgraphSampler):
         self.batch_dependency = batch_dependency
         self.layer_dependency = layer_dependency
         self._cnt = 0
+        self._fast = None
 
     def _sample_one(self, seeds, fanout, layer_idx):
         if self.layer:
@@ -39,9 +40,46 @@ class NeighborSampler(SubgraphSampler):
                                                      seed2_contribution=t)
         return self.graph.sample_neighbors(seeds, fanout, self.replace, self.prob_name)
 
+    def _fast_usable(self, seeds):
+        g = self.graph
+        if self.layer or self.replace or self.prob_name is not None or not self.deduplicate or not torch.is_tensor(seeds):
+            return False
+        if g.type_per_edge is not None or g.node_type_offset is not None or not seeds.is_cuda:
+            return False
+        if not (g.csc_indptr.is_cuda or g.is_pinned()) or g.indices.shape[0] >= 2 ** 31:
+            return False
+        return all(f.numel() == 1 and 1 <= int(f) <= 64 for f in self.fanouts)
+
+    def _sample_fast(self, seeds):
+        """All hops through the one-synchronisation pipeline (sampling/fused_blocks.py); the graph may be device
+        resident or host-pinned (the sampling kernel reads pinned CSC arrays over UVA)."""
+        from ...sampling.fused_blocks import FusedBlockSampler
+        g = self.graph
+        if self._fast is None:
+            self._fast = FusedBlockSampler([int(f) for f in self.fanouts])
+            to32 = lambda t: t if t.dtype == torch.int32 else t.to(torch.int32)  # noqa: E731
+            ip, ix = to32(g.csc_indptr), to32(g.indices)
+            if g.is_pinned() and not ip.is_pinned():
+                from ...utils import pin_memory_inplace
+                pin_memory_inplace(ip), pin_memory_inplace(ix)
+            self._fast_csc = (ip.contiguous(), ix.contiguous())
+        ip, ix = self._fast_csc
+        idt = seeds.dtype
+        subgraphs = []
+        for layer in self._fast.sample_layers(ip, ix, seeds, uva=not ip.is_cuda):
+            ptr, idx, eids = self._fast.layer_to_csc(layer, idt)
+            from ..base import CSCFormatBase
+            sg = SampledSubgraphImpl(sampled_csc=CSCFormatBase(ptr, idx), original_column_node_ids=layer["dst"].to(idt),
+                                     original_row_node_ids=layer["src"].to(idt), original_edge_ids=eids)
+            sg._ell_cache = (layer["nbr"], layer["cnt"], layer["fanout"])
+            subgraphs.append(sg)
+        return subgraphs[0].original_row_node_ids, subgraphs
+
     def sample_subgraphs(self, seeds, seeds_timestamp=None):
         subgraphs = []
         self._cnt += 1
+        if self._fast_usable(seeds):
+            return self._sample_fast(seeds)
         for hop in reversed(range(len(self.fanouts))):
             sg = self._sample_one(seeds, self.fanouts[hop], hop)
             if self.deduplicate:

@@ -167,6 +167,9 @@ class MiniBatch:
                     b.dstdata[NID] = cn
                     if sg.original_edge_ids is not None:
                         b.edata[EID] = sg.original_edge_ids
+                    ell = getattr(sg, "_ell_cache", None)
+                    if ell is not None:                       # sampled as an ELL block: keep that form for the fused layer
+                        b._ell_cache = ell
                 blocks.append(b)
             self._blocks = blocks
         return self._blocks

@@ -91,11 +91,12 @@ class FusedBlockSampler:
             ws = self._ws[key] = _Workspace(cap, self.fanouts, device)
         return ws
 
-    def __call__(self, g, seeds):
+    def sample_layers(self, indptr, indices, seeds, uva=False):
+        """Core pipeline on int32 CSC arrays (device, or host-pinned with ``uva``). Returns per layer l = 1..L a dict with
+        ``dst`` / ``src`` (global ids), ``nbr`` (local ELL), ``cnt``, ``eid`` (CSC positions, ELL shaped), ``fanout``,
+        ``n_dst`` / ``n_src`` / ``n_edges`` (host ints) - after exactly ONE host synchronisation."""
         lib = loader.cuda_lib()
-        dev = g.device
-        idt = g.idtype
-        indptr, indices, csc_eids = _csc_int32(g)
+        dev = seeds.device
         L = len(self.fanouts)
         n_seeds = int(seeds.shape[0])
         ws = self._workspace(n_seeds, dev)
@@ -113,8 +114,9 @@ class FusedBlockSampler:
             f = self.fanouts[l - 1]
             ws.totals[l].zero_()
             lib.fn("dglb200_cuda_sample_ell", "ippiplpilpppppi" + "p")(
-                it, _p(indptr), _p(indices), 0, _p(S[l]), ws.caps[l], _p(ws.n[l]), f, self.seed * 7919 + l + 131 * self._step, 0,
-                _p(ws.nbr_g[l]), _p(ws.eid[l]), _p(ws.cnt[l]), _p(ws.totals[l]), 1, loader.stream_ptr())
+                it, _p(indptr), _p(indices), 1 if uva else 0, _p(S[l]), ws.caps[l], _p(ws.n[l]), f,
+                self.seed * 7919 + l + 131 * self._step, 0, _p(ws.nbr_g[l]), _p(ws.eid[l]), _p(ws.cnt[l]), _p(ws.totals[l]), 1,
+                loader.stream_ptr())
             S[l - 1], nbr_local[l], n_prev, _ = ws.compactors[l].compact(S[l], ws.n[l], ws.nbr_g[l])
             ws.n[l - 1] = n_prev
         # ---- ONE host read: node counts of S_L .. S_0 and the edge count of every layer
@@ -124,23 +126,41 @@ class FusedBlockSampler:
         counts = ws.counts_host.tolist()
         n_nodes = {l: int(counts[L - l]) for l in range(L, -1, -1)}
         n_edges = {l: int(counts[L + 1 + (L - l)]) for l in range(L, 0, -1)}
-        blocks = []
+        layers = []
         for l in range(1, L + 1):
-            f = self.fanouts[l - 1]
-            nd, ns, ne = n_nodes[l], n_nodes[l - 1], n_edges[l]
-            cnt = ws.cnt[l][:nd]
-            ptr64 = torch.zeros(nd + 1, dtype=torch.int64, device=dev)
-            torch.cumsum(cnt, 0, out=ptr64[1:])
-            idx = torch.empty(ne, dtype=idt, device=dev)
-            eids = torch.empty(ne, dtype=idt, device=dev)
-            lib.fn("dglb200_ell_to_csc", "ipppplipppp")(id_code(idt), _p(nbr_local[l]), _p(ws.eid[l]), _p(cnt), _p(ptr64), nd, f,
-                                                       _p(idx), _p(eids), _p(csc_eids), loader.stream_ptr())
-            ug = UnitGraph.from_csc(ns, nd, ptr64.to(idt), idx)
-            block = DGLBlock([ug], None, g.canonical_etypes, [ns, nd], srctypes=list(g.ntypes), dsttypes=list(g.ntypes))
-            block.srcdata[NID] = S[l - 1][:ns].to(idt)
-            block.dstdata[NID] = S[l][:nd].to(idt) if l < L else S[l][:nd].to(idt).clone()   # seeds live in the workspace
+            nd, ns = n_nodes[l], n_nodes[l - 1]
+            dst = S[l][:nd].clone() if l == L else S[l][:nd]           # the seeds live in the reused workspace
+            layers.append(dict(dst=dst, src=S[l - 1][:ns], nbr=nbr_local[l][:nd], cnt=ws.cnt[l][:nd].clone(), eid=ws.eid[l],
+                               fanout=self.fanouts[l - 1], n_dst=nd, n_src=ns, n_edges=n_edges[l]))
+        return layers
+
+    @staticmethod
+    def layer_to_csc(layer, idtype, eid_map=None, want_eids=True):
+        """(indptr, indices, eids) of one sampled layer in ``idtype`` (one cumsum + one ``ell_to_csc`` launch)."""
+        dev = layer["cnt"].device
+        nd, ne = layer["n_dst"], layer["n_edges"]
+        ptr64 = torch.zeros(nd + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(layer["cnt"], 0, out=ptr64[1:])
+        idx = torch.empty(ne, dtype=idtype, device=dev)
+        eids = torch.empty(ne, dtype=idtype, device=dev) if want_eids else None
+        loader.cuda_lib().fn("dglb200_ell_to_csc", "ipppplipppp")(
+            id_code(idtype), _p(layer["nbr"]), _p(layer["eid"]), _p(layer["cnt"]), _p(ptr64), nd, layer["fanout"], _p(idx),
+            _p(eids), _p(eid_map), loader.stream_ptr())
+        return ptr64.to(idtype), idx, eids
+
+    def __call__(self, g, seeds):
+        idt = g.idtype
+        indptr, indices, csc_eids = _csc_int32(g)
+        blocks = []
+        for layer in self.sample_layers(indptr, indices, seeds):
+            ptr, idx, eids = self.layer_to_csc(layer, idt, csc_eids)
+            ug = UnitGraph.from_csc(layer["n_src"], layer["n_dst"], ptr, idx)
+            block = DGLBlock([ug], None, g.canonical_etypes, [layer["n_src"], layer["n_dst"]], srctypes=list(g.ntypes),
+                             dsttypes=list(g.ntypes))
+            block.srcdata[NID] = layer["src"].to(idt)
+            block.dstdata[NID] = layer["dst"].to(idt)
             block.edata[EID] = eids
             # the dense ELL form of the same block (rows = destination nodes): consumed by nn/fused_sage.py
-            block._ell_cache = (nbr_local[l][:nd], cnt.clone(), f)
+            block._ell_cache = (layer["nbr"], layer["cnt"], layer["fanout"])
             blocks.append(block)
         return blocks[0].srcdata[NID], blocks[-1].dstdata[NID], blocks
