@@ -1,6 +1,11 @@
-"""save_graphs / load_graphs / save_info / load_info (parity: /root/reference/python/dgl/data/graph_serialize.py:83,149 and
-the native binary format src/graph/serialize/*). Container: one ``torch.save`` archive with a magic/version header,
-COO structure per relation, node/edge frames and optional label dict; heterographs round-trip."""
+"""save_graphs / load_graphs / save_info / load_info (API parity: /root/reference/python/dgl/data/graph_serialize.py:83,149).
+
+Container: one ``torch.save`` archive holding ONLY tensors and plain Python containers (magic/version header, COO
+structure per relation, node/edge frames, optional label dict), so it is read back with ``weights_only=True``: loading a
+graph file never unpickles arbitrary objects. Heterographs, blocks and batched graphs round-trip.
+
+The reference's ``.bin`` files use libdgl's own binary layout (src/graph/serialize/*, dmlc streams of NDArrays); they
+are not read here. ``tools/convert_dgl_bin.py`` converts them (graphs + labels) with an installed reference build."""
 from __future__ import annotations
 
 import os
@@ -56,20 +61,41 @@ def save_graphs(filename, g_list, labels=None, formats=None):
     torch.save({"magic": MAGIC, "version": VERSION, "graphs": [_pack(g) for g in g_list], "labels": labels or {}}, filename)
 
 
-def load_graphs(filename, idx_list=None):
+def _read_archive(filename):
     if not os.path.exists(filename):
         raise DGLError(f"File {filename} does not exist.")
-    d = torch.load(filename, weights_only=False)
-    if d.get("magic") != MAGIC:
+    try:
+        d = torch.load(filename, weights_only=True, map_location="cpu")
+    except Exception as e:  # noqa: BLE001 - not a torch archive, or it contains objects: refuse, never unpickle them
+        with open(filename, "rb") as fh:
+            head = fh.read(8)
+        if head == b"\x3f\xa1\xb4\x46\xf0\x4f\x2e\xdd":
+            raise DGLError(f"{filename} is a reference (libdgl) binary graph file; convert it with "
+                           "tools/convert_dgl_bin.py") from None
+        raise DGLError(f"{filename} is not a graph archive of this framework: {type(e).__name__}: {e}") from None
+    if not isinstance(d, dict) or d.get("magic") != MAGIC or not isinstance(d.get("graphs"), list):
         raise DGLError("Invalid DGL graph file (bad magic)")
+    if int(d.get("version", 0)) > VERSION:
+        raise DGLError(f"graph archive version {d.get('version')} is newer than this build understands ({VERSION})")
+    return d
+
+
+def load_graphs(filename, idx_list=None):
+    d = _read_archive(filename)
     packs = d["graphs"]
     if idx_list is not None:
-        packs = [packs[i] for i in idx_list]
-    return [_unpack(p) for p in packs], d["labels"]
+        try:
+            packs = [packs[i] for i in idx_list]
+        except IndexError:
+            raise DGLError(f"idx_list {list(idx_list)} out of range: the file holds {len(packs)} graphs") from None
+    try:
+        return [_unpack(p) for p in packs], d.get("labels", {})
+    except (KeyError, TypeError, ValueError) as e:
+        raise DGLError(f"corrupt graph archive {filename}: {type(e).__name__}: {e}") from None
 
 
 def load_labels(filename):
-    return torch.load(filename, weights_only=False)["labels"]
+    return _read_archive(filename).get("labels", {})
 
 
 def save_info(path, info):

@@ -1,5 +1,6 @@
 """Small reference-path modules: mpops.edgewise, multiprocessing.thread_wrapped_func, frame.Scheme, function.TargetCode,
 heterograph helpers, udf/ndarray/container, sampling.EidExcluder, ops.reshape_lhs_rhs, storages registry."""
+import os
 import pickle
 
 import numpy as np
@@ -193,3 +194,35 @@ def test_method_level_additions():
     pol = kvstore.PartitionPolicy("edge:a:r:b", None)
     assert pol.type_name == ("a", "r", "b") and not pol.is_node() and str(pol.get_data_name("w")) == "edge~a:r:b~w"
     assert kvstore.PartitionPolicy("node:user", None).type_name == "user"
+
+
+def test_graph_archive_is_tensor_only_and_rejects_foreign_files(tmp_path):
+    """loading a graph file must not unpickle arbitrary objects; malformed input raises DGLError."""
+    import pickle
+    import dgl_b200 as dgl
+    g = dgl.heterograph({("a", "r", "b"): ([0, 1, 2], [1, 0, 1]), ("b", "s", "a"): ([0, 1], [2, 2])})
+    g.nodes["a"].data["x"] = torch.randn(3, 4)
+    p = str(tmp_path / "g.pt")
+    dgl.save_graphs(p, [g, dgl.batch([dgl.rand_graph(4, 6), dgl.rand_graph(3, 5)])], {"y": torch.tensor([1, 2])})
+    torch.load(p, weights_only=True)                                   # the archive holds tensors + plain containers only
+    gs, labels = dgl.load_graphs(p)
+    assert gs[0].canonical_etypes == g.canonical_etypes and torch.equal(gs[0].nodes["a"].data["x"], g.nodes["a"].data["x"])
+    assert gs[1].batch_size == 2 and labels["y"].tolist() == [1, 2]
+    with pytest.raises(dgl.DGLError):
+        dgl.load_graphs(p, [5])
+
+    class Evil:
+        def __reduce__(self):
+            return (os.system, ("echo pwned > %s" % (tmp_path / "pwned"),))
+
+    bad = str(tmp_path / "evil.pt")
+    with open(bad, "wb") as fh:
+        pickle.dump({"magic": "DGLB200-GRAPHS", "graphs": [Evil()]}, fh)
+    with pytest.raises(dgl.DGLError):
+        dgl.load_graphs(bad)
+    assert not (tmp_path / "pwned").exists()
+    junk = str(tmp_path / "junk.bin")
+    with open(junk, "wb") as fh:
+        fh.write(b"\x3f\xa1\xb4\x46\xf0\x4f\x2e\xdd" + b"\0" * 64)       # libdgl magic: pointed at the converter
+    with pytest.raises(dgl.DGLError, match="convert_dgl_bin"):
+        dgl.load_graphs(junk)
