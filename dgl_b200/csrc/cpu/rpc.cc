@@ -27,6 +27,13 @@
 
 namespace dglb {
 
+// upper bound of one frame (payload + 8-byte header); DGLB200_RPC_MAX_FRAME_MB overrides the 1 GiB default
+static const uint64_t kMaxFrameBytes = [] {
+  const char* e = std::getenv("DGLB200_RPC_MAX_FRAME_MB");
+  const uint64_t mb = e ? std::strtoull(e, nullptr, 10) : 1024;
+  return (mb ? mb : 1024) << 20;
+}();
+
 struct Message {
   int32_t src, tag;
   std::vector<char> data;
@@ -180,9 +187,17 @@ class Endpoint {
         }
         c->buf.insert(c->buf.end(), tmp.data(), tmp.data() + r);
         size_t pos = 0;
+        bool bad_frame = false;
         while (c->buf.size() - pos >= 8) {
           uint64_t total;
           std::memcpy(&total, c->buf.data() + pos, 8);
+          // the length prefix comes from the network: a frame carries at least (src, tag) = 8 bytes and at most
+          // kMaxFrameBytes; anything else is a protocol violation (or an attack) and drops the connection instead of
+          // running assign() with first > last or growing the buffer without bound
+          if (total < 8 || total > kMaxFrameBytes) {
+            bad_frame = true;
+            break;
+          }
           if (c->buf.size() - pos < 8 + total) break;
           Message m;
           std::memcpy(&m.src, c->buf.data() + pos + 8, 4);
@@ -194,6 +209,13 @@ class Endpoint {
             inbox_.push_back(std::move(m));
           }
           q_cv_.notify_one();
+        }
+        if (bad_frame) {
+          epoll_ctl(ep_, EPOLL_CTL_DEL, fd, nullptr);
+          ::close(fd);
+          std::lock_guard<std::mutex> lk(mu_);
+          in_.erase(fd);
+          continue;
         }
         if (pos > 0) c->buf.erase(c->buf.begin(), c->buf.begin() + pos);
       }

@@ -140,10 +140,16 @@ class DataLoader:
             if graph.device.type == "cuda" and num_workers > 0:
                 raise DGLError("num_workers must be 0 if graph and indices are on CUDA.")
             indices_device = graph.device
-        if num_workers > 0:
-            dgl_warning("num_workers > 0 is emulated with a prefetch thread in this build (sampling kernels "
-                        "release the GIL); worker processes are not spawned.")
+        # num_workers > 0 on a host graph: real sampling processes (forked, graph shared copy-on-write, batches returned
+        # through torch.multiprocessing's shared-memory tensors) - see _WorkerPool. DGLB200_LOADER_THREADS=1 keeps the
+        # lighter single prefetch thread instead.
+        self._use_processes = num_workers > 0 and graph.device.type == "cpu" and not use_uva and \
+            os.environ.get("DGLB200_LOADER_THREADS", "0") != "1"
+        if num_workers > 0 and not self._use_processes:
             use_prefetch_thread = True
+        self._pool = None
+        self.persistent_workers = bool(kwargs.pop("persistent_workers", False))
+        self.prefetch_factor = int(kwargs.pop("prefetch_factor", 2) or 2)
         self.use_uva = use_uva
         self.batcher = _IndexBatcher(indices, batch_size, shuffle, drop_last, use_ddp, ddp_seed, indices_device)
         if use_alternate_streams is None:
@@ -178,8 +184,28 @@ class DataLoader:
         batch = _to_device(batch, self.device)
         return batch
 
+    def _iter_processes(self, it):
+        pool = self._pool
+        if pool is None or not pool.alive():
+            pool = self._pool = _WorkerPool(self.graph, self.graph_sampler, self.num_workers, self.prefetch_factor)
+        try:
+            for batch in pool.run(it):
+                yield _to_device(batch, self.device)
+        finally:
+            if not self.persistent_workers:
+                pool.shutdown()
+                self._pool = None
+
+    def __del__(self):
+        pool = getattr(self, "_pool", None)
+        if pool is not None:
+            pool.shutdown()
+
     def __iter__(self):
         it = iter(self.batcher)
+        if self._use_processes:
+            yield from self._iter_processes(it)
+            return
         if not self.use_prefetch_thread:
             stream = torch.cuda.Stream(self.device) if self.use_alternate_streams else None
             for idx in it:
@@ -195,6 +221,16 @@ class DataLoader:
             return
         q = queue.Queue(maxsize=2)
         done = object()
+        stop = threading.Event()          # set when the consumer abandons the iterator: the producer must not block forever
+
+        def offer(item):
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.2)
+                    return True
+                except queue.Full:
+                    continue
+            return False
 
         def worker():
             try:
@@ -202,39 +238,142 @@ class DataLoader:
                     torch.cuda.set_device(self.device)
                 stream = torch.cuda.Stream(self.device) if self.device.type == "cuda" else None
                 for idx in it:
+                    if stop.is_set():
+                        return
                     if stream is not None:
                         with torch.cuda.stream(stream):
                             batch = self._produce(idx)
                         ev = torch.cuda.Event()
                         ev.record(stream)
-                        q.put((batch, ev, None))
-                    else:
-                        q.put((self._produce(idx), None, None))
-                q.put((done, None, None))
+                        if not offer((batch, ev, None)):
+                            return
+                    elif not offer((self._produce(idx), None, None)):
+                        return
+                offer((done, None, None))
             except Exception as e:  # noqa: BLE001
-                q.put((None, None, e))
+                offer((None, None, e))
 
         th = threading.Thread(target=worker, daemon=True)
         th.start()
-        while True:
-            try:
-                batch, ev, exc = q.get(timeout=PREFETCHER_TIMEOUT * 20)
-            except queue.Empty:
-                raise RuntimeError(f"Prefetcher thread timed out at {PREFETCHER_TIMEOUT * 20} seconds.")
-            if exc is not None:
-                raise exc
-            if batch is done:
-                break
-            if ev is not None:
-                torch.cuda.current_stream(self.device).wait_event(ev)
-                _record_stream(batch, torch.cuda.current_stream(self.device))
-            yield batch
-        th.join()
+        try:
+            while True:
+                try:
+                    batch, ev, exc = q.get(timeout=PREFETCHER_TIMEOUT * 20)
+                except queue.Empty:
+                    raise RuntimeError(f"Prefetcher thread timed out at {PREFETCHER_TIMEOUT * 20} seconds.")
+                if exc is not None:
+                    raise exc
+                if batch is done:
+                    break
+                if ev is not None:
+                    torch.cuda.current_stream(self.device).wait_event(ev)
+                    _record_stream(batch, torch.cuda.current_stream(self.device))
+                yield batch
+        finally:                          # normal end, exception, or the generator being closed early (break / GC)
+            stop.set()
+            while True:                   # drop whatever is queued so GPU batches are released
+                try:
+                    q.get_nowait()
+                except queue.Empty:
+                    break
+            th.join(timeout=5)
 
     # CPU affinity helpers kept for API parity (reference dataloader.py:1159-1257)
     def enable_cpu_affinity(self, loader_cores=None, compute_cores=None, verbose=True):
         from contextlib import nullcontext
         return nullcontext()
+
+
+def _worker_loop(graph, sampler, index_q, result_q, wid, base_seed):
+    """Body of one sampling process: receives (task id, index batch), returns (task id, batch | exception)."""
+    import random as _random
+    torch.set_num_threads(1)
+    torch.manual_seed(base_seed + wid)
+    _random.seed(base_seed + wid)
+    try:
+        from .. import random as dgl_random
+        dgl_random.seed(base_seed + wid)
+    except Exception:  # noqa: BLE001
+        pass
+    while True:
+        task = index_q.get()
+        if task is None:
+            return
+        tid, idx = task
+        try:
+            batch = sampler.sample(graph, idx)
+            batch = assign_lazy_features(batch, graph, torch.device("cpu"))
+            result_q.put((tid, batch, None))
+        except Exception as e:  # noqa: BLE001
+            import traceback
+            result_q.put((tid, None, f"{type(e).__name__}: {e}\n{traceback.format_exc()}"))
+
+
+class _WorkerPool:
+    """``num_workers`` forked sampling processes. The (host) graph is inherited copy-on-write, index batches go out
+    round-robin with ``prefetch_factor`` tasks in flight per worker, results come back through one queue (tensors travel
+    in shared memory) and are re-ordered, so iteration order equals the single-process order.
+    Reference: the torch DataLoader worker pool behind python/dgl/dataloading/dataloader.py:925-1090."""
+
+    def __init__(self, graph, sampler, num_workers, prefetch_factor=2):
+        import torch.multiprocessing as mp
+        ctx = mp.get_context("fork")
+        self.n, self.depth = num_workers, max(1, prefetch_factor)
+        self.index_qs = [ctx.Queue() for _ in range(num_workers)]
+        self.result_q = ctx.Queue()
+        seed = int(torch.empty((), dtype=torch.int64).random_().item()) & 0x7FFFFFFF
+        self.procs = [ctx.Process(target=_worker_loop, args=(graph, sampler, self.index_qs[w], self.result_q, w, seed),
+                                  daemon=True) for w in range(num_workers)]
+        for p in self.procs:
+            p.start()
+
+    def alive(self):
+        return all(p.is_alive() for p in self.procs)
+
+    def run(self, index_iter):
+        sent = done = 0
+        pending = {}
+        exhausted = False
+
+        def dispatch():
+            nonlocal sent, exhausted
+            while not exhausted and sent - done < self.n * self.depth:
+                try:
+                    idx = next(index_iter)
+                except StopIteration:
+                    exhausted = True
+                    return
+                self.index_qs[sent % self.n].put((sent, idx.cpu() if torch.is_tensor(idx) else idx))
+                sent += 1
+
+        dispatch()
+        while done < sent:
+            while done not in pending:
+                try:
+                    tid, batch, err = self.result_q.get(timeout=PREFETCHER_TIMEOUT * 20)
+                except queue.Empty:
+                    if not self.alive():
+                        raise RuntimeError("a DataLoader worker process died unexpectedly") from None
+                    raise RuntimeError(f"DataLoader workers timed out at {PREFETCHER_TIMEOUT * 20} seconds.") from None
+                if err is not None:
+                    raise RuntimeError(f"DataLoader worker failed on batch {tid}:\n{err}")
+                pending[tid] = batch
+            batch = pending.pop(done)
+            done += 1
+            dispatch()
+            yield batch
+
+    def shutdown(self):
+        for q_ in self.index_qs:
+            try:
+                q_.put(None)
+            except Exception:  # noqa: BLE001
+                pass
+        for p in self.procs:
+            p.join(timeout=2)
+            if p.is_alive():
+                p.terminate()
+        self.procs = []
 
 
 def _to_device(x, device):

@@ -226,3 +226,43 @@ def test_graph_archive_is_tensor_only_and_rejects_foreign_files(tmp_path):
         fh.write(b"\x3f\xa1\xb4\x46\xf0\x4f\x2e\xdd" + b"\0" * 64)       # libdgl magic: pointed at the converter
     with pytest.raises(dgl.DGLError, match="convert_dgl_bin"):
         dgl.load_graphs(junk)
+
+
+def test_dataloader_worker_processes_and_early_exit():
+    """num_workers > 0 on a host graph = real sampling processes (ordered results, prefetched features); abandoning an
+    iterator - process pool or prefetch thread - neither hangs nor leaks the producer."""
+    import threading
+    import dgl_b200 as dgl
+    from dgl_b200.dataloading import DataLoader, NeighborSampler
+    g = dgl.rand_graph(3000, 30000)
+    g.ndata["feat"] = torch.randn(3000, 8)
+    g.ndata["label"] = torch.randint(0, 4, (3000,))
+    s = NeighborSampler([4, 4], prefetch_node_feats=["feat"], prefetch_labels=["label"])
+    dl = DataLoader(g, torch.arange(1000), s, batch_size=100, num_workers=2)
+    assert dl._use_processes
+    seen = []
+    for inp, out, blocks in dl:
+        seen.append(out)
+        assert torch.equal(blocks[0].srcdata["feat"], g.ndata["feat"][inp])
+        assert torch.equal(blocks[-1].dstdata["label"], g.ndata["label"][out])
+    assert torch.equal(torch.cat(seen), torch.arange(1000))              # same order as the single-process loader
+    assert dl._pool is None                                                # pool shut down at the end of the epoch
+    it = iter(DataLoader(g, torch.arange(1000), s, batch_size=100, num_workers=2))
+    next(it)
+    it.close()                                                             # early exit: workers are stopped
+    before = threading.active_count()
+    os.environ["DGLB200_LOADER_THREADS"] = "1"
+    try:
+        dl2 = DataLoader(g, torch.arange(1000), s, batch_size=100, num_workers=1)
+        assert not dl2._use_processes and dl2.use_prefetch_thread
+        it2 = iter(dl2)
+        next(it2)
+        it2.close()                                                        # the producer thread must notice and exit
+    finally:
+        del os.environ["DGLB200_LOADER_THREADS"]
+    import time
+    for _ in range(50):
+        if threading.active_count() <= before:
+            break
+        time.sleep(0.1)
+    assert threading.active_count() <= before
