@@ -53,18 +53,28 @@ class PartitionPolicy:
         return HeteroDataName(self.is_node(), self.type_name, name)
 
     def to_partid(self, id_tensor):
-        return self._gpb.nid2partid(id_tensor) if self._dom == NODE_PART_POLICY else self._gpb.eid2partid(id_tensor)
+        if self._dom == NODE_PART_POLICY:
+            return self._gpb.nid2partid(id_tensor, self._typ)
+        return self._gpb.eid2partid(id_tensor, self._typ)
 
     def to_local(self, id_tensor):
-        f = self._gpb.nid2localnid if self._dom == NODE_PART_POLICY else self._gpb.eid2localeid
-        return f(id_tensor, self._gpb.partid)
+        if self._dom == NODE_PART_POLICY:
+            return self._gpb.nid2localnid(id_tensor, self._gpb.partid, self._typ)
+        return self._gpb.eid2localeid(id_tensor, self._gpb.partid, self._typ)
+
+    def _range_table(self):
+        """[num_parts, 2] id ranges of THIS policy's node / edge type."""
+        if self._dom == NODE_PART_POLICY:
+            return self._gpb._node_map[self._typ]
+        return self._gpb._edge_map[self._gpb._ekey(self._typ)]
 
     def get_part_size(self):
-        m = self._gpb._node_map["_N"] if self._dom == NODE_PART_POLICY else self._gpb._edge_map[self._gpb._ekey("_E")]
+        m = self._range_table()
         return int(m[self._gpb.partid, 1] - m[self._gpb.partid, 0])
 
     def get_size(self):
-        return self._gpb.num_nodes() if self._dom == NODE_PART_POLICY else self._gpb.num_edges()
+        m = self._range_table()
+        return int((m[:, 1] - m[:, 0]).sum())
 
 
 class KVServer:

@@ -176,11 +176,32 @@ GraphPartitionBook = RangePartitionBook
 def partition_graph(g, graph_name, num_parts, out_path, num_hops=1, part_method="metis", balance_ntypes=None,
                     balance_edges=False, return_mapping=False, num_trainers_per_machine=1, objtype="cut",
                     graph_formats=None, use_graphbolt=False, **kwargs):
-    """Partition a homogeneous graph into ``num_parts`` parts with ``num_hops`` of halo nodes and save the artifacts."""
-    if not g.is_homogeneous:
-        raise DGLError("partition_graph currently supports homogeneous graphs (use dgl.to_homogeneous first)")
+    """Partition a (hetero)graph into ``num_parts`` parts with ``num_hops`` of halo nodes and save the artifacts.
+
+    Heterographs follow the reference flow (python/dgl/distributed/partition.py:817-1400): the graph is homogenised with
+    its NTYPE / ETYPE recorded, the homogeneous nodes are assigned to partitions, and ids are reshuffled so that every
+    partition owns one contiguous range PER TYPE (the layout ``RangePartitionBook`` decodes: partition by partition, type
+    by type inside a partition). Features are written under type-prefixed keys (``ntype/name``, ``src:rel:dst/name``).
+    A partition holds its inner nodes, their ``num_hops``-hop in-neighbourhood as halo nodes, and exactly the in-edges of
+    the inner nodes and of the halo nodes closer than ``num_hops`` (no halo-to-outermost-halo edges)."""
+    from ..base import ETYPE, NTYPE
+    hetero = not g.is_homogeneous
     g = g.cpu() if g.device.type != "cpu" else g
-    n = g.num_nodes()
+    if hetero:
+        from ..convert import to_homogeneous
+        hg = to_homogeneous(g)
+        ntype_of, etype_of = hg.ndata[NTYPE].long(), hg.edata[ETYPE].long()
+        type_nid, type_eid = hg.ndata[NID].long(), hg.edata[EID].long()       # per-type original ids
+        ntypes, cets = list(g.ntypes), list(g.canonical_etypes)
+    else:
+        hg = g
+        ntype_of = torch.zeros(g.num_nodes(), dtype=torch.int64)
+        etype_of = torch.zeros(g.num_edges(), dtype=torch.int64)
+        type_nid, type_eid = torch.arange(g.num_nodes()), torch.arange(g.num_edges())
+        ntypes, cets = ["_N"], [("_N", "_E", "_N")]
+    T, R = len(ntypes), len(cets)
+    ekeys = [":".join(c) for c in cets]
+    n = hg.num_nodes()
     if kwargs.get("node_part") is not None:  # precomputed assignment (tools/dispatch_data.py, ParMETIS output)
         node_part = torch.as_tensor(kwargs["node_part"]).long()
         if node_part.shape[0] != n or int(node_part.max()) >= num_parts:
@@ -189,84 +210,104 @@ def partition_graph(g, graph_name, num_parts, out_path, num_hops=1, part_method=
     elif num_parts == 1:
         node_part = torch.zeros(n, dtype=torch.int64)
     elif part_method == "metis":
-        node_part = metis_partition_assignment(g, num_parts, balance_ntypes=balance_ntypes, balance_edges=balance_edges)
+        bal = balance_ntypes if balance_ntypes is not None or not hetero else None
+        node_part = metis_partition_assignment(hg, num_parts, balance_ntypes=bal, balance_edges=balance_edges)
     elif part_method == "random":
         node_part = torch.randint(0, num_parts, (n,))
     else:
         raise DGLError("Unknown partitioning method: " + part_method)
-    # reshuffle nodes: contiguous ranges per partition
-    order = torch.sort(node_part, stable=True)[1]
+    # ---- reshuffle: homogeneous ids ordered by (partition, type); edges by (partition of dst, type)
+    order = torch.sort(node_part * T + ntype_of, stable=True)[1]
     new_nid = torch.empty_like(order)
     new_nid[order] = torch.arange(n)
-    counts = torch.bincount(node_part, minlength=num_parts)
-    nstart = torch.cumsum(counts, 0) - counts
-    u, v = g.all_edges()
+    ncnt = torch.bincount(node_part * T + ntype_of, minlength=num_parts * T).reshape(num_parts, T)
+    pstart = torch.cumsum(ncnt.sum(1), 0) - ncnt.sum(1)                        # homogeneous start of every partition
+    u, v = hg.all_edges()
     nu, nv = new_nid[u.long()], new_nid[v.long()]
-    # an edge belongs to the partition owning its destination; reshuffle edge ids likewise
-    epart = node_part[v.long()]
-    eorder = torch.sort(epart, stable=True)[1]
+    epart = node_part[v.long()]                                                # an edge lives where its destination lives
+    eorder = torch.sort(epart * R + etype_of, stable=True)[1]
     new_eid = torch.empty_like(eorder)
     new_eid[eorder] = torch.arange(eorder.shape[0])
-    ecounts = torch.bincount(epart, minlength=num_parts)
-    estart = torch.cumsum(ecounts, 0) - ecounts
+    ecnt = torch.bincount(epart * R + etype_of, minlength=num_parts * R).reshape(num_parts, R)
+    epstart = torch.cumsum(ecnt.sum(1), 0) - ecnt.sum(1)
+
+    def per_type_ranges(cnt):
+        start = torch.cumsum(cnt, 0) - cnt                                     # [P, types]: start inside each type's id space
+        return [[[int(start[p, t]), int(start[p, t] + cnt[p, t])] for p in range(num_parts)] for t in range(cnt.shape[1])]
+
+    node_map = dict(zip(ntypes, per_type_ranges(ncnt)))
+    edge_map = dict(zip(ekeys, per_type_ranges(ecnt)))
     os.makedirs(out_path, exist_ok=True)
-    node_map = {"_N": [[int(nstart[i]), int(nstart[i] + counts[i])] for i in range(num_parts)]}
-    edge_map = {"_N:_E:_N": [[int(estart[i]), int(estart[i] + ecounts[i])] for i in range(num_parts)]}
-    meta = {"graph_name": graph_name, "num_nodes": n, "num_edges": g.num_edges(), "part_method": part_method,
+    meta = {"graph_name": graph_name, "num_nodes": n, "num_edges": hg.num_edges(), "part_method": part_method,
             "num_parts": num_parts, "halo_hops": num_hops, "node_map": node_map, "edge_map": edge_map,
-            "ntypes": {"_N": 0}, "etypes": {"_N:_E:_N": 0}}
-    part_of_new = node_part[order]  # partition of every new node id (sorted => monotone)
-    # adjacency in new ids for halo expansion
+            "ntypes": {t: i for i, t in enumerate(ntypes)}, "etypes": {k: i for i, k in enumerate(ekeys)}}
+    part_of_new = node_part[order]  # partition of every new node id (monotone)
+    ntype_new, etype_new_by_orig = ntype_of[order], etype_of
     gn = make_graph((nu, nv), num_nodes=n)
     for p in range(num_parts):
-        inner = torch.arange(int(nstart[p]), int(nstart[p] + counts[p]))
+        inner = torch.arange(int(pstart[p]), int(pstart[p] + ncnt[p].sum()))
         seen = torch.zeros(n, dtype=torch.bool)
         seen[inner] = True
+        dst_ok = seen.clone()                                                  # nodes whose in-edges are stored
         frontier, halo = inner, []
-        for _ in range(num_hops):
+        for hop in range(num_hops):
             src, _ = gn.in_edges(frontier)
             new = torch.unique(src)
             new = new[~seen[new]]
             seen[new] = True
             halo.append(new)
+            if hop < num_hops - 1:
+                dst_ok[new] = True
             frontier = new
             if new.numel() == 0:
                 break
         nodes = torch.cat([inner] + halo)  # inner nodes first => local ids of inner nodes = global - start
         local = torch.full((n,), -1, dtype=torch.int64)
         local[nodes] = torch.arange(nodes.shape[0])
-        # edges whose dst is inner (complete in-neighbourhood of inner nodes) + edges among halo nodes into halo
-        keep = seen[nu] & seen[nv]
+        keep = dst_ok[nv] & seen[nu]
         inner_e = keep & (part_of_new[nv] == p)
         ke = torch.nonzero(keep).squeeze(1)
-        # put inner edges first, ordered by new edge id
+        # inner edges first, ordered by new edge id
         is_inner = inner_e[ke]
         key = (~is_inner).long() * (int(new_eid.max()) + 1 if new_eid.numel() else 1) + new_eid[ke]
         ke = ke[torch.argsort(key)]
         pg = make_graph((local[nu[ke]], local[nv[ke]]), num_nodes=nodes.shape[0])
-        pg.ndata[NID] = nodes
-        pg.ndata["inner_node"] = (part_of_new[nodes] == p).to(torch.uint8)
-        pg.ndata["part_id"] = part_of_new[nodes]
-        pg.ndata["orig_id"] = order[nodes]
-        pg.edata[EID] = new_eid[ke]
-        pg.edata["inner_edge"] = inner_e[ke].to(torch.uint8)
-        pg.edata["orig_id"] = ke
+        ndata = {NID: nodes, "inner_node": (part_of_new[nodes] == p).to(torch.uint8), "part_id": part_of_new[nodes],
+                 "orig_id": order[nodes], NTYPE: ntype_new[nodes]}
+        edata = {EID: new_eid[ke], "inner_edge": inner_e[ke].to(torch.uint8), "orig_id": ke, ETYPE: etype_new_by_orig[ke]}
         pdir = os.path.join(out_path, f"part{p}")
         os.makedirs(pdir, exist_ok=True)
-        torch.save({"src": pg.edges()[0], "dst": pg.edges()[1], "num_nodes": pg.num_nodes(),
-                    "ndata": {k: pg.ndata[k] for k in (NID, "inner_node", "part_id", "orig_id")},
-                    "edata": {k: pg.edata[k] for k in (EID, "inner_edge", "orig_id")}}, os.path.join(pdir, "graph.pt"))
-        inner_orig = order[inner]
-        torch.save({f"_N/{k}": val[inner_orig] for k, val in g.ndata.items()}, os.path.join(pdir, "node_feat.pt"))
-        inner_eorig = eorder[int(estart[p]): int(estart[p] + ecounts[p])]
-        torch.save({f"_N:_E:_N/{k}": val[inner_eorig] for k, val in g.edata.items()}, os.path.join(pdir, "edge_feat.pt"))
+        torch.save({"src": pg.edges()[0], "dst": pg.edges()[1], "num_nodes": pg.num_nodes(), "ndata": ndata, "edata": edata},
+                   os.path.join(pdir, "graph.pt"))
+        nfeat, efeat = {}, {}
+        off = int(pstart[p])
+        for t, nt in enumerate(ntypes):                                        # inner nodes of type t, in new-id order
+            ids = type_nid[order[off: off + int(ncnt[p, t])]]
+            off += int(ncnt[p, t])
+            frame = g.nodes[nt].data if hetero else g.ndata
+            for k, val in frame.items():
+                nfeat[f"{nt}/{k}"] = val[ids]
+        off = int(epstart[p])
+        for r, cet in enumerate(cets):
+            ids = type_eid[eorder[off: off + int(ecnt[p, r])]]
+            off += int(ecnt[p, r])
+            frame = g.edges[cet].data if hetero else g.edata
+            for k, val in frame.items():
+                efeat[f"{ekeys[r]}/{k}"] = val[ids]
+        torch.save(nfeat, os.path.join(pdir, "node_feat.pt"))
+        torch.save(efeat, os.path.join(pdir, "edge_feat.pt"))
         meta[f"part-{p}"] = {"node_feats": f"part{p}/node_feat.pt", "edge_feats": f"part{p}/edge_feat.pt",
                              "part_graph": f"part{p}/graph.pt"}
     cfg = os.path.join(out_path, f"{graph_name}.json")
     with open(cfg, "w") as f:
         json.dump(meta, f, indent=2)
     if return_mapping:
-        return order, eorder
+        if not hetero:
+            return order, eorder
+        # per type: original per-type id of every new per-type id
+        nmap = {nt: type_nid[order[ntype_of[order] == t]] for t, nt in enumerate(ntypes)}
+        emap = {cet: type_eid[eorder[etype_of[eorder] == r]] for r, cet in enumerate(cets)}
+        return nmap, emap
     return None
 
 
@@ -283,14 +324,14 @@ def load_partition(part_config, part_id, load_feats=True, use_graphbolt=False):
         meta = json.load(f)
     base = os.path.dirname(part_config)
     info = meta[f"part-{part_id}"]
-    d = torch.load(os.path.join(base, info["part_graph"]), weights_only=False)
+    d = torch.load(os.path.join(base, info["part_graph"]), weights_only=True)
     g = make_graph((d["src"], d["dst"]), num_nodes=d["num_nodes"])
     for k, v in d["ndata"].items():
         g.ndata[k] = v
     for k, v in d["edata"].items():
         g.edata[k] = v
-    nf = torch.load(os.path.join(base, info["node_feats"]), weights_only=False) if load_feats else {}
-    ef = torch.load(os.path.join(base, info["edge_feats"]), weights_only=False) if load_feats else {}
+    nf = torch.load(os.path.join(base, info["node_feats"]), weights_only=True) if load_feats else {}
+    ef = torch.load(os.path.join(base, info["edge_feats"]), weights_only=True) if load_feats else {}
     gpb, name, ntypes, etypes = load_partition_book(part_config, part_id)
     return g, nf, ef, gpb, name, ntypes, etypes
 
@@ -300,8 +341,8 @@ def load_partition_feats(part_config, part_id, load_nodes=True, load_edges=True)
         meta = json.load(f)
     base = os.path.dirname(part_config)
     info = meta[f"part-{part_id}"]
-    nf = torch.load(os.path.join(base, info["node_feats"]), weights_only=False) if load_nodes else None
-    ef = torch.load(os.path.join(base, info["edge_feats"]), weights_only=False) if load_edges else None
+    nf = torch.load(os.path.join(base, info["node_feats"]), weights_only=True) if load_nodes else None
+    ef = torch.load(os.path.join(base, info["edge_feats"]), weights_only=True) if load_edges else None
     return nf, ef
 
 

@@ -193,3 +193,51 @@ def test_partition_to_graphbolt_conversion():
             assert fg.total_num_nodes == pg.num_nodes() and fg.total_num_edges == pg.num_edges()
             sub = fg.sample_neighbors(torch.arange(10), [3])
             assert int(sub.sampled_csc.indptr[-1]) <= 30
+
+
+def test_hetero_partition_round_trip(tmp_path):
+    """heterographs are partitioned with per-type contiguous ranges, type-prefixed feature keys and
+    canonical edge types in the metadata; the partition book's homogeneous <-> per-type maps agree with the artifacts."""
+    import json
+    from dgl_b200.base import ETYPE, NTYPE
+    from dgl_b200.distributed.kvstore import PartitionPolicy
+    from dgl_b200.distributed.partition import load_partition, partition_graph
+    torch.manual_seed(0)
+    nu, ni = 60, 40
+    g = dgl.heterograph({("user", "buys", "item"): (torch.randint(0, nu, (300,)), torch.randint(0, ni, (300,))),
+                         ("item", "bought_by", "user"): (torch.randint(0, ni, (300,)), torch.randint(0, nu, (300,))),
+                         ("user", "follows", "user"): (torch.randint(0, nu, (200,)), torch.randint(0, nu, (200,)))})
+    g.nodes["user"].data["x"] = torch.randn(nu, 3)
+    g.nodes["item"].data["x"] = torch.randn(ni, 5)
+    g.edges["buys"].data["w"] = torch.randn(300)
+    nmap, emap = partition_graph(g, "het", 3, str(tmp_path), num_hops=1, part_method="random", return_mapping=True)
+    cfg = str(tmp_path / "het.json")
+    meta = json.load(open(cfg))
+    assert set(meta["ntypes"]) == {"user", "item"}
+    assert set(meta["etypes"]) == {"user:buys:item", "item:bought_by:user", "user:follows:user"}
+    tot_inner = {"user": 0, "item": 0}
+    for p in range(3):
+        pg, nf, ef, gpb, name, ntypes, etypes = load_partition(cfg, p)
+        assert sorted(ntypes) == ["item", "user"] and not gpb.is_homogeneous()
+        inner = pg.ndata["inner_node"].bool()
+        homo_ids = pg.ndata[dgl.NID][inner]
+        tid, per_type = gpb.map_to_per_ntype(homo_ids)
+        names = sorted(meta["ntypes"], key=meta["ntypes"].get)
+        assert torch.equal(tid, pg.ndata[NTYPE][inner])                        # the book decodes the stored node types
+        for t, nt in enumerate(names):
+            ids = per_type[tid == t]
+            lo, hi = meta["node_map"][nt][p]
+            assert torch.equal(ids, torch.arange(lo, hi))                      # one contiguous range per type and partition
+            assert torch.equal(gpb.map_to_homo_nid(ids, nt), homo_ids[tid == t])
+            assert torch.equal(nf[f"{nt}/x"], g.nodes[nt].data["x"][nmap[nt][lo:hi]])
+            tot_inner[nt] += hi - lo
+            pol = PartitionPolicy(f"node:{nt}", gpb)
+            assert pol.get_part_size() == hi - lo and pol.get_size() == g.num_nodes(nt)
+        # every stored edge ends in an inner node (1 hop): no halo-to-halo edges
+        _, dst = pg.edges()
+        assert bool(inner[dst].all()) and bool(pg.edata["inner_edge"].bool().all())
+        lo, hi = meta["edge_map"]["user:buys:item"][p]
+        assert torch.equal(ef["user:buys:item/w"], g.edges["buys"].data["w"][emap[("user", "buys", "item")][lo:hi]])
+        et = pg.edata[ETYPE]
+        assert int((et == meta["etypes"]["user:buys:item"]).sum()) == hi - lo
+    assert tot_inner == {"user": nu, "item": ni}
