@@ -41,6 +41,9 @@ class NeighborSampler(SubgraphSampler):
         return self.graph.sample_neighbors(seeds, fanout, self.replace, self.prob_name)
 
     def _fast_usable(self, seeds):
+        from ...sampling.fused_blocks import ENABLED
+        if not ENABLED[0]:
+            return False
         g = self.graph
         if self.layer or self.replace or self.prob_name is not None or not self.deduplicate or not torch.is_tensor(seeds):
             return False

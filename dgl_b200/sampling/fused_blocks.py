@@ -39,7 +39,12 @@ def _csc_int32(g):
     return hit
 
 
+ENABLED = [__import__("os").environ.get("DGLB200_FUSED_SAMPLER", "1") != "0"]   # A/B switch
+
+
 def usable(g, fanouts, prob, replace, edge_dir, exclude_eids):
+    if not ENABLED[0]:
+        return False
     if not (g.device.type == "cuda" and len(g.canonical_etypes) == 1 and len(g.ntypes) == 1):
         return False
     if prob is not None or replace or edge_dir != "in" or exclude_eids is not None:

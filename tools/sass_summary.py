@@ -8,7 +8,8 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 so = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "dgl_b200", "lib", "libdglb200_cuda.so")
-CLASSES = [("UTCHMMA", r"UTC[A-Z]*MMA"), ("LDTM", r"LDTM"), ("UTMALDG", r"UTMALDG"), ("UTMASTG", r"UTMASTG"), ("UTCBAR", r"UTCBAR"),
+CLASSES = [("UTCHMMA", r"UTC[A-Z]*MMA"), ("LDTM", r"LDTM"), ("UTMALDG", r"UTMALDG"), ("UTMASTG", r"UTMASTG"), ("UBLKCP(bulk copy)", r"UBLKCP"), ("UTCBAR", r"UTCBAR"),
+           ("MULTIMEM", r"MULTIMEM|\.MMEM|LDGMC|REDGMC|STGMC"),
            ("SYNCS(mbarrier)", r"SYNCS"), ("LDGSTS(cp.async)", r"LDGSTS"), ("HMMA(legacy)", r"\bHMMA"), ("REDG", r"\bREDG"),
            ("ATOMG", r"\bATOMG"), ("ATOMS", r"\bATOMS"), ("SHFL", r"\bSHFL"), ("LDG.128", r"LDG\.E\.128|LDG\.E\.[A-Z.]*128"),
            ("STG.128", r"STG\.E\.128|STG\.E\.[A-Z.]*128"), ("MEMBAR/FENCE", r"MEMBAR|FENCE"), ("MUFU.EX2", r"MUFU\.EX2")]
