@@ -9,6 +9,7 @@
 // (/root/reference/src/array/cuda/spmm.cuh:413-732, spmm.cu:27-58) with one CSC family; no
 // descriptor creation, no workspace allocation, no host synchronisation per call.
 #include "common.cuh"
+#include "spmm_bulk.cuh"
 
 namespace dglb {
 
@@ -409,8 +410,11 @@ DGLB_API int dglb200_cuda_gspmm_balanced(int has_w, int dtype, int idtype, const
     const int vb = pick_vb_spmm((F / wH) * (int64_t)sizeof(T), x, out);
     DGLB_CHECK(vb != 0 && (F * (int64_t)sizeof(T)) % vb == 0, "feature rows must be 4-byte aligned for the balanced g-SpMM");
 #define RUN(VBV, HW)                                                                                              \
-    launch_vec<T, I, VBV, HW>((const I*)indptr, (const I*)indices, (const I*)eids, num_rows, (const T*)x,           \
-                              (const T*)w, (T*)out, F, st, max_deg, wH);                                            \
+    /* short rows: TMA-staged row gather when the row size allows it (spmm_bulk.cuh), else the SIMT vector kernel */ \
+    if (!(wH == 1 && bulk::launch<T, I, HW>((const I*)indptr, (const I*)indices, (const I*)eids, num_rows,          \
+                                            (const T*)x, (const T*)w, (T*)out, F, max_deg, st)))                    \
+      launch_vec<T, I, VBV, HW>((const I*)indptr, (const I*)indices, (const I*)eids, num_rows, (const T*)x,         \
+                                (const T*)w, (T*)out, F, st, max_deg, wH);                                          \
     if (num_items > 0) {                                                                                            \
       DGLB_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)n_long * F * sizeof(float), st));                         \
       launch_split<T, I, VBV, HW>((const I*)indices, (const I*)eids, (const int32_t*)item_ord,                      \

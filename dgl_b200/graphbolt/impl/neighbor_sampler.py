@@ -69,12 +69,12 @@ class NeighborSampler(SubgraphSampler):
         ip, ix = self._fast_csc
         idt = seeds.dtype
         subgraphs = []
+        from ..base import CSCFormatBase
         for layer in self._fast.sample_layers(ip, ix, seeds, uva=not ip.is_cuda):
-            ptr, idx, eids = self._fast.layer_to_csc(layer, idt)
-            from ..base import CSCFormatBase
-            sg = SampledSubgraphImpl(sampled_csc=CSCFormatBase(ptr, idx), original_column_node_ids=layer["dst"].to(idt),
-                                     original_row_node_ids=layer["src"].to(idt), original_edge_ids=eids)
-            sg._ell_cache = (layer["nbr"], layer["cnt"], layer["fanout"])
+            block, ptr, idx, eids = self._fast.layer_to_block(layer, idt, [("_N", "_E", "_N")], ["_N"])
+            sg = SampledSubgraphImpl(sampled_csc=CSCFormatBase(ptr, idx), original_column_node_ids=block.dstdata["_ID"],
+                                     original_row_node_ids=block.srcdata["_ID"], original_edge_ids=eids)
+            sg._block = block                 # MiniBatch.blocks hands this out as is (no re-validation of the structure)
             subgraphs.append(sg)
         return subgraphs[0].original_row_node_ids, subgraphs
 

@@ -137,6 +137,10 @@ class MiniBatch:
             from ..base import NID, EID
             blocks = []
             for sg in self.sampled_subgraphs:
+                ready = getattr(sg, "_block", None)
+                if ready is not None:                         # built by the one-sync sampler together with the subgraph
+                    blocks.append(ready)
+                    continue
                 rn, cn = sg.original_row_node_ids, sg.original_column_node_ids
                 if isinstance(sg.sampled_csc, dict):
                     data, nsrc, ndst = {}, {}, {}

@@ -61,45 +61,67 @@ class _FusedSAGETC(torch.autograd.Function):
     sage_bwd_da (input gradient whose epilogue scatters through the ELL block) - no cuBLAS call in either direction."""
 
     @staticmethod
-    def forward(ctx, x, w_self, w_neigh, bias, nbr, cnt, fan, relu):
+    def forward(ctx, x, w_self, w_neigh, bias, nbr, cnt, fan, relu, n_dev):
         n_dst = nbr.shape[0]
         F = x.shape[1]
         out_f = w_self.shape[0]
         Np = _np_pad(out_f)
         dev, dt = x.device, x.dtype
-        Wt = torch.zeros((Np, 2 * F), dtype=dt, device=dev)                      # [W_self | W_neigh], K-major
-        Wt[:out_f, :F] = w_self
-        Wt[:out_f, F:] = w_neigh
-        b_pad = torch.zeros(Np, dtype=torch.float32, device=dev)
-        if bias is not None:
-            b_pad[:out_f] = bias.float()
-        n_dev = torch.tensor([n_dst], dtype=torch.int64, device=dev)
-        planes = fused_ops.tf32_split(Wt) if dt == torch.float32 else (Wt, None)
+        # [W_self | W_neigh], K-major: one cat when the width needs no padding (few torch ops: this path is host-bound)
+        Wt = torch.cat((w_self, w_neigh), dim=1)
+        if Np != out_f:
+            Wt = torch.nn.functional.pad(Wt, (0, 0, 0, Np - out_f))
+        if bias is None:
+            b_pad = torch.zeros(Np, dtype=torch.float32, device=dev)
+        else:
+            b_pad = bias.float() if Np == out_f else torch.nn.functional.pad(bias.float(), (0, Np - out_f))
+        if n_dev is None:
+            n_dev = torch.tensor([n_dst], dtype=torch.int64, device=dev)
+        planes = fused_ops.tf32_split(Wt) if dt == torch.float32 else (Wt.contiguous(), None)
         out, A = fused_ops.sage_layer_tc(x, None, nbr, cnt, n_dev, planes[0], b_pad, relu=relu, save_A=True,
                                          Wt_lo=planes[1])                        # A = [x_self | mean x_nbr], kept for dW
-        ctx.save_for_backward(planes[0], planes[1] if planes[1] is not None else torch.empty(0), A, nbr, cnt, n_dev,
-                              out if relu else torch.empty(0))
+        ctx.save_for_backward(planes[0], planes[1] if planes[1] is not None else _EMPTY.get(dev), A, nbr, cnt, n_dev,
+                              out if relu else _EMPTY.get(dev))
         ctx.meta = (x.shape[0], F, out_f, Np, fan, relu, bias is not None)
-        return out[:, :out_f]
+        return out if Np == out_f else out[:, :out_f]
 
     @staticmethod
     def backward(ctx, dout):
         Wt, Wt_lo, A, nbr, cnt, n_dev, out = ctx.saved_tensors
         n_src, F, out_f, Np, fan, relu, has_bias = ctx.meta
-        n_dst = nbr.shape[0]
         dt = A.dtype
-        dZ = torch.zeros((n_dst, Np), dtype=dt, device=dout.device)
-        dZ[:, :out_f] = dout
+        dZ = dout.to(dt)
+        if Np != out_f:
+            dZ = torch.nn.functional.pad(dZ, (0, Np - out_f))
         if relu:
             dZ = dZ * (out > 0)
+        dZ = dZ.contiguous()
         # dWt [Np, 2F] = dZ^T A. The M side of the MMA must be a multiple of 128: A's columns (2F, F % 64 == 0) always are.
         dWt = torch.zeros((Np, 2 * F), dtype=torch.float32, device=dout.device)
         fused_ops.sage_bwd_dw(dWt, dZ, n_dev, P=A, transposed_out=True)
-        dX = torch.zeros((n_src, F), dtype=torch.float32, device=dout.device)
+        dX = None
         if ctx.needs_input_grad[0]:
+            dX = torch.zeros((n_src, F), dtype=torch.float32, device=dout.device)
             fused_ops.sage_bwd_da(dZ, Wt, nbr, cnt, n_dev, dX, Wt_lo=Wt_lo if Wt_lo.numel() else None)
+            dX = dX.to(dt)
         d_bias = dZ.float().sum(0)[:out_f] if has_bias else None
-        return (dX.to(dt), dWt[:out_f, :F].to(dt), dWt[:out_f, F:].to(dt), d_bias, None, None, None, None)
+        return (dX, dWt[:out_f, :F].to(dt), dWt[:out_f, F:].to(dt), d_bias, None, None, None, None, None)
+
+
+class _EmptyCache:
+    """One shared zero-length tensor per device (placeholders in save_for_backward)."""
+
+    def __init__(self):
+        self._t = {}
+
+    def get(self, dev):
+        t = self._t.get(dev)
+        if t is None:
+            t = self._t[dev] = torch.empty(0, device=dev)
+        return t
+
+
+_EMPTY = _EmptyCache()
 
 
 def usable(block, feat, out_feats, edge_weight):
@@ -128,4 +150,4 @@ def fused_sage_mean(block, x, w_self, w_neigh, bias, relu=False):
         ws = torch.nn.functional.pad(ws, (0, Fp - F))
         wn = torch.nn.functional.pad(wn, (0, Fp - F))
     with torch.autocast("cuda", enabled=False):
-        return _FusedSAGETC.apply(x.contiguous(), ws, wn, bias, nbr, cnt, fan, relu)
+        return _FusedSAGETC.apply(x.contiguous(), ws, wn, bias, nbr, cnt, fan, relu, getattr(block, "_n_dst_dev", None))

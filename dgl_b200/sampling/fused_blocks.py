@@ -136,7 +136,8 @@ class FusedBlockSampler:
             nd, ns = n_nodes[l], n_nodes[l - 1]
             dst = S[l][:nd].clone() if l == L else S[l][:nd]           # the seeds live in the reused workspace
             layers.append(dict(dst=dst, src=S[l - 1][:ns], nbr=nbr_local[l][:nd], cnt=ws.cnt[l][:nd].clone(), eid=ws.eid[l],
-                               fanout=self.fanouts[l - 1], n_dst=nd, n_src=ns, n_edges=n_edges[l]))
+                               fanout=self.fanouts[l - 1], n_dst=nd, n_src=ns, n_edges=n_edges[l],
+                               n_dst_dev=ws.n[l].clone()))
         return layers
 
     @staticmethod
@@ -153,19 +154,24 @@ class FusedBlockSampler:
             _p(eids), _p(eid_map), loader.stream_ptr())
         return ptr64.to(idtype), idx, eids
 
-    def __call__(self, g, seeds):
-        idt = g.idtype
-        indptr, indices, csc_eids = _csc_int32(g)
-        blocks = []
-        for layer in self.sample_layers(indptr, indices, seeds):
-            ptr, idx, eids = self.layer_to_csc(layer, idt, csc_eids)
-            ug = UnitGraph.from_csc(layer["n_src"], layer["n_dst"], ptr, idx)
-            block = DGLBlock([ug], None, g.canonical_etypes, [layer["n_src"], layer["n_dst"]], srctypes=list(g.ntypes),
-                             dsttypes=list(g.ntypes))
-            block.srcdata[NID] = layer["src"].to(idt)
-            block.dstdata[NID] = layer["dst"].to(idt)
+    @staticmethod
+    def layer_to_block(layer, idtype, canonical_etypes, ntypes, eid_map=None, want_eids=True):
+        """DGLBlock of one sampled layer, built without any validation pass (sizes and ids are known to be consistent),
+        carrying its ELL form and the device-side destination count for the fused SAGE layer."""
+        ptr, idx, eids = FusedBlockSampler.layer_to_csc(layer, idtype, eid_map, want_eids)
+        ug = UnitGraph.from_csc(layer["n_src"], layer["n_dst"], ptr, idx)
+        block = DGLBlock([ug], None, list(canonical_etypes), [layer["n_src"], layer["n_dst"]], srctypes=list(ntypes),
+                         dsttypes=list(ntypes))
+        block.srcdata[NID] = layer["src"].to(idtype)
+        block.dstdata[NID] = layer["dst"].to(idtype)
+        if eids is not None:
             block.edata[EID] = eids
-            # the dense ELL form of the same block (rows = destination nodes): consumed by nn/fused_sage.py
-            block._ell_cache = (layer["nbr"], layer["cnt"], layer["fanout"])
-            blocks.append(block)
+        block._ell_cache = (layer["nbr"], layer["cnt"], layer["fanout"])
+        block._n_dst_dev = layer["n_dst_dev"]
+        return block, ptr, idx, eids
+
+    def __call__(self, g, seeds):
+        indptr, indices, csc_eids = _csc_int32(g)
+        blocks = [self.layer_to_block(layer, g.idtype, g.canonical_etypes, g.ntypes, csc_eids)[0]
+                  for layer in self.sample_layers(indptr, indices, seeds)]
         return blocks[0].srcdata[NID], blocks[-1].dstdata[NID], blocks

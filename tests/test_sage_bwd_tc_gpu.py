@@ -135,7 +135,7 @@ def test_fused_sageconv_autograd_tc(dt):
     ws = (torch.randn(O, F, device=DEV) * 0.1).to(dt).requires_grad_(True)
     wn = (torch.randn(O, F, device=DEV) * 0.1).to(dt).requires_grad_(True)
     b = torch.randn(O, device=DEV, requires_grad=True)
-    out = fused_sage._FusedSAGETC.apply(x, ws, wn, b, nbr, cnt, fan, True)
+    out = fused_sage._FusedSAGETC.apply(x, ws, wn, b, nbr, cnt, fan, True, None)
     gout = torch.randn_like(out)
     out.backward(gout)
     torch.cuda.synchronize()

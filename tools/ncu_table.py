@@ -16,7 +16,13 @@ COLS = [("time [us]", "gpu__time_duration.sum", 1e-3), ("grid", "launch__grid_si
         ("DRAM wr [MB]", "dram__bytes_write.sum", 1e-6), ("L2 hit %", "lts__t_sector_hit_rate.pct", 1),
         ("L1 hit %", "l1tex__t_sector_hit_rate.pct", 1), ("SM %", "sm__throughput.avg.pct_of_peak_sustained_elapsed", 1),
         ("tensor %", "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", 1)]
-UNIT_SCALE = {"nsecond": 1.0, "usecond": 1e3, "msecond": 1e6, "second": 1e9, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+UNIT_SCALE = {"nsecond": 1.0, "ns": 1.0, "usecond": 1e3, "us": 1e3, "msecond": 1e6, "ms": 1e6, "second": 1e9, "s": 1e9,
+              "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def unit_scale(u):
+    """ncu prints e.g. 'us', 'Mbyte', 'Kbyte/block', 'byte/second' - scale by the numerator's prefix."""
+    return UNIT_SCALE.get(u.split("/")[0].strip(), 1.0)
 
 
 def main():
@@ -40,7 +46,7 @@ def main():
             if i is None or r[i] in ("", "n/a"):
                 vals[label] = None
                 continue
-            x = float(r[i].replace(",", "")) * UNIT_SCALE.get(units[i], 1.0)
+            x = float(r[i].replace(",", "")) * unit_scale(units[i])
             vals[label] = x * scale
         t_us = vals["time [us]"] or 0.0
         rd, wr = vals["DRAM rd [MB]"] or 0.0, vals["DRAM wr [MB]"] or 0.0
