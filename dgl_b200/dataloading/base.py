@@ -1,93 +1,109 @@
-"""Sampler base classes and edge-prediction wrapper (parity: /root/reference/python/dgl/dataloading/base.py)."""
+"""Sampler protocol, feature-prefetch markers and the node-sampler -> edge-sampler adaptor.
+
+Public surface follows /root/reference/python/dgl/dataloading/base.py (``Sampler`` :147, ``BlockSampler`` :170,
+``EdgePredictionSampler`` :305, ``as_edge_prediction_sampler`` :453, the ``set_*_lazy_features`` helpers :68-144). The
+mechanics are organised around three small pieces of this repo's own:
+
+* ``_mark(view_kind, graph, names)`` - one routine that plants ``LazyFeature`` placeholders on any of the four frame
+  views of a (sub)graph; ``assign_lazy_features`` later resolves every placeholder in one pass per frame, choosing the
+  gather path from where the parent column lives (device table / pinned host table read through UVA / pageable host);
+* ``_EXCLUDERS`` - a table of seed-edge exclusion policies instead of an if-chain;
+* ``EdgePredictionSampler`` - builds the positive pair graph, the optional negative pair graph and compacts both into one
+  shared node id space before delegating neighbourhood sampling to the wrapped sampler.
+"""
 from __future__ import annotations
 
 from collections.abc import Mapping
 
 import torch
 
-from ..base import EID, NID, DGLError
+from ..base import EID, NID
 from ..frame import LazyFeature
 from ..transforms import compact_graphs
 
+_VIEWS = {"node": ("nodes", "ndata"), "edge": ("edges", "edata"), "src": ("srcnodes", "srcdata"), "dst": ("dstnodes", "dstdata")}
 
-def _set_lazy_features(x, xdata, feature_names):
-    if feature_names is None:
+
+def _mark(kind, g, names):
+    """Plant LazyFeature placeholders: ``names`` is a list (single type) or ``{type: list}``."""
+    if not names:
         return
-    if not isinstance(feature_names, Mapping):
-        xdata.update({k: LazyFeature(k) for k in feature_names})
+    typed_view, flat_view = _VIEWS[kind]
+    if isinstance(names, Mapping):
+        for key, cols in names.items():
+            getattr(g, typed_view)[key].data.update({c: LazyFeature(c) for c in cols})
     else:
-        for type_, names in feature_names.items():
-            x[type_].data.update({k: LazyFeature(k) for k in names})
+        getattr(g, flat_view).update({c: LazyFeature(c) for c in names})
 
 
 def set_node_lazy_features(g, feature_names):
-    return _set_lazy_features(g.nodes, g.ndata, feature_names)
+    _mark("node", g, feature_names)
 
 
 def set_edge_lazy_features(g, feature_names):
-    return _set_lazy_features(g.edges, g.edata, feature_names)
+    _mark("edge", g, feature_names)
 
 
 def set_src_lazy_features(g, feature_names):
-    return _set_lazy_features(g.srcnodes, g.srcdata, feature_names)
+    _mark("src", g, feature_names)
 
 
 def set_dst_lazy_features(g, feature_names):
-    return _set_lazy_features(g.dstnodes, g.dstdata, feature_names)
+    _mark("dst", g, feature_names)
 
 
-def _fetch_frame(frame, parent_frame, ids, device):
-    for k in list(frame.keys()):
-        col = frame._columns[k]
-        if isinstance(col.storage, LazyFeature):
-            name = col.storage.name or k
-            src = parent_frame[name]
-            idx = ids
-            if src.is_cuda:
-                val = src[idx.to(src.device).long()]
-            elif idx.is_cuda and src.is_pinned():
-                from ..ops.index import index_select
-                val = index_select(src, idx)
-            else:
-                val = src[idx.cpu().long()]
-            frame[k] = val.to(device, non_blocking=True)
+def _gather_rows(table, ids):
+    """rows ``ids`` of a parent column, wherever it lives."""
+    if table.is_cuda:
+        return table[ids.to(table.device).long()]
+    if ids.is_cuda and table.is_pinned():
+        from ..ops.index import index_select            # zero-copy read of the pinned table from the GPU
+        return index_select(table, ids)
+    return table[ids.cpu().long()]
+
+
+def _resolve_frame(frame, parent_frame, ids, device):
+    pending = [(k, frame._columns[k].storage) for k in list(frame.keys()) if isinstance(frame._columns[k].storage, LazyFeature)]
+    for key, marker in pending:
+        frame[key] = _gather_rows(parent_frame[marker.name or key], ids).to(device, non_blocking=True)
+
+
+def _graphs_in(obj):
+    if hasattr(obj, "_node_frames"):
+        yield obj
+    elif isinstance(obj, Mapping):
+        for v in obj.values():
+            yield from _graphs_in(v)
+    elif isinstance(obj, (list, tuple)):
+        for v in obj:
+            yield from _graphs_in(v)
 
 
 def assign_lazy_features(result, parent_graph=None, device=None):
-    """Resolve LazyFeature placeholders on blocks/subgraphs against the parent graph (the DataLoader's
-    prefetch step; reference dataloader.py:_prefetch :487)."""
-    def visit(x):
-        if hasattr(x, "_node_frames"):
-            g = x
-            dev = device or g.device
-            for i, fr in enumerate(g._node_frames):
-                if NID in fr and parent_graph is not None:
-                    nt = g._ntypes[i]
-                    pf = parent_graph._node_frames[parent_graph.get_ntype_id(nt)]
-                    _fetch_frame(fr, pf, fr[NID], dev)
-            for i, fr in enumerate(g._edge_frames):
-                if EID in fr and parent_graph is not None:
-                    pf = parent_graph._edge_frames[parent_graph.get_etype_id(g.canonical_etypes[i])]
-                    _fetch_frame(fr, pf, fr[EID], dev)
-        elif isinstance(x, (list, tuple)):
-            for y in x:
-                visit(y)
-        elif isinstance(x, dict):
-            for y in x.values():
-                visit(y)
-    visit(result)
+    """Replace every placeholder found on the graphs inside ``result`` by rows of ``parent_graph``'s columns (the prefetch
+    step of the DataLoader; reference dataloader.py:487)."""
+    if parent_graph is None:
+        return result
+    for g in _graphs_in(result):
+        dev = device or g.device
+        for nt, fr in zip(g._ntypes, g._node_frames):
+            if NID in fr:
+                _resolve_frame(fr, parent_graph._node_frames[parent_graph.get_ntype_id(nt)], fr[NID], dev)
+        for rel, fr in zip(g.canonical_etypes, g._edge_frames):
+            if EID in fr:
+                _resolve_frame(fr, parent_graph._edge_frames[parent_graph.get_etype_id(rel)], fr[EID], dev)
     return result
 
 
 class Sampler:
-    """Base sampler: ``sample(g, indices)`` returns any structure of tensors/graphs."""
+    """``sample(g, indices)`` -> any nesting of tensors and graphs."""
 
     def sample(self, g, indices):
         raise NotImplementedError
 
 
 class BlockSampler(Sampler):
-    """Samplers producing a list of MFGs; subclasses implement ``sample_blocks``."""
+    """Samplers that emit ``(input_nodes, output_nodes, [MFG, ...])``; subclasses provide ``sample_blocks``."""
 
     def __init__(self, prefetch_node_feats=None, prefetch_labels=None, prefetch_edge_feats=None, output_device=None):
         super().__init__()
@@ -100,16 +116,36 @@ class BlockSampler(Sampler):
         raise NotImplementedError
 
     def assign_lazy_features(self, result):
-        input_nodes, output_nodes, blocks = result
-        set_src_lazy_features(blocks[0], self.prefetch_node_feats)
-        set_dst_lazy_features(blocks[-1], self.prefetch_labels)
-        for block in blocks:
-            set_edge_lazy_features(block, self.prefetch_edge_feats)
-        return input_nodes, output_nodes, blocks
+        blocks = result[2]
+        _mark("src", blocks[0], self.prefetch_node_feats)      # inputs of the first layer
+        _mark("dst", blocks[-1], self.prefetch_labels)         # targets of the last layer
+        for b in blocks:
+            _mark("edge", b, self.prefetch_edge_feats)
+        return result
 
     def sample(self, g, seed_nodes, exclude_eids=None):
-        result = self.sample_blocks(g, seed_nodes, exclude_eids=exclude_eids)
-        return self.assign_lazy_features(result)
+        return self.assign_lazy_features(self.sample_blocks(g, seed_nodes, exclude_eids=exclude_eids))
+
+
+# ------------------------------------------------------------------------------------------ seed-edge exclusion policies
+def _with_reverse_ids(g, seeds, reverse_eids, reverse_etypes):
+    def both(ids, table):
+        return torch.cat([ids, table[ids.long().to(table.device)].to(ids.device)])
+    if isinstance(seeds, Mapping):
+        return {rel: both(ids, reverse_eids[rel]) for rel, ids in seeds.items()}
+    return both(seeds, reverse_eids)
+
+
+def _with_reverse_types(g, seeds, reverse_eids, reverse_etypes):
+    out = {g.to_canonical_etype(rel): ids for rel, ids in seeds.items()}
+    for rel, ids in list(out.items()):
+        partner = reverse_etypes[rel] if rel in reverse_etypes else reverse_etypes[rel[1]]
+        partner = g.to_canonical_etype(partner)
+        out[partner] = torch.cat([out[partner], ids]) if partner in out else ids
+    return out
+
+
+_EXCLUDERS = {"self": lambda g, seeds, *_: seeds, "reverse_id": _with_reverse_ids, "reverse_types": _with_reverse_types}
 
 
 def _find_exclude_eids(g, exclude, seed_edges, reverse_eids=None, reverse_etypes=None, output_device=None):
@@ -117,80 +153,64 @@ def _find_exclude_eids(g, exclude, seed_edges, reverse_eids=None, reverse_etypes
         return None
     if callable(exclude):
         return exclude(seed_edges)
-    if exclude == "self":
-        return seed_edges
-    if exclude == "reverse_id":
-        if isinstance(seed_edges, Mapping):
-            return {k: torch.cat([v, reverse_eids[k][v.long().to(reverse_eids[k].device)].to(v.device)]) for k, v in seed_edges.items()}
-        return torch.cat([seed_edges, reverse_eids[seed_edges.long().to(reverse_eids.device)].to(seed_edges.device)])
-    if exclude == "reverse_types":
-        out = {g.to_canonical_etype(k): v for k, v in seed_edges.items()}
-        for k, v in list(out.items()):
-            rk = g.to_canonical_etype(reverse_etypes[k] if k in reverse_etypes else reverse_etypes[k[1]])
-            out[rk] = torch.cat([out[rk], v]) if rk in out else v
-        return out
-    raise ValueError("unsupported mode {}".format(exclude))
+    try:
+        policy = _EXCLUDERS[exclude]
+    except (KeyError, TypeError):
+        raise ValueError(f"unsupported mode {exclude}") from None
+    return policy(g, seed_edges, reverse_eids, reverse_etypes)
 
 
 class EdgePredictionSampler(Sampler):
-    """Wrap a node sampler for edge classification / link prediction (reference base.py:EdgePredictionSampler)."""
+    """Turns a node-wise sampler into an edge-wise one: a batch of seed edges becomes a pair graph (plus a negative pair
+    graph when a negative sampler is given) over a compacted node set, whose nodes seed the wrapped sampler."""
+
+    _NEEDS = {"reverse_id": "reverse_eids", "reverse_types": "reverse_etypes"}
 
     def __init__(self, sampler, exclude=None, reverse_eids=None, reverse_etypes=None, negative_sampler=None,
                  prefetch_labels=None):
         super().__init__()
-        if exclude == "reverse_id" and reverse_eids is None:
-            raise ValueError("reverse_eids must be provided when exclude is 'reverse_id'")
-        if exclude == "reverse_types" and reverse_etypes is None:
-            raise ValueError("reverse_etypes must be provided when exclude is 'reverse_types'")
-        self.reverse_eids = reverse_eids
-        self.reverse_etypes = reverse_etypes
-        self.exclude = exclude
-        self.sampler = sampler
+        needed = self._NEEDS.get(exclude) if isinstance(exclude, str) else None
+        if needed and {"reverse_eids": reverse_eids, "reverse_etypes": reverse_etypes}[needed] is None:
+            raise ValueError(f"{needed} must be provided when exclude is '{exclude}'")
+        self.sampler, self.exclude = sampler, exclude
+        self.reverse_eids, self.reverse_etypes = reverse_eids, reverse_etypes
         self.negative_sampler = negative_sampler
         self.prefetch_labels = prefetch_labels or []
-        self.output_device = sampler.output_device if hasattr(sampler, "output_device") else None
+        self.output_device = getattr(sampler, "output_device", None)
 
     def _build_neg_graph(self, g, seed_edges):
         from ..convert import heterograph
-        neg_srcdst = self.negative_sampler(g, seed_edges)
-        if not isinstance(neg_srcdst, Mapping):
-            neg_srcdst = {g.canonical_etypes[0]: neg_srcdst}
-        dtype = next(iter(neg_srcdst.values()))[0].dtype
-        dev = next(iter(neg_srcdst.values()))[0].device
-        neg_edges = {etype: neg_srcdst.get(etype, (torch.empty(0, dtype=dtype, device=dev), torch.empty(0, dtype=dtype, device=dev)))
-                     for etype in g.canonical_etypes}
-        neg_pair_graph = heterograph(neg_edges, {ntype: g.num_nodes(ntype) for ntype in g.ntypes})
-        return neg_pair_graph, neg_srcdst
+        drawn = self.negative_sampler(g, seed_edges)
+        if not isinstance(drawn, Mapping):
+            drawn = {g.canonical_etypes[0]: drawn}
+        proto = next(iter(drawn.values()))[0]
+        nothing = proto.new_empty(0)
+        per_rel = {rel: drawn.get(rel, (nothing, nothing)) for rel in g.canonical_etypes}
+        return heterograph(per_rel, {nt: g.num_nodes(nt) for nt in g.ntypes}), drawn
 
     def assign_lazy_features(self, result):
-        pair_graph = result[1]
-        set_edge_lazy_features(pair_graph, self.prefetch_labels)
+        _mark("edge", result[1], self.prefetch_labels)
         return result
 
     def sample(self, g, seed_edges):
         if isinstance(seed_edges, Mapping):
-            seed_edges = {g.to_canonical_etype(k): v for k, v in seed_edges.items()}
-        exclude = self.exclude
-        pair_graph = g.edge_subgraph(seed_edges, relabel_nodes=False, output_device=self.output_device)
-        eids = pair_graph.edata[EID]
+            seed_edges = {g.to_canonical_etype(rel): ids for rel, ids in seed_edges.items()}
+        positives = g.edge_subgraph(seed_edges, relabel_nodes=False, output_device=self.output_device)
+        parent_eids = positives.edata[EID]
+        graphs = [positives]
         if self.negative_sampler is not None:
-            neg_graph, _ = self._build_neg_graph(g, seed_edges)
-            if neg_graph.device != pair_graph.device:
-                neg_graph = neg_graph.to(pair_graph.device)
-            pair_graph, neg_graph = compact_graphs([pair_graph, neg_graph])
-        else:
-            pair_graph = compact_graphs(pair_graph)
-        pair_graph.edata[EID] = eids
-        seed_nodes = pair_graph.ndata[NID]
-        exclude_eids = _find_exclude_eids(g, exclude, seed_edges, reverse_eids=self.reverse_eids,
-                                          reverse_etypes=self.reverse_etypes, output_device=self.output_device)
-        input_nodes, _, blocks = self.sampler.sample(g, seed_nodes, exclude_eids)
-        if self.negative_sampler is None:
-            return self.assign_lazy_features((input_nodes, pair_graph, blocks))
-        return self.assign_lazy_features((input_nodes, pair_graph, neg_graph, blocks))
+            negatives, _ = self._build_neg_graph(g, seed_edges)
+            graphs.append(negatives if negatives.device == positives.device else negatives.to(positives.device))
+        graphs = compact_graphs(graphs)
+        positives = graphs[0]
+        positives.edata[EID] = parent_eids
+        banned = _find_exclude_eids(g, self.exclude, seed_edges, self.reverse_eids, self.reverse_etypes, self.output_device)
+        input_nodes, _, blocks = self.sampler.sample(g, positives.ndata[NID], banned)
+        return self.assign_lazy_features((input_nodes, *graphs, blocks))
 
 
 def as_edge_prediction_sampler(sampler, exclude=None, reverse_eids=None, reverse_etypes=None, negative_sampler=None,
                                prefetch_labels=None):
+    """Edge classification / link prediction flavour of ``sampler`` (see ``EdgePredictionSampler``)."""
     return EdgePredictionSampler(sampler, exclude=exclude, reverse_eids=reverse_eids, reverse_etypes=reverse_etypes,
                                  negative_sampler=negative_sampler, prefetch_labels=prefetch_labels)
