@@ -90,10 +90,13 @@ class TorchBasedFeature(Feature):
 
 
 class DiskBasedFeature(Feature):
-    """Feature stored in a ``.npy`` file; rows are fetched with parallel preads (csrc/cpu/diskio.cc), the
-    counterpart of the reference's io_uring OnDiskNpyArray (graphbolt/src/cnumpy.cc)."""
+    """Feature stored in a ``.npy`` file. Rows are fetched through io_uring rings driven by raw syscalls
+    (csrc/cpu/uring.cc: one ring per worker thread, ``queue_depth`` reads in flight each, short reads resumed) - the
+    counterpart of the reference's OnDiskNpyArray (graphbolt/src/cnumpy.cc:146-330) - and through an OpenMP team of
+    ``pread`` calls (csrc/cpu/diskio.cc) where the kernel or the container's seccomp profile refuses io_uring.
+    ``io_backend``: "auto" (io_uring when available; env ``DGLB200_DISK_IO`` overrides), "uring" or "pread"."""
 
-    def __init__(self, path, metadata=None, num_threads=None):
+    def __init__(self, path, metadata=None, num_threads=None, io_backend="auto", queue_depth=128):
         self._path = path
         self._metadata = metadata or {}
         arr = np.load(path, mmap_mode="r")
@@ -109,6 +112,23 @@ class DiskBasedFeature(Feature):
         self._lib.fn("dglb200_disk_open", "sp")(path.encode(), ctypes.addressof(fd))
         self._fd = fd.value
         self._threads = num_threads or 0
+        self._queue_depth = int(queue_depth)
+        self.io_backend = self._pick_backend(io_backend)
+
+    def _pick_backend(self, wanted):
+        import os
+        wanted = os.environ.get("DGLB200_DISK_IO", wanted) if wanted == "auto" else wanted
+        if wanted not in ("auto", "uring", "pread"):
+            raise DGLError(f"unknown io_backend {wanted!r}")
+        if wanted == "pread":
+            return "pread"
+        ok, why = ctypes.c_int(), ctypes.c_int()
+        self._lib.fn("dglb200_uring_available", "pp")(ctypes.addressof(ok), ctypes.addressof(why))
+        if ok.value:
+            return "uring"
+        if wanted == "uring":
+            raise DGLError(f"io_uring is not available to this process: {os.strerror(why.value)}")
+        return "pread"
 
     def __del__(self):
         try:
@@ -124,8 +144,14 @@ class DiskBasedFeature(Feature):
         out = torch.empty((idx.shape[0],) + self._shape[1:], dtype=self._dtype)
         if dev.type == "cuda":
             out = out.pin_memory()
-        self._lib.fn("dglb200_disk_read_rows", "lllplpi")(self._fd, self._offset, self._row_bytes, idx.data_ptr(),
-                                                          idx.shape[0], out.data_ptr(), self._threads)
+        if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self._shape[0]):
+            raise DGLError(f"row index out of range for a feature with {self._shape[0]} rows")
+        if self.io_backend == "uring":
+            self._lib.fn("dglb200_disk_read_rows_uring", "lllplpii")(self._fd, self._offset, self._row_bytes, idx.data_ptr(),
+                                                                    idx.shape[0], out.data_ptr(), self._threads, self._queue_depth)
+        else:
+            self._lib.fn("dglb200_disk_read_rows", "lllplpi")(self._fd, self._offset, self._row_bytes, idx.data_ptr(),
+                                                              idx.shape[0], out.data_ptr(), self._threads)
         return out.to(dev, non_blocking=True) if dev.type == "cuda" else out
 
     def to(self, device):

@@ -178,3 +178,40 @@ def test_file_helpers(tmp_path):
     with open(os.path.join(ds, "x.txt"), "w") as f:
         f.write("2")
     assert check_dataset_change(ds, "preprocessed")
+
+
+# ----------------------------------------------------------------------------------------------- disk-backed features
+@pytest.mark.parametrize("backend", ["uring", "pread"])
+@pytest.mark.parametrize("dtype,width", [(np.float32, 37), (np.int64, 4), (np.float16, 1031)])
+def test_disk_based_feature_backends(tmp_path, backend, dtype, width):
+    import dgl_b200.graphbolt as gb
+    from dgl_b200.base import DGLError
+    rng = np.random.default_rng(0)
+    table = (rng.random((5000, width)) * 100).astype(dtype)
+    path = str(tmp_path / "feat.npy")
+    np.save(path, table)
+    try:
+        feat = gb.DiskBasedFeature(path, io_backend=backend, queue_depth=16, num_threads=3)
+    except DGLError as e:
+        assert backend == "uring" and "io_uring" in str(e)
+        pytest.skip("io_uring is not permitted in this environment")
+    assert feat.io_backend == backend
+    ids = torch.from_numpy(rng.integers(0, 5000, 3000))          # duplicates, unsorted, more rows than queue slots
+    got = feat.read(ids)
+    assert got.dtype == torch.from_numpy(table[:1]).dtype and tuple(got.shape) == (3000, width)
+    assert np.array_equal(got.numpy(), table[ids.numpy()])
+    assert feat.read(torch.tensor([], dtype=torch.int64)).shape == (0, width)
+    assert np.array_equal(feat.read().numpy(), table)
+    with pytest.raises(DGLError):
+        feat.read(torch.tensor([5000]))
+    assert feat.count() == 5000 and tuple(feat.size()) == (width,)
+
+
+def test_disk_based_feature_auto_backend_env(tmp_path, monkeypatch):
+    import dgl_b200.graphbolt as gb
+    path = str(tmp_path / "f.npy")
+    np.save(path, np.arange(40, dtype=np.float32).reshape(10, 4))
+    monkeypatch.setenv("DGLB200_DISK_IO", "pread")
+    assert gb.DiskBasedFeature(path).io_backend == "pread"
+    monkeypatch.delenv("DGLB200_DISK_IO")
+    assert gb.DiskBasedFeature(path).io_backend in ("uring", "pread")
