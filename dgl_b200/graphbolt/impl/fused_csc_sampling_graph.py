@@ -177,39 +177,50 @@ class FusedCSCSamplingGraph:
             results[et] = (src, cnt, eid_map.to(eid.device)[eid.long()])
         return self._convert(seeds, results)
 
+    def _temporal(self, seeds, seeds_timestamp, fanouts, replace, window, probs_name, node_attr, edge_attr, layer_seed=None):
+        from .temporal import temporal_sample
+        fan = torch.as_tensor(fanouts).reshape(-1).tolist()
+        node_ts = self.node_attributes[node_attr] if node_attr else None
+        edge_ts = self.edge_attributes[edge_attr] if edge_attr else None
+        probs = self.edge_attributes[probs_name] if probs_name else None
+        idx = self.indices
+        if self.node_type_offset is None:
+            src, cnt, pos = temporal_sample(self.csc_indptr, idx, seeds, seeds_timestamp, fan[0], replace, window, node_ts,
+                                            edge_ts, probs, None, layer_seed)
+            return self._convert(seeds, {None: (src, cnt, pos)})
+        if not isinstance(seeds, dict):
+            raise DGLError("heterogeneous graph: seeds, seeds_timestamp (and the time window) must be dicts keyed by node type")
+        if len(fan) == 1:
+            fan = fan * len(self.edge_type_to_id)
+        off = self.node_type_offset
+        results = {}
+        for et, tid in self.edge_type_to_id.items():
+            _, _, d = etype_str_to_tuple(et)
+            if d not in seeds or fan[tid] == 0:
+                continue
+            g_seeds = seeds[d] + int(off[self.node_type_to_id[d]])
+            win = None if window is None else window[d]
+            results[et] = temporal_sample(self.csc_indptr, idx, g_seeds, seeds_timestamp[d], fan[tid], replace, win, node_ts,
+                                          edge_ts, probs, self.type_per_edge == tid, layer_seed)
+        return self._convert(seeds, results)
+
     def temporal_sample_neighbors(self, seeds, seeds_timestamp, fanouts, replace=False, seeds_pre_time_window=None,
                                   probs_name=None, node_timestamp_attr_name=None, edge_timestamp_attr_name=None):
-        """Neighbour sampling restricted to neighbours/edges older than the seed timestamp."""
-        if self.node_type_offset is not None:
-            raise NotImplementedError("temporal sampling on hetero graphs is not implemented")
-        ug = self._unit()
-        indptr, indices, _ = ug.csc()
-        s = indptr[seeds.long()].long()
-        deg = indptr[seeds.long() + 1].long() - s
-        pos = torch.repeat_interleave(s, deg) + (torch.arange(int(deg.sum()), device=s.device) - torch.repeat_interleave(torch.cumsum(deg, 0) - deg, deg))
-        owner = torch.repeat_interleave(torch.arange(seeds.shape[0], device=s.device), deg)
-        ok = torch.ones(pos.shape[0], dtype=torch.bool, device=s.device)
-        ts = seeds_timestamp[owner]
-        if node_timestamp_attr_name:
-            ok &= self.node_attributes[node_timestamp_attr_name][indices[pos].long()] < ts
-        if edge_timestamp_attr_name:
-            ok &= self.edge_attributes[edge_timestamp_attr_name][pos] < ts
-        prob = ok.float()
-        if probs_name:
-            prob = prob * self.edge_attributes[probs_name][pos].float()
-        full = torch.zeros(indices.shape[0], dtype=torch.float32, device=s.device)
-        full[pos] = prob
-        k = int(torch.as_tensor(fanouts).reshape(-1)[0])
-        src, dst, eid, cnt = sample_rel(ug, seeds, k, "in", full, replace, return_counts=True)
-        return self._convert(seeds, {None: (src, cnt, eid)})
+        """Neighbour sampling restricted to sources / edges strictly older than the seed's timestamp (and not older than
+        ``seeds_pre_time_window`` before it). Homogeneous: tensors; typed graphs: dicts keyed by node type, per-edge-type
+        fan-outs. Node timestamps are indexed by homogenised node id (impl/temporal.py)."""
+        return self._temporal(seeds, seeds_timestamp, fanouts, replace, seeds_pre_time_window, probs_name,
+                              node_timestamp_attr_name, edge_timestamp_attr_name)
 
     def temporal_sample_layer_neighbors(self, seeds, seeds_timestamp, fanouts, replace=False, seeds_pre_time_window=None,
                                         probs_name=None, node_timestamp_attr_name=None, edge_timestamp_attr_name=None,
                                         random_seed=None, seed2_contribution=0.0):
-        """Temporal LABOR-style layer sampling (reference fused_csc_sampling_graph.py temporal_sample_layer_neighbors): the
-        temporal constraint is applied as an edge mask, the per-seed sampler draws from the surviving edges."""
-        return self.temporal_sample_neighbors(seeds, seeds_timestamp, fanouts, replace, seeds_pre_time_window, probs_name,
-                                              node_timestamp_attr_name, edge_timestamp_attr_name)
+        """Temporal layer sampling: as above, but a source vertex carries one variate shared by all seeds (and all edge
+        types) of the call, so overlapping neighbourhoods pick overlapping sources (LABOR coupling)."""
+        from ... import random as dgl_random
+        rs = dgl_random.next_seed() if random_seed is None else int(torch.as_tensor(random_seed).reshape(-1)[0])
+        return self._temporal(seeds, seeds_timestamp, fanouts, replace, seeds_pre_time_window, probs_name,
+                              node_timestamp_attr_name, edge_timestamp_attr_name, layer_seed=rs)
 
     def sample_negative_edges_uniform(self, edge_type, node_pairs, negative_ratio):
         """For every positive (src, dst) pair draw ``negative_ratio`` random destinations of the right node type; returns
