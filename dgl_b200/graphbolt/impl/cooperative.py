@@ -32,39 +32,122 @@ def rank_sort(ids, rank, world_size, seed=0):
     return ids[perm], perm, offsets
 
 
-class CooperativeConvFunction(torch.autograd.Function):
-    """h_needed = exchange(h_owned): forward all-to-all of hidden rows, backward the reverse all-to-all."""
+def _world(group):
+    if not dist.is_available() or not dist.is_initialized():
+        return 1, 0
+    return dist.get_world_size(group), dist.get_rank(group)
+
+
+class ExchangePlan:
+    """Routing of a rank's id list to the ranks that own those ids, reusable for any number of row transfers.
+
+    ``route(ids)`` sorts the ids by owner, tells every peer how many ids it will get (one all-to-all of counts), ships the
+    ids (one all-to-all of ids) and deduplicates what arrived: ``owned`` are the distinct ids this rank is responsible for
+    in this round and ``recv_to_owned`` maps every received request to its row in ``owned``. ``pull(h_owned)`` then returns
+    the rows of this rank's ORIGINAL id list (one all-to-all of rows, differentiable: the backward pushes the gradients
+    back and accumulates duplicates on the owner). The reference spreads the same protocol over four datapipe stages
+    (python/dgl/graphbolt/subgraph_sampler.py:199-310, impl/neighbor_sampler.py cooperative branches)."""
+
+    def __init__(self, sort_perm, send_counts, recv_counts, owned, recv_to_owned, group):
+        self.sort_perm, self.send_counts, self.recv_counts = sort_perm, send_counts, recv_counts
+        self.owned, self.recv_to_owned, self.group = owned, recv_to_owned, group
 
     @staticmethod
-    def forward(ctx, counts_sent, counts_received, seed_inverse_ids, h):
-        ctx.counts_sent, ctx.counts_received = counts_sent, counts_received
-        ctx.seed_inverse_ids = seed_inverse_ids
-        ctx.n_in = h.shape[0]
-        if not dist.is_initialized() or dist.get_world_size() == 1:
-            return h[seed_inverse_ids]
-        out = h.new_empty((sum(counts_received),) + h.shape[1:])
-        dist.all_to_all_single(out, h, counts_received, counts_sent)
-        return out[seed_inverse_ids]
+    def route(ids, group=None, seed=0):
+        world, rank = _world(group)
+        if world == 1:
+            owned, inverse = torch.unique(ids, return_inverse=True)
+            n = ids.shape[0]
+            return ExchangePlan(torch.arange(n, device=ids.device), [n], [n], owned, inverse, group)
+        sorted_ids, perm, offsets = rank_sort(ids, rank, world, seed)
+        send = (offsets[1:] - offsets[:-1]).to(torch.int64)
+        recv = torch.empty_like(send)
+        dist.all_to_all_single(recv, send, group=group)
+        send_counts, recv_counts = send.tolist(), recv.tolist()
+        got = sorted_ids.new_empty(sum(recv_counts))
+        dist.all_to_all_single(got, sorted_ids.contiguous(), recv_counts, send_counts, group=group)
+        owned, inverse = torch.unique(got, return_inverse=True)
+        return ExchangePlan(perm, send_counts, recv_counts, owned, inverse, group)
+
+    @property
+    def num_requested(self):
+        return self.sort_perm.shape[0]
+
+    def pull(self, h_owned):
+        """rows of ``h_owned`` (aligned with ``self.owned``) for this rank's original ids, in their original order."""
+        return _PullRows.apply(h_owned, self)
+
+
+class _PullRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h_owned, plan):
+        ctx.plan, ctx.n_owned = plan, h_owned.shape[0]
+        staged = h_owned[plan.recv_to_owned]                          # one row per received request, requester-major
+        world, _ = _world(plan.group)
+        if world == 1:
+            arrived = staged
+        else:
+            arrived = staged.new_empty((sum(plan.send_counts),) + tuple(staged.shape[1:]))
+            dist.all_to_all_single(arrived, staged.contiguous(), plan.send_counts, plan.recv_counts, group=plan.group)
+        out = torch.empty_like(arrived)
+        out[plan.sort_perm] = arrived                                 # undo the owner sort
+        return out
 
     @staticmethod
-    def backward(ctx, grad_output):
-        g = torch.zeros((max(int(ctx.seed_inverse_ids.max()) + 1 if ctx.seed_inverse_ids.numel() else 0, 0),) + grad_output.shape[1:],
-                        dtype=grad_output.dtype, device=grad_output.device)
-        g.index_add_(0, ctx.seed_inverse_ids, grad_output)
-        if not dist.is_initialized() or dist.get_world_size() == 1:
-            out = torch.zeros((ctx.n_in,) + grad_output.shape[1:], dtype=g.dtype, device=g.device)
-            out[: g.shape[0]] = g
-            return None, None, None, out
-        out = g.new_empty((sum(ctx.counts_sent),) + g.shape[1:])
-        dist.all_to_all_single(out, g, ctx.counts_sent, ctx.counts_received)
-        return None, None, None, out
+    def backward(ctx, grad):
+        plan = ctx.plan
+        outgoing = grad[plan.sort_perm].contiguous()
+        world, _ = _world(plan.group)
+        if world == 1:
+            landed = outgoing
+        else:
+            landed = outgoing.new_empty((sum(plan.recv_counts),) + tuple(outgoing.shape[1:]))
+            dist.all_to_all_single(landed, outgoing, plan.recv_counts, plan.send_counts, group=plan.group)
+        g = landed.new_zeros((ctx.n_owned,) + tuple(landed.shape[1:]))
+        g.index_add_(0, plan.recv_to_owned, landed)
+        return g, None
+
+
+def cooperative_sample(sample_layer, seeds, num_layers, group=None, seed=0):
+    """Cooperative multi-layer sampling. ``sample_layer(owned_ids, hop) -> CSCFormatBase`` samples the in-neighbours
+    (global ids) of the ids this rank owns. Returns ``(input_nodes, layers, out_plan)``:
+
+    * ``out_plan``  - routes the caller's seeds to their owners; ``out_plan.pull(h_last)`` fetches the final rows;
+    * ``layers[i]`` - ``dict(csc=compacted CSC, dst=owned ids (columns), src=needed ids (rows; dst is its prefix),
+      plan=ExchangePlan of src)``; before applying layer i the model calls ``plan.pull(h)`` to obtain the rows of ``src``
+      from their owners, the layer then produces rows aligned with ``dst``;
+    * ``input_nodes`` - ids whose input features this rank must load (= ``layers[0]['plan'].owned``).
+
+    Every vertex is expanded by exactly one rank per layer, so neighbourhoods shared between ranks are sampled, fetched and
+    computed once instead of once per rank."""
+    from ..utils import unique_and_compact_csc_formats
+    out_plan = ExchangePlan.route(seeds, group, seed)
+    owned = out_plan.owned
+    layers = []
+    for hop in reversed(range(num_layers)):
+        csc = sample_layer(owned, hop)
+        needed, compacted = unique_and_compact_csc_formats(csc, owned)
+        plan = ExchangePlan.route(needed, group, seed)
+        layers.insert(0, dict(csc=compacted, dst=owned, src=needed, plan=plan))
+        owned = plan.owned
+    return owned, layers, out_plan
+
+
+class CooperativeConvFunction:
+    """Functional form kept for API compatibility: ``apply(subgraph, h)`` pulls the rows the subgraph's sources need."""
+
+    @staticmethod
+    def apply(subgraph, h):
+        return subgraph._plan.pull(h)
 
 
 class CooperativeConv(torch.nn.Module):
+    """``forward(subgraph, h)``: ``h`` holds this rank's owned rows for the layer; returns the rows of the subgraph's source
+    nodes, fetched from their owners (reference python/dgl/graphbolt/impl/cooperative_conv.py:27-93)."""
+
     def forward(self, subgraph, h):
-        return CooperativeConvFunction.apply(getattr(subgraph, "_counts_sent", [h.shape[0]]),
-                                             getattr(subgraph, "_counts_received", [h.shape[0]]),
-                                             getattr(subgraph, "_seed_inverse_ids", torch.arange(h.shape[0], device=h.device)), h)
+        plan = getattr(subgraph, "_plan", None)
+        return h if plan is None else plan.pull(h)
 
 
 class _P2PExchange(torch.autograd.Function):

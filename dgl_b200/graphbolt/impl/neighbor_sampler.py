@@ -25,6 +25,7 @@ class NeighborSampler(SubgraphSampler):
         self.layer = layer
         self.batch_dependency = batch_dependency
         self.layer_dependency = layer_dependency
+        self.cooperative = bool(cooperative)
         self._cnt = 0
         self._fast = None
 
@@ -78,9 +79,37 @@ class NeighborSampler(SubgraphSampler):
             subgraphs.append(sg)
         return subgraphs[0].original_row_node_ids, subgraphs
 
+    def _sample_cooperative(self, seeds):
+        """All ranks sample together: every vertex of every frontier is expanded by the one rank that owns it (hash
+        partition of the id space); see impl/cooperative.py. The minibatch's input nodes are this rank's OWNED inputs and
+        each subgraph carries the exchange plan ``CooperativeConv`` uses to fetch the rows of its source nodes."""
+        from .cooperative import cooperative_sample
+        if not torch.is_tensor(seeds) or self.graph.node_type_offset is not None:
+            from ...base import DGLError
+            raise DGLError("cooperative minibatching is implemented for homogeneous graphs")
+        inputs, layers, out_plan = cooperative_sample(
+            lambda owned, hop: self._sample_one(owned, self.fanouts[hop], hop).sampled_csc, seeds, len(self.fanouts))
+        subgraphs = []
+        for lay in layers:
+            sg = SampledSubgraphImpl(sampled_csc=lay["csc"], original_column_node_ids=lay["dst"], original_row_node_ids=lay["src"])
+            plan = lay["plan"]
+            sg._plan = plan
+            sg._counts_sent, sg._counts_received, sg._seed_inverse_ids = plan.send_counts, plan.recv_counts, plan.recv_to_owned
+            subgraphs.append(sg)
+        self._out_plan = out_plan
+        return inputs, subgraphs
+
+    def _sample(self, minibatch):
+        minibatch = super()._sample(minibatch)
+        if self.cooperative:
+            minibatch._out_plan = self._out_plan          # routes the model output back to the ranks that asked for it
+        return minibatch
+
     def sample_subgraphs(self, seeds, seeds_timestamp=None):
         subgraphs = []
         self._cnt += 1
+        if self.cooperative:
+            return self._sample_cooperative(seeds)
         if self._fast_usable(seeds):
             return self._sample_fast(seeds)
         for hop in reversed(range(len(self.fanouts))):
@@ -117,6 +146,7 @@ class TemporalNeighborSampler(SubgraphSampler):
         self.fanouts = [torch.as_tensor(f).reshape(-1) for f in fanouts]
         self.replace, self.prob_name = replace, prob_name
         self.node_ts, self.edge_ts = node_timestamp_attr_name, edge_timestamp_attr_name
+        self.layer = layer
 
     def _sample(self, minibatch):
         seeds = minibatch.seeds
@@ -138,8 +168,8 @@ class TemporalNeighborSampler(SubgraphSampler):
         subgraphs = []
         ts = seeds_timestamp
         for hop in reversed(range(len(self.fanouts))):
-            sg = self.graph.temporal_sample_neighbors(seeds, ts, self.fanouts[hop], self.replace, None, self.prob_name,
-                                                      self.node_ts, self.edge_ts)
+            pick = self.graph.temporal_sample_layer_neighbors if self.layer else self.graph.temporal_sample_neighbors
+            sg = pick(seeds, ts, self.fanouts[hop], self.replace, None, self.prob_name, self.node_ts, self.edge_ts)
             csc = sg.sampled_csc
             deg = (csc.indptr[1:] - csc.indptr[:-1]).long()
             rows, compacted = compact_csc_format(csc, seeds)
@@ -151,7 +181,13 @@ class TemporalNeighborSampler(SubgraphSampler):
 
 
 class TemporalLayerNeighborSampler(TemporalNeighborSampler):
-    """Layer-wise (LABOR-style) variant; the temporal constraint dominates, so it shares the per-seed sampler."""
+    """Layer-wise variant: source vertices carry one shared variate per call (impl/temporal.py), so overlapping temporal
+    neighbourhoods select overlapping sources."""
+
+    def __init__(self, datapipe, graph, fanouts, replace=False, prob_name=None, node_timestamp_attr_name=None,
+                 edge_timestamp_attr_name=None):
+        super().__init__(datapipe, graph, fanouts, replace, prob_name, node_timestamp_attr_name, edge_timestamp_attr_name,
+                         layer=True)
 
 
 _COMPAT_NAMES = ("NeighborSamplerImpl", "SamplePerLayer", "CompactPerLayer", "FetchInsubgraphData",
