@@ -454,12 +454,21 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="disable CUDA-graph replay (debug)")
     ap.add_argument("--no-tc", action="store_true", help="use the unfused cuBLAS layer path (A/B debug)")
     ap.add_argument("--no-epoch", dest="epoch", action="store_false", help="skip the measured full epoch")
+    ap.add_argument("--mode", default="minibatch", choices=["minibatch", "partitioned"],
+                    help="minibatch (default): the headline sampled-training step; partitioned: full-graph SAGE on a "
+                         "vertex-partitioned graph (benchmarks/bench_partitioned.py), one step = one epoch")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         print(json.dumps({"impl": args.impl, "unavailable": "no CUDA device"}))
         return
     try:
-        if args.impl == "reference":
+        if args.mode == "partitioned":
+            sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "benchmarks"))
+            import bench_partitioned
+            if args.steps == 100 and args.warmup == 10:       # the headline defaults are too long for whole-graph epochs
+                args.steps, args.warmup = 10, 3
+            bench_partitioned.run(args)
+        elif args.impl == "reference":
             run_reference(args)
         else:
             run_ours(args)

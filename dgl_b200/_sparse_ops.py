@@ -212,9 +212,48 @@ def _prep_single(op, ufeat, efeat):
     return None, x2, shp, F, 1, (1, 1, 1, F)
 
 
-def gsddmm(coo, op, lhs, rhs, lhs_target="u", rhs_target="v"):
+def _dst_sorted_view(gidx):
+    """(src, dst, eids|None) of the relation in destination-sorted (CSC) order, if the CSC already exists: walking the edges
+    in this order makes consecutive edges share their destination row (L1 hits instead of a second random gather)."""
+    if gidx is None or getattr(gidx, "_csc", None) is None:
+        return None
+    cache = gidx._degs
+    hit = cache.get("csc_coo")
+    if hit is None:
+        indptr, indices, eids = gidx._csc
+        deg = (indptr[1:] - indptr[:-1]).long()
+        dst = torch.repeat_interleave(torch.arange(gidx.num_dst, dtype=indices.dtype, device=indices.device), deg,
+                                      output_size=int(indices.shape[0]))
+        hit = cache["csc_coo"] = (indices, dst, eids)
+    return hit
+
+
+def _dot_fast_path(gidx, row, col, lhs2, rhs2, out, lt, rt, F, rsz, bc):
+    """staged tensor-free dot kernel (csrc/cuda/sddmm.cu sddmm_dot_staged_kernel); returns False if the shape is not covered."""
+    es = lhs2.element_size()
+    if es > 4 or tuple(bc) != (1, F, 1, F) or lhs2.dtype != rhs2.dtype:
+        return False
+    if F == 1:
+        if (rsz * es) % 4 or lhs2.data_ptr() % 4 or rhs2.data_ptr() % 4:
+            return False
+    else:
+        vec = 16 // es
+        lph = rsz // vec
+        if rsz % vec or lhs2.data_ptr() % 16 or rhs2.data_ptr() % 16 or lph > 32 or lph & (lph - 1) or F * lph > 1024:
+            return False
+    perm = None
+    view = _dst_sorted_view(gidx) if (lt != 1 and rt != 1) else None
+    if view is not None:
+        row, col, perm = view
+    loader.cuda_lib().fn("dglb200_cuda_sddmm_dot", "iippplpppiillp")(
+        dtype_code(lhs2.dtype), id_code(row.dtype), _p(row), _p(col), _p(perm), row.shape[0], _p(lhs2), _p(rhs2), _p(out),
+        lt, rt, F, rsz, loader.stream_ptr())
+    return True
+
+
+def gsddmm(coo, op, lhs, rhs, lhs_target="u", rhs_target="v", gidx=None):
     """out[e] = op(lhs[target_l(e)], rhs[target_r(e)]) in edge-id order.
-    ``coo`` = (row, col) giving (src, dst) per edge id."""
+    ``coo`` = (row, col) giving (src, dst) per edge id; ``gidx`` (optional) lets the kernel pick a better edge order."""
     row, col = coo
     E = row.shape[0]
     use_l = op != "copy_rhs"
@@ -230,11 +269,14 @@ def gsddmm(coo, op, lhs, rhs, lhs_target="u", rhs_target="v"):
             # rows that are not a multiple of 16 bytes (e.g. 41 classes) would force scalar loads on E * rsz elements:
             # zero-pad the reduce dimension of the (much smaller) node operands once and take the vector kernels
             vec = 16 // ref.element_size()
-            if rsz % vec and rsz > vec and E >= 4 * max(l2.shape[0], r2.shape[0]):
+            if (rsz * ref.element_size()) % 4 and rsz > vec and E >= 4 * max(l2.shape[0], r2.shape[0]):
                 pad = vec - rsz % vec
                 l2 = torch.nn.functional.pad(l2.view(l2.shape[0], F, rsz), (0, pad)).reshape(l2.shape[0], -1)
                 r2 = torch.nn.functional.pad(r2.view(r2.shape[0], F, rsz), (0, pad)).reshape(r2.shape[0], -1)
                 rsz += pad
+        if is_cuda and op == "dot" and _dot_fast_path(gidx, row, col, l2, r2, out, TARGETS[lhs_target], TARGETS[rhs_target],
+                                                      F, rsz, bc):
+            return out.reshape(E, *out_shape)
         args = [OPS[op], dtype_code(ref.dtype), id_code(row.dtype), _p(row), _p(col), E, _p(l2), _p(r2), _p(out),
                 TARGETS[lhs_target], TARGETS[rhs_target], F, rsz, *bc]
         if is_cuda:

@@ -264,9 +264,165 @@ __global__ void __launch_bounds__(256) sddmm_dot1_vec_kernel(const I* __restrict
   }
 }
 
+
+// Dot product per edge with the edge endpoints staged through the warp.
+//
+// A warp owns chunks of 32 consecutive edges. Each lane loads the endpoints of ONE edge of the chunk (two coalesced
+// 128-byte index loads per 32 edges, the runtime target selection runs once per lane) and the sub-groups of the warp then
+// walk the chunk U edges at a time, pulling "their" endpoints out of the staging registers with a shuffle. The feature
+// rows are read with 16-byte loads (sub lanes per edge, U edges in flight per group) exactly like sddmm_dot_edge_kernel,
+// but nothing in the inner loop waits on an index load any more - in that kernel the 2 x U dependent endpoint loads
+// (branchy runtime `sel`) serialised in front of the row loads and it ran at 36 % occupancy / 34 % SM throughput; ncu
+// shows the reference's one-edge-per-warp kernel (src/array/cuda/sddmm.cuh:146-196) at 84 %.
+//  * SINGLE (one output per edge): the row may be any multiple of 16 bytes; results are transposed back into lane order
+//    and leave as ONE coalesced store per 32 edges (or a scatter through `perm`).
+//  * multi-head: lph lanes per head (power of two), heads written by their leader lanes.
+// `perm` (optional) maps the processing order to the output position: the caller passes the edges in destination-sorted
+// (CSC) order so that consecutive edges re-read the same destination row out of L1, and scatters to edge-id order.
+template <int VB> struct VecOf;
+template <> struct VecOf<16> { using type = uint4; };
+template <> struct VecOf<8> { using type = uint2; };
+template <> struct VecOf<4> { using type = uint32_t; };
+
+template <typename T, typename I, int U, bool SINGLE, int VB>
+__global__ void __launch_bounds__(256) sddmm_dot_staged_kernel(const I* __restrict__ row, const I* __restrict__ col,
+                                                               const I* __restrict__ perm, int64_t E,
+                                                               const T* __restrict__ lhs, const T* __restrict__ rhs,
+                                                               T* __restrict__ out, int lt, int rt, int H, int lph,
+                                                               int sub, int nvec) {
+  using V = typename VecOf<VB>::type;
+  constexpr int VEC = VB / sizeof(T);
+  const int lane = threadIdx.x & 31;
+  const int gps = 32 / sub;                    // edge groups per warp
+  const int g = lane / sub, gl = lane % sub;   // my group, my lane inside it
+  const int64_t row_elems = (int64_t)nvec * VEC;
+  const int64_t nwarps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t base = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 32; base < E; base += nwarps * 32) {
+    const int64_t my_e = base + lane;
+    const bool mine = my_e < E;
+    const int64_t li = mine ? sel<I>(lt, row, col, my_e) : 0;
+    const int64_t ri = mine ? sel<I>(rt, row, col, my_e) : 0;
+    float res = 0.f;
+    for (int k0 = 0; k0 < 32; k0 += gps * U) {
+      if (base + k0 >= E) break;               // warp-uniform
+      const V* lp[U];
+      const V* rp[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int slot = (k0 + u * gps + g) & 31;
+        lp[u] = reinterpret_cast<const V*>(lhs + __shfl_sync(0xffffffffu, li, slot) * row_elems);
+        rp[u] = reinterpret_cast<const V*>(rhs + __shfl_sync(0xffffffffu, ri, slot) * row_elems);
+      }
+      float acc[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) acc[u] = 0.f;
+      // multi-head: every lane of the warp runs the same number of iterations (the head reduction shuffles inside)
+      const int jend = SINGLE ? nvec : (nvec + sub - 1) / sub * sub;
+      for (int j = gl; j < jend; j += sub) {
+        V a[U], b[U];
+        const bool live = SINGLE || j < nvec;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          a[u] = live ? __ldg(lp[u] + j) : V{};
+          b[u] = live ? __ldg(rp[u] + j) : V{};
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const T* av = reinterpret_cast<const T*>(&a[u]);
+          const T* bv = reinterpret_cast<const T*>(&b[u]);
+          float part = 0.f;
+#pragma unroll
+          for (int q = 0; q < VEC; ++q) part = fmaf(to_f<T>(av[q]), to_f<T>(bv[q]), part);
+          if (SINGLE) {
+            acc[u] += part;
+          } else {
+            for (int o = lph >> 1; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+            const int64_t e = base + k0 + u * gps + g;
+            if (live && (j & (lph - 1)) == 0 && e < E) out[(perm ? (int64_t)perm[e] : e) * H + j / lph] = from_f<T>(part);
+          }
+        }
+      }
+      if (SINGLE) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          for (int o = sub >> 1; o > 0; o >>= 1) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+          // hand the result of slot s to lane s: lane L listens to group (L % gps), which worked on slot k0 + u*gps + L % gps
+          const float v = __shfl_sync(0xffffffffu, acc[u], (lane % gps) * sub);
+          if (k0 + u * gps + (lane % gps) == lane) res = v;
+        }
+      }
+    }
+    if (SINGLE && mine) out[perm ? (int64_t)perm[my_e] : my_e] = from_f<T>(res);
+  }
+}
+
 }  // namespace dglb
 
 using namespace dglb;
+
+static int sddmm_dot_unroll() {
+  static const int u = [] {
+    const char* e = std::getenv("DGLB200_SDDMM_U");
+    const int v = e ? std::atoi(e) : 4;
+    return (v == 2 || v == 4) ? v : 4;
+  }();
+  return u;
+}
+
+template <typename T, typename I>
+static void launch_dot_staged(const void* row, const void* col, const void* perm, int64_t E, const void* lhs, const void* rhs,
+                              void* out, int lt, int rt, int64_t H, int64_t rsz, cudaStream_t st) {
+  DGLB_CHECK(sizeof(T) <= 4, "sddmm_dot: fp64 goes through the generic kernel");
+  const int64_t row_bytes = H * rsz * (int64_t)sizeof(T);
+  const uintptr_t mis = (uintptr_t)lhs | (uintptr_t)rhs;
+  // widest vector that divides a row (and, for heads, a head) and matches the table alignment
+  const int64_t unit = (H > 1 ? rsz : H * rsz) * (int64_t)sizeof(T);
+  int vb = 16;
+  while (vb > 4 && (unit % vb || mis % vb)) vb >>= 1;
+  DGLB_CHECK(unit % vb == 0 && mis % vb == 0 && vb >= (int)sizeof(T), "sddmm_dot: rows must be a multiple of 4 bytes");
+  const int64_t lph64 = rsz * (int64_t)sizeof(T) / vb;   // vectors per head
+  const int64_t nvec = row_bytes / vb;
+  DGLB_CHECK(H == 1 || (vb == 16 && lph64 <= 32 && (lph64 & (lph64 - 1)) == 0), "sddmm_dot: per-head size must be 16 B x 2^k");
+  int sub = 1;
+  while (sub < nvec && sub < 32) sub <<= 1;
+  if (H > 1 && sub < lph64) sub = (int)lph64;
+  const int64_t chunks = (E + 31) / 32;
+  int64_t blocks = (chunks + 7) / 8;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  auto go = [&](auto kern) {
+    kern<<<(unsigned)blocks, 256, 0, st>>>((const I*)row, (const I*)col, (const I*)perm, E, (const T*)lhs, (const T*)rhs,
+                                          (T*)out, lt, rt, (int)H, (int)lph64, sub, (int)nvec);
+  };
+  const bool wide = sddmm_dot_unroll() >= 4;
+  if (H > 1) {
+    if (wide) go(sddmm_dot_staged_kernel<T, I, 4, false, 16>); else go(sddmm_dot_staged_kernel<T, I, 2, false, 16>);
+  } else if (vb == 16) {
+    if (wide) go(sddmm_dot_staged_kernel<T, I, 4, true, 16>); else go(sddmm_dot_staged_kernel<T, I, 2, true, 16>);
+  } else if (vb == 8) {
+    if (wide) go(sddmm_dot_staged_kernel<T, I, 4, true, 8>); else go(sddmm_dot_staged_kernel<T, I, 2, true, 8>);
+  } else {
+    if (wide) go(sddmm_dot_staged_kernel<T, I, 4, true, 4>); else go(sddmm_dot_staged_kernel<T, I, 2, true, 4>);
+  }
+}
+
+// out[perm[e]] (or out[e]) = <lhs[sel_l(e)], rhs[sel_r(e)]> per head. H heads of rsz elements, rows of H * rsz elements
+// H == 1: any row that is a multiple of 4 bytes (16 / 8 / 4-byte loads are picked from the row size and the table
+// alignment); H > 1: rsz * sizeof(T) / 16 a power of two <= 32.
+DGLB_API int dglb200_cuda_sddmm_dot(int dtype, int idtype, const void* row, const void* col, const void* perm, int64_t E,
+                                    const void* lhs, const void* rhs, void* out, int lt, int rt, int64_t H, int64_t rsz,
+                                    void* stream) {
+  DGLB_TRY
+  cudaStream_t st = (cudaStream_t)stream;
+  if (E == 0) return 0;
+  DGLB_ID_SWITCH(idtype, I, {
+    if (dtype == kF32) launch_dot_staged<float, I>(row, col, perm, E, lhs, rhs, out, lt, rt, H, rsz, st);
+    else if (dtype == kBF16) launch_dot_staged<__nv_bfloat16, I>(row, col, perm, E, lhs, rhs, out, lt, rt, H, rsz, st);
+    else if (dtype == kF16) launch_dot_staged<__half, I>(row, col, perm, E, lhs, rhs, out, lt, rt, H, rsz, st);
+    else throw std::runtime_error("sddmm_dot: unsupported dtype");
+  });
+  DGLB_LAUNCH_CHECK();
+  DGLB_CATCH
+}
 
 DGLB_API int dglb200_cuda_gsddmm(int op, int dtype, int idtype, const void* row, const void* col, int64_t E,
                                  const void* lhs, const void* rhs, void* out, int lt, int rt, int64_t F, int64_t rsz,

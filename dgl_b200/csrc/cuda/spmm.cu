@@ -56,7 +56,7 @@ __device__ __forceinline__ V ldg_vec(const V* p) {
 }
 
 // sub lanes cooperate on one row; each lane owns NV vectors per column tile.
-template <typename T, typename I, int VB, int NV, bool HAS_W>
+template <typename T, typename I, int VB, int NV, int HAS_W>  // HAS_W: 0 none, 1 one scalar per edge, 2 one per head
 __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ indptr, const I* __restrict__ indices,
                                                        const I* __restrict__ eids, int64_t num_rows,
                                                        const T* __restrict__ x, const T* __restrict__ w,
@@ -85,13 +85,14 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ ind
   int64_t p = s;
   for (; p + U <= t; p += U) {
     int64_t u[U];
-    float wt[U][NV];
+    constexpr int NW = HAS_W == 2 ? NV : 1;  // a scalar weight is shared by all vectors of the lane
+    float wt[U][NW];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       u[k] = indices[p + k];
       const int64_t eidx = (eids ? (int64_t)eids[p + k] : p + k) * wH;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) wt[k][j] = HAS_W ? to_f<T>(w[eidx + hd[j]]) : 1.f;
+      for (int j = 0; j < NW; ++j) wt[k][j] = HAS_W ? to_f<T>(w[eidx + (HAS_W == 2 ? hd[j] : 0)]) : 1.f;
     }
     V v[U][NV];
 #pragma unroll
@@ -107,7 +108,7 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ ind
     for (int k = 0; k < U; ++k)
 #pragma unroll
       for (int j = 0; j < NV; ++j)
-        if (vbase + j * sub < nvec) VO::fma(acc[j], v[k][j], wt[k][j]);
+        if (vbase + j * sub < nvec) VO::fma(acc[j], v[k][j], wt[k][HAS_W == 2 ? j : 0]);
   }
   for (; p < t; ++p) {
     const int64_t u = indices[p];
@@ -118,7 +119,7 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ ind
       const int c = vbase + j * sub;
       if (c < nvec) {
         V v = ldg_vec(xr + c);
-        VO::fma(acc[j], v, HAS_W ? to_f<T>(w[eidx + hd[j]]) : 1.f);
+        VO::fma(acc[j], v, HAS_W ? to_f<T>(w[eidx + (HAS_W == 2 ? hd[j] : 0)]) : 1.f);
       }
     }
   }
@@ -179,7 +180,7 @@ static int pow2_ge(int64_t x, int cap) {
   return p;
 }
 
-template <typename T, typename I, int VB, bool HAS_W>
+template <typename T, typename I, int VB, int HAS_W>
 void launch_vec(const I* indptr, const I* indices, const I* eids, int64_t n, const T* x, const T* w, T* out, int64_t F,
                 cudaStream_t st, int64_t max_deg = 0, int wH = 1) {
   constexpr int VE = VB / sizeof(T);
@@ -205,7 +206,7 @@ void launch_vec(const I* indptr, const I* indices, const I* eids, int64_t n, con
 // chunk in registers and adds the partial row into an fp32 scratch row with vector red.global.add;
 // spmm_split_finalize converts scratch -> out. Hub rows of power-law graphs are thereby spread over
 // the whole GPU instead of serialising on one warp.
-template <typename T, typename I, int VB, int NV, bool HAS_W>
+template <typename T, typename I, int VB, int NV, int HAS_W>  // HAS_W: 0 none, 1 one scalar per edge, 2 one per head
 __global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ indices, const I* __restrict__ eids,
                                                          const int32_t* __restrict__ item_ord,
                                                          const int64_t* __restrict__ item_start,
@@ -234,13 +235,14 @@ __global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ i
   int64_t p = s;
   for (; p + U <= t; p += U) {
     int64_t u[U];
-    float wt[U][NV];
+    constexpr int NW = HAS_W == 2 ? NV : 1;  // a scalar weight is shared by all vectors of the lane
+    float wt[U][NW];
 #pragma unroll
     for (int k = 0; k < U; ++k) {
       u[k] = indices[p + k];
       const int64_t eidx = (eids ? (int64_t)eids[p + k] : p + k) * wH;
 #pragma unroll
-      for (int j = 0; j < NV; ++j) wt[k][j] = HAS_W ? to_f<T>(w[eidx + hd[j]]) : 1.f;
+      for (int j = 0; j < NW; ++j) wt[k][j] = HAS_W ? to_f<T>(w[eidx + (HAS_W == 2 ? hd[j] : 0)]) : 1.f;
     }
     V v[U][NV];
 #pragma unroll
@@ -254,7 +256,7 @@ __global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ i
     for (int k = 0; k < U; ++k)
 #pragma unroll
       for (int j = 0; j < NV; ++j)
-        if (vbase + j * sub < nvec) VO::fma(acc[j], v[k][j], wt[k][j]);
+        if (vbase + j * sub < nvec) VO::fma(acc[j], v[k][j], wt[k][HAS_W == 2 ? j : 0]);
   }
   for (; p < t; ++p) {
     const int64_t u = indices[p];
@@ -264,7 +266,7 @@ __global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ i
     for (int j = 0; j < NV; ++j)
       if (vbase + j * sub < nvec) {
         V v = ldg_vec(xr + vbase + j * sub);
-        VO::fma(acc[j], v, HAS_W ? to_f<T>(w[eidx + hd[j]]) : 1.f);
+        VO::fma(acc[j], v, HAS_W ? to_f<T>(w[eidx + (HAS_W == 2 ? hd[j] : 0)]) : 1.f);
       }
   }
   float* srow = scratch + (int64_t)item_ord[item] * F;
@@ -289,7 +291,7 @@ __global__ void __launch_bounds__(256) spmm_split_finalize_kernel(const float* _
   }
 }
 
-template <typename T, typename I, int VB, bool HAS_W>
+template <typename T, typename I, int VB, int HAS_W>
 void launch_split(const I* indices, const I* eids, const int32_t* item_ord, const int64_t* item_start,
                   const int32_t* item_len, int64_t num_items, const T* x, const T* w, float* scratch, int64_t F,
                   cudaStream_t st, int wH = 1) {
@@ -411,7 +413,7 @@ DGLB_API int dglb200_cuda_gspmm_balanced(int has_w, int dtype, int idtype, const
     DGLB_CHECK(vb != 0 && (F * (int64_t)sizeof(T)) % vb == 0, "feature rows must be 4-byte aligned for the balanced g-SpMM");
 #define RUN(VBV, HW)                                                                                              \
     /* short rows: TMA-staged row gather when the row size allows it (spmm_bulk.cuh), else the SIMT vector kernel */ \
-    if (!(wH == 1 && bulk::launch<T, I, HW>((const I*)indptr, (const I*)indices, (const I*)eids, num_rows,          \
+    if (!(wH == 1 && bulk::launch<T, I, (HW != 0)>((const I*)indptr, (const I*)indices, (const I*)eids, num_rows,          \
                                             (const T*)x, (const T*)w, (T*)out, F, max_deg, st)))                    \
       launch_vec<T, I, VBV, HW>((const I*)indptr, (const I*)indices, (const I*)eids, num_rows, (const T*)x,         \
                                 (const T*)w, (T*)out, F, st, max_deg, wH);                                          \
@@ -425,9 +427,10 @@ DGLB_API int dglb200_cuda_gspmm_balanced(int has_w, int dtype, int idtype, const
       spmm_split_finalize_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const float*)scratch,                        \
                                                                       (const int64_t*)long_rows, n_long, F, (T*)out); \
     }
-    if (vb == 16) { if (has_w) { RUN(16, true) } else { RUN(16, false) } }
-    else if (vb == 8) { if (has_w) { RUN(8, true) } else { RUN(8, false) } }
-    else { if (has_w) { RUN(4, true) } else { RUN(4, false) } }
+    const int hw = has_w == 0 ? 0 : (wH > 1 ? 2 : 1);
+    if (vb == 16) { if (hw == 2) { RUN(16, 2) } else if (hw == 1) { RUN(16, 1) } else { RUN(16, 0) } }
+    else if (vb == 8) { if (hw == 2) { RUN(8, 2) } else if (hw == 1) { RUN(8, 1) } else { RUN(8, 0) } }
+    else { if (hw == 2) { RUN(4, 2) } else if (hw == 1) { RUN(4, 1) } else { RUN(4, 0) } }
 #undef RUN
   };
   DGLB_ID_SWITCH(idtype, I, {

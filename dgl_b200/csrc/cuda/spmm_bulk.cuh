@@ -139,8 +139,11 @@ bool launch(const I* indptr, const I* indices, const I* eids, int64_t num_rows, 
   const int64_t row_bytes = F * (int64_t)sizeof(T);
   if (row_bytes % 16 || row_bytes < 64 || row_bytes > kMaxRowBytes || ((uintptr_t)x & 15) || ((uintptr_t)out & 15)) return false;
   static const bool enabled = [] {
+    // opt-in: on B200 the SIMT vector kernel wins (0.33-0.95x of it measured over arxiv/reddit/products x F 32..256,
+    // profiles/kernels_bulk_vs_simt.md) - one elected lane issuing row copies and an mbarrier wait per neighbour row leave
+    // the warp latency-bound, while the SIMT kernel keeps 4 rows x NV vectors per lane in flight with no waits.
     const char* e = std::getenv("DGLB200_SPMM_BULK");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   if (!enabled) return false;
   const uint32_t stride = (uint32_t)((row_bytes + 127) / 128 * 128);

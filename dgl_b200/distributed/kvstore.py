@@ -294,6 +294,35 @@ class KVClient:
             st.handlers[name] = func
 
 
+# ---- process-wide client handle + default handlers ----------------------------------------------------------------------
+_CLIENT = {"kv": None}
+
+
+def default_push_handler(target, name, id_tensor, data_tensor):
+    """Plain assignment of pushed rows (reference kvstore.py:39-60): ``target[name][ids] = data``."""
+    target[name][id_tensor.long()] = data_tensor.to(target[name].dtype)
+
+
+def default_pull_handler(target, name, id_tensor):
+    """Row lookup answering a pull (reference kvstore.py:63-80)."""
+    return target[name][id_tensor.long()]
+
+
+def init_kvstore(ip_config=None, num_servers=1, role="default"):
+    """Create the process-wide KVClient once (standalone and distributed mode share the class here)."""
+    if _CLIENT["kv"] is None:
+        _CLIENT["kv"] = KVClient(ip_config, num_servers, role)
+    return _CLIENT["kv"]
+
+
+def close_kvstore():
+    _CLIENT["kv"] = None
+
+
+def get_kvstore():
+    return _CLIENT["kv"]
+
+
 def __getattr__(name):
     # class-based request / response types of this service live in messages.py (lazy: avoids an import cycle)
     if name.startswith("__"):

@@ -385,3 +385,65 @@ def dgl_partition_to_graphbolt(part_config, *, store_eids=True, store_inner_node
         meta[f"part-{pid}"]["part_graph_graphbolt"] = rel
     with open(part_config, "w") as f:
         json.dump(meta, f, sort_keys=True, indent=4)
+
+
+# ---- small public helpers of the partition pipeline (reference partition.py:91-107, :1588-1596, :1623-1720) -------------
+def _narrowest_int(max_value, tensor):
+    """``tensor`` in the smallest integer dtype that can index ``max_value`` items."""
+    for dt in (torch.int32, torch.int64):
+        if max_value <= torch.iinfo(dt).max:
+            return tensor.to(dt)
+    return tensor
+
+
+def process_partitions(g, formats=None, sort_etypes=False):
+    """Normalise a partition graph before it is written: reserved columns in their canonical dtypes and, if requested,
+    CSR / CSC neighbour lists grouped by edge type (what the typed samplers of the servers expect)."""
+    from ..base import ETYPE
+    for name, dt in {**RESERVED_FIELD_DTYPE, "_TYPE": torch.int32}.items():
+        for frame in (g.ndata, g.edata):
+            if name in frame:
+                frame[name] = frame[name].to(dt)
+    if sort_etypes and formats:
+        from ..transforms import sort_csc_by_tag, sort_csr_by_tag
+        if "csr" in formats:
+            g = sort_csr_by_tag(g, tag=g.edata[ETYPE], tag_type="edge")
+        if "csc" in formats:
+            g = sort_csc_by_tag(g, tag=g.edata[ETYPE], tag_type="edge")
+    return g
+
+
+def is_homogeneous(ntypes, etypes):
+    return len(ntypes) == 1 and len(etypes) == 1
+
+
+def init_type_per_edge(graph, gpb):
+    """edge-type id of every edge of a partition graph, recovered from its global edge ids."""
+    return gpb.map_to_per_etype(graph.edata[EID])[0]
+
+
+def cast_various_to_minimum_dtype_gb(num_parts, indptr, indices, type_per_edge, etypes, ntypes, node_attributes,
+                                     edge_attributes, part_meta=None, graph=None, edge_count=None, node_count=None,
+                                     tot_edge_count=None, tot_node_count=None):
+    """Shrink the integer arrays of a GraphBolt partition to the narrowest dtype that holds their value range
+    (indptr: total edge count; indices / node ids: total node count; edge ids: total edge count; type ids: number of
+    types; inner flags: uint8). Returns the same six objects in the same order."""
+    if graph is not None:
+        if part_meta is None:
+            raise DGLError("part_meta is needed when the counts are taken from a graph")
+        tot_edge_count, tot_node_count = graph.num_edges(), graph.num_nodes()
+        node_count, edge_count = part_meta["num_nodes"], part_meta["num_edges"]
+    elif None in (tot_edge_count, tot_node_count, edge_count, node_count):
+        raise DGLError("pass either `graph` + `part_meta` or all four counts")
+    indptr = _narrowest_int(tot_edge_count, indptr)
+    indices = _narrowest_int(tot_node_count, indices)
+    if type_per_edge is not None:
+        type_per_edge = type_per_edge.to(torch.uint8 if len(etypes) <= 255 else torch.int16 if len(etypes) < 2 ** 15 else torch.int32)
+    limits = {NID: node_count, EID: edge_count, "_TYPE": max(len(ntypes), len(etypes))}
+    for attrs in (node_attributes, edge_attributes):
+        for key in list(attrs or {}):
+            if key in limits:
+                attrs[key] = _narrowest_int(limits[key], attrs[key])
+            elif key in RESERVED_FIELD_DTYPE:
+                attrs[key] = attrs[key].to(RESERVED_FIELD_DTYPE[key])
+    return indptr, indices, type_per_edge, node_attributes, edge_attributes

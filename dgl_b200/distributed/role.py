@@ -30,6 +30,11 @@ def get_global_rank():
     return _ROLE["global_rank"]
 
 
+def get_rank():
+    """Rank of this process inside its role (== ``get_trainer_rank`` for trainers; reference role.py:244)."""
+    return _ROLE["rank"]
+
+
 def get_num_trainers():
     return _ROLE["num"]
 

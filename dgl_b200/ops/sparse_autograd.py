@@ -116,7 +116,7 @@ class GSpMM(torch.autograd.Function):
 class GSDDMM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, gidx, op, X, Y, lhs_target, rhs_target):
-        out = K.gsddmm(gidx.coo(), op, X, Y, lhs_target, rhs_target)
+        out = K.gsddmm(gidx.coo(), op, X, Y, lhs_target, rhs_target, gidx=gidx)
         ctx.backward_cache = (gidx, op, lhs_target, rhs_target, None if X is None else X.shape,
                               None if Y is None else Y.shape)
         req_x = X is not None and X.requires_grad

@@ -98,8 +98,8 @@ class PartitionedSAGE(nn.Module):
         return h
 
     @torch.no_grad()
-    def allreduce_gradients(self):
-        """Average the (replicated) parameter gradients over the ranks with the one-shot P2P all-reduce."""
+    def allreduce_gradients(self, average=True):
+        """Combine the (replicated) parameter gradients over the ranks with the one-shot P2P all-reduce (mean, or sum)."""
         ps = [p for p in self.parameters() if p.grad is not None]
         flat = torch.cat([p.grad.reshape(-1).float() for p in ps])
         n = flat.numel()
@@ -110,9 +110,36 @@ class PartitionedSAGE(nn.Module):
         g.zero_()
         g[:n].copy_(flat)
         out = torch.empty(n + pad, device=flat.device)
-        self.comm.all_reduce(self._gsym, out, n + pad, scale=1.0 / self.comm.world_size)
+        self.comm.all_reduce(self._gsym, out, n + pad, scale=1.0 / self.comm.world_size if average else 1.0)
         off = 0
         for p in ps:
             k = p.numel()
             p.grad.copy_(out[off: off + k].view_as(p.grad))
             off += k
+
+
+class PartitionedSAGETC(PartitionedSAGE):
+    """``PartitionedSAGE`` whose dense half runs on the tensor cores: per layer ONE tcgen05 GEMM
+    ``[h | mean_N(h)] @ [W_self ; W_neigh]`` in bf16 with fp32 accumulation (``ops.segment_mm`` with a single segment ->
+    csrc/cuda/grouped_mm_tc.cu ``seg_mm_tc_kernel``; its backward is the same kernel for dA and the MN-major split-K
+    kernel for dW). The aggregation runs in bf16 as well, which halves the halo bytes crossing NVLink. Master weights stay
+    fp32 (the cast is part of the autograd graph)."""
+
+    def __init__(self, comm, indptr, indices_global, shard_rows, in_size, hid_size, out_size, num_layers=2, dropout=0.0):
+        super().__init__(comm, indptr, indices_global, shard_rows, in_size, hid_size, out_size, num_layers, dropout)
+        self.out_size = out_size
+        self._seglen = torch.tensor([int(shard_rows)], device=comm.device)
+
+    def forward(self, x):
+        from ..ops import segment_mm
+        h = x.to(torch.bfloat16)
+        last = len(self.self_lin) - 1
+        for i, (ls, ln) in enumerate(zip(self.self_lin, self.neigh_lin)):
+            w = torch.cat([ls.weight, ln.weight], dim=1).t()                  # [2 * in, out], fp32 master
+            pad = (-w.shape[1]) % 8                                          # the GEMM wants out % 8 == 0 (47 classes -> 48)
+            if pad:
+                w = F.pad(w, (0, pad))
+            z = segment_mm(torch.cat([h, self.agg(h)], dim=1), w.to(torch.bfloat16).unsqueeze(0), self._seglen)
+            z = (z[:, : w.shape[1] - pad] if pad else z) + ls.bias.to(z.dtype)
+            h = self.dropout(F.relu(z)) if i < last else z
+        return h

@@ -144,3 +144,28 @@ def test_message_classes_run_the_server_handlers():
         assert get_service_property(kvstore.PullRequest("a", ids).service_id) == (kvstore.PullRequest, kvstore.PullResponse)
         assert get_service_property(kvstore.PushRequest("a", ids, ids).service_id)[1] is None
     assert dist_graph.NodeDataView is dist_graph.EdgeDataView
+
+
+def test_kvstore_handles_partition_helpers_and_role_rank():
+    import torch
+    import dgl_b200 as dgl
+    from dgl_b200.distributed import kvstore as K, partition as P, role as R
+    store = {"emb": torch.zeros(4, 2)}
+    K.default_push_handler(store, "emb", torch.tensor([1, 3]), torch.ones(2, 2))
+    assert store["emb"].sum() == 4 and K.default_pull_handler(store, "emb", torch.tensor([3])).tolist() == [[1.0, 1.0]]
+    K.close_kvstore()
+    assert K.get_kvstore() is None
+    assert P.is_homogeneous(["_N"], ["_E"]) and not P.is_homogeneous(["a", "b"], ["e"])
+    assert R.get_rank() == R.get_trainer_rank()
+    ip, ix = torch.tensor([0, 2, 5]), torch.tensor([1, 0, 1, 0, 1])
+    out = P.cast_various_to_minimum_dtype_gb(2, ip, ix, torch.tensor([0, 1, 0, 1, 1]), ["a", "b"], ["n"],
+                                             {dgl.NID: torch.arange(2)}, {dgl.EID: torch.arange(5), "inner_edge": torch.ones(5)},
+                                             tot_edge_count=5, tot_node_count=2, edge_count=5, node_count=2)
+    assert out[0].dtype == torch.int32 and out[1].dtype == torch.int32 and out[2].dtype == torch.uint8
+    assert out[4]["inner_edge"].dtype == torch.uint8 and out[3][dgl.NID].dtype == torch.int32
+    big = P.cast_various_to_minimum_dtype_gb(2, ip, ix, None, ["a"], ["n"], {}, {}, tot_edge_count=2 ** 33,
+                                             tot_node_count=10, edge_count=5, node_count=2)
+    assert big[0].dtype == torch.int64 and big[1].dtype == torch.int32 and big[2] is None
+    g = dgl.rand_graph(10, 30)
+    g.ndata["inner_node"] = torch.ones(10)
+    assert P.process_partitions(g).ndata["inner_node"].dtype == torch.uint8
