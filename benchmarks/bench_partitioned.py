@@ -86,13 +86,16 @@ def run_ours(args):
     del u, v
     part, new_id, mine, shard_rows, t_part = partition_and_relabel(n, indptr, indices, world, rank, dev)
     lp, lidx = local_csc(indptr, indices, mine, new_id, shard_rows)
+    # out-edges of the owned vertices for the pull-based backward; the RMAT graph is symmetrised, so CSR == CSC
+    reverse = (lp, lidx)
     lo = rank * shard_rows
     remote = ((lidx < lo) | (lidx >= lo + shard_rows))
     cut_local = float(remote.float().mean()) if lidx.numel() else 0.0
     is_train = torch.zeros(n, dtype=torch.bool, device=dev)
     is_train[train_idx] = True
-    x = torch.zeros(shard_rows, B.FEAT, device=dev, dtype=torch.bfloat16)
-    x[: mine.numel()] = feat[mine].to(torch.bfloat16)
+    feat_w = (B.FEAT + 7) // 8 * 8          # 100 -> 104 zero-padded columns: 16-byte rows for the halo copies and the GEMM
+    x = torch.zeros(shard_rows, feat_w, device=dev, dtype=torch.bfloat16)
+    x[: mine.numel(), : B.FEAT] = feat[mine].to(torch.bfloat16)
     y = torch.zeros(shard_rows, dtype=torch.int64, device=dev)
     y[: mine.numel()] = labels[mine]
     m = torch.zeros(shard_rows, dtype=torch.bool, device=dev)
@@ -102,7 +105,8 @@ def run_ours(args):
     torch.cuda.empty_cache()
     comm = P2PComm(dist.group.WORLD if world > 1 else None, dev)
     torch.manual_seed(1234)
-    model = PartitionedSAGETC(comm, lp, lidx, shard_rows, B.FEAT, HIDDEN, B.CLASSES, num_layers=LAYERS, dropout=0.5).to(dev)
+    model = PartitionedSAGETC(comm, lp, lidx, shard_rows, feat_w, HIDDEN, B.CLASSES, num_layers=LAYERS, dropout=0.5,
+                              reverse=reverse).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=3e-3, fused=True)
     train_rows = m.nonzero().squeeze(1)
 

@@ -71,6 +71,75 @@ def labor0(indptr, indices, eids, seeds, fanout, seed):
     return src, pos, eid, counts
 
 
+def labor_sample(indptr, indices, eids, seeds, fanout, prob, iters, seed1, seed2=0, mix=0.0, num_src=None, cache=None,
+                 return_state=False):
+    """LABOR-i on a CSC, entirely on the device (csrc/cuda/labor.cu). ``iters`` importance iterations (< 0: until the
+    importances stop moving, at most 10), ``prob`` optional per-edge weights (edge-id indexed), ``(seed1, seed2, mix)``
+    the continuous-seed variate. Returns (src, seed position, eid, importance weight[, (c, pi)]). One host read (the number
+    of sampled edges) per call; the importance buffers are indexed by vertex id and live in ``cache`` between calls."""
+    lib = _lib()
+    idt, dev, n = seeds.dtype, seeds.device, seeds.shape[0]
+    num_src = int(num_src if num_src is not None else (int(indices.max()) + 1 if indices.numel() else 1))
+    cache = {} if cache is None else cache
+    key = ("labor_pi", dev.index, num_src)
+    bufs = cache.get(key)
+    if bufs is None:
+        bufs = cache[key] = (torch.ones(num_src, dtype=torch.float32, device=dev), torch.zeros(num_src, dtype=torch.float32, device=dev))
+    pi, pi_next = bufs
+    c = torch.empty(n, dtype=torch.float32, device=dev)
+    pcode = -1 if prob is None else dtype_code(prob.dtype)
+    common = (id_code(idt),)
+    st = loader.stream_ptr
+    solve = lib.fn("dglb200_cuda_labor_solve_c", "ipppplipippp")
+    ppass = lib.fn("dglb200_cuda_labor_pi_pass", "iipppplpppipp")
+    pick = lib.fn("dglb200_cuda_labor_pick", "iipppplppipllfpppppppp")
+    g = (indptr.data_ptr(), indices.data_ptr(), _p(eids), seeds.data_ptr(), n)
+
+    def run_solve():
+        solve(id_code(idt), *g, int(fanout), pi.data_ptr(), pcode, _p(prob), c.data_ptr(), st())
+
+    def run_pass(mode):
+        ppass(id_code(idt), mode, *g, c.data_ptr(), pi.data_ptr(), pi_next.data_ptr(), pcode, _p(prob), st())
+
+    run_solve()
+    rounds = 10 if iters < 0 else int(iters)
+    for _ in range(rounds):
+        run_pass(0)          # pi_next[t] = max_s c_s pi_t a_ts
+        run_pass(1)          # pi[t] <- pi_next[t]
+        run_pass(2)          # pi_next[t] <- 0 (ready for the next round / call)
+        run_solve()
+    counts = torch.empty(n, dtype=torch.int64, device=dev)
+    wsum = torch.empty(n, dtype=torch.float32, device=dev)
+    s1, s2 = int(seed1) & 0x7FFFFFFFFFFFFFFF, int(seed2) & 0x7FFFFFFFFFFFFFFF
+    pick(id_code(idt), 0, *g, c.data_ptr(), pi.data_ptr(), pcode, _p(prob), s1, s2, float(mix), counts.data_ptr(),
+         wsum.data_ptr(), 0, 0, 0, 0, 0, st())
+    offs = torch.cumsum(counts, 0) - counts
+    total = int(counts.sum())
+    src = torch.empty(total, dtype=idt, device=dev)
+    pos = torch.empty(total, dtype=idt, device=dev)
+    eid = torch.empty(total, dtype=idt, device=dev)
+    w = torch.empty(total, dtype=torch.float32, device=dev)
+    if total:
+        pick(id_code(idt), 1, *g, c.data_ptr(), pi.data_ptr(), pcode, _p(prob), s1, s2, float(mix), 0, wsum.data_ptr(),
+             offs.data_ptr(), src.data_ptr(), pos.data_ptr(), eid.data_ptr(), w.data_ptr(), st())
+    state = None
+    if return_state:
+        touched = torch.unique(indices[_expand_rows(indptr, seeds)].long()) if n else torch.empty(0, dtype=torch.long, device=dev)
+        state = (c.clone(), touched, pi[touched].clone())
+    if rounds:
+        run_pass(3)          # pi[t] <- 1 for the touched vertices: the cached buffer is neutral again
+    return (src, pos, eid, w, state) if return_state else (src, pos, eid, w)
+
+
+def _expand_rows(indptr, rows):
+    s = indptr[rows.long()].long()
+    deg = indptr[rows.long() + 1].long() - s
+    total = int(deg.sum())
+    owner = torch.repeat_interleave(torch.arange(rows.shape[0], device=rows.device), deg, output_size=total)
+    first = torch.cumsum(deg, 0) - deg
+    return s[owner] + (torch.arange(total, device=rows.device) - first[owner])
+
+
 def neg_sample(indptr, indices, sorted_rows, n_src, n_dst, exclude_self, trials, seed):
     idt = indptr.dtype
     dev = indptr.device

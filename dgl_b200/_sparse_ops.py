@@ -132,7 +132,7 @@ def _split_meta(indptr):
     return meta
 
 
-def _gspmm_balanced(csr, ufeat2d, ew, num_dst, F, heads=1):
+def _gspmm_balanced(csr, ufeat2d, ew, num_dst, F, heads=1, out=None):
     indptr, indices, eids = csr
     from .global_config import is_deterministic
     # deterministic mode (USE_DETERMINISTIC_ALG=1 / dgl.global_config.set_deterministic): long rows are NOT split into
@@ -144,7 +144,8 @@ def _gspmm_balanced(csr, ufeat2d, ew, num_dst, F, heads=1):
         from .ops.cuda_struct import gather_rows
         ew = gather_rows(ew, eids)
         eids = None
-    out = torch.empty((num_dst, F), dtype=ufeat2d.dtype, device=ufeat2d.device)
+    if out is None:
+        out = torch.empty((num_dst, F), dtype=ufeat2d.dtype, device=ufeat2d.device)
     lib = loader.cuda_lib()
     if meta["n_long"]:
         scratch = torch.empty((meta["n_long"], F), dtype=torch.float32, device=ufeat2d.device)

@@ -311,6 +311,59 @@ class HaloPlan:
         # measured on 2xB200 (profiles/comm_2gpu.json): with (almost) no interior rows every warp should pull first
         self.puller_warps = int(puller_warps) if puller_warps else (8 if self.n_interior * 20 < n else 4)
 
+    # ---- two-phase formulation: bulk halo pull on a side stream || balanced g-SpMM of the interior rows, then the boundary rows
+    def _split(self):
+        """Row-permuted CSC (interior rows first) cut into an interior and a boundary matrix over the ``[local | halo]`` table."""
+        if getattr(self, "_split_cache", None) is None:
+            dev = self.indptr.device
+            n = int(self.order.shape[0])
+            ip = self.indptr.long()
+            deg = ip[1:] - ip[:-1]
+            order = self.order.long()
+            deg_p = deg[order]
+            ptr = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+            ptr[1:] = torch.cumsum(deg_p, 0)
+            total = int(ptr[-1])
+            owner = torch.repeat_interleave(torch.arange(n, device=dev), deg_p, output_size=total)
+            pos = ip[:-1][order][owner] + (torch.arange(total, device=dev) - ptr[:-1][owner])
+            idx = self.indices[pos].contiguous()
+            cut = int(ptr[self.n_interior])
+            it = self.indptr.dtype
+            self._split_cache = dict(
+                interior=(ptr[: self.n_interior + 1].to(it).contiguous(), idx[:cut].contiguous(), None),
+                boundary=((ptr[self.n_interior:] - cut).to(it).contiguous(), idx[cut:].contiguous(), None),
+                inv_order=torch.argsort(order), inv_deg=(1.0 / deg.clamp(min=1).to(torch.float32)).unsqueeze(1),
+                side=torch.cuda.Stream(device=dev))
+        return self._split_cache
+
+    def spmm_balanced(self, buf, table, out, mean=True):
+        """Same contract as ``spmm``. The halo rows are copied out of the owners' shards by ONE gather kernel on a side
+        stream (sorted ids: sequential reads per owner, every row crosses NVLink once) while the main stream aggregates the
+        interior rows with the load-balanced g-SpMM (csrc/cuda/spmm.cu: row-parallel vector kernel + edge-balanced items for
+        hub rows); the boundary rows follow once the pull has landed. On hub-heavy graphs this is several times faster than
+        the one-warp-per-row interior loop of ``halo_pipe_kernel`` (measured: products RMAT, 1 GPU, F = 256: 57 ms -> see
+        profiles/partitioned.md)."""
+        from .._sparse_ops import _gspmm_balanced
+        sp = self._split()
+        F = int(table.shape[1])
+        n, ni = self.rows, self.n_interior
+        main = torch.cuda.current_stream(table.device)
+        if self.n_halo:
+            sp["side"].wait_stream(main)
+            with torch.cuda.stream(sp["side"]):
+                self.comm.gather(buf, self.rows, self.halo_ids, table[n: n + self.n_halo])
+        staged = torch.empty((n, F), dtype=table.dtype, device=table.device)
+        if ni:
+            _gspmm_balanced(sp["interior"], table, None, ni, F, out=staged[:ni])
+        if self.n_halo:
+            main.wait_stream(sp["side"])
+        if n - ni:
+            _gspmm_balanced(sp["boundary"], table, None, n - ni, F, out=staged[ni:])
+        torch.index_select(staged, 0, sp["inv_order"], out=out)
+        if mean:
+            out.mul_(sp["inv_deg"].to(out.dtype))
+        return out
+
     def alloc_features(self, feat_dim, dtype):
         """Symmetric feature buffer with room for the halo rows behind the local shard. Returns (buffer, table);
         ``table[:rows]`` is this rank's shard (what the peers read), ``table[rows:]`` receives the halo rows."""

@@ -29,7 +29,7 @@ class _HaloAggregate(torch.autograd.Function):
         table[: plan.rows].copy_(x)
         comm.barrier(0)                       # every shard is written
         out = torch.empty((plan.rows, x.shape[1]), dtype=x.dtype, device=x.device)
-        plan.spmm(buf, table, out, mean=layer.mean)
+        layer._aggregate(plan, buf, table, out, layer.mean)
         comm.barrier(1)                       # nobody overwrites its shard while a peer is still pulling it
         ctx.layer = layer
         return out
@@ -39,6 +39,18 @@ class _HaloAggregate(torch.autograd.Function):
         layer = ctx.layer
         plan, comm = layer.plan, layer.comm
         Fdim = dout.shape[1]
+        if layer.rev_plan is not None:
+            # pull formulation: dX[u] = sum over out-edges (u -> v) of dOut[v] / indeg(v). Every rank scales ITS rows of
+            # dOut, publishes them and aggregates over the out-neighbours of its own vertices with the same one-kernel
+            # halo pipeline as the forward - no atomics, every halo row crosses NVLink once.
+            rplan = layer.rev_plan
+            buf, table = layer._rev_buffer(Fdim, dout.dtype)
+            torch.mul(dout, layer.inv_deg.to(dout.dtype), out=table[: rplan.rows]) if layer.mean else table[: rplan.rows].copy_(dout)
+            comm.barrier(2)
+            dx = torch.empty((rplan.rows, Fdim), dtype=dout.dtype, device=dout.device)
+            layer._aggregate(rplan, buf, table, dx, False)
+            comm.barrier(3)
+            return dx, None
         dsh, dx = layer._grad_buffer(Fdim)
         dx.zero_()
         comm.barrier(2)                       # all gradient shards are zeroed
@@ -52,12 +64,37 @@ class HaloAggregate(nn.Module):
 
     indptr: CSC row pointers of the owned destination rows, indices_global: GLOBAL source ids."""
 
-    def __init__(self, comm: P2PComm, indptr, indices_global, shard_rows, mean=True):
+    def __init__(self, comm: P2PComm, indptr, indices_global, shard_rows, mean=True, reverse=None):
+        """``reverse`` (optional): ``(indptr_out, indices_out_global)`` - the CSR rows (out-edges, global destination ids) of
+        the owned vertices. With it the backward is a second pull-based halo aggregation over the transposed structure;
+        without it gradients are pushed to the owners with ``red.add`` over NVLink."""
         super().__init__()
         self.comm, self.mean = comm, mean
         self.indices_global = indices_global.contiguous()
         self.plan = HaloPlan(comm, indptr, indices_global, shard_rows)
-        self._fbufs, self._gbufs = {}, {}
+        self._fbufs, self._gbufs, self._rbufs = {}, {}, {}
+        self.rev_plan = None
+        if reverse is not None:
+            self.rev_plan = HaloPlan(comm, reverse[0], reverse[1], shard_rows)
+            deg = (indptr[1:] - indptr[:-1]).clamp(min=1).to(torch.float32)
+            self.inv_deg = (1.0 / deg).unsqueeze(1)
+
+    @staticmethod
+    def _aggregate(plan, buf, table, out, mean):
+        """two-phase (bulk pull || balanced SpMM) when the rows are 16-byte multiples, else the fused one-kernel pipeline;
+        ``DGLB200_HALO_MODE=fused`` forces the latter."""
+        import os
+        row_bytes = table.shape[1] * table.element_size()
+        if os.environ.get("DGLB200_HALO_MODE", "balanced") != "fused" and row_bytes % 16 == 0 and table.element_size() <= 4:
+            plan.spmm_balanced(buf, table, out, mean=mean)
+        else:
+            plan.spmm(buf, table, out, mean=mean)
+
+    def _rev_buffer(self, feat_dim, dtype):
+        key = (feat_dim, dtype)
+        if key not in self._rbufs:
+            self._rbufs[key] = self.rev_plan.alloc_features(feat_dim, dtype)
+        return self._rbufs[key]
 
     def _feature_buffer(self, feat_dim, dtype):
         key = (feat_dim, dtype)
@@ -80,9 +117,10 @@ class PartitionedSAGE(nn.Module):
     ``HaloAggregate``; parameters are replicated, call ``allreduce_gradients`` (or ``comm.fused_allreduce_adam``)
     after backward."""
 
-    def __init__(self, comm, indptr, indices_global, shard_rows, in_size, hid_size, out_size, num_layers=2, dropout=0.0):
+    def __init__(self, comm, indptr, indices_global, shard_rows, in_size, hid_size, out_size, num_layers=2, dropout=0.0,
+                 reverse=None):
         super().__init__()
-        self.agg = HaloAggregate(comm, indptr, indices_global, shard_rows, mean=True)
+        self.agg = HaloAggregate(comm, indptr, indices_global, shard_rows, mean=True, reverse=reverse)
         sizes = [in_size] + [hid_size] * (num_layers - 1) + [out_size]
         self.self_lin = nn.ModuleList(nn.Linear(sizes[i], sizes[i + 1]) for i in range(num_layers))
         self.neigh_lin = nn.ModuleList(nn.Linear(sizes[i], sizes[i + 1], bias=False) for i in range(num_layers))
@@ -125,21 +163,35 @@ class PartitionedSAGETC(PartitionedSAGE):
     kernel for dW). The aggregation runs in bf16 as well, which halves the halo bytes crossing NVLink. Master weights stay
     fp32 (the cast is part of the autograd graph)."""
 
-    def __init__(self, comm, indptr, indices_global, shard_rows, in_size, hid_size, out_size, num_layers=2, dropout=0.0):
-        super().__init__(comm, indptr, indices_global, shard_rows, in_size, hid_size, out_size, num_layers, dropout)
+    def __init__(self, comm, indptr, indices_global, shard_rows, in_size, hid_size, out_size, num_layers=2, dropout=0.0,
+                 reverse=None):
+        super().__init__(comm, indptr, indices_global, shard_rows, in_size, hid_size, out_size, num_layers, dropout, reverse)
         self.out_size = out_size
         self._seglen = torch.tensor([int(shard_rows)], device=comm.device)
+
+    @staticmethod
+    def _pad8(w):
+        pad = (-w.shape[1]) % 8                                   # GEMM output columns in 16-byte units (47 classes -> 48)
+        return (F.pad(w, (0, pad)) if pad else w), pad
 
     def forward(self, x):
         from ..ops import segment_mm
         h = x.to(torch.bfloat16)
         last = len(self.self_lin) - 1
         for i, (ls, ln) in enumerate(zip(self.self_lin, self.neigh_lin)):
-            w = torch.cat([ls.weight, ln.weight], dim=1).t()                  # [2 * in, out], fp32 master
-            pad = (-w.shape[1]) % 8                                          # the GEMM wants out % 8 == 0 (47 classes -> 48)
-            if pad:
-                w = F.pad(w, (0, pad))
-            z = segment_mm(torch.cat([h, self.agg(h)], dim=1), w.to(torch.bfloat16).unsqueeze(0), self._seglen)
-            z = (z[:, : w.shape[1] - pad] if pad else z) + ls.bias.to(z.dtype)
+            n_in, n_out = ls.in_features, ls.out_features
+            if n_in > n_out:
+                # mean() is linear: project first, aggregate the NARROW rows (fewer bytes gathered and fewer halo bytes)
+                ws, pad = self._pad8(ls.weight.t())
+                wn, _ = self._pad8(ln.weight.t())
+                width = ws.shape[1]
+                z = segment_mm(h, torch.cat([ws, wn], dim=1).to(torch.bfloat16).unsqueeze(0), self._seglen)
+                z = z[:, :width] + self.agg(z[:, width:].contiguous())
+                z = z[:, :n_out] if pad else z
+            else:
+                w, pad = self._pad8(torch.cat([ls.weight, ln.weight], dim=1).t())      # [2 * in, out]
+                z = segment_mm(torch.cat([h, self.agg(h)], dim=1), w.to(torch.bfloat16).unsqueeze(0), self._seglen)
+                z = z[:, :n_out] if pad else z
+            z = z + ls.bias.to(z.dtype)
             h = self.dropout(F.relu(z)) if i < last else z
         return h

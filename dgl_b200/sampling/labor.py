@@ -26,6 +26,15 @@ def _labor_rel(ug, seeds, fanout, prob, importance_sampling, random_seed, seed2_
         src, pos, eid, counts = labor0(indptr, indices, eids, seeds.contiguous(), fanout, random_seed)
         w = 1.0 / counts[pos.long()].clamp(min=1).float()     # Hajek-normalised: equal inclusion prob inside a seed
         return src, seeds[pos.long()], eid, w
+    if dev.type == "cuda" and indptr.is_cuda and seeds.dtype == indptr.dtype and fanout >= 0:
+        # LABOR-i / weighted / continuous-seed variants: importance iterations, normalisers and the Bernoulli pass are
+        # device kernels over the CSC (csrc/cuda/labor.cu); one host read per call
+        from .._graph_kernels import labor_sample
+        p = None if prob is None else prob.to(dev).contiguous()
+        src, pos, eid, w = labor_sample(indptr, indices, eids, seeds.contiguous(), fanout, p, importance_sampling,
+                                        random_seed, int(random_seed) + 1, float(seed2_contribution), num_src=ug.num_src,
+                                        cache=ug._degs)
+        return src, seeds[pos.long()], eid, w
     indptr_d, indices_d = indptr.to(dev), indices.to(dev)
     s = indptr_d[seeds.long()].long()
     deg = indptr_d[seeds.long() + 1].long() - s

@@ -252,6 +252,68 @@ def _w_partitioned_sage(rank, world, comm):
     return float(loss)
 
 
+def _w_partitioned_sage_pull_backward(rank, world, comm):
+    """Pull-based backward (second halo plan over the out-edges) and the tcgen05 dense half: gradients of the partitioned
+    model vs a single-process fp32 oracle; also the fused one-kernel pipeline vs the two-phase aggregation."""
+    import os
+    import dgl_b200 as dgl
+    from dgl_b200.parallel import PartitionedSAGE
+    from dgl_b200.parallel.partitioned import PartitionedSAGETC
+    dev = comm.device
+    rows, Fin, C = 1024, 32, 8
+    N = rows * world
+    gen = torch.Generator().manual_seed(5)
+    u = torch.cat([torch.randint(0, N, (30000,), generator=gen), torch.randint(0, N, (4000,), generator=gen)]).int()
+    v = torch.cat([torch.randint(0, N, (30000,), generator=gen), torch.full((4000,), 17)]).int()      # one hub row
+    g = dgl.graph((u, v), num_nodes=N, idtype=torch.int32)
+    x = torch.randn(N, Fin, generator=gen)
+    y = torch.randint(0, C, (N,), generator=gen)
+    lo, hi = rank * rows, (rank + 1) * rows
+
+    def rows_of(fmt):
+        indptr, indices, _ = fmt
+        return (indptr[lo:hi + 1] - indptr[lo]).to(dev), indices[int(indptr[lo]): int(indptr[hi])].to(dev)
+
+    ip, ix = rows_of(g._graphs[0].csc())
+    rp, rx = rows_of(g._graphs[0].csr())
+    outs = {}
+    for mode in ("balanced", "fused"):
+        os.environ["DGLB200_HALO_MODE"] = mode
+        torch.manual_seed(0)
+        model = PartitionedSAGE(comm, ip, ix, rows, Fin, 16, C, num_layers=2, reverse=(rp, rx)).to(dev)
+        xin = x[lo:hi].to(dev).requires_grad_()
+        logits = model(xin)
+        (torch.nn.functional.cross_entropy(logits, y[lo:hi].to(dev), reduction="sum") / N).backward()
+        outs[mode] = (logits.detach().cpu(), xin.grad.cpu(), [p_.grad.cpu().clone() for p_ in model.parameters()])
+    os.environ.pop("DGLB200_HALO_MODE")
+    import copy
+    sl, nl = copy.deepcopy(model.self_lin).cpu(), copy.deepcopy(model.neigh_lin).cpu()
+    for p_ in list(sl.parameters()) + list(nl.parameters()):
+        p_.grad = None
+    xo = x.clone().requires_grad_()
+    h = xo
+    for i in range(2):
+        h = sl[i](h) + nl[i](dgl.ops.copy_u_mean(g, h))
+        if i == 0:
+            h = torch.relu(h)
+    (torch.nn.functional.cross_entropy(h, y, reduction="sum") / N).backward()
+    for mode, (lg, gx, _) in outs.items():
+        assert torch.allclose(lg, h[lo:hi].detach(), atol=1e-4), mode
+        assert torch.allclose(gx, xo.grad[lo:hi], atol=1e-5), (mode, (gx - xo.grad[lo:hi]).abs().max())
+    # tensor-core variant (bf16): same function within bf16 tolerance, including the transform-first last layer (16 -> 8)
+    torch.manual_seed(0)
+    tc = PartitionedSAGETC(comm, ip, ix, rows, Fin, 16, C, num_layers=2, reverse=(rp, rx)).to(dev)
+    lt = tc(x[lo:hi].to(dev)).float()
+    assert (lt.cpu() - h[lo:hi].detach()).abs().max() < 0.08 * h.detach().abs().max().clamp(min=1.0)
+    (torch.nn.functional.cross_entropy(lt, y[lo:hi].to(dev), reduction="sum") / N).backward()
+    tc.allreduce_gradients(average=False)
+    for a, b in zip(list(tc.self_lin.parameters()) + list(tc.neigh_lin.parameters()),
+                    list(sl.parameters()) + list(nl.parameters())):
+        scale = b.grad.abs().max().clamp(min=1e-3)
+        assert (a.grad.cpu() - b.grad).abs().max() < 0.08 * scale, ((a.grad.cpu() - b.grad).abs().max(), scale)
+    return True
+
+
 def _w_p2p_cooperative(rank, world, comm):
     import torch.distributed as dist
     from dgl_b200.graphbolt.impl.cooperative import P2PCooperativeConv
@@ -409,6 +471,10 @@ def test_p2p_cooperative_exchange():
 
 def test_partitioned_fullgraph_sage_matches_single_process():
     _run(_w_partitioned_sage)
+
+
+def test_partitioned_sage_pull_backward_and_tensor_core_dense():
+    _run(_w_partitioned_sage_pull_backward)
 
 
 

@@ -2,6 +2,8 @@
 import pytest
 import torch
 
+import dgl_b200 as dgl
+
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
@@ -167,3 +169,144 @@ def test_fused_block_sampler_matches_block_contract(idtype):
     finally:
         fused_sage.ENABLED[0] = True
     assert torch.allclose(y_fused, y_ref, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------------- LABOR-i on the device
+def _labor_oracle(indptr, indices, eids, seeds, fanout, prob, iters):
+    """c, pi by the defining equations, plain Python / fp64 on the host."""
+    indptr, indices = indptr.cpu().tolist(), indices.cpu().tolist()
+    eids = None if eids is None else eids.cpu().tolist()
+    a = (lambda q: 1.0) if prob is None else (lambda q: float(prob[eids[q] if eids is not None else q]))
+    pi = {}
+    rows = [list(range(indptr[s], indptr[s + 1])) for s in seeds.cpu().tolist()]
+    for r in rows:
+        for q in r:
+            pi[indices[q]] = 1.0
+
+    def solve():
+        cs = []
+        for r in rows:
+            w = [pi[indices[q]] * a(q) for q in r]
+            live = sum(1 for x in w if x > 0)
+            if live <= fanout:
+                cs.append(float("inf"))
+                continue
+            lo, hi = 0.0, 1.0
+            while sum(min(1.0, hi * x) for x in w) < fanout:
+                hi *= 2
+            for _ in range(100):
+                mid = (lo + hi) / 2
+                if sum(min(1.0, mid * x) for x in w) >= fanout:
+                    hi = mid
+                else:
+                    lo = mid
+            cs.append(hi)
+        return cs
+
+    c = solve()
+    for _ in range(iters):
+        nxt = {t: 0.0 for t in pi}
+        for r, cs in zip(rows, c):
+            for q in r:
+                t = indices[q]
+                nxt[t] = max(nxt[t], min(cs, 1e30) * pi[t] * a(q))
+        pi = {t: max(v, 1e-12) for t, v in nxt.items()}
+        c = solve()
+    return c, pi, rows
+
+
+@pytest.mark.parametrize("iters", [0, 1, 3])
+@pytest.mark.parametrize("weighted", [False, True])
+def test_labor_importance_kernels_match_oracle(iters, weighted, idtype):
+    from dgl_b200._graph_kernels import labor_sample
+    torch.manual_seed(0)
+    n = 300
+    g = dgl.rand_graph(n, 6000, idtype=idtype)
+    indptr, indices, eids = g._graphs[0].csc()
+    prob = None
+    if weighted:
+        prob = torch.rand(g.num_edges()) + 0.05
+        prob[::7] = 0.0
+    seeds = torch.randperm(n)[:64].to(idtype)
+    fanout = 5
+    d = lambda t: None if t is None else t.to(DEV)
+    src, pos, eid, w, (c, touched, pi) = labor_sample(d(indptr), d(indices), d(eids), d(seeds), fanout, d(prob), iters, 11, 12, 0.0,
+                                                      num_src=n, return_state=True)
+    oc, opi, rows = _labor_oracle(indptr, indices, eids, seeds, fanout, prob, iters)
+    c = c.cpu()
+    for i, (a, b) in enumerate(zip(c.tolist(), oc)):
+        assert (a > 1e37) == (b == float("inf")) and (b == float("inf") or abs(a - b) <= 2e-3 * b), (i, a, b)
+    got_pi = dict(zip(touched.cpu().tolist(), pi.cpu().tolist()))
+    assert set(got_pi) == set(opi)
+    for t, v in opi.items():
+        assert abs(got_pi[t] - v) <= 2e-3 * max(v, 1e-6), (t, got_pi[t], v)
+    # sampled edges are in-edges of their seed, weights are Hajek-normalised, zero-probability edges never appear
+    ind_l, eid_l = indices.tolist(), (None if eids is None else eids.tolist())
+    pos, src, eid, w = pos.cpu().long(), src.cpu(), eid.cpu(), w.cpu()
+    for i, r in enumerate(rows):
+        sel = (pos == i).nonzero().squeeze(1)
+        allowed = {(eid_l[q] if eid_l is not None else q): ind_l[q] for q in r}
+        for j in sel.tolist():
+            assert int(eid[j]) in allowed and allowed[int(eid[j])] == int(src[j])
+            if prob is not None:
+                assert prob[int(eid[j])] > 0
+        if sel.numel():
+            assert abs(float(w[sel].sum()) - 1.0) < 1e-4
+    # a second call sees neutral cached importances again (same result for the same seeds)
+    again = labor_sample(d(indptr), d(indices), d(eids), d(seeds), fanout, d(prob), iters, 11, 12, 0.0, num_src=n)
+    assert torch.equal(again[0].cpu(), src) and torch.allclose(again[3].cpu(), w)
+
+
+def test_labor_shared_variates_expected_size_and_continuous_seed():
+    from dgl_b200._graph_kernels import labor_sample
+    torch.manual_seed(1)
+    n = 2000
+    g = dgl.rand_graph(n, 80000, idtype=torch.int32).to(DEV)
+    indptr, indices, eids = g._graphs[0].csc()
+    seeds = torch.arange(512, dtype=torch.int32, device=DEV)
+    fanout = 10
+    cache = {}
+    sizes, uniq = [], {}
+    for it in (0, 2):
+        tot, un = 0, 0
+        for s in range(20):
+            src, pos, eid, w = labor_sample(indptr, indices, eids, seeds, fanout, None, it, 100 + s, 0, 0.0, num_src=n, cache=cache)
+            tot += src.numel()
+            un += torch.unique(src).numel()
+        sizes.append(tot / 20 / 512)
+        uniq[it] = un / 20
+    assert all(abs(s - fanout) < 0.5 for s in sizes), sizes        # E[#edges per seed] = fanout
+    assert uniq[2] < uniq[0]                                         # importance iterations shrink the union of sources
+    # one variate per source vertex: a source is kept by ALL or NONE of the seeds whose threshold it passes
+    src, pos, eid, w = labor_sample(indptr, indices, eids, seeds, fanout, None, 0, 5, 0, 0.0, num_src=n, cache=cache)
+    deg = (indptr[1:] - indptr[:-1])[seeds.long()].float()
+    thr = (fanout / deg).clamp(max=1.0)
+    kept_thr_min = torch.full((n,), 2.0, device=DEV).scatter_reduce(0, src.long(), thr[pos.long()], "amin")
+    # every (seed, t) in-edge with threshold >= the smallest threshold at which t was kept must be kept too
+    from dgl_b200._graph_kernels import _expand_rows
+    q = _expand_rows(indptr, seeds)
+    owner = torch.repeat_interleave(torch.arange(512, device=DEV), (indptr[1:] - indptr[:-1])[seeds.long()].long())
+    t_all = indices[q].long()
+    must = thr[owner] >= kept_thr_min[t_all]
+    kept_pairs = set(zip(pos.tolist(), src.tolist()))
+    all_pairs = list(zip(owner[must].tolist(), t_all[must].tolist()))
+    assert all(p in kept_pairs for p in all_pairs)
+    # continuous seed: mix = 0 / 1 reproduce the two end-point streams, in between the overlap decays smoothly
+    def keys(mix, s1=7, s2=8):
+        r = labor_sample(indptr, indices, eids, seeds, fanout, None, 0, s1, s2, mix, num_src=n, cache=cache)
+        return set(zip(r[1].tolist(), r[0].tolist()))
+    a, b = keys(0.0), keys(1.0)
+    assert a == keys(0.0, 7, 999) and b == keys(0.0, 8, 0)
+    jac = [len(a & keys(m)) / len(a | keys(m)) for m in (0.1, 0.5, 0.9)]
+    assert jac[0] > jac[1] > jac[2] > len(a & b) / len(a | b) - 0.02
+
+
+def test_sample_labors_uses_device_kernels_for_importance_sampling():
+    g = dgl.rand_graph(500, 20000).to(DEV)
+    g.edata["p"] = torch.rand(g.num_edges(), device=DEV)
+    sg, ws = dgl.sampling.sample_labors(g, torch.arange(100, device=DEV), 5, prob="p", importance_sampling=2, random_seed=3)
+    assert sg.num_edges() == ws[0].numel() > 0
+    u, v = sg.edges()
+    assert set(v.tolist()) <= set(range(100)) and g.has_edges_between(u, v).all()
+    sg2, ws2 = dgl.sampling.sample_labors(g, torch.arange(100, device=DEV), 5, prob="p", importance_sampling=2, random_seed=3)
+    assert torch.equal(sg.edata[dgl.EID], sg2.edata[dgl.EID])
