@@ -26,6 +26,34 @@ import torch.nn.functional as F
 _KEEP = []
 
 
+def make_model(nnmod, kind, in_f=128, hid=256, out_f=172, heads=4):
+    """The same 3-layer mini-batch model on either arm (``nnmod`` = dgl.nn or dgl_b200.nn): GraphSAGE-mean or GAT."""
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            if kind == "gat":
+                d = hid // heads
+                self.layers = nn.ModuleList([nnmod.GATConv(in_f, d, heads, allow_zero_in_degree=True),
+                                             nnmod.GATConv(hid, d, heads, allow_zero_in_degree=True),
+                                             nnmod.GATConv(hid, out_f, 1, allow_zero_in_degree=True)])
+            else:
+                self.layers = nn.ModuleList([nnmod.SAGEConv(in_f, hid, "mean"), nnmod.SAGEConv(hid, hid, "mean"),
+                                             nnmod.SAGEConv(hid, out_f, "mean")])
+            self.dropout = nn.Dropout(0.5)
+
+        def forward(self, blocks, x):
+            h = x
+            for l, (layer, block) in enumerate(zip(self.layers, blocks)):
+                h = layer(block, h)
+                h = h.flatten(1) if h.dim() == 3 else h
+                if l != 2:
+                    h = self.dropout(F.relu(h))
+            return h
+
+    return Net()
+
+
 def make_graph(scale):
     n = int(111_059_956 * scale)
     e = int(1_615_685_872 * scale)
@@ -60,7 +88,7 @@ def run_ours(args, n, u, v, feat, labels, train):
     dp = dp.sample_neighbor(fg, args.fanouts).fetch_feature(store, ["feat"])
     # with the prefetch thread the UVA gather is capped to 10240 threads (gb default) so that it leaves SMs to the model
     loader = gb.DataLoader(dp, num_workers=args.workers, max_uva_threads=10240 if args.workers else 0)
-    model = GraphSAGE(128, 256, 172, 3, 0.5).to(dev)
+    model = (GraphSAGE(128, 256, 172, 3, 0.5) if args.model == "sage" else make_model(dgl.nn, args.model)).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 
     def batches():
@@ -92,22 +120,7 @@ def run_reference(args, n, u, v, feat, labels, train):
     dl = dgl.dataloading.DataLoader(g, train.int().to(dev), sampler, device=dev, batch_size=args.batch, shuffle=True,
                                     drop_last=False, num_workers=0, use_uva=not device_resident)
 
-    class SAGE(nn.Module):
-        def __init__(self):
-            super().__init__()
-            self.layers = nn.ModuleList([dglnn.SAGEConv(128, 256, "mean"), dglnn.SAGEConv(256, 256, "mean"),
-                                         dglnn.SAGEConv(256, 172, "mean")])
-            self.dropout = nn.Dropout(0.5)
-
-        def forward(self, blocks, x):
-            h = x
-            for l, (layer, block) in enumerate(zip(self.layers, blocks)):
-                h = layer(block, h)
-                if l != 2:
-                    h = self.dropout(F.relu(h))
-            return h
-
-    model = SAGE().to(dev)
+    model = make_model(dglnn, args.model).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=1e-3)
 
     def batches():
@@ -131,6 +144,7 @@ def main():
     ap.add_argument("--resident", default="host", choices=["host", "device"],
                     help="host: graph + features pinned in host memory (UVA, config 5); device: both in HBM")
     ap.add_argument("--amp", action="store_true", help="bf16 autocast (ours: SAGEConv takes the tcgen05 fused layer)")
+    ap.add_argument("--model", default="sage", choices=["sage", "gat"], help="3-layer GraphSAGE-mean (default) or 4-head GAT")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
     args.fanouts = [10, 10, 10]
@@ -162,7 +176,7 @@ def main():
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / args.steps
-    rec = dict(bench="sage_uva_pipeline" if args.resident == "host" else "sage_generic_pipeline_device_resident", impl=args.impl, scale=args.scale, nodes=n, edges=int(u.shape[0]), feat_dim=128,
+    rec = dict(bench=f"{args.model}_uva_pipeline" if args.resident == "host" else f"{args.model}_generic_pipeline_device_resident", impl=args.impl, scale=args.scale, nodes=n, edges=int(u.shape[0]), feat_dim=128,
                batch=args.batch, fanouts=args.fanouts, ms_per_step=ms, sampled_edges_per_s=edges / args.steps / ms * 1e3,
                input_rows_per_step=inputs / args.steps, uva_feature_GBps=inputs / args.steps * 512 / ms / 1e6,
                gpu_cache_mb=args.cache_mb, workers=args.workers, amp=args.amp, final_loss=loss, steps=args.steps, warmup=args.warmup, graph_build_s=gen_s)

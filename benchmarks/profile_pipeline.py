@@ -18,6 +18,7 @@ def main():
         pass
     args = A()
     args.resident, args.cache_mb, args.batch, args.workers, args.fanouts, args.amp = "device", 0, 1024, 0, [10, 10, 10], False
+    args.model = "sage"
     n, u, v, feat, labels, train = B.make_graph(float(os.environ.get("SCALE", "0.02")))
     model, opt, it, _, _ = B.run_ours(args, n, u, v, feat, labels, train)
 
