@@ -11,6 +11,9 @@ import torch
 
 from ..base import DGLError
 from .kvstore import EDGE_PART_POLICY, NODE_PART_POLICY, KVClient, PartitionPolicy
+from .kvstore import close_kvstore, default_pull_handler, default_push_handler, get_kvstore, init_kvstore  # noqa: F401,E402
+from .partition import (cast_various_to_minimum_dtype_gb, init_type_per_edge, is_homogeneous,  # noqa: F401,E402
+                        process_partitions)
 
 __all__ = ["IdMap", "HeteroDataName", "parse_hetero_data_name", "NodePartitionPolicy", "EdgePartitionPolicy",
            "get_shared_mem_partition_book", "get_node_partition_from_book", "default_pull_handler",
@@ -144,32 +147,6 @@ def get_node_partition_from_book(book, device):
 
 
 # ---- kvstore module-level API ------------------------------------------------------------------------------------------
-def default_pull_handler(target, name, id_tensor):
-    """Rows ``id_tensor`` of the local shard ``target[name]``."""
-    return target[name][id_tensor]
-
-
-def default_push_handler(target, name, id_tensor, data_tensor):
-    """Overwrite rows ``id_tensor`` of the local shard (no aggregation)."""
-    target[name][id_tensor] = data_tensor
-
-
-_KVSTORE = [None]
-
-
-def init_kvstore(ip_config=None, num_servers=1, role="default"):
-    """Create the process-wide :class:`KVClient` (requires ``dgl.distributed.initialize()``)."""
-    if _KVSTORE[0] is None:
-        _KVSTORE[0] = KVClient(ip_config, num_servers, role)
-    return _KVSTORE[0]
-
-
-def get_kvstore():
-    return _KVSTORE[0]
-
-
-def close_kvstore():
-    _KVSTORE[0] = None
 
 
 # ---- rpc_client helpers ------------------------------------------------------------------------------------------------
@@ -340,43 +317,6 @@ class Collator:
 
 
 # ---- partition.py helpers ------------------------------------------------------------------------------------------------
-def is_homogeneous(ntypes, etypes):
-    return len(ntypes) == 1 and len(etypes) == 1
-
-
-def init_type_per_edge(graph, gpb):
-    """Edge-type id of every edge of a partition's local graph (from its global edge ids)."""
-    from ..base import EID
-    etype_ids, _ = gpb.map_to_per_etype(graph.edata[EID])
-    return etype_ids.to(torch.int32 if len(gpb.etypes) < 2 ** 15 else torch.int64)
-
-
-def cast_various_to_minimum_dtype_gb(num_parts, indptr, indices, type_per_edge, etypes, ntypes, node_attributes,
-                                     edge_attributes, part_meta=None, graph=None, edge_count=None, node_count=None):
-    """Narrow the arrays of a GraphBolt partition to the smallest integer type that holds their value range
-    (structure ids by node/edge count, type ids by the number of types). Returns the same tuple of arrays."""
-    def narrow(t, upper):
-        if t is None:
-            return None
-        for dt in (torch.int8, torch.int16, torch.int32):
-            if upper <= torch.iinfo(dt).max:
-                return t.to(dt)
-        return t.to(torch.int64)
-
-    n_edges = int(indices.shape[0]) if edge_count is None else int(edge_count)
-    n_nodes = int(indptr.shape[0] - 1) if node_count is None else int(node_count)
-    indptr = indptr.to(torch.int32) if n_edges <= torch.iinfo(torch.int32).max else indptr.to(torch.int64)
-    indices = indices.to(torch.int32) if n_nodes <= torch.iinfo(torch.int32).max else indices.to(torch.int64)
-    type_per_edge = narrow(type_per_edge, len(etypes))
-    return indptr, indices, type_per_edge
-
-
-def process_partitions(g, formats=None, sort_etypes=False):
-    """Prepare a partition's local graph for saving: build the requested sparse formats (and only those)."""
-    if formats is not None:
-        g = g.formats(list(formats) if not isinstance(formats, str) else [formats])
-        g.create_formats_()
-    return g
 
 
 # ---- dist_context -------------------------------------------------------------------------------------------------------

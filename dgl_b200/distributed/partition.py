@@ -433,8 +433,11 @@ def cast_various_to_minimum_dtype_gb(num_parts, indptr, indices, type_per_edge, 
             raise DGLError("part_meta is needed when the counts are taken from a graph")
         tot_edge_count, tot_node_count = graph.num_edges(), graph.num_nodes()
         node_count, edge_count = part_meta["num_nodes"], part_meta["num_edges"]
-    elif None in (tot_edge_count, tot_node_count, edge_count, node_count):
-        raise DGLError("pass either `graph` + `part_meta` or all four counts")
+    else:                                            # counts not given: take them from the arrays themselves
+        tot_edge_count = int(indptr[-1]) if tot_edge_count is None else tot_edge_count
+        tot_node_count = int(indptr.shape[0]) - 1 if tot_node_count is None else tot_node_count
+        edge_count = tot_edge_count if edge_count is None else edge_count
+        node_count = tot_node_count if node_count is None else node_count
     indptr = _narrowest_int(tot_edge_count, indptr)
     indices = _narrowest_int(tot_node_count, indices)
     if type_per_edge is not None:

@@ -17,118 +17,15 @@ import torch
 from .datapipes import MiniBatchTransformer, _Stage
 from .impl.caches import FeatureCache, GPUCache
 from .impl.features import Feature
+from .dataset import Dataset, Task  # noqa: F401
+from .feature_store import FeatureKey, FeatureStore  # noqa: F401
+from .impl.legacy_dataset import LegacyDataset  # noqa: F401
+from .impl.ondisk_metadata import (ExtraMetaData, OnDiskFeatureData, OnDiskFeatureDataDomain,  # noqa: F401
+                                   OnDiskFeatureDataFormat, OnDiskGraphTopology, OnDiskGraphTopologyType, OnDiskMetaData,
+                                   OnDiskTaskData, OnDiskTVTSet, OnDiskTVTSetData)
+from .sampling_graph import SamplingGraph  # noqa: F401
 
 # ---------------------------------------------------------------------------------------------- abstract bases
-FeatureKey = namedtuple("FeatureKey", ["domain", "type", "name"])
-
-
-class FeatureStore:
-    """Abstract collection of features addressed by (domain, type, name) (reference feature_store.py)."""
-
-    def __getitem__(self, feature_key) -> Feature:
-        raise NotImplementedError
-
-    def __setitem__(self, feature_key, feature):
-        raise NotImplementedError
-
-    def __contains__(self, feature_key) -> bool:
-        raise NotImplementedError
-
-    def read(self, domain, type_name, feature_name, ids=None):
-        return self[(domain, type_name, feature_name)].read(ids)
-
-    def size(self, domain, type_name, feature_name):
-        return self[(domain, type_name, feature_name)].size()
-
-    def count(self, domain, type_name, feature_name):
-        return self[(domain, type_name, feature_name)].count()
-
-    def metadata(self, domain, type_name, feature_name):
-        return self[(domain, type_name, feature_name)].metadata()
-
-    def update(self, domain, type_name, feature_name, value, ids=None):
-        self[(domain, type_name, feature_name)].update(value, ids)
-
-    def keys(self):
-        raise NotImplementedError
-
-
-class SamplingGraph:
-    """Abstract sampling graph (reference sampling_graph.py)."""
-
-    @property
-    def num_nodes(self):
-        raise NotImplementedError
-
-    @property
-    def num_edges(self):
-        raise NotImplementedError
-
-    def copy_to_shared_memory(self, shared_memory_name):
-        raise NotImplementedError
-
-    def to(self, device):
-        raise NotImplementedError
-
-
-class Task:
-    """Abstract task: metadata + train / validation / test item sets (reference dataset.py)."""
-
-    metadata: Dict[str, Any] = None
-    train_set = validation_set = test_set = None
-
-
-class Dataset:
-    """Abstract dataset: tasks, graph, feature store, name, all-nodes set (reference dataset.py)."""
-
-    @property
-    def tasks(self):
-        raise NotImplementedError
-
-    @property
-    def graph(self):
-        raise NotImplementedError
-
-    @property
-    def feature(self):
-        raise NotImplementedError
-
-    @property
-    def dataset_name(self):
-        raise NotImplementedError
-
-    @property
-    def all_nodes_set(self):
-        raise NotImplementedError
-
-
-class LegacyDataset(Dataset):
-    """GraphBolt view of a legacy ``dgl.data`` node-classification dataset (reference impl/legacy_dataset.py)."""
-
-    def __init__(self, legacy):
-        from .impl.features import BasicFeatureStore, TorchBasedFeature
-        from .impl.fused_csc_sampling_graph import from_dglgraph
-        from .itemset import ItemSet
-        g = legacy[0]
-        self._name = getattr(legacy, "name", type(legacy).__name__)
-        self._graph = from_dglgraph(g)
-        self._feature = BasicFeatureStore({("node", None, k): TorchBasedFeature(v) for k, v in g.ndata.items()
-                                           if v.is_floating_point()})
-        task = Task()
-        task.metadata = {"name": "node_classification", "num_classes": getattr(legacy, "num_classes", None)}
-        lab = g.ndata.get("label")
-        for split, mask in (("train_set", "train_mask"), ("validation_set", "val_mask"), ("test_set", "test_mask")):
-            if mask in g.ndata and lab is not None:
-                ids = g.ndata[mask].nonzero().squeeze(1)
-                setattr(task, split, ItemSet((ids, lab[ids]), names=("seeds", "labels")))
-        self._tasks = [task]
-        self._all = ItemSet(g.num_nodes(), names="seeds")
-
-    tasks = property(lambda self: self._tasks)
-    graph = property(lambda self: self._graph)
-    feature = property(lambda self: self._feature)
-    dataset_name = property(lambda self: self._name)
-    all_nodes_set = property(lambda self: self._all)
 
 
 CPUFeatureCache = FeatureCache
@@ -242,77 +139,6 @@ def minibatcher_default(batch, names):
 
 
 # ---------------------------------------------------------------------------------------------- metadata.yaml models
-class OnDiskFeatureDataFormat(str, enum.Enum):
-    TORCH = "torch"
-    NUMPY = "numpy"
-
-
-class OnDiskTVTSetData(dict):
-    """One entry of a train / validation / test set: name, format, in_memory, path (reference ondisk_metadata.py)."""
-
-    def __init__(self, name=None, format="numpy", in_memory=True, path=None, **kw):
-        super().__init__(name=name, format=str(getattr(format, "value", format)), in_memory=in_memory, path=path, **kw)
-        self.__dict__ = self
-
-
-class OnDiskTVTSet(dict):
-    def __init__(self, type=None, data=None, **kw):
-        super().__init__(type=type, data=[OnDiskTVTSetData(**d) if not isinstance(d, OnDiskTVTSetData) else d for d in (data or [])], **kw)
-        self.__dict__ = self
-
-
-class OnDiskFeatureDataDomain(str, enum.Enum):
-    NODE = "node"
-    EDGE = "edge"
-    GRAPH = "graph"
-
-
-class OnDiskFeatureData(dict):
-    def __init__(self, domain=None, type=None, name=None, format="numpy", path=None, in_memory=True, **kw):
-        super().__init__(domain=str(getattr(domain, "value", domain)), type=type, name=name,
-                         format=str(getattr(format, "value", format)), path=path, in_memory=in_memory, **kw)
-        self.__dict__ = self
-
-
-class OnDiskGraphTopologyType(str, enum.Enum):
-    FUSED_CSC_SAMPLING = "FusedCSCSamplingGraph"
-
-
-class OnDiskGraphTopology(dict):
-    def __init__(self, type=OnDiskGraphTopologyType.FUSED_CSC_SAMPLING, path=None, **kw):
-        super().__init__(type=str(getattr(type, "value", type)), path=path, **kw)
-        self.__dict__ = self
-
-
-class OnDiskTaskData(dict):
-    def __init__(self, train_set=None, validation_set=None, test_set=None, **extra_fields):
-        super().__init__(train_set=train_set or [], validation_set=validation_set or [], test_set=test_set or [], **extra_fields)
-        self.__dict__ = self
-
-
-class ExtraMetaData(dict):
-    """Base of the metadata models: unknown keys are kept and grouped under ``extra_fields`` (reference
-    impl/ondisk_metadata.py:24)."""
-
-    _known = ()
-
-    def __init__(self, **kw):
-        extra = dict(kw.pop("extra_fields", None) or {})
-        for k in list(kw):
-            if self._known and k not in self._known:
-                extra[k] = kw.pop(k)
-        super().__init__(extra_fields=extra, **kw)
-        self.__dict__ = self
-
-
-class OnDiskMetaData(dict):
-    """Top-level model of ``metadata.yaml`` (dataset_name, graph_topology, feature_data, tasks, include_original_edge_id)."""
-
-    def __init__(self, dataset_name=None, graph_topology=None, feature_data=None, tasks=None, include_original_edge_id=False,
-                 **kw):
-        super().__init__(dataset_name=dataset_name, graph_topology=graph_topology, feature_data=feature_data or [],
-                         tasks=tasks or [], include_original_edge_id=include_original_edge_id, **kw)
-        self.__dict__ = self
 
 
 def preprocess_ondisk_dataset(dataset_dir, include_original_edge_id=False, force_preprocess=None, auto_cast_to_optimal_dtype=True):
