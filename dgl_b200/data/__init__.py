@@ -7,6 +7,8 @@ def __getattr__(name):
     if name.startswith("__"):
         raise AttributeError(name)
     import importlib
+    if name == "citegrh":        # legacy alias of the citation-graph module (reference data/__init__.py)
+        return importlib.import_module(f"{__name__}.citation_graph")
     for modname in ("dgl_dataset", "graph_serialize", "more", "builtin", "csv_dataset", "utils", "extra", "compat"):
         mod = importlib.import_module(f"{__name__}.{modname}")
         if hasattr(mod, name):

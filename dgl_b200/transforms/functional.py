@@ -529,11 +529,15 @@ def pairwise_squared_distance(x):
     return x2 + x2.transpose(-1, -2) - 2 * x @ x.transpose(-1, -2)
 
 
+NN_DESCENT_MIN_POINTS = 4096   # below this the exact kernels are cheaper than the descent rounds
+
+
 def knn(k, x, x_segs, y=None, y_segs=None, algorithm="bruteforce", dist="euclidean"):
     """For every point of every segment of ``y`` the ``k`` nearest points of the same segment of ``x`` (self query when
     ``y`` is None). Returns a ``[2, k * len(y)]`` id tensor: row 0 indexes ``y``, row 1 indexes ``x`` (reference
     functional.py:641). 'kd-tree' (host) uses the native tree; the brute-force names use the shared-memory kernel on
-    the GPU and the tree / GEMM path on the host; 'nn-descent' is served exactly."""
+    the GPU and the tree / GEMM path on the host; 'nn-descent' (self query) runs the approximate tensorised NN-descent for
+    sets larger than ``NN_DESCENT_MIN_POINTS`` and the exact search below it."""
     if algorithm == "nn-descent" and y is not None:
         raise DGLError("Currently 'nn-descent' only supports self-query cases.")
     if y is None:
@@ -561,7 +565,11 @@ def knn(k, x, x_segs, y=None, y_segs=None, algorithm="bruteforce", dist="euclide
         y = y / (y.norm(dim=1, keepdim=True) + 1e-5)
     xo = torch.cat([torch.zeros(1, dtype=torch.long), x_segs.cumsum(0)])
     yo = torch.cat([torch.zeros(1, dtype=torch.long), y_segs.cumsum(0)])
-    if x.device.type == "cpu" and x.dtype == y.dtype and x.dtype in (torch.float32, torch.float64) and \
+    if algorithm == "nn-descent" and x.shape[0] > NN_DESCENT_MIN_POINTS:
+        # approximate search for large sets (any dimension, any device): tensorised NN-descent, transforms/nn_descent.py
+        from .nn_descent import nn_descent
+        idx = nn_descent(x, xo, k)
+    elif x.device.type == "cpu" and x.dtype == y.dtype and x.dtype in (torch.float32, torch.float64) and \
             (algorithm == "kd-tree" or x.shape[1] <= 16):
         idx = kdtree_knn(x, y, k, xo, yo)[0]
     elif x.is_cuda and x.shape[1] <= 16 and k <= 64 and x.dtype == y.dtype and x.dtype in (

@@ -108,3 +108,37 @@ def test_neighbor_matching_is_a_maximal_matching(weighted, idtype):
     torch.manual_seed(7)  # same visiting order -> same matching, now relabelled to 0..C-1
     r = neighbor_matching(g, w)
     assert int(r.max()) + 1 == int((sizes > 0).sum())
+
+
+def test_nn_descent_recall_segments_and_knn_entry():
+    """Approximate kNN: neighbours stay inside their segment, no duplicates, self first, high recall on clustered data;
+    ``knn(..., algorithm='nn-descent')`` switches to it for large sets."""
+    import dgl_b200 as dgl
+    from dgl_b200.transforms import functional as TF
+    from dgl_b200.transforms.nn_descent import nn_descent
+    torch.manual_seed(0)
+    centres = torch.randn(40, 24) * 4
+    x = centres[torch.randint(0, 40, (5000,))] + torch.randn(5000, 24)
+    offs = [0, 1800, 5000]
+    k = 8
+    nb = nn_descent(x, offs, k)
+    hits = 0
+    for lo, hi in zip(offs[:-1], offs[1:]):
+        got = nb[lo:hi]
+        assert (got >= lo).all() and (got < hi).all()
+        exact = torch.cdist(x[lo:hi], x[lo:hi]).topk(k, largest=False).indices + lo
+        hits += sum(len(set(a.tolist()) & set(b.tolist())) for a, b in zip(exact, got))
+    assert hits / (5000 * k) > 0.93
+    assert (nb[:, 0] == torch.arange(5000)).all() and all(len(set(r)) == k for r in nb.tolist())
+    # tiny segments (fewer points than k + 1) are still served
+    small = nn_descent(torch.randn(7, 3), [0, 3, 7], 3)
+    assert small.shape == (7, 3) and (small[:3] < 3).all() and (small[3:] >= 3).all()
+    old = TF.NN_DESCENT_MIN_POINTS
+    TF.NN_DESCENT_MIN_POINTS = 1000
+    try:
+        pairs = dgl.knn(k, x, [1800, 3200], algorithm="nn-descent")
+    finally:
+        TF.NN_DESCENT_MIN_POINTS = old
+    assert pairs.shape == (2, 5000 * k) and pairs[0].tolist() == torch.arange(5000).repeat_interleave(k).tolist()
+    g = dgl.knn_graph(x, k, algorithm="nn-descent")
+    assert g.num_edges() == 5000 * k
