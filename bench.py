@@ -135,7 +135,10 @@ def dist_setup(n_gpus):
     torch.cuda.set_device(dev)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        # a mismatched collective must fail fast, not sit in the default 10-minute watchdog on a multi-GPU box
+        import datetime
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev,
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("BENCH_NCCL_TIMEOUT_S", "240"))))
     return rank, world, dev
 
 

@@ -135,11 +135,13 @@ def run_ours(args):
     B.barrier_sync(dev)
     ms = B.max_over_ranks(e0.elapsed_time(e1), dev) / args.steps
     ck = clocks.stop()
-    loss_g = B.sum_over_ranks(float(loss) / world, dev)
+    loss_g = B.sum_over_ranks(float(loss.detach()) / world, dev)
     plan = model.agg.plan
     halo_rows = B.sum_over_ranks(plan.n_halo, dev)
     cut = B.sum_over_ranks(cut_local * lidx.numel(), dev) / max(B.sum_over_ranks(lidx.numel(), dev), 1)
     peak = B.max_over_ranks(torch.cuda.max_memory_allocated(dev) / 2 ** 30, dev)
+    edges_max = B.max_over_ranks(lidx.numel(), dev)               # collectives: every rank, outside the rank-0 branch
+    edges_mean = B.sum_over_ranks(lidx.numel(), dev) / world
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": ms / 1e3, "unit": "s/epoch", "impl": "ours", "mode": "partitioned", "n_gpus": world,
@@ -149,7 +151,7 @@ def run_ours(args):
                        "parallelism": f"vertex-partition x{world} (LDG edge-cut partitioner, P2P halo)",
                        "edge_cut_fraction": cut, "halo_rows_total": halo_rows, "shard_rows": shard_rows,
                        "partition_time_s": t_part, "peak_mem_gib": peak,
-                       "local_edges_max": B.max_over_ranks(lidx.numel(), dev), "local_edges_mean": B.sum_over_ranks(lidx.numel(), dev) / world,
+                       "local_edges_max": edges_max, "local_edges_mean": edges_mean,
                        "halo_bytes_per_layer_fwd": halo_rows * HIDDEN * 2}}), flush=True)
     if dist.is_initialized():
         dist.destroy_process_group()

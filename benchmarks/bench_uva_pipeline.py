@@ -74,6 +74,22 @@ def run_ours(args, n, u, v, feat, labels, train):
     from dgl_b200.models import GraphSAGE
     dev = "cuda"
     g = dgl.graph((u.int(), v.int()), num_nodes=n, idtype=torch.int32)
+    if args.graphed:
+        # the same nn.Module model and torch optimizer, but the whole step (sampling .. optimizer) replayed as ONE CUDA graph
+        from dgl_b200.dataloading import GraphedTrainer
+        g = g.to(dev)
+        g.create_formats_()
+        model = GraphSAGE(128, 256, 172, 3, 0.5).to(dev)
+        opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
+        trainer = GraphedTrainer(g, feat.to(dev), labels.to(dev), model, opt, args.fanouts, args.batch, amp=args.amp)
+        args._trainer = trainer
+
+        def seed_batches():
+            while True:
+                perm = train[torch.randperm(train.numel())]
+                for i in range(0, perm.numel(), args.batch):
+                    yield perm[i:i + args.batch]
+        return model, opt, seed_batches(), None, None
     if args.resident == "device":          # graph + features in HBM: the generic (non-fused) GPU pipeline
         fg = gb.from_dglgraph(g).to(dev)
         feature = gb.TorchBasedFeature(feat.to(dev))
@@ -144,6 +160,7 @@ def main():
     ap.add_argument("--resident", default="host", choices=["host", "device"],
                     help="host: graph + features pinned in host memory (UVA, config 5); device: both in HBM")
     ap.add_argument("--amp", action="store_true", help="bf16 autocast (ours: SAGEConv takes the tcgen05 fused layer)")
+    ap.add_argument("--graphed", action="store_true", help="ours, device resident: dataloading.GraphedTrainer (whole step as one CUDA graph)")
     ap.add_argument("--model", default="sage", choices=["sage", "gat"], help="3-layer GraphSAGE-mean (default) or 4-head GAT")
     ap.add_argument("--out", default=None)
     args = ap.parse_args()
@@ -153,7 +170,15 @@ def main():
     gen_s = time.time() - t0
     model, opt, it, count_edges, count_inputs = (run_ours if args.impl == "ours" else run_reference)(args, n, u, v, feat, labels, train)
 
+    def graphed_step():
+        tr = args._trainer
+        before = tr.edges.clone()
+        loss = tr.step(next(it))
+        return float(loss), int((tr.edges - before).item()), 0
+
     def step():
+        if args.graphed:
+            return graphed_step()
         blocks, x, y = next(it)
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=args.amp):
             logits = model(blocks, x)
@@ -179,7 +204,7 @@ def main():
     rec = dict(bench=f"{args.model}_uva_pipeline" if args.resident == "host" else f"{args.model}_generic_pipeline_device_resident", impl=args.impl, scale=args.scale, nodes=n, edges=int(u.shape[0]), feat_dim=128,
                batch=args.batch, fanouts=args.fanouts, ms_per_step=ms, sampled_edges_per_s=edges / args.steps / ms * 1e3,
                input_rows_per_step=inputs / args.steps, uva_feature_GBps=inputs / args.steps * 512 / ms / 1e6,
-               gpu_cache_mb=args.cache_mb, workers=args.workers, amp=args.amp, final_loss=loss, steps=args.steps, warmup=args.warmup, graph_build_s=gen_s)
+               gpu_cache_mb=args.cache_mb, workers=args.workers, amp=args.amp, graphed=args.graphed, final_loss=loss, steps=args.steps, warmup=args.warmup, graph_build_s=gen_s)
     print(json.dumps(rec), flush=True)
     if args.out:
         with open(args.out, "a") as f:

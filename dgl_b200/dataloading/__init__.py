@@ -29,3 +29,5 @@ def __getattr__(name):
         from ..distributed import dist_graph
         return getattr(dist_graph, name)
     raise AttributeError(name)
+
+from .graphed import CapacityBlock, GraphedTrainer  # noqa: F401,E402

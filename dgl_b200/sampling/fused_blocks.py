@@ -96,11 +96,32 @@ class FusedBlockSampler:
             ws = self._ws[key] = _Workspace(cap, self.fanouts, device)
         return ws
 
+    def enqueue(self, ws, indptr, indices, uva=False, step_dev=None):
+        """Enqueue every layer on the workspace's capacity buffers (seeds in ``ws.seeds``, their count in ``ws.n[L]``)
+        WITHOUT reading anything back: returns (S, nbr_local) lists indexed by layer. With ``step_dev`` (int64[1] on the
+        device) the random stream is keyed by that counter instead of a host value, so the sequence is CUDA-graph
+        capturable and still differs from replay to replay."""
+        lib = loader.cuda_lib()
+        L = len(self.fanouts)
+        S = [None] * (L + 1)
+        nbr_local = [None] * (L + 1)
+        S[L] = ws.seeds
+        it = id_code(torch.int32)
+        for l in range(L, 0, -1):
+            f = self.fanouts[l - 1]
+            ws.totals[l].zero_()
+            host_seed = self.seed * 7919 + l + (0 if step_dev is not None else 131 * self._step)
+            lib.fn("dglb200_cuda_sample_ell", "ippiplpilpppppi" + "p")(
+                it, _p(indptr), _p(indices), 1 if uva else 0, _p(S[l]), ws.caps[l], _p(ws.n[l]), f, host_seed, _p(step_dev),
+                _p(ws.nbr_g[l]), _p(ws.eid[l]), _p(ws.cnt[l]), _p(ws.totals[l]), 1, loader.stream_ptr())
+            S[l - 1], nbr_local[l], n_prev, _ = ws.compactors[l].compact(S[l], ws.n[l], ws.nbr_g[l])
+            ws.n[l - 1] = n_prev
+        return S, nbr_local
+
     def sample_layers(self, indptr, indices, seeds, uva=False):
         """Core pipeline on int32 CSC arrays (device, or host-pinned with ``uva``). Returns per layer l = 1..L a dict with
         ``dst`` / ``src`` (global ids), ``nbr`` (local ELL), ``cnt``, ``eid`` (CSC positions, ELL shaped), ``fanout``,
         ``n_dst`` / ``n_src`` / ``n_edges`` (host ints) - after exactly ONE host synchronisation."""
-        lib = loader.cuda_lib()
         dev = seeds.device
         L = len(self.fanouts)
         n_seeds = int(seeds.shape[0])
@@ -110,20 +131,7 @@ class FusedBlockSampler:
             ws.seeds[n_seeds:] = -1
         ws.n[L].fill_(n_seeds)
         self._step += 1
-        S = [None] * (L + 1)
-        nbr_local = [None] * (L + 1)
-        S[L] = ws.seeds
-        it = id_code(torch.int32)
-        # ---- every layer enqueued without looking at a size
-        for l in range(L, 0, -1):
-            f = self.fanouts[l - 1]
-            ws.totals[l].zero_()
-            lib.fn("dglb200_cuda_sample_ell", "ippiplpilpppppi" + "p")(
-                it, _p(indptr), _p(indices), 1 if uva else 0, _p(S[l]), ws.caps[l], _p(ws.n[l]), f,
-                self.seed * 7919 + l + 131 * self._step, 0, _p(ws.nbr_g[l]), _p(ws.eid[l]), _p(ws.cnt[l]), _p(ws.totals[l]), 1,
-                loader.stream_ptr())
-            S[l - 1], nbr_local[l], n_prev, _ = ws.compactors[l].compact(S[l], ws.n[l], ws.nbr_g[l])
-            ws.n[l - 1] = n_prev
+        S, nbr_local = self.enqueue(ws, indptr, indices, uva)
         # ---- ONE host read: node counts of S_L .. S_0 and the edge count of every layer
         packed = torch.cat([ws.n[l].view(1) for l in range(L, -1, -1)] + [ws.totals[l].sum().view(1) for l in range(L, 0, -1)])
         ws.counts_host.copy_(packed, non_blocking=True)
