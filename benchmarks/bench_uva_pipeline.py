@@ -81,7 +81,8 @@ def run_ours(args, n, u, v, feat, labels, train):
         g.create_formats_()
         model = GraphSAGE(128, 256, 172, 3, 0.5).to(dev)
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
-        trainer = GraphedTrainer(g, feat.to(dev), labels.to(dev), model, opt, args.fanouts, args.batch, amp=args.amp)
+        trainer = GraphedTrainer(g, feat.to(dev), labels.to(dev), model, opt, args.fanouts, args.batch, amp=args.amp,
+                                 gather_inputs=not args.table_input)
         args._trainer = trainer
 
         def seed_batches():
@@ -160,6 +161,7 @@ def main():
     ap.add_argument("--resident", default="host", choices=["host", "device"],
                     help="host: graph + features pinned in host memory (UVA, config 5); device: both in HBM")
     ap.add_argument("--amp", action="store_true", help="bf16 autocast (ours: SAGEConv takes the tcgen05 fused layer)")
+    ap.add_argument("--table-input", action="store_true", help="with --graphed: the first SAGEConv reads the feature table in place")
     ap.add_argument("--graphed", action="store_true", help="ours, device resident: dataloading.GraphedTrainer (whole step as one CUDA graph)")
     ap.add_argument("--model", default="sage", choices=["sage", "gat"], help="3-layer GraphSAGE-mean (default) or 4-head GAT")
     ap.add_argument("--out", default=None)
@@ -204,7 +206,7 @@ def main():
     rec = dict(bench=f"{args.model}_uva_pipeline" if args.resident == "host" else f"{args.model}_generic_pipeline_device_resident", impl=args.impl, scale=args.scale, nodes=n, edges=int(u.shape[0]), feat_dim=128,
                batch=args.batch, fanouts=args.fanouts, ms_per_step=ms, sampled_edges_per_s=edges / args.steps / ms * 1e3,
                input_rows_per_step=inputs / args.steps, uva_feature_GBps=inputs / args.steps * 512 / ms / 1e6,
-               gpu_cache_mb=args.cache_mb, workers=args.workers, amp=args.amp, graphed=args.graphed, final_loss=loss, steps=args.steps, warmup=args.warmup, graph_build_s=gen_s)
+               gpu_cache_mb=args.cache_mb, workers=args.workers, amp=args.amp, graphed=args.graphed, table_input=args.table_input, final_loss=loss, steps=args.steps, warmup=args.warmup, graph_build_s=gen_s)
     print(json.dumps(rec), flush=True)
     if args.out:
         with open(args.out, "a") as f:

@@ -18,11 +18,15 @@ def main():
         pass
     args = A()
     args.resident, args.cache_mb, args.batch, args.workers, args.fanouts, args.amp = "device", 0, 1024, 0, [10, 10, 10], False
-    args.model = "sage"
+    args.model = os.environ.get("MODEL", "sage")
+    args.graphed = os.environ.get("GRAPHED", "0") == "1"
+    args.table_input = os.environ.get("TABLE", "0") == "1"
     n, u, v, feat, labels, train = B.make_graph(float(os.environ.get("SCALE", "0.02")))
     model, opt, it, _, _ = B.run_ours(args, n, u, v, feat, labels, train)
 
     def step():
+        if args.graphed:
+            return args._trainer.step(next(it))
         blocks, x, y = next(it)
         loss = F.cross_entropy(model(blocks, x).float(), y)
         opt.zero_grad(set_to_none=True)
@@ -38,8 +42,9 @@ def main():
         for _ in range(10):
             step()
         torch.cuda.synchronize()
-    print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=35, max_name_column_width=60))
-    print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=25, max_name_column_width=60))
+    if not args.graphed:
+        print(prof.key_averages().table(sort_by="self_cpu_time_total", row_limit=25, max_name_column_width=60))
+    print(prof.key_averages().table(sort_by="self_cuda_time_total", row_limit=30, max_name_column_width=90))
 
 
 if __name__ == "__main__":

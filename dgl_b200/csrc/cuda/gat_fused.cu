@@ -46,7 +46,9 @@ __global__ void __launch_bounds__(256) gat_fwd_kernel(const I* __restrict__ indp
                                                       float* __restrict__ lbuf, int sub) {
   constexpr int VEC = Vec16<T>::N;
   const int rpb = blockDim.x / sub;
-  const int lane = threadIdx.x % sub;
+  // rows wider than 32 vectors are covered by column tiles (blockIdx.y); every lane carries the softmax state of its own
+  // head, so tiles are independent. `lane` is the vector index inside the row from here on.
+  const int lane = blockIdx.y * sub + threadIdx.x % sub;
   const int nvec = H * D / VEC;
   const bool active = lane < nvec;
   const int h = active ? (lane * VEC) / D : 0;
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(256) gat_bwd_kernel(const I* __restrict__ indp
                                                       float* __restrict__ d_er, int sub, int red_width) {
   constexpr int VEC = Vec16<T>::N;
   const int rpb = blockDim.x / sub;
-  const int lane = threadIdx.x % sub;
+  const int lane = blockIdx.y * sub + threadIdx.x % sub;   // vector index inside the row (column tiles in blockIdx.y)
   const int nvec = H * D / VEC;
   const bool active = lane < nvec;
   const int h = active ? (lane * VEC) / D : 0;
@@ -191,13 +193,16 @@ DGLB_API int dglb200_cuda_gat_fwd(int dtype, int idtype, const void* indptr, con
   auto run = [&](auto tag) {
     using T = decltype(tag);
     constexpr int VEC = 16 / (int)sizeof(T);
-    DGLB_CHECK(D % VEC == 0 && H * D / VEC <= 32, "gat_fwd: D must be a multiple of 16 bytes and H*D <= 512 bytes");
-    const int sub = gat_sub(H * D / VEC);
+    const int nvec = H * D / VEC, lph = D / VEC;
+    DGLB_CHECK(D % VEC == 0 && (nvec <= 32 || (H > 1 && lph <= 32 && (lph & (lph - 1)) == 0)),
+               "gat_fwd: rows over 512 bytes need heads of 16 B x 2^k (<= 512 B each)");
+    const int sub = gat_sub(nvec);
     const int rpb = 256 / sub;
     int64_t blocks = (n_dst + rpb - 1) / rpb;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    const dim3 grid((unsigned)blocks, (unsigned)((nvec + sub - 1) / sub));
     DGLB_ID_SWITCH(idtype, I, {
-      gat_fwd_kernel<T, I><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      gat_fwd_kernel<T, I><<<grid, 256, 0, (cudaStream_t)stream>>>(
           (const I*)indptr, (const I*)indices, n_dst, (const T*)el, (const T*)er, (const T*)ft, H, D, slope, (T*)out,
           (float*)mbuf, (float*)lbuf, sub);
     });
@@ -220,15 +225,17 @@ DGLB_API int dglb200_cuda_gat_bwd(int dtype, int idtype, const void* indptr, con
     using T = decltype(tag);
     constexpr int VEC = 16 / (int)sizeof(T);
     const int lph = D / VEC;
-    DGLB_CHECK(D % VEC == 0 && H * D / VEC <= 32, "gat_bwd: D must be a multiple of 16 bytes and H*D <= 512 bytes");
+    const int nvec = H * D / VEC;
+    DGLB_CHECK(D % VEC == 0 && (nvec <= 32 || (H > 1 && lph <= 32)), "gat_bwd: rows over 512 bytes need heads <= 512 B");
     DGLB_CHECK(H == 1 || (lph & (lph - 1)) == 0, "gat_bwd: lanes per head must be a power of two when H > 1");
-    const int sub = gat_sub(H * D / VEC);
+    const int sub = gat_sub(nvec);
     const int red_width = H == 1 ? sub : lph;
     const int rpb = 256 / sub;
     int64_t blocks = (n_src + rpb - 1) / rpb;
     if (blocks > 148 * 16) blocks = 148 * 16;
+    const dim3 grid((unsigned)blocks, (unsigned)((nvec + sub - 1) / sub));
     DGLB_ID_SWITCH(idtype, I, {
-      gat_bwd_kernel<T, I><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+      gat_bwd_kernel<T, I><<<grid, 256, 0, (cudaStream_t)stream>>>(
           (const I*)indptr, (const I*)indices, n_src, (const T*)el, (const T*)ft, (const T*)dout, (const float4*)aux, H, D,
           slope, (T*)d_ft, (float*)d_el, (float*)d_er, sub, red_width);
     });

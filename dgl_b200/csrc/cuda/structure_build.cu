@@ -14,10 +14,25 @@
 namespace dglb {
 namespace sb {
 
+// The default stream-ordered pool gives memory back to the driver at every synchronisation (release threshold 0), which
+// made each cudaMallocAsync a ~1.8 ms driver call in a loop that builds one CSR per sampled block (measured with
+// torch.profiler on the GAT mini-batch pipeline). Keep the pool's memory: set the threshold once per device.
+static void keep_pool_memory() {
+  static bool done[64] = {};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || done[dev]) return;
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+    uint64_t keep = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+  }
+  done[dev] = true;
+}
+
 struct Scratch {
   cudaStream_t st;
   std::vector<void*> ptrs;
-  explicit Scratch(cudaStream_t s) : st(s) {}
+  explicit Scratch(cudaStream_t s) : st(s) { keep_pool_memory(); }
   template <typename T>
   T* get(size_t n) {
     void* p = nullptr;

@@ -61,7 +61,9 @@ class _FusedSAGETC(torch.autograd.Function):
     sage_bwd_da (input gradient whose epilogue scatters through the ELL block) - no cuBLAS call in either direction."""
 
     @staticmethod
-    def forward(ctx, x, w_self, w_neigh, bias, nbr, cnt, fan, relu, n_dev):
+    def forward(ctx, x, w_self, w_neigh, bias, nbr, cnt, fan, relu, n_dev, self_ids=None):
+        # self_ids (int32 [n_dst]) + nbr in the row space of ``x``: ``x`` is then a feature TABLE read in place (no gathered
+        # copy of the input frontier exists); without it row d of the output reads x[d] as its own row
         n_dst = nbr.shape[0]
         F = x.shape[1]
         out_f = w_self.shape[0]
@@ -78,10 +80,12 @@ class _FusedSAGETC(torch.autograd.Function):
         if n_dev is None:
             n_dev = torch.tensor([n_dst], dtype=torch.int64, device=dev)
         planes = fused_ops.tf32_split(Wt) if dt == torch.float32 else (Wt.contiguous(), None)
-        out, A = fused_ops.sage_layer_tc(x, None, nbr, cnt, n_dev, planes[0], b_pad, relu=relu, save_A=True,
+        out, A = fused_ops.sage_layer_tc(x, self_ids, nbr, cnt, n_dev, planes[0], b_pad, relu=relu, save_A=True,
                                          Wt_lo=planes[1])                        # A = [x_self | mean x_nbr], kept for dW
         ctx.save_for_backward(planes[0], planes[1] if planes[1] is not None else _EMPTY.get(dev), A, nbr, cnt, n_dev,
                               out if relu else _EMPTY.get(dev))
+        if self_ids is not None and x.requires_grad:
+            raise RuntimeError("a feature table read in place cannot require grad")
         ctx.meta = (x.shape[0], F, out_f, Np, fan, relu, bias is not None)
         return out if Np == out_f else out[:, :out_f]
 
@@ -105,7 +109,7 @@ class _FusedSAGETC(torch.autograd.Function):
             fused_ops.sage_bwd_da(dZ, Wt, nbr, cnt, n_dev, dX, Wt_lo=Wt_lo if Wt_lo.numel() else None)
             dX = dX.to(dt)
         d_bias = dZ.float().sum(0)[:out_f] if has_bias else None
-        return (dX, dWt[:out_f, :F].to(dt), dWt[:out_f, F:].to(dt), d_bias, None, None, None, None, None)
+        return (dX, dWt[:out_f, :F].to(dt), dWt[:out_f, F:].to(dt), d_bias, None, None, None, None, None, None)
 
 
 class _EmptyCache:
@@ -143,6 +147,12 @@ def fused_sage_mean(block, x, w_self, w_neigh, bias, relu=False):
     F = x.shape[1]
     Fp = _pad_to(F, 64)
     dt = torch.bfloat16 if (x.dtype == torch.bfloat16 or torch.is_autocast_enabled()) else torch.float32
+    self_ids = None
+    table = getattr(block, "_global_input", None)          # (self ids, neighbour ids) in the row space of a feature table
+    if table is not None:
+        if Fp != F or x.dtype != dt or x.requires_grad:
+            return None                                     # padding / casting a whole table per step would defeat the point
+        self_ids, nbr = table
     x = x.to(dt)
     ws, wn = w_self.to(dt), w_neigh.to(dt)
     if Fp != F:                                                   # zero columns: mathematically identical
@@ -150,4 +160,5 @@ def fused_sage_mean(block, x, w_self, w_neigh, bias, relu=False):
         ws = torch.nn.functional.pad(ws, (0, Fp - F))
         wn = torch.nn.functional.pad(wn, (0, Fp - F))
     with torch.autocast("cuda", enabled=False):
-        return _FusedSAGETC.apply(x.contiguous(), ws, wn, bias, nbr, cnt, fan, relu, getattr(block, "_n_dst_dev", None))
+        return _FusedSAGETC.apply(x.contiguous(), ws, wn, bias, nbr, cnt, fan, relu, getattr(block, "_n_dst_dev", None),
+                                  self_ids)

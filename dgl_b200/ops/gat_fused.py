@@ -17,10 +17,13 @@ def supported(el, ft, num_heads, head_dim):
     if not (ft.is_cuda and ft.dtype in (torch.float32, torch.bfloat16, torch.float16) and el.dtype == ft.dtype):
         return False
     vec = 16 // ft.element_size()
-    if head_dim % vec or num_heads * head_dim // vec > 32:
+    if head_dim % vec:
         return False
     lph = head_dim // vec
-    return num_heads == 1 or (lph & (lph - 1)) == 0
+    if num_heads * lph <= 32:
+        return num_heads == 1 or (lph & (lph - 1)) == 0
+    # wider rows run as column tiles of 32 vectors: heads must not straddle a tile
+    return num_heads > 1 and lph <= 32 and (lph & (lph - 1)) == 0 and num_heads * lph <= 512
 
 
 class _FusedGAT(torch.autograd.Function):

@@ -96,11 +96,12 @@ class FusedBlockSampler:
             ws = self._ws[key] = _Workspace(cap, self.fanouts, device)
         return ws
 
-    def enqueue(self, ws, indptr, indices, uva=False, step_dev=None):
+    def enqueue(self, ws, indptr, indices, uva=False, step_dev=None, compact_input=True):
         """Enqueue every layer on the workspace's capacity buffers (seeds in ``ws.seeds``, their count in ``ws.n[L]``)
         WITHOUT reading anything back: returns (S, nbr_local) lists indexed by layer. With ``step_dev`` (int64[1] on the
         device) the random stream is keyed by that counter instead of a host value, so the sequence is CUDA-graph
-        capturable and still differs from replay to replay."""
+        capturable and still differs from replay to replay. ``compact_input=False`` skips the compaction of the input layer
+        (``S[0]`` / ``nbr_local[1]`` stay None; ``ws.nbr_g[1]`` holds global ids)."""
         lib = loader.cuda_lib()
         L = len(self.fanouts)
         S = [None] * (L + 1)
@@ -114,6 +115,8 @@ class FusedBlockSampler:
             lib.fn("dglb200_cuda_sample_ell", "ippiplpilpppppi" + "p")(
                 it, _p(indptr), _p(indices), 1 if uva else 0, _p(S[l]), ws.caps[l], _p(ws.n[l]), f, host_seed, _p(step_dev),
                 _p(ws.nbr_g[l]), _p(ws.eid[l]), _p(ws.cnt[l]), _p(ws.totals[l]), 1, loader.stream_ptr())
+            if l == 1 and not compact_input:
+                continue          # the input layer will read the feature table by global id: its frontier is never built
             S[l - 1], nbr_local[l], n_prev, _ = ws.compactors[l].compact(S[l], ws.n[l], ws.nbr_g[l])
             ws.n[l - 1] = n_prev
         return S, nbr_local
@@ -160,7 +163,14 @@ class FusedBlockSampler:
         loader.cuda_lib().fn("dglb200_ell_to_csc", "ipppplipppp")(
             id_code(idtype), _p(layer["nbr"]), _p(layer["eid"]), _p(layer["cnt"]), _p(ptr64), nd, layer["fanout"], _p(idx),
             _p(eids), _p(eid_map), loader.stream_ptr())
-        return ptr64.to(idtype), idx, eids
+        ptr = ptr64.to(idtype)
+        from .._sparse_ops import SPLIT_DEG
+        if layer["fanout"] <= SPLIT_DEG:
+            try:                           # every row has at most `fanout` entries: the balanced g-SpMM needs no work items
+                ptr._dglb_split_meta = {"n_long": 0}
+            except Exception:  # noqa: BLE001
+                pass
+        return ptr, idx, eids
 
     @staticmethod
     def layer_to_block(layer, idtype, canonical_etypes, ntypes, eid_map=None, want_eids=True):

@@ -161,3 +161,31 @@ def test_graphed_trainer_matches_eager_semantics_and_learns():
         pred = model.full_forward(g, x.cuda()).argmax(1).cpu() if hasattr(model, "full_forward") else None
     if pred is not None:
         assert (pred == y).float().mean() > 0.8
+
+
+def test_graphed_trainer_table_input_mode_learns():
+    """gather_inputs=False: the first SAGEConv reads the feature table in place through global ids."""
+    import dgl_b200 as dgl
+    from dgl_b200.dataloading import GraphedTrainer
+    from dgl_b200.models import GraphSAGE
+    torch.manual_seed(1)
+    n, C, Fdim = 4000, 5, 64
+    y = torch.randint(0, C, (n,))
+    x = (torch.randn(C, Fdim) * 1.5)[y] + torch.randn(n, Fdim)
+    src = torch.randint(0, n, (60000,))
+    dst = torch.randint(0, n, (60000,))
+    g = dgl.graph((src.int(), dst.int()), num_nodes=n, idtype=torch.int32).to("cuda")
+    g.create_formats_()
+    for amp in (False, True):
+        model = GraphSAGE(Fdim, 64, C, 2, 0.0).cuda()
+        opt = torch.optim.Adam(model.parameters(), lr=5e-3, capturable=True)
+        tr = GraphedTrainer(g, x.cuda(), y.cuda(), model, opt, [4, 4], 512, amp=amp, gather_inputs=False)
+        losses = []
+        for ep in range(5):
+            perm = torch.randperm(n)
+            for i in range(0, n - 511, 512):
+                losses.append(tr.step(perm[i:i + 512]).clone())
+        losses = torch.stack(losses).cpu()
+        assert torch.isfinite(losses).all() and losses[-4:].mean() < 0.5 * losses[:4].mean(), (amp, losses[:4], losses[-4:])
+    with pytest.raises(dgl.DGLError):
+        GraphedTrainer(g, x[:, :20].cuda(), y.cuda(), model, opt, [4, 4], 512, gather_inputs=False)

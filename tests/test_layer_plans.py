@@ -95,7 +95,8 @@ def test_trace_records_native_ops():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("H,D,dtype", [(8, 8, torch.float32), (1, 41, torch.float32), (4, 16, torch.bfloat16), (2, 32, torch.float32)])
+@pytest.mark.parametrize("H,D,dtype", [(8, 8, torch.float32), (1, 41, torch.float32), (4, 16, torch.bfloat16), (2, 32, torch.float32),
+                                       (4, 64, torch.float32), (8, 64, torch.bfloat16), (3, 128, torch.float32)])   # column tiles
 def test_fused_gat_matches_unfused(H, D, dtype):
     from dgl_b200.ops import gat_fused
     torch.manual_seed(0)
