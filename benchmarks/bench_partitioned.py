@@ -150,7 +150,7 @@ def run_ours(args):
             "config": {"model": f"GraphSAGE-mean {LAYERS}x{HIDDEN} full-graph", "nodes": n, "edges": int(B.NUM_EDGES * args.scale) * 2,
                        "parallelism": f"vertex-partition x{world} (LDG edge-cut partitioner, P2P halo)",
                        "edge_cut_fraction": cut, "halo_rows_total": halo_rows, "shard_rows": shard_rows,
-                       "partition_time_s": t_part, "peak_mem_gib": peak,
+                       "partition_time_s": t_part, "peak_mem_gib": peak, "halo_mode": os.environ.get("DGLB200_HALO_MODE", "balanced"),
                        "local_edges_max": edges_max, "local_edges_mean": edges_mean,
                        "halo_bytes_per_layer_fwd": halo_rows * HIDDEN * 2}}), flush=True)
     if dist.is_initialized():
