@@ -138,7 +138,7 @@ def dist_setup(n_gpus):
         # a mismatched collective must fail fast, not sit in the default 10-minute watchdog on a multi-GPU box
         import datetime
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev,
-                                timeout=datetime.timedelta(seconds=int(os.environ.get("BENCH_NCCL_TIMEOUT_S", "240"))))
+                                timeout=datetime.timedelta(seconds=int(os.environ.get("BENCH_NCCL_TIMEOUT_S", "600"))))
     return rank, world, dev
 
 

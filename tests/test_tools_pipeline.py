@@ -124,3 +124,46 @@ def test_parmetis_pre_post_process(tmp_path):
     np.savetxt(out, np.stack([np.arange(50), np.arange(50) % 2], 1), fmt="%d")
     pdir = post_process(chunked, out, str(tmp_path / "parts"))
     assert np.loadtxt(os.path.join(pdir, "a.txt")).shape[0] == 30 and np.loadtxt(os.path.join(pdir, "b.txt")).shape[0] == 20
+
+
+def test_launcher_watchdog_cleans_recorded_groups_when_launcher_dies(tmp_path):
+    """tools/launch.py: a job whose launcher is killed with SIGKILL must not leave its children behind - the detached
+    watchdog signals exactly the process groups recorded in the pid files."""
+    import signal
+    import subprocess
+    import sys
+    import time
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ipc = tmp_path / "ip_config.txt"
+    ipc.write_text("127.0.0.1 30050\n")
+    marker = tmp_path / "alive.txt"
+    # the "training command": a server-role process that keeps touching a file; trainers exit immediately
+    script = tmp_path / "job.py"
+    script.write_text(
+        "import os, sys, time\n"
+        "if os.environ.get('DGL_ROLE') != 'server':\n"
+        "    time.sleep(600)\n"
+        f"p = {str(marker)!r}\n"
+        "while True:\n"
+        "    open(p, 'w').write(str(time.time()))\n"
+        "    time.sleep(0.1)\n")
+    launcher = subprocess.Popen([sys.executable, os.path.join(root, "tools", "launch.py"), "--workspace", str(tmp_path),
+                                 "--num_trainers", "1", "--num_servers", "1", "--part_config", "none.json", "--ip_config", str(ipc),
+                                 f"{sys.executable} {script}"], start_new_session=True)
+    try:
+        deadline = time.time() + 30
+        while not marker.exists() and time.time() < deadline:
+            time.sleep(0.1)
+        assert marker.exists(), "the server process never started"
+        os.kill(launcher.pid, signal.SIGKILL)            # no chance to run its own cleanup
+        launcher.wait()
+        # the watchdog notices within ~1 s and terminates the recorded groups: the file stops changing
+        time.sleep(4.0)
+        a = marker.read_text()
+        time.sleep(1.0)
+        assert marker.read_text() == a, "a child survived the launcher"
+    finally:
+        try:
+            os.killpg(os.getpgid(launcher.pid), signal.SIGKILL)
+        except Exception:  # noqa: BLE001
+            pass
