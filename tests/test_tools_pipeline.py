@@ -167,3 +167,32 @@ def test_launcher_watchdog_cleans_recorded_groups_when_launcher_dies(tmp_path):
             os.killpg(os.getpgid(launcher.pid), signal.SIGKILL)
         except Exception:  # noqa: BLE001
             pass
+
+
+def test_cli_recipe_train_apply_roundtrip(tmp_path):
+    """dgl_cli: recipes come from tools/recipes/*.yaml, the dataset named in the config is honoured, ``train`` writes a
+    checkpoint and ``apply`` reproduces the trained model's predictions from it."""
+    import subprocess
+    import sys
+    import torch
+    import yaml
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cli = [sys.executable, os.path.join(root, "tools", "dgl_cli.py")]
+    names = subprocess.run(cli + ["recipe", "list"], capture_output=True, text=True, check=True).stdout.split()
+    assert "nodepred_citeseer_gcn" in names and "linkpred_cora_sage" in names and len(names) >= 12
+    cfg_path = tmp_path / "c.yaml"
+    subprocess.run(cli + ["recipe", "get", "nodepred_citeseer_gcn", "--cfg", str(cfg_path)], check=True, capture_output=True)
+    cfg = yaml.safe_load(open(cfg_path))
+    assert cfg["data"]["name"] == "citeseer" and cfg["model"] == "gcn"
+    cfg["general_pipeline"].update(num_epochs=5, save_path=str(tmp_path / "m.pt"))
+    yaml.safe_dump(cfg, open(cfg_path, "w"))
+    out = subprocess.run(cli + ["train", "--cfg", str(cfg_path)], capture_output=True, text=True, cwd=tmp_path)
+    assert out.returncode == 0 and "checkpoint written" in out.stdout, out.stderr[-800:]
+    out = subprocess.run(cli + ["apply", "--cfg", str(cfg_path), "--checkpoint", str(tmp_path / "m.pt"), "--output",
+                                str(tmp_path / "p.pt")], capture_output=True, text=True, cwd=tmp_path)
+    assert out.returncode == 0 and "predictions written" in out.stdout, out.stderr[-800:]
+    pred = torch.load(tmp_path / "p.pt")
+    import dgl_b200.data as D
+    assert pred.shape[0] == D.CiteseerGraphDataset()[0].num_nodes()
+    bad = subprocess.run(cli + ["recipe", "get", "nope"], capture_output=True, text=True)
+    assert bad.returncode != 0
