@@ -299,7 +299,10 @@ def run_ours(args):
                        "seeds_per_s": BATCH * world * args.steps / (r["ms"] / 1e3),
                        "sampled_edges_per_step_per_gpu": r["edges"] / args.steps / world,
                        "frontier_caps": r["caps"], "overflow": r["overflow"],
-                       "cuda_graph": not args.no_graph, "final_loss": r["loss"], "scale": args.scale},
+                       "cuda_graph": not args.no_graph, "final_loss": r["loss"], "scale": args.scale,
+                       "grad_allreduce": ("none (1 GPU)" if world == 1 else "nccl" if args.comm == "nccl" else
+                                          "NVLS multimem.ld_reduce fused with Adam" if getattr(comm, "nvls", False)
+                                          else "P2P peer loads fused with Adam (CUDA IPC)")},
             "clocks": clk,
             "e2e": {"value": r["edges_e2e"] / (r["ms_e2e"] / 1e3), "unit": "edges/s",
                     "ms_per_step": r["ms_e2e"] / args.steps,

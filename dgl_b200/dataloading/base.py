@@ -214,3 +214,15 @@ def as_edge_prediction_sampler(sampler, exclude=None, reverse_eids=None, reverse
     """Edge classification / link prediction flavour of ``sampler`` (see ``EdgePredictionSampler``)."""
     return EdgePredictionSampler(sampler, exclude=exclude, reverse_eids=reverse_eids, reverse_etypes=reverse_etypes,
                                  negative_sampler=negative_sampler, prefetch_labels=prefetch_labels)
+
+
+def __getattr__(name):
+    # names the reference keeps in this module but that live elsewhere in this package
+    if name.startswith("__"):
+        raise AttributeError(name)
+    import importlib
+    for modname in ('dgl_b200.dataloading.tensorized',):
+        mod = importlib.import_module(modname)
+        if name in vars(mod):
+            return vars(mod)[name]
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

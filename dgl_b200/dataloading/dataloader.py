@@ -443,3 +443,15 @@ class GraphDataLoader(torch.utils.data.DataLoader):
 
 class DistNodeDataLoaderStub:
     """Placeholder kept for import parity; see dgl_b200.distributed.DistNodeDataLoader."""
+
+
+def __getattr__(name):
+    # names the reference keeps in this module but that live elsewhere in this package
+    if name.startswith("__"):
+        raise AttributeError(name)
+    import importlib
+    for modname in ('dgl_b200.dataloading.tensorized', 'dgl_b200.distributed.dist_graph', 'dgl_b200.distributed.compat'):
+        mod = importlib.import_module(modname)
+        if name in vars(mod):
+            return vars(mod)[name]
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

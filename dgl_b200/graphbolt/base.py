@@ -86,3 +86,15 @@ class CSCFormatBase:
 
     def __repr__(self):
         return f"CSCFormatBase(indptr={self.indptr},\n              indices={self.indices},\n)"
+
+
+def __getattr__(name):
+    # names the reference keeps in this module but that live elsewhere in this package
+    if name.startswith("__"):
+        raise AttributeError(name)
+    import importlib
+    for modname in ('dgl_b200.graphbolt.dataloader', 'dgl_b200.graphbolt.compat'):
+        mod = importlib.import_module(modname)
+        if name in vars(mod):
+            return vars(mod)[name]
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

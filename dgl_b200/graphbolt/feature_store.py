@@ -43,3 +43,15 @@ class FeatureStore:
 
     def keys(self):
         raise NotImplementedError
+
+
+def __getattr__(name):
+    # names the reference keeps in this module but that live elsewhere in this package
+    if name.startswith("__"):
+        raise AttributeError(name)
+    import importlib
+    for modname in ('dgl_b200.graphbolt.compat',):
+        mod = importlib.import_module(modname)
+        if name in vars(mod):
+            return vars(mod)[name]
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

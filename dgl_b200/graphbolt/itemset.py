@@ -183,3 +183,15 @@ class DistributedItemSampler(ItemSampler):
         self._drop_uneven_inputs = drop_uneven_inputs
         if dist.is_initialized():
             self._rank, self._world = dist.get_rank(), dist.get_world_size()
+
+
+def __getattr__(name):
+    # names the reference keeps in this module but that live elsewhere in this package
+    if name.startswith("__"):
+        raise AttributeError(name)
+    import importlib
+    for modname in ('dgl_b200.graphbolt.compat',):
+        mod = importlib.import_module(modname)
+        if name in vars(mod):
+            return vars(mod)[name]
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
