@@ -1,5 +1,9 @@
-"""SpotTarget exclusion callable (parity: /root/reference/python/dgl/dataloading/spot_target.py):
-exclude the target edges (and their reverses) only when incident to a low-degree node."""
+"""SpotTarget (Guo et al., "Rethinking Target Edge Leakage"): during link-prediction training only those target edges are
+hidden from message passing that touch a LOW-degree endpoint - for high-degree endpoints removing one edge changes little
+and keeping it avoids a train / test distribution shift.
+
+Callable for the ``exclude=`` argument of ``as_edge_prediction_sampler`` (reference
+python/dgl/dataloading/spot_target.py:26-90)."""
 from __future__ import annotations
 
 import torch
@@ -7,20 +11,14 @@ import torch
 
 class SpotTarget:
     def __init__(self, g, exclude, degree_threshold=10, reverse_eids=None, reverse_etypes=None):
-        self.g = g
-        self.exclude = exclude
-        self.degree_threshold = degree_threshold
-        self.reverse_eids = reverse_eids
-        self.reverse_etypes = reverse_etypes
+        self.g, self.exclude, self.degree_threshold = g, exclude, degree_threshold
+        self.reverse_eids, self.reverse_etypes = reverse_eids, reverse_etypes
 
     def __call__(self, seed_edges):
-        g = self.g
-        src, dst = g.find_edges(seed_edges)
-        head_degree = g.in_degrees(src)
-        tail_degree = g.in_degrees(dst)
-        degree = torch.min(head_degree, tail_degree)
-        low = degree < self.degree_threshold
-        edges = seed_edges[low]
+        u, v = self.g.find_edges(seed_edges)
+        weakest = torch.minimum(self.g.in_degrees(u), self.g.in_degrees(v))     # the sparser endpoint decides
+        hidden = seed_edges[weakest < self.degree_threshold]
         if self.exclude == "reverse_id" and self.reverse_eids is not None:
-            return torch.cat([edges, self.reverse_eids[edges.long()]])
-        return edges
+            partner = self.reverse_eids.to(hidden.device)[hidden.long()]
+            hidden = torch.cat([hidden, partner])
+        return hidden

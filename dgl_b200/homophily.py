@@ -1,59 +1,67 @@
-"""Homophily measures (parity: /root/reference/python/dgl/homophily.py)."""
+"""Homophily measures of a node-labelled graph.
+
+Definitions follow /root/reference/python/dgl/homophily.py:27-270 (node / edge / LINKX class-insensitive / adjusted
+homophily). All four are computed from ONE pair of per-edge tensors (endpoint labels) with scatter reductions over class
+and node ids - no message-passing round trip and no Python loop over classes."""
 from __future__ import annotations
 
 import torch
-
-from . import function as fn
 
 __all__ = ["node_homophily", "edge_homophily", "linkx_homophily", "adjusted_homophily"]
 
 
 def check_pytorch():
-    """The measures are written against torch tensors (the reference guards on its backend switch here)."""
+    """Kept for API parity (the reference guards on its backend switch); this package is torch-only."""
     return True
 
 
 def get_long_edges(graph):
-    """(src, dst) of every edge as int64 tensors."""
-    src, dst = graph.edges()
-    return src.long(), dst.long()
+    u, v = graph.edges()
+    return u.long(), v.long()
 
 
-def node_homophily(graph, y):
-    with graph.local_scope():
-        src, dst = graph.edges()
-        graph.edata["same_class"] = (y[src.long()] == y[dst.long()]).float()
-        graph.update_all(fn.copy_e("same_class", "m"), fn.mean("m", "same_class_deg"))
-        return graph.ndata["same_class_deg"].mean(dim=0).item()
+def _agreement(graph, y):
+    """(dst ids, 1.0 where an edge joins two nodes of the same class else 0.0)."""
+    u, v = get_long_edges(graph)
+    return v, (y[u] == y[v]).to(torch.float32)
 
 
 def edge_homophily(graph, y):
-    src, dst = graph.edges()
-    return (y[src.long()] == y[dst.long()]).float().mean().item()
+    """Fraction of edges whose endpoints share a label."""
+    return _agreement(graph, y)[1].mean().item()
+
+
+def node_homophily(graph, y):
+    """Mean over nodes of the fraction of in-neighbours with the node's own label (nodes without in-edges count 0)."""
+    v, same = _agreement(graph, y)
+    n = graph.num_nodes()
+    hits = torch.zeros(n, device=same.device).index_add_(0, v, same)
+    deg = torch.zeros(n, device=same.device).index_add_(0, v, torch.ones_like(same))
+    return (hits / deg.clamp(min=1)).mean().item()
 
 
 def linkx_homophily(graph, y):
-    with graph.local_scope():
-        src, dst = graph.edges()
-        graph.edata["same_class"] = (y[src.long()] == y[dst.long()]).float()
-        graph.update_all(fn.copy_e("same_class", "m"), fn.sum("m", "same_class_deg"))
-        deg = graph.in_degrees().float()
-        num_nodes = graph.num_nodes()
-        num_classes = int(y.max()) + 1
-        value = torch.tensor(0.0, device=graph.device)
-        for k in range(num_classes):
-            class_mask = y == k
-            same_class_deg_k = graph.ndata["same_class_deg"][class_mask].sum()
-            deg_k = deg[class_mask].sum()
-            num_nodes_k = class_mask.sum()
-            value = value + torch.clamp(same_class_deg_k / deg_k.clamp(min=1) - num_nodes_k / num_nodes, min=0)
-        return (value / max(num_classes - 1, 1)).item()
+    """Class-insensitive homophily of Lim et al.: (1 / (C - 1)) * sum_k max(0, h_k - |C_k| / N), h_k the fraction of the
+    in-edges of class-k nodes that come from class k."""
+    v, same = _agreement(graph, y)
+    y = y.long()
+    num_classes = int(y.max()) + 1
+    cls_of_dst = y[v]
+    same_per_class = torch.zeros(num_classes, device=same.device).index_add_(0, cls_of_dst, same)
+    edges_per_class = torch.zeros(num_classes, device=same.device).index_add_(0, cls_of_dst, torch.ones_like(same))
+    share = torch.bincount(y, minlength=num_classes).to(torch.float32) / graph.num_nodes()
+    excess = (same_per_class / edges_per_class.clamp(min=1) - share.to(same.device)).clamp(min=0)
+    return (excess.sum() / max(num_classes - 1, 1)).item()
 
 
 def adjusted_homophily(graph, y):
-    edge_homo = edge_homophily(graph, y)
-    degrees = graph.in_degrees().float()
+    """Edge homophily corrected for the class degree distribution: (h_edge - sum_k D_k^2 / (E)^2) / (1 - sum_k D_k^2 / E^2)
+    with D_k the total degree of class k (Platonov et al.). Defined on the undirected simple graph: the input is symmetrised
+    and de-duplicated first."""
+    from .transforms import to_bidirected
+    graph = to_bidirected(graph.cpu()).to(y.device)
+    v, same = _agreement(graph, y)
     num_classes = int(y.max()) + 1
-    degree_sums = torch.zeros(num_classes, device=graph.device).index_add_(0, y.long(), degrees)
-    adjust = (degree_sums ** 2).sum() / graph.num_edges() ** 2
-    return ((edge_homo - adjust) / (1 - adjust)).item()
+    class_degree = torch.zeros(num_classes, device=same.device).index_add_(0, y.long()[v], torch.ones_like(same))
+    expected = (class_degree ** 2).sum() / float(graph.num_edges()) ** 2
+    return ((same.mean() - expected) / (1 - expected)).item()

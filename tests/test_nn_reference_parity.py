@@ -331,3 +331,16 @@ def test_graph_transformer_blocks():
     for model, kw in (("Transformer", {"n_head": 2}), ("DeepSet", {"num_post_layer": 2}), ("DeepSet", {"batch_norm": True})):
         ours, ref = pair("LapPosEncoder", model, 3 if model == "DeepSet" else 1, 5, 8, **kw)
         close(ours(ea.clone(), ev.clone()), ref(ea.clone(), ev.clone()), 1e-3)
+
+
+def test_homophily_measures_match_reference():
+    """node / edge / LINKX / adjusted homophily vs the installed reference on a random labelled graph (and the docstring
+    example of the adjusted measure, which symmetrises the graph first)."""
+    torch.manual_seed(3)
+    u, v = torch.randint(0, 150, (2500,)), torch.randint(0, 150, (2500,))
+    y = torch.randint(0, 6, (150,))
+    go, gr = odgl.graph((u, v), num_nodes=150), rdgl.graph((u, v), num_nodes=150)
+    for name in ("node_homophily", "edge_homophily", "linkx_homophily", "adjusted_homophily"):
+        assert abs(getattr(odgl, name)(go, y) - getattr(rdgl, name)(gr, y)) < 1e-6, name
+    tiny = odgl.graph(([1, 2, 0, 4], [0, 1, 2, 3]))
+    assert abs(odgl.adjusted_homophily(tiny, torch.tensor([0, 0, 0, 0, 1])) + 0.1428571492433548) < 1e-6
