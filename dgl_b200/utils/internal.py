@@ -101,8 +101,4 @@ def set_new_frames(graph, *, node_frames=None, edge_frames=None):
         graph._edge_frames = edge_frames
 
 
-from .containers_extra import (FlattenedDict, HybridDict, InconsistentDtypeException, LazyDict, ReadOnlyDict,  # noqa: E402,F401
-                               alias_func, apply_each, build_relabel_dict, build_relabel_map, cached_member, compensate,
-                               get_num_threads, get_numa_nodes_cores, group_as_dict, is_dict_like, is_iterable, is_listlike,
-                               make_invmap, maybe_flatten_dict, recursive_apply_pair, relabel, reorder_index,
-                               retry_method_with_fix, set_diff, set_num_threads, to_nbits_int, zero_index)
+from .containers import *  # noqa: E402,F401,F403  (Index, dict views, relabel family, thread-count / NUMA queries ...)
