@@ -211,6 +211,8 @@ def main():
     if args.out:
         with open(args.out, "a") as f:
             f.write(json.dumps(rec) + "\n")
+    if hasattr(it, "close"):
+        it.close()          # ends the endless batch generator: the loader's producer thread is stopped and joined
 
 
 if __name__ == "__main__":

@@ -8,6 +8,8 @@
 // Replaces the reference's SpMMCsrKernel / cuSPARSE / COO-atomic paths
 // (/root/reference/src/array/cuda/spmm.cuh:413-732, spmm.cu:27-58) with one CSC family; no
 // descriptor creation, no workspace allocation, no host synchronisation per call.
+#include <type_traits>
+
 #include "common.cuh"
 #include "spmm_bulk.cuh"
 
@@ -61,7 +63,7 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ ind
                                                        const I* __restrict__ eids, int64_t num_rows,
                                                        const T* __restrict__ x, const T* __restrict__ w,
                                                        T* __restrict__ out, int64_t F, int nvec, int sub,
-                                                       int64_t max_deg, int wH, int vph) {
+                                                       int64_t max_deg, int wH, int vph, int zero_long) {
   using VO = VecOps<T, VB>;
   using V = typename VO::V;
   constexpr int VE = VO::VE;
@@ -80,7 +82,19 @@ __global__ void __launch_bounds__(256) spmm_vec_kernel(const I* __restrict__ ind
 #pragma unroll
     for (int i = 0; i < VE; ++i) acc[j][i] = 0.f;
   const int64_t s = indptr[row], t = indptr[row + 1];
-  if (max_deg > 0 && t - s > max_deg) return;  // long rows are handled by the edge-balanced split kernel
+  if (max_deg > 0 && t - s > max_deg) {
+    // long rows are handled by the edge-balanced split kernel; when it accumulates straight into `out` (fp32) the row is
+    // cleared here, which saves the scratch memset and the finalize pass
+    if (zero_long) {
+      V* zr = reinterpret_cast<V*>(out + row * F);
+#pragma unroll
+      for (int j = 0; j < NV; ++j) {
+        const int c = vbase + j * sub;
+        if (c < nvec) zr[c] = VO::pack(acc[j], 0.f);
+      }
+    }
+    return;
+  }
   const int64_t rowvecs = F / VE;  // == nvec
   int64_t p = s;
   for (; p + U <= t; p += U) {
@@ -182,7 +196,7 @@ static int pow2_ge(int64_t x, int cap) {
 
 template <typename T, typename I, int VB, int HAS_W>
 void launch_vec(const I* indptr, const I* indices, const I* eids, int64_t n, const T* x, const T* w, T* out, int64_t F,
-                cudaStream_t st, int64_t max_deg = 0, int wH = 1) {
+                cudaStream_t st, int64_t max_deg = 0, int wH = 1, int zero_long = 0) {
   constexpr int VE = VB / sizeof(T);
   const int nvec = (int)(F / VE);
   const int vph = wH > 1 ? nvec / wH : nvec;  // vectors per head
@@ -191,12 +205,12 @@ void launch_vec(const I* indptr, const I* indices, const I* eids, int64_t n, con
   const unsigned gx = (unsigned)((n + rows_per_block - 1) / rows_per_block);
   const int per_lane = (nvec + sub - 1) / sub;
   if (per_lane <= 1) {
-    spmm_vec_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg, wH, vph);
+    spmm_vec_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg, wH, vph, zero_long);
   } else if (per_lane <= 2) {
-    spmm_vec_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg, wH, vph);
+    spmm_vec_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg, wH, vph, zero_long);
   } else {
     const unsigned gy = (unsigned)((nvec + sub * 4 - 1) / (sub * 4));
-    spmm_vec_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg, wH, vph);
+    spmm_vec_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indptr, indices, eids, n, x, w, out, F, nvec, sub, max_deg, wH, vph, zero_long);
   }
 }
 
@@ -213,7 +227,7 @@ __global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ i
                                                          const int32_t* __restrict__ item_len, int64_t num_items,
                                                          const T* __restrict__ x, const T* __restrict__ w,
                                                          float* __restrict__ scratch, int64_t F, int nvec, int sub,
-                                                         int wH, int vph) {
+                                                         int wH, int vph, const int64_t* __restrict__ row_map) {
   using VO = VecOps<T, VB>;
   using V = typename VO::V;
   constexpr int VE = VO::VE;
@@ -269,7 +283,8 @@ __global__ void __launch_bounds__(256) spmm_split_kernel(const I* __restrict__ i
         VO::fma(acc[j], v, HAS_W ? to_f<T>(w[eidx + (HAS_W == 2 ? hd[j] : 0)]) : 1.f);
       }
   }
-  float* srow = scratch + (int64_t)item_ord[item] * F;
+  // row_map != nullptr: `scratch` is the fp32 output itself and row_map the long-row ids (direct accumulation)
+  float* srow = scratch + (row_map ? row_map[item_ord[item]] : (int64_t)item_ord[item]) * F;
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     const int c = vbase + j * sub;
@@ -294,7 +309,7 @@ __global__ void __launch_bounds__(256) spmm_split_finalize_kernel(const float* _
 template <typename T, typename I, int VB, int HAS_W>
 void launch_split(const I* indices, const I* eids, const int32_t* item_ord, const int64_t* item_start,
                   const int32_t* item_len, int64_t num_items, const T* x, const T* w, float* scratch, int64_t F,
-                  cudaStream_t st, int wH = 1) {
+                  cudaStream_t st, int wH = 1, const int64_t* row_map = nullptr) {
   constexpr int VE = VB / sizeof(T);
   const int nvec = (int)(F / VE);
   const int vph = wH > 1 ? nvec / wH : nvec;
@@ -303,12 +318,12 @@ void launch_split(const I* indices, const I* eids, const int32_t* item_ord, cons
   const unsigned gx = (unsigned)((num_items + ipb - 1) / ipb);
   const int per_lane = (nvec + sub - 1) / sub;
   if (per_lane <= 1) {
-    spmm_split_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub, wH, vph);
+    spmm_split_kernel<T, I, VB, 1, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub, wH, vph, row_map);
   } else if (per_lane <= 2) {
-    spmm_split_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub, wH, vph);
+    spmm_split_kernel<T, I, VB, 2, HAS_W><<<dim3(gx, 1), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub, wH, vph, row_map);
   } else {
     const unsigned gy = (unsigned)((nvec + sub * 4 - 1) / (sub * 4));
-    spmm_split_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub, wH, vph);
+    spmm_split_kernel<T, I, VB, 4, HAS_W><<<dim3(gx, gy), 256, 0, st>>>(indices, eids, item_ord, item_start, item_len, num_items, x, w, scratch, F, nvec, sub, wH, vph, row_map);
   }
 }
 
@@ -412,12 +427,18 @@ DGLB_API int dglb200_cuda_gspmm_balanced(int has_w, int dtype, int idtype, const
     const int vb = pick_vb_spmm((F / wH) * (int64_t)sizeof(T), x, out);
     DGLB_CHECK(vb != 0 && (F * (int64_t)sizeof(T)) % vb == 0, "feature rows must be 4-byte aligned for the balanced g-SpMM");
 #define RUN(VBV, HW)                                                                                              \
-    /* short rows: TMA-staged row gather when the row size allows it (spmm_bulk.cuh), else the SIMT vector kernel */ \
-    if (!(wH == 1 && bulk::launch<T, I, (HW != 0)>((const I*)indptr, (const I*)indices, (const I*)eids, num_rows,          \
-                                            (const T*)x, (const T*)w, (T*)out, F, max_deg, st)))                    \
+    /* fp32 outputs: the split kernel adds straight into `out` (rows cleared by the row kernel) - 2 launches instead */ \
+    /* of 4; 16-bit outputs accumulate in an fp32 scratch that a finalize pass converts                            */ \
+    const bool direct = std::is_same<T, float>::value && num_items > 0;                                             \
+    if (direct || !(wH == 1 && bulk::launch<T, I, (HW != 0)>((const I*)indptr, (const I*)indices, (const I*)eids,    \
+                                                             num_rows, (const T*)x, (const T*)w, (T*)out, F, max_deg, st))) \
       launch_vec<T, I, VBV, HW>((const I*)indptr, (const I*)indices, (const I*)eids, num_rows, (const T*)x,         \
-                                (const T*)w, (T*)out, F, st, max_deg, wH);                                          \
-    if (num_items > 0) {                                                                                            \
+                                (const T*)w, (T*)out, F, st, max_deg, wH, direct ? 1 : 0);                          \
+    if (direct) {                                                                                                   \
+      launch_split<T, I, VBV, HW>((const I*)indices, (const I*)eids, (const int32_t*)item_ord,                      \
+                                  (const int64_t*)item_start, (const int32_t*)item_len, num_items, (const T*)x,     \
+                                  (const T*)w, (float*)out, F, st, wH, (const int64_t*)long_rows);                  \
+    } else if (num_items > 0) {                                                                                     \
       DGLB_CUDA_CHECK(cudaMemsetAsync(scratch, 0, (size_t)n_long * F * sizeof(float), st));                         \
       launch_split<T, I, VBV, HW>((const I*)indices, (const I*)eids, (const int32_t*)item_ord,                      \
                                   (const int64_t*)item_start, (const int32_t*)item_len, num_items, (const T*)x,     \

@@ -79,60 +79,61 @@ class DataLoader:
             return
         q = queue.Queue(maxsize=self.prefetch)
         done = object()
+        stop = threading.Event()
         use_cuda = torch.cuda.is_available()
         dev = torch.cuda.current_device() if use_cuda else None
 
+        def hand_over(entry):
+            """put with a stop check: a consumer that went away must not leave this thread blocked on a full queue"""
+            while not stop.is_set():
+                try:
+                    q.put(entry, timeout=0.1)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
         def worker():
             try:
+                stream = None
                 if use_cuda:
                     torch.cuda.set_device(dev)
                     stream = torch.cuda.Stream()
-                    ctx = torch.cuda.stream(stream)
-                else:
-                    stream, ctx = None, None
                 it = iter(self.datapipe)
-                while True:
-                    if ctx is not None:
-                        with torch.cuda.stream(stream):
-                            try:
+                while not stop.is_set():
+                    ev = None
+                    try:
+                        if stream is not None:
+                            with torch.cuda.stream(stream):
                                 item = next(it)
-                            except StopIteration:
-                                break
-                        ev = torch.cuda.Event()
-                        ev.record(stream)
-                        q.put((item, ev, None))
-                    else:
-                        try:
+                            ev = torch.cuda.Event()
+                            ev.record(stream)
+                        else:
                             item = next(it)
-                        except StopIteration:
-                            break
-                        q.put((item, None, None))
-                q.put((done, None, None))
+                    except StopIteration:
+                        break
+                    if not hand_over((item, ev, None)):
+                        return
+                hand_over((done, None, None))
             except Exception as e:  # noqa: BLE001
-                q.put((None, None, e))
+                hand_over((None, None, e))
 
         th = threading.Thread(target=worker, daemon=True)
         th.start()
-        while True:
-            item, ev, exc = q.get()
-            if exc is not None:
-                raise exc
-            if item is done:
-                break
-            if ev is not None:
-                cur = torch.cuda.current_stream()
-                cur.wait_event(ev)
-                _record_stream(item, cur)   # memory allocated on the producer stream is consumed on this one
-            yield item
-        th.join()
-
-
-def __getattr__(name):
-    # remaining names of the reference module of this path (markers, helpers) are defined in graphbolt/compat.py
-    if name.startswith("__"):
-        raise AttributeError(name)
-    from . import compat
-    try:
-        return getattr(compat, name)
-    except AttributeError:
-        raise AttributeError(f"module {__name__!r} has no attribute {name!r}") from None
+        try:
+            while True:
+                item, ev, exc = q.get()
+                if exc is not None:
+                    raise exc
+                if item is done:
+                    break
+                if ev is not None:
+                    cur = torch.cuda.current_stream()
+                    cur.wait_event(ev)
+                    _record_stream(item, cur)   # memory allocated on the producer stream is consumed on this one
+                yield item
+        finally:
+            # normal end, an exception, or an abandoned iteration (generator closed / collected): stop the producer and wait
+            # for it, so that no thread is inside a CUDA call when the interpreter tears down
+            stop.set()
+            th.join(timeout=10)

@@ -13,7 +13,12 @@ from .._native import loader
 from ..base import dtype_code, id_code
 
 
+_ENABLED = [__import__("os").environ.get("DGLB200_GAT_FUSED", "1") != "0"]      # A/B switch
+
+
 def supported(el, ft, num_heads, head_dim):
+    if not _ENABLED[0]:
+        return False
     if not (ft.is_cuda and ft.dtype in (torch.float32, torch.bfloat16, torch.float16) and el.dtype == ft.dtype):
         return False
     vec = 16 // ft.element_size()
