@@ -138,10 +138,10 @@ def _gspmm_balanced(csr, ufeat2d, ew, num_dst, F, heads=1, out=None):
     # deterministic mode (USE_DETERMINISTIC_ALG=1 / dgl.global_config.set_deterministic): long rows are NOT split into
     # work items that meet in fp32 red.add scratch, so every output element is reduced by one sub-warp in a fixed order
     meta = {"n_long": 0} if is_deterministic() else _split_meta(indptr)
-    if ew is not None and eids is not None and F * ufeat2d.element_size() < 256:
-        # narrow rows: bring the per-edge scalars into CSC order once (sequential reads in the kernel instead of one random
-        # 32-byte sector per edge). For rows of 256 bytes and more the sector is small next to the gathered row and the
-        # kernel reads w[eid] in place - one launch and 12 bytes per edge of traffic less (measured: u_mul_e F >= 100 fp32)
+    if ew is not None and eids is not None:
+        # bring the per-edge scalars into CSC order once (sequential reads in the kernel instead of one random 32-byte
+        # sector per edge). Reading w[eid] inside the kernel was measured and is slower even for 512-byte rows
+        # (reddit F=128 fp32: 2.08 ms vs 1.68 ms with this pass).
         from .ops.cuda_struct import gather_rows
         ew = gather_rows(ew, eids)
         eids = None

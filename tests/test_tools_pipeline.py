@@ -196,3 +196,26 @@ def test_cli_recipe_train_apply_roundtrip(tmp_path):
     assert pred.shape[0] == D.CiteseerGraphDataset()[0].num_nodes()
     bad = subprocess.run(cli + ["recipe", "get", "nope"], capture_output=True, text=True)
     assert bad.returncode != 0
+
+
+def test_distgraphlaunch_sets_rendezvous_env_and_propagates_failure(tmp_path):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ipc = tmp_path / "ip_config.txt"
+    ipc.write_text("127.0.0.1\n")
+    script = tmp_path / "w.py"
+    script.write_text("import os\n"
+                      f"open(os.path.join({str(tmp_path)!r}, 'r' + os.environ['RANK']), 'w').write("
+                      "','.join(os.environ[k] for k in ('WORLD_SIZE', 'LOCAL_RANK', 'MASTER_ADDR', 'MASTER_PORT', 'FOO')))\n")
+    cmd = [sys.executable, os.path.join(root, "tools", "distgraphlaunch.py"), "--workspace", str(tmp_path), "--num_proc_per_machine", "3",
+           "--extra_envs", "FOO=bar", "--ip_config", str(ipc), "--master_port", "12345", f"{sys.executable} {script}"]
+    assert subprocess.run(cmd, timeout=60).returncode == 0
+    for r in range(3):
+        assert (tmp_path / f"r{r}").read_text() == f"3,{r},127.0.0.1,12345,bar"
+    bad = tmp_path / "bad.py"
+    bad.write_text("import os, sys, time\nif os.environ['RANK'] == '1':\n    sys.exit(7)\ntime.sleep(30)\n")
+    cmd[-1] = f"{sys.executable} {bad}"
+    t0 = __import__("time").time()
+    assert subprocess.run(cmd, timeout=60).returncode == 7
+    assert __import__("time").time() - t0 < 20          # the surviving copies were terminated, not waited for
