@@ -219,3 +219,22 @@ def test_distgraphlaunch_sets_rendezvous_env_and_propagates_failure(tmp_path):
     t0 = __import__("time").time()
     assert subprocess.run(cmd, timeout=60).returncode == 7
     assert __import__("time").time() - t0 < 20          # the surviving copies were terminated, not waited for
+
+
+def test_launcher_waits_for_the_job_and_returns_its_status(tmp_path):
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ipc = tmp_path / "ip_config.txt"
+    ipc.write_text("127.0.0.1 30050\n")
+    script = tmp_path / "job.py"
+    script.write_text("import os, time\n"
+                      "time.sleep(1.5)\n"
+                      f"open(os.path.join({str(tmp_path)!r}, 'done_' + os.environ['DGL_ROLE']), 'w').write('x')\n")
+    cmd = [sys.executable, os.path.join(root, "tools", "launch.py"), "--workspace", str(tmp_path), "--num_trainers", "1",
+           "--num_servers", "1", "--part_config", "none.json", "--ip_config", str(ipc), f"{sys.executable} {script}"]
+    out = subprocess.run(cmd, timeout=120)
+    assert out.returncode == 0
+    assert (tmp_path / "done_server").exists() and (tmp_path / "done_client").exists()
+    script.write_text("import os, sys, time\nsys.exit(5 if os.environ['DGL_ROLE'] == 'server' else time.sleep(60))\n")
+    assert subprocess.run(cmd, timeout=120).returncode == 5

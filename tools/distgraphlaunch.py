@@ -37,7 +37,7 @@ def build_commands(args, udf_command, job_tag):
             exports = " ".join(f"{k}={shlex.quote(str(v))}" for k, v in env.items())
             pidfile = f"/tmp/dglb200_distgraphlaunch_{job_tag}_{rank}.pid"
             body = f"cd {shlex.quote(args.workspace)} && {exports} {udf_command}"
-            wrapped = f"exec setsid bash -c {shlex.quote('echo $$ > ' + shlex.quote(pidfile) + '; ' + body)}"
+            wrapped = f"exec setsid -w bash -c {shlex.quote('echo $$ > ' + shlex.quote(pidfile) + '; ' + body)}"
             if is_local(ip):
                 argv = ["bash", "-c", wrapped]
             else:

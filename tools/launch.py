@@ -39,7 +39,7 @@ def wrap_cmd(ip, ssh_port, cmd, env, pidfile=None):
     full = f"cd {shlex.quote(env['DGL_WORKSPACE'])} && {exports} {cmd}"
     if pidfile:
         # own session on the target host; the group id (== pid of the session leader) is what cleanup signals
-        full = f"exec setsid bash -c {shlex.quote('echo $$ > ' + shlex.quote(pidfile) + '; ' + full)}"
+        full = f"exec setsid -w bash -c {shlex.quote('echo $$ > ' + shlex.quote(pidfile) + '; ' + full)}"
     if is_local(ip):
         return ["bash", "-c", full]
     return ["ssh", "-o", "StrictHostKeyChecking=no", "-p", str(ssh_port), ip, full]
