@@ -108,9 +108,9 @@ def build_commands(args, udf_command, job_tag=None):
         torch_cmd = (f"{sys.executable} -m torch.distributed.run --nproc_per_node={args.num_trainers} "
                      f"--nnodes={len(hosts)} --node_rank={node_rank} --master_addr={master_ip} "
                      f"--master_port={args.master_port} ")
-        trainer = udf_command
-        if trainer.startswith("python"):
-            trainer = trainer.split(" ", 1)[1] if " " in trainer else ""
+        # torch.distributed.run supplies the interpreter: drop a leading "python" / "/path/to/python3.x" token
+        first, _, rest = udf_command.partition(" ")
+        trainer = rest if os.path.basename(first).startswith("python") else udf_command
         pf = pidfile()
         cmds.append((ip, wrap_cmd(ip, args.ssh_port, torch_cmd + trainer, env, pf)) + ((pf,) if pf else ()))
     return cmds
