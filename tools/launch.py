@@ -164,8 +164,8 @@ def main():
             r = p.poll()
             if r is None:
                 alive = True
-            elif r != 0:
-                rc = r
+            elif r != 0 and rc == 0:
+                rc = r                      # the FIRST failure is the job's status; the rest die from the cleanup below
                 cleanup()
         if not alive:
             break
