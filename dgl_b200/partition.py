@@ -54,10 +54,14 @@ def _sym_csr(g):
 
 
 def metis_partition_assignment(g, k, balance_ntypes=None, balance_edges=False, mode="k-way", objtype="cut",
-                               refine_iters=8, imbalance=1.03):
+                               refine_iters=8, imbalance=1.03, algorithm="multilevel"):
     """Assign every node to one of ``k`` parts minimising the edge cut under a balance constraint.
-    (The reference calls METIS; this build uses the native LDG + label-propagation partitioner,
-    csrc/cpu/partition.cc.) Returns an int64 tensor of part ids."""
+    The reference calls METIS; this build ships its own partitioners (csrc/cpu/partition.cc): ``algorithm="multilevel"``
+    (default: heavy-edge-matching coarsening, LDG on the coarsest graph, k-way boundary refinement on the way back) or
+    ``"ldg"`` (one streaming pass + label propagation: faster, weaker on graphs with community structure).
+    Returns an int64 tensor of part ids."""
+    if algorithm not in ("multilevel", "ldg"):
+        raise DGLError("algorithm must be 'multilevel' or 'ldg'")
     if mode not in ("k-way", "recursive"):
         raise DGLError("mode must be 'k-way' or 'recursive'")
     hg, indptr, indices, n = _sym_csr(g)
@@ -67,7 +71,7 @@ def metis_partition_assignment(g, k, balance_ntypes=None, balance_edges=False, m
     if balance_edges:
         vwgt = (indptr[1:] - indptr[:-1]).clamp(min=1).contiguous()
     part = torch.empty(n, dtype=torch.int64)
-    loader.cpu_lib().fn("dglb200_cpu_ldg_partition", "ipplipidlp")(
+    loader.cpu_lib().fn("dglb200_cpu_ml_partition" if algorithm == "multilevel" else "dglb200_cpu_ldg_partition", "ipplipidlp")(
         id_code(torch.int64), indptr.data_ptr(), indices.data_ptr(), n, int(k), 0 if vwgt is None else vwgt.data_ptr(),
         int(refine_iters), float(imbalance), dgl_random.next_seed(), part.data_ptr())
     if balance_ntypes is not None:
