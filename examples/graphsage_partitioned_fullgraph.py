@@ -1,6 +1,8 @@
-"""Full-graph GraphSAGE on a vertex-partitioned graph across the GPUs of one NVLink domain: each layer's halo features
-are pulled over NVLink INSIDE the aggregation kernel (HaloPlan / halo_pipe_kernel), gradients of remote rows are pushed
-back with red.add, parameter gradients use the fused P2P all-reduce. No NCCL call on the training path.
+"""Full-graph GraphSAGE on a vertex-partitioned graph across the GPUs of one NVLink domain: per layer the de-duplicated
+halo rows are pulled from their owners over NVLink by one gather kernel on a side stream while the load-balanced g-SpMM
+aggregates the interior rows; the dense half is one tcgen05 GEMM per layer (``--tc``), parameter gradients use the fused
+P2P all-reduce. No NCCL call on the training path. (``bench.py --mode partitioned`` is the measured version of this on the
+products-shaped graph with the repo's partitioner; this script builds a synthetic partition with a chosen edge cut.)
 
   python -m torch.distributed.run --nproc-per-node 8 --master-addr 127.0.0.1 examples/graphsage_partitioned_fullgraph.py
 """
@@ -24,6 +26,7 @@ def main():
     ap.add_argument("--hidden", type=int, default=128)
     ap.add_argument("--classes", type=int, default=47)
     ap.add_argument("--epochs", type=int, default=20)
+    ap.add_argument("--tc", action="store_true", help="bf16 tcgen05 dense half (PartitionedSAGETC)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", rank)))
@@ -31,6 +34,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from dgl_b200.parallel import P2PComm, PartitionedSAGE
+    from dgl_b200.parallel.partitioned import PartitionedSAGETC
     comm = P2PComm()
     rows, deg = args.rows_per_rank, args.deg
     gen = torch.Generator().manual_seed(100 + rank)
@@ -44,7 +48,8 @@ def main():
     x = torch.randn(rows, args.feat, generator=gen).to(dev)
     y = torch.randint(0, args.classes, (rows,), generator=gen).to(dev)
     torch.manual_seed(0)                                           # identical initial weights on every rank
-    model = PartitionedSAGE(comm, indptr, indices, rows, args.feat, args.hidden, args.classes, num_layers=3).to(dev)
+    cls = PartitionedSAGETC if args.tc else PartitionedSAGE
+    model = cls(comm, indptr, indices, rows, args.feat, args.hidden, args.classes, num_layers=3).to(dev)
     opt = torch.optim.Adam(model.parameters(), lr=5e-3)
     for epoch in range(args.epochs):
         torch.cuda.synchronize()
