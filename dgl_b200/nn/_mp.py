@@ -166,3 +166,38 @@ def attend(g, scores):
 def edge_softmax_agg(g, scores, values_src):
     """softmax(scores) over in-edges, then the attention-weighted sum of source values: the GAT aggregation."""
     return gather_sum(g, values_src, attend(g, scores))
+
+
+# ---------------------------------------------------------------------------------------------- capacity-shaped blocks
+def is_capacity_block(graph):
+    """True for the fixed-capacity blocks of the whole-step CUDA-graph trainer (dataloading/graphed.py): an ELL neighbour
+    table plus a device-side live-row count instead of variable-shaped CSR arrays."""
+    return getattr(graph, "_caps", None) is not None and getattr(graph, "_ell_cache", None) is not None
+
+
+def capacity_aggregate(graph, x_src, reduce="mean"):
+    """(rows of the destination nodes, their neighbourhood reduction) on a capacity block: one ELL kernel forward, one
+    scatter kernel backward, no size read back (``ops.fused.ell_mean_concat``). ``reduce``: 'mean' or 'sum'."""
+    from ..ops.fused import ell_mean_concat
+    nbr, cnt, _ = graph._ell_cache
+    width = x_src.shape[1]
+    both = ell_mean_concat(x_src, nbr, cnt, graph._n_dst_dev)
+    own, pooled = both[:, :width], both[:, width:]
+    if reduce == "sum":
+        pooled = pooled * cnt.clamp(min=0).unsqueeze(1).to(pooled.dtype)
+    elif reduce != "mean":
+        raise DGLError(f"capacity blocks support 'mean' and 'sum' aggregation, got {reduce!r}")
+    return own, pooled
+
+
+def capacity_degrees(graph, n_src):
+    """(in-degree of every destination row, out-degree of every source row INSIDE the block) as float tensors, computed
+    on the device from the ELL table (padding rows / slots excluded)."""
+    nbr, cnt, fanout = graph._ell_cache
+    n_cap = nbr.shape[0]
+    live_row = torch.arange(n_cap, device=nbr.device).unsqueeze(1) < graph._n_dst_dev
+    live = (torch.arange(fanout, device=nbr.device).unsqueeze(0) < cnt.unsqueeze(1)) & live_row
+    indeg = (cnt * live_row.squeeze(1)).to(torch.float32)
+    outdeg = torch.zeros(n_src, dtype=torch.float32, device=nbr.device)
+    outdeg.index_add_(0, nbr.clamp(min=0).reshape(-1).long(), live.reshape(-1).to(torch.float32))
+    return indeg, outdeg

@@ -85,7 +85,34 @@ class GraphConv(nn.Module):
                            "parameter. Please create the module with flag weight=False.")
         return external
 
+    def _forward_capacity(self, graph, feat, W):
+        """Capacity-shaped block (whole-step CUDA graph): ELL aggregation kernels, degrees from the ELL table."""
+        x = feat[0] if isinstance(feat, (tuple, list)) else feat
+        shrink_first = W is not None and self._in_feats > self._out_feats
+        if self._norm in ("both", "left"):
+            _, outdeg = _mp.capacity_degrees(graph, x.shape[0])
+            x = x * outdeg.clamp(min=1).pow(-0.5 if self._norm == "both" else -1.0).unsqueeze(1).to(x.dtype)
+        if shrink_first:
+            x = x @ W.to(x.dtype)
+        pad = (-x.shape[1]) % 4
+        if pad:
+            x = torch.nn.functional.pad(x, (0, pad))
+        _, h = _mp.capacity_aggregate(graph, x, "mean" if self._norm == "right" else "sum")
+        h = h[:, : h.shape[1] - pad] if pad else h
+        if self._norm == "both":
+            indeg, _ = _mp.capacity_degrees(graph, x.shape[0])
+            h = h * indeg.clamp(min=1).pow(-0.5).unsqueeze(1).to(h.dtype)
+        if W is not None and not shrink_first:
+            h = h @ W.to(h.dtype)
+        if self.bias is not None:
+            h = h + self.bias.to(h.dtype)
+        return h if self._activation is None else self._activation(h)
+
     def forward(self, graph, feat, weight=None, edge_weight=None):
+        if _mp.is_capacity_block(graph):
+            if edge_weight is not None:
+                raise DGLError("edge weights are not supported on capacity blocks")
+            return self._forward_capacity(graph, feat, self._pick_weight(weight))
         _mp.require_in_edges(graph, self._allow_zero_in_degree, "GraphConv")
         if edge_weight is not None and edge_weight.shape[0] != graph.num_edges():
             raise DGLError("edge_weight must have one entry per edge")

@@ -130,6 +130,24 @@ class SAGEConv(nn.Module):
         fused = self._try_fused(graph, feat, edge_weight)
         if fused is not None:
             return fused
+        from .. import _mp
+        if _mp.is_capacity_block(graph):
+            # shapes the tcgen05 layer does not take (e.g. > 256 columns): ELL aggregation kernels + plain linear layers
+            if self._aggre_type not in ("mean", "gcn") or isinstance(feat, tuple):
+                raise DGLError("capacity blocks support the 'mean' and 'gcn' aggregators on a single feature tensor")
+            x = self.feat_drop(feat)
+            pad = (-x.shape[1]) % 4
+            own, pooled = _mp.capacity_aggregate(graph, torch.nn.functional.pad(x, (0, pad)) if pad else x, "mean")
+            own, pooled = (own[:, : x.shape[1]], pooled[:, : x.shape[1]]) if pad else (own, pooled)
+            if self._aggre_type == "gcn":
+                nbr, cnt, _ = graph._ell_cache
+                c = cnt.clamp(min=0).unsqueeze(1).to(pooled.dtype)
+                out = self.fc_neigh((pooled * c + own) / (c + 1))
+                out = out if self.bias is None else out + self.bias
+            else:
+                out = self.fc_self(own) + self.fc_neigh(pooled)
+            out = out if self.activation is None else self.activation(out)
+            return out if self.norm is None else self.norm(out)
         if edge_weight is not None and edge_weight.shape[0] != graph.num_edges():
             raise DGLError(f"edge_weight has {edge_weight.shape[0]} rows but the graph has {graph.num_edges()} edges")
         if isinstance(feat, tuple):

@@ -63,6 +63,13 @@ class GINConv(nn.Module):
         _eps_holder(self, init_eps, learn_eps)
 
     def forward(self, graph, feat, edge_weight=None):
+        if _mp.is_capacity_block(graph):                              # whole-step CUDA graph: ELL kernels, no size reads
+            x = feat[0] if isinstance(feat, (tuple, list)) else feat
+            x_dst, pooled = _mp.capacity_aggregate(graph, x, self._aggregator_type)
+            out = torch.addcmul(pooled, x_dst, (1 + self.eps).to(x_dst.dtype))
+            if self.apply_func is not None:
+                out = self.apply_func(out)
+            return out if self.activation is None else self.activation(out)
         x_src, x_dst = _mp.src_dst(graph, feat)
         if edge_weight is not None and edge_weight.shape[0] != graph.num_edges():
             raise DGLError("edge_weight must have one entry per edge")

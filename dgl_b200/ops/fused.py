@@ -130,3 +130,44 @@ class FrontierCompactor:
             self.hcap, _p(self.slot), _p(nodes), self.out_cap, _p(nbr_local), _p(count), _p(self.counter),
             _p(self.overflow), loader.stream_ptr())
         return nodes, nbr_local, count, self.overflow
+
+
+# ------------------------------------------------------------------------------------------- ELL aggregation with autograd
+class _EllMeanConcat(torch.autograd.Function):
+    """A[d] = [x[self(d)] | mean_{k < cnt[d]} x[nbr[d, k]]] for d < n_dev, zero rows beyond (csrc/cuda/engine.cu
+    ``agg_concat_kernel``); backward scatters both halves back with vector ``red.add`` (``scatter_grad_kernel``).
+    Everything is indexed by the device-side row count, so the op runs unchanged on capacity-shaped buffers inside a
+    captured CUDA graph (dataloading/graphed.py)."""
+
+    @staticmethod
+    def forward(ctx, x, nbr, cnt, n_dev):
+        n_cap, fanout = nbr.shape
+        F = x.shape[1]
+        A = torch.empty((n_cap, 2 * F), dtype=x.dtype, device=x.device)
+        from ..base import id_code
+        loader.cuda_lib().fn("dglb200_engine_agg_concat", "iippppplii" + "pi" + "p")(
+            dtype_code(x.dtype), id_code(torch.int32), _p(x), 0, _p(nbr), _p(cnt), _p(n_dev), n_cap, fanout, F, _p(A), 1,
+            loader.stream_ptr())
+        ctx.save_for_backward(nbr, cnt, n_dev)
+        ctx.shape = (x.shape[0], F, x.dtype)
+        return A
+
+    @staticmethod
+    def backward(ctx, dA):
+        nbr, cnt, n_dev = ctx.saved_tensors
+        n_src, F, dt = ctx.shape
+        from ..base import id_code
+        dX = torch.zeros((n_src, F), dtype=torch.float32, device=dA.device)
+        dA = dA.contiguous()
+        loader.cuda_lib().fn("dglb200_engine_scatter_grad", "iipppplii" + "p" + "p")(
+            dtype_code(dA.dtype), id_code(torch.int32), _p(dA), _p(nbr), _p(cnt), _p(n_dev), nbr.shape[0], nbr.shape[1], F,
+            _p(dX), loader.stream_ptr())
+        return dX.to(dt), None, None, None
+
+
+def ell_mean_concat(x, nbr, cnt, n_dev):
+    """[x_self | mean of the ELL neighbours]; x: [n_src, F] bf16 / fp32 (F % 4 == 0), nbr: int32 [n_dst_cap, fanout] local
+    source rows, cnt: int32 [n_dst_cap], n_dev: int64 [1] live destination rows. Differentiable in ``x``."""
+    if x.dtype not in (torch.bfloat16, torch.float32) or x.shape[1] % 4:
+        raise DGLError("ell_mean_concat needs bf16 / fp32 rows with a width that is a multiple of 4")
+    return _EllMeanConcat.apply(x.contiguous(), nbr, cnt, n_dev)

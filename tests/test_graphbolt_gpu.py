@@ -189,3 +189,95 @@ def test_graphed_trainer_table_input_mode_learns():
         assert torch.isfinite(losses).all() and losses[-4:].mean() < 0.5 * losses[:4].mean(), (amp, losses[:4], losses[-4:])
     with pytest.raises(dgl.DGLError):
         GraphedTrainer(g, x[:, :20].cuda(), y.cuda(), model, opt, [4, 4], 512, gather_inputs=False)
+
+
+def _capacity_and_real_blocks(n_src=600, n_dst=200, fanout=6, seed=0):
+    """One sampled layer as (CapacityBlock with padding rows, equivalent DGLBlock)."""
+    from dgl_b200.dataloading.graphed import CapacityBlock
+    g = torch.Generator().manual_seed(seed)
+    cap = n_dst + 56                                             # padding rows beyond the live count
+    cnt = torch.randint(0, fanout + 1, (cap,), generator=g).int()
+    nbr = torch.randint(0, n_src, (cap, fanout), generator=g).int()
+    nbr[torch.arange(fanout).unsqueeze(0) >= cnt.unsqueeze(1)] = -1
+    n_dev = torch.tensor([n_dst], dtype=torch.int64)
+    cb = CapacityBlock(nbr.cuda(), cnt.cuda(), fanout, n_src, cap, n_dev.cuda())
+    rows = torch.arange(n_dst).repeat_interleave(cnt[:n_dst].long())
+    cols = nbr[:n_dst][nbr[:n_dst] >= 0].long()
+    block = dgl.create_block((cols, rows), num_src_nodes=n_src, num_dst_nodes=n_dst).to("cuda")
+    return cb, block, n_dst
+
+
+@pytest.mark.parametrize("layer", ["gcn_both", "gcn_right", "gcn_none", "gcn_left", "gin_sum", "gin_mean", "sage_wide", "sage_gcn"])
+def test_capacity_block_layers_match_regular_blocks(layer):
+    """GraphConv / GINConv / SAGEConv on a capacity block (ELL kernels, device-side degrees) equal the same layer on the
+    equivalent variable-shape block: outputs of the live rows and all gradients."""
+    import copy
+    import dgl_b200.nn as dglnn
+    torch.manual_seed(0)
+    cb, block, n_dst = _capacity_and_real_blocks()
+    F_in, F_out = 20, 12
+    if layer.startswith("gcn"):
+        m = dglnn.GraphConv(F_in, F_out, norm=layer.split("_")[1], allow_zero_in_degree=True)
+    elif layer.startswith("gin"):
+        m = dglnn.GINConv(torch.nn.Linear(F_in, F_out), layer.split("_")[1], learn_eps=True)
+    elif layer == "sage_wide":
+        F_in = 320                                             # wider than the tcgen05 layer takes: ELL fallback
+        m = dglnn.SAGEConv(F_in, F_out, "mean")
+    else:
+        m = dglnn.SAGEConv(F_in, F_out, "gcn")
+    m = m.cuda()
+    ref = copy.deepcopy(m)
+    x = torch.randn(600, F_in, device="cuda")
+    xa, xb = x.clone().requires_grad_(), x.clone().requires_grad_()
+    out_c = m(cb, xa)[:n_dst]
+    out_r = ref(block, xb)
+    assert out_c.shape == out_r.shape and torch.allclose(out_c, out_r, atol=2e-4), (out_c - out_r).abs().max()
+    go = torch.randn_like(out_r)
+    out_c.backward(go)
+    out_r.backward(go)
+    assert torch.allclose(xa.grad, xb.grad, atol=2e-4)
+    for pa, pb in zip(m.parameters(), ref.parameters()):
+        assert torch.allclose(pa.grad, pb.grad, atol=5e-4), (pa.grad - pb.grad).abs().max()
+
+
+def test_graphed_trainer_with_gcn_and_gin_models():
+    """The whole-step CUDA graph is not tied to SAGE: a GCN stack and a GIN stack built from the public nn layers train."""
+    import dgl_b200.nn as dglnn
+    from dgl_b200.dataloading import GraphedTrainer
+    torch.manual_seed(0)
+    n, C, Fdim = 3000, 4, 32
+    y = torch.randint(0, C, (n,))
+    x = (torch.randn(C, Fdim) * 1.5)[y] + torch.randn(n, Fdim)
+    src = torch.randint(0, n, (50000,))
+    dst = torch.randint(0, n, (50000,))
+    g = dgl.graph((src.int(), dst.int()), num_nodes=n, idtype=torch.int32).to("cuda")
+    g.create_formats_()
+
+    class Net(torch.nn.Module):
+        def __init__(self, kind):
+            super().__init__()
+            if kind == "gcn":
+                self.l1 = dglnn.GraphConv(Fdim, 48, norm="both", allow_zero_in_degree=True)
+                self.l2 = dglnn.GraphConv(48, 48, norm="right", allow_zero_in_degree=True)
+            else:
+                self.l1 = dglnn.GINConv(torch.nn.Linear(Fdim, 48), "mean")
+                self.l2 = dglnn.GINConv(torch.nn.Linear(48, 48), "sum")
+            self.skip = torch.nn.Linear(Fdim, 48)
+            self.out = torch.nn.Linear(48, C)
+
+        def forward(self, blocks, h):
+            h1 = torch.relu(self.l1(blocks[0], h))
+            h2 = torch.relu(self.l2(blocks[1], h1))
+            return self.out(h2)
+
+    for kind in ("gcn", "gin"):
+        model = Net(kind).cuda()
+        opt = torch.optim.Adam(model.parameters(), lr=5e-3, capturable=True)
+        tr = GraphedTrainer(g, x.cuda(), y.cuda(), model, opt, [5, 5], 256)
+        losses = []
+        for ep in range(6):
+            perm = torch.randperm(n)
+            for i in range(0, n - 255, 256):
+                losses.append(tr.step(perm[i:i + 256]).clone())
+        losses = torch.stack(losses).cpu()
+        assert torch.isfinite(losses).all() and losses[-5:].mean() < 0.7 * losses[:5].mean(), (kind, losses[:5], losses[-5:])
