@@ -79,7 +79,7 @@ def run_ours(args, n, u, v, feat, labels, train):
         from dgl_b200.dataloading import GraphedTrainer
         g = g.to(dev)
         g.create_formats_()
-        model = GraphSAGE(128, 256, 172, 3, 0.5).to(dev)
+        model = (GraphSAGE(128, 256, 172, 3, 0.5) if args.model == "sage" else make_model(dgl.nn, args.model)).to(dev)
         opt = torch.optim.Adam(model.parameters(), lr=1e-3, capturable=True)
         trainer = GraphedTrainer(g, feat.to(dev), labels.to(dev), model, opt, args.fanouts, args.batch, amp=args.amp,
                                  gather_inputs=not args.table_input)

@@ -146,7 +146,33 @@ class GATConv(_HeadedAttention):
         out = gat_fused.fused_gat(g._graphs[0], s_src, s_dst, z, self.leaky_relu.negative_slope)
         return out[..., : self._out_feats] if pad else out
 
+    def _forward_capacity(self, graph, feat):
+        """Capacity-shaped block (whole-step CUDA graph): attention over the ELL table as dense [rows, fanout, heads]
+        tensors with the padding slots masked - plain tensor ops of fixed shape, so the step stays capturable and
+        autograd needs no custom backward."""
+        if isinstance(feat, (tuple, list)):
+            raise DGLError("capacity blocks take one feature tensor (destinations are the prefix of the sources)")
+        nbr, cnt, fanout = graph._ell_cache
+        h_src = self.feat_drop(feat)
+        h_dst = h_src[: graph.num_dst_nodes()]
+        z_src, z_dst = self._project(graph, h_src, h_dst, shared_input=True)
+        s_src = (z_src * self.attn_l).sum(-1)                      # [N_src, H]
+        s_dst = (z_dst * self.attn_r).sum(-1)                      # [N_dst_cap, H]
+        slot = nbr.clamp(min=0).long()                             # [N_dst_cap, fanout]
+        live = torch.arange(fanout, device=nbr.device).unsqueeze(0) < cnt.unsqueeze(1)
+        score = self.leaky_relu(s_src[slot] + s_dst.unsqueeze(1))  # [N_dst_cap, fanout, H]
+        score = score.masked_fill(~live.unsqueeze(-1), float("-inf"))
+        attn = torch.softmax(score, dim=1)
+        attn = torch.nan_to_num(attn, nan=0.0)                     # rows without neighbours: all slots masked
+        attn = self.attn_drop(attn)
+        out = (attn.unsqueeze(-1) * z_src[slot]).sum(1)            # [N_dst_cap, H, D]
+        return self._epilogue(out, h_dst, self.bias)
+
     def forward(self, graph, feat, edge_weight=None, get_attention=False):
+        if _mp.is_capacity_block(graph):
+            if edge_weight is not None or get_attention:
+                raise DGLError("edge weights / attention output are not available on capacity blocks")
+            return self._forward_capacity(graph, feat)
         _mp.require_in_edges(graph, self._allow_zero_in_degree, self._layer_name)
         g, emap, edge_weight = _attention_view(graph, edge_weight)
         h_src, h_dst = self._inputs(g, feat, self.feat_drop)
