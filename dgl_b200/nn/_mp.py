@@ -201,3 +201,42 @@ def capacity_degrees(graph, n_src):
     outdeg = torch.zeros(n_src, dtype=torch.float32, device=nbr.device)
     outdeg.index_add_(0, nbr.clamp(min=0).reshape(-1).long(), live.reshape(-1).to(torch.float32))
     return indeg, outdeg
+
+
+class CapacityRelation:
+    """The two sparse layouts the fused GAT kernels need, built ON THE DEVICE from a capacity block's ELL table with
+    capacity-sized buffers (nothing is read back, so construction is CUDA-graph capturable):
+
+    * ``csc()``  - destination-major: ``indptr`` = exclusive scan of the live per-row counts, ``indices`` compacted by one
+      ``ell_to_csc`` launch (the tail of the buffer beyond the live edge count is never addressed);
+    * ``csr()``  - source-major, for the backward: the ELL slots as a COO list in which padding slots are sent to a
+      sentinel source row ``n_src`` and sorted away by the radix-sort CSR builder (``structure_build.cu``)."""
+
+    def __init__(self, graph, n_src):
+        from .._native import loader
+        from ..base import id_code
+        from ..ops.cuda_struct import cuda_coo_to_csr
+        nbr, cnt, fanout = graph._ell_cache
+        dev = nbr.device
+        n_cap = nbr.shape[0]
+        live_row = torch.arange(n_cap, device=dev) < graph._n_dst_dev
+        cnt_live = (cnt * live_row).to(torch.int32)
+        ptr64 = torch.zeros(n_cap + 1, dtype=torch.int64, device=dev)
+        torch.cumsum(cnt_live, 0, out=ptr64[1:])
+        idx = torch.zeros(n_cap * fanout, dtype=torch.int32, device=dev)
+        loader.cuda_lib().fn("dglb200_ell_to_csc", "ipppplipppp")(
+            id_code(torch.int32), nbr.data_ptr(), 0, cnt_live.data_ptr(), ptr64.data_ptr(), n_cap, fanout, idx.data_ptr(), 0, 0,
+            loader.stream_ptr())
+        self._csc = (ptr64.to(torch.int32), idx, None)
+        live = torch.arange(fanout, device=dev).unsqueeze(0) < cnt_live.unsqueeze(1)
+        src = torch.where(live, nbr, torch.full_like(nbr, n_src)).reshape(-1)
+        dst = torch.arange(n_cap, dtype=torch.int32, device=dev).repeat_interleave(fanout)
+        rp, ri, _ = cuda_coo_to_csr(src, dst, n_src + 1)           # row n_src collects the padding slots
+        self._csr = (rp[: n_src + 1].contiguous(), ri, None)
+        self.num_src, self.num_dst = n_src, n_cap
+
+    def csc(self):
+        return self._csc
+
+    def csr(self):
+        return self._csr

@@ -140,6 +140,7 @@ class GATConv(_HeadedAttention):
         """Scores + softmax + aggregation in the fused kernels; None when the shape is not covered."""
         from ...ops import gat_fused
         pad = (-self._out_feats) % (16 // z_src.element_size())   # per-head rows padded to 16 bytes
+        s_src, s_dst = s_src.to(z_src.dtype), s_dst.to(z_src.dtype)  # autocast leaves the score reductions in fp32
         if not gat_fused.supported(s_src.unsqueeze(-1), z_src, self._num_heads, self._out_feats + pad):
             return None
         z = F.pad(z_src, (0, pad)) if pad else z_src
@@ -147,12 +148,10 @@ class GATConv(_HeadedAttention):
         return out[..., : self._out_feats] if pad else out
 
     def _forward_capacity(self, graph, feat):
-        """Capacity-shaped block (whole-step CUDA graph): attention over the ELL table as dense [rows, fanout, heads]
-        tensors with the padding slots masked - plain tensor ops of fixed shape, so the step stays capturable and
-        autograd needs no custom backward. This is a FUNCTIONAL path, not a fast one: the gathered [rows, fanout, H, D]
-        tensor is materialised and its backward is an index-add over all slots (measured 175 ms/step on the papers100M x
-        0.05 pipeline, against 16 ms for the eager fused-kernel path on variable-shape blocks) - ELL-native attention
-        kernels are the open item here."""
+        """Capacity-shaped block (whole-step CUDA graph). Fast path: the fused attention kernels over a CSC / CSR pair
+        built on the device from the ELL table (``_mp.CapacityRelation``). Shapes the kernels do not take, or attention
+        dropout in training, use dense masked attention over the ELL table ([rows, fanout, heads] tensors of fixed shape -
+        functional, but slow: the gathered tensor is materialised and its backward is an index-add over all slots)."""
         if isinstance(feat, (tuple, list)):
             raise DGLError("capacity blocks take one feature tensor (destinations are the prefix of the sources)")
         nbr, cnt, fanout = graph._ell_cache
@@ -161,6 +160,16 @@ class GATConv(_HeadedAttention):
         z_src, z_dst = self._project(graph, h_src, h_dst, shared_input=True)
         s_src = (z_src * self.attn_l).sum(-1)                      # [N_src, H]
         s_dst = (z_dst * self.attn_r).sum(-1)                      # [N_dst_cap, H]
+        from ...ops import gat_fused
+        pad = (-self._out_feats) % (16 // z_src.element_size())
+        s_src, s_dst = s_src.to(z_src.dtype), s_dst.to(z_src.dtype)   # autocast leaves the score reductions in fp32
+        if not (self.training and self.attn_drop.p > 0) and \
+                gat_fused.supported(s_src.unsqueeze(-1), z_src, self._num_heads, self._out_feats + pad):
+            rel = _mp.CapacityRelation(graph, z_src.shape[0])
+            z = F.pad(z_src, (0, pad)) if pad else z_src
+            out = gat_fused.fused_gat(rel, s_src, s_dst, z, self.leaky_relu.negative_slope)
+            out = out[..., : self._out_feats] if pad else out
+            return self._epilogue(out, h_dst, self.bias)
         slot = nbr.clamp(min=0).long()                             # [N_dst_cap, fanout]
         live = torch.arange(fanout, device=nbr.device).unsqueeze(0) < cnt.unsqueeze(1)
         score = self.leaky_relu(s_src[slot] + s_dst.unsqueeze(1))  # [N_dst_cap, fanout, H]
