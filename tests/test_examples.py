@@ -98,3 +98,19 @@ def test_tutorials_run(script):
         runpy.run_path(os.path.join(ROOT, "docs", "tutorials", script), run_name="__main__")
     finally:
         sys.argv = old
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("model", ["gcn", "gat"])
+def test_graphed_minibatch_example_learns(model):
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("graphed_example", os.path.join(ROOT, "examples", "graphed_minibatch_training.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    old = sys.argv
+    sys.argv = ["x", "--model", model, "--nodes", "20000", "--epochs", "3", "--batch", "512"]
+    try:
+        loss = mod.main()
+    finally:
+        sys.argv = old
+    assert loss < 1.0          # 8 classes: chance is ln 8 = 2.08
