@@ -17,7 +17,7 @@ def main():
     class A:
         pass
     args = A()
-    args.resident, args.cache_mb, args.batch, args.workers, args.fanouts, args.amp = "device", 0, 1024, 0, [10, 10, 10], False
+    args.resident, args.cache_mb, args.batch, args.workers, args.fanouts, args.amp = "device", 0, 1024, 0, [10, 10, 10], os.environ.get("AMP", "0") == "1"
     args.model = os.environ.get("MODEL", "sage")
     args.graphed = os.environ.get("GRAPHED", "0") == "1"
     args.table_input = os.environ.get("TABLE", "0") == "1"

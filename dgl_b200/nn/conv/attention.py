@@ -136,6 +136,19 @@ class GATConv(_HeadedAttention):
             if self.res_fc.bias is not None:
                 nn.init.zeros_(self.res_fc.bias)
 
+    def _scores(self, h_src, h_dst, z_src, z_dst):
+        """Attention logit halves ``a_l . (W h_j)`` and ``a_r . (W h_i)`` per head. The attention vectors are folded into the
+        projection, ``a . (W h) = (W^T a) . h``, so each half is ONE [N, in] x [in, H] product instead of a broadcast
+        multiply and a reduction over the [N, H, D] projections (those two elementwise passes and their backward were
+        the largest items of the GAT mini-batch step in the profile)."""
+        H, D = self._num_heads, self._out_feats
+        lin_src, lin_dst = (self.fc, self.fc) if hasattr(self, "fc") else (self.fc_src, self.fc_dst)
+        if lin_src.bias is not None or lin_dst.bias is not None or h_src.dim() != 2:
+            return (z_src * self.attn_l).sum(-1), (z_dst * self.attn_r).sum(-1)
+        w_l = (lin_src.weight.view(H, D, -1) * self.attn_l.view(H, D, 1)).sum(1)      # [H, in]
+        w_r = (lin_dst.weight.view(H, D, -1) * self.attn_r.view(H, D, 1)).sum(1)
+        return h_src @ w_l.t().to(h_src.dtype), h_dst @ w_r.t().to(h_dst.dtype)
+
     def _fused(self, g, z_src, s_src, s_dst):
         """Scores + softmax + aggregation in the fused kernels; None when the shape is not covered."""
         from ...ops import gat_fused
@@ -158,8 +171,7 @@ class GATConv(_HeadedAttention):
         h_src = self.feat_drop(feat)
         h_dst = h_src[: graph.num_dst_nodes()]
         z_src, z_dst = self._project(graph, h_src, h_dst, shared_input=True)
-        s_src = (z_src * self.attn_l).sum(-1)                      # [N_src, H]
-        s_dst = (z_dst * self.attn_r).sum(-1)                      # [N_dst_cap, H]
+        s_src, s_dst = self._scores(h_src, h_dst, z_src, z_dst)   # [N_src, H], [N_dst_cap, H]
         from ...ops import gat_fused
         pad = (-self._out_feats) % (16 // z_src.element_size())
         s_src, s_dst = s_src.to(z_src.dtype), s_dst.to(z_src.dtype)   # autocast leaves the score reductions in fp32
@@ -189,8 +201,7 @@ class GATConv(_HeadedAttention):
         g, emap, edge_weight = _attention_view(graph, edge_weight)
         h_src, h_dst = self._inputs(g, feat, self.feat_drop)
         z_src, z_dst = self._project(g, h_src, h_dst, shared_input=not isinstance(feat, (tuple, list)))
-        s_src = (z_src * self.attn_l).sum(-1)                      # [N_src, H]
-        s_dst = (z_dst * self.attn_r).sum(-1)
+        s_src, s_dst = self._scores(h_src, h_dst, z_src, z_dst)   # [N_src, H], [N_dst, H]
         plain = edge_weight is None and not get_attention and not (self.training and self.attn_drop.p > 0)
         if plain and z_src.is_cuda and z_src.dim() == 3 and len(g.canonical_etypes) == 1:
             out = self._fused(g, z_src, s_src, s_dst)
