@@ -103,3 +103,24 @@ def test_cugraph_base_pad_offsets_and_small_functions():
     assert torch.allclose(pairwise_squared_distance(x), torch.cdist(x, x) ** 2, atol=1e-4)
     g = gaussian(torch.tensor([0.0]), torch.tensor([0.0]), torch.tensor([1.0]))
     assert abs(float(g) - 0.39894) < 1e-3
+
+
+def test_gat_score_folding_equals_direct_form():
+    """``a . (W h) == (W^T a) . h``: the folded logit halves of GATConv equal the direct broadcast-multiply-reduce form,
+    for the shared projection and for separate source / destination projections."""
+    import torch
+    import dgl_b200.nn as dglnn
+    torch.manual_seed(0)
+    for in_feats in (12, (12, 7)):
+        conv = dglnn.GATConv(in_feats, 5, 3)
+        n_src, n_dst = 20, 9
+        h_src = torch.randn(n_src, 12)
+        h_dst = h_src[:n_dst] if isinstance(in_feats, int) else torch.randn(n_dst, 7)
+        if isinstance(in_feats, int):
+            z_src = conv.fc(h_src).view(n_src, 3, 5)
+            z_dst = z_src[:n_dst]
+        else:
+            z_src, z_dst = conv.fc_src(h_src).view(n_src, 3, 5), conv.fc_dst(h_dst).view(n_dst, 3, 5)
+        a, b = conv._scores(h_src, h_dst, z_src, z_dst)
+        assert torch.allclose(a, (z_src * conv.attn_l).sum(-1), atol=1e-5)
+        assert torch.allclose(b, (z_dst * conv.attn_r).sum(-1), atol=1e-5)
