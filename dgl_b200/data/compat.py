@@ -12,6 +12,7 @@ import numpy as np
 import torch
 
 from ..base import DGLError
+from . import dgl_binary
 from . import more as _more
 from .graph_serialize import MAGIC, VERSION, load_graphs, load_labels, save_graphs
 
@@ -196,13 +197,15 @@ def save_tensors(filename, tensor_dict):
         if not torch.is_tensor(v):
             raise DGLError("Dict value has to be backend tensor or dgl ndarray")
     os.makedirs(os.path.dirname(os.path.abspath(filename)), exist_ok=True)
-    torch.save({"magic": MAGIC + "-TENSORS", "version": VERSION,
-                "tensors": {k: v.detach().cpu() for k, v in tensor_dict.items()}}, filename)
+    # the reference's tensor container (read back by either framework, memory mapped here)
+    dgl_binary.write_tensors(filename, tensor_dict)
     return True
 
 
 def load_tensors(filename, return_dgl_ndarray=False):
-    d = torch.load(filename, weights_only=False)
+    if dgl_binary.is_dgl_binary(filename):
+        return dgl_binary.read_tensors(filename)
+    d = torch.load(filename, weights_only=True)
     if d.get("magic") != MAGIC + "-TENSORS":
         raise DGLError("Invalid tensor archive (bad magic)")
     return d["tensors"]

@@ -4,8 +4,11 @@ Container: one ``torch.save`` archive holding ONLY tensors and plain Python cont
 structure per relation, node/edge frames, optional label dict), so it is read back with ``weights_only=True``: loading a
 graph file never unpickles arbitrary objects. Heterographs, blocks and batched graphs round-trip.
 
-The reference's ``.bin`` files use libdgl's own binary layout (src/graph/serialize/*, dmlc streams of NDArrays); they
-are not read here. ``tools/convert_dgl_bin.py`` converts them (graphs + labels) with an installed reference build."""
+The reference's binary layout (src/graph/serialize/*, dmlc streams of NDArrays) is implemented by ``dgl_binary.py``:
+``load_graphs`` recognises such files by their magic and reads them in place (memory mapped), and
+``save_graphs(..., container="dgl")`` -- the default for ``*.bin`` / ``*.dgl`` names of plain ``DGLGraph`` lists, the
+names the reference's users and its partition tools produce -- writes files the reference's ``dgl.load_graphs`` reads.
+Blocks and batched graphs carry state that layout has no field for, so they always use the tensor archive."""
 from __future__ import annotations
 
 import os
@@ -17,6 +20,7 @@ from ..base import DGLError
 from ..frame import Frame
 from ..graph_index import UnitGraph
 from ..heterograph import DGLGraph
+from . import dgl_binary
 
 MAGIC = "DGLB200-GRAPHS"
 VERSION = 1
@@ -51,13 +55,30 @@ def _unpack(d):
     return g
 
 
-def save_graphs(filename, g_list, labels=None, formats=None):
+def _binary_ok(g_list):
+    return all(type(g) is DGLGraph and g._srctypes is None and g._batch_num_nodes is None and g._batch_num_edges is None
+               for g in g_list)
+
+
+def save_graphs(filename, g_list, labels=None, formats=None, container=None):
+    """``container``: "dgl" (reference binary layout), "archive" (tensor-only torch archive) or None = by file name."""
     if isinstance(g_list, DGLGraph):
         g_list = [g_list]
     if labels is not None and not isinstance(labels, dict):
         raise DGLError("labels must be a dict of tensors")
+    if os.path.isdir(filename):
+        raise DGLError(f"Filename {filename} is an existing directory.")
     d = os.path.dirname(os.path.abspath(filename))
     os.makedirs(d, exist_ok=True)
+    if container is None:
+        container = "dgl" if str(filename).endswith((".bin", ".dgl")) and _binary_ok(g_list) else "archive"
+    if container == "dgl":
+        if not _binary_ok(g_list):
+            raise DGLError("the DGL binary layout stores plain DGLGraph objects only (no blocks / batched graphs)")
+        dgl_binary.write_graphs(filename, g_list, labels, formats)
+        return
+    if container != "archive":
+        raise DGLError(f"unknown container {container!r}")
     torch.save({"magic": MAGIC, "version": VERSION, "graphs": [_pack(g) for g in g_list], "labels": labels or {}}, filename)
 
 
@@ -69,9 +90,6 @@ def _read_archive(filename):
     except Exception as e:  # noqa: BLE001 - not a torch archive, or it contains objects: refuse, never unpickle them
         with open(filename, "rb") as fh:
             head = fh.read(8)
-        if head == b"\x3f\xa1\xb4\x46\xf0\x4f\x2e\xdd":
-            raise DGLError(f"{filename} is a reference (libdgl) binary graph file; convert it with "
-                           "tools/convert_dgl_bin.py") from None
         raise DGLError(f"{filename} is not a graph archive of this framework: {type(e).__name__}: {e}") from None
     if not isinstance(d, dict) or d.get("magic") != MAGIC or not isinstance(d.get("graphs"), list):
         raise DGLError("Invalid DGL graph file (bad magic)")
@@ -81,6 +99,8 @@ def _read_archive(filename):
 
 
 def load_graphs(filename, idx_list=None):
+    if dgl_binary.is_dgl_binary(filename):
+        return dgl_binary.read_graphs(filename, idx_list)
     d = _read_archive(filename)
     packs = d["graphs"]
     if idx_list is not None:
@@ -95,6 +115,8 @@ def load_graphs(filename, idx_list=None):
 
 
 def load_labels(filename):
+    if dgl_binary.is_dgl_binary(filename):
+        return dgl_binary.read_labels(filename)
     return _read_archive(filename).get("labels", {})
 
 
