@@ -2,7 +2,7 @@
 
 Parity: /root/reference/python/dgl/distributed/partition.py (partition_graph :817-1400, load_partition :286,
 load_partition_book, inner_node/inner_edge masks :37-45) and graph_partition_book.py (RangePartitionBook).
-Artifacts: ``<out>/<name>.json`` + ``<out>/part<i>/{graph.pt,node_feat.pt,edge_feat.pt}``. Node (and edge) ids are
+Artifacts: ``<out>/<name>.json`` + ``<out>/part<i>/{graph.dgl,node_feat.dgl,edge_feat.dgl}``. Node (and edge) ids are
 reshuffled so every partition owns one contiguous global-id range per type; ``orig_id`` keeps the mapping."""
 from __future__ import annotations
 
@@ -14,6 +14,7 @@ import torch
 
 from ..base import EID, NID, DGLError
 from ..convert import graph as make_graph
+from ..data import dgl_binary as _binary
 from ..partition import metis_partition_assignment
 
 RESERVED_FIELD_DTYPE = {"inner_node": torch.uint8, "inner_edge": torch.uint8}
@@ -277,8 +278,13 @@ def partition_graph(g, graph_name, num_parts, out_path, num_hops=1, part_method=
         edata = {EID: new_eid[ke], "inner_edge": inner_e[ke].to(torch.uint8), "orig_id": ke, ETYPE: etype_new_by_orig[ke]}
         pdir = os.path.join(out_path, f"part{p}")
         os.makedirs(pdir, exist_ok=True)
-        torch.save({"src": pg.edges()[0], "dst": pg.edges()[1], "num_nodes": pg.num_nodes(), "ndata": ndata, "edata": edata},
-                   os.path.join(pdir, "graph.pt"))
+        for k, v in ndata.items():
+            pg.ndata[k] = v
+        for k, v in edata.items():
+            pg.edata[k] = v
+        # the reference's artifact names and binary containers: partitions written by either framework load in the other,
+        # and loading memory-maps the files instead of reading them
+        _binary.write_graphs(os.path.join(pdir, "graph.dgl"), [pg])
         nfeat, efeat = {}, {}
         off = int(pstart[p])
         for t, nt in enumerate(ntypes):                                        # inner nodes of type t, in new-id order
@@ -294,10 +300,10 @@ def partition_graph(g, graph_name, num_parts, out_path, num_hops=1, part_method=
             frame = g.edges[cet].data if hetero else g.edata
             for k, val in frame.items():
                 efeat[f"{ekeys[r]}/{k}"] = val[ids]
-        torch.save(nfeat, os.path.join(pdir, "node_feat.pt"))
-        torch.save(efeat, os.path.join(pdir, "edge_feat.pt"))
-        meta[f"part-{p}"] = {"node_feats": f"part{p}/node_feat.pt", "edge_feats": f"part{p}/edge_feat.pt",
-                             "part_graph": f"part{p}/graph.pt"}
+        _binary.write_tensors(os.path.join(pdir, "node_feat.dgl"), nfeat)
+        _binary.write_tensors(os.path.join(pdir, "edge_feat.dgl"), efeat)
+        meta[f"part-{p}"] = {"node_feats": f"part{p}/node_feat.dgl", "edge_feats": f"part{p}/edge_feat.dgl",
+                             "part_graph": f"part{p}/graph.dgl"}
     cfg = os.path.join(out_path, f"{graph_name}.json")
     with open(cfg, "w") as f:
         json.dump(meta, f, indent=2)
@@ -309,6 +315,25 @@ def partition_graph(g, graph_name, num_parts, out_path, num_hops=1, part_method=
         emap = {cet: type_eid[eorder[etype_of[eorder] == r]] for r, cet in enumerate(cets)}
         return nmap, emap
     return None
+
+
+def _load_part_graph(path):
+    """Partition structure file: the reference's binary container (graph.dgl) or the round-1 tensor archive (graph.pt)."""
+    if _binary.is_dgl_binary(path):
+        return _binary.read_graphs(path)[0][0]
+    d = torch.load(path, weights_only=True)
+    g = make_graph((d["src"], d["dst"]), num_nodes=d["num_nodes"])
+    for k, v in d["ndata"].items():
+        g.ndata[k] = v
+    for k, v in d["edata"].items():
+        g.edata[k] = v
+    return g
+
+
+def _load_feat_file(path):
+    if _binary.is_dgl_binary(path):
+        return _binary.read_tensors(path)
+    return torch.load(path, weights_only=True)
 
 
 def load_partition_book(part_config, part_id):
@@ -324,14 +349,9 @@ def load_partition(part_config, part_id, load_feats=True, use_graphbolt=False):
         meta = json.load(f)
     base = os.path.dirname(part_config)
     info = meta[f"part-{part_id}"]
-    d = torch.load(os.path.join(base, info["part_graph"]), weights_only=True)
-    g = make_graph((d["src"], d["dst"]), num_nodes=d["num_nodes"])
-    for k, v in d["ndata"].items():
-        g.ndata[k] = v
-    for k, v in d["edata"].items():
-        g.edata[k] = v
-    nf = torch.load(os.path.join(base, info["node_feats"]), weights_only=True) if load_feats else {}
-    ef = torch.load(os.path.join(base, info["edge_feats"]), weights_only=True) if load_feats else {}
+    g = _load_part_graph(os.path.join(base, info["part_graph"]))
+    nf = _load_feat_file(os.path.join(base, info["node_feats"])) if load_feats else {}
+    ef = _load_feat_file(os.path.join(base, info["edge_feats"])) if load_feats else {}
     gpb, name, ntypes, etypes = load_partition_book(part_config, part_id)
     return g, nf, ef, gpb, name, ntypes, etypes
 
@@ -341,8 +361,8 @@ def load_partition_feats(part_config, part_id, load_nodes=True, load_edges=True)
         meta = json.load(f)
     base = os.path.dirname(part_config)
     info = meta[f"part-{part_id}"]
-    nf = torch.load(os.path.join(base, info["node_feats"]), weights_only=True) if load_nodes else None
-    ef = torch.load(os.path.join(base, info["edge_feats"]), weights_only=True) if load_edges else None
+    nf = _load_feat_file(os.path.join(base, info["node_feats"])) if load_nodes else None
+    ef = _load_feat_file(os.path.join(base, info["edge_feats"])) if load_edges else None
     return nf, ef
 
 

@@ -200,3 +200,45 @@ def test_files_written_here_load_in_the_reference(tmp_path, formats):
         for c in ours.canonical_etypes:
             for k, v in ours.edges[c].data.items():
                 assert theirs["edata"][c[1]][k] == v.float().tolist()
+
+
+_REF_PARTITION = r"""
+import sys, torch, unittest.mock as um
+sys.path.insert(0, sys.argv[1])
+import dgl
+# GraphBolt's C++ library is not part of the reference build used here; dgl.distributed only needs the name to import
+_gb = um.MagicMock(); _gb.FusedCSCSamplingGraph = type("FusedCSCSamplingGraph", (), {}); sys.modules["dgl.graphbolt"] = _gb
+import dgl.distributed
+torch.manual_seed(0)
+g = dgl.rand_graph(200, 1500)
+g.ndata["feat"] = torch.arange(200, dtype=torch.float32).unsqueeze(1).repeat(1, 4)
+g.edata["w"] = torch.arange(1500, dtype=torch.float32)
+dgl.distributed.partition_graph(g, "tg", 2, sys.argv[2], part_method="random", num_hops=1)
+torch.save({"src": g.edges()[0], "dst": g.edges()[1]}, sys.argv[2] + "/orig.pt")
+"""
+
+
+@needs_ref
+def test_partitions_written_by_the_reference_serve_a_distgraph(tmp_path):
+    import dgl_b200.distributed as dist
+    out = str(tmp_path / "parts")
+    env = dict(os.environ, DGLBACKEND="pytorch", CUDA_VISIBLE_DEVICES="")
+    r = subprocess.run([sys.executable, "-c", _REF_PARTITION, REF, out], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    cfg = os.path.join(out, "tg.json")
+    total_inner = 0
+    for p in (0, 1):
+        g, nf, ef, gpb, name, ntypes, etypes = dist.load_partition(cfg, p)
+        assert name == "tg" and ntypes == ["_N"] and {"_ID", "inner_node", "part_id"} <= set(g.ndata.keys())
+        inner = g.ndata["inner_node"].bool()
+        total_inner += int(inner.sum())
+        assert nf["_N/feat"].shape == (int(inner.sum()), 4) and ef["_N:_E:_N/w"].shape[0] == int(g.edata["inner_edge"].sum())
+    assert total_inner == 200
+    dist.initialize(None)
+    dg = dist.DistGraph("tg", part_config=cfg)
+    assert dg.num_nodes() == 200 and dg.num_edges() == 1500
+    rows = dg.ndata["feat"][torch.arange(200)]
+    # the reference relabels nodes; every original row appears exactly once
+    assert sorted(rows[:, 0].tolist()) == list(range(200))
+    fr = dist.sample_neighbors(dg, torch.arange(50), 3)
+    assert 0 < fr.num_edges() <= 150

@@ -37,11 +37,19 @@ def build_partition(part_id, inner_new_ids, inner_orig_ids, edges_new, edge_new_
 def write_partition(out_dir, part_id, graph_dict, node_feats, edge_feats):
     pdir = os.path.join(out_dir, f"part{part_id}")
     os.makedirs(pdir, exist_ok=True)
-    torch.save(graph_dict, os.path.join(pdir, "graph.pt"))
-    torch.save(node_feats, os.path.join(pdir, "node_feat.pt"))
-    torch.save(edge_feats, os.path.join(pdir, "edge_feat.pt"))
-    return {"node_feats": f"part{part_id}/node_feat.pt", "edge_feats": f"part{part_id}/edge_feat.pt",
-            "part_graph": f"part{part_id}/graph.pt"}
+    # same artifact names and binary containers as the reference pipeline (tools/distpartitioning/convert_partition.py)
+    import dgl_b200
+    from dgl_b200.data import dgl_binary
+    pg = dgl_b200.graph((graph_dict["src"], graph_dict["dst"]), num_nodes=graph_dict["num_nodes"])
+    for k, v in graph_dict["ndata"].items():
+        pg.ndata[k] = v
+    for k, v in graph_dict["edata"].items():
+        pg.edata[k] = v
+    dgl_binary.write_graphs(os.path.join(pdir, "graph.dgl"), [pg])
+    dgl_binary.write_tensors(os.path.join(pdir, "node_feat.dgl"), node_feats)
+    dgl_binary.write_tensors(os.path.join(pdir, "edge_feat.dgl"), edge_feats)
+    return {"node_feats": f"part{part_id}/node_feat.dgl", "edge_feats": f"part{part_id}/edge_feat.dgl",
+            "part_graph": f"part{part_id}/graph.dgl"}
 
 
 def write_metadata(out_dir, graph_name, num_nodes, num_edges, node_ranges, edge_ranges, part_files):
