@@ -59,6 +59,15 @@ def __getattr__(name):
         "linkx_homophily": ("homophily", "linkx_homophily"), "adjusted_homophily": ("homophily", "adjusted_homophily"),
         "edge_label_informativeness": ("label_informativeness", "edge_label_informativeness"),
         "node_label_informativeness": ("label_informativeness", "node_label_informativeness"),
+        "register_func": ("_native.registry", "register_func"), "get_global_func": ("_native.registry", "get_global_func"),
+        "list_global_func_names": ("_native.registry", "list_global_func_names"),
+        "extract_ext_funcs": ("_native.registry", "extract_ext_funcs"), "TypeCode": ("_native.registry", "TypeCode"),
+        "apply_each": ("utils.containers", "apply_each"), "copy_u": ("ops", "copy_u"), "copy_v": ("ops", "copy_v"),
+        "set_src_lazy_features": ("dataloading.base", "set_src_lazy_features"),
+        "set_dst_lazy_features": ("dataloading.base", "set_dst_lazy_features"),
+        "set_node_lazy_features": ("dataloading.base", "set_node_lazy_features"),
+        "set_edge_lazy_features": ("dataloading.base", "set_edge_lazy_features"),
+        "load_backend": ("backend", "load_backend"), "backend_name": ("backend", "backend_name"),
         "use_libxsmm": ("global_config", "use_libxsmm"), "is_libxsmm_enabled": ("global_config", "is_libxsmm_enabled"),
     }
     if name in _late:

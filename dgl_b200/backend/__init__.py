@@ -329,3 +329,22 @@ builtins_max = _builtins.max
 # sparse autograd ops of the backend (reference backend/pytorch/sparse.py): same entry points, our kernels
 from ..ops.sparse_autograd import edge_softmax, gsddmm, gspmm, segment_reduce  # noqa: E402,F401
 from ..nn.functional_native import gather_mm, segment_mm  # noqa: E402,F401
+
+
+# ---- names of the reference's backend loader (backend/__init__.py:51-118); PyTorch is the only backend here -----------
+from .._sparse_ops import to_dgl_nd  # noqa: E402,F401
+
+
+def from_dgl_nd(x):
+    """NDArray -> tensor; tensors are the array type of this framework, so this is the identity."""
+    return x
+
+
+def load_backend(mod_name="pytorch"):
+    if mod_name != "pytorch":
+        raise NotImplementedError(f"backend {mod_name!r}: this framework is PyTorch-only (DGLBACKEND is ignored otherwise)")
+
+
+def is_enabled(api):
+    """Whether the backend provides ``api`` (reference backend/__init__.py:is_enabled)."""
+    return api in globals() and callable(globals()[api])

@@ -31,3 +31,6 @@ def __getattr__(name):
     raise AttributeError(name)
 
 from .graphed import CapacityBlock, GraphedTrainer  # noqa: F401,E402
+
+from ..frame import LazyFeature  # noqa: F401,E402
+from ..sampling.utils import EidExcluder  # noqa: F401,E402

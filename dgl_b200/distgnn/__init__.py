@@ -109,3 +109,5 @@ def load_proteins(dataset):
         download_proteins()
         save(proteins_mtx2dgl(), dataset)
     return load_graphs(graph_file)[0][0]
+
+from . import partition, tools  # noqa: F401,E402  (reference distgnn/__init__.py)

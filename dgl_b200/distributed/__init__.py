@@ -44,7 +44,13 @@ class EdgeCollator(NodeCollator):
 
 from . import compat, rpc_api  # noqa: F401,E402
 from .compat import *  # noqa: F401,F403,E402
-from .rpc_api import Request, Response  # noqa: F401,E402
+from .rpc_api import *  # noqa: F401,F403,E402  (reference distributed/__init__.py:`from .rpc import *`)
+from .rpc_api import (client_barrier, connect_receiver, connect_receiver_finalize, copy_data_to_shared_memory,  # noqa: F401,E402
+                      create_receiver, create_sender, fast_pull, finalize_receiver, finalize_sender, finalize_server,
+                      recv_request, recv_response, recv_responses, recv_rpc_message, remote_call, remote_call_to_machine,
+                      send_request, send_request_to_machine, send_requests_to_machine, send_response, send_rpc_message,
+                      wait_for_senders)
+from .rpc import read_ip_config  # noqa: F401,E402
 
 
 _COMPAT_LAZY = ("SubgraphResponse", "FindEdgeResponse", "InDegreeResponse", "OutDegreeResponse", "SamplingRequest",
@@ -55,3 +61,11 @@ def __getattr__(name):
     if name in _COMPAT_LAZY:
         return getattr(compat, name)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
+
+# reference distributed/constants.py
+MAX_QUEUE_SIZE = 20 * 1024 * 1024 * 1024
+SERVER_EXIT = "server_exit"
+DEFAULT_NTYPE = "_N"
+DEFAULT_ETYPE = (DEFAULT_NTYPE, "_E", DEFAULT_NTYPE)
+DGL2GB_EID = "_dgl2gb_eid"
+GB_DST_ID = "_gb_dst_id"

@@ -42,3 +42,6 @@ from .compat import (FeatureKey, GBWarning, all_to_all, built_with_cuda, bytes_t
                      indptr_edge_ids, is_listlike, is_wsl, minibatcher_default, preprocess_ondisk_dataset, recursive_apply,
                      recursive_apply_reduce_all, revert_to_homo, seed, wrap_with_cached_feature)
 from .impl.negative_sampler import NegativeSampler  # noqa: F401,E402
+
+from .datapipes.utils import datapipe_graph_to_adjlist, find_dps, replace_dp, traverse_dps  # noqa: F401,E402
+from .datapipes.visualization import to_graph  # noqa: F401,E402

@@ -13,3 +13,5 @@ def __getattr__(name):
         raise AttributeError(name)
     from .. import __getattr__ as _parent_getattr
     return _parent_getattr(name)
+from ...transforms.functional import knn_graph, radius_graph, segmented_knn_graph  # noqa: F401,E402  (reference nn/pytorch/factory.py)
+from .factory import pairwise_squared_distance  # noqa: F401,E402
