@@ -20,6 +20,9 @@ __all__ = ["sample_neighbors", "sample_etype_neighbors", "sample_neighbors_fused
            "select_topk", "sample_rel"]
 
 
+_TOPK_WDTYPE = {torch.float32: 0, torch.float64: 1, torch.int64: 2}
+
+
 def _p(t):
     return 0 if t is None else t.data_ptr()
 
@@ -173,6 +176,23 @@ def sample_neighbors(g, nodes, fanout, edge_dir="in", prob=None, replace=False, 
     return ret if output_device is None else ret.to(output_device)
 
 
+def _native_pick(symbol, sig, idt, n, head, tail_after_offsets):
+    """Two-phase driver of the host row-wise pickers in csrc/cpu/rowwise_pick.cc: the count pass (offsets = NULL) sizes the
+    outputs, the fill pass writes (neighbour, seed, edge id). ``head`` are the arguments before ``offsets``,
+    ``tail_after_offsets`` those between ``offsets`` and ``counts``."""
+    lib = loader.cpu_lib()
+    fn = lib.fn(symbol, sig)
+    counts = torch.empty(n, dtype=torch.int64)
+    fn(*head, 0, *tail_after_offsets, _p(counts), 0, 0, 0)
+    offsets = torch.zeros(n + 1, dtype=torch.int64)
+    torch.cumsum(counts, 0, out=offsets[1:])
+    total = int(offsets[-1])
+    nb, sd, eid = (torch.empty(total, dtype=idt) for _ in range(3))
+    if total:
+        fn(*head, _p(offsets), *tail_after_offsets, _p(counts), _p(nb), _p(sd), _p(eid))
+    return nb, sd, eid
+
+
 def sample_etype_neighbors(g, nodes, etype_offset, fanout, edge_dir="in", prob=None, replace=False, copy_ndata=True,
                            copy_edata=True, etype_sorted=False, _dist_training=False, output_device=None):
     """Per-edge-type fan-outs on a homogenised graph whose edges are grouped by type:
@@ -185,6 +205,21 @@ def sample_etype_neighbors(g, nodes, etype_offset, fanout, edge_dir="in", prob=N
     ntype_edges = len(etype_offset) - 1
     if fan.numel() == 1:
         fan = fan.repeat(ntype_edges)
+    if g.device.type == "cpu" and nodes.device.type == "cpu":
+        # host path: one native pass buckets every row's neighbours by edge type and draws each bucket's fan-out
+        ug = g._graphs[0]
+        indptr, indices, eids_ = ug.csc() if edge_dir == "in" else ug.csr()
+        off = torch.as_tensor(etype_offset, dtype=torch.int64).contiguous()
+        fan64 = fan.to(torch.int64).contiguous()
+        p = None if prob is None else g.edata[prob].to(torch.float32).contiguous()
+        seeds = nodes.contiguous()
+        nb, sd, eid = _native_pick(
+            "dglb200_cpu_etype_pick", "ippppLpLpippLpppp".replace("L", "l"), idt, seeds.shape[0],
+            (id_code(idt), _p(indptr), _p(indices), _p(eids_), _p(seeds), seeds.shape[0], _p(off), ntype_edges, _p(fan64),
+             int(bool(replace)), _p(p)), (dgl_random.next_seed(),))
+        src, dst = (nb, sd) if edge_dir == "in" else (sd, nb)
+        ret = _build_result(g, [(src, dst, eid)], copy_ndata, copy_edata, nodes.device)
+        return ret if output_device is None else ret.to(output_device)
     srcs, dsts, eids = [], [], []
     u, v = g._graphs[0].coo()
     for t in range(ntype_edges):
@@ -227,6 +262,20 @@ def sample_neighbors_biased(g, nodes, fanout, bias, edge_dir="in", tag_offset_na
     ug = g._graphs[0]
     indptr, indices, eids = ug.csc() if edge_dir == "in" else ug.csr()
     off = (g.dstdata if edge_dir == "in" else g.srcdata)[tag_offset_name]
+    if indptr.device.type == "cpu":
+        # host path: native two-level draw over the tag ranges, no per-edge probability array is materialised
+        seeds = _to_tensor(nodes, g.idtype, g.device).contiguous()
+        off64 = off.to(torch.int64).contiguous()
+        b64 = torch.as_tensor(bias, dtype=torch.float64).contiguous()
+        if off64.shape[1] != b64.shape[0] + 1:
+            raise DGLError(f"bias has {b64.shape[0]} entries but the tag offsets describe {off64.shape[1] - 1} tags")
+        nb, sd, eid = _native_pick(
+            "dglb200_cpu_biased_pick", "ippppLpLpLipLpppp".replace("L", "l"), g.idtype, seeds.shape[0],
+            (id_code(g.idtype), _p(indptr), _p(indices), _p(eids), _p(seeds), seeds.shape[0], _p(off64), b64.shape[0],
+             _p(b64), int(fanout), int(bool(replace))), (dgl_random.next_seed(),))
+        src, dst = (nb, sd) if edge_dir == "in" else (sd, nb)
+        ret = _build_result(g, [(src, dst, eid)], copy_ndata, copy_edata, seeds.device)
+        return ret if output_device is None else ret.to(output_device)
     bias = torch.as_tensor(bias, dtype=torch.float32, device=indptr.device)
     deg = (indptr[1:] - indptr[:-1]).long()
     rows = torch.repeat_interleave(torch.arange(indptr.shape[0] - 1, device=indptr.device), deg)
@@ -262,6 +311,23 @@ def select_topk(g, k, weight, nodes=None, edge_dir="in", ascending=False, copy_n
             continue
         seeds = _to_tensor(nodes[seed_type], g.idtype, g.device)
         indptr, indices, eids = ug.csc() if edge_dir == "in" else ug.csr()
+        wt = g._edge_frames[i][weight]
+        if indptr.device.type == "cpu" and wt.dim() == 1 and wt.dtype in _TOPK_WDTYPE:
+            # host path: per-row partial sort in native code (csrc/cpu/rowwise_pick.cc), stable on ties
+            seeds = seeds.contiguous()
+            deg = indptr[seeds.long() + 1].long() - indptr[seeds.long()].long()
+            cnt = deg if kd[c] < 0 else deg.clamp(max=int(kd[c]))
+            offsets = torch.zeros(seeds.shape[0] + 1, dtype=torch.int64)
+            torch.cumsum(cnt, 0, out=offsets[1:])
+            total = int(offsets[-1])
+            nb, sd, ee = (torch.empty(total, dtype=g.idtype) for _ in range(3))
+            if total:
+                wt = wt.contiguous()
+                loader.cpu_lib().fn("dglb200_cpu_topk_pick", "iipppplplipppp")(
+                    id_code(g.idtype), _TOPK_WDTYPE[wt.dtype], _p(indptr), _p(indices), _p(eids), _p(seeds), seeds.shape[0],
+                    _p(wt), int(kd[c]), int(bool(ascending)), _p(offsets), _p(nb), _p(sd), _p(ee))
+            per_etype.append((nb, sd, ee) if edge_dir == "in" else (sd, nb, ee))
+            continue
         s = indptr[seeds.long()].long()
         cnt = indptr[seeds.long() + 1].long() - s
         pos = torch.repeat_interleave(s, cnt) + (torch.arange(int(cnt.sum()), device=s.device)
