@@ -51,6 +51,8 @@ from .rpc_api import (client_barrier, connect_receiver, connect_receiver_finaliz
                       send_request, send_request_to_machine, send_requests_to_machine, send_response, send_rpc_message,
                       wait_for_senders)
 from .rpc import read_ip_config  # noqa: F401,E402
+# the context-aware variants stay the package-level names (the RPC-state accessors remain reachable as rpc_api.*)
+from .dist_graph import get_num_client, get_rank  # noqa: F401,E402
 
 
 _COMPAT_LAZY = ("SubgraphResponse", "FindEdgeResponse", "InDegreeResponse", "OutDegreeResponse", "SamplingRequest",

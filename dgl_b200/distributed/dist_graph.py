@@ -595,7 +595,7 @@ def node_split(nodes, partition_book=None, ntype="_N", rank=None, force_even=Tru
     (reference dist_graph.py:node_split)."""
     import torch.distributed as dist
     nodes = torch.as_tensor(nodes)
-    if nodes.dtype == torch.bool:
+    if nodes.dtype in (torch.bool, torch.uint8):  # masks read back from partition files are uint8, as in the reference
         nodes = torch.nonzero(nodes).squeeze(1)
     if num_trainers is None:
         num_trainers = dist.get_world_size() if dist.is_initialized() else 1
@@ -611,7 +611,7 @@ def node_split(nodes, partition_book=None, ntype="_N", rank=None, force_even=Tru
 def edge_split(edges, partition_book=None, etype="_E", rank=None, force_even=True, num_trainers=None, **kw):
     import torch.distributed as dist
     edges = torch.as_tensor(edges)
-    if edges.dtype == torch.bool:
+    if edges.dtype in (torch.bool, torch.uint8):
         edges = torch.nonzero(edges).squeeze(1)
     if num_trainers is None:
         num_trainers = dist.get_world_size() if dist.is_initialized() else 1

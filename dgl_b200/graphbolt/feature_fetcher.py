@@ -1,12 +1,53 @@
 """``FeatureFetcher``: reads the node features of ``input_nodes`` and the edge features of every sampled layer from a
 feature store (device tables, pinned host tables through UVA, GPU / CPU caches, disk).
 
-Parity: /root/reference/python/dgl/graphbolt/feature_fetcher.py:40-190."""
+Parity: /root/reference/python/dgl/graphbolt/feature_fetcher.py:40-190. With ``overlap_fetch=True`` (the default, as in
+the reference) every read goes through the features' staged ``read_async`` generators and the fetcher keeps a software
+pipeline of mini-batches in flight: each step advances every in-flight mini-batch by one stage (cache lookup -> disk /
+host gather -> H2D copy ...), so batch *k*'s copy overlaps batch *k+1*'s disk read and batch *k+2*'s cache lookup. The
+stages run on the shared I/O pool and the copy stream of ``graphbolt/internal/futures.py``; the mini-batch handed
+downstream only carries an ordering of the consumer's CUDA stream after the copies, never a host stall."""
 from __future__ import annotations
+
+from collections import deque
 
 from .minibatch_transformer import MiniBatchTransformer
 
 __all__ = ["FeatureFetcher"]
+
+
+class _Pending:
+    """One mini-batch whose reads are in flight: a list of (slot, generator, remaining stages, last future)."""
+
+    __slots__ = ("data", "reads", "edge_slots")
+
+    def __init__(self, data):
+        self.data, self.reads, self.edge_slots = data, [], 0
+
+    def add(self, slot, feature, ids):
+        self.reads.append([slot, feature.read_async(ids), feature.read_async_num_stages(ids.device), None])
+
+    @property
+    def stages_left(self):
+        return max((r[2] for r in self.reads), default=0)
+
+    def advance(self):
+        for r in self.reads:
+            if r[2] > 0:
+                r[3] = next(r[1])
+                r[2] -= 1
+
+    def finish(self):
+        node_features, edge_features = {}, [dict() for _ in range(self.edge_slots)]
+        for (kind, layer, key), _gen, _left, fut in self.reads:
+            value = fut.wait()
+            if kind == "node":
+                node_features[key] = value
+            else:
+                edge_features[layer][key] = value
+        self.data.set_node_features(node_features)
+        self.data.set_edge_features(edge_features)
+        return self.data
 
 
 class FeatureFetcher(MiniBatchTransformer):
@@ -18,9 +59,12 @@ class FeatureFetcher(MiniBatchTransformer):
         self.feature_store = feature_store
         self.node_feature_keys = node_feature_keys
         self.edge_feature_keys = edge_feature_keys
+        self.overlap_fetch = bool(overlap_fetch)
+        self.cooperative = bool(cooperative)
 
-    def _read(self, data):
-        node_features, edge_features = {}, []
+    # ---- what to read -------------------------------------------------------------------------------------------
+    def _requests(self, data):
+        """Yield (slot, feature-store key, ids) for every tensor this mini-batch needs; slot = (kind, layer, name)."""
         input_nodes = data.input_nodes
         if self.node_feature_keys and input_nodes is not None:
             if isinstance(self.node_feature_keys, dict):
@@ -29,29 +73,67 @@ class FeatureFetcher(MiniBatchTransformer):
                     if nodes is None:
                         continue
                     for name in names:
-                        node_features[(type_name, name)] = self.feature_store.read("node", type_name, name, nodes)
+                        yield ("node", 0, (type_name, name)), ("node", type_name, name), nodes
             else:
                 for name in self.node_feature_keys:
-                    node_features[name] = self.feature_store.read("node", None, name, input_nodes)
+                    yield ("node", 0, name), ("node", None, name), input_nodes
         if self.edge_feature_keys and data.sampled_subgraphs:
-            for sg in data.sampled_subgraphs:
-                ef = {}
+            for layer, sg in enumerate(data.sampled_subgraphs):
                 eids = sg.original_edge_ids
-                if eids is not None:
-                    if isinstance(self.edge_feature_keys, dict):
-                        for type_name, names in self.edge_feature_keys.items():
-                            e = eids.get(type_name) if isinstance(eids, dict) else eids
-                            if e is None:
-                                continue
-                            for name in names:
-                                ef[(type_name, name)] = self.feature_store.read("edge", type_name, name, e)
-                    else:
-                        for name in self.edge_feature_keys:
-                            ef[name] = self.feature_store.read("edge", None, name, eids)
-                edge_features.append(ef)
+                if eids is None:
+                    continue
+                if isinstance(self.edge_feature_keys, dict):
+                    for type_name, names in self.edge_feature_keys.items():
+                        e = eids.get(type_name) if isinstance(eids, dict) else eids
+                        if e is None:
+                            continue
+                        for name in names:
+                            yield ("edge", layer, (type_name, name)), ("edge", type_name, name), e
+                else:
+                    for name in self.edge_feature_keys:
+                        yield ("edge", layer, name), ("edge", None, name), eids
+
+    def _edge_slots(self, data):
+        return len(data.sampled_subgraphs) if self.edge_feature_keys and data.sampled_subgraphs else 0
+
+    # ---- synchronous path ---------------------------------------------------------------------------------------
+    def _read(self, data):
+        node_features, edge_features = {}, [dict() for _ in range(self._edge_slots(data))]
+        for (kind, layer, key), store_key, ids in self._requests(data):
+            value = self.feature_store.read(*store_key, ids)
+            if kind == "node":
+                node_features[key] = value
+            else:
+                edge_features[layer][key] = value
         data.set_node_features(node_features)
         data.set_edge_features(edge_features)
         return data
+
+    # ---- overlapped path ----------------------------------------------------------------------------------------
+    def _start(self, data):
+        pending = _Pending(data)
+        pending.edge_slots = self._edge_slots(data)
+        for slot, store_key, ids in self._requests(data):
+            pending.add(slot, self.feature_store[store_key], ids)
+        return pending
+
+    def __iter__(self):
+        if not self.overlap_fetch:
+            yield from super().__iter__()
+            return
+        inflight = deque()
+        for data in self.datapipe:
+            inflight.append(self._start(data))
+            # one step of the pipeline: every mini-batch in flight moves one stage forward
+            for p in inflight:
+                p.advance()
+            while inflight and inflight[0].stages_left == 0:
+                yield inflight.popleft().finish()
+        while inflight:
+            for p in inflight:
+                p.advance()
+            while inflight and inflight[0].stages_left == 0:
+                yield inflight.popleft().finish()
 
 
 def __getattr__(name):

@@ -5,6 +5,7 @@ from __future__ import annotations
 
 import ctypes
 import os
+import threading
 
 import numpy as np
 import torch
@@ -12,7 +13,15 @@ import torch
 from ..._native import loader
 from ...base import DGLError
 from ..base import index_select
+from ..internal import futures as _fut
 from .caches import FeatureCache, GPUCache
+
+
+def _drain(feature, ids):
+    """Run a nested ``read_async`` to completion stage by stage, yielding each stage's future to the caller."""
+    gen = feature.read_async(ids)
+    for _ in range(feature.read_async_num_stages(ids.device)):
+        yield next(gen)
 
 
 class Feature:
@@ -20,11 +29,13 @@ class Feature:
         raise NotImplementedError
 
     def read_async_num_stages(self, ids_device=None):
-        """Number of stages the ``read_async`` generator yields before the result (reference feature_store.py)."""
+        """How many futures the ``read_async`` generator yields; the last one's ``wait()`` is the result
+        (reference feature_store.py:60-120). Call ``next()`` that many times, interleaving other work between calls."""
         return 1
 
     def read_async(self, ids):
-        yield self.read(ids)
+        """Staged asynchronous read; the default is one stage running ``read`` on the I/O pool."""
+        yield _fut.launch(self.read, ids)
 
     def size(self):
         raise NotImplementedError
@@ -52,6 +63,35 @@ class TorchBasedFeature(Feature):
         if ids is None:
             return self._tensor
         return index_select(self._tensor, ids)
+
+    def _host_table_device_ids(self, ids_device):
+        return (ids_device is not None and torch.device(ids_device).type == "cuda" and not self._tensor.is_cuda
+                and not self._tensor.is_pinned())
+
+    def read_async_num_stages(self, ids_device=None):
+        # pageable host table read with device ids: host gather into pinned memory, then the H2D copy
+        return 2 if self._host_table_device_ids(ids_device) else 1
+
+    def read_async(self, ids):
+        if ids is None:
+            yield _fut.completed(self._tensor)
+        elif self._host_table_device_ids(ids.device):
+            dev = ids.device
+
+            def gather():
+                idx = ids.cpu()
+                out = torch.empty((idx.shape[0],) + tuple(self._tensor.shape[1:]), dtype=self._tensor.dtype).pin_memory()
+                torch.index_select(self._tensor, 0, idx, out=out)
+                return out
+
+            host = _fut.launch(gather)
+            yield host
+            yield _fut.on_side_stream(lambda: host.wait().to(dev, non_blocking=True), device=dev)
+        elif ids.is_cuda:
+            # device table or pinned table (UVA gather kernel): enqueue on the copy stream
+            yield _fut.on_side_stream(self.read, ids, device=ids.device)
+        else:
+            yield _fut.launch(self.read, ids)
 
     def size(self):
         return self._tensor.size()[1:]
@@ -136,13 +176,31 @@ class DiskBasedFeature(Feature):
         except Exception:  # noqa: BLE001
             pass
 
+    def read_async_num_stages(self, ids_device=None):
+        return 2 if ids_device is not None and torch.device(ids_device).type == "cuda" else 1
+
+    def read_async(self, ids):
+        """Stage 1: the io_uring / pread row fetch on the I/O pool (into pinned memory when the ids are on a GPU);
+        stage 2 (GPU ids only): the H2D copy on the copy stream."""
+        if ids is None or not ids.is_cuda:
+            yield _fut.launch(self.read, ids)
+            return
+        dev = ids.device
+        host = _fut.launch(self._read_host, ids, True)
+        yield host
+        yield _fut.on_side_stream(lambda: host.wait().to(dev, non_blocking=True), device=dev)
+
     def read(self, ids=None):
         if ids is None:
             return torch.from_numpy(np.load(self._path))
         dev = ids.device
+        out = self._read_host(ids, dev.type == "cuda")
+        return out.to(dev, non_blocking=True) if dev.type == "cuda" else out
+
+    def _read_host(self, ids, pinned):
         idx = ids.to(torch.int64).cpu().contiguous()
         out = torch.empty((idx.shape[0],) + self._shape[1:], dtype=self._dtype)
-        if dev.type == "cuda":
+        if pinned:
             out = out.pin_memory()
         if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self._shape[0]):
             raise DGLError(f"row index out of range for a feature with {self._shape[0]} rows")
@@ -152,7 +210,7 @@ class DiskBasedFeature(Feature):
         else:
             self._lib.fn("dglb200_disk_read_rows", "lllplpi")(self._fd, self._offset, self._row_bytes, idx.data_ptr(),
                                                               idx.shape[0], out.data_ptr(), self._threads)
-        return out.to(dev, non_blocking=True) if dev.type == "cuda" else out
+        return out
 
     def to(self, device):
         """Disk-backed features stay on disk; only an explicit "cpu"/"pinned" target is accepted (reference
@@ -200,6 +258,7 @@ class CPUCachedFeature(Feature):
         cache_rows = max(1, max_cache_size_in_bytes // max(row_bytes, 1))
         self._feature = FeatureCache((cache_rows,) + tuple(feat0.shape[1:]), feat0.dtype, policy or "sieve",
                                      pin_memory=pin_memory)
+        self._mutex = threading.Lock()  # lookups and insertions of overlapping mini-batches are serialised
         self._cache_bytes = cache_rows * row_bytes
 
     @property
@@ -210,14 +269,57 @@ class CPUCachedFeature(Feature):
         if ids is None:
             return self._fallback_feature.read()
         dev = ids.device
-        values, hit_idx, miss_idx, miss_keys = self._feature.query(ids)
+        with self._mutex:
+            values, hit_idx, miss_idx, miss_keys = self._feature.query(ids)
         out = torch.empty((ids.shape[0],) + tuple(values.shape[1:]), dtype=values.dtype)
         out[hit_idx] = values
         if miss_keys.numel():
             missing = self._fallback_feature.read(miss_keys).cpu()
             out[miss_idx] = missing
-            self._feature.replace(miss_keys, missing)
+            with self._mutex:
+                self._feature.replace(miss_keys, missing)
         return out.to(dev)
+
+    def read_async_num_stages(self, ids_device=None):
+        # cache lookup, the fallback's own stages for the missing rows (host ids), combine + insert (+ H2D)
+        return 2 + self._fallback_feature.read_async_num_stages(torch.device("cpu"))
+
+    def read_async(self, ids):
+        if ids is None:
+            for _ in range(self.read_async_num_stages() - 1):
+                yield _fut.completed(None)
+            yield _fut.launch(self._fallback_feature.read)
+            return
+        dev = ids.device
+
+        def lookup():
+            with self._mutex:
+                return self._feature.query(ids)
+
+        looked = _fut.launch(lookup)
+        yield looked
+        values, hit_idx, miss_idx, miss_keys = looked.wait()
+        last = None
+        for last in _drain(self._fallback_feature, miss_keys.cpu()):
+            yield last
+
+        def combine():
+            out = torch.empty((ids.shape[0],) + tuple(values.shape[1:]), dtype=values.dtype)
+            if dev.type == "cuda":
+                out = out.pin_memory()
+            out[hit_idx] = values
+            if miss_keys.numel():
+                missing = last.wait().cpu()
+                out[miss_idx] = missing
+                with self._mutex:
+                    self._feature.replace(miss_keys, missing)
+            return out
+
+        host = _fut.launch(combine)
+        if dev.type == "cuda":
+            yield _fut.then(host, lambda t: t.to(dev, non_blocking=True))
+        else:
+            yield host
 
     def size(self):
         return self._fallback_feature.size()
@@ -270,6 +372,39 @@ class GPUCachedFeature(Feature):
             values[missing_index] = missing_values
             self._feature.replace(missing_keys, missing_values)
         return values
+
+    def _fallback_ids(self, missing_keys):
+        fb = self._fallback_feature
+        direct = (isinstance(fb, TorchBasedFeature) and (fb.is_pinned() or fb._tensor.is_cuda))
+        return missing_keys if direct else missing_keys.cpu()
+
+    def read_async_num_stages(self, ids_device=None):
+        # device cache lookup, the fallback's stages for the missing rows, scatter + insert
+        fb = self._fallback_feature
+        direct = isinstance(fb, TorchBasedFeature) and (fb.is_pinned() or fb._tensor.is_cuda)
+        return 2 + fb.read_async_num_stages(ids_device if direct else torch.device("cpu"))
+
+    def read_async(self, ids):
+        if ids is None:
+            for _ in range(self.read_async_num_stages() - 1):
+                yield _fut.completed(None)
+            yield _fut.launch(self._fallback_feature.read)
+            return
+        looked = _fut.on_side_stream(self._feature.query, ids, device=ids.device, key="cache")
+        yield looked
+        values, missing_index, missing_keys = looked.wait()
+        last = None
+        for last in _drain(self._fallback_feature, self._fallback_ids(missing_keys)):
+            yield last
+
+        def fill():
+            if missing_keys.numel():
+                missing_values = last.wait().to(values.device, non_blocking=True)
+                values[missing_index] = missing_values
+                self._feature.replace(missing_keys, missing_values)
+            return values
+
+        yield _fut.on_side_stream(fill, device=ids.device, key="cache")
 
     def size(self):
         return self._fallback_feature.size()

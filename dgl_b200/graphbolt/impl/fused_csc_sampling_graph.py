@@ -16,6 +16,25 @@ from ..base import CSCFormatBase, ORIGINAL_EDGE_ID, etype_str_to_tuple, etype_tu
 from ..minibatch import SampledSubgraphImpl
 
 
+def _asyncable(method):
+    """``async_op=True`` turns a sampling entry point into a future (reference: the ``*Async`` bindings of
+    graphbolt/src/python_binding.cc and ``async_op`` of fused_csc_sampling_graph.py:640-760): device seeds run on the
+    sampling side stream - the returned future orders the caller's stream after it - and host seeds on the I/O pool."""
+    import functools
+
+    @functools.wraps(method)
+    def wrapper(self, seeds, *args, async_op=False, **kwargs):
+        if not async_op:
+            return method(self, seeds, *args, **kwargs)
+        from ..internal import futures
+        first = next(iter(seeds.values())) if isinstance(seeds, dict) else seeds
+        if torch.is_tensor(first) and first.is_cuda:
+            return futures.on_side_stream(method, self, seeds, *args, key="sample", device=first.device, **kwargs)
+        return futures.launch(method, self, seeds, *args, **kwargs)
+
+    return wrapper
+
+
 class FusedCSCSamplingGraph:
     def __init__(self, csc_indptr, indices, node_type_offset=None, type_per_edge=None, node_type_to_id=None,
                  edge_type_to_id=None, node_attributes=None, edge_attributes=None):
@@ -111,7 +130,8 @@ class FusedCSCSamplingGraph:
             oes[et] = oe
         return SampledSubgraphImpl(sampled_csc=csc, original_edge_ids=oes)
 
-    def sample_neighbors(self, seeds, fanouts, replace=False, probs_name=None, returning_indices_and_original_edge_ids_are_optional=False, async_op=False, overlap_graph_fetch=False):
+    @_asyncable
+    def sample_neighbors(self, seeds, fanouts, replace=False, probs_name=None, returning_indices_and_original_edge_ids_are_optional=False, overlap_graph_fetch=False):
         """Sample in-neighbours of ``seeds`` (tensor, or dict ntype -> tensor for hetero graphs)."""
         fan = torch.as_tensor(fanouts).reshape(-1).tolist()
         prob = self.edge_attributes[probs_name] if probs_name else None
@@ -137,6 +157,7 @@ class FusedCSCSamplingGraph:
             results[et] = (src, cnt, eid_map.to(eid.device)[eid.long()])
         return self._convert(seeds, results)
 
+    @_asyncable
     def sample_layer_neighbors(self, seeds, fanouts, replace=False, probs_name=None, random_seed=None,
                                seed2_contribution=0.0, **kwargs):
         """LABOR layer sampling (shared per-vertex variates)."""
@@ -204,6 +225,7 @@ class FusedCSCSamplingGraph:
                                           edge_ts, probs, self.type_per_edge == tid, layer_seed)
         return self._convert(seeds, results)
 
+    @_asyncable
     def temporal_sample_neighbors(self, seeds, seeds_timestamp, fanouts, replace=False, seeds_pre_time_window=None,
                                   probs_name=None, node_timestamp_attr_name=None, edge_timestamp_attr_name=None):
         """Neighbour sampling restricted to sources / edges strictly older than the seed's timestamp (and not older than
@@ -212,6 +234,7 @@ class FusedCSCSamplingGraph:
         return self._temporal(seeds, seeds_timestamp, fanouts, replace, seeds_pre_time_window, probs_name,
                               node_timestamp_attr_name, edge_timestamp_attr_name)
 
+    @_asyncable
     def temporal_sample_layer_neighbors(self, seeds, seeds_timestamp, fanouts, replace=False, seeds_pre_time_window=None,
                                         probs_name=None, node_timestamp_attr_name=None, edge_timestamp_attr_name=None,
                                         random_seed=None, seed2_contribution=0.0):
@@ -252,6 +275,7 @@ class FusedCSCSamplingGraph:
             self.edge_attributes = {}
         self.edge_attributes[name] = tensor
 
+    @_asyncable
     def in_subgraph(self, nodes):
         """All in-edges of ``nodes`` as a SampledSubgraph (fanout = -1)."""
         return self.sample_neighbors(nodes, [-1])
