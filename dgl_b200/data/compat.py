@@ -252,7 +252,11 @@ class StorageMetaData:
 
     @staticmethod
     def load(filename):
-        d = torch.load(filename, weights_only=False)
+        if dgl_binary.is_dgl_binary(filename):
+            c = dgl_binary._Cursor(filename)
+            num_graph, _ = c.header()
+            return StorageMetaData(2, num_graph, dict(c.named_tensors()))
+        d = torch.load(filename, weights_only=True)
         return StorageMetaData(d.get("version"), len(d.get("graphs", [])), d.get("labels", {}))
 
 

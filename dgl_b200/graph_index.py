@@ -37,6 +37,10 @@ def coo_to_csr(row, col, num_rows, idtype):
         # (csrc/cuda/structure_build.cu) - no torch.sort, one pass over the edge list per radix digit
         from .ops.cuda_struct import cuda_coo_to_csr
         return cuda_coo_to_csr(row.contiguous(), col, num_rows)
+    elif not row.is_cuda and row.dtype == idtype and col.dtype == idtype:
+        # host build: native stable counting sort (csrc/cpu/spmat.cc), O(E) instead of a comparison sort
+        from .ops.cpu_struct import coo_to_csr as _native_coo_to_csr
+        return _native_coo_to_csr(row, col, num_rows)
     else:
         perm = _stable_argsort(row)
         srow, scol = row[perm], col[perm]

@@ -32,14 +32,102 @@ def sort_rows(indptr, indices, perm=None):
 
 
 def transpose(indptr, indices, n_cols):
-    """CSR -> CSR of the transpose. Rows of the result are column-sorted because CSR order is row-ascending and the
-    sort is stable. Returns (t_indptr, t_indices, perm) with ``perm`` = position in the input of every output nnz."""
-    n_rows = indptr.shape[0] - 1
-    order = torch.sort(indices, stable=True).indices
-    rows = torch.repeat_interleave(torch.arange(n_rows, dtype=indptr.dtype), (indptr[1:] - indptr[:-1]).long())
-    t_indptr = torch.zeros(n_cols + 1, dtype=indptr.dtype)
-    t_indptr[1:] = torch.cumsum(torch.bincount(indices.long(), minlength=n_cols), 0)
-    return t_indptr, rows[order].contiguous(), order
+    """CSR -> CSR of the transpose (native stable counting sort, csrc/cpu/spmat.cc). Rows of the result are
+    column-sorted because CSR order is row-ascending and the sort is stable. Returns (t_indptr, t_indices, perm) with
+    ``perm`` = position in the input of every output nnz."""
+    t_indptr, t_indices, perm = csr_transpose(indptr, indices, None, n_cols)
+    return t_indptr, t_indices, perm.long()
+
+
+def coo_to_csr(row, col, n_rows):
+    """(indptr, indices, eids) of a host COO, rows in ascending order, edge order kept inside a row."""
+    idt = row.dtype
+    row, col = row.contiguous(), col.contiguous()
+    E = row.shape[0]
+    indptr = torch.empty(n_rows + 1, dtype=idt)
+    indices = torch.empty(E, dtype=idt)
+    eids = torch.empty(E, dtype=idt)
+    loader.cpu_lib().fn("dglb200_cpu_coo_to_csr", "ippllppp")(
+        id_code(idt), _p(row), _p(col), E, int(n_rows), _p(indptr), _p(indices), _p(eids))
+    return indptr, indices, eids
+
+
+def csr_transpose(indptr, indices, data, n_cols):
+    """CSR(+edge ids) -> (t_indptr, t_indices, t_data) of the transposed matrix; ``data=None`` means positions."""
+    idt = indptr.dtype
+    indptr, indices = indptr.contiguous(), indices.contiguous()
+    data = None if data is None else data.contiguous()
+    E = indices.shape[0]
+    t_indptr = torch.empty(n_cols + 1, dtype=idt)
+    t_indices = torch.empty(E, dtype=idt)
+    t_data = torch.empty(E, dtype=idt)
+    loader.cpu_lib().fn("dglb200_cpu_csr_transpose", "ippplLppp".replace("L", "l"))(
+        id_code(idt), _p(indptr), _p(indices), _p(data), indptr.shape[0] - 1, int(n_cols), _p(t_indptr), _p(t_indices),
+        _p(t_data))
+    return t_indptr, t_indices, t_data
+
+
+def coalesce(row, col, n_rows, n_cols):
+    """Distinct (row, col) pairs of a host COO in lexicographic order: (out_row, out_col, group, count, first) where
+    ``group[e]`` is the pair id of edge ``e``, ``count`` the multiplicities and ``first`` the smallest member edge id."""
+    idt = row.dtype
+    row, col = row.contiguous(), col.contiguous()
+    E = row.shape[0]
+    group = torch.empty(E, dtype=torch.int64)
+    out_row, out_col = torch.empty(E, dtype=idt), torch.empty(E, dtype=idt)
+    count, first = torch.empty(E, dtype=torch.int64), torch.empty(E, dtype=torch.int64)
+    n_out = torch.zeros(1, dtype=torch.int64)
+    loader.cpu_lib().fn("dglb200_cpu_coalesce", "ipplllpppppp")(
+        id_code(idt), _p(row), _p(col), E, int(n_rows), int(n_cols), _p(group), _p(out_row), _p(out_col), _p(count),
+        _p(first), _p(n_out))
+    n = int(n_out)
+    return out_row[:n], out_col[:n], group, count[:n], first[:n]
+
+
+def slice_rows(indptr, indices, data, rows):
+    """Rows ``rows`` of a CSR: (sub_indptr, sub_indices, sub_data); ``sub_data`` holds edge ids (positions if ``data`` is None)."""
+    idt = indptr.dtype
+    rows = rows.to(idt).contiguous()
+    nr = rows.shape[0]
+    fn = loader.cpu_lib().fn("dglb200_cpu_csr_slice_rows", "ippppLppp".replace("L", "l"))
+    sub_indptr = torch.empty(nr + 1, dtype=idt)
+    fn(id_code(idt), _p(indptr), _p(indices), _p(data), _p(rows), nr, _p(sub_indptr), 0, 0)
+    nnz = int(sub_indptr[-1])
+    sub_indices, sub_data = torch.empty(nnz, dtype=idt), torch.empty(nnz, dtype=idt)
+    if nnz:
+        fn(id_code(idt), _p(indptr), _p(indices), _p(data), _p(rows), nr, _p(sub_indptr), _p(sub_indices), _p(sub_data))
+    return sub_indptr, sub_indices, sub_data
+
+
+def slice_matrix(indptr, indices, data, rows, col_map):
+    """Sub-matrix rows x {c : col_map[c] >= 0} with columns relabelled by ``col_map``."""
+    idt = indptr.dtype
+    rows, col_map = rows.to(idt).contiguous(), col_map.to(idt).contiguous()
+    nr = rows.shape[0]
+    fn = loader.cpu_lib().fn("dglb200_cpu_csr_slice_matrix", "ippppLpppp".replace("L", "l"))
+    sub_indptr = torch.empty(nr + 1, dtype=idt)
+    fn(id_code(idt), _p(indptr), _p(indices), _p(data), _p(rows), nr, _p(col_map), _p(sub_indptr), 0, 0)
+    nnz = int(sub_indptr[-1])
+    sub_indices, sub_data = torch.empty(nnz, dtype=idt), torch.empty(nnz, dtype=idt)
+    if nnz:
+        fn(id_code(idt), _p(indptr), _p(indices), _p(data), _p(rows), nr, _p(col_map), _p(sub_indptr), _p(sub_indices),
+           _p(sub_data))
+    return sub_indptr, sub_indices, sub_data
+
+
+def line_graph(u, v, indptr, csr_eids, backtracking=True):
+    """Edge list (i, j) of the line graph, grouped by i in edge-id order (csrc/cpu/spmat.cc)."""
+    idt = u.dtype
+    u, v = u.contiguous(), v.contiguous()
+    E = u.shape[0]
+    fn = loader.cpu_lib().fn("dglb200_cpu_line_graph", "ipplppippp")
+    lg_indptr = torch.empty(E + 1, dtype=idt)
+    fn(id_code(idt), _p(u), _p(v), E, _p(indptr), _p(csr_eids), int(bool(backtracking)), _p(lg_indptr), 0, 0)
+    n = int(lg_indptr[-1])
+    src, dst = torch.empty(n, dtype=idt), torch.empty(n, dtype=idt)
+    if n:
+        fn(id_code(idt), _p(u), _p(v), E, _p(indptr), _p(csr_eids), int(bool(backtracking)), _p(lg_indptr), _p(src), _p(dst))
+    return src, dst
 
 
 def csr_mm(ap, ai, av, bp, bi, bv, n_cols):

@@ -165,6 +165,15 @@ def to_simple(g, return_counts="count", writeback_mapping=False, copy_ndata=True
     graphs, counts, maps, firsts = [], [], [], []
     for i, ug in enumerate(g._graphs):
         row, col = ug.coo()
+        if not row.is_cuda:
+            # host: native two-pass counting sort on (row, col) with group ids, multiplicities and first members
+            from ..ops import cpu_struct
+            r, c, inverse, cnt, first = cpu_struct.coalesce(row, col, ug.num_src, ug.num_dst)
+            graphs.append(UnitGraph.from_coo(ug.num_src, ug.num_dst, r, c))
+            counts.append(cnt)
+            maps.append(inverse.to(g.idtype))
+            firsts.append(first)
+            continue
         nd = max(ug.num_dst, 1)
         key = row.long() * nd + col.long()
         uniq, inverse, cnt = torch.unique(key, return_inverse=True, return_counts=True)
@@ -403,6 +412,13 @@ def line_graph(g, backtracking=True, shared=False):
     u, v = g.all_edges()
     E = u.shape[0]
     indptr, _, eids = g._graphs[0].csr()
+    if not u.is_cuda:
+        from ..ops import cpu_struct
+        li, lj = cpu_struct.line_graph(u.to(g.idtype), v.to(g.idtype), indptr, eids, backtracking)
+        lg = make_graph((li, lj), num_nodes=E, idtype=g.idtype, device=g.device)
+        if shared:
+            lg._node_frames = [g._edge_frames[0].clone()]
+        return lg
     # for each edge i (u_i -> v_i) connect to all out-edges j of v_i
     s = indptr[v.long()].long()
     cnt = indptr[v.long() + 1].long() - s
