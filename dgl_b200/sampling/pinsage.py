@@ -1,5 +1,7 @@
 """PinSAGE-style random-walk neighbor samplers (parity: /root/reference/python/dgl/sampling/pinsage.py;
-visit counting replaces src/graph/sampling/randomwalks/frequency_hashmap.cu with a sort + run-length pass)."""
+visit counting: on the GPU one CTA per seed counts in a shared-memory hash table and extracts the top-k in place
+(csrc/cuda/visit_count.cu, counterpart of src/graph/sampling/randomwalks/frequency_hashmap.cu); on the host a sort +
+run-length pass)."""
 from __future__ import annotations
 
 import torch
@@ -44,6 +46,10 @@ class RandomWalkNeighborSampler:
         rep = seed_nodes.repeat_interleave(self.num_random_walks)
         paths, _ = random_walk(G, rep, metapath=self.full_metapath, restart_prob=self.restart_prob.to(G.device))
         ends = paths[:, self.metapath_hops:: self.metapath_hops]
+        n = G.num_nodes(self.ntype)
+        M = self.num_random_walks * ends.shape[1]
+        if ends.is_cuda and 0 < M <= 8192 and n < (1 << 40):
+            return self._device_topk(seed_nodes, ends.reshape(seed_nodes.shape[0], M).contiguous(), n)
         src = ends.reshape(-1)
         dst = rep.unsqueeze(1).expand_as(ends).reshape(-1)
         ok = src >= 0
@@ -61,6 +67,25 @@ class RandomWalkNeighborSampler:
         keep = order[rank < self.num_neighbors]
         g = make_graph((s[keep].to(G.idtype), d[keep].to(G.idtype)), num_nodes=n, idtype=G.idtype, device=G.device)
         g.edata[self.weight_column] = cnt[keep]
+        return g
+
+
+    def _device_topk(self, seed_nodes, visits, n):
+        """Top ``num_neighbors`` visited nodes per seed, counted and selected inside one kernel."""
+        from .._native import loader
+        from ..base import id_code
+        G = self.G
+        S, M = visits.shape
+        K = int(self.num_neighbors)
+        out_node = torch.empty((S, K), dtype=visits.dtype, device=visits.device)
+        out_cnt = torch.empty((S, K), dtype=torch.int32, device=visits.device)
+        loader.cuda_lib().fn("dglb200_cuda_visit_topk", "ipliippp")(
+            id_code(visits.dtype), visits.data_ptr(), S, M, K, out_node.data_ptr(), out_cnt.data_ptr(), loader.stream_ptr())
+        keep = out_cnt.reshape(-1) > 0
+        src = out_node.reshape(-1)[keep]
+        dst = seed_nodes.unsqueeze(1).expand(S, K).reshape(-1)[keep]
+        g = make_graph((src.to(G.idtype), dst.to(G.idtype)), num_nodes=n, idtype=G.idtype, device=G.device)
+        g.edata[self.weight_column] = out_cnt.reshape(-1)[keep].long()
         return g
 
 
