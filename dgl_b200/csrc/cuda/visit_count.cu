@@ -5,8 +5,9 @@
 // (node, seed) pairs, a device-wide radix sort of the counts per seed and a compaction pass.
 // Design for sm_100a: a seed's visits are few (walks x traversals, typically 10^2..10^3), so the whole problem of one
 // seed fits in shared memory. One CTA per seed builds an open-addressing table in shared memory with shared-memory
-// atomics, then extracts the top K with K block-wide arg-max rounds over the table (a 64-bit packed key per slot and
-// one shared atomicMax per thread and round). Global traffic is exactly one read of the visit row and one write of K
+// atomics, folds (count, id) of every slot into one 64-bit word in place and extracts the top K with K block-wide
+// arg-max rounds over those words (one 8-byte shared load per slot, one shared atomicMax per thread and two barriers per
+// round; the winner's owner clears its slot). Global traffic is exactly one read of the visit row and one write of K
 // results per seed; there is no device-wide sort, no scratch allocation and no host synchronisation, so the call is
 // CUDA-graph capturable.
 #include "common.cuh"
@@ -21,7 +22,7 @@ __global__ void __launch_bounds__(128) visit_topk_kernel(const I* __restrict__ v
   extern __shared__ __align__(16) unsigned char smem_raw[];
   long long* keys = reinterpret_cast<long long*>(smem_raw);
   int* cnts = reinterpret_cast<int*>(keys + H);
-  __shared__ unsigned long long best;
+  __shared__ unsigned long long best[2];  // double-buffered by round parity: two barriers per round suffice
   const unsigned mask = (unsigned)H - 1u;
   for (int64_t seed = blockIdx.x; seed < n_seeds; seed += gridDim.x) {
     for (int s = threadIdx.x; s < H; s += blockDim.x) {
@@ -45,21 +46,28 @@ __global__ void __launch_bounds__(128) visit_topk_kernel(const I* __restrict__ v
       }
     }
     __syncthreads();
+    // fold (count, key) of every slot into one comparable word, in place: count (24 bits) | inverted node id (40 bits).
+    // A max over the words picks the highest count and, on ties, the smallest id; empty slots become 0.
+    unsigned long long* packed = reinterpret_cast<unsigned long long*>(keys);
+    for (int s = threadIdx.x; s < H; s += blockDim.x) {
+      const int c = cnts[s];
+      packed[s] = c > 0 ? (((unsigned long long)c << 40) | (0xFFFFFFFFFFull - (unsigned long long)keys[s])) : 0ull;
+    }
+    if (threadIdx.x == 0) best[0] = 0ull;
+    __syncthreads();
     for (int k = 0; k < K; ++k) {
-      if (threadIdx.x == 0) best = 0ull;
-      __syncthreads();
-      // packed = count (24 bits) | inverted node id (40 bits): max picks the highest count, smallest id on ties
       unsigned long long mine = 0ull;
+      int mine_slot = -1;
       for (int s = threadIdx.x; s < H; s += blockDim.x) {
-        const int c = cnts[s];
-        if (c > 0) {
-          const unsigned long long p = ((unsigned long long)c << 40) | (0xFFFFFFFFFFull - (unsigned long long)keys[s]);
-          mine = p > mine ? p : mine;
+        const unsigned long long p = packed[s];
+        if (p > mine) {
+          mine = p;
+          mine_slot = s;
         }
       }
-      if (mine) atomicMax(&best, mine);
+      if (mine) atomicMax(&best[k & 1], mine);
       __syncthreads();
-      const unsigned long long b = best;
+      const unsigned long long b = best[k & 1];
       if (b == 0ull) {
         for (int r = k + (int)threadIdx.x; r < K; r += blockDim.x) {
           out_node[seed * K + r] = I(-1);
@@ -67,14 +75,13 @@ __global__ void __launch_bounds__(128) visit_topk_kernel(const I* __restrict__ v
         }
         break;
       }
-      const long long node = (long long)(0xFFFFFFFFFFull - (b & 0xFFFFFFFFFFull));
-      if (threadIdx.x == 0) {
-        out_node[seed * K + k] = I(node);
+      if (mine == b) {  // node ids are distinct inside a table, so exactly one thread owns the winner
+        packed[mine_slot] = 0ull;
+        out_node[seed * K + k] = I((long long)(0xFFFFFFFFFFull - (b & 0xFFFFFFFFFFull)));
         out_cnt[seed * K + k] = (int)(b >> 40);
       }
-      for (int s = threadIdx.x; s < H; s += blockDim.x)
-        if (keys[s] == node) cnts[s] = 0;  // taken
-      __syncthreads();
+      if (threadIdx.x == 0) best[(k + 1) & 1] = 0ull;  // last read in round k-1, next written after the barrier below
+      __syncthreads();  // slot clearing and the reset are visible before the next round's scan
     }
     __syncthreads();
   }

@@ -80,7 +80,8 @@ class TorchBasedFeature(Feature):
 
             def gather():
                 idx = ids.cpu()
-                out = torch.empty((idx.shape[0],) + tuple(self._tensor.shape[1:]), dtype=self._tensor.dtype).pin_memory()
+                out = torch.empty((idx.shape[0],) + tuple(self._tensor.shape[1:]), dtype=self._tensor.dtype,
+                                  pin_memory=True)  # caching host allocator: no cudaHostAlloc in steady state
                 torch.index_select(self._tensor, 0, idx, out=out)
                 return out
 
@@ -199,9 +200,8 @@ class DiskBasedFeature(Feature):
 
     def _read_host(self, ids, pinned):
         idx = ids.to(torch.int64).cpu().contiguous()
-        out = torch.empty((idx.shape[0],) + self._shape[1:], dtype=self._dtype)
-        if pinned:
-            out = out.pin_memory()
+        # pinned staging comes from torch's caching host allocator (``.pin_memory()`` would allocate AND copy every call)
+        out = torch.empty((idx.shape[0],) + self._shape[1:], dtype=self._dtype, pin_memory=bool(pinned))
         if idx.numel() and (int(idx.min()) < 0 or int(idx.max()) >= self._shape[0]):
             raise DGLError(f"row index out of range for a feature with {self._shape[0]} rows")
         if self.io_backend == "uring":
@@ -271,14 +271,14 @@ class CPUCachedFeature(Feature):
         dev = ids.device
         with self._mutex:
             values, hit_idx, miss_idx, miss_keys = self._feature.query(ids)
-        out = torch.empty((ids.shape[0],) + tuple(values.shape[1:]), dtype=values.dtype)
+        out = torch.empty((ids.shape[0],) + tuple(values.shape[1:]), dtype=values.dtype, pin_memory=dev.type == "cuda")
         out[hit_idx] = values
         if miss_keys.numel():
             missing = self._fallback_feature.read(miss_keys).cpu()
             out[miss_idx] = missing
             with self._mutex:
                 self._feature.replace(miss_keys, missing)
-        return out.to(dev)
+        return out.to(dev, non_blocking=True) if dev.type == "cuda" else out
 
     def read_async_num_stages(self, ids_device=None):
         # cache lookup, the fallback's own stages for the missing rows (host ids), combine + insert (+ H2D)
@@ -304,9 +304,7 @@ class CPUCachedFeature(Feature):
             yield last
 
         def combine():
-            out = torch.empty((ids.shape[0],) + tuple(values.shape[1:]), dtype=values.dtype)
-            if dev.type == "cuda":
-                out = out.pin_memory()
+            out = torch.empty((ids.shape[0],) + tuple(values.shape[1:]), dtype=values.dtype, pin_memory=dev.type == "cuda")
             out[hit_idx] = values
             if miss_keys.numel():
                 missing = last.wait().cpu()

@@ -39,6 +39,7 @@ class RandomWalkNeighborSampler:
         restart_prob = torch.zeros(self.metapath_hops * num_traversals)
         restart_prob[self.metapath_hops:: self.metapath_hops] = termination_prob
         self.restart_prob = restart_prob
+        self.device_counter = True  # GPU graphs: count visits in the shared-memory kernel (False = sort / run-length)
 
     def __call__(self, seed_nodes):
         G = self.G
@@ -48,7 +49,7 @@ class RandomWalkNeighborSampler:
         ends = paths[:, self.metapath_hops:: self.metapath_hops]
         n = G.num_nodes(self.ntype)
         M = self.num_random_walks * ends.shape[1]
-        if ends.is_cuda and 0 < M <= 8192 and n < (1 << 40):
+        if ends.is_cuda and self.device_counter and 0 < M <= 8192 and n < (1 << 40):
             return self._device_topk(seed_nodes, ends.reshape(seed_nodes.shape[0], M).contiguous(), n)
         src = ends.reshape(-1)
         dst = rep.unsqueeze(1).expand_as(ends).reshape(-1)
