@@ -28,6 +28,9 @@ from .version import __version__  # noqa: F401
 from .random import seed  # noqa: F401
 from . import backend  # noqa: F401,E402
 from .logging import enable_verbose_logging  # noqa: F401,E402
+from .utils import cpu_quota as _cpu_quota  # noqa: E402
+
+_cpu_quota.apply()  # container-aware thread budget (see utils/cpu_quota.py); DGLB200_CPU_QUOTA=0 opts out
 
 _LAZY = {"sampling", "dataloading", "graphbolt", "sparse", "distributed", "optim", "data", "parallel", "models",
          "utils", "multiprocessing", "cuda", "geometry", "partition", "traversal", "propagate", "storages",

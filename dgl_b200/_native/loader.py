@@ -106,6 +106,8 @@ def cpu_lib() -> _Lib:
                     except OSError:
                         pass
                 _cpu = _Lib(p)
+                from ..utils import cpu_quota
+                cpu_quota.cap_native(_cpu)  # OpenMP teams sized by the cgroup CPU quota, not by the visible core count
     return _cpu
 
 

@@ -5,6 +5,8 @@
 #pragma once
 #include <omp.h>
 
+#include <atomic>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -102,7 +104,22 @@ inline void parallel_for_dynamic(int64_t begin, int64_t end, int64_t chunk, F&& 
 
 }  // namespace dglb
 
-#define DGLB_TRY try {
+// Process-wide OpenMP team size. omp_set_num_threads() only changes the CALLING thread's setting, and threads that
+// were not created by OpenMP (Python's I/O pool, DataLoader threads) start from the environment default - the visible
+// core count, not the cgroup CPU budget the loader computed. Every exported entry point therefore re-applies the global
+// value to its calling thread first (a relaxed load and a compare when nothing changed).
+namespace dglb {
+inline std::atomic<int>& team_size_global() {
+  static std::atomic<int> v{0};
+  return v;
+}
+inline void sync_team() {
+  const int t = team_size_global().load(std::memory_order_relaxed);
+  if (t > 0 && omp_get_max_threads() != t) omp_set_num_threads(t);
+}
+}  // namespace dglb
+
+#define DGLB_TRY try { dglb::sync_team();
 #define DGLB_CATCH                               \
   }                                              \
   catch (const std::exception& e) {              \

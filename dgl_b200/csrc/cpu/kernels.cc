@@ -240,8 +240,14 @@ using namespace dglb;
 
 DGLB_API const char* dglb200_last_error() { return dglb::get_last_error(); }
 
-DGLB_API int dglb200_cpu_num_threads() { return omp_get_max_threads(); }
+DGLB_API int dglb200_cpu_num_threads() {
+  const int t = dglb::team_size_global().load(std::memory_order_relaxed);
+  return t > 0 ? t : omp_get_max_threads();
+}
+// process-wide: every entry point re-applies it to its calling thread (common.h sync_team)
 DGLB_API int dglb200_cpu_set_num_threads(int n) {
+  if (n < 1) n = 1;
+  dglb::team_size_global().store(n, std::memory_order_relaxed);
   omp_set_num_threads(n);
   return 0;
 }
