@@ -113,8 +113,14 @@ inline std::atomic<int>& team_size_global() {
   static std::atomic<int> v{0};
   return v;
 }
+// per-thread override (> 0): threads of a pool that runs several native calls side by side take a share of the budget
+inline int& team_size_thread() {
+  static thread_local int v = 0;
+  return v;
+}
 inline void sync_team() {
-  const int t = team_size_global().load(std::memory_order_relaxed);
+  int t = team_size_thread();
+  if (t <= 0) t = team_size_global().load(std::memory_order_relaxed);
   if (t > 0 && omp_get_max_threads() != t) omp_set_num_threads(t);
 }
 }  // namespace dglb

@@ -252,6 +252,12 @@ DGLB_API int dglb200_cpu_set_num_threads(int n) {
   return 0;
 }
 
+// calling-thread override of the team size (0 = follow the process-wide value)
+DGLB_API int dglb200_cpu_set_thread_team(int n) {
+  dglb::team_size_thread() = n < 0 ? 0 : n;
+  return 0;
+}
+
 DGLB_API int dglb200_cpu_gspmm(int op, int red, int dtype, int idtype, const void* indptr, const void* indices,
                                const void* eids, int64_t num_rows, const void* ufeat, const void* efeat, void* out,
                                void* arg_u, void* arg_e, int64_t F, int64_t ldiv, int64_t lmod, int64_t rdiv,

@@ -40,12 +40,25 @@ def set_num_io_threads(n):
         old.shutdown(wait=False)
 
 
+def _init_worker():
+    """Pool threads run native calls side by side (lookup of batch k, disk read of k-1, combine of k-2): each takes a
+    third of the CPU budget for its OpenMP team instead of a full team, so three stages in flight do not oversubscribe
+    the container's quota (spinning OpenMP workers count against it)."""
+    try:
+        from ..._native import loader
+        from ...utils.cpu_quota import effective_cpu_count
+        loader.cpu_lib().fn("dglb200_cpu_set_thread_team", "i")(max(2, effective_cpu_count() // 3))
+    except Exception:  # noqa: BLE001 - sizing only
+        pass
+
+
 def _executor():
     global _pool
     if _pool is None:
         with _lock:
             if _pool is None:
-                _pool = ThreadPoolExecutor(max_workers=get_num_io_threads(), thread_name_prefix="dglb200-io")
+                _pool = ThreadPoolExecutor(max_workers=get_num_io_threads(), thread_name_prefix="dglb200-io",
+                                           initializer=_init_worker)
     return _pool
 
 
