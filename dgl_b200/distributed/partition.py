@@ -134,6 +134,8 @@ class RangePartitionBook:
     def _ekey(self, etype):
         if etype in self._edge_map:
             return etype
+        if isinstance(etype, tuple) and ":".join(etype) in self._edge_map:  # canonical tuple for "src:rel:dst" keys
+            return ":".join(etype)
         for k in self._edge_map:
             if isinstance(k, tuple) and k[1] == etype or (isinstance(k, str) and k.split(":")[1:2] == [etype]):
                 return k

@@ -23,8 +23,13 @@ def verify(orig_dir, part_config):
     u, v = g.edges()
     seen_n = torch.zeros(g.num_nodes(), dtype=torch.int64)
     seen_e = torch.zeros(g.num_edges(), dtype=torch.int64)
+    import verification_utils as vu
+    schema = vu.load_part_schema(part_config)
     for p in range(num_parts):
         pg, nf, ef, gpb, name, nts, ets = dd.load_partition(part_config, p)
+        vu.verify_partition_data_types(pg, p)
+        vu.verify_partition_formats(pg, None, p)
+        vu.verify_metadata_counts(schema, pg, p)
         inner = pg.ndata["inner_node"].bool()
         seen_n[pg.ndata["orig_id"][inner]] += 1
         ie = pg.edata["inner_edge"].bool()
