@@ -9,7 +9,7 @@ def __getattr__(name):
     import importlib
     if name == "citegrh":        # legacy alias of the citation-graph module (reference data/__init__.py)
         return importlib.import_module(f"{__name__}.citation_graph")
-    if name in ("dgl_binary", "graph_serialize", "compat", "more", "builtin", "extra", "utils", "dgl_dataset", "csv_dataset"):
+    if name in ("dgl_binary", "graph_serialize", "compat", "more", "builtin", "extra", "utils", "dgl_dataset", "csv_dataset", "raw_readers"):
         return importlib.import_module(f"{__name__}.{name}")
     for modname in ("dgl_dataset", "graph_serialize", "more", "builtin", "csv_dataset", "utils", "extra", "compat"):
         mod = importlib.import_module(f"{__name__}.{modname}")

@@ -9,21 +9,40 @@ import os
 import torch
 
 from ..convert import graph as make_graph
-from .dgl_dataset import DGLBuiltinDataset
+from .dgl_dataset import DGLBuiltinDataset, get_download_dir
 from .graph_serialize import load_graphs, save_graphs
+from .raw_readers import find_node_source, load_node_source
 from .synthetic import SHAPES, rmat_edges
 
 
 class _SyntheticNodeDataset(DGLBuiltinDataset):
     _key = None
+    _source_key = None      # key into raw_readers.NODE_SOURCES when it differs from ``_key``
     _scale = 1.0
 
-    def __init__(self, raw_dir=None, force_reload=False, verbose=False, transform=None, reverse_edge=True, scale=None):
+    def __init__(self, raw_dir=None, force_reload=False, verbose=False, transform=None, reverse_edge=True, scale=None,
+                 reorder=False):
         self._scale = self._scale if scale is None else scale
-        super().__init__(self._key + "-synthetic", raw_dir=raw_dir, hash_key=(self._key, self._scale),
-                         force_reload=force_reload, verbose=verbose, transform=transform)
+        self._raw_options = {"reverse_edge": reverse_edge, "reorder": reorder}
+        self._raw_root = find_node_source(self._source_key or self._key,
+                                          raw_dir if raw_dir is not None else get_download_dir())
+        if self._raw_root is not None:
+            name, key = self._key, (self._key, "raw", reverse_edge, reorder)
+        else:
+            name, key = self._key + "-synthetic", (self._key, self._scale)
+        super().__init__(name, raw_dir=raw_dir, hash_key=key, force_reload=force_reload, verbose=verbose,
+                         transform=transform)
+
+    @property
+    def is_synthetic(self):
+        """False when the graph was parsed from the reference's raw files found under ``raw_dir``."""
+        return self._raw_root is None
 
     def process(self):
+        if self._raw_root is not None:          # the reference's downloaded files are on disk: parse them
+            parsed = load_node_source(self._source_key or self._key, self._raw_root, **self._raw_options)
+            self._g, self._num_classes = parsed.graph, parsed.num_classes
+            return
         n, e, f, c, sym = SHAPES[self._key]
         n, e = max(32, int(n * self._scale)), max(64, int(e * self._scale))
         u, v = rmat_edges(n, e // 2 if not sym else e, seed=0)
@@ -74,6 +93,7 @@ class RedditDataset(_SyntheticNodeDataset):
     _scale = 0.01
 
     def __init__(self, self_loop=False, raw_dir=None, force_reload=False, verbose=False, transform=None, scale=None):
+        self._source_key = "reddit_self_loop" if self_loop else "reddit"
         super().__init__(raw_dir, force_reload, verbose, transform, scale=scale)
 
 

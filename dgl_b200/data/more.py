@@ -14,8 +14,10 @@ import torch
 
 from ..convert import graph as make_graph
 from ..convert import heterograph as make_heterograph
-from .dgl_dataset import DGLBuiltinDataset
+from .dgl_dataset import DGLBuiltinDataset, get_download_dir
 from .graph_serialize import load_graphs, save_graphs
+from . import raw_readers as raw
+from .raw_readers import find_node_source, load_node_source
 from .synthetic import rmat_edges
 
 # ------------------------------------------------------------------ single-graph node classification
@@ -40,10 +42,22 @@ class _StatNodeDataset(DGLBuiltinDataset):
 
     def __init__(self, raw_dir=None, force_reload=False, verbose=False, transform=None, scale=None, **kw):
         self._scale = self._default_scale if scale is None else scale
-        super().__init__(self._key, raw_dir=raw_dir, hash_key=(self._key, self._scale), force_reload=force_reload,
+        self._raw_options = {k: kw[k] for k in ("reverse_edge", "reorder") if k in kw}
+        self._raw_root = find_node_source(self._key, raw_dir if raw_dir is not None else get_download_dir())
+        key = (self._key, "raw", tuple(sorted(self._raw_options.items()))) if self._raw_root else (self._key, self._scale)
+        super().__init__(self._key, raw_dir=raw_dir, hash_key=key, force_reload=force_reload,
                          verbose=verbose, transform=transform)
 
+    @property
+    def is_synthetic(self):
+        """False when the graph was parsed from the reference's raw files found under ``raw_dir``."""
+        return self._raw_root is None
+
     def process(self):
+        if self._raw_root is not None:          # the reference's downloaded files are on disk: parse them
+            parsed = load_node_source(self._key, self._raw_root, **self._raw_options)
+            self._g, self._num_classes = parsed.graph, parsed.num_classes
+            return
         n, e, f, c, multi = NODE_STATS[self._key]
         n, e = max(32, int(n * self._scale)), max(64, int(e * self._scale))
         u, v = rmat_edges(n, e // 2, seed=hash(self._key) % 1000)
@@ -147,6 +161,26 @@ GRAPH_STATS = {
 
 class _GraphCollection(DGLBuiltinDataset):
     """Base of the multi-graph datasets: ``dataset[i] -> (graph, label)``."""
+    _raw_root = None     # set by subclasses that found the reference's raw files under ``raw_dir``
+
+    @staticmethod
+    def _find_raw(raw_dir, names, required=()):
+        return raw.locate(raw_dir if raw_dir is not None else get_download_dir(), names, required)
+
+    @property
+    def is_synthetic(self):
+        """False when the graphs were parsed from the reference's raw files found under ``raw_dir``."""
+        return self._raw_root is None
+
+    def _adopt(self, parsed):
+        """Take over a parsed ``RawCollection``: graphs, labels and its dataset-level attributes."""
+        self.graphs = parsed.graphs
+        self.labels = parsed.labels if parsed.labels is not None else torch.zeros(len(parsed.graphs), dtype=torch.long)
+        for k, v in parsed.extra.items():
+            if isinstance(getattr(type(self), k, None), property):     # num_labels / num_classes read _num_targets
+                self._num_targets = v
+            else:
+                setattr(self, k, v)
 
     def _gen(self, num, avg_n, avg_deg, fdim, num_targets, seed, regression=False, edge_feat=0, scale=1.0):
         gen = torch.Generator().manual_seed(seed)
@@ -183,20 +217,49 @@ class _GraphCollection(DGLBuiltinDataset):
 
 
 class TUDataset(_GraphCollection):
-    def __init__(self, name, raw_dir=None, force_reload=False, verbose=False, transform=None, scale=1.0):
+    """TU Dortmund graph-kernel benchmarks. With ``<raw_dir>/<name>/<name>_A.txt`` & co on disk (the reference's
+    extracted download, tu.py) the real files are parsed; otherwise a stand-in with the published shape is generated."""
+    _legacy = False
+
+    def __init__(self, name, raw_dir=None, force_reload=False, verbose=False, transform=None, scale=1.0, **kw):
         self._tu, self._scale = name, scale
-        if name not in GRAPH_STATS:
-            raise KeyError(f"TUDataset {name!r}: known shapes are {sorted(GRAPH_STATS)}")
-        super().__init__("tu_" + name, raw_dir=raw_dir, hash_key=(name, scale), transform=transform)
+        self._raw_root = self._find_raw(raw_dir, [name, os.path.join(name, name)], [name + "_A.txt"])
+        if self._raw_root is None and name not in GRAPH_STATS:
+            raise KeyError(f"TUDataset {name!r}: no raw files under raw_dir and no known shape ({sorted(GRAPH_STATS)})")
+        key = (name, "raw", self._legacy) if self._raw_root else (name, scale)
+        super().__init__("tu_" + name, raw_dir=raw_dir, hash_key=key, force_reload=force_reload, transform=transform)
 
     def process(self):
+        if self._raw_root is not None:
+            self._adopt(raw.read_tu(self._raw_root, self._tu, legacy=self._legacy))
+            self.graph_lists, self.graph_labels = self.graphs, self.labels
+            return
         num, an, ad, f, c = GRAPH_STATS[self._tu]
         self._gen(num, an, ad, f, c, seed=len(self._tu), scale=self._scale)
         self.graph_labels = self.labels.unsqueeze(1)
         self.max_num_node = max(g.num_nodes() for g in self.graphs)
 
 
-LegacyTUDataset = TUDataset
+class LegacyTUDataset(TUDataset):
+    """The older TU loader (tu.py:LegacyTUDataset): every graph carries a ``feat`` matrix (one-hot node label, node
+    attributes or a constant column) and ``node_label``."""
+    _legacy = True
+
+    def __init__(self, name, use_pandas=False, hidden_size=10, max_allow_node=None, raw_dir=None, force_reload=False,
+                 verbose=False, transform=None, scale=1.0):
+        self.hidden_size, self.max_allow_node = hidden_size, max_allow_node
+        super().__init__(name, raw_dir=raw_dir, force_reload=force_reload, verbose=verbose, transform=transform, scale=scale)
+
+    def process(self):
+        super().process()
+        if self._raw_root is not None and self.max_allow_node:
+            keep = [i for i, g in enumerate(self.graphs) if g.num_nodes() <= self.max_allow_node]
+            self.graphs = self.graph_lists = [self.graphs[i] for i in keep]
+            self.labels = self.graph_labels = self.labels[torch.tensor(keep, dtype=torch.long)]
+            self.max_num_node = max(g.num_nodes() for g in self.graphs)
+
+    def statistics(self):
+        return self.graphs[0].ndata["feat"].shape[1], self.num_classes, self.max_num_node
 
 
 class GINDataset(_GraphCollection):
@@ -207,10 +270,17 @@ class GINDataset(_GraphCollection):
         key = {"PTC": "PTC_MR", "IMDBBINARY": "IMDB-BINARY", "IMDBMULTI": "IMDB-MULTI", "REDDITBINARY": "REDDIT-BINARY",
                "REDDITMULTI5K": "REDDIT-MULTI-5K"}.get(name, name)
         self._gin, self._self_loop, self._deg, self._scale = key, self_loop, degree_as_nlabel, scale
-        super().__init__("gin_" + name, raw_dir=raw_dir, hash_key=(name, self_loop, degree_as_nlabel, scale),
-                         transform=transform)
+        self._raw_root = self._find_raw(raw_dir, [os.path.join("GINDataset", "dataset", name, name + ".txt"),
+                                                  os.path.join("dataset", name, name + ".txt"),
+                                                  os.path.join(name, name + ".txt")])
+        hk = (name, self_loop, degree_as_nlabel, "raw" if self._raw_root else scale)
+        super().__init__("gin_" + name, raw_dir=raw_dir, hash_key=hk, force_reload=force_reload, transform=transform)
 
     def process(self):
+        if self._raw_root is not None:     # the "How powerful are GNNs" text file is on disk (gindt.py)
+            self._adopt(raw.read_gin_text(self._raw_root, self._self_loop, self._deg))
+            self._num_targets = self.gclasses
+            return
         num, an, ad, f, c = GRAPH_STATS[self._gin]
         self._gen(num, an, ad, f, c, seed=11, scale=self._scale)
         from ..transforms import add_self_loop
@@ -228,9 +298,16 @@ class QM9Dataset(_GraphCollection):
     def __init__(self, label_keys=("mu",), cutoff=5.0, raw_dir=None, force_reload=False, verbose=False, transform=None,
                  scale=0.01):
         self.label_keys, self.cutoff, self._scale = list(label_keys), cutoff, scale
-        super().__init__("qm9", raw_dir=raw_dir, hash_key=(tuple(label_keys), scale), transform=transform)
+        self._raw_root = self._find_raw(raw_dir, ["qm9_eV.npz", os.path.join("qm9", "qm9_eV.npz")])
+        hk = (tuple(label_keys), cutoff, "raw") if self._raw_root else (tuple(label_keys), scale)
+        super().__init__("qm9", raw_dir=raw_dir, hash_key=hk, force_reload=force_reload, transform=transform)
 
     def process(self):
+        if self._raw_root is not None:     # qm9_eV.npz on disk: molecules are built lazily on access (qm9.py)
+            self._mols = raw.QM9Molecules(self._raw_root, self.label_keys, self.cutoff)
+            self.graphs, self.labels = self._mols, torch.as_tensor(self._mols.label.astype("float32"))
+            self._num_targets = len(self.label_keys)
+            return
         self._gen(130831, 18.0, 8.0, 0, len(self.label_keys), seed=9, regression=True, scale=self._scale)
         gen = torch.Generator().manual_seed(10)
         for g in self.graphs:
@@ -241,6 +318,12 @@ class QM9Dataset(_GraphCollection):
     def num_tasks(self):
         return len(self.label_keys)
 
+    def __getitem__(self, idx):
+        if self._raw_root is None:
+            return super().__getitem__(idx)
+        g, y = self._mols[idx]
+        return (g if self._transform is None else self._transform(g)), y
+
 
 QM9EdgeDataset = QM9Dataset
 
@@ -248,9 +331,15 @@ QM9EdgeDataset = QM9Dataset
 class QM7bDataset(_GraphCollection):
     def __init__(self, raw_dir=None, force_reload=False, verbose=False, transform=None, scale=0.1):
         self._scale = scale
-        super().__init__("qm7b", raw_dir=raw_dir, hash_key=(scale,), transform=transform)
+        self._raw_root = self._find_raw(raw_dir, ["qm7b.mat", os.path.join("qm7b", "qm7b.mat")])
+        super().__init__("qm7b", raw_dir=raw_dir, hash_key=("raw",) if self._raw_root else (scale,),
+                         force_reload=force_reload, transform=transform)
 
     def process(self):
+        if self._raw_root is not None:
+            self._adopt(raw.read_qm7b(self._raw_root))
+            self._num_targets = self.num_tasks
+            return
         self._gen(7211, 15.4, 14.0, 0, 14, seed=12, regression=True, scale=self._scale)
         for g in self.graphs:
             g.edata["h"] = torch.rand(g.num_edges(), 1)
@@ -277,9 +366,16 @@ class PPIDataset(_GraphCollection):
 
     def __init__(self, mode="train", raw_dir=None, force_reload=False, verbose=False, transform=None, scale=0.2):
         self.mode, self._scale = mode, scale
-        super().__init__("ppi_" + mode, raw_dir=raw_dir, hash_key=(mode, scale), transform=transform)
+        self._raw_root = self._find_raw(raw_dir, ["ppi"], [f"{mode}_graph.json", f"{mode}_feats.npy",
+                                                           f"{mode}_labels.npy", f"{mode}_graph_id.npy"])
+        super().__init__("ppi_" + mode, raw_dir=raw_dir, hash_key=(mode, "raw" if self._raw_root else scale),
+                         force_reload=force_reload, transform=transform)
 
     def process(self):
+        if self._raw_root is not None:
+            self._adopt(raw.read_ppi(self._raw_root, self.mode))
+            self._num_targets = 121
+            return
         num = {"train": 20, "valid": 2, "test": 2}[self.mode]
         self._gen(num, 2373 * self._scale, 28.8, 50, 121, seed=15, scale=1.0)
         gen = torch.Generator().manual_seed(16)
@@ -293,9 +389,16 @@ class PPIDataset(_GraphCollection):
 
 class BitcoinOTCDataset(_GraphCollection):
     def __init__(self, raw_dir=None, force_reload=False, verbose=False, transform=None):
-        super().__init__("bitcoinotc", raw_dir=raw_dir, transform=transform)
+        self._raw_root = self._find_raw(raw_dir, [os.path.join("bitcoinotc", "soc-sign-bitcoinotc.csv"),
+                                                  os.path.join("bitcoinotc", "soc-sign-bitcoinotc.csv.gz")])
+        super().__init__("bitcoinotc", raw_dir=raw_dir, hash_key=("raw",) if self._raw_root else (),
+                         force_reload=force_reload, transform=transform)
 
     def process(self):
+        if self._raw_root is not None:
+            self._adopt(raw.read_bitcoinotc(self._raw_root))
+            self._num_targets = 1
+            return
         self._gen(136, 5881 * 0.05, 2.0, 0, 1, seed=17)
         for g in self.graphs:
             g.edata["h"] = torch.randint(-10, 11, (g.num_edges(), 1)).float()
@@ -325,12 +428,22 @@ class FakeNewsDataset(_GraphCollection):
 
 class GDELTDataset(_GraphCollection):
     _spec = (2304 // 24, 300, 6.0)
+    _raw_name, _time_step = "GDELT", 15
+    is_temporal = True
 
     def __init__(self, mode="train", raw_dir=None, force_reload=False, verbose=False, transform=None):
         self.mode = mode
-        super().__init__(type(self).__name__.lower() + "_" + mode, raw_dir=raw_dir, hash_key=(mode,), transform=transform)
+        stem = {"valid": "valid", "train": "train", "test": "test"}[mode]
+        self._raw_root = self._find_raw(raw_dir, [os.path.join(self._raw_name, stem + ".txt")])
+        super().__init__(type(self).__name__.lower() + "_" + mode, raw_dir=raw_dir,
+                         hash_key=(mode, "raw") if self._raw_root else (mode,), force_reload=force_reload,
+                         transform=transform)
 
     def process(self):
+        if self._raw_root is not None:     # subject / relation / object / time rows on disk (gdelt.py, icews18.py)
+            self._adopt(raw.read_temporal_quadruples(self._raw_root, self._time_step))
+            self._num_targets = 1
+            return
         num, an, ad = self._spec
         self._gen(num, an, ad, 0, 1, seed=19)
         for g in self.graphs:
@@ -343,6 +456,7 @@ class GDELTDataset(_GraphCollection):
 
 class ICEWS18Dataset(GDELTDataset):
     _spec = (240, 400, 5.0)
+    _raw_name, _time_step = "ICEWS18", 24
 
 
 class SSTDataset(_GraphCollection):
@@ -350,10 +464,19 @@ class SSTDataset(_GraphCollection):
 
     def __init__(self, mode="train", glove_embed_file=None, vocab_file=None, raw_dir=None, force_reload=False,
                  verbose=False, transform=None, scale=0.05):
-        self.mode, self._scale = mode, scale
-        super().__init__("sst_" + mode, raw_dir=raw_dir, hash_key=(mode, scale), transform=transform)
+        self.mode, self._scale, self._vocab_file = mode, scale, vocab_file
+        self._raw_root = self._find_raw(raw_dir, ["sst"], [mode + ".txt"] + ([] if vocab_file else ["vocab.txt"]))
+        super().__init__("sst_" + mode, raw_dir=raw_dir, hash_key=(mode, "raw" if self._raw_root else scale),
+                         force_reload=force_reload, transform=transform)
+
+    PAD_WORD, UNK_WORD = raw.SST_PAD, raw.SST_UNK
 
     def process(self):
+        if self._raw_root is not None:     # treebank files on disk (tree.py), parsed without nltk
+            self._adopt(raw.read_sst(self._raw_root, self.mode, self._vocab_file))
+            self.trees, self.vocab_size, self._num_targets = self.graphs, len(self.vocab), 5
+            self.pretrained_emb = None
+            return
         num = max(4, int({"train": 8544, "dev": 1101, "test": 2210, "tiny": 5}[self.mode] * self._scale))
         gen = torch.Generator().manual_seed(20)
         self.graphs = []
@@ -491,9 +614,21 @@ class _KGDataset(DGLBuiltinDataset):
 
     def __init__(self, reverse=True, raw_dir=None, force_reload=False, verbose=False, transform=None, scale=0.1):
         self.reverse, self._scale = reverse, scale
-        super().__init__(self._key, raw_dir=raw_dir, hash_key=(self._key, reverse, scale), transform=transform)
+        self._raw_root = raw.locate(raw_dir if raw_dir is not None else get_download_dir(), [self._key],
+                                    ["entities.dict", "relations.dict", "train.txt", "valid.txt", "test.txt"])
+        super().__init__(self._key, raw_dir=raw_dir, hash_key=(self._key, reverse, "raw" if self._raw_root else scale),
+                         force_reload=force_reload, transform=transform)
+
+    @property
+    def is_synthetic(self):
+        return self._raw_root is None
 
     def process(self):
+        if self._raw_root is not None:     # entities.dict / relations.dict / split triplets on disk (knowledge_graph.py)
+            parsed = raw.read_kg_triplets(self._raw_root, self.reverse)
+            self._g, self.num_nodes, self.num_rels = parsed.graph, parsed.extra["num_nodes"], parsed.extra["num_rels"]
+            self.train, self.valid, self.test = (parsed.extra[k] for k in ("train", "valid", "test"))
+            return
         ne, nr, tr, va, te = KG_STATS[self._key]
         ne = max(64, int(ne * self._scale))
         tr, va, te = (max(16, int(x * self._scale)) for x in (tr, va, te))
@@ -599,9 +734,20 @@ class FraudDataset(DGLBuiltinDataset):
     def __init__(self, name, raw_dir=None, random_seed=717, train_size=0.7, val_size=0.1, force_reload=False,
                  verbose=False, transform=None, scale=0.1):
         self._fname, self.seed, self.train_size, self.val_size, self._scale = name, random_seed, train_size, val_size, scale
-        super().__init__("fraud_" + name, raw_dir=raw_dir, hash_key=(name, random_seed, scale), transform=transform)
+        self._raw_root = raw.locate(raw_dir if raw_dir is not None else get_download_dir(), [name, "fraud_" + name],
+                                    [raw.FRAUD_LAYOUT[name][0]])
+        hk = (name, random_seed, train_size, val_size, "raw") if self._raw_root else (name, random_seed, scale)
+        super().__init__("fraud_" + name, raw_dir=raw_dir, hash_key=hk, force_reload=force_reload, transform=transform)
+
+    @property
+    def is_synthetic(self):
+        return self._raw_root is None
 
     def process(self):
+        if self._raw_root is not None:     # YelpChi.mat / Amazon.mat on disk (fraud.py)
+            self._g = self.graph = raw.read_fraud_mat(self._raw_root, self._fname, self.seed, self.train_size,
+                                                      self.val_size).graph
+            return
         n, f, rels, es = self._spec[self._fname]
         n = max(64, int(n * self._scale))
         gen = torch.Generator().manual_seed(self.seed)

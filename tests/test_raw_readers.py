@@ -1,0 +1,598 @@
+"""The builtin datasets parse the reference's raw download layouts when they are on disk (dgl_b200/data/raw_readers.py).
+
+Every test writes a miniature raw directory in the exact on-disk format the reference downloads, loads it through the
+public dataset class and checks the parsed content against the values that were written. When the unmodified reference
+is installed (baseline/_ref) the same directory is also loaded by the reference class and both results must agree
+(node order is compared through a unique id column where the loaders reorder nodes)."""
+import collections
+import json
+import os
+import pickle
+import sys
+
+import numpy as np
+import pytest
+import scipy.io
+import scipy.sparse as sp
+import torch
+
+import dgl_b200 as dgl
+from dgl_b200 import data as D
+from dgl_b200.data import raw_readers as R
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "baseline", "_ref")
+rdata = None
+if os.path.isdir(os.path.join(REF, "dgl")):
+    sys.path.insert(0, REF)
+    os.environ.setdefault("DGLBACKEND", "pytorch")
+    try:
+        import dgl.data as rdata  # noqa: E402
+    except Exception:  # noqa: BLE001
+        rdata = None
+needs_ref = pytest.mark.skipif(rdata is None, reason="reference build not installed (baseline/_ref)")
+
+
+def edge_set(g, ids=None, etype=None):
+    u, v = g.edges(etype=etype) if etype else g.edges()
+    u, v = u.long(), v.long()
+    if ids is not None:
+        u, v = ids[u], ids[v]
+    return sorted(zip(u.tolist(), v.tolist()))
+
+
+def by_id(g, key, idcol="feat"):
+    """Node field rows ordered by the unique id stored in column 0 of ``idcol``."""
+    ids = g.ndata[idcol][:, 0].round().long()
+    out = torch.empty_like(g.ndata[key])
+    out[ids] = g.ndata[key]
+    return out
+
+
+# ------------------------------------------------------------------------------------------------------ planetoid ----
+def write_planetoid(root, name, n_train=6, n_unlab=10, n_test=8, nfeat=12, ncls=3, holes=()):
+    """ind.<name>.* with ``allx`` = train + unlabeled rows and ``tx`` = test rows in shuffled ``test.index`` order."""
+    os.makedirs(root, exist_ok=True)
+    rng = np.random.RandomState(0)
+    n_all = n_train + n_unlab
+    test_ids = [i for i in range(n_all, n_all + n_test + len(holes)) if i not in holes]
+    n = n_all + n_test + len(holes)
+    feats = (rng.rand(n, nfeat) < 0.4).astype(np.float32)
+    feats[:, 0] = 1.0
+    labels = rng.randint(0, ncls, n)
+    onehot = np.eye(ncls, dtype=np.int32)[labels]
+    order = rng.permutation(test_ids)
+    adj = collections.defaultdict(list)
+    for _ in range(3 * n):
+        a, b = rng.randint(0, n, 2)
+        if a in holes or b in holes:
+            continue
+        adj[int(a)].append(int(b))
+        adj[int(b)].append(int(a))
+    for i in range(n):
+        adj.setdefault(i, [])
+    # the files hold the test rows in sorted-id order (that is what the reference's Citeseer repair assumes)
+    sorted_test = sorted(test_ids)
+    parts = {"x": sp.csr_matrix(feats[:n_train]), "y": onehot[:n_train], "allx": sp.csr_matrix(feats[:n_all]),
+             "ally": onehot[:n_all], "tx": sp.csr_matrix(feats[sorted_test]), "ty": onehot[sorted_test], "graph": adj}
+    for k, v in parts.items():
+        with open(os.path.join(root, f"ind.{name}.{k}"), "wb") as f:
+            pickle.dump(v, f)
+    with open(os.path.join(root, f"ind.{name}.test.index"), "w") as f:
+        f.write("\n".join(str(int(i)) for i in order) + "\n")
+    return feats, labels, adj, sorted_test, order
+
+
+def test_planetoid_cora(tmp_path):
+    feats, labels, adj, test_sorted, order = write_planetoid(str(tmp_path / "cora_v2"), "cora_v2", n_unlab=600)
+    ds = D.CoraGraphDataset(raw_dir=str(tmp_path))
+    assert not ds.is_synthetic and ds.num_classes == 3
+    g = ds[0]
+    n = len(labels)
+    assert g.num_nodes() == n
+    # row order[k] of the result is the file's k-th sorted test row
+    expect = feats.copy()
+    expect[order] = feats[test_sorted]
+    lab = labels.copy()
+    lab[order] = labels[test_sorted]
+    norm = expect / expect.sum(1, keepdims=True)
+    assert torch.allclose(g.ndata["feat"], torch.tensor(norm), atol=1e-6)
+    assert g.ndata["label"].tolist() == lab.tolist()
+    pairs = {(a, b) for a, nb in adj.items() for b in nb} | {(b, a) for a, nb in adj.items() for b in nb}
+    assert edge_set(g) == sorted(pairs)
+    assert g.ndata["train_mask"].nonzero().squeeze(1).tolist() == list(range(6))
+    assert g.ndata["val_mask"].sum() == 500 and g.ndata["test_mask"].nonzero().squeeze(1).tolist() == test_sorted
+    # the processed cache is reused and a one-direction variant hashes to a different cache entry
+    again = D.CoraGraphDataset(raw_dir=str(tmp_path))
+    assert edge_set(again[0]) == edge_set(g)
+    single = D.CoraGraphDataset(raw_dir=str(tmp_path), reverse_edge=False)[0]
+    assert single.num_edges() == len({(min(a, b), max(a, b)) for a, b in pairs})
+
+
+def test_planetoid_citeseer_holes(tmp_path):
+    n_all = 6 + 600
+    holes = (n_all + 2, n_all + 5)
+    feats, labels, adj, test_sorted, order = write_planetoid(str(tmp_path / "citeseer"), "citeseer", n_unlab=600, holes=holes)
+    g = D.CiteseerGraphDataset(raw_dir=str(tmp_path))[0]
+    assert g.num_nodes() == len(labels)
+    for h in holes:                         # isolated ids become zero rows with label 0 and no edges
+        assert float(g.ndata["feat"][h].abs().sum()) == 0.0
+        assert int(g.in_degrees(h)) == 0 and int(g.out_degrees(h)) == 0
+    assert int(g.ndata["test_mask"].sum()) == len(test_sorted)
+
+
+@needs_ref
+def test_planetoid_matches_reference(tmp_path):
+    for cls, name, holes in (("CoraGraphDataset", "cora_v2", ()), ("CiteseerGraphDataset", "citeseer", (610, 611))):
+        root = tmp_path / name
+        write_planetoid(str(root), name, n_unlab=600, holes=holes)
+        ours = getattr(D, cls)(raw_dir=str(tmp_path))[0]
+        ref = getattr(rdata, cls)(raw_dir=str(tmp_path), verbose=False)[0]
+        assert edge_set(ours) == edge_set(ref)
+        for k in ("feat", "label", "train_mask", "val_mask", "test_mask"):
+            assert torch.allclose(ours.ndata[k].float(), ref.ndata[k].float(), atol=1e-6), (cls, k)
+
+
+# ----------------------------------------------------------------------------------------- npz / json node datasets ----
+def tagged_features(n, f, rng):
+    x = rng.rand(n, f).astype(np.float32)
+    x[:, 0] = np.arange(n)
+    return x
+
+
+def test_attributed_npz_and_reference(tmp_path):
+    rng = np.random.RandomState(1)
+    n = 30
+    a = sp.random(n, n, density=0.1, random_state=rng, format="csr")
+    a.data[:] = 1
+    x = sp.csr_matrix(tagged_features(n, 7, rng))
+    y = rng.randint(0, 4, n)
+    root = tmp_path / "amazon_co_buy_photo"
+    os.makedirs(root)
+    np.savez(root / "amazon_co_buy_photo.npz", adj_data=a.data, adj_indices=a.indices, adj_indptr=a.indptr,
+             adj_shape=a.shape, attr_data=x.data, attr_indices=x.indices, attr_indptr=x.indptr, attr_shape=x.shape,
+             labels=y)
+    ds = D.AmazonCoBuyPhotoDataset(raw_dir=str(tmp_path))
+    g = ds[0]
+    assert not ds.is_synthetic and ds.num_classes == 4
+    ids = g.ndata["feat"][:, 0].round().long()
+    coo = a.tocoo()
+    want = {(int(r), int(c)) for r, c in zip(coo.row, coo.col)}
+    want |= {(c, r) for r, c in want}
+    assert edge_set(g, ids) == sorted(want)
+    assert by_id(g, "label").tolist() == y.tolist()
+    # destination-sorted edge order after the locality reorder
+    assert torch.all(g.edges()[1][1:] >= g.edges()[1][:-1])
+    if rdata is not None:
+        ref = rdata.AmazonCoBuyPhotoDataset(raw_dir=str(tmp_path), verbose=False)[0]
+        rid = ref.ndata["feat"][:, 0].round().long()
+        assert edge_set(ref, rid) == edge_set(g, ids)
+        assert by_id(ref, "label").tolist() == by_id(g, "label").tolist()
+
+
+def test_reddit_npz_pair(tmp_path):
+    rng = np.random.RandomState(2)
+    n = 40
+    a = sp.random(n, n, density=0.08, random_state=rng, format="coo")
+    a.data[:] = 1
+    root = tmp_path / "reddit"
+    os.makedirs(root)
+    sp.save_npz(root / "reddit_graph.npz", a)
+    feat = tagged_features(n, 5, rng)
+    np.savez(root / "reddit_data.npz", feature=feat, label=rng.randint(0, 41, n), node_types=rng.randint(1, 4, n),
+             node_ids=np.arange(n))
+    blob = np.load(root / "reddit_data.npz")
+    ds = D.RedditDataset(raw_dir=str(tmp_path))
+    g = ds[0]
+    assert not ds.is_synthetic and ds.num_classes == 41 and g.num_edges() == a.nnz
+    ids = g.ndata["feat"][:, 0].round().long()
+    assert edge_set(g, ids) == sorted(zip(a.row.tolist(), a.col.tolist()))
+    assert by_id(g, "label").tolist() == blob["label"].tolist()
+    assert by_id(g, "train_mask").tolist() == (blob["node_types"] == 1).tolist()
+    assert by_id(g, "test_mask").tolist() == (blob["node_types"] == 3).tolist()
+    if rdata is not None:
+        ref = rdata.RedditDataset(raw_dir=str(tmp_path), verbose=False)[0]
+        assert edge_set(ref, ref.ndata["feat"][:, 0].round().long()) == edge_set(g, ids)
+        assert by_id(ref, "val_mask").tolist() == by_id(g, "val_mask").tolist()
+
+
+def test_graphsaint_wikics_heterophilous(tmp_path):
+    rng = np.random.RandomState(3)
+    n = 25
+    # GraphSAINT directory (Flickr single-label, Yelp multi-label)
+    for name, multi in (("flickr", False), ("yelp", True)):
+        root = tmp_path / name
+        os.makedirs(root)
+        a = sp.random(n, n, density=0.1, random_state=rng, format="csr")
+        a.data[:] = 1
+        sp.save_npz(root / "adj_full.npz", a)
+        np.save(root / "feats.npy", tagged_features(n, 6, rng))
+        cmap = {str(i): ([int(b) for b in rng.randint(0, 2, 5)] if multi else int(rng.randint(0, 7))) for i in range(n)}
+        json.dump(cmap, open(root / "class_map.json", "w"))
+        perm = rng.permutation(n).tolist()
+        json.dump({"tr": perm[:10], "va": perm[10:15], "te": perm[15:]}, open(root / "role.json", "w"))
+        cls = D.YelpDataset if multi else D.FlickrDataset
+        g = cls(raw_dir=str(tmp_path))[0]
+        assert g.num_edges() == a.nnz and g.ndata["train_mask"].nonzero().squeeze(1).tolist() == sorted(perm[:10])
+        assert g.ndata["label"].tolist() == [cmap[str(i)] for i in range(n)]
+        if rdata is not None:
+            ref = (rdata.YelpDataset if multi else rdata.FlickrDataset)(raw_dir=str(tmp_path), verbose=False)[0]
+            assert edge_set(ref) == edge_set(g) and torch.equal(ref.ndata["label"], g.ndata["label"])
+            assert torch.equal(ref.ndata["test_mask"].bool(), g.ndata["test_mask"])
+    # Wiki-CS
+    root = tmp_path / "wiki_cs"
+    os.makedirs(root)
+    links = [sorted(set(rng.randint(0, n, 3).tolist()) - {i}) for i in range(n)]
+    blob = {"features": tagged_features(n, 4, rng).tolist(), "labels": rng.randint(0, 10, n).tolist(), "links": links,
+            "train_masks": (rng.rand(20, n) < 0.3).tolist(), "val_masks": (rng.rand(20, n) < 0.3).tolist(),
+            "stopping_masks": (rng.rand(20, n) < 0.3).tolist(), "test_mask": (rng.rand(n) < 0.5).tolist()}
+    json.dump(blob, open(root / "data.json", "w"))
+    g = D.WikiCSDataset(raw_dir=str(tmp_path))[0]
+    ids = g.ndata["feat"][:, 0].round().long()
+    want = {(i, j) for i, js in enumerate(links) for j in js}
+    want |= {(j, i) for i, j in want}
+    assert edge_set(g, ids) == sorted(want)
+    assert g.ndata["train_mask"].shape == (n, 20)
+    assert by_id(g, "train_mask").tolist() == np.array(blob["train_masks"]).T.tolist()
+    assert by_id(g, "test_mask").tolist() == blob["test_mask"]
+    # heterophilous npz (hyphenated directory names)
+    root = tmp_path / "roman-empire"
+    os.makedirs(root)
+    edges = rng.randint(0, n, (40, 2))
+    np.savez(root / "roman-empire.npz", edges=edges, node_features=tagged_features(n, 3, rng),
+             node_labels=rng.randint(0, 18, n), train_masks=rng.rand(10, n) < 0.5, val_masks=rng.rand(10, n) < 0.25,
+             test_masks=rng.rand(10, n) < 0.25)
+    ds = D.RomanEmpireDataset(raw_dir=str(tmp_path))
+    g = ds[0]
+    want = {(int(a), int(b)) for a, b in edges} | {(int(b), int(a)) for a, b in edges}
+    assert edge_set(g) == sorted(want) and g.ndata["val_mask"].shape == (n, 10) and not ds.is_synthetic
+    if rdata is not None:
+        ref = rdata.RomanEmpireDataset(raw_dir=str(tmp_path), verbose=False)
+        assert edge_set(ref[0]) == edge_set(g) and ref.num_classes == ds.num_classes
+        assert torch.equal(ref[0].ndata["train_mask"], g.ndata["train_mask"])
+
+
+def write_geom(root, name, n, rng, bow):
+    os.makedirs(root)
+    lines = ["node_id\tfeature\tlabel"]
+    feats = []
+    for i in range(n):
+        if bow:
+            on = sorted(set(rng.randint(0, 9, 3).tolist()))
+            feats.append(on)
+            lines.append(f"{i}\t{','.join(map(str, on))}\t{rng.randint(0, 5)}")
+        else:
+            row = rng.randint(0, 2, 6)
+            feats.append(row.tolist())
+            lines.append(f"{i}\t{','.join(map(str, row))}\t{rng.randint(0, 5)}")
+    open(os.path.join(root, "out1_node_feature_label.txt"), "w").write("\n".join(lines) + "\n")
+    edges = rng.randint(0, n, (30, 2))
+    open(os.path.join(root, "out1_graph_edges.txt"), "w").write(
+        "node_id\tnode_id\n" + "\n".join(f"{a}\t{b}" for a, b in edges) + "\n")
+    for i in range(10):
+        np.savez(os.path.join(root, f"{name}_split_0.6_0.2_{i}.npz"), train_mask=rng.rand(n) < 0.6,
+                 val_mask=rng.rand(n) < 0.2, test_mask=rng.rand(n) < 0.2)
+    return feats, edges
+
+
+def test_geom_gcn_and_actor(tmp_path):
+    rng = np.random.RandomState(4)
+    feats, edges = write_geom(str(tmp_path / "texas"), "texas", 20, rng, bow=False)
+    ds = D.TexasDataset(raw_dir=str(tmp_path))
+    g = ds[0]
+    assert g.ndata["feat"].tolist() == [[float(x) for x in r] for r in feats]
+    assert edge_set(g) == sorted((int(b), int(a)) for a, b in edges)       # file rows are (dst, src)
+    assert g.ndata["train_mask"].shape == (20, 10) and g.ndata["train_mask"].dtype == torch.bool
+    feats, edges = write_geom(str(tmp_path / "actor"), "actor", 20, rng, bow=True)
+    ga = D.ActorDataset(raw_dir=str(tmp_path))[0]
+    for i, on in enumerate(feats):
+        assert ga.ndata["feat"][i].nonzero().squeeze(1).tolist() == on
+    if rdata is not None:
+        ref = rdata.TexasDataset(raw_dir=str(tmp_path), verbose=False)
+        assert edge_set(ref[0]) == edge_set(g) and ref.num_classes == ds.num_classes
+        assert torch.equal(ref[0].ndata["feat"], g.ndata["feat"]) and torch.equal(ref[0].ndata["test_mask"], g.ndata["test_mask"])
+        refa = rdata.ActorDataset(raw_dir=str(tmp_path), verbose=False)[0]
+        assert torch.equal(refa.ndata["feat"], ga.ndata["feat"]) and torch.equal(refa.ndata["label"], ga.ndata["label"])
+
+
+def test_fraud_mat(tmp_path):
+    rng = np.random.RandomState(5)
+    n = 60
+    root = tmp_path / "yelp"
+    os.makedirs(root)
+    rels = {r: sp.random(n, n, density=0.05, random_state=rng, format="csc") for r in ("net_rsr", "net_rtr", "net_rur")}
+    feat = sp.csc_matrix(rng.rand(n, 8))
+    label = (rng.rand(1, n) < 0.2).astype(np.int64)
+    scipy.io.savemat(root / "YelpChi.mat", {"features": feat, "label": label, "homo": rels["net_rur"], **rels})
+    ds = D.FraudYelpDataset(raw_dir=str(tmp_path))
+    g = ds[0]
+    assert g.ntypes == ["review"] and sorted(g.etypes) == sorted(rels) and not ds.is_synthetic
+    for r, m in rels.items():
+        coo = m.tocoo()
+        assert edge_set(g, etype=r) == sorted(zip(coo.row.tolist(), coo.col.tolist()))
+    assert torch.allclose(g.ndata["feature"], torch.tensor(feat.todense(), dtype=torch.float32))
+    assert g.ndata["label"].tolist() == label.ravel().tolist()
+    tr, va, te = (g.ndata[k] for k in ("train_mask", "val_mask", "test_mask"))
+    assert int(tr.sum()) == 42 and int(va.sum()) == 6 and int((tr | va | te).sum()) == n and not bool((tr & te).any())
+    if rdata is not None:
+        ref = rdata.FraudYelpDataset(raw_dir=str(tmp_path), verbose=False)[0]
+        for k in ("train_mask", "val_mask", "test_mask"):
+            assert torch.equal(ref.ndata[k].bool(), g.ndata[k])
+
+
+# ------------------------------------------------------------------------------------------------ knowledge graph ----
+def test_knowledge_graph_triplets(tmp_path):
+    root = tmp_path / "FB15k-237"
+    os.makedirs(root)
+    ents, rels = [f"/m/e{i}" for i in range(12)], [f"/r/{i}" for i in range(4)]
+    open(root / "entities.dict", "w").write("".join(f"{i}\t{e}\n" for i, e in enumerate(ents)))
+    open(root / "relations.dict", "w").write("".join(f"{i}\t{r}\n" for i, r in enumerate(rels)))
+    rng = np.random.RandomState(6)
+    splits = {}
+    for name, m in (("train", 30), ("valid", 6), ("test", 7)):
+        t = np.stack([rng.randint(0, 12, m), rng.randint(0, 4, m), rng.randint(0, 12, m)], 1)
+        splits[name] = t
+        open(root / f"{name}.txt", "w").write("".join(f"{ents[h]}\t{rels[r]}\t{ents[o]}\n" for h, r, o in t))
+    ds = D.FB15k237Dataset(raw_dir=str(tmp_path))
+    g = ds[0]
+    assert not ds.is_synthetic and ds.num_nodes == 12 and ds.num_rels == 4 and g.num_edges() == 2 * 43
+    u, v = g.edges()
+    et = g.edata["etype"]
+    got_train = sorted(zip(u[g.edata["train_edge_mask"]].tolist(), et[g.edata["train_edge_mask"]].tolist(),
+                           v[g.edata["train_edge_mask"]].tolist()))
+    assert got_train == sorted(map(tuple, splits["train"].tolist()))
+    # inverse copies: relation shifted by num_rels, endpoints swapped, excluded from *_edge_mask but inside *_mask
+    rev = et >= 4
+    assert int(rev.sum()) == 43 and not bool((g.edata["train_edge_mask"] & rev).any())
+    assert int(g.edata["train_mask"].sum()) == 60 and int(g.edata["val_mask"].sum()) == 12
+    fwd = sorted(zip(u[~rev].tolist(), et[~rev].tolist(), v[~rev].tolist()))
+    back = sorted(zip(v[rev].tolist(), (et[rev] - 4).tolist(), u[rev].tolist()))
+    assert fwd == back
+    if rdata is not None:
+        ref = rdata.FB15k237Dataset(raw_dir=str(tmp_path), verbose=False)[0]
+        assert torch.equal(ref.edges()[0], u) and torch.equal(ref.edges()[1], v)      # same edge order as well
+        for k in ("etype", "train_edge_mask", "valid_edge_mask", "test_edge_mask", "train_mask", "val_mask", "test_mask"):
+            assert torch.equal(ref.edata[k].long(), g.edata[k].long()), k
+    one_way = D.FB15k237Dataset(raw_dir=str(tmp_path), reverse=False)[0]
+    assert one_way.num_edges() == 43
+
+
+# --------------------------------------------------------------------------------------------------- collections ----
+def write_tu(root, name, rng, sizes=(4, 3, 5), node_attr=True):
+    os.makedirs(root)
+    indicator, edges, offset = [], [], 0
+    for gi, n in enumerate(sizes):
+        indicator += [gi + 1] * n
+        for _ in range(2 * n):
+            a, b = rng.randint(0, n, 2)
+            edges.append((offset + a + 1, offset + b + 1))
+        offset += n
+    tot = sum(sizes)
+
+    def w(kind, rows):
+        open(os.path.join(root, f"{name}_{kind}.txt"), "w").write("\n".join(rows) + "\n")
+    w("A", [f"{a}, {b}" for a, b in edges])
+    w("graph_indicator", [str(i) for i in indicator])
+    glabels = [(-1) ** i for i in range(len(sizes))]
+    w("graph_labels", [str(x) for x in glabels])
+    nl = rng.randint(3, 6, tot)
+    w("node_labels", [str(x) for x in nl])
+    el = rng.randint(0, 3, len(edges))
+    w("edge_labels", [str(x) for x in el])
+    na = rng.rand(tot, 2).round(3)
+    if node_attr:
+        w("node_attributes", [f"{a}, {b}" for a, b in na])
+    return edges, indicator, glabels, nl, el, na
+
+
+def test_tu_dataset(tmp_path):
+    rng = np.random.RandomState(7)
+    sizes = (4, 3, 5)
+    edges, indicator, glabels, nl, el, na = write_tu(str(tmp_path / "TOY"), "TOY", rng, sizes)
+    ds = D.TUDataset("TOY", raw_dir=str(tmp_path))
+    assert len(ds) == 3 and not ds.is_synthetic and ds.num_labels == 2 and ds.max_num_node == 5
+    starts = np.concatenate([[0], np.cumsum(sizes)])
+    for i in range(3):
+        g, y = ds[i]
+        assert int(y) == (0 if glabels[i] == -1 else 1)
+        lo = starts[i]
+        mine = [(a - 1 - lo, b - 1 - lo) for a, b in edges if lo < a <= starts[i + 1]]
+        assert list(zip(g.edges()[0].tolist(), g.edges()[1].tolist())) == mine          # file order kept
+        assert g.ndata["node_labels"].squeeze(1).tolist() == (nl[lo: starts[i + 1]] - nl.min()).tolist()
+        assert torch.allclose(g.ndata["node_attr"], torch.tensor(na[lo: starts[i + 1]]))
+    all_el = torch.cat([ds[i][0].edata["edge_labels"].squeeze(1) for i in range(3)])
+    assert all_el.tolist() == (el - el.min()).tolist()
+    if rdata is not None:
+        ref = rdata.TUDataset("TOY", raw_dir=str(tmp_path), verbose=False)
+        for i in range(3):
+            (g, y), (rg, ry) = ds[i], ref[i]
+            assert edge_set(g) == edge_set(rg) and int(y) == int(ry)
+            assert torch.equal(g.ndata["node_labels"], rg.ndata["node_labels"])
+            assert torch.allclose(g.ndata["node_attr"].double(), rg.ndata["node_attr"].double())
+
+
+def test_legacy_tu_dataset(tmp_path):
+    rng = np.random.RandomState(8)
+    edges, indicator, glabels, nl, el, na = write_tu(str(tmp_path / "TOY2"), "TOY2", rng, (4, 6, 3), node_attr=False)
+    ds = D.LegacyTUDataset("TOY2", raw_dir=str(tmp_path))
+    g, y = ds[1]
+    width = int(nl.max() - nl.min()) + 1
+    assert g.ndata["feat"].shape == (6, width) and torch.all(g.ndata["feat"].sum(1) == 1)
+    assert g.ndata["feat"].argmax(1).tolist() == g.ndata["node_label"].tolist()
+    # the legacy loader only shifts graph labels to start at zero ({-1, 1} -> {0, 2}), so it reports max + 1 classes
+    assert ds.statistics() == (width, 3, 6) and sorted(set(ds.labels.tolist())) == [0, 2]
+    small = D.LegacyTUDataset("TOY2", raw_dir=str(tmp_path), max_allow_node=4, force_reload=True)
+    assert len(small) == 2 and small.max_num_node == 4
+
+
+def test_gin_text_format(tmp_path):
+    root = tmp_path / "GINDataset" / "dataset" / "TOYGIN"
+    os.makedirs(root)
+    text = """3
+3 7
+5 2 1 2
+9 1 0
+5 1 0
+2 4
+9 1 1
+5 1 0
+4 7
+5 1 1
+5 2 0 2
+9 2 1 3
+11 1 2
+"""
+    open(root / "TOYGIN.txt", "w").write(text)
+    ds = D.GINDataset("TOYGIN", self_loop=False, raw_dir=str(tmp_path))
+    assert len(ds) == 3 and ds.gclasses == 2 and ds.nclasses == 3 and ds.dim_nfeats == 3
+    g, y = ds[0]
+    assert edge_set(g) == [(0, 1), (0, 2), (1, 0), (2, 0)] and int(y) == 0 and int(ds[1][1]) == 1 and int(ds[2][1]) == 0
+    assert g.ndata["label"].tolist() == [0, 1, 0]                         # tags 5, 9, 11 -> 0, 1, 2 by first appearance
+    assert ds[2][0].ndata["attr"].argmax(1).tolist() == [0, 0, 1, 2]
+    loops = D.GINDataset("TOYGIN", self_loop=True, raw_dir=str(tmp_path))
+    assert loops[0][0].num_edges() == 4 + 3
+    deg = D.GINDataset("TOYGIN", self_loop=False, degree_as_nlabel=True, raw_dir=str(tmp_path))
+    assert deg[0][0].ndata["label"].tolist() == [2, 1, 1] and deg.dim_nfeats == 2
+    if rdata is not None:
+        ref = rdata.GINDataset("TOYGIN", self_loop=True, raw_dir=str(tmp_path), verbose=False)
+        for i in range(3):
+            assert edge_set(ref[i][0]) == edge_set(loops[i][0])
+            assert torch.equal(ref[i][0].ndata["attr"], loops[i][0].ndata["attr"]) and int(ref[i][1]) == int(loops[i][1])
+        refd = rdata.GINDataset("TOYGIN", self_loop=False, degree_as_nlabel=True, raw_dir=str(tmp_path), verbose=False)
+        assert torch.equal(refd[2][0].ndata["attr"], deg[2][0].ndata["attr"])
+
+
+def test_ppi_layout(tmp_path):
+    rng = np.random.RandomState(9)
+    root = tmp_path / "ppi"
+    os.makedirs(root)
+    sizes = [5, 4]                       # graph ids 21 and 22 of the validation split
+    n = sum(sizes)
+    gid = np.repeat([21, 22], sizes)
+    links = []
+    for lo, hi in ((0, 5), (5, 9)):
+        for _ in range(6):
+            a, b = rng.randint(lo, hi, 2)
+            if a != b:
+                links.append({"source": int(a), "target": int(b)})
+    json.dump({"directed": False, "multigraph": False, "graph": {}, "nodes": [{"id": i} for i in range(n)], "links": links},
+              open(root / "valid_graph.json", "w"))
+    feats, labels = rng.rand(n, 50).astype(np.float32), (rng.rand(n, 121) < 0.3).astype(np.int64)
+    np.save(root / "valid_feats.npy", feats)
+    np.save(root / "valid_labels.npy", labels)
+    np.save(root / "valid_graph_id.npy", gid)
+    ds = D.PPIDataset("valid", raw_dir=str(tmp_path))
+    assert len(ds) == 2 and not ds.is_synthetic
+    g0, g1 = ds[0], ds[1]
+    assert g0.num_nodes() == 5 and g1.num_nodes() == 4
+    want0 = {(l["source"], l["target"]) for l in links if l["source"] < 5}
+    want0 |= {(b, a) for a, b in want0}
+    assert edge_set(g0) == sorted(want0)
+    assert torch.allclose(g1.ndata["feat"], torch.tensor(feats[5:])) and g1.ndata["label"].dtype == torch.float32
+    assert torch.equal(g1.ndata["label"], torch.tensor(labels[5:], dtype=torch.float32))
+
+
+def test_sst_trees(tmp_path):
+    root = tmp_path / "sst"
+    os.makedirs(root)
+    open(root / "vocab.txt", "w").write("\n".join(["the", "movie", "is", "great", "bad"]) + "\n")
+    open(root / "train.txt", "w").write("(3 (2 (2 The) (2 movie)) (4 (2 is) (4 great)))\n(1 (2 Plot) (0 bad))\n")
+    trees = R.parse_bracketed_trees("(3 (2 a) (1 (0 b) (4 c)))")
+    assert trees == [("3", [("2", ["a"]), ("1", [("0", ["b"]), ("4", ["c"])])])]
+    with pytest.raises(dgl.DGLError):
+        R.parse_bracketed_trees("(3 (2 a)")
+    ds = D.SSTDataset("train", raw_dir=str(tmp_path))
+    assert len(ds) == 2 and ds.vocab_size == 5 and not ds.is_synthetic
+    g = ds[0]
+    # pre-order numbering: 0 root, 1 (The movie), 2 The, 3 movie, 4 (is great), 5 is, 6 great
+    assert g.ndata["y"].tolist() == [3, 2, 2, 2, 4, 2, 4]
+    assert g.ndata["mask"].tolist() == [0, 0, 1, 1, 0, 1, 1]
+    assert g.ndata["x"].tolist() == [-1, -1, 0, 1, -1, 2, 3]
+    assert edge_set(g) == [(1, 0), (2, 1), (3, 1), (4, 0), (5, 4), (6, 4)]
+    assert ds[1].ndata["x"].tolist() == [-1, ds.UNK_WORD, 4]                  # "Plot" is out of vocabulary
+
+
+def test_qm7b_qm9_bitcoin_temporal(tmp_path):
+    rng = np.random.RandomState(10)
+    x = np.zeros((3, 5, 5))
+    for i in range(3):
+        m = rng.rand(5, 5) * (rng.rand(5, 5) < 0.5)
+        x[i] = m + m.T
+    t = rng.rand(3, 14)
+    scipy.io.savemat(tmp_path / "qm7b.mat", {"X": x, "T": t})
+    ds = D.QM7bDataset(raw_dir=str(tmp_path))
+    g, y = ds[1]
+    r, c = np.nonzero(x[1])
+    assert edge_set(g) == sorted(zip(r.tolist(), c.tolist())) and torch.allclose(y, torch.tensor(t[1], dtype=torch.float32))
+    assert torch.allclose(g.edata["h"].squeeze(1), torch.tensor(x[1][g.edges()[0].numpy(), g.edges()[1].numpy()],
+                                                                dtype=torch.float32))
+    # QM9: concatenated atoms, distance-cutoff graphs built on access
+    counts = np.array([3, 4])
+    pos = rng.rand(7, 3) * 3
+    np.savez(tmp_path / "qm9_eV.npz", N=counts, R=pos, Z=rng.randint(1, 9, 7), mu=rng.rand(2), homo=rng.rand(2))
+    q = D.QM9Dataset(label_keys=["mu", "homo"], cutoff=1.5, raw_dir=str(tmp_path))
+    assert len(q) == 2 and q.num_tasks == 2 and not q.is_synthetic
+    g, y = q[1]
+    d = np.linalg.norm(pos[3:, None] - pos[None, 3:], axis=-1)
+    want = sorted((i, j) for i in range(4) for j in range(4) if i != j and d[i, j] <= 1.5)
+    assert edge_set(g) == want and g.ndata["R"].shape == (4, 3) and y.shape == (2,)
+    # Bitcoin-OTC snapshots of 13.8 days
+    root = tmp_path / "bitcoinotc"
+    os.makedirs(root)
+    day = 86400
+    rows = [(6, 2, 4, 0), (6, 5, 2, 5 * day), (1, 15, 1, 14 * day), (4, 3, -7, 15 * day), (13, 16, 8, 30 * day)]
+    open(root / "soc-sign-bitcoinotc.csv", "w").write("".join(f"{a},{b},{r},{1289241911 + t}\n" for a, b, r, t in rows))
+    b = D.BitcoinOTCDataset(raw_dir=str(tmp_path))
+    assert [b[i].num_edges() for i in range(len(b))] == [2, 2, 1] and b[0].num_nodes() == 9
+    assert b[1].edata["h"].squeeze(1).tolist() == [1.0, -7.0]
+    # temporal quadruples (ICEWS18 layout)
+    root = tmp_path / "ICEWS18"
+    os.makedirs(root)
+    quads = [(0, 1, 2, 0), (2, 0, 3, 0), (1, 1, 0, 24), (3, 2, 1, 48), (0, 0, 1, 48)]
+    open(root / "train.txt", "w").write("".join(f"{s}\t{r}\t{o}\t{t}\t0\n" for s, r, o, t in quads))
+    ic = D.ICEWS18Dataset("train", raw_dir=str(tmp_path))
+    assert len(ic) == 3 and [ic[i].num_edges() for i in range(3)] == [2, 1, 2] and ic.is_temporal
+    assert ic[2].edata["rel_type"].tolist() == [2, 0] and ic[0].num_nodes() == 4
+
+
+def test_movielens_and_rdf(tmp_path):
+    root = tmp_path / "ml-100k"
+    os.makedirs(root)
+    ratings = [(1, 10, 5, 100), (1, 11, 3, 101), (2, 10, 4, 102), (3, 12, 1, 103), (3, 11, 2, 104)] * 4
+    open(root / "u.data", "w").write("".join(f"{u}\t{i}\t{r}\t{t}\n" for u, i, r, t in ratings))
+    open(root / "u.user", "w").write("1|24|M|technician|85711\n2|53|F|other|94043\n3|23|M|writer|32067\n")
+    genre = "|".join(["0"] * 18 + ["1"])
+    open(root / "u.item", "w", encoding="latin1").write("".join(f"{i}|Title {i}|01-Jan-1995||http://x|{genre}\n" for i in (10, 11, 12)))
+    parsed = R.read_movielens_100k(str(root))
+    g = parsed.graph
+    assert g.num_nodes("user") == 3 and g.num_nodes("movie") == 3 and g.num_edges("user-movie") == 20
+    assert g.edges["user-movie"].data["rate"][:5].tolist() == [5.0, 3.0, 4.0, 1.0, 2.0]
+    masks = [g.edges["user-movie"].data[k] for k in ("train_mask", "valid_mask", "test_mask")]
+    assert int(sum(m.sum() for m in masks)) == 20 and int(masks[2].sum()) == 2
+    assert g.nodes["user"].data["feat"].shape == (3, 2 + 3) and g.nodes["movie"].data["feat"][:, -1].tolist() == [1.0] * 3
+    # N-Triples -> typed heterograph
+    nt = tmp_path / "toy.nt"
+    ty = "http://www.w3.org/1999/02/22-rdf-syntax-ns#type"
+    nt.write_text(f"""<http://x/p1> <{ty}> <http://x/onto#Person> .
+<http://x/p2> <{ty}> <http://x/onto#Person> .
+<http://x/g1> <{ty}> <http://x/onto#Group> .
+<http://x/p1> <http://x/onto#memberOf> <http://x/g1> .
+<http://x/p2> <http://x/onto#memberOf> <http://x/g1> .
+<http://x/p1> <http://x/onto#name> "Ann Lee"@en .
+# a comment
+_:b0 <http://x/onto#knows> <http://x/p2> .
+""")
+    triples = R.parse_ntriples(str(nt))
+    assert len(triples) == 7 and triples[5][2] == '"Ann Lee"@en'
+    hg, members = R.rdf_heterograph(triples)
+    assert hg.num_nodes("Person") == 2 and hg.num_nodes("Group") == 1 and hg.num_nodes("_Literal") == 1
+    assert hg.num_edges(("Person", "memberOf", "Group")) == 2 and hg.num_edges(("Group", "rev-memberOf", "Person")) == 2
+    assert hg.num_edges(("_Thing", "knows", "Person")) == 1 and members["Person"] == ["http://x/p1", "http://x/p2"]
+
+
+def test_synthetic_fallback_is_flagged(tmp_path):
+    """Without raw files the classes keep generating shaped stand-ins and say so."""
+    ds = D.CiteseerGraphDataset(raw_dir=str(tmp_path), scale=0.05)
+    assert ds.is_synthetic and ds[0].ndata["feat"].shape[1] == 3703
+    assert D.PPIDataset("test", raw_dir=str(tmp_path)).is_synthetic
+    assert D.GINDataset("MUTAG", self_loop=True, raw_dir=str(tmp_path)).is_synthetic
