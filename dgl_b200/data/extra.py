@@ -7,6 +7,8 @@ from __future__ import annotations
 
 import math
 
+import os
+
 import torch
 
 from ..convert import graph as make_graph
@@ -345,9 +347,22 @@ class MovieLensDataset(DGLBuiltinDataset):
     def __init__(self, name="ml-100k", valid_ratio=0.1, test_ratio=0.1, raw_dir=None, force_reload=False, verbose=False,
                  transform=None, random_state=0, scale=1.0):
         self._ml, self._vr, self._tr, self._rs, self._scale = name, valid_ratio, test_ratio, random_state, scale
-        super().__init__(name, raw_dir=raw_dir, hash_key=(name, valid_ratio, test_ratio, random_state, scale), transform=transform)
+        from . import raw_readers as raw
+        from .dgl_dataset import get_download_dir
+        self._raw_root = (raw.locate(raw_dir if raw_dir is not None else get_download_dir(),
+                                     [name, os.path.join(name, name)], ["u.data"]) if name == "ml-100k" else None)
+        super().__init__(name, raw_dir=raw_dir, force_reload=force_reload, transform=transform,
+                         hash_key=(name, valid_ratio, test_ratio, random_state, "raw" if self._raw_root else scale))
+
+    @property
+    def is_synthetic(self):
+        return self._raw_root is None
 
     def process(self):
+        if self._raw_root is not None:      # u.data / u.user / u.item on disk (movielens.py)
+            from . import raw_readers as raw
+            self._graph = raw.read_movielens_100k(self._raw_root, self._tr, self._vr, self._rs).graph
+            return
         nu, nm, ne, fu, fm = self.SHAPES[self._ml]
         nu, nm, ne = max(8, int(nu * self._scale)), max(8, int(nm * self._scale)), max(32, int(ne * self._scale))
         gen = torch.Generator().manual_seed(self._rs)

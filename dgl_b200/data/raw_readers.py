@@ -28,6 +28,7 @@ import gzip
 import json
 import os
 import pickle
+import re
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -56,17 +57,27 @@ class RawCollection:
 
 
 # --------------------------------------------------------------------------------------------------------- helpers ----
+_HASHED = re.compile(r".+_[0-9a-f]{8}")
+
+
 def locate(raw_dir, names, required=()):
     """First ``<raw_dir>/<name>`` (directory or file) that exists and holds every file of ``required``.
     ``names`` are tried in order; returns None when nothing matches."""
     if raw_dir is None:
         return None
+    base = os.path.expanduser(raw_dir)
     for name in names:
-        path = os.path.join(os.path.expanduser(raw_dir), name)
-        if os.path.isdir(path) and all(os.path.exists(os.path.join(path, r)) for r in required):
-            return path
-        if os.path.isfile(path) and not required:
-            return path
+        head, _, tail = name.partition(os.sep)
+        # the reference extracts a download into ``<name>_<sha1(url)[:8]>`` (dgl_dataset.py:_get_hash_url_suffix)
+        heads = [head]
+        if os.path.isdir(base):
+            heads += sorted(d for d in os.listdir(base) if _HASHED.fullmatch(d) and d[:-9] == head)
+        for h in heads:
+            path = os.path.join(base, h, tail) if tail else os.path.join(base, h)
+            if os.path.isdir(path) and all(os.path.exists(os.path.join(path, r)) for r in required):
+                return path
+            if os.path.isfile(path) and not required:
+                return path
     return None
 
 
@@ -881,7 +892,10 @@ def _npz_source(name):
 
 
 def _hetero_source(name):
-    return ([name], [name + ".npz"], lambda root, **kw: read_heterophilous_npz(os.path.join(root, name + ".npz")))
+    # heterophilous_graphs.py lower-cases the name and turns '-' into '_' for both the directory and the archive
+    under = name.replace("-", "_")
+    return ([os.path.join(under, under + ".npz"), os.path.join(name, name + ".npz")], [],
+            lambda root, **kw: read_heterophilous_npz(root))
 
 
 def _geom_source(name, bow=False):
