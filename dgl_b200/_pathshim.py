@@ -55,11 +55,13 @@ class AliasFinder(importlib.abc.MetaPathFinder):
         if not fullname.startswith(_PKG + "."):
             return None
         aliases, groups = _table()
-        entry = aliases.get(fullname[len(_PKG) + 1:])
+        key = fullname[len(_PKG) + 1:]
+        entry = aliases.get(key)
         if entry is None:
             return None
         group, names = entry
-        return importlib.machinery.ModuleSpec(fullname, _AliasLoader(groups[group], names))
+        nested = any(k.startswith(key + ".") for k in aliases)     # e.g. backend.pytorch holds backend.pytorch.sparse
+        return importlib.machinery.ModuleSpec(fullname, _AliasLoader(groups[group], names), is_package=nested)
 
 
 def install():

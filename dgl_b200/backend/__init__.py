@@ -348,3 +348,113 @@ def load_backend(mod_name="pytorch"):
 def is_enabled(api):
     """Whether the backend provides ``api`` (reference backend/__init__.py:is_enabled)."""
     return api in globals() and callable(globals()[api])
+
+
+# ---- autograd bookkeeping of the backend API (reference backend/backend.py:1930-2050). PyTorch records eagerly, so the
+# ---- recording scope is a no-op context and "attaching" a gradient is requires_grad_ ---------------------------------
+def attach_grad(x):
+    """Make ``x`` a leaf that accumulates a gradient, clearing any old one."""
+    if x.grad is not None:
+        x.grad.zero_()
+        return x
+    return x.requires_grad_()
+
+
+def backward(x, head_gradient=None):
+    """Back-propagate from ``x`` (summed when no head gradient is given and ``x`` is not a scalar)."""
+    if head_gradient is not None and head_gradient.shape[0] == 1 and head_gradient.dim() == 1 and x.dim() == 0:
+        head_gradient = head_gradient[0]
+    x.backward(head_gradient)
+
+
+def grad(x):
+    return x.grad
+
+
+def is_no_grad(x):
+    """True when ``x`` holds no gradient yet or the gradient is identically zero."""
+    return x.grad is None or _builtins.bool((x.grad == 0).all())
+
+
+def is_recording():
+    return torch.is_grad_enabled()
+
+
+class record_grad:
+    """Scope in which operations are recorded for differentiation - always the case in eager PyTorch."""
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+no_grad = torch.no_grad
+
+
+def sync():
+    """Wait for queued device work (reference ``F.sync``); nothing to do on a CPU-only process."""
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+
+
+# ---- remaining tensor helpers ------------------------------------------------------------------------------------------
+def empty(shape, dtype, ctx):  # noqa: A002
+    return torch.empty(shape, dtype=dtype, device=ctx)
+
+
+def cumsum(x, dim):
+    return torch.cumsum(x, dim)
+
+
+def floor_div(x, y):
+    return torch.div(x, y, rounding_mode="floor")
+
+
+def inverse(x):
+    return torch.inverse(x)
+
+
+def get_preferred_sparse_format():
+    """Layout ``sparse_matrix`` produces without conversion."""
+    return "coo"
+
+
+def sparse_matrix(data, index, shape, force_format=False):  # noqa: A002, ARG001
+    """Backend sparse tensor from ``('coo', [2, nnz] ids)`` or ``('csr', (indices, indptr, edge order))``.
+    Returns ``(matrix, permutation-or-None)`` like the reference (backend.py:sparse_matrix); CSR input is expanded to
+    COO through the row pointer, so no reordering of ``data`` is ever needed."""
+    fmt, payload = index
+    if fmt == "coo":
+        ids = payload
+    elif fmt == "csr":
+        indices, indptr = payload[0], payload[1]
+        rows = torch.repeat_interleave(torch.arange(len(indptr) - 1, device=indices.device), indptr[1:] - indptr[:-1])
+        ids = torch.stack([rows, indices.long()])
+    else:
+        raise TypeError(f"unsupported sparse index format {fmt!r}")
+    return torch.sparse_coo_tensor(ids, data, shape), None
+
+
+def sparse_matrix_indices(spmat):
+    return "coo", spmat.coalesce().indices() if not spmat.is_coalesced() else spmat.indices()
+
+
+def zerocopy_to_dgl_ndarray(x):
+    """Tensors are the array type of the native layer (pointer + stream hand-off), so this is the identity."""
+    return x
+
+
+zerocopy_to_dgl_ndarray_for_write = zerocopy_to_dgl_ndarray
+
+
+def zerocopy_from_dgl_ndarray(x):
+    return x
+
+
+# graph-level sparse algebra and the typed (heterogeneous) message-passing entry points live in sparse_api
+from .sparse_api import (CSRMM, CSRSum, CSRMask, ScatterAdd, binary_reduce, copy_reduce, csrmask, csrmm,  # noqa: E402,F401
+                         csrsum, edge_softmax_hetero, gsddmm_hetero, gspmm_hetero, scatter_add)
+from ..ops.sparse_autograd import GSDDMM, EdgeSoftmax, GSpMM, SegmentReduce  # noqa: E402,F401
+from ..nn.sparse_emb import NodeEmbedding  # noqa: E402,F401
