@@ -7,6 +7,8 @@ def __getattr__(name):
     if name.startswith("__"):
         raise AttributeError(name)
     import importlib
+    if name == "sbm":            # as in the reference, ``dgl.data.sbm`` is the module; the generator is ``dgl.data.sbm.sbm``
+        return importlib.import_module(f"{__name__}.sbm")
     if name == "citegrh":        # legacy alias of the citation-graph module (reference data/__init__.py)
         return importlib.import_module(f"{__name__}.citation_graph")
     if name in ("dgl_binary", "graph_serialize", "compat", "more", "builtin", "extra", "utils", "dgl_dataset", "csv_dataset", "raw_readers"):

@@ -35,7 +35,7 @@ def test_named_bases_and_loaders():
 def test_sbm_generator_statistics():
     rng = np.random.RandomState(0)
     n_blocks, size, p, q = 4, 200, 16.0, 2.0
-    A = D.sbm(n_blocks, size, p, q, rng)
+    A = D.sbm.sbm(n_blocks, size, p, q, rng)     # dgl.data.sbm is the module, as in the reference
     n = n_blocks * size
     assert A.shape == (n, n) and abs(A - A.T).nnz == 0
     comm = np.arange(n) // size
