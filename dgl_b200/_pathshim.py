@@ -12,6 +12,7 @@ import importlib
 import importlib.abc
 import importlib.machinery
 import sys
+import types
 
 _PKG = __name__.rsplit(".", 1)[0]
 
@@ -19,6 +20,21 @@ _PKG = __name__.rsplit(".", 1)[0]
 def _table():
     from ._alias_table import ALIASES, SOURCE_GROUPS
     return ALIASES, SOURCE_GROUPS
+
+
+class _GuardedPackage(types.ModuleType):
+    """Package type that keeps a function when an alias module of the same name is imported under it.
+
+    ``dgl.ops.edge_softmax`` is both a function of ``dgl.ops`` and a module path of the reference; there the package's
+    ``from .edge_softmax import *`` makes the function win. Here the alias module is created on demand, and the import
+    system would bind it over the function afterwards - this ``__setattr__`` declines exactly that one rebinding (the
+    module stays importable through ``sys.modules``)."""
+
+    def __setattr__(self, name, value):
+        held = self.__dict__.get(name)
+        if getattr(value, "__alias_module__", False) and held is not None and not isinstance(held, types.ModuleType):
+            return
+        super().__setattr__(name, value)
 
 
 class _AliasLoader(importlib.abc.Loader):
@@ -41,6 +57,12 @@ class _AliasLoader(importlib.abc.Loader):
                     continue
             raise AttributeError(f"module {modname!r} has no attribute {name!r}")
 
+        module.__alias_module__ = True
+        parent_name, _, leaf = modname.rpartition(".")
+        parent = sys.modules.get(parent_name)
+        if (parent is not None and type(parent) is types.ModuleType and leaf in parent.__dict__
+                and not isinstance(parent.__dict__[leaf], types.ModuleType)):
+            parent.__class__ = _GuardedPackage
         module.__getattr__ = __getattr__
         module.__dir__ = lambda: list(names)
         module.__all__ = list(names)

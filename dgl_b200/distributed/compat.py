@@ -286,9 +286,51 @@ def _service_classes():
         def process_request(self, server_state):
             return OutDegreeResponse(self._degree(server_state, "out"), self.order_id)
 
+    from .rpc_api import register_service
+    for sid, req, res in ((SAMPLING_SERVICE_ID, SamplingRequest, SubgraphResponse),
+                          (INSUBGRAPH_SERVICE_ID, InSubgraphRequest, SubgraphResponse),
+                          (EDGES_SERVICE_ID, EdgesRequest, FindEdgeResponse),
+                          (OUTDEGREE_SERVICE_ID, OutDegreeRequest, OutDegreeResponse),
+                          (INDEGREE_SERVICE_ID, InDegreeRequest, InDegreeResponse),
+                          (ETYPE_SAMPLING_SERVICE_ID, SamplingRequestEtype, SubgraphResponse)):
+        register_service(sid, req, res)
     return {c.__name__: c for c in (SubgraphResponse, FindEdgeResponse, InDegreeResponse, OutDegreeResponse,
                                     SamplingRequest, SamplingRequestEtype, InSubgraphRequest, EdgesRequest,
                                     InDegreeRequest, OutDegreeRequest)}
+
+
+from .service_ids import (EDGES_SERVICE_ID, ETYPE_SAMPLING_SERVICE_ID, INDEGREE_SERVICE_ID,  # noqa: E402,F401
+                          INSUBGRAPH_SERVICE_ID, OUTDEGREE_SERVICE_ID, SAMPLING_SERVICE_ID)
+
+
+class LocalSampledGraph:
+    """What a partition-local sampling call yields (graph_services.py:LocalSampledGraph): global source / destination
+    / edge ids of the sampled edges and, for typed sampling, their edge type ids."""
+
+    def __init__(self, global_src, global_dst, global_eids, etype_ids=None):
+        self.global_src, self.global_dst, self.global_eids, self.etype_ids = global_src, global_dst, global_eids, etype_ids
+
+
+# per-process counters / slots the reference keeps at module level
+DIST_TENSOR_ID = 0           # dist_tensor.py: suffix of anonymous DistTensor names
+DATALOADER_ID = 0            # dist_dataloader.py: id of the next DistDataLoader in this process
+SAMPLER_POOL = None          # dist_context.py: the sampler worker pool (none: samplers run in the trainer here)
+NUM_SAMPLER_WORKERS = 0
+INITIALIZED = False          # dist_context.py: flipped by initialize()
+CANONICAL_ETYPE_DELIMITER = ":"                                            # graph_partition_book.py
+EMB_STATES, WORLD_SIZE, IDS, PARAMS, STATES = "emb_states", "world_size", "ids", "params", "states"   # sparse_optim.py
+
+
+def _dtype_tables():
+    import torch
+    from ..backend import data_type_dict
+    names = {v: k for k, v in data_type_dict.items()}                                    # shared_mem_utils.DTYPE_DICT
+    check = {"node_map": torch.int64, "edge_map": torch.int64, "inner_node": torch.uint8, "inner_edge": torch.uint8,
+             "part_id": torch.int64, "_ID": torch.int64, "orig_id": torch.int64}         # partition.DTYPES_TO_CHECK
+    return names, check
+
+
+DTYPE_DICT, DTYPES_TO_CHECK = _dtype_tables()
 
 
 _SERVICE_CLASSES = None

@@ -863,6 +863,15 @@ SparseAdam = DistSparseAdam
 
 
 NodeDataView = EdgeDataView = _DistDataView          # reference names of the ndata / edata views
+
+# what ``g.nodes[ntype]`` / ``g.edges[etype]`` hand back in the reference (dist_graph.py:343-372): a record whose only field
+# is the data view; ``_DistTypeView`` items expose the same ``.data``
+from collections import namedtuple  # noqa: E402
+
+NodeSpace = namedtuple("NodeSpace", ["data"])
+EdgeSpace = namedtuple("EdgeSpace", ["data"])
+from .service_ids import (ADD_EDGE_ATTRIBUTE_FROM_KV, ADD_EDGE_ATTRIBUTE_FROM_SHARED_MEM, INIT_GRAPH,  # noqa: E402,F401
+                          QUERY_IF_USE_GRAPHBOLT)
 HeteroNodeView = HeteroEdgeView = _DistTypeView      # reference names of g.nodes[...] / g.edges[...] views
 
 

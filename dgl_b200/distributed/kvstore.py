@@ -10,6 +10,12 @@ import torch
 
 from ..base import DGLError
 
+from .service_ids import (BARRIER, BARRIER_MSG, COUNT_LOCAL_NONZERO, DELETE_DATA, DELETE_MSG, GET_PART_SHAPE,  # noqa: F401
+                          GET_SHARED, GET_SHARED_MSG, INIT_DATA, INIT_MSG, KVSTORE_PULL, KVSTORE_PUSH, REGISTER_PULL,
+                          REGISTER_PULL_MSG, REGISTER_PUSH, REGISTER_PUSH_MSG, SEND_META_TO_BACKUP,
+                          SEND_META_TO_BACKUP_MSG)
+
+KVCLIENT = None        # the reference's module-level client slot; this package keeps it in ``_CLIENT`` (get_kvstore())
 NODE_PART_POLICY = "node"
 EDGE_PART_POLICY = "edge"
 

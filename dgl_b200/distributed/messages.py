@@ -3,7 +3,7 @@
 
 The live services of this package are the function handlers of ``dist_graph`` (``_h_pull`` ...), addressed by small
 integer ids; the classes here run the *same* handlers from ``process_request`` so either calling convention reaches
-the same server-side code. They are registered under their own ids (901xx) with :func:`rpc_api.register_service`."""
+the same server-side code. They are registered under the reference's wire ids (service_ids.py) with :func:`rpc_api.register_service`."""
 from __future__ import annotations
 
 import torch
@@ -289,14 +289,22 @@ class AddEdgeAttributeFromSharedMemRequest(AddEdgeAttributeFromKVRequest):
         super().__init__(name, "edge~_N:_E:_N~" + name)
 
 
-for _i, (_req, _res) in enumerate([
-        (PullRequest, PullResponse), (PushRequest, None), (InitDataRequest, InitDataResponse),
-        (BarrierRequest, BarrierResponse), (RegisterPushHandlerRequest, RegisterPushHandlerResponse),
-        (RegisterPullHandlerRequest, RegisterPullHandlerResponse), (GetSharedDataRequest, GetSharedDataResponse),
-        (GetPartShapeRequest, GetPartShapeResponse), (DeleteDataRequest, DeleteDataResponse),
-        (CountLocalNonzeroRequest, CountLocalNonzeroResponse), (SendMetaToBackupRequest, SendMetaToBackupResponse),
-        (RegisterRoleRequest, RegisterRoleResponse), (GetRoleRequest, GetRoleResponse),
-        (InitGraphRequest, InitGraphResponse), (QueryIfUseGraphBoltRequest, QueryIfUseGraphBoltResponse),
-        (AddEdgeAttributeFromKVRequest, AddEdgeAttributeFromKVResponse),
-        (AddEdgeAttributeFromSharedMemRequest, AddEdgeAttributeFromSharedMemResponse)]):
-    register_service(90100 + _i, _req, _res)
+from . import service_ids as _ids  # noqa: E402
+
+for _sid, _req, _res in (
+        (_ids.KVSTORE_PULL, PullRequest, PullResponse), (_ids.KVSTORE_PUSH, PushRequest, None),
+        (_ids.INIT_DATA, InitDataRequest, InitDataResponse), (_ids.BARRIER, BarrierRequest, BarrierResponse),
+        (_ids.REGISTER_PUSH, RegisterPushHandlerRequest, RegisterPushHandlerResponse),
+        (_ids.REGISTER_PULL, RegisterPullHandlerRequest, RegisterPullHandlerResponse),
+        (_ids.GET_SHARED, GetSharedDataRequest, GetSharedDataResponse),
+        (_ids.GET_PART_SHAPE, GetPartShapeRequest, GetPartShapeResponse),
+        (_ids.DELETE_DATA, DeleteDataRequest, DeleteDataResponse),
+        (_ids.COUNT_LOCAL_NONZERO, CountLocalNonzeroRequest, CountLocalNonzeroResponse),
+        (_ids.SEND_META_TO_BACKUP, SendMetaToBackupRequest, SendMetaToBackupResponse),
+        (_ids.REGISTER_ROLE, RegisterRoleRequest, RegisterRoleResponse), (_ids.GET_ROLE, GetRoleRequest, GetRoleResponse),
+        (_ids.INIT_GRAPH, InitGraphRequest, InitGraphResponse),
+        (_ids.QUERY_IF_USE_GRAPHBOLT, QueryIfUseGraphBoltRequest, QueryIfUseGraphBoltResponse),
+        (_ids.ADD_EDGE_ATTRIBUTE_FROM_KV, AddEdgeAttributeFromKVRequest, AddEdgeAttributeFromKVResponse),
+        (_ids.ADD_EDGE_ATTRIBUTE_FROM_SHARED_MEM, AddEdgeAttributeFromSharedMemRequest,
+         AddEdgeAttributeFromSharedMemResponse)):
+    register_service(_sid, _req, _res)

@@ -4,11 +4,20 @@ from __future__ import annotations
 
 import os
 
+from .service_ids import GET_ROLE, GET_ROLE_MSG, REG_ROLE_MSG, REGISTER_ROLE  # noqa: F401
+
 _ROLE = {"name": None, "rank": 0, "global_rank": 0, "num": 1}
+# registry views with the reference's names (role.py:114-123): role -> {client id -> rank inside the role} / global rank
+PER_ROLE_RANK = {}
+GLOBAL_RANK = {}
+CUR_ROLE = None
+IS_STANDALONE = False
 
 
 def init_role(role):
-    _ROLE["name"] = role
+    global CUR_ROLE, IS_STANDALONE
+    _ROLE["name"] = CUR_ROLE = role
+    IS_STANDALONE = os.environ.get("DGL_DIST_MODE", "standalone") == "standalone"
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized():
         _ROLE["rank"] = _ROLE["global_rank"] = dist.get_rank()
@@ -16,6 +25,8 @@ def init_role(role):
     else:
         _ROLE["rank"] = _ROLE["global_rank"] = int(os.environ.get("RANK", "0"))
         _ROLE["num"] = int(os.environ.get("WORLD_SIZE", "1"))
+    PER_ROLE_RANK.setdefault(role, {})[_ROLE["global_rank"]] = _ROLE["rank"]
+    GLOBAL_RANK[_ROLE["global_rank"]] = _ROLE["global_rank"]
 
 
 def get_role():

@@ -17,6 +17,8 @@ from ..base import DGLError
 
 TAG_REQUEST, TAG_RESPONSE, TAG_HELLO, TAG_SHUTDOWN = 1, 2, 3, 4
 _SERVICES = {}
+from .service_ids import DEFUALT_PORT  # noqa: E402,F401
+
 
 
 def register_service(service_id, handler):
@@ -200,6 +202,13 @@ def __getattr__(name):
     if name.startswith("__"):
         raise AttributeError(name)
     from . import rpc_api
+    # class registries under the reference's names (rpc.py:49-51)
+    if name == "REQUEST_CLASS_TO_SERVICE_ID":
+        return rpc_api._REQ2ID
+    if name == "SERVICE_ID_TO_PROPERTY":
+        return rpc_api._ID2PAIR
+    if name == "RESPONSE_CLASS_TO_SERVICE_ID":
+        return {res: sid for sid, (_, res) in rpc_api._ID2PAIR.items() if res is not None}
     if hasattr(rpc_api, name):
         return getattr(rpc_api, name)
     raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

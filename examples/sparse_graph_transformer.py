@@ -61,7 +61,7 @@ def main():
     ap.add_argument("--epochs", type=int, default=40)
     a = ap.parse_args()
     torch.manual_seed(0)
-    from dgl_b200.data import sbm
+    from dgl_b200.data.sbm import sbm
     n_blocks, size = 3, 60
     adj = sbm(n_blocks, size, 14.0, 1.0, np.random.RandomState(0))
     g = dgl.add_self_loop(dgl.graph((torch.as_tensor(adj.row), torch.as_tensor(adj.col)), num_nodes=n_blocks * size))

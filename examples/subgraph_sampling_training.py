@@ -27,7 +27,7 @@ def main():
     ap.add_argument("--epochs", type=int, default=30)
     a = ap.parse_args()
     torch.manual_seed(0)
-    from dgl_b200.data import sbm
+    from dgl_b200.data.sbm import sbm
     blocks, size = 4, 150
     adj = sbm(blocks, size, 12.0, 1.5, np.random.RandomState(1))
     g = dgl.graph((torch.as_tensor(adj.row), torch.as_tensor(adj.col)), num_nodes=blocks * size)

@@ -16,7 +16,7 @@ def main():
     ap.add_argument("--epochs", type=int, default=60)
     a = ap.parse_args()
     torch.manual_seed(0)
-    from dgl_b200.data import sbm
+    from dgl_b200.data.sbm import sbm
     blocks, size = 3, 120
     adj = sbm(blocks, size, 10.0, 1.0, np.random.RandomState(2))
     g = dgl.add_self_loop(dgl.graph((torch.as_tensor(adj.row), torch.as_tensor(adj.col)), num_nodes=blocks * size)).to(a.device)

@@ -184,3 +184,12 @@ def test_reference_backend_module_paths():
         mod = importlib.import_module("dgl_b200." + path)
         for n in names:
             assert getattr(mod, n) is not None, (path, n)
+    # a module path that shares its name with a function of the package must not shadow the function
+    import types
+    g = dgl.graph((torch.tensor([0, 1]), torch.tensor([1, 1])))
+    assert not isinstance(dgl.ops.edge_softmax, types.ModuleType)
+    assert torch.allclose(dgl.ops.edge_softmax(g, torch.zeros(2)), torch.tensor([0.5, 0.5]))
+    assert callable(dgl.to_block) and callable(dgl.transforms.to_block) and callable(dgl.sparse.softmax)
+    assert callable(dgl.sparse.matmul) and callable(dgl.sparse.sddmm) and callable(dgl.ops.gather_mm)
+    from dgl_b200.ops.edge_softmax import edge_softmax as via_path
+    assert via_path is dgl.ops.edge_softmax
