@@ -5,3 +5,6 @@ from .gat import GAT  # noqa: F401
 from .rgcn import RGCN  # noqa: F401
 from .zoo import (APPNP, DGI, GATv2, GCNII, GIN, HGT, SGC, TAGCN, ChebNet, HeteroRGCN, JKNet, LabelPropagationModel,  # noqa: F401
                   LinkPredictor)
+from .zoo_extra import (ARMA, DAGNN, DGCNN, GAE, GCMC, GRACE, GRAND, HAN, LGNN, MPNN, SIGN, STGCN, CompGCN,  # noqa: F401
+                        CorrectAndSmooth, DeeperGCN, EdgeConvNet, GNNFiLM, MixHop, MoNet, Node2VecModel, PinSAGEModel,
+                        SAGPoolNet, drnl_node_labeling, sym_norm_propagate)

@@ -60,6 +60,7 @@ def main():
     ap.add_argument("--ref", default="/root/reference")
     ap.add_argument("--threshold", type=float, default=0.25)
     ap.add_argument("--min-lines", type=int, default=12)
+    ap.add_argument("--show", action="store_true", help="print the matching lines of the given paths")
     ap.add_argument("paths", nargs="*", default=None)
     args = ap.parse_args()
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -76,6 +77,11 @@ def main():
             continue
         hit = sum(1 for l in ls if l in ref_lines)
         rows.append((hit / len(ls), len(ls), os.path.relpath(f, root)))
+        if args.show and args.paths:
+            print(f"== {os.path.relpath(f, root)}: {hit}/{len(ls)}")
+            for l in ls:
+                if l in ref_lines:
+                    print("   ", l)
     rows.sort(reverse=True)
     bad = [r for r in rows if r[0] >= args.threshold]
     for frac, n, f in rows[:40]:
