@@ -114,3 +114,31 @@ def test_graphed_minibatch_example_learns(model):
     finally:
         sys.argv = old
     assert loss < 1.0          # 8 classes: chance is ln 8 = 2.08
+
+
+def test_sign_and_correct_smooth_example():
+    sign_acc, mlp_acc, cs_acc = _main_of("sign_correct_smooth.py", "--epochs", "60")
+    assert sign_acc > 0.9 and cs_acc > mlp_acc + 0.1
+
+
+def test_vgae_example_ranks_hidden_edges():
+    assert _main_of("vgae_link_reconstruction.py", "--epochs", "100") > 0.65
+    assert _main_of("vgae_link_reconstruction.py", "--epochs", "100", "--plain") > 0.65
+
+
+def test_han_example_learns_from_metapaths():
+    assert _main_of("han_metapath.py", "--epochs", "80") > 0.65
+
+
+def test_stgcn_example_beats_persistence():
+    mse, naive = _main_of("stgcn_forecast.py", "--epochs", "40")
+    assert mse < 0.5 * naive
+
+
+def test_seal_example_classifies_links():
+    assert _main_of("seal_link_prediction.py", "--epochs", "20", "--pairs", "240") > 0.65
+
+
+def test_grace_example_improves_on_raw_features():
+    emb_acc, raw_acc = _main_of("grace_contrastive.py", "--epochs", "60")
+    assert emb_acc > 0.9 and emb_acc >= raw_acc
