@@ -108,7 +108,27 @@ def cpu_lib() -> _Lib:
                 _cpu = _Lib(p)
                 from ..utils import cpu_quota
                 cpu_quota.cap_native(_cpu)  # OpenMP teams sized by the cgroup CPU quota, not by the visible core count
+                _guard_forked_children(_cpu)
     return _cpu
+
+
+_FORK_GUARD = []
+
+
+def _guard_forked_children(lib):
+    """GNU OpenMP does not survive ``fork()``: a child inherits the parent's thread-pool bookkeeping without the
+    threads, and its first parallel region with more than one thread waits for them forever. Every forked child
+    (DataLoader workers, ``multiprocessing`` pools, user code) therefore starts with one-thread native teams - those
+    run inline and never touch the pool. A child that wants parallel native kernels again calls
+    ``dgl_b200.utils.cpu_quota.apply(force=True)`` after it has exec'ed or re-initialised OpenMP."""
+    if _FORK_GUARD or not hasattr(os, "register_at_fork"):
+        return
+    try:
+        setter = lib.fn("dglb200_cpu_set_num_threads", "i")
+    except Exception:  # noqa: BLE001 - library without the setter: nothing to pin
+        return
+    _FORK_GUARD.append(setter)
+    os.register_at_fork(after_in_child=lambda: setter(1))
 
 
 def cuda_lib() -> _Lib:

@@ -287,7 +287,18 @@ class DataLoader:
 def _worker_loop(graph, sampler, index_q, result_q, wid, base_seed):
     """Body of one sampling process: receives (task id, index batch), returns (task id, batch | exception)."""
     import random as _random
+    if os.environ.get("DGLB200_DEBUG_WORKER"):            # dump every thread's stack if the worker stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["DGLB200_DEBUG_WORKER"]), exit=True)
     torch.set_num_threads(1)
+    # GNU OpenMP does not survive fork(): the child inherits the parent's thread-pool bookkeeping without the threads,
+    # and the first parallel region with more than one thread waits for them forever. One-thread teams run inline and
+    # never touch the pool, so the native library is pinned to one thread before the first native call of this process.
+    try:
+        from .._native import loader as _loader
+        _loader.cpu_lib().fn("dglb200_cpu_set_num_threads", "i")(1)
+    except Exception:  # noqa: BLE001 - a build without the setter has no OpenMP teams to worry about
+        pass
     torch.manual_seed(base_seed + wid)
     _random.seed(base_seed + wid)
     try:

@@ -266,3 +266,32 @@ def test_dataloader_worker_processes_and_early_exit():
             break
         time.sleep(0.1)
     assert threading.active_count() <= before
+
+
+def _forked_native_call(q):
+    import torch
+    import dgl_b200 as dgl
+    g = dgl.rand_graph(20000, 200000)
+    q.put(float(dgl.ops.copy_u_sum(g, torch.ones(20000, 8)).sum()))
+
+
+def test_native_kernels_survive_fork_after_parallel_regions():
+    """A child forked after the parent has run multi-threaded native kernels must not deadlock in OpenMP: the loader
+    pins forked children to one-thread teams (GNU OpenMP keeps no threads across fork)."""
+    import multiprocessing as mp
+    import dgl_b200 as dgl
+    big = dgl.rand_graph(100000, 1000000)
+    x = torch.randn(100000, 16)
+    for _ in range(3):                                        # make sure the parent's OpenMP pool exists
+        dgl.ops.copy_u_sum(big, x)
+    dgl.sampling.sample_neighbors(big, torch.arange(20000), 5)
+    ctx = mp.get_context("fork")
+    q = ctx.Queue()
+    p = ctx.Process(target=_forked_native_call, args=(q,), daemon=True)
+    p.start()
+    try:
+        assert q.get(timeout=60) == 200000 * 8.0
+    finally:
+        p.join(timeout=5)
+        if p.is_alive():
+            p.terminate()
