@@ -128,3 +128,12 @@ def save_info(path, info):
 def load_info(path):
     with open(path, "rb") as f:
         return pickle.load(f)
+
+
+def __getattr__(name):
+    # container records and the versioned loaders of the reference's graph_serialize.py live in compat.py
+    if name in ("StorageMetaData", "GraphData", "is_local_path", "check_local_file_exists", "load_graph_v1",
+                "load_graph_v2", "load_labels_v1", "load_labels_v2"):
+        from . import compat
+        return getattr(compat, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

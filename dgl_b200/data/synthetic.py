@@ -67,3 +67,11 @@ def shaped_dataset(name, device="cpu", seed=0, idtype=torch.int32, feat_dtype=to
     ntrain = max(1, int(n * train_frac))
     train_idx = torch.randperm(n, device=device, generator=gen)[:ntrain]
     return g, feat, labels, train_idx, c
+
+
+def __getattr__(name):
+    # the explanation benchmarks of the reference's synthetic.py (BA-Shapes & co) are generated in extra.py
+    if name in ("BAShapeDataset", "BACommunityDataset", "TreeCycleDataset", "TreeGridDataset", "BA2MotifDataset"):
+        from . import extra
+        return getattr(extra, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -212,3 +212,13 @@ def add_node_property_split(dataset, part_ratios, property_name, ascending=True,
         masks = mask_nodes_by_property(_node_property(g, property_name, ascending), part_ratios, random_seed)
         for k, m in masks.items():
             g.ndata[k] = m
+
+
+def __getattr__(name):
+    if name == "get_download_dir":
+        from .dgl_dataset import get_download_dir
+        return get_download_dir
+    if name in ("save_tensors", "load_tensors"):
+        from . import compat
+        return getattr(compat, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")
