@@ -142,3 +142,16 @@ def test_seal_example_classifies_links():
 def test_grace_example_improves_on_raw_features():
     emb_acc, raw_acc = _main_of("grace_contrastive.py", "--epochs", "60")
     assert emb_acc > 0.9 and emb_acc >= raw_acc
+
+
+def test_gcmc_example_beats_the_mean_predictor():
+    rmse, base = _main_of("gcmc_rating_prediction.py", "--epochs", "120")
+    assert rmse < 0.6 * base
+
+
+def test_pointcloud_example():
+    assert _main_of("pointcloud_edgeconv.py", "--epochs", "30") > 0.85
+
+
+def test_line_graph_example_generalises_to_unseen_graphs():
+    assert _main_of("line_graph_community.py", "--epochs", "60") > 0.7
