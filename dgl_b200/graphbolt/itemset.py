@@ -120,6 +120,7 @@ class ItemSampler:
         self._seed = seed if seed is not None else 0
         self._rank, self._world = 0, 1
         self._drop_uneven_inputs = False
+        self._worker, self._num_workers = 0, 1      # set inside loader worker processes: batch b goes to worker b % n
 
     def _positions(self):
         n = len(self._item_set)
@@ -141,10 +142,17 @@ class ItemSampler:
                 pos = pos[: nb * self._batch_size]
         n = len(pos)
         nb = n // self._batch_size if self._drop_last else math.ceil(n / self._batch_size)
-        for b in range(nb):
+        for b in range(self._worker, nb, self._num_workers):
             idx = pos[b * self._batch_size: (b + 1) * self._batch_size]
             yield self._minibatcher(self._item_set[idx], self._names)
         self._epoch += 1
+
+    def shard_for_worker(self, worker, num_workers, epoch=None):
+        """Restrict iteration to the batches ``worker, worker + num_workers, ...`` (the permutation of an epoch is the
+        same in every process because it is seeded by ``seed + epoch``)."""
+        self._worker, self._num_workers = int(worker), max(1, int(num_workers))
+        if epoch is not None:
+            self._epoch = int(epoch)
 
     def __len__(self):
         n = len(self._item_set)
