@@ -389,7 +389,8 @@ class PPIDataset(_GraphCollection):
 
 class BitcoinOTCDataset(_GraphCollection):
     def __init__(self, raw_dir=None, force_reload=False, verbose=False, transform=None):
-        self._raw_root = self._find_raw(raw_dir, [os.path.join("bitcoinotc", "soc-sign-bitcoinotc.csv"),
+        self._raw_root = self._find_raw(raw_dir, [os.path.join("bitcoinotc", "bitcoinotc.csv"),      # the reference's extraction
+                                                  os.path.join("bitcoinotc", "soc-sign-bitcoinotc.csv"),
                                                   os.path.join("bitcoinotc", "soc-sign-bitcoinotc.csv.gz")])
         super().__init__("bitcoinotc", raw_dir=raw_dir, hash_key=("raw",) if self._raw_root else (),
                          force_reload=force_reload, transform=transform)

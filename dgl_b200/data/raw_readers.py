@@ -720,43 +720,57 @@ def _open_text(path):
     return gzip.open(path, "rt") if path.endswith(".gz") else open(path)
 
 
-def read_bitcoinotc(path, num_snapshots=None):
-    """Bitcoin-OTC trust network (bitcoinotc.py): csv rows ``source, target, rating, unix time``. Node ids are
-    compacted, and the edges are cut into consecutive windows of 13.8 days -> a list of snapshot graphs over the
-    same node set with the rating in ``edata['h']``."""
+class CumulativeSnapshots:
+    """Lazy sequence of growing graphs over one event table: snapshot ``i`` holds every event whose time bucket is
+    ``<= first_bucket + i``, in file order (what the reference's temporal datasets hand out). Graphs are built on access -
+    the sequence costs one table, not one graph per time step. Node counts follow the events included so far
+    (``max id + 1``), as in the reference, unless ``num_nodes`` fixes them."""
+
+    def __init__(self, src, dst, bucket, edge_data, first, count, num_nodes=None):
+        self.src, self.dst, self.bucket, self.edge_data = src, dst, bucket, edge_data
+        self.first, self.count, self.num_nodes = int(first), int(count), num_nodes
+
+    def __len__(self):
+        return self.count
+
+    def __iter__(self):
+        return (self[i] for i in range(self.count))
+
+    def __getitem__(self, i):
+        if i < 0:
+            i += self.count
+        if not 0 <= i < self.count:
+            raise IndexError(i)
+        keep = self.bucket <= self.first + i
+        g = make_graph((torch.as_tensor(self.src[keep]), torch.as_tensor(self.dst[keep])), num_nodes=self.num_nodes)
+        for k, v in self.edge_data.items():
+            g.edata[k] = torch.as_tensor(v[keep])
+        return g
+
+
+def read_bitcoinotc(path):
+    """Bitcoin-OTC trust network (bitcoinotc.py): csv rows ``source, target, rating, unix time``. Ids are shifted so
+    that the smallest one is 0, time is bucketed in 14-day steps (rounded), and snapshot ``i`` accumulates every rating
+    up to bucket ``i`` with the rating in ``edata['h']`` ([E, 1], int64); the last bucket closes the range and is not
+    emitted, like in the reference."""
     with _open_text(path) as f:
-        rows = np.array([ln.split(",") for ln in f.read().split("\n") if ln.strip()], dtype=np.float64)
-    ids, inv = np.unique(rows[:, :2].astype(np.int64), return_inverse=True)
-    pairs = inv.reshape(-1, 2)
-    stamp = rows[:, 3]
-    window = (stamp.max() - stamp.min()) / num_snapshots if num_snapshots else 13.8 * 86400
-    which = np.minimum(((stamp - stamp.min()) // window).astype(np.int64),
-                       (num_snapshots - 1) if num_snapshots else np.iinfo(np.int64).max)
-    graphs = []
-    for w in range(int(which.max()) + 1):
-        sel = which == w
-        g = make_graph((torch.as_tensor(pairs[sel, 0]), torch.as_tensor(pairs[sel, 1])), num_nodes=len(ids))
-        g.edata["h"] = torch.as_tensor(rows[sel, 2].reshape(-1, 1).astype(np.float32))
-        graphs.append(g)
-    return RawCollection(graphs, None, {"num_nodes": len(ids)})
+        rows = np.array([ln.split(",") for ln in f.read().split("\n") if ln.strip()], dtype=np.float64).astype(np.int64)
+    pairs = rows[:, :2] - rows[:, :2].min()
+    bucket = np.around((rows[:, 3] - rows[:, 3].min()) / (14 * 86400.0)).astype(np.int64)
+    graphs = CumulativeSnapshots(pairs[:, 0], pairs[:, 1], bucket, {"h": rows[:, 2].reshape(-1, 1)}, 0, int(bucket.max()))
+    return RawCollection(graphs, None, {"num_nodes": int(pairs.max()) + 1})
 
 
 def read_temporal_quadruples(path, time_step=1):
-    """Event knowledge graphs (gdelt.py / icews18.py): rows ``subject relation object time [..]``. One graph per
-    distinct time stamp (in increasing order) with ``edata['rel_type']``; node ids are global."""
+    """Event knowledge graphs (gdelt.py / icews18.py): rows ``subject relation object time [..]``. Time is bucketed by
+    ``floor(time / time_step)`` (15 minutes-units for GDELT, 24 hours for ICEWS18); snapshot ``i`` accumulates every
+    event up to bucket ``start + i`` with the relation id in ``edata['rel_type']`` ([E, 1], int64)."""
     table = _int_table(path)[:, :4]
-    n = int(table[:, [0, 2]].max()) + 1
-    times = np.unique(table[:, 3])
-    order = np.argsort(table[:, 3], kind="stable")
-    table = table[order]
-    bounds = np.searchsorted(table[:, 3], times, side="left").tolist() + [len(table)]
-    graphs = []
-    for i in range(len(times)):
-        rows = table[bounds[i]: bounds[i + 1]]
-        g = make_graph((torch.as_tensor(rows[:, 0].copy()), torch.as_tensor(rows[:, 2].copy())), num_nodes=n)
-        g.edata["rel_type"] = torch.as_tensor(rows[:, 1].copy())
-        graphs.append(g)
-    return RawCollection(graphs, None, {"times": times, "time_step": time_step})
+    bucket = np.floor(table[:, 3] / time_step).astype(np.int64)
+    start, end = int(bucket.min()), int(bucket.max())
+    graphs = CumulativeSnapshots(table[:, 0].copy(), table[:, 2].copy(), bucket, {"rel_type": table[:, 1].reshape(-1, 1).copy()},
+                                 start, end - start + 1)
+    return RawCollection(graphs, None, {"start_time": start, "end_time": end, "time_step": time_step})
 
 
 def read_movielens_100k(root, test_ratio=0.1, valid_ratio=0.1, seed=0):

@@ -418,7 +418,7 @@ def test_tu_dataset(tmp_path):
 
 def test_legacy_tu_dataset(tmp_path):
     rng = np.random.RandomState(8)
-    edges, indicator, glabels, nl, el, na = write_tu(str(tmp_path / "TOY2"), "TOY2", rng, (4, 6, 3), node_attr=False)
+    edges, indicator, glabels, nl, el, na = write_tu(str(tmp_path / "TOY2" / "TOY2"), "TOY2", rng, (4, 6, 3), node_attr=False)
     ds = D.LegacyTUDataset("TOY2", raw_dir=str(tmp_path))
     g, y = ds[1]
     width = int(nl.max() - nl.min()) + 1
@@ -426,6 +426,13 @@ def test_legacy_tu_dataset(tmp_path):
     assert g.ndata["feat"].argmax(1).tolist() == g.ndata["node_label"].tolist()
     # the legacy loader only shifts graph labels to start at zero ({-1, 1} -> {0, 2}), so it reports max + 1 classes
     assert ds.statistics() == (width, 3, 6) and sorted(set(ds.labels.tolist())) == [0, 2]
+    if rdata is not None:
+        ref = rdata.LegacyTUDataset("TOY2", raw_dir=str(tmp_path), verbose=False)
+        assert tuple(int(v) for v in ref.statistics()) == ds.statistics()
+        for i in range(3):
+            (g2, y2), (rg, ry) = ds[i], ref[i]
+            assert edge_set(g2) == edge_set(rg) and int(y2) == int(ry)
+            assert torch.equal(g2.ndata["feat"].float(), rg.ndata["feat"].float())
     small = D.LegacyTUDataset("TOY2", raw_dir=str(tmp_path), max_allow_node=4, force_reload=True)
     assert len(small) == 2 and small.max_num_node == 4
 
@@ -547,23 +554,36 @@ def test_qm7b_qm9_bitcoin_temporal(tmp_path):
     d = np.linalg.norm(pos[3:, None] - pos[None, 3:], axis=-1)
     want = sorted((i, j) for i in range(4) for j in range(4) if i != j and d[i, j] <= 1.5)
     assert edge_set(g) == want and g.ndata["R"].shape == (4, 3) and y.shape == (2,)
-    # Bitcoin-OTC snapshots of 13.8 days
+    # Bitcoin-OTC: cumulative snapshots in 14-day buckets, ids shifted to start at zero, last bucket not emitted
     root = tmp_path / "bitcoinotc"
     os.makedirs(root)
     day = 86400
     rows = [(6, 2, 4, 0), (6, 5, 2, 5 * day), (1, 15, 1, 14 * day), (4, 3, -7, 15 * day), (13, 16, 8, 30 * day)]
-    open(root / "soc-sign-bitcoinotc.csv", "w").write("".join(f"{a},{b},{r},{1289241911 + t}\n" for a, b, r, t in rows))
+    open(root / "bitcoinotc.csv", "w").write("".join(f"{a},{b},{r},{1289241911 + t}\n" for a, b, r, t in rows))
     b = D.BitcoinOTCDataset(raw_dir=str(tmp_path))
-    assert [b[i].num_edges() for i in range(len(b))] == [2, 2, 1] and b[0].num_nodes() == 9
-    assert b[1].edata["h"].squeeze(1).tolist() == [1.0, -7.0]
-    # temporal quadruples (ICEWS18 layout)
+    assert [b[i].num_edges() for i in range(len(b))] == [2, 4] and not b.is_synthetic
+    assert edge_set(b[0]) == [(5, 1), (5, 4)] and b[1].edata["h"].squeeze(1).tolist() == [4, 2, 1, -7]
+    assert b[1].edata["h"].shape == (4, 1) and b[1].edata["h"].dtype == torch.int64
+    # temporal quadruples (ICEWS18 layout): cumulative over 24-hour buckets
     root = tmp_path / "ICEWS18"
     os.makedirs(root)
     quads = [(0, 1, 2, 0), (2, 0, 3, 0), (1, 1, 0, 24), (3, 2, 1, 48), (0, 0, 1, 48)]
-    open(root / "train.txt", "w").write("".join(f"{s}\t{r}\t{o}\t{t}\t0\n" for s, r, o, t in quads))
+    for split in ("train", "valid", "test"):
+        open(root / f"{split}.txt", "w").write("".join(f"{s}\t{r}\t{o}\t{t}\t0\n" for s, r, o, t in quads))
     ic = D.ICEWS18Dataset("train", raw_dir=str(tmp_path))
-    assert len(ic) == 3 and [ic[i].num_edges() for i in range(3)] == [2, 1, 2] and ic.is_temporal
-    assert ic[2].edata["rel_type"].tolist() == [2, 0] and ic[0].num_nodes() == 4
+    assert len(ic) == 3 and [ic[i].num_edges() for i in range(3)] == [2, 3, 5] and ic.is_temporal
+    assert ic[2].edata["rel_type"].squeeze(1).tolist() == [1, 0, 1, 2, 0] and ic[0].num_nodes() == 4
+    assert ic.start_time == 0 and ic.end_time == 2 and [g.num_edges() for g in ic.graphs] == [2, 3, 5]
+    if rdata is not None:
+        rb = rdata.BitcoinOTCDataset(raw_dir=str(tmp_path), verbose=False)
+        assert len(rb) == len(b)
+        for i in range(len(b)):
+            assert edge_set(rb[i]) == edge_set(b[i]) and torch.equal(rb[i].edata["h"], b[i].edata["h"])
+        ri = rdata.ICEWS18Dataset("train", raw_dir=str(tmp_path), verbose=False)
+        assert len(ri) == len(ic)
+        for i in range(len(ic)):
+            assert edge_set(ri[i]) == edge_set(ic[i]) and torch.equal(ri[i].edata["rel_type"], ic[i].edata["rel_type"])
+            assert ri[i].num_nodes() == ic[i].num_nodes()
 
 
 def test_movielens_and_rdf(tmp_path):
