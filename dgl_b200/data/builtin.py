@@ -136,30 +136,109 @@ class AsNodePredDataset:
         return 1
 
 
-class MiniGCDataset(DGLBuiltinDataset):
-    """Synthetic graph-classification dataset of 8 graph families (reference data/minigc.py)."""
+def _undirected(n, pairs):
+    """Graph on ``n`` nodes with both directions of every pair plus one self loop per node."""
+    import numpy as np
+    a = np.asarray(pairs, dtype=np.int64).reshape(-1, 2)
+    u = np.concatenate([a[:, 0], a[:, 1], np.arange(n)])
+    v = np.concatenate([a[:, 1], a[:, 0], np.arange(n)])
+    return make_graph((torch.as_tensor(u), torch.as_tensor(v)), num_nodes=n)
 
-    def __init__(self, num_graphs, min_num_v, max_num_v, seed=0, transform=None):
+
+def _cycle(n):
+    return [(i, (i + 1) % n) for i in range(n)] if n > 2 else [(0, 1)][: n - 1]
+
+
+# the eight families of MiniGC as (label order) edge-list builders; every builder returns (num_nodes, undirected pairs)
+def _family_cycle(n, draw):
+    return n, _cycle(n)
+
+
+def _family_star(n, draw):
+    return n, [(0, i) for i in range(1, n)]
+
+
+def _family_wheel(n, draw):
+    rim = [(1 + i, 1 + (i + 1) % (n - 1)) for i in range(n - 1)] if n > 3 else [(1, 2)][: max(n - 2, 0)]
+    return n, [(0, i) for i in range(1, n)] + rim
+
+
+def _family_lollipop(n, draw):
+    tail = int(draw(2, n // 2))
+    head = n - tail
+    clique = [(i, j) for i in range(head) for j in range(i + 1, head)]
+    return n, clique + [(head - 1 + i, head + i) for i in range(tail)]
+
+
+def _family_hypercube(n, draw):
+    import math
+    d = int(math.log(n, 2))
+    return 1 << d, [(i, i ^ (1 << k)) for i in range(1 << d) for k in range(d) if i < i ^ (1 << k)]
+
+
+def _family_grid(n, draw):
+    rows = int(draw(2, n // 2))
+    cols = n // rows
+    node = lambda r, c: c * rows + r  # noqa: E731 - the first dimension varies fastest in networkx's labelling
+    pairs = [(node(r, c), node(r + 1, c)) for r in range(rows - 1) for c in range(cols)]
+    pairs += [(node(r, c), node(r, c + 1)) for r in range(rows) for c in range(cols - 1)]
+    return rows * cols, pairs
+
+
+def _family_clique(n, draw):
+    return n, [(i, j) for i in range(n) for j in range(i + 1, n)]
+
+
+def _family_ladder(n, draw):
+    k = n // 2
+    return 2 * k, _cycle(k) + [(k + a, k + b) for a, b in _cycle(k)] + [(i, k + i) for i in range(k)]
+
+
+MINIGC_FAMILIES = (_family_cycle, _family_star, _family_wheel, _family_lollipop, _family_hypercube, _family_grid,
+                   _family_clique, _family_ladder)
+
+
+class MiniGCDataset(DGLBuiltinDataset):
+    """Synthetic graph classification over eight graph families (reference data/minigc.py): cycle, star, wheel,
+    lollipop, hypercube, grid, clique, circular ladder - ``num_graphs // 8`` of each in this order (the last family
+    takes the remainder), sizes drawn from ``[min_num_v, max_num_v)`` by one seeded stream, self loops added.
+
+    The draws replay the reference's sequence (same seed -> same sizes, tail lengths and grid shapes) and the edge
+    lists are written out directly with networkx's node numbering, so graphs are identical to the reference's without
+    building networkx objects (``tests/test_raw_readers.py`` compares them)."""
+
+    def __init__(self, num_graphs, min_num_v, max_num_v, seed=0, save_graph=True, force_reload=False, verbose=False,
+                 transform=None):
         self.num_graphs, self.min_num_v, self.max_num_v, self.seed = num_graphs, min_num_v, max_num_v, seed
-        super().__init__("minigc", hash_key=(num_graphs, min_num_v, max_num_v, seed), transform=transform)
+        self.save_graph = save_graph
+        super().__init__("minigc", hash_key=(num_graphs, min_num_v, max_num_v, seed), force_reload=force_reload,
+                         verbose=verbose, transform=transform)
 
     def process(self):
-        import networkx as nx
-        from ..convert import from_networkx
         import numpy as np
-        rng = np.random.RandomState(self.seed)
-        gens = [lambda n: nx.cycle_graph(n), lambda n: nx.star_graph(n - 1), lambda n: nx.wheel_graph(n),
-                lambda n: nx.lollipop_graph(n // 2, n - n // 2), lambda n: nx.hypercube_graph(max(1, int(np.log2(n)))),
-                lambda n: nx.grid_graph([max(2, int(np.sqrt(n)))] * 2), lambda n: nx.complete_graph(n),
-                lambda n: nx.circular_ladder_graph(max(2, n // 2))]
-        self.graphs, self.labels = [], []
-        for i in range(self.num_graphs):
-            c = i % 8
-            n = rng.randint(self.min_num_v, self.max_num_v)
-            nxg = nx.convert_node_labels_to_integers(gens[c](n))
-            self.graphs.append(from_networkx(nxg))
-            self.labels.append(c)
-        self.labels = torch.tensor(self.labels)
+        rng = np.random.RandomState(self.seed) if self.seed is not None else np.random.RandomState()
+        share = self.num_graphs // 8
+        counts = [share] * 7 + [self.num_graphs - 7 * share]
+        self.graphs, labels = [], []
+        for label, (family, count) in enumerate(zip(MINIGC_FAMILIES, counts)):
+            for _ in range(count):
+                n = int(rng.randint(self.min_num_v, self.max_num_v))
+                if family is _family_grid and n < 4:
+                    raise ValueError(f"a grid needs at least 4 nodes, got {n}")
+                self.graphs.append(_undirected(*family(n, rng.randint)))
+                labels.append(label)
+        self.labels = torch.tensor(labels, dtype=torch.int64)
+
+    def has_cache(self):
+        return os.path.exists(os.path.join(self.save_path, f"dgl_graph_{self.hash}.bin"))
+
+    def save(self):
+        if self.save_graph:
+            save_graphs(os.path.join(self.save_path, f"dgl_graph_{self.hash}.bin"), self.graphs, {"labels": self.labels})
+
+    def load(self):
+        self.graphs, lab = load_graphs(os.path.join(self.save_path, f"dgl_graph_{self.hash}.bin"))
+        self.labels = lab["labels"]
 
     @property
     def num_classes(self):

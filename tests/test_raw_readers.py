@@ -638,3 +638,62 @@ def test_synthetic_fallback_is_flagged(tmp_path):
     assert ds.is_synthetic and ds[0].ndata["feat"].shape[1] == 3703
     assert D.PPIDataset("test", raw_dir=str(tmp_path)).is_synthetic
     assert D.GINDataset("MUTAG", self_loop=True, raw_dir=str(tmp_path)).is_synthetic
+
+
+def test_minigc_families():
+    ds = D.MiniGCDataset(40, 10, 20, seed=3, force_reload=True)
+    assert len(ds) == 40 and ds.num_classes == 8 and ds.labels.tolist() == sorted(ds.labels.tolist())
+    for i in range(40):
+        g, y = ds[i]
+        u, v = g.edges()
+        assert int((u == v).sum()) == g.num_nodes()                         # one self loop per node
+        deg = g.in_degrees() - 1
+        if int(y) == 0:
+            assert torch.all(deg == 2)                                       # cycle
+        if int(y) == 1:
+            assert int(deg.max()) == g.num_nodes() - 1 and int((deg == 1).sum()) == g.num_nodes() - 1   # star
+        if int(y) == 4:
+            assert g.num_nodes() & (g.num_nodes() - 1) == 0 and torch.all(deg == deg[0])               # hypercube
+        if int(y) == 6:
+            assert torch.all(deg == g.num_nodes() - 1)                       # clique
+        if int(y) == 7:
+            assert torch.all(deg == 3)                                       # circular ladder
+    again = D.MiniGCDataset(40, 10, 20, seed=3)                              # served from the cache
+    assert all(edge_set(again[i][0]) == edge_set(ds[i][0]) for i in range(40))
+
+
+@needs_ref
+def test_generated_and_lazy_datasets_match_reference(tmp_path):
+    ours, ref = D.MiniGCDataset(80, 10, 20, seed=1, force_reload=True), rdata.MiniGCDataset(80, 10, 20, seed=1, force_reload=True)
+    assert [int(ours[i][1]) for i in range(80)] == [int(ref[i][1]) for i in range(80)]
+    assert all(edge_set(ours[i][0]) == edge_set(ref[i][0]) for i in range(80))
+    k, rk = D.KarateClubDataset()[0], rdata.KarateClubDataset()[0]
+    assert edge_set(k) == edge_set(rk) and torch.equal(k.ndata["label"], rk.ndata["label"])
+    rng = np.random.RandomState(3)
+    counts, pos = np.array([3, 4, 5]), rng.rand(12, 3) * 3
+    np.savez(tmp_path / "qm9_eV.npz", N=counts, R=pos, Z=rng.randint(1, 9, 12), mu=rng.rand(3), homo=rng.rand(3))
+    q = D.QM9Dataset(label_keys=["mu", "homo"], cutoff=5.0, raw_dir=str(tmp_path))
+    rq = rdata.QM9Dataset(label_keys=["mu", "homo"], cutoff=5.0, raw_dir=str(tmp_path), verbose=False)
+    for i in range(3):
+        (g, y), (rg, ry) = q[i], rq[i]
+        assert edge_set(g) == edge_set(rg) and torch.allclose(y, ry) and torch.equal(g.ndata["Z"], rg.ndata["Z"])
+        assert torch.allclose(g.ndata["R"], rg.ndata["R"])
+
+
+@needs_ref
+def test_wikics_matches_reference(tmp_path):
+    rng = np.random.RandomState(11)
+    n = 25
+    root = tmp_path / "wiki_cs"
+    os.makedirs(root)
+    links = [sorted(set(rng.randint(0, n, 3).tolist()) - {i}) for i in range(n)]
+    blob = {"features": tagged_features(n, 4, rng).tolist(), "labels": rng.randint(0, 10, n).tolist(), "links": links,
+            "train_masks": (rng.rand(20, n) < 0.3).tolist(), "val_masks": (rng.rand(20, n) < 0.3).tolist(),
+            "stopping_masks": (rng.rand(20, n) < 0.3).tolist(), "test_mask": (rng.rand(n) < 0.5).tolist()}
+    json.dump(blob, open(root / "data.json", "w"))
+    g = D.WikiCSDataset(raw_dir=str(tmp_path))[0]
+    rg = rdata.WikiCSDataset(raw_dir=str(tmp_path), verbose=False)[0]
+    ids, rid = g.ndata["feat"][:, 0].round().long(), rg.ndata["feat"][:, 0].round().long()
+    assert edge_set(g, ids) == edge_set(rg, rid) and by_id(g, "label").tolist() == by_id(rg, "label").tolist()
+    for k in ("train_mask", "val_mask", "stopping_mask", "test_mask"):
+        assert torch.equal(by_id(g, k).bool(), by_id(rg, k).bool()), k
